@@ -1,0 +1,125 @@
+/*
+ * plslam_b200.h — C ABI of the B200-native stereo point+line front-end.
+ *
+ * This is the drop-in boundary.  The reference (rubengooj/pl-slam) consumes the
+ * per-frame hot path through the C++ class API of stvo-pl (StVO::StereoFrame / StereoFrameHandler,
+ * free functions match()/matchGrid()) and of the vendored 3rdparty/line_descriptor; none of it is a
+ * C ABI.  Every entry point below names the reference interface it replaces (file:line relative to
+ * the reference tree).  The C++ shim in pl-slam_b200/cpp/ re-creates the class API on top of these
+ * functions; INTEGRATION.md shows the binding a pl-slam maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross the boundary;
+ *   - every function returns plf_status (0 = ok, <0 = error); plf_last_error() gives the text;
+ *   - "host" entry points take HOST pointers and copy H2D/D2H internally (the reference-facing
+ *     calls); the *_dev / plf_batch_* entry points work on buffers already resident in HBM;
+ *   - no CPU fallback exists: without a CUDA device plf_create fails with PLF_ERR_NO_DEVICE.
+ */
+#ifndef PLSLAM_B200_H
+#define PLSLAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PLF_ABI_VERSION 1
+#define PLF_DESC_BYTES 32 /* ORB rBRIEF-256 and LBD-256: 32 bytes per descriptor */
+
+typedef int plf_status;
+enum {
+  PLF_OK = 0,
+  PLF_ERR_INVALID = -1,   /* bad argument */
+  PLF_ERR_NO_DEVICE = -2, /* no CUDA device / CUDA runtime failure at create */
+  PLF_ERR_CUDA = -3,      /* CUDA runtime error during a call */
+  PLF_ERR_CAPACITY = -4,  /* a fixed-capacity device buffer overflowed (see plf_limits) */
+  PLF_ERR_STATE = -5      /* call sequence error */
+};
+
+typedef struct plf_ctx plf_ctx; /* opaque; one per (device, stream); not thread-safe per ctx */
+
+/* Front-end parameters: the stvo-pl Config keys that pl-slam inherits
+ * (config/config/config_euroc.yaml:9-77, SlamConfig : Config at include/slamConfig.h:28). */
+typedef struct plf_params {
+  /* switches (config_euroc.yaml:9-18) */
+  int has_points, has_lines, best_lr_matches;
+  /* point tracking (config_euroc.yaml:22-25) */
+  float max_dist_epip, min_disp, min_ratio_12_p;
+  /* line tracking (config_euroc.yaml:27-34) */
+  float line_sim_th, stereo_overlap_th, f2f_overlap_th, min_line_length, line_horiz_th,
+      min_ratio_12_l, ls_min_disp_ratio;
+  /* optimiser (config_euroc.yaml:43-51) */
+  double homog_th;
+  int min_features, max_iters, max_iters_ref;
+  double min_error, min_error_change, inlier_k;
+  /* ORB (config_euroc.yaml:59-67) */
+  int orb_nfeatures;
+  float orb_scale_factor;
+  int orb_nlevels, orb_edge_th, orb_wta_k, orb_score, orb_patch_size, orb_fast_th;
+  /* LSD (config_euroc.yaml:68-77) */
+  int lsd_nfeatures, lsd_refine;
+  float lsd_scale, lsd_sigma_scale, lsd_quant, lsd_ang_th, lsd_log_eps, lsd_density_th;
+  int lsd_n_bins;
+} plf_params;
+
+/* Rectified pinhole stereo rig (stvo-pl PinholeStereoCamera; schema
+ * config/dataset_params/kitti00-02.yaml:1-21). */
+typedef struct plf_camera {
+  int width, height;
+  double fx, fy, cx, cy, b;
+} plf_camera;
+
+/* Fixed device capacities chosen at create time. */
+typedef struct plf_limits {
+  int max_batch;     /* stereo pairs per plf_batch_* call */
+  int max_keypoints; /* ORB keypoints per image (all levels, ties included) */
+  int max_segments;  /* raw LSD segments per image */
+  int max_lines;     /* KeyLines kept per image after the top-K */
+} plf_limits;
+
+/* Fills *p with the reference defaults (config/config/config_euroc.yaml). */
+void plf_default_params(plf_params* p);
+void plf_default_limits(plf_limits* l);
+
+int plf_abi_version(void);
+/* Human-readable text of the last error on this ctx (or of the last failed plf_create if ctx==NULL). */
+const char* plf_last_error(const plf_ctx* ctx);
+
+/* Replaces: `new StereoFrameHandler(cam)` app/plslam_dataset.cpp:109 (+ Config singleton load,
+ * src/slamConfig.cpp:106-164). Allocates all device buffers for `limits` on `device`. */
+plf_status plf_create(const plf_params* params, const plf_camera* cam, const plf_limits* limits,
+                      int device, plf_ctx** out);
+void plf_destroy(plf_ctx* ctx);
+/* Number of kernels this ctx has launched since creation (bench.py "gpu_launches"). */
+long long plf_launch_count(const plf_ctx* ctx);
+/* The CUDA stream (cudaStream_t) all work of this ctx is enqueued on, for event timing. */
+void* plf_stream(const plf_ctx* ctx);
+plf_status plf_sync(plf_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------------
+ * Descriptor matching
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Hamming 2-nearest-neighbour search.  Replaces cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) as
+ * called by stvo-pl matchNNR (call sites src/mapHandler.cpp:277,424,597,712,3223,3249) and the
+ * popcount primitive 3rdparty/line_descriptor/src/bitops_custom.hpp:83-96.
+ * d1: n1 x 32 bytes (queries), d2: n2 x 32 bytes (train), row-major, host pointers.
+ * Outputs (host, length n1): index and distance of the nearest and second nearest train row under
+ * the (distance, index) lexicographic order (OpenCV's tie rule); idx = -1, dist = -1 when absent. */
+plf_status plf_hamming_knn2(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                            int32_t* idx1, int32_t* dist1, int32_t* idx2, int32_t* dist2);
+
+/* NNR + mutual-consistency matcher.  Replaces stvo-pl `int match(const Mat&, const Mat&, float nnr,
+ * vector<int>& matches_12)` (src/mapHandler.cpp:277,424,597,712,3223,3249).
+ * matches_12[i] = j if row i of d1 matches row j of d2 (best.distance < nnr * second.distance in
+ * f32, and — when best_lr != 0 — i is also the ratio-accepted best of j in the reverse direction),
+ * else -1.  *n_matches receives the count (the reference's return value). */
+plf_status plf_match(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr,
+                     int best_lr, int32_t* matches_12, int* n_matches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PLSLAM_B200_H */

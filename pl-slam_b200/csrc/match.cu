@@ -1,0 +1,210 @@
+// Hamming 2-NN brute-force matcher + NNR / mutual-consistency filter.
+//
+// Replaces cv::BFMatcher(NORM_HAMMING).knnMatch(k=2) + the ratio / mutual logic of stvo-pl
+// match()/matchNNR() (call sites src/mapHandler.cpp:277,424,597,712,3223,3249) and the popcount
+// distance of 3rdparty/line_descriptor/src/bitops_custom.hpp:83-96.
+//
+// Layout: descriptors are 32 bytes = 8 x u32 = 2 x uint4, row-major, 16-byte aligned.
+// Mapping: a block of 256 threads owns 64 queries; each query is owned by KNN_SPLIT=4 adjacent
+// lanes which stride over the train tile staged in shared memory (8 KB, 256 descriptors, filled
+// with coalesced 16-byte loads).  Each lane keeps (best, second) as packed u32 keys
+// (distance << 16 | train index), so the (distance, index) lexicographic order of OpenCV's
+// batch-distance kNN is a plain unsigned min.  The 4 partial results are merged with warp shuffles.
+// The work is integer XOR+POPC; DRAM traffic is the two descriptor sets once (they sit in L2 for
+// the other query blocks), so this kernel is bound by the POPC issue rate, not by HBM.
+#include "plf_internal.h"
+
+#define KNN_THREADS 256
+#define KNN_SPLIT 4
+#define KNN_QPB (KNN_THREADS / KNN_SPLIT)
+#define KNN_TILE 256
+#define KNN_NONE 0xFFFFFFFFu
+
+__device__ __forceinline__ int hamming256(const uint4& qa, const uint4& qb, const uint4& a,
+                                          const uint4& b) {
+  return __popc(qa.x ^ a.x) + __popc(qa.y ^ a.y) + __popc(qa.z ^ a.z) + __popc(qa.w ^ a.w) +
+         __popc(qb.x ^ b.x) + __popc(qb.y ^ b.y) + __popc(qb.z ^ b.z) + __popc(qb.w ^ b.w);
+}
+
+__global__ void __launch_bounds__(KNN_THREADS) k_hamming_knn2(const KnnProblem* __restrict__ probs) {
+  const KnnProblem P = probs[blockIdx.y];
+  const int nq = P.nq_ptr ? *P.nq_ptr : P.nq;
+  const int nt = P.nt_ptr ? *P.nt_ptr : P.nt;
+  const int q0 = blockIdx.x * KNN_QPB;
+  if (q0 >= nq) return;
+  __shared__ uint4 tile[KNN_TILE * 2];
+  const int sub = threadIdx.x & (KNN_SPLIT - 1);
+  const int qi = q0 + (threadIdx.x / KNN_SPLIT);
+  const bool active = qi < nq;
+  uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+  if (active) {
+    const uint4* qp = reinterpret_cast<const uint4*>(P.q) + 2 * (size_t)qi;
+    qa = qp[0];
+    qb = qp[1];
+  }
+  uint32_t best = KNN_NONE, second = KNN_NONE;
+  const uint4* tp = reinterpret_cast<const uint4*>(P.t);
+  for (int t0 = 0; t0 < nt; t0 += KNN_TILE) {
+    const int cnt = min(KNN_TILE, nt - t0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cnt * 2; i += KNN_THREADS) tile[i] = tp[(size_t)t0 * 2 + i];
+    __syncthreads();
+#pragma unroll 4
+    for (int j = sub; j < cnt; j += KNN_SPLIT) {
+      const uint4 a = tile[2 * j], b = tile[2 * j + 1];
+      const uint32_t key = ((uint32_t)hamming256(qa, qb, a, b) << 16) | (uint32_t)(t0 + j);
+      second = min(second, max(best, key));
+      best = min(best, key);
+    }
+  }
+  // merge the KNN_SPLIT partial (best, second) pairs of this query
+#pragma unroll
+  for (int off = 1; off < KNN_SPLIT; off <<= 1) {
+    const uint32_t ob = __shfl_xor_sync(0xFFFFFFFFu, best, off);
+    const uint32_t os = __shfl_xor_sync(0xFFFFFFFFu, second, off);
+    const uint32_t nb = min(best, ob);
+    second = min(min(second, os), max(best, ob));
+    best = nb;
+  }
+  if (active && sub == 0) {
+    P.best[qi] = best;
+    P.second[qi] = second;
+  }
+}
+
+plf_status plf_launch_knn2(plf_ctx* ctx, const KnnProblem* d_probs, int nprob, int max_nq) {
+  if (nprob <= 0 || max_nq <= 0) return PLF_OK;
+  dim3 grid((max_nq + KNN_QPB - 1) / KNN_QPB, nprob);
+  k_hamming_knn2<<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs);
+  PLF_LAUNCH_CHECK(ctx);
+  return PLF_OK;
+}
+
+// matches_[i][0].distance < matches_[i][1].distance * nnr, evaluated in f32 exactly as the
+// reference writes it (DMatch.distance is float; the product is rounded to f32 before the compare).
+__device__ __forceinline__ bool nnr_accept(uint32_t best, uint32_t second, float nnr) {
+  if (best == KNN_NONE || second == KNN_NONE) return false;  // fewer than 2 train rows: no match
+  const float d1 = (float)(best >> 16), d2 = (float)(second >> 16);
+  return d1 < __fmul_rn(d2, nnr);
+}
+
+__global__ void __launch_bounds__(256) k_nnr_mutual(const NnrProblem* __restrict__ probs) {
+  const NnrProblem P = probs[blockIdx.y];
+  const int n1 = P.n1_ptr ? *P.n1_ptr : P.n1;
+  const int n2 = P.n2_ptr ? *P.n2_ptr : P.n2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int m = -1;
+  if (i < n1 && n2 > 0) {
+    const uint32_t b = P.best12[i], s = P.second12[i];
+    if (nnr_accept(b, s, P.nnr)) {
+      m = (int)(b & 0xFFFFu);
+      if (P.best_lr) {
+        const uint32_t b2 = P.best21[m], s2 = P.second21[m];
+        if (!(nnr_accept(b2, s2, P.nnr) && (int)(b2 & 0xFFFFu) == i)) m = -1;
+      }
+    }
+  }
+  if (i < n1) P.matches12[i] = m;
+  const unsigned ball = __ballot_sync(0xFFFFFFFFu, m >= 0);
+  if ((threadIdx.x & 31) == 0 && ball && P.count) atomicAdd(P.count, __popc(ball));
+}
+
+plf_status plf_launch_nnr(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, int max_n1) {
+  if (nprob <= 0 || max_n1 <= 0) return PLF_OK;
+  dim3 grid((max_n1 + 255) / 256, nprob);
+  k_nnr_mutual<<<grid, 256, 0, ctx->stream>>>(d_probs);
+  PLF_LAUNCH_CHECK(ctx);
+  return PLF_OK;
+}
+
+// ---- host-pointer operator entry points ---------------------------------------------------------
+
+static size_t align256(size_t x) { return (x + 255) & ~size_t(255); }
+
+extern "C" plf_status plf_hamming_knn2(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2,
+                                       int n2, int32_t* idx1, int32_t* dist1, int32_t* idx2,
+                                       int32_t* dist2) {
+  if (!ctx) return PLF_ERR_INVALID;
+  if (n1 < 0 || n2 < 0 || n2 > 65535 || (n1 > 0 && !d1) || (n2 > 0 && !d2))
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_hamming_knn2: bad sizes n1=%d n2=%d (n2 <= 65535)", n1,
+                    n2);
+  if (n1 == 0) return PLF_OK;
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t b1 = align256((size_t)n1 * 32), b2 = align256((size_t)(n2 > 0 ? n2 : 1) * 32),
+               bk = align256((size_t)n1 * 4);
+  uint8_t* base = (uint8_t*)plf_scratch(ctx, 0, b1 + b2 + 2 * bk + 256);
+  if (!base) return PLF_ERR_CUDA;
+  uint8_t *dq = base, *dt = base + b1;
+  uint32_t *dbest = (uint32_t*)(base + b1 + b2), *dsec = (uint32_t*)(base + b1 + b2 + bk);
+  KnnProblem* dprob = (KnnProblem*)(base + b1 + b2 + 2 * bk);
+  PLF_CUDA(ctx, cudaMemcpyAsync(dq, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, ctx->stream));
+  if (n2 > 0)
+    PLF_CUDA(ctx, cudaMemcpyAsync(dt, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, ctx->stream));
+  KnnProblem hp = {(const uint32_t*)dq, (const uint32_t*)dt, nullptr, nullptr, n1, n2, dbest, dsec};
+  PLF_CUDA(ctx, cudaMemcpyAsync(dprob, &hp, sizeof hp, cudaMemcpyHostToDevice, ctx->stream));
+  plf_status st = plf_launch_knn2(ctx, dprob, 1, n1);
+  if (st) return st;
+  std::vector<uint32_t> hb(n1), hs(n1);
+  PLF_CUDA(ctx, cudaMemcpyAsync(hb.data(), dbest, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(hs.data(), dsec, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < n1; ++i) {
+    const bool vb = hb[i] != KNN_NONE, vs = hs[i] != KNN_NONE;
+    if (idx1) idx1[i] = vb ? (int32_t)(hb[i] & 0xFFFF) : -1;
+    if (dist1) dist1[i] = vb ? (int32_t)(hb[i] >> 16) : -1;
+    if (idx2) idx2[i] = vs ? (int32_t)(hs[i] & 0xFFFF) : -1;
+    if (dist2) dist2[i] = vs ? (int32_t)(hs[i] >> 16) : -1;
+  }
+  return PLF_OK;
+}
+
+extern "C" plf_status plf_match(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2,
+                                float nnr, int best_lr, int32_t* matches_12, int* n_matches) {
+  if (!ctx) return PLF_ERR_INVALID;
+  if (n1 < 0 || n2 < 0 || n1 > 65535 || n2 > 65535 || (n1 > 0 && (!d1 || !matches_12)) ||
+      (n2 > 0 && !d2))
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_match: bad arguments n1=%d n2=%d (each <= 65535)", n1,
+                    n2);
+  if (n_matches) *n_matches = 0;
+  if (n1 == 0) return PLF_OK;
+  if (n2 == 0) {
+    for (int i = 0; i < n1; ++i) matches_12[i] = -1;
+    return PLF_OK;
+  }
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t b1 = align256((size_t)n1 * 32), b2 = align256((size_t)n2 * 32),
+               k1 = align256((size_t)n1 * 4), k2 = align256((size_t)n2 * 4);
+  uint8_t* base = (uint8_t*)plf_scratch(ctx, 0, b1 + b2 + 3 * k1 + 2 * k2 + 1024);
+  if (!base) return PLF_ERR_CUDA;
+  uint8_t* p = base;
+  uint8_t* dq = p; p += b1;
+  uint8_t* dt = p; p += b2;
+  uint32_t* b12 = (uint32_t*)p; p += k1;
+  uint32_t* s12 = (uint32_t*)p; p += k1;
+  int32_t* dm = (int32_t*)p; p += k1;
+  uint32_t* b21 = (uint32_t*)p; p += k2;
+  uint32_t* s21 = (uint32_t*)p; p += k2;
+  int* dcount = (int*)p; p += 256;
+  KnnProblem* dkp = (KnnProblem*)p; p += 256;
+  NnrProblem* dnp = (NnrProblem*)p;
+  PLF_CUDA(ctx, cudaMemcpyAsync(dq, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(dt, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, ctx->stream));
+  PLF_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(int), ctx->stream));
+  KnnProblem hk[2] = {
+      {(const uint32_t*)dq, (const uint32_t*)dt, nullptr, nullptr, n1, n2, b12, s12},
+      {(const uint32_t*)dt, (const uint32_t*)dq, nullptr, nullptr, n2, n1, b21, s21}};
+  NnrProblem hn = {b12, s12, b21, s21, nullptr, nullptr, n1, n2, nnr, best_lr ? 1 : 0, dm, dcount};
+  const int nk = best_lr ? 2 : 1;
+  PLF_CUDA(ctx, cudaMemcpyAsync(dkp, hk, sizeof(KnnProblem) * nk, cudaMemcpyHostToDevice, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(dnp, &hn, sizeof hn, cudaMemcpyHostToDevice, ctx->stream));
+  plf_status st = plf_launch_knn2(ctx, dkp, nk, n1 > n2 ? n1 : n2);
+  if (st) return st;
+  st = plf_launch_nnr(ctx, dnp, 1, n1);
+  if (st) return st;
+  int hcount = 0;
+  PLF_CUDA(ctx, cudaMemcpyAsync(matches_12, dm, (size_t)n1 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&hcount, dcount, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n_matches) *n_matches = hcount;
+  return PLF_OK;
+}

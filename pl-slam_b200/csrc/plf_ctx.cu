@@ -1,0 +1,195 @@
+// Context lifetime, error reporting, scratch memory.  Host-side plumbing only; no kernels here.
+#include <stdarg.h>
+
+#include "plf_internal.h"
+
+static thread_local std::string g_create_err;
+
+plf_status plf_fail(plf_ctx* ctx, plf_status code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->err = buf;
+  else
+    g_create_err = buf;
+  return code;
+}
+
+void* plf_scratch(plf_ctx* ctx, int slot, size_t bytes) {
+  DevBuf& b = ctx->scratch[slot];
+  if (b.bytes >= bytes && b.p) return b.p;
+  if (b.p) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+  }
+  size_t want = bytes < 4096 ? 4096 : bytes;
+  want = (want + 255) & ~size_t(255);
+  cudaError_t e = cudaMalloc(&b.p, want);
+  if (e != cudaSuccess) {
+    plf_fail(ctx, PLF_ERR_CUDA, "cudaMalloc(%zu) scratch slot %d: %s", want, slot,
+             cudaGetErrorString(e));
+    b.p = nullptr;
+    return nullptr;
+  }
+  b.bytes = want;
+  return b.p;
+}
+
+void* plf_pinned(plf_ctx* ctx, size_t bytes) {
+  if (ctx->pinned_bytes >= bytes && ctx->pinned) return ctx->pinned;
+  if (ctx->pinned) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFreeHost(ctx->pinned);
+    ctx->pinned = nullptr;
+    ctx->pinned_bytes = 0;
+  }
+  size_t want = bytes < (1 << 20) ? (1 << 20) : bytes;
+  cudaError_t e = cudaHostAlloc(&ctx->pinned, want, cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    plf_fail(ctx, PLF_ERR_CUDA, "cudaHostAlloc(%zu): %s", want, cudaGetErrorString(e));
+    ctx->pinned = nullptr;
+    return nullptr;
+  }
+  ctx->pinned_bytes = want;
+  return ctx->pinned;
+}
+
+extern "C" {
+
+int plf_abi_version(void) { return PLF_ABI_VERSION; }
+
+const char* plf_last_error(const plf_ctx* ctx) {
+  return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+// Defaults = config/config/config_euroc.yaml:9-77 of the reference.
+void plf_default_params(plf_params* p) {
+  memset(p, 0, sizeof *p);
+  p->has_points = 1;
+  p->has_lines = 1;
+  p->best_lr_matches = 1;
+  p->max_dist_epip = 1.0f;
+  p->min_disp = 1.0f;
+  p->min_ratio_12_p = 0.9f;
+  p->line_sim_th = 0.75f;
+  p->stereo_overlap_th = 0.75f;
+  p->f2f_overlap_th = 0.75f;
+  p->min_line_length = 0.025f;
+  p->line_horiz_th = 0.1f;
+  p->min_ratio_12_l = 0.9f;
+  p->ls_min_disp_ratio = 0.7f;
+  p->homog_th = 1e-7;
+  p->min_features = 10;
+  p->max_iters = 5;
+  p->max_iters_ref = 10;
+  p->min_error = 1e-7;
+  p->min_error_change = 1e-7;
+  p->inlier_k = 4.0;
+  p->orb_nfeatures = 800;
+  p->orb_scale_factor = 1.2f;
+  p->orb_nlevels = 4;
+  p->orb_edge_th = 19;
+  p->orb_wta_k = 2;
+  p->orb_score = 1;
+  p->orb_patch_size = 31;
+  p->orb_fast_th = 20;
+  p->lsd_nfeatures = 300;
+  p->lsd_refine = 0;
+  p->lsd_scale = 1.2f;
+  p->lsd_sigma_scale = 0.6f;
+  p->lsd_quant = 2.0f;
+  p->lsd_ang_th = 22.5f;
+  p->lsd_log_eps = 1.0f;
+  p->lsd_density_th = 0.6f;
+  p->lsd_n_bins = 1024;
+}
+
+void plf_default_limits(plf_limits* l) {
+  l->max_batch = 8;
+  l->max_keypoints = 4096;
+  l->max_segments = 8192;
+  l->max_lines = 1024;
+}
+
+plf_status plf_create(const plf_params* params, const plf_camera* cam, const plf_limits* limits,
+                      int device, plf_ctx** out) {
+  if (!out) return plf_fail(nullptr, PLF_ERR_INVALID, "plf_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return plf_fail(nullptr, PLF_ERR_NO_DEVICE,
+                    "plf_create: no CUDA device (%s); this library has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+  if (device < 0 || device >= ndev)
+    return plf_fail(nullptr, PLF_ERR_INVALID, "plf_create: device %d out of range [0,%d)", device,
+                    ndev);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess)
+    return plf_fail(nullptr, PLF_ERR_NO_DEVICE, "cudaSetDevice(%d): %s", device,
+                    cudaGetErrorString(e));
+  plf_ctx* ctx = new plf_ctx();
+  ctx->device = device;
+  if (params)
+    ctx->params = *params;
+  else
+    plf_default_params(&ctx->params);
+  if (cam)
+    ctx->cam = *cam;
+  else {
+    plf_camera c = {1242, 375, 718.856, 718.856, 607.1928, 185.2157, 0.537165719};
+    ctx->cam = c;
+  }
+  if (limits)
+    ctx->limits = *limits;
+  else
+    plf_default_limits(&ctx->limits);
+  if (ctx->cam.width <= 0 || ctx->cam.height <= 0 || ctx->limits.max_batch <= 0) {
+    delete ctx;
+    return plf_fail(nullptr, PLF_ERR_INVALID, "plf_create: bad camera size or max_batch");
+  }
+  e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete ctx;
+    return plf_fail(nullptr, PLF_ERR_NO_DEVICE, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  *out = ctx;
+  return PLF_OK;
+}
+
+// subsystem destructors (defined in their own translation units)
+void plf_orb_free(plf_ctx* ctx);
+void plf_lsd_free(plf_ctx* ctx);
+void plf_lbd_free(plf_ctx* ctx);
+void plf_pipe_free(plf_ctx* ctx);
+
+void plf_destroy(plf_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  plf_pipe_free(ctx);
+  plf_orb_free(ctx);
+  plf_lsd_free(ctx);
+  plf_lbd_free(ctx);
+  for (auto& b : ctx->scratch)
+    if (b.p) cudaFree(b.p);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+long long plf_launch_count(const plf_ctx* ctx) { return ctx ? ctx->launches : 0; }
+void* plf_stream(const plf_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+plf_status plf_sync(plf_ctx* ctx) {
+  if (!ctx) return PLF_ERR_INVALID;
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PLF_OK;
+}
+
+}  // extern "C"

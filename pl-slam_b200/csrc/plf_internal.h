@@ -1,0 +1,96 @@
+// Internal declarations shared by the CUDA translation units of libplslam_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "plslam_b200.h"
+
+#define PLF_NUM_SMS 148
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+// Scratch arena: grows on demand (cudaMalloc), never shrinks; all users are stream-ordered on
+// ctx->stream so reuse between calls is safe.
+struct Scratch {
+  std::vector<DevBuf> bufs;
+};
+
+struct plf_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  plf_params params;
+  plf_camera cam;
+  plf_limits limits;
+  std::string err;
+  long long launches = 0;
+  // generic scratch slots (device) used by the host-pointer operator entry points
+  DevBuf scratch[16];
+  // pinned host staging
+  void* pinned = nullptr;
+  size_t pinned_bytes = 0;
+  // subsystem state (owned by the respective .cu)
+  struct OrbState* orb = nullptr;
+  struct LsdState* lsd = nullptr;
+  struct LbdState* lbd = nullptr;
+  struct PipeState* pipe = nullptr;
+};
+
+plf_status plf_fail(plf_ctx* ctx, plf_status code, const char* fmt, ...);
+// Ensures scratch slot `slot` holds at least `bytes`; returns device pointer or nullptr (error set).
+void* plf_scratch(plf_ctx* ctx, int slot, size_t bytes);
+void* plf_pinned(plf_ctx* ctx, size_t bytes);
+
+#define PLF_CUDA(ctx, call)                                                                  \
+  do {                                                                                       \
+    cudaError_t _e = (call);                                                                 \
+    if (_e != cudaSuccess)                                                                   \
+      return plf_fail((ctx), PLF_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call,        \
+                      cudaGetErrorString(_e));                                               \
+  } while (0)
+
+#define PLF_LAUNCH_CHECK(ctx)                                                                \
+  do {                                                                                       \
+    (ctx)->launches++;                                                                       \
+    cudaError_t _e = cudaGetLastError();                                                     \
+    if (_e != cudaSuccess)                                                                   \
+      return plf_fail((ctx), PLF_ERR_CUDA, "%s:%d kernel launch: %s", __FILE__, __LINE__,    \
+                      cudaGetErrorString(_e));                                               \
+  } while (0)
+
+// ---- matcher (match.cu) -----------------------------------------------------------------------
+// One kNN problem: queries q[nq][8 x u32] against train t[nt][8 x u32]. If nq_ptr/nt_ptr are
+// non-null the counts are read on the device (pipeline use), else nq/nt are used.
+struct KnnProblem {
+  const uint32_t* q;
+  const uint32_t* t;
+  const int* nq_ptr;
+  const int* nt_ptr;
+  int nq, nt;
+  uint32_t* best;    // [nq] packed (dist << 16 | idx), 0xFFFFFFFF if none
+  uint32_t* second;  // [nq]
+};
+// Launches the kNN kernel over `nprob` problems (device array), max_nq = upper bound of nq.
+plf_status plf_launch_knn2(plf_ctx* ctx, const KnnProblem* d_probs, int nprob, int max_nq);
+
+struct NnrProblem {
+  const uint32_t* best12;
+  const uint32_t* second12;
+  const uint32_t* best21;  // may be null when !best_lr
+  const uint32_t* second21;
+  const int* n1_ptr;
+  const int* n2_ptr;
+  int n1, n2;
+  float nnr;
+  int best_lr;
+  int32_t* matches12;  // [n1]
+  int* count;          // device counter (accumulated with atomicAdd; caller zeroes)
+};
+plf_status plf_launch_nnr(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, int max_n1);

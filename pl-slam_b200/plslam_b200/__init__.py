@@ -1,0 +1,187 @@
+"""ctypes binding of libplslam_b200.so (the C ABI in include/plslam_b200.h).
+
+Thin by design: numpy arrays in, numpy arrays out, every call goes straight through the C ABI to the
+CUDA kernels.  There is NO CPU fallback: if the shared library is missing or no CUDA device is
+present, construction raises.  Used by tests/, bench.py and __graft_entry__.py.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+import numpy as np
+
+_PKG_DIR = Path(__file__).resolve().parent.parent  # pl-slam_b200/
+REPO_ROOT = _PKG_DIR.parent
+LIB_PATH = _PKG_DIR / "lib" / "libplslam_b200.so"
+
+DESC_BYTES = 32
+
+
+class PlfError(RuntimeError):
+    pass
+
+
+class plf_params(C.Structure):
+    _fields_ = [
+        ("has_points", C.c_int), ("has_lines", C.c_int), ("best_lr_matches", C.c_int),
+        ("max_dist_epip", C.c_float), ("min_disp", C.c_float), ("min_ratio_12_p", C.c_float),
+        ("line_sim_th", C.c_float), ("stereo_overlap_th", C.c_float), ("f2f_overlap_th", C.c_float),
+        ("min_line_length", C.c_float), ("line_horiz_th", C.c_float), ("min_ratio_12_l", C.c_float),
+        ("ls_min_disp_ratio", C.c_float),
+        ("homog_th", C.c_double),
+        ("min_features", C.c_int), ("max_iters", C.c_int), ("max_iters_ref", C.c_int),
+        ("min_error", C.c_double), ("min_error_change", C.c_double), ("inlier_k", C.c_double),
+        ("orb_nfeatures", C.c_int), ("orb_scale_factor", C.c_float),
+        ("orb_nlevels", C.c_int), ("orb_edge_th", C.c_int), ("orb_wta_k", C.c_int),
+        ("orb_score", C.c_int), ("orb_patch_size", C.c_int), ("orb_fast_th", C.c_int),
+        ("lsd_nfeatures", C.c_int), ("lsd_refine", C.c_int),
+        ("lsd_scale", C.c_float), ("lsd_sigma_scale", C.c_float), ("lsd_quant", C.c_float),
+        ("lsd_ang_th", C.c_float), ("lsd_log_eps", C.c_float), ("lsd_density_th", C.c_float),
+        ("lsd_n_bins", C.c_int),
+    ]
+
+
+class plf_camera(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("b", C.c_double)]
+
+
+class plf_limits(C.Structure):
+    _fields_ = [("max_batch", C.c_int), ("max_keypoints", C.c_int), ("max_segments", C.c_int),
+                ("max_lines", C.c_int)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """Loads libplslam_b200.so; raises PlfError (never falls back) if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise PlfError(f"{LIB_PATH} not built: run `make` (or __graft_entry__.build()) first; "
+                       "there is no CPU fallback")
+    lib = C.CDLL(str(LIB_PATH))
+    lib.plf_last_error.restype = C.c_char_p
+    lib.plf_last_error.argtypes = [C.c_void_p]
+    lib.plf_launch_count.restype = C.c_longlong
+    lib.plf_launch_count.argtypes = [C.c_void_p]
+    lib.plf_stream.restype = C.c_void_p
+    lib.plf_stream.argtypes = [C.c_void_p]
+    lib.plf_destroy.restype = None
+    lib.plf_destroy.argtypes = [C.c_void_p]
+    lib.plf_default_params.restype = None
+    lib.plf_default_limits.restype = None
+    _lib = lib
+    return lib
+
+
+def default_params() -> plf_params:
+    p = plf_params()
+    load_library().plf_default_params(C.byref(p))
+    return p
+
+
+def default_limits() -> plf_limits:
+    l = plf_limits()
+    load_library().plf_default_limits(C.byref(l))
+    return l
+
+
+KITTI_CAMERA = dict(width=1242, height=375, fx=718.856, fy=718.856, cx=607.1928, cy=185.2157,
+                    b=0.537165719)  # config/dataset_params/kitti00-02.yaml:2-10
+EUROC_CAMERA = dict(width=752, height=480, fx=458.654, fy=457.296, cx=367.215, cy=248.375,
+                    b=0.110077842)  # config/dataset_params/euroc_params.yaml:2,8 (pre-rectified)
+
+
+def _u8(a, shape_tail=None):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a
+
+
+def _ptr(a, ctype):
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+class Frontend:
+    """One plf_ctx (one device, one stream).  Mirrors the role of `StereoFrameHandler`
+    (app/plslam_dataset.cpp:109) plus the free operators the reference calls on the path."""
+
+    def __init__(self, params: plf_params | None = None, camera: dict | plf_camera | None = None,
+                 limits: plf_limits | None = None, device: int = 0, **overrides):
+        self.lib = load_library()
+        self.params = params if params is not None else default_params()
+        for k, v in overrides.items():
+            if hasattr(self.params, k):
+                setattr(self.params, k, v)
+            else:
+                raise PlfError(f"unknown parameter {k}")
+        if camera is None:
+            camera = KITTI_CAMERA
+        self.camera = camera if isinstance(camera, plf_camera) else plf_camera(**camera)
+        self.limits = limits if limits is not None else default_limits()
+        self._ctx = C.c_void_p()
+        st = self.lib.plf_create(C.byref(self.params), C.byref(self.camera), C.byref(self.limits),
+                                 int(device), C.byref(self._ctx))
+        if st != 0:
+            raise PlfError(f"plf_create failed ({st}): {self.lib.plf_last_error(None).decode()}")
+
+    # -- plumbing --------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self.lib.plf_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, st: int, what: str):
+        if st != 0:
+            raise PlfError(f"{what} failed ({st}): {self.lib.plf_last_error(self._ctx).decode()}")
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.plf_launch_count(self._ctx))
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.plf_stream(self._ctx) or 0)
+
+    def sync(self):
+        self._check(self.lib.plf_sync(self._ctx), "plf_sync")
+
+    # -- matching --------------------------------------------------------------------------------
+    def hamming_knn2(self, d1, d2):
+        """cv::BFMatcher(NORM_HAMMING).knnMatch(d1, d2, k=2): returns idx1, dist1, idx2, dist2."""
+        d1 = _u8(d1).reshape(-1, DESC_BYTES)
+        d2 = _u8(d2).reshape(-1, DESC_BYTES)
+        n1, n2 = len(d1), len(d2)
+        out = [np.full(n1, -1, np.int32) for _ in range(4)]
+        st = self.lib.plf_hamming_knn2(self._ctx, _ptr(d1, C.c_uint8), n1, _ptr(d2, C.c_uint8), n2,
+                                       *[_ptr(o, C.c_int32) for o in out])
+        self._check(st, "plf_hamming_knn2")
+        return tuple(out)
+
+    def match(self, d1, d2, nnr: float, best_lr: bool = True):
+        """stvo-pl match(): returns (matches_12 int32[n1], n_matches)."""
+        d1 = _u8(d1).reshape(-1, DESC_BYTES)
+        d2 = _u8(d2).reshape(-1, DESC_BYTES)
+        n1, n2 = len(d1), len(d2)
+        m = np.full(n1, -1, np.int32)
+        cnt = C.c_int(0)
+        st = self.lib.plf_match(self._ctx, _ptr(d1, C.c_uint8), n1, _ptr(d2, C.c_uint8), n2,
+                                C.c_float(nnr), int(bool(best_lr)), _ptr(m, C.c_int32), C.byref(cnt))
+        self._check(st, "plf_match")
+        return m, cnt.value
