@@ -119,6 +119,38 @@ plf_status plf_hamming_knn2(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8
 plf_status plf_match(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr,
                      int best_lr, int32_t* matches_12, int* n_matches);
 
+/* ------------------------------------------------------------------------------------------------
+ * Line features
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Field-for-field mirror of cv::line_descriptor::KeyLine
+ * (3rdparty/line_descriptor/include/line_descriptor/descriptor_custom.hpp:105-176); 68 bytes. */
+typedef struct plf_keyline {
+  float angle;
+  int class_id;
+  int octave;
+  float ptx, pty;
+  float response;
+  float size;
+  float startPointX, startPointY, endPointX, endPointY;
+  float sPointInOctaveX, sPointInOctaveY, ePointInOctaveX, ePointInOctaveY;
+  float lineLength;
+  int numOfPixels;
+} plf_keyline;
+
+/* LBD prelude: GaussianBlur 5x5 sigma 1 then Sobel k=3 to CV_16S.  Replaces
+ * BinaryDescriptor::computeSobel (binary_descriptor_custom.cpp:373-398 -> :350-370).
+ * img: h rows of `stride` bytes (host). dxdy: h*w interleaved int16 pairs (dx,dy) (host). */
+plf_status plf_lbd_gradients(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride, int16_t* dxdy);
+
+/* LBD descriptors.  Replaces BinaryDescriptor::compute(image, keylines, descriptors, returnFloat)
+ * (binary_descriptor_custom.cpp:524-528 -> computeImpl :539-687 -> computeLBD :1026-1372).
+ * Uses from each KeyLine: sPointInOctave*, ePointInOctave*, numOfPixels, angle (octave 0 only, as the
+ * front-end calls it).  desc: n x 32 bytes (host).  desc_float (optional): n x 72 floats.
+ * n == 0 returns PLF_OK without touching desc (the reference prints a message and returns). */
+plf_status plf_lbd(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride,
+                   const plf_keyline* keylines, int n, uint8_t* desc, float* desc_float);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,3 +94,10 @@ struct NnrProblem {
   int* count;          // device counter (accumulated with atomicAdd; caller zeroes)
 };
 plf_status plf_launch_nnr(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, int max_n1);
+
+// ---- LBD (lbd.cu) ------------------------------------------------------------------------------
+plf_status plf_launch_blur5_sobel(plf_ctx* ctx, const uint8_t* imgs, int pitch, size_t img_stride,
+                                  int w, int h, int nimg, short2* grad, size_t grad_stride);
+plf_status plf_launch_lbd(plf_ctx* ctx, const short2* grad, size_t grad_stride, int w, int h, int nimg,
+                          const plf_keyline* kls, const int* counts, int max_lines, uint8_t* desc,
+                          float* desc_f);

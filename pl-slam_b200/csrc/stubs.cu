@@ -3,6 +3,5 @@
 extern "C" {
 void plf_orb_free(plf_ctx*) {}
 void plf_lsd_free(plf_ctx*) {}
-void plf_lbd_free(plf_ctx*) {}
 void plf_pipe_free(plf_ctx*) {}
 }

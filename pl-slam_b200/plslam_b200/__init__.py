@@ -53,6 +53,14 @@ class plf_limits(C.Structure):
                 ("max_lines", C.c_int)]
 
 
+KEYLINE_DTYPE = np.dtype([
+    ("angle", np.float32), ("class_id", np.int32), ("octave", np.int32),
+    ("ptx", np.float32), ("pty", np.float32), ("response", np.float32), ("size", np.float32),
+    ("startPointX", np.float32), ("startPointY", np.float32), ("endPointX", np.float32),
+    ("endPointY", np.float32), ("sPointInOctaveX", np.float32), ("sPointInOctaveY", np.float32),
+    ("ePointInOctaveX", np.float32), ("ePointInOctaveY", np.float32), ("lineLength", np.float32),
+    ("numOfPixels", np.int32)])  # == plf_keyline == cv::line_descriptor::KeyLine
+
 _lib = None
 
 
@@ -185,3 +193,28 @@ class Frontend:
                                 C.c_float(nnr), int(bool(best_lr)), _ptr(m, C.c_int32), C.byref(cnt))
         self._check(st, "plf_match")
         return m, cnt.value
+
+    # -- line descriptor -------------------------------------------------------------------------
+    def lbd_gradients(self, img):
+        """BinaryDescriptor::computeSobel: returns (dx, dy) int16 of the 5x5-blurred image."""
+        img = _u8(img)
+        h, w = img.shape
+        out = np.empty((h, w, 2), np.int16)
+        st = self.lib.plf_lbd_gradients(self._ctx, _ptr(img, C.c_uint8), w, h, img.strides[0],
+                                        _ptr(out, C.c_int16))
+        self._check(st, "plf_lbd_gradients")
+        return out[..., 0].copy(), out[..., 1].copy()
+
+    def lbd(self, img, keylines, want_float=False):
+        """BinaryDescriptor::compute(img, keylines, desc): returns uint8[n,32] (and float32[n,72])."""
+        img = _u8(img)
+        h, w = img.shape
+        kl = np.ascontiguousarray(keylines, KEYLINE_DTYPE)
+        n = len(kl)
+        desc = np.zeros((n, 32), np.uint8)
+        fl = np.zeros((n, 72), np.float32) if want_float else None
+        st = self.lib.plf_lbd(self._ctx, _ptr(img, C.c_uint8), w, h, img.strides[0],
+                              kl.ctypes.data_as(C.c_void_p), n, _ptr(desc, C.c_uint8),
+                              _ptr(fl, C.c_float) if want_float else None)
+        self._check(st, "plf_lbd")
+        return (desc, fl) if want_float else desc
