@@ -151,6 +151,43 @@ plf_status plf_lbd_gradients(plf_ctx* ctx, const uint8_t* img, int w, int h, int
 plf_status plf_lbd(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride,
                    const plf_keyline* keylines, int n, uint8_t* desc, float* desc_float);
 
+/* ------------------------------------------------------------------------------------------------
+ * Pose refinement
+ * ---------------------------------------------------------------------------------------------- */
+
+typedef struct plf_gn_opts {
+  double homog_th;   /* Config::homogTh (config_euroc.yaml:45; src/mapHandler.cpp:3344,3355) */
+  int max_iters;     /* stage 1 iterations (config_euroc.yaml:47) */
+  int max_iters_ref; /* stage 2 iterations (config_euroc.yaml:48) */
+  double eps_err;    /* stop if e < eps_err (twin: DBL_EPSILON :3434; stvo-pl: min_error) */
+  double eps_change; /* stop if |e - e_prev| < eps_change (twin: DBL_EPSILON; stvo-pl: min_error_change) */
+  double eps_step;   /* stop if |dx| < eps_step (twin: DBL_EPSILON :3441) */
+} plf_gn_opts;
+
+typedef struct plf_pose_result {
+  double T[16];   /* row-major 4x4 pose increment (T_inc / stvo-pl DT) */
+  double cov[36]; /* H^-1 of the last accumulation (DT_cov, src/mapHandler.cpp:3491) */
+  double x[6];    /* logmap_se3(T) = [t; w] */
+  double err;     /* normalised weighted error of the last accumulation */
+  int iters1, iters2, n_inliers_pt, n_inliers_ls;
+} plf_pose_result;
+
+/* Two-stage robust (Cauchy) Gauss-Newton on point + line reprojection residuals.  Replaces
+ * StereoFrameHandler::optimizePose (app/plslam_dataset.cpp:128; src/mapHandler.cpp:780); arithmetic of
+ * its in-tree twin MapHandler::computeRelativePoseRobustGN (src/mapHandler.cpp:3566-3957).
+ * P: np x 3 (3-D points, previous camera frame), pl_obs: np x 2 (observed pixels, current frame),
+ * sP,eP: nl x 3 (3-D endpoints), le_obs: nl x 3 (observed normalised line), all f64 host arrays;
+ * inlier_pt / inlier_ls: u8 flags, in (rows to use) and out (after the chi2 gate).  T_init: row-major
+ * 4x4 or NULL (identity).  opts NULL => thresholds from the ctx params (stvo-pl min_error/min_error_change). */
+plf_status plf_gn_pose(plf_ctx* ctx, const plf_gn_opts* opts, const double* P, const double* pl_obs,
+                       uint8_t* inlier_pt, int np, const double* sP, const double* eP,
+                       const double* le_obs, uint8_t* inlier_ls, int nl, const double* T_init,
+                       plf_pose_result* out);
+
+/* se(3) helpers of stvo-pl auxiliar.h used throughout src/mapHandler.cpp (e.g. :137-142,:3439,:3558):
+ * op 0 = expmap_se3 (in: 6 = [t; w], out: 16 row-major), op 1 = logmap_se3 (in: 16, out: 6). */
+plf_status plf_se3(plf_ctx* ctx, int op, const double* in, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -71,3 +71,61 @@ def lbd_compute(img, keylines, want_float=False):
     lib().orc_lbd_compute(_p(img), img.shape[1], img.shape[0], _p(kl), n, _p(desc),
                           _p(fl) if want_float else None)
     return (desc, fl) if want_float else desc
+
+
+# ---- Gauss-Newton (oracle/gn.c) --------------------------------------------------------------------
+class orc_camera(C.Structure):
+    _fields_ = [("width", C.c_int), ("height", C.c_int), ("fx", C.c_double), ("fy", C.c_double),
+                ("cx", C.c_double), ("cy", C.c_double), ("b", C.c_double)]
+
+
+class orc_gn_opts(C.Structure):
+    _fields_ = [("homog_th", C.c_double), ("max_iters", C.c_int), ("max_iters_ref", C.c_int),
+                ("eps_err", C.c_double), ("eps_change", C.c_double), ("eps_step", C.c_double)]
+
+
+class orc_pose_result(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("cov", C.c_double * 36), ("x", C.c_double * 6),
+                ("err", C.c_double), ("iters1", C.c_int), ("iters2", C.c_int),
+                ("n_inliers_pt", C.c_int), ("n_inliers_ls", C.c_int)]
+
+
+def gn_opts(homog_th=1e-7, max_iters=5, max_iters_ref=10, eps_err=1e-7, eps_change=1e-7,
+            eps_step=2.220446049250313e-16):
+    return orc_gn_opts(homog_th, max_iters, max_iters_ref, eps_err, eps_change, eps_step)
+
+
+def expmap_se3(x):
+    x = np.ascontiguousarray(x, np.float64).reshape(6); T = np.zeros(16)
+    lib().orc_expmap_se3(_p(x), _p(T)); return T.reshape(4, 4)
+
+
+def logmap_se3(T):
+    T = np.ascontiguousarray(T, np.float64).reshape(16); x = np.zeros(6)
+    lib().orc_logmap_se3(_p(T), _p(x)); return x
+
+
+def inverse_se3(T):
+    T = np.ascontiguousarray(T, np.float64).reshape(16); Ti = np.zeros(16)
+    lib().orc_inverse_se3(_p(T), _p(Ti)); return Ti.reshape(4, 4)
+
+
+def colpiv_qr_solve6(H, g):
+    H = np.ascontiguousarray(H, np.float64).reshape(36); g = np.ascontiguousarray(g, np.float64).reshape(6)
+    x = np.zeros(6); lib().orc_colpiv_qr_solve6(_p(H), _p(g), _p(x)); return x
+
+
+def gn_pose(cam, P, pl_obs, sP, eP, le_obs, inlier_pt=None, inlier_ls=None, T_init=None, opts=None):
+    f64 = lambda a, k: np.ascontiguousarray(a, np.float64).reshape(-1, k)
+    P, pl_obs, sP, eP, le_obs = f64(P, 3), f64(pl_obs, 2), f64(sP, 3), f64(eP, 3), f64(le_obs, 3)
+    ip = np.ones(len(P), np.uint8) if inlier_pt is None else np.ascontiguousarray(inlier_pt, np.uint8).copy()
+    il = np.ones(len(sP), np.uint8) if inlier_ls is None else np.ascontiguousarray(inlier_ls, np.uint8).copy()
+    T0 = np.eye(4).reshape(16) if T_init is None else np.ascontiguousarray(T_init, np.float64).reshape(16)
+    c = orc_camera(**cam) if isinstance(cam, dict) else cam
+    o = opts if opts is not None else gn_opts()
+    out = orc_pose_result()
+    lib().orc_gn_pose(C.byref(c), C.byref(o), _p(P), _p(pl_obs), _p(ip), len(P), _p(sP), _p(eP), _p(le_obs),
+                      _p(il), len(sP), _p(T0), C.byref(out))
+    return dict(T=np.array(out.T).reshape(4, 4), cov=np.array(out.cov).reshape(6, 6), x=np.array(out.x),
+                err=out.err, iters=(out.iters1, out.iters2), inlier_pt=ip, inlier_ls=il,
+                n_inliers=(out.n_inliers_pt, out.n_inliers_ls))

@@ -25,4 +25,30 @@ void orc_lbd_weights(double* gaussCoefL, double* gaussCoefG);
 void orc_lbd_compute(const uint8_t* img, int w, int h, const orc_keyline* kls, int n, uint8_t* desc_bin,
                      float* desc_float);
 int orc_keylines_from_segments(const float* segs, int m, int w, int h, double min_length, orc_keyline* out);
+
+/* ---- Gauss-Newton pose refinement (oracle/gn.c) ---- */
+typedef struct orc_camera { int width, height; double fx, fy, cx, cy, b; } orc_camera;
+typedef struct orc_gn_opts {
+  double homog_th;       /* Config::homogTh, config_euroc.yaml:45 */
+  int max_iters;         /* stage 1, config_euroc.yaml:47 */
+  int max_iters_ref;     /* stage 2, config_euroc.yaml:48 */
+  double eps_err;        /* stop if e < eps_err           (twin: DBL_EPSILON; stvo-pl: min_error) */
+  double eps_change;     /* stop if |e - e_prev| < eps_change (twin: DBL_EPSILON; stvo-pl: min_error_change) */
+  double eps_step;       /* stop if |dx| < eps_step        (twin: DBL_EPSILON) */
+} orc_gn_opts;
+typedef struct orc_pose_result {
+  double T[16];   /* row-major 4x4 increment T_inc */
+  double cov[36]; /* H^-1 of the last accumulation */
+  double x[6];    /* logmap_se3(T) = [t; w] */
+  double err;
+  int iters1, iters2, n_inliers_pt, n_inliers_ls;
+} orc_pose_result;
+void orc_expmap_se3(const double* x, double* T);
+void orc_logmap_se3(const double* T, double* x);
+void orc_inverse_se3(const double* T, double* Ti);
+void orc_colpiv_qr_solve6(const double* H, const double* g, double* x);
+int orc_inverse6(const double* A, double* Ainv);
+void orc_gn_pose(const orc_camera* cam, const orc_gn_opts* o, const double* P, const double* obs, uint8_t* inl_p,
+                 int np, const double* sP, const double* eP, const double* le, uint8_t* inl_l, int nl,
+                 const double* T_init, orc_pose_result* out);
 #endif

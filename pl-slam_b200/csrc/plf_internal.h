@@ -101,3 +101,22 @@ plf_status plf_launch_blur5_sobel(plf_ctx* ctx, const uint8_t* imgs, int pitch, 
 plf_status plf_launch_lbd(plf_ctx* ctx, const short2* grad, size_t grad_stride, int w, int h, int nimg,
                           const plf_keyline* kls, const int* counts, int max_lines, uint8_t* desc,
                           float* desc_f);
+
+// ---- Gauss-Newton (gn.cu) -----------------------------------------------------------------------
+struct GnProblem {
+  const double* P;    // [np][3]
+  const double* obs;  // [np][2]
+  uint8_t* inl_p;     // [np]
+  const int* np_ptr;
+  int np;
+  const double* sP;   // [nl][3]
+  const double* eP;
+  const double* le;
+  uint8_t* inl_l;
+  const int* nl_ptr;
+  int nl;
+  const double* T_init;  // 16 or null
+  plf_pose_result* out;
+};
+plf_gn_opts plf_gn_opts_from_params(const plf_params& p);
+plf_status plf_launch_gn(plf_ctx* ctx, const GnProblem* d_probs, int nprob, const plf_gn_opts& o);

@@ -53,6 +53,17 @@ class plf_limits(C.Structure):
                 ("max_lines", C.c_int)]
 
 
+class plf_gn_opts(C.Structure):
+    _fields_ = [("homog_th", C.c_double), ("max_iters", C.c_int), ("max_iters_ref", C.c_int),
+                ("eps_err", C.c_double), ("eps_change", C.c_double), ("eps_step", C.c_double)]
+
+
+class plf_pose_result(C.Structure):
+    _fields_ = [("T", C.c_double * 16), ("cov", C.c_double * 36), ("x", C.c_double * 6),
+                ("err", C.c_double), ("iters1", C.c_int), ("iters2", C.c_int),
+                ("n_inliers_pt", C.c_int), ("n_inliers_ls", C.c_int)]
+
+
 KEYLINE_DTYPE = np.dtype([
     ("angle", np.float32), ("class_id", np.int32), ("octave", np.int32),
     ("ptx", np.float32), ("pty", np.float32), ("response", np.float32), ("size", np.float32),
@@ -218,3 +229,37 @@ class Frontend:
                               _ptr(fl, C.c_float) if want_float else None)
         self._check(st, "plf_lbd")
         return (desc, fl) if want_float else desc
+
+    # -- pose refinement -------------------------------------------------------------------------
+    def gn_pose(self, P, pl_obs, sP, eP, le_obs, inlier_pt=None, inlier_ls=None, T_init=None, opts=None):
+        """StereoFrameHandler::optimizePose.  Returns dict(T, cov, x, err, iters, inlier_pt, inlier_ls)."""
+        f64 = lambda a, k: np.ascontiguousarray(a, np.float64).reshape(-1, k)
+        P, pl_obs, sP, eP, le_obs = f64(P, 3), f64(pl_obs, 2), f64(sP, 3), f64(eP, 3), f64(le_obs, 3)
+        n_p, n_l = len(P), len(sP)
+        ip = np.ones(n_p, np.uint8) if inlier_pt is None else np.ascontiguousarray(inlier_pt, np.uint8).copy()
+        il = np.ones(n_l, np.uint8) if inlier_ls is None else np.ascontiguousarray(inlier_ls, np.uint8).copy()
+        T0 = None if T_init is None else np.ascontiguousarray(T_init, np.float64).reshape(16)
+        out = plf_pose_result()
+        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double)) if a is not None and a.size else None
+        up = lambda a: a.ctypes.data_as(C.POINTER(C.c_uint8)) if a.size else None
+        st = self.lib.plf_gn_pose(self._ctx, C.byref(opts) if opts is not None else None, dp(P), dp(pl_obs),
+                                  up(ip), n_p, dp(sP), dp(eP), dp(le_obs), up(il), n_l,
+                                  dp(T0) if T0 is not None else None, C.byref(out))
+        self._check(st, "plf_gn_pose")
+        return dict(T=np.array(out.T).reshape(4, 4), cov=np.array(out.cov).reshape(6, 6), x=np.array(out.x),
+                    err=out.err, iters=(out.iters1, out.iters2), inlier_pt=ip, inlier_ls=il,
+                    n_inliers=(out.n_inliers_pt, out.n_inliers_ls))
+
+    def expmap_se3(self, x):
+        x = np.ascontiguousarray(x, np.float64).reshape(6)
+        T = np.zeros(16)
+        self._check(self.lib.plf_se3(self._ctx, 0, x.ctypes.data_as(C.POINTER(C.c_double)),
+                                     T.ctypes.data_as(C.POINTER(C.c_double))), "plf_se3")
+        return T.reshape(4, 4)
+
+    def logmap_se3(self, T):
+        T = np.ascontiguousarray(T, np.float64).reshape(16)
+        x = np.zeros(6)
+        self._check(self.lib.plf_se3(self._ctx, 1, T.ctypes.data_as(C.POINTER(C.c_double)),
+                                     x.ctypes.data_as(C.POINTER(C.c_double))), "plf_se3")
+        return x
