@@ -129,3 +129,44 @@ def gn_pose(cam, P, pl_obs, sP, eP, le_obs, inlier_pt=None, inlier_ls=None, T_in
     return dict(T=np.array(out.T).reshape(4, 4), cov=np.array(out.cov).reshape(6, 6), x=np.array(out.x),
                 err=out.err, iters=(out.iters1, out.iters2), inlier_pt=ip, inlier_ls=il,
                 n_inliers=(out.n_inliers_pt, out.n_inliers_ls))
+
+
+# ---- ORB (oracle/orb.c) ------------------------------------------------------------------------------
+KEYPOINT_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.float32), ("angle", np.float32),
+                           ("response", np.float32), ("octave", np.int32), ("lx", np.int32), ("ly", np.int32)])
+
+
+def resize_linear_exact(img, dw, dh, fx=None, fy=None):
+    img = np.ascontiguousarray(img, np.uint8)
+    sh, sw = img.shape
+    out = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_exact(_p(img), sw, sh, _p(out), dw, dh, C.c_double(fx if fx else dw / sw),
+                                  C.c_double(fy if fy else dh / sh))
+    return out
+
+
+def fast_score_map(img, threshold):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.empty_like(img)
+    lib().orc_fast_score_map(_p(img), img.shape[1], img.shape[0], int(threshold), _p(out))
+    return out
+
+
+def fast_atan2(y, x):
+    f = lib().orc_fast_atan2
+    f.restype = C.c_float
+    f.argtypes = [C.c_float, C.c_float]
+    return f(y, x)
+
+
+def orb(img, nfeatures=800, scale_factor=1.2, nlevels=4, edge_th=19, patch_size=31, fast_th=20, cap=20000):
+    img = np.ascontiguousarray(img, np.uint8)
+    kps = np.zeros(cap, KEYPOINT_DTYPE)
+    desc = np.zeros((cap, 32), np.uint8)
+    f = lib().orc_orb_detect_and_compute
+    f.restype = C.c_int
+    n = f(_p(img), img.shape[1], img.shape[0], int(nfeatures), C.c_float(scale_factor), int(nlevels), int(edge_th),
+          int(patch_size), int(fast_th), _p(kps), _p(desc), cap)
+    if n < 0:
+        raise RuntimeError("orb oracle: capacity exceeded")
+    return kps[:n].copy(), desc[:n].copy()

@@ -67,9 +67,10 @@ void orc_gaussian_kernel_q8(int ksize, double sigma, int* taps) {
   taps[ksize / 2] = 256 - 2 * s;
 }
 
-void orc_gaussian_blur_u8(const uint8_t* src, int w, int h, int ksize, double sigma, uint8_t* dst) {
-  int taps[33];
-  orc_gaussian_kernel_q8(ksize, sigma, taps);
+/* Separable integer filter with Q8 taps and one final rounding ((acc + 2^15) >> 16, saturated):
+ * the common core of OpenCV's CV_8U bit-exact GaussianBlur and of its generic 8U separable filter
+ * (createSeparableLinearFilter with bits = 8). BORDER_REFLECT_101. */
+void orc_blur_taps_u8(const uint8_t* src, int w, int h, int ksize, const int* taps, uint8_t* dst) {
   const int r = ksize / 2;
   uint32_t* tmp = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)w * h);
   for (int y = 0; y < h; y++)
@@ -86,6 +87,12 @@ void orc_gaussian_blur_u8(const uint8_t* src, int w, int h, int ksize, double si
       dst[(size_t)y * w + x] = (uint8_t)(v > 255 ? 255 : v);
     }
   free(tmp);
+}
+
+void orc_gaussian_blur_u8(const uint8_t* src, int w, int h, int ksize, double sigma, uint8_t* dst) {
+  int taps[33];
+  orc_gaussian_kernel_q8(ksize, sigma, taps);
+  orc_blur_taps_u8(src, w, h, ksize, taps, dst);
 }
 
 void orc_sobel3_i16(const uint8_t* src, int w, int h, int16_t* dx, int16_t* dy) {

@@ -19,12 +19,30 @@ typedef struct orc_keyline {
 } orc_keyline;
 
 void orc_gaussian_kernel_q8(int ksize, double sigma, int* taps);
+void orc_blur_taps_u8(const uint8_t* src, int w, int h, int ksize, const int* taps, uint8_t* dst);
 void orc_gaussian_blur_u8(const uint8_t* src, int w, int h, int ksize, double sigma, uint8_t* dst);
 void orc_sobel3_i16(const uint8_t* src, int w, int h, int16_t* dx, int16_t* dy);
 void orc_lbd_weights(double* gaussCoefL, double* gaussCoefG);
 void orc_lbd_compute(const uint8_t* img, int w, int h, const orc_keyline* kls, int n, uint8_t* desc_bin,
                      float* desc_float);
 int orc_keylines_from_segments(const float* segs, int m, int w, int h, double min_length, orc_keyline* out);
+
+/* ---- ORB (oracle/orb.c) ---- */
+typedef struct orc_keypoint {
+  float x, y;      /* cv::KeyPoint.pt (level-0 coordinates) */
+  float size, angle, response;
+  int octave;
+  int lx, ly;      /* integer coordinates inside its pyramid level (not a cv::KeyPoint field) */
+} orc_keypoint;
+void orc_resize_linear_exact(const uint8_t* src, int sw, int sh, uint8_t* dst, int dw, int dh, double inv_scale_x,
+                             double inv_scale_y);
+void orc_fast_score_map(const uint8_t* img, int w, int h, int threshold, uint8_t* score);
+float orc_fast_atan2(float y, float x);
+void orc_gaussian_kernel_f32(int ksize, double sigma, float* k);
+void orc_orb_blur7(const uint8_t* src, int w, int h, uint8_t* dst);
+int orc_orb_detect_and_compute(const uint8_t* image, int w, int h, int nfeatures, float scaleFactor, int nlevels,
+                               int edgeThreshold, int patchSize, int fastThreshold, orc_keypoint* kps,
+                               uint8_t* desc, int cap);
 
 /* ---- Gauss-Newton pose refinement (oracle/gn.c) ---- */
 typedef struct orc_camera { int width, height; double fx, fy, cx, cy, b; } orc_camera;
