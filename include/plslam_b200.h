@@ -120,6 +120,28 @@ plf_status plf_match(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2,
                      int best_lr, int32_t* matches_12, int* n_matches);
 
 /* ------------------------------------------------------------------------------------------------
+ * Point features
+ * ---------------------------------------------------------------------------------------------- */
+
+/* Field-for-field mirror of cv::KeyPoint (pt.x, pt.y, size, angle, response, octave, class_id); 28 bytes. */
+typedef struct plf_keypoint {
+  float x, y;
+  float size, angle, response;
+  int octave, class_id;
+} plf_keypoint;
+
+/* ORB detect + describe on one image.  Replaces stvo-pl StereoFrame::detectPointFeatures ->
+ * cv::ORB::create(orb_nfeatures, orb_scale_factor, orb_nlevels, orb_edge_th, 0, orb_wta_k, orb_score,
+ * orb_patch_size, orb_fast_th)->detectAndCompute(img, Mat(), kps, desc, false)
+ * (parameters config/config/config_euroc.yaml:59-67; descriptor rows used at src/mapHandler.cpp:86-88,302).
+ * Output order is canonical (octave, y, x): OpenCV's own order inside a level is the implementation-defined
+ * result of std::nth_element (KeyPointsFilter::retainBest); the SET of keypoints, every field and every
+ * descriptor are identical to OpenCV's.  kps/desc: host buffers with room for `cap` entries; *n receives
+ * the count (PLF_ERR_CAPACITY if it exceeds cap or the ctx limit max_keypoints). */
+plf_status plf_orb(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride, plf_keypoint* kps,
+                   uint8_t* desc, int cap, int* n);
+
+/* ------------------------------------------------------------------------------------------------
  * Line features
  * ---------------------------------------------------------------------------------------------- */
 

@@ -38,9 +38,12 @@ static const int h_comb[32][2] = {
     {4, 5}, {4, 6}, {4, 7}, {4, 8}, {5, 6}, {5, 7}, {5, 8}, {6, 7}, {6, 8}, {7, 8}};
 
 __device__ __forceinline__ int reflect101(int i, int n) {
-  if (i < 0) i = -i;
-  if (i >= n) i = 2 * (n - 1) - i;
-  return min(max(i, 0), n - 1);  // far-outside coordinates (partial tiles) are don't-care but must stay in bounds
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) {  // iterates more than once only for images narrower than the halo
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+  }
+  return i;
 }
 
 // grid: (ceil(w/64), ceil(h/16), nimg); block 256

@@ -1,0 +1,666 @@
+// ORB keypoints + rBRIEF-256 descriptors, batched over images.
+//
+// Replaces stvo-pl StereoFrame::detectPointFeatures -> cv::ORB::create(nfeatures, scaleFactor, nlevels, edgeTh, 0,
+// wtaK=2, FAST_SCORE, patchSize, fastTh)->detectAndCompute (parameters config/config/config_euroc.yaml:59-67; rows
+// consumed as pdesc_l at src/mapHandler.cpp:86-88,302).  OpenCV is not vendored by the reference; the arithmetic
+// mirrored here is OpenCV's published ORB (features2d orb.cpp / fast.cpp / fast_score.cpp, imgproc resize
+// INTER_LINEAR_EXACT and the float sepFilter2D Gaussian), pinned integer-for-integer against cv2 4.13 by oracle/orb.c.
+//
+// Kernels (all gridded [tile or feature, image]; one launch covers every image of the batch)
+//   k_resize_exact   pyramid level l from level l-1: Q8.8 x Q8.8 bilinear, one rounding (bit-exact INTER_LINEAR_EXACT)
+//   k_fast_nms       FAST-9/16 corner score + 3x3 non-max suppression + border filter on a 64x16 tile staged in
+//                    shared memory (halo 4); survivors are appended to a per-(image,level) candidate list and a
+//                    256-bin response histogram
+//   k_select_sort    KeyPointsFilter::retainBest: per-level response threshold from the histogram (n-th largest,
+//                    ties kept), compaction, in-shared-memory bitonic sort to the canonical (octave, y, x) order
+//   k_ic_angle       intensity-centroid orientation: integer moments over the 31-px circular patch, one warp per
+//                    keypoint, cv::fastAtan2 polynomial
+//   k_orb_blur7      7x7 sigma-2 Gaussian in float with FMA (OpenCV takes its sepFilter2D path for the pyramid ROI)
+//   k_rbrief         256 rotated pair tests, one warp per keypoint (lane = descriptor byte)
+// Roofline: every kernel streams u8 maps once (HBM-bound when batched); per-image algorithmic bytes are
+// A0 + 2*sum(A_k>=1) + 2*S + 56*N.
+#include "orb_pattern.h"
+#include "plf_internal.h"
+
+#define ORB_MAX_LEVELS 8
+#define ORB_TW 64
+#define ORB_TH 16
+#define ORB_SORT_CAP 4096
+
+struct OrbGeom {
+  int nlevels;
+  int w[ORB_MAX_LEVELS], h[ORB_MAX_LEVELS];
+  float scale[ORB_MAX_LEVELS];
+  int nfeat[ORB_MAX_LEVELS];
+  int umax[20];
+  size_t pyr_off[ORB_MAX_LEVELS];   // byte offset of level l (l>=1) inside one image's pyramid block
+  size_t pyr_stride;                // bytes of levels 1.. per image
+  size_t blur_off[ORB_MAX_LEVELS];  // blurred levels 0..
+  size_t blur_stride;
+  int cand_cap[ORB_MAX_LEVELS];
+  size_t cand_off[ORB_MAX_LEVELS];  // in entries
+  size_t cand_stride;
+  int tile_start[ORB_MAX_LEVELS + 1];  // FAST tiles: prefix over levels
+  int tiles_x[ORB_MAX_LEVELS];
+  int edge, fast_th, patch, half_patch;
+  int max_kp;
+};
+
+struct OrbState {
+  int w = 0, h = 0, nimg = 0;
+  OrbGeom g;
+  uint8_t* pyr = nullptr;    // levels 1..n-1, all images
+  uint8_t* blur = nullptr;   // blurred levels 0..n-1
+  uint32_t* cand = nullptr;  // candidate keys
+  int* cand_count = nullptr; // [nimg][levels]
+  int* hist = nullptr;       // [nimg][levels][256]
+  // resize tables per level l>=1: x: ofs (int), c1 (int); y likewise
+  int* rs_tab = nullptr;
+  size_t rs_x_off[ORB_MAX_LEVELS], rs_y_off[ORB_MAX_LEVELS];
+  // outputs
+  plf_keypoint* kps = nullptr;  // [nimg][max_kp]
+  short2* kp_lxy = nullptr;     // level coordinates
+  uint8_t* desc = nullptr;      // [nimg][max_kp][32]
+  int* kp_count = nullptr;      // [nimg]
+  int* overflow = nullptr;      // [1]
+  float blur_k[7];
+};
+
+__constant__ float c_blur7[7];
+
+__device__ __forceinline__ int orb_reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+  }
+  return i;
+}
+
+// ---- pyramid ---------------------------------------------------------------------------------------
+// tab layout per level: [ox(dw) | cx(dw) | oy(dh) | cy(dh)]
+__global__ void __launch_bounds__(256) k_resize_exact(const uint8_t* __restrict__ src, size_t src_stride, int sw,
+                                                      int sh, uint8_t* __restrict__ dst, size_t dst_stride, int dw,
+                                                      int dh, const int* __restrict__ tabx,
+                                                      const int* __restrict__ taby) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x >= dw) return;
+  const uint8_t* s = src + (size_t)blockIdx.z * src_stride;
+  const int ox = tabx[x], cx = tabx[dw + x], oy = taby[y], cy = taby[dh + y];
+  const uint8_t* r0 = s + (size_t)oy * sw + ox;
+  const uint8_t* r1 = r0 + sw;
+  const uint32_t h0 = r0[0] * (256 - cx) + r0[1] * cx;
+  const uint32_t h1 = r1[0] * (256 - cx) + r1[1] * cx;
+  const uint32_t v = (h0 * (256 - cy) + h1 * cy + 32768u) >> 16;
+  dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dw + x] = (uint8_t)(v > 255 ? 255 : v);
+}
+
+// ---- FAST + NMS ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool has_run9(uint32_t m16) {
+  uint32_t m = m16 | (m16 << 16);  // circular
+  uint32_t r = m & (m >> 1);       // runs of 2
+  r &= r >> 2;                     // 4
+  r &= r >> 4;                     // 8
+  r &= m >> 8;                     // 9
+  return (r & 0xFFFFu) != 0;
+}
+
+// exact cornerScore<16>: (max over 9-arcs of min signed difference, either polarity) - 1
+__device__ int fast_corner_score(const int* d /*16*/) {
+  int best = 0;
+#pragma unroll
+  for (int pol = 0; pol < 2; ++pol) {
+    int m2[16], m4[16], m8[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int a = pol ? -d[i] : d[i], b = pol ? -d[(i + 1) & 15] : d[(i + 1) & 15];
+      m2[i] = min(a, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m4[i] = min(m2[i], m2[(i + 2) & 15]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m8[i] = min(m4[i], m4[(i + 4) & 15]);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const int last = pol ? -d[(i + 8) & 15] : d[(i + 8) & 15];
+      best = max(best, min(m8[i], last));
+    }
+  }
+  return best - 1;
+}
+
+__global__ void __launch_bounds__(256) k_fast_nms(const uint8_t* __restrict__ img0, size_t img0_stride,
+                                                  const uint8_t* __restrict__ pyr, OrbGeom g,
+                                                  uint32_t* __restrict__ cand, int* __restrict__ cand_count,
+                                                  int* __restrict__ hist, int* __restrict__ overflow) {
+  // which level does this tile belong to
+  int l = 0;
+  while (l + 1 < g.nlevels && (int)blockIdx.x >= g.tile_start[l + 1]) ++l;
+  const int t = blockIdx.x - g.tile_start[l];
+  const int W = g.w[l], H = g.h[l];
+  const int x0 = (t % g.tiles_x[l]) * ORB_TW, y0 = (t / g.tiles_x[l]) * ORB_TH;
+  const int img = blockIdx.y;
+  const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride
+                                : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
+  __shared__ uint8_t px[ORB_TH + 8][ORB_TW + 8];   // halo 4
+  __shared__ uint8_t sc[ORB_TH + 2][ORB_TW + 4];   // halo 1 (padded)
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (ORB_TH + 8) * (ORB_TW + 8); i += 256) {
+    const int ry = i / (ORB_TW + 8), rx = i - ry * (ORB_TW + 8);
+    const int gx = min(max(x0 - 4 + rx, 0), W - 1), gy = min(max(y0 - 4 + ry, 0), H - 1);
+    px[ry][rx] = src[(size_t)gy * W + gx];
+  }
+  __syncthreads();
+  const int th = g.fast_th;
+  for (int i = tid; i < (ORB_TH + 2) * (ORB_TW + 2); i += 256) {
+    const int sy = i / (ORB_TW + 2), sx = i - sy * (ORB_TW + 2);
+    const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
+    int score = 0;
+    if (gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3) {
+      const int cy = sy + 3, cx = sx + 3;  // position in px
+      const int v = px[cy][cx];
+      // quick rejection on the 4 compass points (any 9-arc contains at least 2 of them... OpenCV tests pairs)
+      int d[16];
+      d[0] = v - px[cy + 3][cx];      d[1] = v - px[cy + 3][cx + 1];  d[2] = v - px[cy + 2][cx + 2];
+      d[3] = v - px[cy + 1][cx + 3];  d[4] = v - px[cy][cx + 3];      d[5] = v - px[cy - 1][cx + 3];
+      d[6] = v - px[cy - 2][cx + 2];  d[7] = v - px[cy - 3][cx + 1];  d[8] = v - px[cy - 3][cx];
+      d[9] = v - px[cy - 3][cx - 1];  d[10] = v - px[cy - 2][cx - 2]; d[11] = v - px[cy - 1][cx - 3];
+      d[12] = v - px[cy][cx - 3];     d[13] = v - px[cy + 1][cx - 3]; d[14] = v - px[cy + 2][cx - 2];
+      d[15] = v - px[cy + 3][cx - 1];
+      uint32_t md = 0, mb = 0;
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        md |= (d[k] > th ? 1u : 0u) << k;   // neighbour darker than centre by more than th
+        mb |= (d[k] < -th ? 1u : 0u) << k;  // brighter
+      }
+      if (has_run9(md) || has_run9(mb)) score = fast_corner_score(d);
+    }
+    sc[sy][sx] = (uint8_t)score;
+  }
+  __syncthreads();
+  for (int i = tid; i < ORB_TH * ORB_TW; i += 256) {
+    const int ty = i / ORB_TW, tx = i - ty * ORB_TW;
+    const int gx = x0 + tx, gy = y0 + ty;
+    const int s = sc[ty + 1][tx + 1];
+    if (s == 0) continue;
+    if (gx < g.edge || gx >= W - g.edge || gy < g.edge || gy >= H - g.edge) continue;  // runByImageBorder
+    if (!(s > sc[ty + 1][tx] && s > sc[ty + 1][tx + 2] && s > sc[ty][tx] && s > sc[ty][tx + 1] &&
+          s > sc[ty][tx + 2] && s > sc[ty + 2][tx] && s > sc[ty + 2][tx + 1] && s > sc[ty + 2][tx + 2]))
+      continue;
+    const int slot = atomicAdd(&cand_count[img * ORB_MAX_LEVELS + l], 1);
+    if (slot < g.cand_cap[l])
+      cand[(size_t)img * g.cand_stride + g.cand_off[l] + slot] = ((uint32_t)gy << 20) | ((uint32_t)gx << 8) | (uint32_t)s;
+    else
+      *overflow = 1;
+    atomicAdd(&hist[(img * ORB_MAX_LEVELS + l) * 256 + s], 1);
+  }
+}
+
+// ---- retainBest + canonical ordering -----------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_select_sort(OrbGeom g, const uint32_t* __restrict__ cand,
+                                                      const int* __restrict__ cand_count,
+                                                      const int* __restrict__ hist, plf_keypoint* __restrict__ kps,
+                                                      short2* __restrict__ kp_lxy, int* __restrict__ kp_count,
+                                                      int* __restrict__ overflow) {
+  __shared__ uint32_t keys[ORB_SORT_CAP];
+  __shared__ int s_cnt, s_thr;
+  const int img = blockIdx.x, tid = threadIdx.x;
+  int base = 0;
+  for (int l = 0; l < g.nlevels; ++l) {
+    const int n = min(cand_count[img * ORB_MAX_LEVELS + l], g.cand_cap[l]);
+    if (tid == 0) {
+      s_cnt = 0;
+      int thr = 0;
+      const int want = g.nfeat[l];
+      if (want < n) {
+        if (want == 0) {
+          thr = 256;
+        } else {
+          const int* hh = hist + (img * ORB_MAX_LEVELS + l) * 256;
+          int acc = 0;
+          for (int s = 255; s >= 0; --s) {
+            acc += hh[s];
+            if (acc >= want) {
+              thr = s;
+              break;
+            }
+          }
+        }
+      }
+      s_thr = thr;
+    }
+    __syncthreads();
+    const int thr = s_thr;
+    const uint32_t* c = cand + (size_t)img * g.cand_stride + g.cand_off[l];
+    for (int i = tid; i < n; i += 1024) {
+      const uint32_t k = c[i];
+      if ((int)(k & 0xFFu) >= thr) {
+        const int pos = atomicAdd(&s_cnt, 1);
+        if (pos < ORB_SORT_CAP) keys[pos] = k;
+      }
+    }
+    __syncthreads();
+    int m = s_cnt;
+    if (m > ORB_SORT_CAP) {
+      if (tid == 0) *overflow = 1;
+      m = ORB_SORT_CAP;
+    }
+    int p2 = 1;
+    while (p2 < m) p2 <<= 1;
+    for (int i = m + tid; i < p2; i += 1024) keys[i] = 0xFFFFFFFFu;
+    __syncthreads();
+    for (int k = 2; k <= p2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < p2; i += 1024) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const uint32_t a = keys[i], b = keys[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) {
+              keys[i] = b;
+              keys[ixj] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    for (int i = tid; i < m; i += 1024) {
+      const int o = base + i;
+      if (o < g.max_kp) {
+        const uint32_t k = keys[i];
+        const int y = k >> 20, x = (k >> 8) & 0xFFF, s = k & 0xFF;
+        plf_keypoint kp;
+        kp.x = __fmul_rn((float)x, g.scale[l]);
+        kp.y = __fmul_rn((float)y, g.scale[l]);
+        kp.size = __fmul_rn((float)g.patch, g.scale[l]);
+        kp.angle = -1.f;
+        kp.response = (float)s;
+        kp.octave = l;
+        kp.class_id = -1;
+        kps[(size_t)img * g.max_kp + o] = kp;
+        kp_lxy[(size_t)img * g.max_kp + o] = make_short2((short)x, (short)y);
+      } else if (i == m - 1) {
+        *overflow = 1;
+      }
+    }
+    base = min(base + m, g.max_kp);
+    __syncthreads();
+  }
+  if (tid == 0) kp_count[img] = base;
+}
+
+// ---- orientation -------------------------------------------------------------------------------------
+// cv::fastAtan2 scalar path (degrees); unfused float ops in OpenCV's order.
+__device__ __forceinline__ float orb_fast_atan2(float y, float x) {
+  const float p1 = 0.9997878412794807f * (float)(180 / 3.14159265358979323846);
+  const float p3 = -0.3258083974640975f * (float)(180 / 3.14159265358979323846);
+  const float p5 = 0.1555786518463281f * (float)(180 / 3.14159265358979323846);
+  const float p7 = -0.04432655554792128f * (float)(180 / 3.14159265358979323846);
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, (float)2.2204460492503131e-16));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, (float)2.2204460492503131e-16));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+__global__ void __launch_bounds__(256) k_ic_angle(const uint8_t* __restrict__ img0, size_t img0_stride,
+                                                  const uint8_t* __restrict__ pyr, OrbGeom g,
+                                                  plf_keypoint* __restrict__ kps, const short2* __restrict__ kp_lxy,
+                                                  const int* __restrict__ kp_count) {
+  const int img = blockIdx.y;
+  const int ki = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ki >= kp_count[img]) return;
+  plf_keypoint* kp = &kps[(size_t)img * g.max_kp + ki];
+  const int l = kp->octave;
+  const short2 p = kp_lxy[(size_t)img * g.max_kp + ki];
+  const int W = g.w[l];
+  const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride
+                                : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
+  const uint8_t* center = src + (size_t)p.y * W + p.x;
+  const int hp = g.half_patch;
+  int m01 = 0, m10 = 0;
+  const int u = lane - hp;  // lanes 0..2*hp cover u = -hp..hp (hp = 15 -> 31 lanes)
+  if (lane <= 2 * hp) {
+    m10 += u * center[u];
+    for (int v = 1; v <= hp; ++v) {
+      const int d = g.umax[v];
+      if (u >= -d && u <= d) {
+        const int vp = center[u + v * W], vm = center[u - v * W];
+        m01 += v * (vp - vm);
+        m10 += u * (vp + vm);
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    m01 += __shfl_xor_sync(0xFFFFFFFFu, m01, off);
+    m10 += __shfl_xor_sync(0xFFFFFFFFu, m10, off);
+  }
+  if (lane == 0) kp->angle = orb_fast_atan2((float)m01, (float)m10);
+}
+
+// ---- descriptor-stage blur -----------------------------------------------------------------------------
+// float row pass (sequential, FMA), symmetric float column pass (FMA), round-half-even saturate: OpenCV's sepFilter2D
+// path for the pyramid ROI on FMA-capable hosts (see oracle/orb.c orc_orb_blur7).
+__global__ void __launch_bounds__(256) k_orb_blur7(const uint8_t* __restrict__ img0, size_t img0_stride,
+                                                   const uint8_t* __restrict__ pyr, OrbGeom g,
+                                                   uint8_t* __restrict__ blur) {
+  int l = 0;
+  while (l + 1 < g.nlevels && (int)blockIdx.x >= g.tile_start[l + 1]) ++l;
+  const int t = blockIdx.x - g.tile_start[l];
+  const int W = g.w[l], H = g.h[l];
+  const int x0 = (t % g.tiles_x[l]) * ORB_TW, y0 = (t / g.tiles_x[l]) * ORB_TH;
+  const int img = blockIdx.y;
+  const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride
+                                : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
+  uint8_t* dst = blur + (size_t)img * g.blur_stride + g.blur_off[l];
+  __shared__ uint8_t raw[ORB_TH + 6][ORB_TW + 8];
+  __shared__ float hrow[ORB_TH + 6][ORB_TW];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (ORB_TH + 6) * (ORB_TW + 6); i += 256) {
+    const int ry = i / (ORB_TW + 6), rx = i - ry * (ORB_TW + 6);
+    raw[ry][rx] = src[(size_t)orb_reflect101(y0 - 3 + ry, H) * W + orb_reflect101(x0 - 3 + rx, W)];
+  }
+  __syncthreads();
+  for (int i = tid; i < (ORB_TH + 6) * ORB_TW; i += 256) {
+    const int ry = i / ORB_TW, tx = i - ry * ORB_TW;
+    const uint8_t* p = &raw[ry][tx];
+    float a = __fmul_rn(c_blur7[0], (float)p[0]);
+#pragma unroll
+    for (int k = 1; k < 7; ++k) a = __fmaf_rn(c_blur7[k], (float)p[k], a);
+    hrow[ry][tx] = a;
+  }
+  __syncthreads();
+  for (int i = tid; i < ORB_TH * ORB_TW; i += 256) {
+    const int ty = i / ORB_TW, tx = i - ty * ORB_TW;
+    const int gx = x0 + tx, gy = y0 + ty;
+    if (gx >= W || gy >= H) continue;
+    float a = __fmul_rn(c_blur7[3], hrow[ty + 3][tx]);
+#pragma unroll
+    for (int k = 1; k <= 3; ++k) a = __fmaf_rn(c_blur7[3 + k], __fadd_rn(hrow[ty + 3 + k][tx], hrow[ty + 3 - k][tx]), a);
+    int v = __float2int_rn(a);
+    v = v < 0 ? 0 : (v > 255 ? 255 : v);
+    dst[(size_t)gy * W + gx] = (uint8_t)v;
+  }
+}
+
+// ---- rBRIEF --------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur, OrbGeom g,
+                                                const plf_keypoint* __restrict__ kps,
+                                                const int* __restrict__ kp_count, const int8_t* __restrict__ pattern,
+                                                uint8_t* __restrict__ desc) {
+  __shared__ int8_t pat[1024];
+  for (int i = threadIdx.x; i < 1024; i += 256) pat[i] = pattern[i];
+  __syncthreads();
+  const int img = blockIdx.y;
+  const int ki = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (ki >= kp_count[img]) return;
+  const plf_keypoint kp = kps[(size_t)img * g.max_kp + ki];
+  const int l = kp.octave, W = g.w[l];
+  const float scale = __fdiv_rn(1.f, g.scale[l]);
+  const float angle = __fmul_rn(kp.angle, (float)(3.14159265358979323846 / 180.f));
+  const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+  const uint8_t* center = blur + (size_t)img * g.blur_stride + g.blur_off[l] +
+                          (size_t)__float2int_rn(__fmul_rn(kp.y, scale)) * W + __float2int_rn(__fmul_rn(kp.x, scale));
+  unsigned val = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int8_t* q = pat + (lane * 8 + j) * 4;
+    const float qx0 = (float)q[0], qy0 = (float)q[1], qx1 = (float)q[2], qy1 = (float)q[3];
+    const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(qx0, a), __fmul_rn(qy0, b)));
+    const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(qx0, b), __fmul_rn(qy0, a)));
+    const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(qx1, a), __fmul_rn(qy1, b)));
+    const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(qx1, b), __fmul_rn(qy1, a)));
+    const int t0 = center[iy0 * W + ix0], t1 = center[iy1 * W + ix1];
+    val |= (t0 < t1 ? 1u : 0u) << j;
+  }
+  desc[((size_t)img * g.max_kp + ki) * 32 + lane] = (uint8_t)val;
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+static int cv_round_f(float v) { return (int)nearbyintf(v); }
+
+static void linear_coeffs_host(int srcsize, int dstsize, double scale, int* ofs, int* c1) {
+  // interpolationLinear::getCoeffs (resize.cpp, bit-exact path); clamped cases folded into (ofs, c1)
+  int mn = 0, mx = dstsize;
+  for (int v = 0; v < dstsize; v++) {
+    const double fval = scale * ((double)v + 0.5) - 0.5;
+    const int ival = (int)floor(fval);
+    ofs[v] = 0;
+    c1[v] = 0;
+    if (ival >= 0 && srcsize > 1) {
+      if (ival < srcsize - 1) {
+        ofs[v] = ival;
+        c1[v] = (int)nearbyint((fval - ival) * 256.0);
+      } else if (v < mx) {
+        mx = v;
+      }
+    } else if (v + 1 > mn) {
+      mn = v + 1;
+    }
+  }
+  for (int v = 0; v < dstsize; v++) {
+    if (v < mn) {
+      ofs[v] = 0;
+      c1[v] = 0;
+    } else if (v >= mx) {
+      ofs[v] = srcsize >= 2 ? srcsize - 2 : 0;
+      c1[v] = srcsize >= 2 ? 256 : 0;
+    }
+  }
+}
+
+static void orb_release(OrbState* s) {
+  if (!s) return;
+  cudaFree(s->pyr); cudaFree(s->blur); cudaFree(s->cand); cudaFree(s->cand_count); cudaFree(s->hist);
+  cudaFree(s->rs_tab); cudaFree(s->kps); cudaFree(s->kp_lxy); cudaFree(s->desc); cudaFree(s->kp_count);
+  cudaFree(s->overflow);
+  s->pyr = s->blur = s->desc = nullptr;
+}
+
+extern "C" void plf_orb_free(plf_ctx* ctx) {
+  if (ctx->orb) {
+    orb_release(ctx->orb);
+    delete ctx->orb;
+    ctx->orb = nullptr;
+  }
+}
+
+static int8_t* g_dev_pattern = nullptr;  // shared by all contexts on a device (read-only)
+static int g_dev_pattern_device = -1;
+
+// (Re)builds the ORB state for images of w x h and up to nimg images per launch.
+plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg) {
+  OrbState* s = ctx->orb;
+  if (s && s->w == w && s->h == h && s->nimg >= nimg) return PLF_OK;
+  if (s) {
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    orb_release(s);
+  } else {
+    s = ctx->orb = new OrbState();
+  }
+  const plf_params& P = ctx->params;
+  if (P.orb_nlevels < 1 || P.orb_nlevels > ORB_MAX_LEVELS || P.orb_wta_k != 2 || P.orb_score != 1 ||
+      P.orb_patch_size != 31)
+    return plf_fail(ctx, PLF_ERR_INVALID,
+                    "ORB: supported configuration is 1..8 levels, WTA_K=2, FAST score, patch 31 (got levels=%d "
+                    "wta_k=%d score=%d patch=%d)", P.orb_nlevels, P.orb_wta_k, P.orb_score, P.orb_patch_size);
+  if (w >= 4096 || h >= 4096) return plf_fail(ctx, PLF_ERR_INVALID, "ORB: image larger than 4095 px");
+  s->w = w; s->h = h; s->nimg = nimg;
+  OrbGeom& g = s->g;
+  memset(&g, 0, sizeof g);
+  g.nlevels = P.orb_nlevels;
+  g.edge = P.orb_edge_th; g.fast_th = min(max(P.orb_fast_th, 0), 255);
+  g.patch = P.orb_patch_size; g.half_patch = P.orb_patch_size / 2;
+  g.max_kp = ctx->limits.max_keypoints;
+  const double scaleFactor = (double)P.orb_scale_factor;
+  size_t pyr = 0, blur = 0, cand = 0;
+  int tiles = 0;
+  for (int l = 0; l < g.nlevels; ++l) {
+    const float sc = (float)pow(scaleFactor, (double)l);
+    g.scale[l] = sc;
+    const float inv = 1.0f / sc;
+    g.w[l] = cv_round_f(w * inv);
+    g.h[l] = cv_round_f(h * inv);
+    if (g.w[l] < 2 * g.edge + 8 || g.h[l] < 2 * g.edge + 8)
+      return plf_fail(ctx, PLF_ERR_INVALID, "ORB: level %d (%dx%d) too small for edge threshold %d", l, g.w[l],
+                      g.h[l], g.edge);
+    const size_t a = ((size_t)g.w[l] * g.h[l] + 255) & ~size_t(255);
+    if (l >= 1) { g.pyr_off[l] = pyr; pyr += a; }
+    g.blur_off[l] = blur; blur += a;
+    g.cand_cap[l] = (int)std::min<size_t>((size_t)g.w[l] * g.h[l] / 9 + 64, 32768);
+    g.cand_off[l] = cand; cand += g.cand_cap[l];
+    g.tiles_x[l] = (g.w[l] + ORB_TW - 1) / ORB_TW;
+    g.tile_start[l] = tiles;
+    tiles += g.tiles_x[l] * ((g.h[l] + ORB_TH - 1) / ORB_TH);
+  }
+  g.tile_start[g.nlevels] = tiles;
+  for (int l = g.nlevels + 1; l <= ORB_MAX_LEVELS; ++l) g.tile_start[l] = tiles;
+  g.pyr_stride = pyr; g.blur_stride = blur; g.cand_stride = cand;
+  {  // nfeaturesPerLevel (orb.cpp computeKeyPoints)
+    const float factor = (float)(1.0 / scaleFactor);
+    float nd = P.orb_nfeatures * (1 - factor) / (1 - (float)pow((double)factor, (double)g.nlevels));
+    int sum = 0;
+    for (int l = 0; l < g.nlevels - 1; ++l) {
+      g.nfeat[l] = cv_round_f(nd);
+      sum += g.nfeat[l];
+      nd *= factor;
+    }
+    g.nfeat[g.nlevels - 1] = std::max(P.orb_nfeatures - sum, 0);
+  }
+  {  // umax
+    const int hp = g.half_patch;
+    int v, v0, vmax = (int)floor(hp * sqrt(2.f) / 2 + 1), vmin = (int)ceil(hp * sqrt(2.f) / 2);
+    for (v = 0; v <= vmax; ++v) g.umax[v] = (int)nearbyint(sqrt((double)hp * hp - v * v));
+    for (v = hp, v0 = 0; v >= vmin; --v) {
+      while (g.umax[v0] == g.umax[v0 + 1]) ++v0;
+      g.umax[v] = v0;
+      ++v0;
+    }
+  }
+  // resize tables
+  std::vector<int> tab;
+  for (int l = 1; l < g.nlevels; ++l) {
+    const int sw = g.w[l - 1], sh = g.h[l - 1], dw = g.w[l], dh = g.h[l];
+    s->rs_x_off[l] = tab.size();
+    tab.resize(tab.size() + 2 * dw);
+    linear_coeffs_host(sw, dw, 1.0 / ((double)dw / sw), &tab[s->rs_x_off[l]], &tab[s->rs_x_off[l] + dw]);
+    s->rs_y_off[l] = tab.size();
+    tab.resize(tab.size() + 2 * dh);
+    linear_coeffs_host(sh, dh, 1.0 / ((double)dh / sh), &tab[s->rs_y_off[l]], &tab[s->rs_y_off[l] + dh]);
+  }
+  const size_t N = (size_t)nimg;
+  PLF_CUDA(ctx, cudaMalloc(&s->pyr, std::max<size_t>(pyr, 256) * N));
+  PLF_CUDA(ctx, cudaMalloc(&s->blur, blur * N));
+  PLF_CUDA(ctx, cudaMalloc(&s->cand, cand * N * sizeof(uint32_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->cand_count, N * ORB_MAX_LEVELS * sizeof(int)));
+  PLF_CUDA(ctx, cudaMalloc(&s->hist, N * ORB_MAX_LEVELS * 256 * sizeof(int)));
+  PLF_CUDA(ctx, cudaMalloc(&s->rs_tab, std::max<size_t>(tab.size(), 1) * sizeof(int)));
+  PLF_CUDA(ctx, cudaMalloc(&s->kps, N * g.max_kp * sizeof(plf_keypoint)));
+  PLF_CUDA(ctx, cudaMalloc(&s->kp_lxy, N * g.max_kp * sizeof(short2)));
+  PLF_CUDA(ctx, cudaMalloc(&s->desc, N * g.max_kp * 32));
+  PLF_CUDA(ctx, cudaMalloc(&s->kp_count, N * sizeof(int)));
+  PLF_CUDA(ctx, cudaMalloc(&s->overflow, sizeof(int)));
+  PLF_CUDA(ctx, cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream));
+  if (!tab.empty())
+    PLF_CUDA(ctx, cudaMemcpyAsync(s->rs_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  {  // getGaussianKernel(7, 2, CV_32F): host doubles -> float (pinned equal to cv2 in tests)
+    double d[7], sum = 0;
+    for (int i = 0; i < 7; ++i) {
+      const double x = i - 3.0;
+      d[i] = exp(-0.5 / (2.0 * 2.0) * x * x);
+      sum += d[i];
+    }
+    sum = 1. / sum;
+    for (int i = 0; i < 7; ++i) s->blur_k[i] = (float)(d[i] * sum);
+    PLF_CUDA(ctx, cudaMemcpyToSymbolAsync(c_blur7, s->blur_k, sizeof s->blur_k, 0, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (!g_dev_pattern || g_dev_pattern_device != ctx->device) {
+    int8_t hp[1024];
+    for (int i = 0; i < 1024; ++i) hp[i] = (int8_t)h_orb_bit_pattern_31[i];
+    PLF_CUDA(ctx, cudaMalloc(&g_dev_pattern, 1024));
+    PLF_CUDA(ctx, cudaMemcpyAsync(g_dev_pattern, hp, 1024, cudaMemcpyHostToDevice, ctx->stream));
+    g_dev_pattern_device = ctx->device;
+  }
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PLF_OK;
+}
+
+// Runs ORB on nimg images resident at d_imgs ([nimg][h][w], stride img_stride bytes). Results stay on the device.
+plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg) {
+  plf_status st = plf_orb_prepare(ctx, w, h, nimg);
+  if (st) return st;
+  OrbState* s = ctx->orb;
+  const OrbGeom& g = s->g;
+  cudaStream_t cs = ctx->stream;
+  PLF_CUDA(ctx, cudaMemsetAsync(s->cand_count, 0, (size_t)nimg * ORB_MAX_LEVELS * sizeof(int), cs));
+  PLF_CUDA(ctx, cudaMemsetAsync(s->hist, 0, (size_t)nimg * ORB_MAX_LEVELS * 256 * sizeof(int), cs));
+  for (int l = 1; l < g.nlevels; ++l) {
+    const uint8_t* src = (l == 1) ? d_imgs : s->pyr + g.pyr_off[l - 1];
+    const size_t sstride = (l == 1) ? img_stride : g.pyr_stride;
+    dim3 grid((g.w[l] + 255) / 256, g.h[l], nimg);
+    k_resize_exact<<<grid, 256, 0, cs>>>(src, sstride, g.w[l - 1], g.h[l - 1], s->pyr + g.pyr_off[l], g.pyr_stride,
+                                         g.w[l], g.h[l], s->rs_tab + s->rs_x_off[l], s->rs_tab + s->rs_y_off[l]);
+    PLF_LAUNCH_CHECK(ctx);
+  }
+  const int tiles = g.tile_start[g.nlevels];
+  k_fast_nms<<<dim3(tiles, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->cand, s->cand_count, s->hist,
+                                                 s->overflow);
+  PLF_LAUNCH_CHECK(ctx);
+  k_select_sort<<<nimg, 1024, 0, cs>>>(g, s->cand, s->cand_count, s->hist, s->kps, s->kp_lxy, s->kp_count, s->overflow);
+  PLF_LAUNCH_CHECK(ctx);
+  k_ic_angle<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->kps, s->kp_lxy, s->kp_count);
+  PLF_LAUNCH_CHECK(ctx);
+  k_orb_blur7<<<dim3(tiles, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->blur);
+  PLF_LAUNCH_CHECK(ctx);
+  k_rbrief<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(s->blur, g, s->kps, s->kp_count, g_dev_pattern, s->desc);
+  PLF_LAUNCH_CHECK(ctx);
+  return PLF_OK;
+}
+
+// device-side accessors for the pipeline
+void plf_orb_outputs(plf_ctx* ctx, plf_keypoint** kps, uint8_t** desc, int** counts, int* max_kp) {
+  OrbState* s = ctx->orb;
+  *kps = s->kps; *desc = s->desc; *counts = s->kp_count; *max_kp = s->g.max_kp;
+}
+
+extern "C" plf_status plf_orb(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride, plf_keypoint* kps,
+                              uint8_t* desc, int cap, int* n_out) {
+  if (!ctx || !img || !n_out || w < 8 || h < 8 || stride < w || cap < 0 || (cap > 0 && (!kps || !desc)))
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_orb: bad arguments");
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint8_t* dimg = (uint8_t*)plf_scratch(ctx, 3, (size_t)w * h);
+  if (!dimg) return PLF_ERR_CUDA;
+  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, w, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  plf_status st = plf_orb_run(ctx, dimg, (size_t)w * h, w, h, 1);
+  if (st) return st;
+  OrbState* s = ctx->orb;
+  int n = 0, ovf = 0;
+  PLF_CUDA(ctx, cudaMemcpyAsync(&n, s->kp_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ovf) {
+    cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream);
+    return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_orb: keypoint capacity exceeded (max_keypoints=%d)", s->g.max_kp);
+  }
+  *n_out = n;
+  if (n > cap) return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_orb: %d keypoints > caller capacity %d", n, cap);
+  if (n > 0) {
+    PLF_CUDA(ctx, cudaMemcpyAsync(kps, s->kps, (size_t)n * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpyAsync(desc, s->desc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return PLF_OK;
+}

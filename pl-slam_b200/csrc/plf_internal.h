@@ -5,6 +5,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -120,3 +121,8 @@ struct GnProblem {
 };
 plf_gn_opts plf_gn_opts_from_params(const plf_params& p);
 plf_status plf_launch_gn(plf_ctx* ctx, const GnProblem* d_probs, int nprob, const plf_gn_opts& o);
+
+// ---- ORB (orb.cu) --------------------------------------------------------------------------------
+plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg);
+plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg);
+void plf_orb_outputs(plf_ctx* ctx, plf_keypoint** kps, uint8_t** desc, int** counts, int* max_kp);

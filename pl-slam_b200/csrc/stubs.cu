@@ -1,7 +1,6 @@
 // Temporary no-op destructors for subsystems that are not built yet (removed as they land).
 #include "plf_internal.h"
 extern "C" {
-void plf_orb_free(plf_ctx*) {}
 void plf_lsd_free(plf_ctx*) {}
 void plf_pipe_free(plf_ctx*) {}
 }

@@ -72,6 +72,9 @@ KEYLINE_DTYPE = np.dtype([
     ("ePointInOctaveX", np.float32), ("ePointInOctaveY", np.float32), ("lineLength", np.float32),
     ("numOfPixels", np.int32)])  # == plf_keyline == cv::line_descriptor::KeyLine
 
+KEYPOINT_DTYPE = np.dtype([("x", np.float32), ("y", np.float32), ("size", np.float32), ("angle", np.float32),
+                           ("response", np.float32), ("octave", np.int32), ("class_id", np.int32)])  # cv::KeyPoint
+
 _lib = None
 
 
@@ -263,3 +266,17 @@ class Frontend:
         self._check(self.lib.plf_se3(self._ctx, 1, T.ctypes.data_as(C.POINTER(C.c_double)),
                                      x.ctypes.data_as(C.POINTER(C.c_double))), "plf_se3")
         return x
+
+    # -- point features --------------------------------------------------------------------------
+    def orb(self, img, cap=8192):
+        """cv::ORB::detectAndCompute with the ctx parameters: returns (keypoints[KEYPOINT_DTYPE], desc u8[n,32])
+        in canonical (octave, y, x) order."""
+        img = _u8(img)
+        h, w = img.shape
+        kps = np.zeros(cap, KEYPOINT_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        st = self.lib.plf_orb(self._ctx, _ptr(img, C.c_uint8), w, h, img.strides[0],
+                              kps.ctypes.data_as(C.c_void_p), _ptr(desc, C.c_uint8), cap, C.byref(n))
+        self._check(st, "plf_orb")
+        return kps[:n.value].copy(), desc[:n.value].copy()
