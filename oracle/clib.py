@@ -170,3 +170,16 @@ def orb(img, nfeatures=800, scale_factor=1.2, nlevels=4, edge_th=19, patch_size=
     if n < 0:
         raise RuntimeError("orb oracle: capacity exceeded")
     return kps[:n].copy(), desc[:n].copy()
+
+
+# ---- LSD (oracle/lsd.c) ------------------------------------------------------------------------------
+def lsd(img, scale=1.2, sigma_scale=0.6, quant=2.0, ang_th=22.5, n_bins=1024, order_mode=0, trig_mode=0, cap=65536):
+    img = np.ascontiguousarray(img, np.uint8)
+    segs = np.zeros((cap, 4), np.float32)
+    f = lib().orc_lsd_detect
+    f.restype = C.c_int
+    n = f(_p(img), img.shape[1], img.shape[0], C.c_double(scale), C.c_double(sigma_scale), C.c_double(quant),
+          C.c_double(ang_th), int(n_bins), int(order_mode), int(trig_mode), _p(segs), cap)
+    if n < 0:
+        raise RuntimeError("lsd oracle: capacity exceeded")
+    return segs[:n].copy()

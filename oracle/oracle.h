@@ -44,6 +44,11 @@ int orc_orb_detect_and_compute(const uint8_t* image, int w, int h, int nfeatures
                                int edgeThreshold, int patchSize, int fastThreshold, orc_keypoint* kps,
                                uint8_t* desc, int cap);
 
+/* ---- LSD (oracle/lsd.c) ---- */
+uint8_t* orc_lsd_scaled_image(const uint8_t* img, int w, int h, double scale, double sigma_scale, int* ow, int* oh);
+int orc_lsd_detect(const uint8_t* img, int w, int h, double scale, double sigma_scale, double quant, double ang_th,
+                   int n_bins, int order_mode, int trig_mode, float* segs, int cap);
+
 /* ---- Gauss-Newton pose refinement (oracle/gn.c) ---- */
 typedef struct orc_camera { int width, height; double fx, fy, cx, cy, b; } orc_camera;
 typedef struct orc_gn_opts {
