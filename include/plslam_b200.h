@@ -60,7 +60,7 @@ typedef struct plf_params {
   int orb_nlevels, orb_edge_th, orb_wta_k, orb_score, orb_patch_size, orb_fast_th;
   /* LSD (config_euroc.yaml:68-77) */
   int lsd_nfeatures, lsd_refine;
-  float lsd_scale, lsd_sigma_scale, lsd_quant, lsd_ang_th, lsd_log_eps, lsd_density_th;
+  double lsd_scale, lsd_sigma_scale, lsd_quant, lsd_ang_th, lsd_log_eps, lsd_density_th; /* LSDOptions: double */
   int lsd_n_bins;
 } plf_params;
 
@@ -159,6 +159,23 @@ typedef struct plf_keyline {
   float lineLength;
   int numOfPixels;
 } plf_keyline;
+
+/* Raw LSD segments.  Replaces cv::createLineSegmentDetector(lsd_refine (0), lsd_scale, lsd_sigma_scale, lsd_quant,
+ * lsd_ang_th, lsd_log_eps, lsd_density_th, lsd_n_bins)->detect(img, lines) as called at
+ * 3rdparty/line_descriptor/src/LSDDetector_custom.cpp:246-264.  segs: cap x 4 floats (x1,y1,x2,y2), OpenCV's
+ * output order (seed order).  *n receives the count. */
+plf_status plf_lsd(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* segs, int cap, int* n);
+
+/* Line features of one image.  Replaces stvo-pl StereoFrame::detectLineFeatures (LSD branch):
+ * LSDDetectorC::detect(img, lines, scale, 1, opts) (LSDDetector_custom.cpp:218-324, opts.min_length =
+ * min_line_length * min(w,h)), then — when more than lsd_nfeatures lines are found and lsd_nfeatures != 0 — sort by
+ * response (descending; ties keep detection order), keep lsd_nfeatures and set class_id = rank, then
+ * BinaryDescriptor::compute (binary_descriptor_custom.cpp:524).  keylines/desc: host buffers of `cap` entries. */
+plf_status plf_detect_lines(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride,
+                            plf_keyline* keylines, uint8_t* desc, int cap, int* n);
+
+/* Test hook: evaluates the device port of glibc sinf/cosf used by the LSD region-angle update. */
+plf_status plf_debug_sincosf(plf_ctx* ctx, const float* in, float* s, float* c, int n);
 
 /* LBD prelude: GaussianBlur 5x5 sigma 1 then Sobel k=3 to CV_16S.  Replaces
  * BinaryDescriptor::computeSobel (binary_descriptor_custom.cpp:373-398 -> :350-370).

@@ -1,0 +1,813 @@
+// LSD line segment detector, batched over images, and the LSDDetectorC KeyLine stage.
+//
+// Replaces LSDDetectorC::detect -> detectImpl (3rdparty/line_descriptor/src/LSDDetector_custom.cpp:218-324):
+//   cv::createLineSegmentDetector(refine=0, scale, sigma_scale, quant, ang_th, log_eps, density_th, n_bins)
+//   ->detect(img)  (:246-264; OpenCV imgproc lsd.cpp, not vendored by the reference — arithmetic pinned bit-exact
+//   against cv2 4.13 by oracle/lsd.c), endpoint clamp (:76-102), min-length filter (:280-281), KeyLine fill
+//   (:284-303), and stvo-pl's "sort by response, keep lsd_nfeatures" (SURVEY Appendix A.2).
+//
+// With refine = LSD_REFINE_NONE the detector is: Gaussian pre-blur (CV_8U fixed-point) + INTER_LINEAR_EXACT resample
+// -> level-line angle / gradient magnitude -> 1024-bin pseudo-ordering of the seeds (bins descending, raster order
+// inside a bin) -> greedy region growing -> rectangle fit.  No NFA validation runs at refine 0.
+//
+// Kernels
+//   k_blur_q8        separable Q8.8 Gaussian (tile in shared memory), one rounding
+//   k_resize_exact   (orb.cu) INTER_LINEAR_EXACT resample to scale
+//   k_lsd_grad       2x2 gradient -> (gx,gy) int16 pair + level-line angle (cv::fastAtan2, degrees, f32) per pixel,
+//                    per-image max of |grad|^2
+//   k_lsd_rowhist / k_lsd_binscan / k_lsd_scatter
+//                    stable counting sort of the defined pixels by magnitude bin (descending), raster order inside a
+//                    bin == OpenCV's ordered_points
+//   k_lsd_grow       region growing.  The algorithm is a sequential greedy partition (each accepted pixel updates the
+//                    region angle that the next test uses, and regions compete through the `used` map), so it is run by
+//                    ONE WARP PER IMAGE with many images in flight: lanes 0..8 fetch the 3x3 neighbourhood of the
+//                    current region point in one memory round trip, the 9 alignment tests are then replayed in the
+//                    reference order; the seed scan looks 32 seeds ahead per round trip.  `used` is folded into the
+//                    angle map (a used pixel gets the NOTDEF sentinel; both are rejected identically).
+//   k_lsd_rects      one thread per region: weighted centroid, inertia-matrix angle, extent — sequential fp64 sums in
+//                    region order (bit-exact with the CPU loop)
+//   k_keylines       clamp + length filter + KeyLine fill with ordered compaction, optional top-K by response
+// Roofline: gradient / ordering / blur stream each map once (HBM-bound when batched); region growing is
+// latency-bound by construction and is reported as time, not as a roofline fraction.
+#include <float.h>
+
+#include "glibc_sincosf.cuh"
+#include "plf_internal.h"
+
+#define LSD_NOTDEF (-1024.0f)
+#define LSD_PI 3.1415926535897932384626433832795
+#define LSD_3_2_PI ((3 * LSD_PI) / 2)
+#define LSD_2PI (2 * LSD_PI)
+#define LSD_DEG2RAD (LSD_PI / 180)
+#define LSD_BINS_MAX 1024
+#define LSD_QCAP 1024  // shared-memory window of the region queue (entries)
+
+struct LsdState {
+  int w = 0, h = 0, nimg = 0;
+  int ws = 0, hs = 0;       // scaled size
+  int ksize = 0;
+  int taps[16];
+  int n_bins = 1024;
+  double scale = 1.2, prec = 0, p = 0, rho = 0;
+  int min_reg_size = 0;
+  int max_regions = 0, max_lines = 0;
+  uint8_t* blur = nullptr;    // [nimg][h*w]
+  uint8_t* scaled = nullptr;  // [nimg][hs*ws]
+  short2* gxy = nullptr;      // [nimg][hs*ws]
+  float* adeg = nullptr;      // [nimg][hs*ws]  level-line angle in degrees, LSD_NOTDEF = undefined or used
+  uint16_t* binmap = nullptr; // [nimg][hs*ws]
+  int* maxmag2 = nullptr;     // [nimg]
+  uint32_t* rowcnt = nullptr; // [nimg][hs][n_bins]
+  uint32_t* binstart = nullptr; // [nimg][n_bins]
+  int* nseeds = nullptr;      // [nimg]
+  uint32_t* order = nullptr;  // [nimg][hs*ws]
+  uint32_t* regpts = nullptr; // [nimg][hs*ws]
+  uint4* regions = nullptr;   // [nimg][max_regions] {start, count, angle_lo, angle_hi}
+  int* nregions = nullptr;    // [nimg]
+  float4* segs = nullptr;     // [nimg][max_regions]
+  plf_keyline* kls = nullptr; // [nimg][max_lines]  final KeyLines (after top-K)
+  plf_keyline* kls_all = nullptr; // [nimg][max_regions] before top-K
+  int* nlines = nullptr;      // [nimg]
+  int* overflow = nullptr;    // [1]
+  int* rs_tab = nullptr;      // resize tables
+  size_t rs_x_off = 0, rs_y_off = 0;
+};
+
+__constant__ int c_lsd_taps[16];
+
+__device__ __forceinline__ int lsd_reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) {
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+  }
+  return i;
+}
+
+// ---- fixed-point Gaussian (ksize <= 15) ------------------------------------------------------------------
+#define BQ_TW 64
+#define BQ_TH 16
+#define BQ_R 7
+__global__ void __launch_bounds__(256) k_blur_q8(const uint8_t* __restrict__ src, size_t src_stride, int pitch,
+                                                 int w, int h, int r, uint8_t* __restrict__ dst, size_t dst_stride) {
+  __shared__ uint8_t raw[BQ_TH + 2 * BQ_R][BQ_TW + 2 * BQ_R + 2];
+  __shared__ uint16_t hrow[BQ_TH + 2 * BQ_R][BQ_TW];
+  const uint8_t* s = src + (size_t)blockIdx.z * src_stride;
+  uint8_t* d = dst + (size_t)blockIdx.z * dst_stride;
+  const int x0 = blockIdx.x * BQ_TW, y0 = blockIdx.y * BQ_TH, tid = threadIdx.x;
+  const int RW = BQ_TW + 2 * r, RH = BQ_TH + 2 * r;
+  for (int i = tid; i < RH * RW; i += 256) {
+    const int ry = i / RW, rx = i - ry * RW;
+    raw[ry][rx] = s[(size_t)lsd_reflect101(y0 - r + ry, h) * pitch + lsd_reflect101(x0 - r + rx, w)];
+  }
+  __syncthreads();
+  const int ks = 2 * r + 1;
+  for (int i = tid; i < RH * BQ_TW; i += 256) {
+    const int ry = i / BQ_TW, tx = i - ry * BQ_TW;
+    uint32_t a = 0;
+    for (int k = 0; k < ks; ++k) a += (uint32_t)c_lsd_taps[k] * raw[ry][tx + k];
+    hrow[ry][tx] = (uint16_t)a;
+  }
+  __syncthreads();
+  for (int i = tid; i < BQ_TH * BQ_TW; i += 256) {
+    const int ty = i / BQ_TW, tx = i - ty * BQ_TW;
+    const int gx = x0 + tx, gy = y0 + ty;
+    if (gx >= w || gy >= h) continue;
+    uint32_t a = 0;
+    for (int k = 0; k < ks; ++k) a += (uint32_t)c_lsd_taps[k] * hrow[ty + k][tx];
+    const uint32_t v = (a + (1u << 15)) >> 16;
+    d[(size_t)gy * w + gx] = (uint8_t)(v > 255 ? 255 : v);
+  }
+}
+
+// ---- gradient ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float lsd_fast_atan2(float y, float x) {  // cv::fastAtan2, see orb.cu
+  const float p1 = 0.9997878412794807f * (float)(180 / 3.14159265358979323846);
+  const float p3 = -0.3258083974640975f * (float)(180 / 3.14159265358979323846);
+  const float p5 = 0.1555786518463281f * (float)(180 / 3.14159265358979323846);
+  const float p7 = -0.04432655554792128f * (float)(180 / 3.14159265358979323846);
+  const float ax = fabsf(x), ay = fabsf(y);
+  float a, c, c2;
+  if (ax >= ay) {
+    c = __fdiv_rn(ay, __fadd_rn(ax, (float)2.2204460492503131e-16));
+    c2 = __fmul_rn(c, c);
+    a = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c);
+  } else {
+    c = __fdiv_rn(ax, __fadd_rn(ay, (float)2.2204460492503131e-16));
+    c2 = __fmul_rn(c, c);
+    a = __fsub_rn(90.f, __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(p7, c2), p5), c2), p3), c2), p1), c));
+  }
+  if (x < 0) a = __fsub_rn(180.f, a);
+  if (y < 0) a = __fsub_rn(360.f, a);
+  return a;
+}
+
+__global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int W, int H,
+                                                  double rho, size_t stride, short2* __restrict__ gxy,
+                                                  float* __restrict__ adeg, int* __restrict__ maxmag2) {
+  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, im = blockIdx.z;
+  int mag2 = -1;
+  if (x < W) {
+    const size_t o = (size_t)im * stride + (size_t)y * W + x;
+    short2 g = make_short2(0, 0);
+    float a = LSD_NOTDEF;
+    if (x < W - 1 && y < H - 1) {
+      const uint8_t* r0 = img + (size_t)im * img_stride + (size_t)y * W + x;
+      const uint8_t* r1 = r0 + W;
+      const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
+      const int gx = DA + BC, gy = DA - BC;
+      g = make_short2((short)gx, (short)gy);
+      const int m2 = gx * gx + gy * gy;
+      const double norm = sqrt((double)m2 / 4.0);
+      if (!(norm <= rho)) {
+        a = lsd_fast_atan2((float)gx, (float)(-gy));
+        mag2 = m2;
+      }
+    }
+    gxy[o] = g;
+    adeg[o] = a;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mag2 = max(mag2, __shfl_xor_sync(0xFFFFFFFFu, mag2, off));
+  if ((threadIdx.x & 31) == 0 && mag2 >= 0) atomicMax(&maxmag2[im], mag2);
+}
+
+// ---- pseudo-ordering (stable counting sort, bins descending) ---------------------------------------------------
+__device__ __forceinline__ double lsd_bin_coef(int maxmag2, int n_bins) {
+  if (maxmag2 < 0) return 0.0;
+  const double max_grad = sqrt((double)maxmag2 / 4.0);
+  return max_grad > 0 ? (double)(n_bins - 1) / max_grad : 0.0;
+}
+
+__global__ void __launch_bounds__(256) k_lsd_rowhist(const short2* __restrict__ gxy, const float* __restrict__ adeg,
+                                                     size_t stride, int W, int H, int n_bins,
+                                                     const int* __restrict__ maxmag2, uint16_t* __restrict__ binmap,
+                                                     uint32_t* __restrict__ rowcnt) {
+  __shared__ uint32_t hist[LSD_BINS_MAX];
+  const int y = blockIdx.x, im = blockIdx.y;
+  for (int i = threadIdx.x; i < n_bins; i += 256) hist[i] = 0;
+  __syncthreads();
+  const double coef = lsd_bin_coef(maxmag2[im], n_bins);
+  const size_t o = (size_t)im * stride + (size_t)y * W;
+  for (int x = threadIdx.x; x < W - 1; x += 256) {
+    if (adeg[o + x] == LSD_NOTDEF) continue;
+    const short2 g = gxy[o + x];
+    const double norm = sqrt((double)(g.x * g.x + g.y * g.y) / 4.0);
+    const int b = (int)(norm * coef);
+    binmap[o + x] = (uint16_t)b;
+    atomicAdd(&hist[b], 1u);
+  }
+  __syncthreads();
+  uint32_t* out = rowcnt + ((size_t)im * H + y) * n_bins;
+  for (int i = threadIdx.x; i < n_bins; i += 256) out[i] = hist[i];
+}
+
+// one block (n_bins threads, <= 1024) per image: per-bin prefix over rows, then start of each bin (bins descending)
+__global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ rowcnt, int H, int n_bins,
+                                                      uint32_t* __restrict__ binstart, int* __restrict__ nseeds) {
+  __shared__ uint32_t tot[LSD_BINS_MAX];
+  const int im = blockIdx.x, b = threadIdx.x;
+  uint32_t run = 0;
+  if (b < n_bins) {
+    uint32_t* c = rowcnt + (size_t)im * H * n_bins + b;
+    for (int y = 0; y < H - 1; ++y) {
+      const uint32_t v = c[(size_t)y * n_bins];
+      c[(size_t)y * n_bins] = run;
+      run += v;
+    }
+    tot[b] = run;
+  }
+  __syncthreads();
+  if (b == 0) {  // 1024-element serial scan: ~1 us, once per image
+    uint32_t acc = 0;
+    for (int k = n_bins - 1; k >= 0; --k) {
+      const uint32_t t = tot[k];
+      binstart[(size_t)im * n_bins + k] = acc;
+      acc += t;
+    }
+    nseeds[im] = (int)acc;
+  }
+}
+
+// one warp per (row, image): stable ranks inside the row via match_any, raster order preserved
+__global__ void __launch_bounds__(128) k_lsd_scatter(const float* __restrict__ adeg, const uint16_t* __restrict__ binmap,
+                                                     size_t stride, int W, int H, int n_bins,
+                                                     const uint32_t* __restrict__ rowcnt,
+                                                     const uint32_t* __restrict__ binstart,
+                                                     uint32_t* __restrict__ order) {
+  __shared__ uint32_t cnt[4][LSD_BINS_MAX];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int y = blockIdx.x * 4 + wid, im = blockIdx.y;
+  if (y >= H - 1) return;
+  uint32_t* c = cnt[wid];
+  const uint32_t* rc = rowcnt + ((size_t)im * H + y) * n_bins;
+  const uint32_t* bs = binstart + (size_t)im * n_bins;
+  for (int i = lane; i < n_bins; i += 32) c[i] = rc[i] + bs[i];
+  __syncwarp();
+  const size_t o = (size_t)im * stride + (size_t)y * W;
+  uint32_t* ord = order + (size_t)im * stride;
+  for (int x0 = 0; x0 < W - 1; x0 += 32) {
+    const int x = x0 + lane;
+    const bool valid = x < W - 1 && adeg[o + x] != LSD_NOTDEF;
+    const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
+    if (valid) {
+      const int b = binmap[o + x];
+      const unsigned peers = __match_any_sync(vm, b);
+      const int rank = __popc(peers & ((1u << lane) - 1));
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (lane == leader) {
+        base = c[b];
+        c[b] = base + __popc(peers);
+      }
+      base = __shfl_sync(peers, base, leader);
+      ord[base + rank] = (uint32_t)(y * W + x);
+    }
+    __syncwarp();
+  }
+}
+
+// ---- region growing ----------------------------------------------------------------------------------------
+__device__ __forceinline__ bool lsd_aligned(float a_deg, double theta, double prec) {
+  if (a_deg == LSD_NOTDEF) return false;
+  const double a = (double)a_deg * LSD_DEG2RAD;
+  double n_theta = theta - a;
+  if (n_theta < 0) n_theta = -n_theta;
+  if (n_theta > LSD_3_2_PI) {
+    n_theta -= LSD_2PI;
+    if (n_theta < 0) n_theta = -n_theta;
+  }
+  return n_theta <= prec;
+}
+
+__global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, size_t stride, int W, int H,
+                                                 const uint32_t* __restrict__ order_all,
+                                                 const int* __restrict__ nseeds, double prec, int min_reg_size,
+                                                 uint32_t* __restrict__ regpts_all, uint4* __restrict__ regions_all,
+                                                 int max_regions, int* __restrict__ nregions,
+                                                 int* __restrict__ overflow) {
+  __shared__ uint32_t q[LSD_QCAP];
+  const int im = blockIdx.x, lane = threadIdx.x;
+  float* adeg = adeg_all + (size_t)im * stride;
+  const uint32_t* order = order_all + (size_t)im * stride;
+  uint32_t* regpts = regpts_all + (size_t)im * stride;
+  uint4* regions = regions_all + (size_t)im * max_regions;
+  const int ns = nseeds[im];
+  uint32_t cursor = 0;  // write position in regpts (kept regions only)
+  int nreg_out = 0;
+  for (int s0 = 0; s0 < ns; s0 += 32) {
+    const int si = s0 + lane;
+    const uint32_t seed = si < ns ? order[si] : 0u;
+    float a0 = si < ns ? __ldcg(&adeg[seed]) : LSD_NOTDEF;
+    unsigned pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF);
+    while (pending) {
+      const int src = __ffs(pending) - 1;
+      const uint32_t sidx = __shfl_sync(0xFFFFFFFFu, seed, src);
+      const float sdeg = __shfl_sync(0xFFFFFFFFu, a0, src);
+      // ---- region_grow from this seed ----
+      const int sx = sidx % W, sy = sidx / W;
+      double reg_angle = (double)sdeg * LSD_DEG2RAD;
+      float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+      if (lane == 0) {
+        adeg[sidx] = LSD_NOTDEF;
+        regpts[cursor] = ((uint32_t)sy << 16) | (uint32_t)sx;
+        q[0] = ((uint32_t)sy << 16) | (uint32_t)sx;
+      }
+      __syncwarp();
+      uint32_t nreg = 1;
+      for (uint32_t r = 0; r < nreg; ++r) {
+        // queue entry r: from the shared window when it still holds it, else from global
+        uint32_t pt;
+        if (nreg - r <= LSD_QCAP)  // entries r..nreg-1 all live in the ring
+          pt = q[r % LSD_QCAP];
+        else
+          pt = __ldcg(&regpts[cursor + r]);
+        const int px = pt & 0xFFFF, py = pt >> 16;
+        // lanes 0..8 fetch the 3x3 neighbourhood (row-major: yy outer, xx inner — the reference order)
+        float a = LSD_NOTDEF;
+        int nx = 0, ny = 0;
+        if (lane < 9) {
+          ny = py - 1 + lane / 3;
+          nx = px - 1 + lane % 3;
+          if (nx >= 0 && ny >= 0 && nx < W && ny < H) a = __ldcg(&adeg[(size_t)ny * W + nx]);
+        }
+        unsigned cand = __ballot_sync(0xFFFFFFFFu, a != LSD_NOTDEF) & 0x1FFu;
+        while (cand) {
+          const int k = __ffs(cand) - 1;
+          cand &= cand - 1;
+          const float ak = __shfl_sync(0xFFFFFFFFu, a, k);
+          if (!lsd_aligned(ak, reg_angle, prec)) continue;
+          const int ax = px - 1 + k % 3, ay = py - 1 + k / 3;
+          const uint32_t packed = ((uint32_t)ay << 16) | (uint32_t)ax;
+          if (lane == 0) {
+            adeg[(size_t)ay * W + ax] = LSD_NOTDEF;
+            regpts[cursor + nreg] = packed;
+            q[nreg % LSD_QCAP] = packed;
+          }
+          ++nreg;
+          const float af = (float)((double)ak * LSD_DEG2RAD);
+          sumdx = __fadd_rn(sumdx, glibc_cosf(af));
+          sumdy = __fadd_rn(sumdy, glibc_sinf(af));
+          reg_angle = (double)lsd_fast_atan2(sumdy, sumdx) * LSD_DEG2RAD;
+        }
+        __syncwarp();
+      }
+      if ((int)nreg >= min_reg_size) {
+        if (nreg_out < max_regions) {
+          if (lane == 0) {
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(reg_angle);
+            regions[nreg_out] = make_uint4(cursor, nreg, (uint32_t)bits, (uint32_t)(bits >> 32));
+          }
+          ++nreg_out;
+          cursor += nreg;
+        } else if (lane == 0) {
+          *overflow = 1;
+        }
+      }
+      // re-validate the rest of this batch of seeds (the region may have consumed some of them)
+      pending &= ~((2u << src) - 1u);
+      if (pending) {
+        a0 = (pending >> lane) & 1u ? __ldcg(&adeg[seed]) : LSD_NOTDEF;
+        pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF);
+      }
+    }
+  }
+  if (lane == 0) nregions[im] = nreg_out;
+}
+
+// ---- rectangle fit -------------------------------------------------------------------------------------------
+__device__ __forceinline__ double lsd_angle_diff(double a, double b) {
+  double diff = a - b;
+  while (diff <= -LSD_PI) diff += LSD_2PI;
+  while (diff > LSD_PI) diff -= LSD_2PI;
+  if (diff < 0.0) diff = -diff;
+  return diff;
+}
+
+__global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gxy_all, size_t stride, int W,
+                                                   const uint32_t* __restrict__ regpts_all,
+                                                   const uint4* __restrict__ regions_all, int max_regions,
+                                                   const int* __restrict__ nregions, double prec, double scale,
+                                                   float4* __restrict__ segs_all) {
+  const int im = blockIdx.y, ri = blockIdx.x * 128 + threadIdx.x;
+  if (ri >= nregions[im]) return;
+  const uint4 R = regions_all[(size_t)im * max_regions + ri];
+  const uint32_t* pts = regpts_all + (size_t)im * stride + R.x;
+  const short2* gxy = gxy_all + (size_t)im * stride;
+  const int n = (int)R.y;
+  const double reg_angle = __longlong_as_double((long long)(((unsigned long long)R.w << 32) | R.z));
+  double x = 0, y = 0, sum = 0;
+  for (int k = 0; k < n; ++k) {
+    const uint32_t p = pts[k];
+    const int px = p & 0xFFFF, py = p >> 16;
+    const short2 g = gxy[(size_t)py * W + px];
+    const double wgt = sqrt((double)(g.x * g.x + g.y * g.y) / 4.0);
+    x += (double)px * wgt;
+    y += (double)py * wgt;
+    sum += wgt;
+  }
+  x /= sum;
+  y /= sum;
+  double Ixx = 0, Iyy = 0, Ixy = 0;
+  for (int k = 0; k < n; ++k) {
+    const uint32_t p = pts[k];
+    const int px = p & 0xFFFF, py = p >> 16;
+    const short2 g = gxy[(size_t)py * W + px];
+    const double wgt = sqrt((double)(g.x * g.x + g.y * g.y) / 4.0);
+    const double dx = (double)px - x, dy = (double)py - y;
+    Ixx += dy * dy * wgt;
+    Iyy += dx * dx * wgt;
+    Ixy -= dx * dy * wgt;
+  }
+  const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
+  double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)lsd_fast_atan2((float)(lambda - Ixx), (float)Ixy)
+                                         : (double)lsd_fast_atan2((float)Ixy, (float)(lambda - Iyy));
+  theta *= LSD_DEG2RAD;
+  if (lsd_angle_diff(theta, reg_angle) > prec) theta += LSD_PI;
+  const double dx = cos(theta), dy = sin(theta);
+  double l_min = 0, l_max = 0;
+  for (int k = 0; k < n; ++k) {
+    const uint32_t p = pts[k];
+    const double regdx = (double)(p & 0xFFFF) - x, regdy = (double)(p >> 16) - y;
+    const double l = regdx * dx + regdy * dy;
+    if (l > l_max) l_max = l;
+    else if (l < l_min) l_min = l;
+  }
+  double x1 = x + l_min * dx, y1 = y + l_min * dy, x2 = x + l_max * dx, y2 = y + l_max * dy;
+  x1 += 0.5; y1 += 0.5; x2 += 0.5; y2 += 0.5;
+  if (scale != 1) { x1 /= scale; y1 /= scale; x2 /= scale; y2 /= scale; }
+  segs_all[(size_t)im * max_regions + ri] = make_float4((float)x1, (float)y1, (float)x2, (float)y2);
+}
+
+// ---- KeyLines (LSDDetector_custom.cpp:267-308) + stvo-pl top-K ---------------------------------------------------
+#define KL_SORT_CAP 4096
+__global__ void __launch_bounds__(1024) k_keylines(const float4* __restrict__ segs_all, const int* __restrict__ nsegs,
+                                                   int max_regions, int w, int h, double min_length, int nfeatures,
+                                                   plf_keyline* __restrict__ kls_all, plf_keyline* __restrict__ kls_out,
+                                                   int max_lines, int* __restrict__ nlines, int* __restrict__ overflow) {
+  __shared__ unsigned long long keys[KL_SORT_CAP];  // (response desc, index asc) for the top-K
+  __shared__ int s_scan[1024];
+  __shared__ int s_total;
+  const int im = blockIdx.x, tid = threadIdx.x;
+  const int n = min(nsegs[im], max_regions);
+  const float4* segs = segs_all + (size_t)im * max_regions;
+  plf_keyline* all = kls_all + (size_t)im * max_regions;
+  plf_keyline* out = kls_out + (size_t)im * max_lines;
+  // pass 1: accept flags + ordered compaction (class_id = running counter of accepted lines, :299)
+  int base = 0;
+  for (int c0 = 0; c0 < n; c0 += 1024) {
+    const int i = c0 + tid;
+    bool ok = false;
+    plf_keyline kl;
+    if (i < n) {
+      float4 e = segs[i];
+      if (e.x < 0) e.x = 0;
+      if (e.x >= w) e.x = (float)w - 1.0f;
+      if (e.z < 0) e.z = 0;
+      if (e.z >= w) e.z = (float)w - 1.0f;
+      if (e.y < 0) e.y = 0;
+      if (e.y >= h) e.y = (float)h - 1.0f;
+      if (e.w < 0) e.w = 0;
+      if (e.w >= h) e.w = (float)h - 1.0f;
+      const double ddx = (double)__fsub_rn(e.x, e.z), ddy = (double)__fsub_rn(e.y, e.w);
+      const double length = (double)(float)sqrt(ddx * ddx + ddy * ddy);
+      ok = length > min_length;
+      if (ok) {
+        kl.startPointX = e.x; kl.startPointY = e.y; kl.endPointX = e.z; kl.endPointY = e.w;  // octaveScale = 1
+        kl.sPointInOctaveX = e.x; kl.sPointInOctaveY = e.y; kl.ePointInOctaveX = e.z; kl.ePointInOctaveY = e.w;
+        kl.lineLength = (float)length;
+        const int x1 = __float2int_rn(e.x), y1 = __float2int_rn(e.y), x2 = __float2int_rn(e.z), y2 = __float2int_rn(e.w);
+        kl.numOfPixels = max(abs(x2 - x1), abs(y2 - y1)) + 1;  // LineIterator(8-connected).count
+        kl.angle = (float)atan2((double)__fsub_rn(kl.endPointY, kl.startPointY), (double)__fsub_rn(kl.endPointX, kl.startPointX));
+        kl.octave = 0;
+        kl.size = __fmul_rn(__fsub_rn(kl.endPointX, kl.startPointX), __fsub_rn(kl.endPointY, kl.startPointY));
+        kl.response = __fdiv_rn(kl.lineLength, (float)max(w, h));
+        kl.ptx = __fdiv_rn(__fadd_rn(kl.endPointX, kl.startPointX), 2.f);
+        kl.pty = __fdiv_rn(__fadd_rn(kl.endPointY, kl.startPointY), 2.f);
+      }
+    }
+    // block exclusive scan of ok flags
+    s_scan[tid] = ok ? 1 : 0;
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {
+      const int v = tid >= off ? s_scan[tid - off] : 0;
+      __syncthreads();
+      s_scan[tid] += v;
+      __syncthreads();
+    }
+    const int incl = s_scan[tid];
+    if (tid == 1023) s_total = incl;
+    if (ok) {
+      kl.class_id = base + incl - 1;
+      all[base + incl - 1] = kl;
+    }
+    __syncthreads();
+    base += s_total;
+    __syncthreads();
+  }
+  const int m = base;
+  int keep = m;
+  if (nfeatures != 0 && m > nfeatures) {
+    // stvo-pl: sort by response (descending), keep nfeatures, class_id = rank.  Ties: detection order.
+    if (m > KL_SORT_CAP) {
+      if (tid == 0) *overflow = 1;
+    }
+    const int mm = min(m, KL_SORT_CAP);
+    int p2 = 1;
+    while (p2 < mm) p2 <<= 1;
+    for (int i = tid; i < p2; i += 1024) {
+      if (i < mm) {
+        const uint32_t rb = __float_as_uint(all[i].response);  // responses are positive floats: bit order == value order
+        keys[i] = ((unsigned long long)(~rb) << 32) | (uint32_t)i;
+      } else {
+        keys[i] = ~0ull;
+      }
+    }
+    __syncthreads();
+    for (int k = 2; k <= p2; k <<= 1)
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        for (int i = tid; i < p2; i += 1024) {
+          const int ixj = i ^ j;
+          if (ixj > i) {
+            const unsigned long long a = keys[i], b = keys[ixj];
+            const bool up = (i & k) == 0;
+            if ((a > b) == up) {
+              keys[i] = b;
+              keys[ixj] = a;
+            }
+          }
+        }
+        __syncthreads();
+      }
+    keep = nfeatures;
+    if (keep > max_lines) {
+      if (tid == 0) *overflow = 1;
+      keep = max_lines;
+    }
+    for (int i = tid; i < keep; i += 1024) {
+      plf_keyline kl = all[(uint32_t)(keys[i] & 0xFFFFFFFFu)];
+      kl.class_id = i;
+      out[i] = kl;
+    }
+  } else {
+    if (keep > max_lines) {
+      if (tid == 0) *overflow = 1;
+      keep = max_lines;
+    }
+    for (int i = tid; i < keep; i += 1024) out[i] = all[i];
+  }
+  if (tid == 0) nlines[im] = keep;
+}
+
+// ---- host side -------------------------------------------------------------------------------------------------
+static void lsd_release(LsdState* s) {
+  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->gxy); cudaFree(s->adeg); cudaFree(s->binmap);
+  cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->nseeds); cudaFree(s->order);
+  cudaFree(s->regpts); cudaFree(s->regions); cudaFree(s->nregions); cudaFree(s->segs); cudaFree(s->kls);
+  cudaFree(s->kls_all); cudaFree(s->nlines); cudaFree(s->overflow); cudaFree(s->rs_tab);
+}
+
+extern "C" void plf_lsd_free(plf_ctx* ctx) {
+  if (ctx->lsd) {
+    lsd_release(ctx->lsd);
+    delete ctx->lsd;
+    ctx->lsd = nullptr;
+  }
+}
+
+// getGaussianKernelBitExact + fixed-point error diffusion (see oracle/lbd.c orc_gaussian_kernel_q8)
+static void gaussian_taps_q8(int ksize, double sigma, int* taps) {
+  double k[33], sum = 0;
+  const double scale2x = -0.5 / (sigma * sigma);
+  for (int i = 0; i < ksize; i++) {
+    const double x = i - (ksize - 1) * 0.5;
+    k[i] = exp(scale2x * x * x);
+    sum += k[i];
+  }
+  sum = 1. / sum;
+  double err = 0;
+  int s = 0;
+  for (int i = 0; i < ksize / 2; i++) {
+    const double adj = k[i] * sum * 256.0 + err;
+    const int v0 = (int)nearbyint(adj);
+    err = adj - v0;
+    taps[i] = taps[ksize - 1 - i] = v0;
+    s += v0;
+  }
+  taps[ksize / 2] = 256 - 2 * s;
+}
+
+plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg) {
+  LsdState* s = ctx->lsd;
+  if (s && s->w == w && s->h == h && s->nimg >= nimg) return PLF_OK;
+  if (s) {
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    lsd_release(s);
+    *s = LsdState();
+  } else {
+    s = ctx->lsd = new LsdState();
+  }
+  const plf_params& P = ctx->params;
+  if (P.lsd_refine != 0)
+    return plf_fail(ctx, PLF_ERR_INVALID, "LSD: only lsd_refine = 0 (LSD_REFINE_NONE, the reference configs) is supported");
+  if (P.lsd_n_bins < 1 || P.lsd_n_bins > LSD_BINS_MAX)
+    return plf_fail(ctx, PLF_ERR_INVALID, "LSD: lsd_n_bins must be in [1,%d]", LSD_BINS_MAX);
+  s->w = w; s->h = h; s->nimg = nimg;
+  s->scale = P.lsd_scale;
+  s->n_bins = P.lsd_n_bins;
+  s->prec = LSD_PI * P.lsd_ang_th / 180;
+  s->p = P.lsd_ang_th / 180;
+  s->rho = P.lsd_quant / sin(s->prec);
+  if (s->scale != 1.0) {
+    const double sigma = (s->scale < 1) ? (P.lsd_sigma_scale / s->scale) : P.lsd_sigma_scale;
+    const unsigned hk = (unsigned)(ceil(sigma * sqrt(2 * 3.0 * log(10.0))));
+    s->ksize = 1 + 2 * (int)hk;
+    if (s->ksize > 15) return plf_fail(ctx, PLF_ERR_INVALID, "LSD: Gaussian kernel %d > 15 unsupported", s->ksize);
+    gaussian_taps_q8(s->ksize, sigma, s->taps);
+    s->ws = (int)nearbyint(w * s->scale);
+    s->hs = (int)nearbyint(h * s->scale);
+  } else {
+    s->ksize = 0;
+    s->ws = w;
+    s->hs = h;
+  }
+  if (s->ws >= 65536 || s->hs >= 65536 || s->ws < 3 || s->hs < 3)
+    return plf_fail(ctx, PLF_ERR_INVALID, "LSD: scaled image %dx%d out of range", s->ws, s->hs);
+  const double LOG_NT = 5 * (log10((double)s->ws) + log10((double)s->hs)) / 2 + log10(11.0);
+  s->min_reg_size = (int)(size_t)(-LOG_NT / log10(s->p));
+  s->max_regions = ctx->limits.max_segments;
+  s->max_lines = ctx->limits.max_lines;
+  const size_t N = (size_t)nimg, A = (size_t)w * h, As = (size_t)s->ws * s->hs;
+  PLF_CUDA(ctx, cudaMalloc(&s->blur, A * N));
+  PLF_CUDA(ctx, cudaMalloc(&s->scaled, As * N));
+  PLF_CUDA(ctx, cudaMalloc(&s->gxy, As * N * sizeof(short2)));
+  PLF_CUDA(ctx, cudaMalloc(&s->adeg, As * N * sizeof(float)));
+  PLF_CUDA(ctx, cudaMalloc(&s->binmap, As * N * sizeof(uint16_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->maxmag2, N * sizeof(int)));
+  PLF_CUDA(ctx, cudaMalloc(&s->rowcnt, N * s->hs * s->n_bins * sizeof(uint32_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->binstart, N * s->n_bins * sizeof(uint32_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->nseeds, N * sizeof(int)));
+  PLF_CUDA(ctx, cudaMalloc(&s->order, As * N * sizeof(uint32_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->regpts, As * N * sizeof(uint32_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->regions, N * s->max_regions * sizeof(uint4)));
+  PLF_CUDA(ctx, cudaMalloc(&s->nregions, N * sizeof(int)));
+  PLF_CUDA(ctx, cudaMalloc(&s->segs, N * s->max_regions * sizeof(float4)));
+  PLF_CUDA(ctx, cudaMalloc(&s->kls, N * s->max_lines * sizeof(plf_keyline)));
+  PLF_CUDA(ctx, cudaMalloc(&s->kls_all, N * s->max_regions * sizeof(plf_keyline)));
+  PLF_CUDA(ctx, cudaMalloc(&s->nlines, N * sizeof(int)));
+  PLF_CUDA(ctx, cudaMalloc(&s->overflow, sizeof(int)));
+  PLF_CUDA(ctx, cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream));
+  if (s->scale != 1.0) {
+    std::vector<int> tab(2 * (size_t)s->ws + 2 * (size_t)s->hs);
+    s->rs_x_off = 0;
+    s->rs_y_off = 2 * (size_t)s->ws;
+    plf_linear_coeffs_host(w, s->ws, 1.0 / s->scale, &tab[0], &tab[s->ws]);
+    plf_linear_coeffs_host(h, s->hs, 1.0 / s->scale, &tab[s->rs_y_off], &tab[s->rs_y_off + s->hs]);
+    PLF_CUDA(ctx, cudaMalloc(&s->rs_tab, tab.size() * sizeof(int)));
+    PLF_CUDA(ctx, cudaMemcpyAsync(s->rs_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return PLF_OK;
+}
+
+// LSD + KeyLines on nimg images resident on the device.  Results stay on the device (LsdState).
+plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg) {
+  plf_status st = plf_lsd_prepare(ctx, w, h, nimg);
+  if (st) return st;
+  LsdState* s = ctx->lsd;
+  cudaStream_t cs = ctx->stream;
+  const int W = s->ws, H = s->hs;
+  const size_t As = (size_t)W * H;
+  const uint8_t* scaled = d_imgs;
+  size_t scaled_stride = img_stride;
+  if (s->scale != 1.0) {
+    PLF_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lsd_taps, s->taps, sizeof(int) * 16, 0, cudaMemcpyHostToDevice, cs));
+    dim3 gb((w + BQ_TW - 1) / BQ_TW, (h + BQ_TH - 1) / BQ_TH, nimg);
+    k_blur_q8<<<gb, 256, 0, cs>>>(d_imgs, img_stride, w, w, h, s->ksize / 2, s->blur, (size_t)w * h);
+    PLF_LAUNCH_CHECK(ctx);
+    st = plf_launch_resize_exact(ctx, s->blur, (size_t)w * h, w, h, s->scaled, As, W, H, s->rs_tab + s->rs_x_off,
+                                 s->rs_tab + s->rs_y_off, nimg);
+    if (st) return st;
+    scaled = s->scaled;
+    scaled_stride = As;
+  }
+  PLF_CUDA(ctx, cudaMemsetAsync(s->maxmag2, 0xFF, (size_t)nimg * sizeof(int), cs));  // -1
+  k_lsd_grad<<<dim3((W + 255) / 256, H, nimg), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->rho, As, s->gxy, s->adeg, s->maxmag2);
+  PLF_LAUNCH_CHECK(ctx);
+  // gxy/adeg/binmap/order/regpts are laid out with stride As per image
+  k_lsd_rowhist<<<dim3(H - 1, nimg), 256, 0, cs>>>(s->gxy, s->adeg, As, W, H, s->n_bins, s->maxmag2, s->binmap, s->rowcnt);
+  PLF_LAUNCH_CHECK(ctx);
+  k_lsd_binscan<<<nimg, 1024, 0, cs>>>(s->rowcnt, H, s->n_bins, s->binstart, s->nseeds);
+  PLF_LAUNCH_CHECK(ctx);
+  k_lsd_scatter<<<dim3((H - 1 + 3) / 4, nimg), 128, 0, cs>>>(s->adeg, s->binmap, As, W, H, s->n_bins, s->rowcnt, s->binstart, s->order);
+  PLF_LAUNCH_CHECK(ctx);
+  k_lsd_grow<<<nimg, 32, 0, cs>>>(s->adeg, As, W, H, s->order, s->nseeds, s->prec, s->min_reg_size, s->regpts,
+                                  s->regions, s->max_regions, s->nregions, s->overflow);
+  PLF_LAUNCH_CHECK(ctx);
+  k_lsd_rects<<<dim3((s->max_regions + 127) / 128, nimg), 128, 0, cs>>>(s->gxy, As, W, s->regpts, s->regions, s->max_regions,
+                                                                        s->nregions, s->prec, s->scale, s->segs);
+  PLF_LAUNCH_CHECK(ctx);
+  const double min_length = (double)ctx->params.min_line_length * (double)std::min(w, h);
+  k_keylines<<<nimg, 1024, 0, cs>>>(s->segs, s->nregions, s->max_regions, w, h, min_length, ctx->params.lsd_nfeatures,
+                                    s->kls_all, s->kls, s->max_lines, s->nlines, s->overflow);
+  PLF_LAUNCH_CHECK(ctx);
+  return PLF_OK;
+}
+
+void plf_lsd_outputs(plf_ctx* ctx, plf_keyline** kls, int** nlines, int* max_lines) {
+  LsdState* s = ctx->lsd;
+  *kls = s->kls; *nlines = s->nlines; *max_lines = s->max_lines;
+}
+
+static plf_status lsd_check_overflow(plf_ctx* ctx, const char* what) {
+  LsdState* s = ctx->lsd;
+  int ovf = 0;
+  PLF_CUDA(ctx, cudaMemcpyAsync(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ovf) {
+    cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream);
+    return plf_fail(ctx, PLF_ERR_CAPACITY, "%s: segment/line capacity exceeded (max_segments=%d, max_lines=%d)", what,
+                    s->max_regions, s->max_lines);
+  }
+  return PLF_OK;
+}
+
+extern "C" plf_status plf_lsd(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride, float* segs, int cap,
+                              int* n_out) {
+  if (!ctx || !img || !n_out || w < 3 || h < 3 || stride < w || cap < 0 || (cap > 0 && !segs))
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_lsd: bad arguments");
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  uint8_t* dimg = (uint8_t*)plf_scratch(ctx, 4, (size_t)w * h);
+  if (!dimg) return PLF_ERR_CUDA;
+  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, w, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  plf_status st = plf_lsd_run(ctx, dimg, (size_t)w * h, w, h, 1);
+  if (st) return st;
+  LsdState* s = ctx->lsd;
+  int n = 0;
+  PLF_CUDA(ctx, cudaMemcpyAsync(&n, s->nregions, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  st = lsd_check_overflow(ctx, "plf_lsd");
+  if (st) return st;
+  *n_out = n;
+  if (n > cap) return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_lsd: %d segments > caller capacity %d", n, cap);
+  if (n > 0) {
+    PLF_CUDA(ctx, cudaMemcpyAsync(segs, s->segs, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return PLF_OK;
+}
+
+extern "C" plf_status plf_detect_lines(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride,
+                                       plf_keyline* keylines, uint8_t* desc, int cap, int* n_out) {
+  if (!ctx || !img || !n_out || w < 3 || h < 3 || stride < w || cap < 0 || (cap > 0 && (!keylines || !desc)))
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_detect_lines: bad arguments");
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t A = ((size_t)w * h + 255) & ~size_t(255);
+  uint8_t* base = (uint8_t*)plf_scratch(ctx, 4, A + A * 4 + (size_t)ctx->limits.max_lines * 32 + 256);
+  if (!base) return PLF_ERR_CUDA;
+  uint8_t* dimg = base;
+  short2* dgrad = (short2*)(base + A);
+  uint8_t* ddesc = base + A + A * 4;
+  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, w, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  plf_status st = plf_lsd_run(ctx, dimg, (size_t)w * h, w, h, 1);
+  if (st) return st;
+  LsdState* s = ctx->lsd;
+  st = plf_launch_blur5_sobel(ctx, dimg, w, 0, w, h, 1, dgrad, 0);
+  if (st) return st;
+  st = plf_launch_lbd(ctx, dgrad, 0, w, h, 1, s->kls, s->nlines, s->max_lines, ddesc, nullptr);
+  if (st) return st;
+  int n = 0;
+  PLF_CUDA(ctx, cudaMemcpyAsync(&n, s->nlines, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  st = lsd_check_overflow(ctx, "plf_detect_lines");
+  if (st) return st;
+  *n_out = n;
+  if (n > cap) return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_detect_lines: %d lines > caller capacity %d", n, cap);
+  if (n > 0) {
+    PLF_CUDA(ctx, cudaMemcpyAsync(keylines, s->kls, (size_t)n * sizeof(plf_keyline), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpyAsync(desc, ddesc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  return PLF_OK;
+}
+
+// glibc sinf/cosf port check hook (tests only exercise it through this entry point)
+__global__ void k_sincosf_probe(const float* in, float* s, float* c, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    s[i] = glibc_sinf(in[i]);
+    c[i] = glibc_cosf(in[i]);
+  }
+}
+
+extern "C" plf_status plf_debug_sincosf(plf_ctx* ctx, const float* in, float* s, float* c, int n) {
+  if (!ctx || n <= 0) return PLF_ERR_INVALID;
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  float* d = (float*)plf_scratch(ctx, 4, (size_t)n * 12);
+  if (!d) return PLF_ERR_CUDA;
+  PLF_CUDA(ctx, cudaMemcpyAsync(d, in, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+  k_sincosf_probe<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d, d + n, d + 2 * (size_t)n, n);
+  PLF_LAUNCH_CHECK(ctx);
+  PLF_CUDA(ctx, cudaMemcpyAsync(s, d + n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(c, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PLF_OK;
+}

@@ -96,6 +96,14 @@ __global__ void __launch_bounds__(256) k_resize_exact(const uint8_t* __restrict_
   dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dw + x] = (uint8_t)(v > 255 ? 255 : v);
 }
 
+plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_stride, int sw, int sh, uint8_t* dst,
+                                   size_t dst_stride, int dw, int dh, const int* tabx, const int* taby, int nimg) {
+  dim3 grid((dw + 255) / 256, dh, nimg);
+  k_resize_exact<<<grid, 256, 0, ctx->stream>>>(src, src_stride, sw, sh, dst, dst_stride, dw, dh, tabx, taby);
+  PLF_LAUNCH_CHECK(ctx);
+  return PLF_OK;
+}
+
 // ---- FAST + NMS ------------------------------------------------------------------------------------
 __device__ __forceinline__ bool has_run9(uint32_t m16) {
   uint32_t m = m16 | (m16 << 16);  // circular
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur
 // ---- host side -----------------------------------------------------------------------------------------
 static int cv_round_f(float v) { return (int)nearbyintf(v); }
 
-static void linear_coeffs_host(int srcsize, int dstsize, double scale, int* ofs, int* c1) {
+void plf_linear_coeffs_host(int srcsize, int dstsize, double scale, int* ofs, int* c1) {
   // interpolationLinear::getCoeffs (resize.cpp, bit-exact path); clamped cases folded into (ofs, c1)
   int mn = 0, mx = dstsize;
   for (int v = 0; v < dstsize; v++) {
@@ -556,10 +564,10 @@ plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg) {
     const int sw = g.w[l - 1], sh = g.h[l - 1], dw = g.w[l], dh = g.h[l];
     s->rs_x_off[l] = tab.size();
     tab.resize(tab.size() + 2 * dw);
-    linear_coeffs_host(sw, dw, 1.0 / ((double)dw / sw), &tab[s->rs_x_off[l]], &tab[s->rs_x_off[l] + dw]);
+    plf_linear_coeffs_host(sw, dw, 1.0 / ((double)dw / sw), &tab[s->rs_x_off[l]], &tab[s->rs_x_off[l] + dw]);
     s->rs_y_off[l] = tab.size();
     tab.resize(tab.size() + 2 * dh);
-    linear_coeffs_host(sh, dh, 1.0 / ((double)dh / sh), &tab[s->rs_y_off[l]], &tab[s->rs_y_off[l] + dh]);
+    plf_linear_coeffs_host(sh, dh, 1.0 / ((double)dh / sh), &tab[s->rs_y_off[l]], &tab[s->rs_y_off[l] + dh]);
   }
   const size_t N = (size_t)nimg;
   PLF_CUDA(ctx, cudaMalloc(&s->pyr, std::max<size_t>(pyr, 256) * N));

@@ -100,12 +100,12 @@ void plf_default_params(plf_params* p) {
   p->orb_fast_th = 20;
   p->lsd_nfeatures = 300;
   p->lsd_refine = 0;
-  p->lsd_scale = 1.2f;
-  p->lsd_sigma_scale = 0.6f;
-  p->lsd_quant = 2.0f;
-  p->lsd_ang_th = 22.5f;
-  p->lsd_log_eps = 1.0f;
-  p->lsd_density_th = 0.6f;
+  p->lsd_scale = 1.2;
+  p->lsd_sigma_scale = 0.6;
+  p->lsd_quant = 2.0;
+  p->lsd_ang_th = 22.5;
+  p->lsd_log_eps = 1.0;
+  p->lsd_density_th = 0.6;
   p->lsd_n_bins = 1024;
 }
 

@@ -126,3 +126,11 @@ plf_status plf_launch_gn(plf_ctx* ctx, const GnProblem* d_probs, int nprob, cons
 plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg);
 plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg);
 void plf_orb_outputs(plf_ctx* ctx, plf_keypoint** kps, uint8_t** desc, int** counts, int* max_kp);
+void plf_linear_coeffs_host(int srcsize, int dstsize, double scale, int* ofs, int* c1);
+plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_stride, int sw, int sh, uint8_t* dst,
+                                   size_t dst_stride, int dw, int dh, const int* tabx, const int* taby, int nimg);
+
+// ---- LSD (lsd.cu) --------------------------------------------------------------------------------
+plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg);
+plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg);
+void plf_lsd_outputs(plf_ctx* ctx, plf_keyline** kls, int** nlines, int* max_lines);

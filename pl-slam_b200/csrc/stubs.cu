@@ -1,6 +1,5 @@
 // Temporary no-op destructors for subsystems that are not built yet (removed as they land).
 #include "plf_internal.h"
 extern "C" {
-void plf_lsd_free(plf_ctx*) {}
 void plf_pipe_free(plf_ctx*) {}
 }

@@ -37,8 +37,8 @@ class plf_params(C.Structure):
         ("orb_nlevels", C.c_int), ("orb_edge_th", C.c_int), ("orb_wta_k", C.c_int),
         ("orb_score", C.c_int), ("orb_patch_size", C.c_int), ("orb_fast_th", C.c_int),
         ("lsd_nfeatures", C.c_int), ("lsd_refine", C.c_int),
-        ("lsd_scale", C.c_float), ("lsd_sigma_scale", C.c_float), ("lsd_quant", C.c_float),
-        ("lsd_ang_th", C.c_float), ("lsd_log_eps", C.c_float), ("lsd_density_th", C.c_float),
+        ("lsd_scale", C.c_double), ("lsd_sigma_scale", C.c_double), ("lsd_quant", C.c_double),
+        ("lsd_ang_th", C.c_double), ("lsd_log_eps", C.c_double), ("lsd_density_th", C.c_double),
         ("lsd_n_bins", C.c_int),
     ]
 
@@ -280,3 +280,34 @@ class Frontend:
                               kps.ctypes.data_as(C.c_void_p), _ptr(desc, C.c_uint8), cap, C.byref(n))
         self._check(st, "plf_orb")
         return kps[:n.value].copy(), desc[:n.value].copy()
+
+    # -- line features ---------------------------------------------------------------------------
+    def lsd(self, img, cap=16384):
+        """cv::LineSegmentDetector::detect with the ctx LSD parameters: float32[n,4] in OpenCV's order."""
+        img = _u8(img)
+        h, w = img.shape
+        segs = np.zeros((cap, 4), np.float32)
+        n = C.c_int(0)
+        st = self.lib.plf_lsd(self._ctx, _ptr(img, C.c_uint8), w, h, img.strides[0], _ptr(segs, C.c_float), cap,
+                              C.byref(n))
+        self._check(st, "plf_lsd")
+        return segs[:n.value].copy()
+
+    def detect_lines(self, img, cap=4096):
+        """stvo-pl detectLineFeatures: (keylines[KEYLINE_DTYPE], LBD desc u8[n,32])."""
+        img = _u8(img)
+        h, w = img.shape
+        kl = np.zeros(cap, KEYLINE_DTYPE)
+        desc = np.zeros((cap, 32), np.uint8)
+        n = C.c_int(0)
+        st = self.lib.plf_detect_lines(self._ctx, _ptr(img, C.c_uint8), w, h, img.strides[0],
+                                       kl.ctypes.data_as(C.c_void_p), _ptr(desc, C.c_uint8), cap, C.byref(n))
+        self._check(st, "plf_detect_lines")
+        return kl[:n.value].copy(), desc[:n.value].copy()
+
+    def debug_sincosf(self, x):
+        x = np.ascontiguousarray(x, np.float32)
+        s = np.empty_like(x); c = np.empty_like(x)
+        st = self.lib.plf_debug_sincosf(self._ctx, _ptr(x, C.c_float), _ptr(s, C.c_float), _ptr(c, C.c_float), len(x))
+        self._check(st, "plf_debug_sincosf")
+        return s, c
