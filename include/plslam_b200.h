@@ -227,6 +227,66 @@ plf_status plf_gn_pose(plf_ctx* ctx, const plf_gn_opts* opts, const double* P, c
  * op 0 = expmap_se3 (in: 6 = [t; w], out: 16 row-major), op 1 = logmap_se3 (in: 16, out: 6). */
 plf_status plf_se3(plf_ctx* ctx, int op, const double* in, double* out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Batched per-frame front-end (call pattern app/plslam_dataset.cpp:111-163)
+ * ---------------------------------------------------------------------------------------------- */
+
+/* What StereoFrameHandler exposes after insertStereoPair + optimizePose for one frame. */
+typedef struct plf_frame_result {
+  double DT[16];     /* curr_frame->DT = inverse_se3(optimised increment), row-major; identity if status != 0 */
+  double DT_cov[36]; /* curr_frame->DT_cov */
+  double err;        /* curr_frame->err_norm (-1 when no optimisation ran) */
+  int status;        /* 0 = tracked, 1 = fewer than min_features correspondences, 2 = first frame (initialize) */
+  int n_kp_l, n_kp_r, n_lines_l, n_lines_r; /* detected features per image */
+  int n_stereo_pt, n_stereo_ls;             /* stereo_pt.size(), stereo_ls.size() */
+  int n_matched_pt, n_matched_ls;           /* matched_pt.size(), matched_ls.size() */
+  int n_inliers_pt, n_inliers_ls;           /* n_inliers_pt, n_inliers_ls */
+  int iters1, iters2;
+} plf_frame_result;
+
+/* Host destination for the stereo-valid features of one frame (the StereoFrame fields KeyFrame copies,
+ * src/keyFrame.cpp:39-53; row i of pdesc/ldesc <-> stereo_pt[i]/stereo_ls[i]).  Any array may be NULL. */
+typedef struct plf_frame_view {
+  int cap_pt, cap_ls;  /* in: capacity of the arrays; out: n_pt / n_ls filled */
+  int n_pt, n_ls;
+  double* pt_pl;       /* n_pt x 2   PointFeature::pl */
+  double* pt_disp;     /* n_pt       PointFeature::disp */
+  double* pt_P;        /* n_pt x 3   PointFeature::P */
+  int32_t* pt_octave;  /* n_pt */
+  uint8_t* pdesc;      /* n_pt x 32  StereoFrame::pdesc_l */
+  double* ls_spl;      /* n_ls x 2   LineFeature::spl */
+  double* ls_epl;      /* n_ls x 2 */
+  double* ls_sdisp;    /* n_ls */
+  double* ls_edisp;    /* n_ls */
+  double* ls_sP;       /* n_ls x 3 */
+  double* ls_eP;       /* n_ls x 3 */
+  double* ls_le;       /* n_ls x 3   LineFeature::le (normalised line equation) */
+  float* ls_angle;     /* n_ls */
+  uint8_t* ldesc;      /* n_ls x 32  StereoFrame::ldesc_l */
+} plf_frame_view;
+
+/* Forget the previous frame (next batch starts with initialize(), app/plslam_dataset.cpp:115). */
+plf_status plf_reset_sequence(plf_ctx* ctx);
+
+/* Replaces B consecutive iterations of the VO part of the hot loop:
+ *   StVO->insertStereoPair(img_l, img_r, k); StVO->optimizePose();   (app/plslam_dataset.cpp:127-128)
+ * left/right: B images each, h rows of `stride` bytes, image k at offset k*stride*h (host).  out: B results.
+ * The caller chains Tfw = prev.Tfw * DT (as optimizePose does) and applies its keyframe policy. */
+plf_status plf_process_batch(plf_ctx* ctx, int B, const uint8_t* left, const uint8_t* right, int stride,
+                             plf_frame_result* out);
+
+/* The three phases of plf_process_batch, for callers that keep images resident in HBM:
+ * upload (H2D) -> run (all kernels, asynchronous on plf_stream) -> download (D2H of the B results + sync). */
+plf_status plf_batch_upload(plf_ctx* ctx, int B, const uint8_t* left, const uint8_t* right, int stride);
+plf_status plf_batch_run(plf_ctx* ctx, int B);
+plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out);
+/* Device buffer [2*max_batch][h][w] read by plf_batch_run (image 2k = left k, 2k+1 = right k). */
+void* plf_batch_device_images(plf_ctx* ctx);
+
+/* Stereo-valid features of frame k of the last batch (what `new KeyFrame(StVO->curr_frame)` deep-copies,
+ * app/plslam_dataset.cpp:143, src/keyFrame.cpp:39-53). */
+plf_status plf_get_frame(plf_ctx* ctx, int k, plf_frame_view* view);
+
 #ifdef __cplusplus
 }
 #endif

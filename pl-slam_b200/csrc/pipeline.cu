@@ -1,0 +1,558 @@
+// Batched stereo front-end: extraction -> L/R stereo association -> frame-to-frame tracking -> pose refinement
+// (SURVEY §8 a6, a7, a10 and the call pattern of app/plslam_dataset.cpp:111-163).
+//
+// Replaces, per stereo pair: StereoFrameHandler::insertStereoPair (app/plslam_dataset.cpp:127) = new StereoFrame +
+// extractStereoFeatures (ORB + LSD/LBD on both images, matchStereoPoints / matchStereoLines) + f2fTracking, and
+// StereoFrameHandler::optimizePose (app/plslam_dataset.cpp:128).  stvo-pl is not vendored by the reference; the
+// association rules restate SURVEY.md Appendix A.2/A.3 (see oracle/frontend.py, which this file must match
+// bit-for-bit on features / matches and to 1e-4 on the pose).
+//
+// One call processes B consecutive stereo pairs of ONE sequence.  Everything except the final SE(3) chaining is
+// independent per pair (extraction, stereo association) or per consecutive pair (tracking and the pose increment
+// start from identity: use_motion_model = false, config_euroc.yaml:18), so all B pairs run in the same launches:
+// images [2B][H][W] (2k = left, 2k+1 = right) -> ORB / LSD / LBD over 2B images -> per-pair kernels.  The last
+// frame's stereo features are carried to the next call (slot 0).
+#include "plf_internal.h"
+
+struct FrameSlots {  // stereo-valid features per frame slot: [slots][cap]
+  double2* pt_pl; double* pt_disp; double* pt_P; int* pt_octave; uint8_t* pdesc; int* pt_count;
+  double2* ls_spl; double2* ls_epl; double* ls_sdisp; double* ls_edisp; double* ls_sP; double* ls_eP; double* ls_le;
+  float* ls_angle; uint8_t* ldesc; int* ls_count;
+};
+
+struct PipeState {
+  int w = 0, h = 0, B = 0, max_kp = 0, max_ln = 0;
+  bool has_prev = false;
+  uint8_t* imgs = nullptr;     // [2B][h][w]
+  short2* lbd_grad = nullptr;  // [2B][h*w]
+  uint8_t* ldesc_raw = nullptr;  // [2B][max_ln][32]  LBD of every kept KeyLine
+  FrameSlots fs;               // B+1 slots
+  // matching scratch
+  uint32_t* knn_keys = nullptr;   // [B][8][2][max_kp]
+  int32_t* m12 = nullptr;         // [B][4][max_kp]  stereo pts, stereo lines, f2f pts, f2f lines
+  int* mcount = nullptr;          // [B][4]
+  KnnProblem* knn_stereo = nullptr;  // [B*4]
+  KnnProblem* knn_f2f = nullptr;     // [B*4]
+  NnrProblem* nnr_stereo = nullptr;  // [B*2]
+  NnrProblem* nnr_f2f = nullptr;     // [B*2]
+  // GN inputs / outputs
+  double* gnP = nullptr; double* gnObs = nullptr; uint8_t* gnInlP = nullptr; int* gnNp = nullptr;
+  double* gn_sP = nullptr; double* gn_eP = nullptr; double* gn_le = nullptr; uint8_t* gnInlL = nullptr; int* gnNl = nullptr;
+  GnProblem* gn_probs = nullptr;
+  plf_pose_result* gn_out = nullptr;
+  plf_frame_result* results = nullptr;  // [B] device
+  plf_frame_result* h_results = nullptr;  // pinned host mirror
+  void* orb_kps_seen = nullptr;  // sub-system output pointers baked into the problem descriptors
+  void* lsd_kls_seen = nullptr;
+  std::vector<void*> allocs;
+};
+
+template <typename T>
+static plf_status pipe_alloc(plf_ctx* ctx, PipeState* s, T** p, size_t n) {
+  void* q = nullptr;
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 256));
+  if (e != cudaSuccess) return plf_fail(ctx, PLF_ERR_CUDA, "pipeline cudaMalloc(%zu): %s", n * sizeof(T), cudaGetErrorString(e));
+  *p = (T*)q;
+  s->allocs.push_back(q);
+  return PLF_OK;
+}
+
+extern "C" void plf_pipe_free(plf_ctx* ctx) {
+  PipeState* s = ctx->pipe;
+  if (!s) return;
+  for (void* p : s->allocs) cudaFree(p);
+  if (s->h_results) cudaFreeHost(s->h_results);
+  delete s;
+  ctx->pipe = nullptr;
+}
+
+struct StereoPrm {
+  float max_dist_epip, min_disp, line_horiz_th, stereo_overlap_th, ls_min_disp_ratio;
+  double fx, fy, cx, cy, b;
+};
+
+__device__ __forceinline__ void back_projection(const StereoPrm& c, double u, double v, double disp, double* P) {
+  const double Z = c.fx * c.b / disp;  // PinholeStereoCamera::backProjection
+  P[0] = Z * (u - c.cx) / c.fx;
+  P[1] = Z * (v - c.cy) / c.fy;
+  P[2] = Z;
+}
+
+// block-wide inclusive scan of 0/1 flags (1024 threads); returns inclusive prefix, total in *total
+__device__ __forceinline__ int block_scan_flags(bool flag, int* s_scan, int* s_total) {
+  const int tid = threadIdx.x;
+  s_scan[tid] = flag ? 1 : 0;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const int v = tid >= off ? s_scan[tid - off] : 0;
+    __syncthreads();
+    s_scan[tid] += v;
+    __syncthreads();
+  }
+  const int incl = s_scan[tid];
+  if (tid == 1023) *s_total = incl;
+  __syncthreads();
+  return incl;
+}
+
+// matchStereoPoints: epipolar + disparity gates, back-projection, compaction in left-index order.
+__global__ void __launch_bounds__(1024) k_stereo_points(const plf_keypoint* __restrict__ kps, const uint8_t* __restrict__ desc,
+                                                         const int* __restrict__ kp_count, int max_kp,
+                                                         const int32_t* __restrict__ m12_all, int m12_stride, StereoPrm prm,
+                                                         FrameSlots fs, int slot0) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_total;
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const int il = 2 * k, ir = 2 * k + 1, slot = slot0 + k;
+  const plf_keypoint* kl = kps + (size_t)il * max_kp;
+  const plf_keypoint* kr = kps + (size_t)ir * max_kp;
+  const int32_t* m12 = m12_all + (size_t)k * m12_stride;
+  const int n = min(kp_count[il], max_kp);
+  int base = 0;
+  for (int c0 = 0; c0 < n; c0 += 1024) {
+    const int i = c0 + tid;
+    bool ok = false;
+    float xl = 0, yl = 0;
+    double d = 0;
+    int oct = 0;
+    if (i < n) {
+      const int j = m12[i];
+      if (j >= 0) {
+        const plf_keypoint a = kl[i], b = kr[j];
+        xl = a.x; yl = a.y; oct = a.octave;
+        if (fabsf(__fsub_rn(a.y, b.y)) <= prm.max_dist_epip) {
+          d = (double)__fsub_rn(a.x, b.x);
+          ok = d >= (double)prm.min_disp;
+        }
+      }
+    }
+    const int incl = block_scan_flags(ok, s_scan, &s_total);
+    if (ok) {
+      const size_t o = (size_t)slot * max_kp + base + incl - 1;
+      fs.pt_pl[o] = make_double2((double)xl, (double)yl);
+      fs.pt_disp[o] = d;
+      back_projection(prm, (double)xl, (double)yl, d, fs.pt_P + 3 * o);
+      fs.pt_octave[o] = oct;
+      const uint4* src = reinterpret_cast<const uint4*>(desc + ((size_t)il * max_kp + i) * 32);
+      uint4* dst = reinterpret_cast<uint4*>(fs.pdesc + o * 32);
+      dst[0] = src[0];
+      dst[1] = src[1];
+    }
+    base += s_total;
+    __syncthreads();
+  }
+  if (tid == 0) fs.pt_count[slot] = base;
+}
+
+__device__ __forceinline__ double line_overlap_stereo(double spl_obs, double epl_obs, double spl_proj, double epl_proj,
+                                                      double line_horiz_th) {
+  double overlap = 1.0;
+  if (fabs(epl_obs - spl_obs) > line_horiz_th) {
+    const double sln = fmin(spl_obs, epl_obs), eln = fmax(spl_obs, epl_obs);
+    const double spn = fmin(spl_proj, epl_proj), epn = fmax(spl_proj, epl_proj);
+    const double length = eln - spn;
+    if (epn < sln || spn > eln) overlap = 0.0;
+    else if (epn > eln && spn < sln) overlap = eln - sln;
+    else overlap = fmin(eln, epn) - fmax(sln, spn);
+    overlap = (length > (double)0.01f) ? overlap / length : 0.0;
+    if (overlap > 1.0) overlap = 1.0;
+  }
+  return overlap;
+}
+
+// matchStereoLines
+__global__ void __launch_bounds__(1024) k_stereo_lines(const plf_keyline* __restrict__ kls, const uint8_t* __restrict__ ldesc,
+                                                        const int* __restrict__ nlines, int max_ln,
+                                                        const int32_t* __restrict__ m12_all, int m12_stride, StereoPrm prm,
+                                                        FrameSlots fs, int slot0) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_total;
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const int il = 2 * k, ir = 2 * k + 1, slot = slot0 + k;
+  const plf_keyline* L = kls + (size_t)il * max_ln;
+  const plf_keyline* R = kls + (size_t)ir * max_ln;
+  const int32_t* m12 = m12_all + (size_t)k * m12_stride;
+  const int n = min(nlines[il], max_ln);
+  int base = 0;
+  for (int c0 = 0; c0 < n; c0 += 1024) {
+    const int i = c0 + tid;
+    bool ok = false;
+    double spl[2] = {0, 0}, epl[2] = {0, 0}, le_l[3] = {0, 0, 0}, disp_s = 0, disp_e = 0;
+    float angle = 0;
+    if (i < n) {
+      const int j = m12[i];
+      if (j >= 0) {
+        const plf_keyline a = L[i], b = R[j];
+        const double sxl = a.startPointX, syl = a.startPointY, exl = a.endPointX, eyl = a.endPointY;
+        const double sxr = b.startPointX, syr = b.startPointY, exr = b.endPointX, eyr = b.endPointY;
+        // le = sp x ep with homogeneous 1
+        double l0 = syl * 1.0 - 1.0 * eyl, l1 = 1.0 * exl - sxl * 1.0, l2 = sxl * eyl - syl * exl;
+        const double nrm = sqrt(l0 * l0 + l1 * l1);
+        le_l[0] = l0 / nrm; le_l[1] = l1 / nrm; le_l[2] = l2 / nrm;
+        const double r0 = syr * 1.0 - 1.0 * eyr, r1 = 1.0 * exr - sxr * 1.0, r2 = sxr * eyr - syr * exr;
+        const double overlap = line_overlap_stereo(syl, eyl, syr, eyr, (double)prm.line_horiz_th);
+        const double sx_on_r = -(r2 + r1 * syl) / r0;
+        const double ex_on_r = -(r2 + r1 * eyl) / r0;
+        disp_s = sxl - sx_on_r;
+        disp_e = exl - ex_on_r;
+        if (!(fmin(disp_s, disp_e) / fmax(disp_s, disp_e) >= (double)prm.ls_min_disp_ratio)) disp_s = disp_e = -1.0;
+        ok = disp_s >= (double)prm.min_disp && disp_e >= (double)prm.min_disp &&
+             fabsf((float)r0) > prm.line_horiz_th && overlap > (double)prm.stereo_overlap_th;
+        spl[0] = sxl; spl[1] = syl; epl[0] = exl; epl[1] = eyl;
+        angle = a.angle;
+      }
+    }
+    const int incl = block_scan_flags(ok, s_scan, &s_total);
+    if (ok) {
+      const size_t o = (size_t)slot * max_ln + base + incl - 1;
+      fs.ls_spl[o] = make_double2(spl[0], spl[1]);
+      fs.ls_epl[o] = make_double2(epl[0], epl[1]);
+      fs.ls_sdisp[o] = disp_s;
+      fs.ls_edisp[o] = disp_e;
+      back_projection(prm, spl[0], spl[1], disp_s, fs.ls_sP + 3 * o);
+      back_projection(prm, epl[0], epl[1], disp_e, fs.ls_eP + 3 * o);
+      fs.ls_le[3 * o] = le_l[0]; fs.ls_le[3 * o + 1] = le_l[1]; fs.ls_le[3 * o + 2] = le_l[2];
+      fs.ls_angle[o] = angle;
+      const uint4* src = reinterpret_cast<const uint4*>(ldesc + ((size_t)il * max_ln + i) * 32);
+      uint4* dst = reinterpret_cast<uint4*>(fs.ldesc + o * 32);
+      dst[0] = src[0];
+      dst[1] = src[1];
+    }
+    base += s_total;
+    __syncthreads();
+  }
+  if (tid == 0) fs.ls_count[slot] = base;
+}
+
+// f2fTracking: gather the matched rows into the GN problem of pair k (prev slot = slot0+k-1 ... see host code)
+__global__ void __launch_bounds__(1024) k_f2f_build(FrameSlots fs, int prev_slot0, int max_kp, int max_ln,
+                                                    const int32_t* __restrict__ m_pt_all, const int32_t* __restrict__ m_ls_all,
+                                                    int m_stride, double* __restrict__ gnP, double* __restrict__ gnObs,
+                                                    uint8_t* __restrict__ gnInlP, int* __restrict__ gnNp,
+                                                    double* __restrict__ gn_sP, double* __restrict__ gn_eP,
+                                                    double* __restrict__ gn_le, uint8_t* __restrict__ gnInlL,
+                                                    int* __restrict__ gnNl) {
+  __shared__ int s_scan[1024];
+  __shared__ int s_total;
+  const int k = blockIdx.x, tid = threadIdx.x;
+  const int ps = prev_slot0 + k, cs = ps + 1;
+  {  // points
+    const int32_t* m = m_pt_all + (size_t)k * m_stride;
+    const int n = min(fs.pt_count[ps], max_kp);
+    int base = 0;
+    for (int c0 = 0; c0 < n; c0 += 1024) {
+      const int i = c0 + tid;
+      const int j = i < n ? m[i] : -1;
+      const bool ok = j >= 0;
+      const int incl = block_scan_flags(ok, s_scan, &s_total);
+      if (ok) {
+        const size_t o = (size_t)k * max_kp + base + incl - 1;
+        const double* P = fs.pt_P + 3 * ((size_t)ps * max_kp + i);
+        gnP[3 * o] = P[0]; gnP[3 * o + 1] = P[1]; gnP[3 * o + 2] = P[2];
+        const double2 q = fs.pt_pl[(size_t)cs * max_kp + j];
+        gnObs[2 * o] = q.x; gnObs[2 * o + 1] = q.y;
+        gnInlP[o] = 1;
+      }
+      base += s_total;
+      __syncthreads();
+    }
+    if (tid == 0) gnNp[k] = base;
+  }
+  {  // lines
+    const int32_t* m = m_ls_all + (size_t)k * m_stride;
+    const int n = min(fs.ls_count[ps], max_ln);
+    int base = 0;
+    for (int c0 = 0; c0 < n; c0 += 1024) {
+      const int i = c0 + tid;
+      const int j = i < n ? m[i] : -1;
+      const bool ok = j >= 0;
+      const int incl = block_scan_flags(ok, s_scan, &s_total);
+      if (ok) {
+        const size_t o = (size_t)k * max_ln + base + incl - 1;
+        const size_t pi = (size_t)ps * max_ln + i, ci = (size_t)cs * max_ln + j;
+        for (int c = 0; c < 3; ++c) {
+          gn_sP[3 * o + c] = fs.ls_sP[3 * pi + c];
+          gn_eP[3 * o + c] = fs.ls_eP[3 * pi + c];
+          gn_le[3 * o + c] = fs.ls_le[3 * ci + c];
+        }
+        gnInlL[o] = 1;
+      }
+      base += s_total;
+      __syncthreads();
+    }
+    if (tid == 0) gnNl[k] = base;
+  }
+}
+
+// optimizePose epilogue: curr.DT = inverse_se3(T_inc); identity when there were too few correspondences
+__global__ void k_finalize(const plf_pose_result* __restrict__ gn, const int* __restrict__ gnNp, const int* __restrict__ gnNl,
+                           const int* __restrict__ kp_count, const int* __restrict__ nlines, FrameSlots fs, int slot0,
+                           int min_features, int first_is_init, int B, plf_frame_result* __restrict__ out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= B) return;
+  plf_frame_result r;
+  for (int i = 0; i < 16; ++i) r.DT[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  for (int i = 0; i < 36; ++i) r.DT_cov[i] = 0.0;
+  r.err = -1.0;
+  r.n_kp_l = kp_count[2 * k]; r.n_kp_r = kp_count[2 * k + 1];
+  r.n_lines_l = nlines[2 * k]; r.n_lines_r = nlines[2 * k + 1];
+  r.n_stereo_pt = fs.pt_count[slot0 + k]; r.n_stereo_ls = fs.ls_count[slot0 + k];
+  r.n_matched_pt = r.n_matched_ls = r.n_inliers_pt = r.n_inliers_ls = r.iters1 = r.iters2 = 0;
+  if (k == 0 && first_is_init) {
+    r.status = 2;
+  } else {
+    const plf_pose_result& g = gn[k];
+    r.n_matched_pt = gnNp[k]; r.n_matched_ls = gnNl[k];
+    if (r.n_matched_pt + r.n_matched_ls < min_features) {
+      r.status = 1;
+    } else {
+      r.status = 0;
+      const double* T = g.T;
+      for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) r.DT[4 * i + j] = T[4 * j + i];
+        r.DT[4 * i + 3] = -(T[i] * T[3] + T[4 + i] * T[7] + T[8 + i] * T[11]);
+      }
+      for (int i = 0; i < 36; ++i) r.DT_cov[i] = g.cov[i];
+      r.err = g.err;
+      r.n_inliers_pt = g.n_inliers_pt; r.n_inliers_ls = g.n_inliers_ls;
+      r.iters1 = g.iters1; r.iters2 = g.iters2;
+    }
+  }
+  out[k] = r;
+}
+
+static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
+  PipeState* s = ctx->pipe;
+  if (s && s->w == w && s->h == h) {
+    // a standalone operator call on another image size may have rebuilt the ORB / LSD state meanwhile
+    plf_status st0;
+    if ((st0 = plf_orb_prepare(ctx, w, h, 2 * s->B))) return st0;
+    if ((st0 = plf_lsd_prepare(ctx, w, h, 2 * s->B))) return st0;
+    plf_keypoint* kps0; uint8_t* d0; int* c0; int m0;
+    plf_orb_outputs(ctx, &kps0, &d0, &c0, &m0);
+    plf_keyline* kl0; int* lc0; int ml0;
+    plf_lsd_outputs(ctx, &kl0, &lc0, &ml0);
+    if (kps0 == s->orb_kps_seen && kl0 == s->lsd_kls_seen) return PLF_OK;
+  }
+  if (s) plf_pipe_free(ctx);
+  s = ctx->pipe = new PipeState();
+  const int B = ctx->limits.max_batch, K = ctx->limits.max_keypoints, Ln = ctx->limits.max_lines;
+  if (Ln > K || K > 65535)
+    return plf_fail(ctx, PLF_ERR_INVALID, "limits: need max_lines <= max_keypoints <= 65535 (got %d, %d)", Ln, K);
+  s->w = w; s->h = h; s->B = B; s->max_kp = K; s->max_ln = Ln;
+  plf_status st;
+#define PA(ptr, n) if ((st = pipe_alloc(ctx, s, &(ptr), (n)))) return st
+  const size_t A = (size_t)w * h, S = (size_t)B + 1;
+  PA(s->imgs, 2 * (size_t)B * A);
+  PA(s->lbd_grad, 2 * (size_t)B * A);
+  PA(s->ldesc_raw, 2 * (size_t)B * Ln * 32);
+  FrameSlots& f = s->fs;
+  PA(f.pt_pl, S * K); PA(f.pt_disp, S * K); PA(f.pt_P, S * K * 3); PA(f.pt_octave, S * K); PA(f.pdesc, S * K * 32); PA(f.pt_count, S);
+  PA(f.ls_spl, S * Ln); PA(f.ls_epl, S * Ln); PA(f.ls_sdisp, S * Ln); PA(f.ls_edisp, S * Ln); PA(f.ls_sP, S * Ln * 3);
+  PA(f.ls_eP, S * Ln * 3); PA(f.ls_le, S * Ln * 3); PA(f.ls_angle, S * Ln); PA(f.ldesc, S * Ln * 32); PA(f.ls_count, S);
+  PA(s->knn_keys, (size_t)B * 8 * 2 * K);
+  PA(s->m12, (size_t)B * 4 * K);
+  PA(s->mcount, (size_t)B * 4);
+  PA(s->knn_stereo, (size_t)B * 4); PA(s->knn_f2f, (size_t)B * 4); PA(s->nnr_stereo, (size_t)B * 2); PA(s->nnr_f2f, (size_t)B * 2);
+  PA(s->gnP, (size_t)B * K * 3); PA(s->gnObs, (size_t)B * K * 2); PA(s->gnInlP, (size_t)B * K); PA(s->gnNp, B);
+  PA(s->gn_sP, (size_t)B * Ln * 3); PA(s->gn_eP, (size_t)B * Ln * 3); PA(s->gn_le, (size_t)B * Ln * 3); PA(s->gnInlL, (size_t)B * Ln); PA(s->gnNl, B);
+  PA(s->gn_probs, B); PA(s->gn_out, B); PA(s->results, B);
+#undef PA
+  PLF_CUDA(ctx, cudaHostAlloc(&s->h_results, sizeof(plf_frame_result) * B, cudaHostAllocDefault));
+  PLF_CUDA(ctx, cudaMemsetAsync(f.pt_count, 0, S * sizeof(int), ctx->stream));
+  PLF_CUDA(ctx, cudaMemsetAsync(f.ls_count, 0, S * sizeof(int), ctx->stream));
+  // sub-systems sized for 2B images
+  if ((st = plf_orb_prepare(ctx, w, h, 2 * B))) return st;
+  if ((st = plf_lsd_prepare(ctx, w, h, 2 * B))) return st;
+  // static problem descriptors (pointers never change; counts are read on the device)
+  plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
+  plf_orb_outputs(ctx, &kps, &odesc, &kcnt, &mk);
+  plf_keyline* kls; int* lcnt; int ml;
+  plf_lsd_outputs(ctx, &kls, &lcnt, &ml);
+  s->orb_kps_seen = kps;
+  s->lsd_kls_seen = kls;
+  std::vector<KnnProblem> ks(B * 4), kf(B * 4);
+  std::vector<NnrProblem> ns(B * 2), nf(B * 2);
+  const plf_params& P = ctx->params;
+  for (int k = 0; k < B; ++k) {
+    auto key = [&](int prob, int which) { return s->knn_keys + (((size_t)k * 8 + prob) * 2 + which) * K; };
+    const uint32_t* dl = (const uint32_t*)(odesc + (size_t)(2 * k) * K * 32);
+    const uint32_t* dr = (const uint32_t*)(odesc + (size_t)(2 * k + 1) * K * 32);
+    const uint32_t* ll = (const uint32_t*)(s->ldesc_raw + (size_t)(2 * k) * Ln * 32);
+    const uint32_t* lr = (const uint32_t*)(s->ldesc_raw + (size_t)(2 * k + 1) * Ln * 32);
+    ks[4 * k + 0] = {dl, dr, kcnt + 2 * k, kcnt + 2 * k + 1, 0, 0, key(0, 0), key(0, 1)};
+    ks[4 * k + 1] = {dr, dl, kcnt + 2 * k + 1, kcnt + 2 * k, 0, 0, key(1, 0), key(1, 1)};
+    ks[4 * k + 2] = {ll, lr, lcnt + 2 * k, lcnt + 2 * k + 1, 0, 0, key(2, 0), key(2, 1)};
+    ks[4 * k + 3] = {lr, ll, lcnt + 2 * k + 1, lcnt + 2 * k, 0, 0, key(3, 0), key(3, 1)};
+    ns[2 * k + 0] = {key(0, 0), key(0, 1), key(1, 0), key(1, 1), kcnt + 2 * k, kcnt + 2 * k + 1, 0, 0, P.min_ratio_12_p,
+                     P.best_lr_matches ? 1 : 0, s->m12 + ((size_t)k * 4 + 0) * K, s->mcount + 4 * k + 0};
+    ns[2 * k + 1] = {key(2, 0), key(2, 1), key(3, 0), key(3, 1), lcnt + 2 * k, lcnt + 2 * k + 1, 0, 0, P.min_ratio_12_l,
+                     P.best_lr_matches ? 1 : 0, s->m12 + ((size_t)k * 4 + 1) * K, s->mcount + 4 * k + 1};
+    // f2f: prev slot k, curr slot k+1
+    const uint32_t* pp = (const uint32_t*)(f.pdesc + (size_t)k * K * 32);
+    const uint32_t* pc = (const uint32_t*)(f.pdesc + (size_t)(k + 1) * K * 32);
+    const uint32_t* lp = (const uint32_t*)(f.ldesc + (size_t)k * Ln * 32);
+    const uint32_t* lc = (const uint32_t*)(f.ldesc + (size_t)(k + 1) * Ln * 32);
+    kf[4 * k + 0] = {pp, pc, f.pt_count + k, f.pt_count + k + 1, 0, 0, key(4, 0), key(4, 1)};
+    kf[4 * k + 1] = {pc, pp, f.pt_count + k + 1, f.pt_count + k, 0, 0, key(5, 0), key(5, 1)};
+    kf[4 * k + 2] = {lp, lc, f.ls_count + k, f.ls_count + k + 1, 0, 0, key(6, 0), key(6, 1)};
+    kf[4 * k + 3] = {lc, lp, f.ls_count + k + 1, f.ls_count + k, 0, 0, key(7, 0), key(7, 1)};
+    nf[2 * k + 0] = {key(4, 0), key(4, 1), key(5, 0), key(5, 1), f.pt_count + k, f.pt_count + k + 1, 0, 0, P.min_ratio_12_p,
+                     P.best_lr_matches ? 1 : 0, s->m12 + ((size_t)k * 4 + 2) * K, s->mcount + 4 * k + 2};
+    nf[2 * k + 1] = {key(6, 0), key(6, 1), key(7, 0), key(7, 1), f.ls_count + k, f.ls_count + k + 1, 0, 0, P.min_ratio_12_l,
+                     P.best_lr_matches ? 1 : 0, s->m12 + ((size_t)k * 4 + 3) * K, s->mcount + 4 * k + 3};
+  }
+  std::vector<GnProblem> gp(B);
+  for (int k = 0; k < B; ++k)
+    gp[k] = {s->gnP + (size_t)k * K * 3, s->gnObs + (size_t)k * K * 2, s->gnInlP + (size_t)k * K, s->gnNp + k, 0,
+             s->gn_sP + (size_t)k * Ln * 3, s->gn_eP + (size_t)k * Ln * 3, s->gn_le + (size_t)k * Ln * 3,
+             s->gnInlL + (size_t)k * Ln, s->gnNl + k, 0, nullptr, s->gn_out + k};
+  cudaStream_t cs = ctx->stream;
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->knn_stereo, ks.data(), ks.size() * sizeof(KnnProblem), cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->knn_f2f, kf.data(), kf.size() * sizeof(KnnProblem), cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->nnr_stereo, ns.data(), ns.size() * sizeof(NnrProblem), cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->nnr_f2f, nf.data(), nf.size() * sizeof(NnrProblem), cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->gn_probs, gp.data(), gp.size() * sizeof(GnProblem), cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaStreamSynchronize(cs));
+  return PLF_OK;
+}
+
+static plf_status copy_slot(plf_ctx* ctx, PipeState* s, int from, int to) {
+  FrameSlots& f = s->fs;
+  const size_t K = s->max_kp, Ln = s->max_ln;
+  cudaStream_t cs = ctx->stream;
+#define CP(ptr, per) PLF_CUDA(ctx, cudaMemcpyAsync((char*)(ptr) + (size_t)to * (per), (char*)(ptr) + (size_t)from * (per), (per), cudaMemcpyDeviceToDevice, cs))
+  CP(f.pt_pl, K * sizeof(double2)); CP(f.pt_disp, K * 8); CP(f.pt_P, K * 24); CP(f.pt_octave, K * 4); CP(f.pdesc, K * 32); CP(f.pt_count, 4);
+  CP(f.ls_spl, Ln * 16); CP(f.ls_epl, Ln * 16); CP(f.ls_sdisp, Ln * 8); CP(f.ls_edisp, Ln * 8); CP(f.ls_sP, Ln * 24);
+  CP(f.ls_eP, Ln * 24); CP(f.ls_le, Ln * 24); CP(f.ls_angle, Ln * 4); CP(f.ldesc, Ln * 32); CP(f.ls_count, 4);
+#undef CP
+  return PLF_OK;
+}
+
+extern "C" {
+
+plf_status plf_reset_sequence(plf_ctx* ctx) {
+  if (!ctx) return PLF_ERR_INVALID;
+  if (ctx->pipe) ctx->pipe->has_prev = false;
+  return PLF_OK;
+}
+
+plf_status plf_batch_upload(plf_ctx* ctx, int B, const uint8_t* left, const uint8_t* right, int stride) {
+  if (!ctx || !left || !right || B < 1 || B > ctx->limits.max_batch || stride < ctx->cam.width)
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_upload: bad arguments (B=%d, max_batch=%d)", B, ctx ? ctx->limits.max_batch : 0);
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int w = ctx->cam.width, h = ctx->cam.height;
+  plf_status st = pipe_prepare(ctx, w, h);
+  if (st) return st;
+  PipeState* s = ctx->pipe;
+  const size_t A = (size_t)w * h, hs = (size_t)stride * h;
+  // interleave: device image 2k = left k, 2k+1 = right k
+  for (int k = 0; k < B; ++k) {
+    PLF_CUDA(ctx, cudaMemcpy2DAsync(s->imgs + (size_t)(2 * k) * A, w, left + k * hs, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpy2DAsync(s->imgs + (size_t)(2 * k + 1) * A, w, right + k * hs, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return PLF_OK;
+}
+
+void* plf_batch_device_images(plf_ctx* ctx) {
+  if (!ctx) return nullptr;
+  if (pipe_prepare(ctx, ctx->cam.width, ctx->cam.height)) return nullptr;
+  return ctx->pipe->imgs;
+}
+
+plf_status plf_batch_run(plf_ctx* ctx, int B) {
+  if (!ctx || B < 1 || B > ctx->limits.max_batch) return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_run: bad B");
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int w = ctx->cam.width, h = ctx->cam.height;
+  plf_status st = pipe_prepare(ctx, w, h);
+  if (st) return st;
+  PipeState* s = ctx->pipe;
+  const size_t A = (size_t)w * h;
+  const int K = s->max_kp, Ln = s->max_ln;
+  cudaStream_t cs = ctx->stream;
+  const plf_params& P = ctx->params;
+  if (!s->has_prev) {  // initialize(): no previous frame to track against
+    PLF_CUDA(ctx, cudaMemsetAsync(s->fs.pt_count, 0, sizeof(int), cs));
+    PLF_CUDA(ctx, cudaMemsetAsync(s->fs.ls_count, 0, sizeof(int), cs));
+  }
+  // --- extraction over 2B images
+  if ((st = plf_orb_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
+  if ((st = plf_lsd_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
+  plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
+  plf_orb_outputs(ctx, &kps, &odesc, &kcnt, &mk);
+  plf_keyline* kls; int* lcnt; int ml;
+  plf_lsd_outputs(ctx, &kls, &lcnt, &ml);
+  if ((st = plf_launch_blur5_sobel(ctx, s->imgs, w, A, w, h, 2 * B, s->lbd_grad, A))) return st;
+  if ((st = plf_launch_lbd(ctx, s->lbd_grad, A, w, h, 2 * B, kls, lcnt, Ln, s->ldesc_raw, nullptr))) return st;
+  // --- stereo association
+  PLF_CUDA(ctx, cudaMemsetAsync(s->mcount, 0, (size_t)B * 4 * sizeof(int), cs));
+  if ((st = plf_launch_knn2(ctx, s->knn_stereo, 4 * B, std::max(K, Ln)))) return st;
+  if ((st = plf_launch_nnr(ctx, s->nnr_stereo, 2 * B, std::max(K, Ln)))) return st;
+  StereoPrm sp = {P.max_dist_epip, P.min_disp, P.line_horiz_th, P.stereo_overlap_th, P.ls_min_disp_ratio,
+                  ctx->cam.fx, ctx->cam.fy, ctx->cam.cx, ctx->cam.cy, ctx->cam.b};
+  k_stereo_points<<<B, 1024, 0, cs>>>(kps, odesc, kcnt, K, s->m12, 4 * K, sp, s->fs, 1);
+  PLF_LAUNCH_CHECK(ctx);
+  k_stereo_lines<<<B, 1024, 0, cs>>>(kls, s->ldesc_raw, lcnt, Ln, s->m12 + K, 4 * K, sp, s->fs, 1);
+  PLF_LAUNCH_CHECK(ctx);
+  // --- frame-to-frame tracking + pose (pair k: prev slot k, curr slot k+1; k = 0 uses the carried frame)
+  if ((st = plf_launch_knn2(ctx, s->knn_f2f, 4 * B, std::max(K, Ln)))) return st;
+  if ((st = plf_launch_nnr(ctx, s->nnr_f2f, 2 * B, std::max(K, Ln)))) return st;
+  k_f2f_build<<<B, 1024, 0, cs>>>(s->fs, 0, K, Ln, s->m12 + 2 * K, s->m12 + 3 * K, 4 * K, s->gnP, s->gnObs, s->gnInlP, s->gnNp,
+                                  s->gn_sP, s->gn_eP, s->gn_le, s->gnInlL, s->gnNl);
+  PLF_LAUNCH_CHECK(ctx);
+  if ((st = plf_launch_gn(ctx, s->gn_probs, B, plf_gn_opts_from_params(P)))) return st;
+  k_finalize<<<(B + 127) / 128, 128, 0, cs>>>(s->gn_out, s->gnNp, s->gnNl, kcnt, lcnt, s->fs, 1, P.min_features,
+                                               s->has_prev ? 0 : 1, B, s->results);
+  PLF_LAUNCH_CHECK(ctx);
+  // carry the last frame
+  if ((st = copy_slot(ctx, s, B, 0))) return st;
+  s->has_prev = true;
+  return PLF_OK;
+}
+
+plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out) {
+  if (!ctx || !ctx->pipe || !out || B < 1 || B > ctx->limits.max_batch)
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_download: bad arguments");
+  PipeState* s = ctx->pipe;
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->h_results, s->results, sizeof(plf_frame_result) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  memcpy(out, s->h_results, sizeof(plf_frame_result) * B);
+  return PLF_OK;
+}
+
+plf_status plf_process_batch(plf_ctx* ctx, int B, const uint8_t* left, const uint8_t* right, int stride,
+                             plf_frame_result* out) {
+  plf_status st = plf_batch_upload(ctx, B, left, right, stride);
+  if (st) return st;
+  if ((st = plf_batch_run(ctx, B))) return st;
+  return plf_batch_download(ctx, B, out);
+}
+
+// Copies the stereo-valid features of frame k of the last batch to host arrays (any pointer may be NULL).
+plf_status plf_get_frame(plf_ctx* ctx, int k, plf_frame_view* v) {
+  if (!ctx || !ctx->pipe || !v || k < 0 || k >= ctx->limits.max_batch)
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_get_frame: bad arguments");
+  PipeState* s = ctx->pipe;
+  FrameSlots& f = s->fs;
+  const int slot = k + 1;
+  const size_t K = s->max_kp, Ln = s->max_ln;
+  cudaStream_t cs = ctx->stream;
+  int np = 0, nl = 0;
+  PLF_CUDA(ctx, cudaMemcpyAsync(&np, f.pt_count + slot, 4, cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&nl, f.ls_count + slot, 4, cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaStreamSynchronize(cs));
+  v->n_pt = np; v->n_ls = nl;
+  if (np > v->cap_pt || nl > v->cap_ls)
+    return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_get_frame: %d points / %d lines exceed the view capacity", np, nl);
+#define GET(dst, src, per, n, base) if ((dst) && (n) > 0) PLF_CUDA(ctx, cudaMemcpyAsync((dst), (const char*)(src) + (size_t)slot * (base) * (per), (size_t)(n) * (per), cudaMemcpyDeviceToHost, cs))
+  GET(v->pt_pl, f.pt_pl, 16, np, K); GET(v->pt_disp, f.pt_disp, 8, np, K); GET(v->pt_P, f.pt_P, 24, np, K);
+  GET(v->pt_octave, f.pt_octave, 4, np, K); GET(v->pdesc, f.pdesc, 32, np, K);
+  GET(v->ls_spl, f.ls_spl, 16, nl, Ln); GET(v->ls_epl, f.ls_epl, 16, nl, Ln); GET(v->ls_sdisp, f.ls_sdisp, 8, nl, Ln);
+  GET(v->ls_edisp, f.ls_edisp, 8, nl, Ln); GET(v->ls_sP, f.ls_sP, 24, nl, Ln); GET(v->ls_eP, f.ls_eP, 24, nl, Ln);
+  GET(v->ls_le, f.ls_le, 24, nl, Ln); GET(v->ls_angle, f.ls_angle, 4, nl, Ln); GET(v->ldesc, f.ldesc, 32, nl, Ln);
+#undef GET
+  PLF_CUDA(ctx, cudaStreamSynchronize(cs));
+  return PLF_OK;
+}
+
+}  // extern "C"

@@ -64,6 +64,25 @@ class plf_pose_result(C.Structure):
                 ("n_inliers_pt", C.c_int), ("n_inliers_ls", C.c_int)]
 
 
+class plf_frame_result(C.Structure):
+    _fields_ = [("DT", C.c_double * 16), ("DT_cov", C.c_double * 36), ("err", C.c_double), ("status", C.c_int),
+                ("n_kp_l", C.c_int), ("n_kp_r", C.c_int), ("n_lines_l", C.c_int), ("n_lines_r", C.c_int),
+                ("n_stereo_pt", C.c_int), ("n_stereo_ls", C.c_int), ("n_matched_pt", C.c_int),
+                ("n_matched_ls", C.c_int), ("n_inliers_pt", C.c_int), ("n_inliers_ls", C.c_int),
+                ("iters1", C.c_int), ("iters2", C.c_int)]
+
+
+class plf_frame_view(C.Structure):
+    _fields_ = [("cap_pt", C.c_int), ("cap_ls", C.c_int), ("n_pt", C.c_int), ("n_ls", C.c_int),
+                ("pt_pl", C.c_void_p), ("pt_disp", C.c_void_p), ("pt_P", C.c_void_p), ("pt_octave", C.c_void_p),
+                ("pdesc", C.c_void_p), ("ls_spl", C.c_void_p), ("ls_epl", C.c_void_p), ("ls_sdisp", C.c_void_p),
+                ("ls_edisp", C.c_void_p), ("ls_sP", C.c_void_p), ("ls_eP", C.c_void_p), ("ls_le", C.c_void_p),
+                ("ls_angle", C.c_void_p), ("ldesc", C.c_void_p)]
+
+
+RESULT_FIELDS = ["status", "n_kp_l", "n_kp_r", "n_lines_l", "n_lines_r", "n_stereo_pt", "n_stereo_ls", "n_matched_pt",
+                 "n_matched_ls", "n_inliers_pt", "n_inliers_ls", "iters1", "iters2"]
+
 KEYLINE_DTYPE = np.dtype([
     ("angle", np.float32), ("class_id", np.int32), ("octave", np.int32),
     ("ptx", np.float32), ("pty", np.float32), ("response", np.float32), ("size", np.float32),
@@ -95,6 +114,8 @@ def load_library() -> C.CDLL:
     lib.plf_stream.argtypes = [C.c_void_p]
     lib.plf_destroy.restype = None
     lib.plf_destroy.argtypes = [C.c_void_p]
+    lib.plf_batch_device_images.restype = C.c_void_p
+    lib.plf_batch_device_images.argtypes = [C.c_void_p]
     lib.plf_default_params.restype = None
     lib.plf_default_limits.restype = None
     _lib = lib
@@ -311,3 +332,76 @@ class Frontend:
         st = self.lib.plf_debug_sincosf(self._ctx, _ptr(x, C.c_float), _ptr(s, C.c_float), _ptr(c, C.c_float), len(x))
         self._check(st, "plf_debug_sincosf")
         return s, c
+
+    # -- batched front-end -----------------------------------------------------------------------
+    def reset_sequence(self):
+        self._check(self.lib.plf_reset_sequence(self._ctx), "plf_reset_sequence")
+
+    @staticmethod
+    def _result_dicts(res, B):
+        out = []
+        for k in range(B):
+            r = res[k]
+            d = {f: getattr(r, f) for f in RESULT_FIELDS}
+            d["DT"] = np.array(r.DT).reshape(4, 4)
+            d["DT_cov"] = np.array(r.DT_cov).reshape(6, 6)
+            d["err"] = r.err
+            out.append(d)
+        return out
+
+    def _stack(self, left, right):
+        left = np.ascontiguousarray(left, np.uint8); right = np.ascontiguousarray(right, np.uint8)
+        if left.ndim == 2:
+            left, right = left[None], right[None]
+        assert left.shape == right.shape and left.shape[1:] == (self.camera.height, self.camera.width)
+        return left, right
+
+    def process_batch(self, left, right):
+        """B x (insertStereoPair + optimizePose): left/right uint8 [B,H,W] host arrays -> list of result dicts."""
+        left, right = self._stack(left, right)
+        B = left.shape[0]
+        res = (plf_frame_result * B)()
+        st = self.lib.plf_process_batch(self._ctx, B, _ptr(left, C.c_uint8), _ptr(right, C.c_uint8),
+                                        self.camera.width, res)
+        self._check(st, "plf_process_batch")
+        return self._result_dicts(res, B)
+
+    def batch_upload(self, left, right):
+        left, right = self._stack(left, right)
+        self._check(self.lib.plf_batch_upload(self._ctx, left.shape[0], _ptr(left, C.c_uint8), _ptr(right, C.c_uint8),
+                                              self.camera.width), "plf_batch_upload")
+        return left.shape[0]
+
+    def batch_upload_raw(self, B, left_ptr, right_ptr):
+        """Upload from raw host addresses (e.g. pinned memory)."""
+        self._check(self.lib.plf_batch_upload(self._ctx, int(B), C.c_void_p(left_ptr), C.c_void_p(right_ptr),
+                                              self.camera.width), "plf_batch_upload")
+
+    def batch_run(self, B):
+        self._check(self.lib.plf_batch_run(self._ctx, int(B)), "plf_batch_run")
+
+    def batch_download(self, B):
+        res = (plf_frame_result * B)()
+        self._check(self.lib.plf_batch_download(self._ctx, int(B), res), "plf_batch_download")
+        return self._result_dicts(res, B)
+
+    @property
+    def device_images(self) -> int:
+        return int(self.lib.plf_batch_device_images(self._ctx) or 0)
+
+    def get_frame(self, k):
+        """Stereo-valid features of frame k of the last batch (dict of numpy arrays)."""
+        K, Ln = self.limits.max_keypoints, self.limits.max_lines
+        a = dict(pt_pl=np.zeros((K, 2)), pt_disp=np.zeros(K), pt_P=np.zeros((K, 3)), pt_octave=np.zeros(K, np.int32),
+                 pdesc=np.zeros((K, 32), np.uint8), ls_spl=np.zeros((Ln, 2)), ls_epl=np.zeros((Ln, 2)),
+                 ls_sdisp=np.zeros(Ln), ls_edisp=np.zeros(Ln), ls_sP=np.zeros((Ln, 3)), ls_eP=np.zeros((Ln, 3)),
+                 ls_le=np.zeros((Ln, 3)), ls_angle=np.zeros(Ln, np.float32), ldesc=np.zeros((Ln, 32), np.uint8))
+        v = plf_frame_view(cap_pt=K, cap_ls=Ln)
+        for name, arr in a.items():
+            setattr(v, name, arr.ctypes.data)
+        self._check(self.lib.plf_get_frame(self._ctx, int(k), C.byref(v)), "plf_get_frame")
+        out = {}
+        for name, arr in a.items():
+            n = v.n_pt if name.startswith("pt_") or name == "pdesc" else v.n_ls
+            out[name] = arr[:n].copy()
+        return out

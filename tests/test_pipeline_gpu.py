@@ -1,0 +1,89 @@
+"""GPU parity tests for the batched front-end (stereo association, f2f tracking, pose) through the C ABI, against
+the oracle pipeline (oracle/frontend.py: C restatements of ORB / LSD / LBD / GN + numpy matcher)."""
+import numpy as np
+import pytest
+
+import plslam_b200 as plf
+from oracle import clib, synth
+from oracle import frontend as ofe
+
+pytestmark = pytest.mark.gpu
+POSE_REL_TOL = 1e-4   # north_star: pose within 1e-4 relative on the se(3) log
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-9)
+
+
+def check_frame(fg, fo: ofe.Frame):
+    assert len(fg["pt_pl"]) == len(fo.pt_pl) and len(fg["ls_spl"]) == len(fo.ls_spl)
+    assert np.array_equal(fg["pt_pl"], fo.pt_pl) and np.array_equal(fg["pt_disp"], fo.pt_disp)
+    assert np.array_equal(fg["pt_P"], fo.pt_P) and np.array_equal(fg["pt_octave"], fo.pt_octave)
+    assert np.array_equal(fg["pdesc"], fo.pdesc)
+    for k, v in (("ls_spl", fo.ls_spl), ("ls_epl", fo.ls_epl), ("ls_sdisp", fo.ls_sdisp), ("ls_edisp", fo.ls_edisp),
+                 ("ls_sP", fo.ls_sP), ("ls_eP", fo.ls_eP), ("ls_le", fo.ls_le), ("ls_angle", fo.ls_angle), ("ldesc", fo.ldesc)):
+        assert np.array_equal(fg[k], v), k
+
+
+def run_both(cam, frames, B, **prm_over):
+    prm = dict(ofe.DEFAULTS, **prm_over)
+    ref = ofe.run_sequence(cam, [(a, b) for a, b, _ in frames], prm)
+    lim = plf.default_limits(); lim.max_batch = B
+    kw = {k: v for k, v in prm_over.items() if k in ("orb_nfeatures", "lsd_nfeatures", "max_iters", "max_iters_ref", "min_features")}
+    got, feats = [], []
+    with plf.Frontend(camera=cam, limits=lim, **kw) as fe:
+        for s0 in range(0, len(frames), B):
+            chunk = frames[s0:s0 + B]
+            res = fe.process_batch(np.stack([c[0] for c in chunk]), np.stack([c[1] for c in chunk]))
+            got += res
+            feats += [fe.get_frame(k) for k in range(len(chunk))]
+    return ref, got, feats
+
+
+def compare(ref, got, feats):
+    for k, (r, g) in enumerate(zip(ref, got)):
+        assert g["status"] == r["status"], k
+        assert (g["n_stereo_pt"], g["n_stereo_ls"]) == (r["n_pt"], r["n_ls"]), k
+        check_frame(feats[k], r["frame"])
+        if r["status"] == 0:
+            assert g["n_matched_pt"] == len(r["res"]["inlier_pt"]) and g["n_matched_ls"] == len(r["res"]["inlier_ls"])
+            assert (g["n_inliers_pt"], g["n_inliers_ls"]) == r["res"]["n_inliers"]
+            assert rel(clib.logmap_se3(g["DT"]), clib.logmap_se3(r["DT"])) < POSE_REL_TOL
+        else:
+            assert np.array_equal(g["DT"], np.eye(4))
+
+
+def test_pipeline_kitti_shape_stream(built):
+    """BASELINE config 2 shape: 1242x375, ~1500 ORB + 200 lines, tracking a planted trajectory; batches of 3."""
+    cam = plf.KITTI_CAMERA
+    frames = list(synth.stream(cam, 6))
+    ref, got, feats = run_both(cam, frames, 3, orb_nfeatures=1500, lsd_nfeatures=200)
+    compare(ref, got, feats)
+    # the planted motion is recovered (ATE-style check on the chained trajectory)
+    T = np.eye(4)
+    for g in got:
+        T = T @ g["DT"]
+    T_true = np.linalg.inv(frames[0][2]) @ frames[-1][2]
+    assert np.linalg.norm(T[:3, 3] - T_true[:3, 3]) < 0.05 * np.linalg.norm(T_true[:3, 3])
+
+
+def test_pipeline_euroc_shape_stream(built):
+    """BASELINE config 3 shape: 752x480 full front-end + pose refine (max_iters 5 / 10); one frame per call."""
+    cam = plf.EUROC_CAMERA
+    world = synth.World(seed=8, length=40.0, n_quads=220, n_segs=120, half_width=5.0, half_height=3.0)
+    frames = list(synth.stream(cam, 4, world=world, seed=43, step=0.08, yaw_deg=0.8))
+    ref, got, feats = run_both(cam, frames, 1, orb_nfeatures=1200, lsd_nfeatures=300)
+    compare(ref, got, feats)
+
+
+def test_pipeline_reset_and_too_few_features(built):
+    cam = dict(plf.KITTI_CAMERA, width=320, height=200, cx=160.0, cy=100.0)
+    lim = plf.default_limits(); lim.max_batch = 2
+    flat = np.full((2, 200, 320), 100, np.uint8)
+    with plf.Frontend(camera=cam, limits=lim, orb_nlevels=2) as fe:
+        r = fe.process_batch(flat, flat)
+        assert r[0]["status"] == 2 and r[1]["status"] == 1          # first frame; then nothing to track
+        assert np.array_equal(r[1]["DT"], np.eye(4)) and r[1]["n_stereo_pt"] == 0
+        fe.reset_sequence()
+        r = fe.process_batch(flat[:1], flat[:1])
+        assert r[0]["status"] == 2
