@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py — stereo-pairs/sec of the B200-native stereo point+line front-end (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N>1: launched by torch.distributed.run, one rank per GPU)
+  python bench.py --impl reference ...                     (the CPU path timed on the host cores; rank 0 only)
+
+One "step" = one pass of the hot path (ORB + LSD/LBD extraction of both images, L/R stereo association,
+frame-to-frame tracking, robust Gauss-Newton pose) over one batch of B consecutive synthetic stereo pairs of a
+KITTI-00-shape stream (BASELINE.json configs[1]).  `value` = pairs/s with the batch already resident in HBM
+(device time, CUDA events on the library's stream, max over ranks); `e2e` = the same metric through the
+reference-facing C-ABI call plf_process_batch with pinned HOST buffers (H2D of the images and D2H of the per-frame
+results inside the timed region).  Rank 0 prints ONE JSON line.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "pl-slam_b200"))
+
+METRIC = "stereo_pairs_per_sec"
+UNIT = "pairs/s"
+CAM = dict(width=1242, height=375, fx=718.856, fy=718.856, cx=607.1928, cy=185.2157, b=0.537165719)  # kitti00-02.yaml:2-10
+PRM = dict(orb_nfeatures=1500, lsd_nfeatures=200)  # BASELINE.json configs[1]: ~1500 ORB + 200 lines per frame
+WORKLOAD = "kitti00_shape_synthetic_stream_1242x375_orb1500_lsd200_tracking"
+
+
+def algorithmic_bytes_per_pair(w, h, s=1.2, n_kp=1500, m_lines=200, lbar=90):
+    """BYTES_PER_PAIR = 2*(ORB + LSD + LBD) + MATCH."""
+    A0 = w * h
+    A = [round(w / 1.2 ** k) * round(h / 1.2 ** k) for k in range(4)]
+    S = sum(A)
+    Ns = round(w * s) * round(h * s)
+    orb = A0 + 2 * sum(A[1:]) + 2 * S + 56 * n_kp
+    lsd = A0 + 2 * Ns + 8 * Ns + 8 * Ns + 6 * Ns + 16 * m_lines
+    lbd = A0 + 4 * A0 + min(4 * A0, 63 * lbar * 4 * m_lines) + 32 * m_lines
+    match = 2 * 32 * n_kp + 4 * n_kp + 2 * 32 * m_lines + 4 * m_lines
+    return dict(orb=orb, lsd=lsd, lbd=lbd, match=match, pair=2 * (orb + lsd + lbd) + match, Ns=Ns, A0=A0, S=S, A=A)
+
+
+# algorithmic bytes per IMAGE (or per pair where noted) of each kernel, for the per-kernel GB/s table
+def kernel_bytes(name, ab, n_kp, m_lines):
+    A0, Ns, A, S = ab["A0"], ab["Ns"], ab["A"], ab["S"]
+    t = {
+        "orb.k_resize_exact": sum(A[:3]) + sum(A[1:]),          # read level k-1, write level k
+        "orb.k_fast_nms": S + 8 * n_kp,                           # read the pyramid once, candidates out
+        "orb.k_select_sort": 8 * n_kp + 28 * n_kp,
+        "orb.k_ic_angle": 961 * n_kp,
+        "orb.k_orb_blur7": 2 * S,                                 # read + write every level
+        "orb.k_rbrief": 512 * n_kp + 32 * n_kp,
+        "lsd.k_blur_q8": 2 * A0,
+        "lsd.k_resize_exact": A0 + Ns,
+        "lsd.k_lsd_grad": Ns + 8 * Ns,                            # read scaled u8, write (gx,gy) + angle
+        "lsd.k_lsd_rowhist": 8 * Ns + 2 * Ns,
+        "lsd.k_lsd_binscan": 2 * 4 * 1024 * round(ab["Ns"] ** 0.5),
+        "lsd.k_lsd_scatter": 6 * Ns + 4 * Ns,
+        "lsd.k_lsd_grow": 6 * Ns,                                 # read angle + r/w used mask
+        "lsd.k_lsd_rects": 3 * 8 * Ns // 4,
+        "lsd.k_keylines": 16 * 1200 + 68 * 1200,
+        "lbd.k_blur5_sobel": A0 + 4 * A0,
+        "lbd.k_lbd": 63 * 90 * 4 * m_lines + 32 * m_lines,
+    }
+    return t.get(name)
+
+
+def render_pool(cam, n, seed):
+    from oracle import synth
+    world = synth.World(seed=7 + seed)
+    return [(L, R) for (L, R, _) in synth.stream(cam, n, world=world, seed=42 + seed)]
+
+
+def fill_batch(pool, B, dstL, dstR):
+    """Ping-pong over the rendered frames so that consecutive pairs are always neighbours on the trajectory."""
+    n = len(pool)
+    period = list(range(n)) + list(range(n - 2, 0, -1)) if n > 2 else list(range(n))
+    for k in range(B):
+        L, R = pool[period[k % len(period)]]
+        dstL[k] = L
+        dstR[k] = R
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [x.strip() for x in ln.split(",")]
+            if len(p) < 7:
+                continue
+            try:
+                sm.append(float(p[0])); mx.append(float(p[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return dict(sm_mhz=float(np.median(sm)) if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline_run(n_frames, threads=None):
+    from oracle import baseline
+    pool = render_pool(CAM, n_frames, seed=0)
+    t0 = time.perf_counter()
+    res, cores = baseline.run(CAM, pool, PRM, threads=threads)
+    dt = time.perf_counter() - t0
+    return len(pool) / dt, cores, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU path (cv2 ORB / LSD / BFMatcher + C restatements of LBD / GN) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import baseline
+    cores = os.cpu_count() or 1
+    n = max(8, min(4 * cores, 96))         # bounded sample per step
+    pool = render_pool(CAM, min(n, 24), seed=0)
+    pairs = [pool[i % len(pool)] for i in range(n)]
+    for _ in range(args.warmup):
+        baseline.run(CAM, pairs[:max(cores, 8)], PRM)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        baseline.run(CAM, pairs, PRM)
+    dt = time.perf_counter() - t0
+    v = n * args.steps / dt
+    line = dict(metric=METRIC, value=v, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8/f32/f64",
+                data="synthetic", impl="reference",
+                config=dict(workload=WORKLOAD, pairs_per_step=n, **PRM),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
+                                  sample=f"{n} pairs/step x {args.steps} steps: cv2 4.13 ORB+LSD+BFMatcher + C LBD/GN, {cores} worker processes"),
+                e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLF_BENCH_BATCH", "256")))
+    ap.add_argument("--pool", type=int, default=24, help="distinct rendered frames (ping-ponged to fill a batch)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch
+    import plslam_b200 as plf
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    B = args.batch
+    w, h = CAM["width"], CAM["height"]
+    lim = plf.default_limits()
+    lim.max_batch = B; lim.max_keypoints = 4096; lim.max_segments = 8192; lim.max_lines = 1024
+    fe = plf.Frontend(camera=CAM, limits=lim, device=local_rank, **PRM)
+    pool = render_pool(CAM, args.pool, seed=rank)            # rank r tracks its own sequence (BASELINE config 4)
+    hostL = torch.empty((B, h, w), dtype=torch.uint8, pin_memory=True)
+    hostR = torch.empty((B, h, w), dtype=torch.uint8, pin_memory=True)
+    fill_batch(pool, B, hostL.numpy(), hostR.numpy())
+    ext = torch.cuda.ExternalStream(fe.stream, device=torch.device("cuda", local_rank))
+    pose_buf = torch.zeros((B, 16), dtype=torch.float64, device="cuda")
+    gather_buf = torch.zeros((world * B, 16), dtype=torch.float64, device="cuda") if world > 1 else None
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def gather_poses(results):
+        """The path's only exchange: one NCCL all-gather of the B poses per rank."""
+        if dist is None:
+            return
+        pose_buf.copy_(torch.from_numpy(np.stack([r["DT"].reshape(16) for r in results])), non_blocking=True)
+        dist.all_gather_into_tensor(gather_buf, pose_buf)
+
+    # ---- warm-up through the public call (also builds every lazily allocated buffer)
+    last = None
+    for _ in range(args.warmup):
+        last = fe.process_batch(hostL.numpy(), hostR.numpy())
+        gather_poses(last)
+    barrier()
+    stats = {k: float(np.mean([r[k] for r in last[1:]])) for k in ("n_kp_l", "n_lines_l", "n_stereo_pt", "n_stereo_ls", "n_matched_pt", "n_matched_ls", "n_inliers_pt", "n_inliers_ls")}
+    tracked = float(np.mean([r["status"] == 0 for r in last[1:]]))
+
+    # ---- `value`: batch resident in HBM, K x plf_batch_run, device time on the library's stream
+    fe.batch_upload_raw(B, hostL.data_ptr(), hostR.data_ptr())
+    fe.sync()
+    sampler = ClockSampler(local_rank); sampler.start()
+    l0 = fe.launches
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.cuda.stream(ext):
+        e0.record(ext)
+        for _ in range(args.steps):
+            fe.batch_run(B)
+        e1.record(ext)
+    barrier()
+    dev_ms = e0.elapsed_time(e1)
+    launches = fe.launches - l0
+    clocks = sampler.stop()
+
+    # ---- `e2e`: pinned host buffers -> plf_batch_upload + run + download (+ the pose gather), K steps
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fe.batch_upload_raw(B, hostL.data_ptr(), hostR.data_ptr())
+        fe.batch_run(B)
+        res = fe.batch_download(B)
+        gather_poses(res)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- per-kernel device times (one extra profiled pass, outside both timed regions)
+    fe.profile_enable(True)
+    fe.batch_run(B)
+    stages = [(n, ms) for n, ms in fe.profile_read() if n != "start"]
+    fe.profile_enable(False)
+
+    t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(t[0]), float(t[1])
+    if rank == 0:
+        total_pairs = world * B * args.steps
+        value = total_pairs / (dev_ms * 1e-3)
+        e2e_v = total_pairs / (e2e_ms * 1e-3)
+        peak, peak_src = measured_peaks()
+        ab = algorithmic_bytes_per_pair(w, h, 1.2, int(round(stats["n_kp_l"])), int(round(stats["n_lines_l"])))
+        step_ms = sum(ms for _, ms in stages)
+        ktab = []
+        for name, ms in stages:
+            kb = kernel_bytes(name, ab, stats["n_kp_l"], stats["n_lines_l"])
+            gbs = (kb * 2 * B / (ms * 1e-3) / 1e9) if (kb and ms > 0) else None
+            ktab.append(dict(kernel=name, ms=round(ms, 4), share=round(ms / step_ms, 4) if step_ms else None,
+                             algo_gbs=round(gbs, 1) if gbs else None, frac_hbm=round(gbs / peak, 4) if gbs else None))
+        dom = max(ktab, key=lambda r: r["ms"]) if ktab else None
+        roof = None
+        if dom and dom["algo_gbs"]:
+            roof = dict(kernel=dom["kernel"], bound="hbm", achieved=dom["algo_gbs"], peak=peak, unit="GB/s",
+                        frac=round(dom["algo_gbs"] / peak, 5), traffic=None, peak_source=peak_src,
+                        note=("share of step %.0f%%; region growing is a sequential greedy partition per image: latency-bound, "
+                              "reported against HBM for completeness" % (100 * dom["share"])) if "grow" in dom["kernel"] else None)
+        whole = dict(algorithmic_bytes_per_pair=ab["pair"], achieved_gbs=round(ab["pair"] * value / 1e9, 1),
+                     frac_hbm=round(ab["pair"] * value / 1e9 / peak, 4))
+        line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype="u8/f32/f64", data="synthetic",
+                    config=dict(workload=WORKLOAD, pairs_per_step_per_gpu=B, image=[w, h], **PRM,
+                                rendered_frames=args.pool,
+                                l2="per-step working set %.0f MB (images + pyramids + LSD maps) >> 126 MB L2" % (B * 36.0),
+                                features_per_frame=stats, tracked_fraction=tracked),
+                    e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=2 * B * w * h,
+                             d2h_bytes_per_step=B * ctypes.sizeof(plf.plf_frame_result), ms_per_step=e2e_ms / args.steps),
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, pipeline_vs_hbm=whole, kernels=ktab)
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = max(8, min(2 * cores, 64))
+            v, c, dt = cpu_baseline_run(min(n, 24) if n <= 24 else 24, None)
+            line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=c, kind="port",
+                                        sample="%d rendered pairs of the same stream, one pass (%.1f s): cv2 4.13 ORB+LSD+BFMatcher + C LBD/GN, %d worker processes" % (min(n, 24), dt, c))
+        print(json.dumps(line))
+    fe.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -98,6 +98,13 @@ long long plf_launch_count(const plf_ctx* ctx);
 void* plf_stream(const plf_ctx* ctx);
 plf_status plf_sync(plf_ctx* ctx);
 
+/* Per-kernel device timing of plf_batch_run (CUDA events on plf_stream; replaces the reference's only
+ * instrumentation, the ms Timer around insertStereoPair+optimizePose, app/plslam_dataset.cpp:126-132).
+ * plf_profile_read: after a run with profiling on, ms[i] = device time of stage i, names_buf = ';'-separated
+ * stage names; *n = number of stages. */
+plf_status plf_profile_enable(plf_ctx* ctx, int on);
+plf_status plf_profile_read(plf_ctx* ctx, char* names_buf, int buf_len, float* ms, int cap, int* n);
+
 /* ------------------------------------------------------------------------------------------------
  * Descriptor matching
  * ---------------------------------------------------------------------------------------------- */

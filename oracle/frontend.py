@@ -90,8 +90,8 @@ class Frame:
     ldesc: np.ndarray = field(default_factory=lambda: np.zeros((0, 32), np.uint8))
 
 
-def stereo_points(cam, kp_l, desc_l, kp_r, desc_r, prm):
-    m12, _ = om.match(desc_l, desc_r, prm["min_ratio_12_p"], prm["best_lr_matches"])
+def stereo_points(cam, kp_l, desc_l, kp_r, desc_r, prm, match_fn=None):
+    m12, _ = (match_fn or om.match)(desc_l, desc_r, prm["min_ratio_12_p"], prm["best_lr_matches"])
     pl, disp, P, octv, rows = [], [], [], [], []
     for i, j in enumerate(m12):
         if j < 0:
@@ -107,8 +107,8 @@ def stereo_points(cam, kp_l, desc_l, kp_r, desc_r, prm):
             np.array(octv, np.int32), desc_l[rows].reshape(n, 32))
 
 
-def stereo_lines(cam, kl_l, desc_l, kl_r, desc_r, prm):
-    m12, _ = om.match(desc_l, desc_r, prm["min_ratio_12_l"], prm["best_lr_matches"])
+def stereo_lines(cam, kl_l, desc_l, kl_r, desc_r, prm, match_fn=None):
+    m12, _ = (match_fn or om.match)(desc_l, desc_r, prm["min_ratio_12_l"], prm["best_lr_matches"])
     out = dict(spl=[], epl=[], sdisp=[], edisp=[], sP=[], eP=[], le=[], angle=[], rows=[])
     for i, j in enumerate(m12):
         if j < 0:
@@ -141,18 +141,23 @@ def stereo_lines(cam, kl_l, desc_l, kl_r, desc_r, prm):
             np.array(out["angle"], np.float32), desc_l[out["rows"]].reshape(n, 32))
 
 
-def extract_stereo(cam, left, right, prm, orb_fn=None, lines_fn=None):
+def extract_stereo(cam, left, right, prm, orb_fn=None, lines_fn=None, match_fn=None, pool=None):
     """StereoFrame::extractStereoFeatures.  orb_fn / lines_fn default to the C restatements (bit-identical to cv2)."""
     if orb_fn is None:
         orb_fn = lambda im: _orb_c(im, prm)
     if lines_fn is None:
         lines_fn = lambda im: detect_lines(im, prm["lsd_nfeatures"], prm["min_line_length"])
-    kp_l, d_l = orb_fn(left); kp_r, d_r = orb_fn(right)
-    kl_l, ld_l = lines_fn(left); kl_r, ld_r = lines_fn(right)
+    if pool is not None:   # lr_in_parallel / pl_in_parallel (config_euroc.yaml:14-15): 4 concurrent tasks
+        fa, fb, fc, fd = (pool.submit(orb_fn, left), pool.submit(orb_fn, right), pool.submit(lines_fn, left),
+                          pool.submit(lines_fn, right))
+        (kp_l, d_l), (kp_r, d_r), (kl_l, ld_l), (kl_r, ld_r) = fa.result(), fb.result(), fc.result(), fd.result()
+    else:
+        kp_l, d_l = orb_fn(left); kp_r, d_r = orb_fn(right)
+        kl_l, ld_l = lines_fn(left); kl_r, ld_r = lines_fn(right)
     f = Frame()
-    f.pt_pl, f.pt_disp, f.pt_P, f.pt_octave, f.pdesc = stereo_points(cam, kp_l, d_l, kp_r, d_r, prm)
+    f.pt_pl, f.pt_disp, f.pt_P, f.pt_octave, f.pdesc = stereo_points(cam, kp_l, d_l, kp_r, d_r, prm, match_fn)
     (f.ls_spl, f.ls_epl, f.ls_sdisp, f.ls_edisp, f.ls_sP, f.ls_eP, f.ls_le, f.ls_angle, f.ldesc) = \
-        stereo_lines(cam, kl_l, ld_l, kl_r, ld_r, prm)
+        stereo_lines(cam, kl_l, ld_l, kl_r, ld_r, prm, match_fn)
     return f
 
 
@@ -160,12 +165,12 @@ def _orb_c(img, prm):
     return clib.orb(img, prm["orb_nfeatures"], 1.2, prm["orb_nlevels"], 19, 31, prm["orb_fast_th"])
 
 
-def track(prev: Frame, curr: Frame, prm):
+def track(prev: Frame, curr: Frame, prm, match_fn=None):
     """f2fTracking: brute-force NNR + mutual match of the stereo-valid descriptors (A.2), building the GN rows."""
-    mp, _ = om.match(prev.pdesc, curr.pdesc, prm["min_ratio_12_p"], prm["best_lr_matches"])
+    mp, _ = (match_fn or om.match)(prev.pdesc, curr.pdesc, prm["min_ratio_12_p"], prm["best_lr_matches"])
     ip = np.nonzero(mp >= 0)[0]
     P, obs = prev.pt_P[ip], curr.pt_pl[mp[ip]]
-    ml, _ = om.match(prev.ldesc, curr.ldesc, prm["min_ratio_12_l"], prm["best_lr_matches"])
+    ml, _ = (match_fn or om.match)(prev.ldesc, curr.ldesc, prm["min_ratio_12_l"], prm["best_lr_matches"])
     il = np.nonzero(ml >= 0)[0]
     sP, eP, le = prev.ls_sP[il], prev.ls_eP[il], curr.ls_le[ml[il]]
     return dict(P=P, obs=obs, sP=sP, eP=eP, le=le, mp=mp, ml=ml)
@@ -182,16 +187,16 @@ def optimize_pose(cam, tr, prm):
     return clib.inverse_se3(r["T"]), r, 0
 
 
-def run_sequence(cam, pairs, prm=None, orb_fn=None, lines_fn=None):
+def run_sequence(cam, pairs, prm=None, orb_fn=None, lines_fn=None, match_fn=None, pool=None, frames=None):
     """The hot loop of app/plslam_dataset.cpp:111-163 without keyframe hand-off: returns per-frame DT (4x4), Tfw."""
     prm = dict(DEFAULTS, **(prm or {}))
     prev, Tfw, out = None, np.eye(4), []
-    for (L, R) in pairs:
-        cur = extract_stereo(cam, L, R, prm, orb_fn, lines_fn)
+    for idx, (L, R) in enumerate(pairs):
+        cur = frames[idx] if frames is not None else extract_stereo(cam, L, R, prm, orb_fn, lines_fn, match_fn, pool)
         if prev is None:
             DT, status, res = np.eye(4), 2, None      # initialize(): first frame
         else:
-            tr = track(prev, cur, prm)
+            tr = track(prev, cur, prm, match_fn)
             DT, res, status = optimize_pose(cam, tr, prm)
         Tfw = Tfw @ DT
         out.append(dict(DT=DT, Tfw=Tfw.copy(), status=status, n_pt=len(cur.pt_pl), n_ls=len(cur.ls_spl), res=res, frame=cur))

@@ -685,32 +685,41 @@ plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
     dim3 gb((w + BQ_TW - 1) / BQ_TW, (h + BQ_TH - 1) / BQ_TH, nimg);
     k_blur_q8<<<gb, 256, 0, cs>>>(d_imgs, img_stride, w, w, h, s->ksize / 2, s->blur, (size_t)w * h);
     PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "lsd.k_blur_q8");
     st = plf_launch_resize_exact(ctx, s->blur, (size_t)w * h, w, h, s->scaled, As, W, H, s->rs_tab + s->rs_x_off,
                                  s->rs_tab + s->rs_y_off, nimg);
     if (st) return st;
+    plf_mark(ctx, "lsd.k_resize_exact");
     scaled = s->scaled;
     scaled_stride = As;
   }
   PLF_CUDA(ctx, cudaMemsetAsync(s->maxmag2, 0xFF, (size_t)nimg * sizeof(int), cs));  // -1
   k_lsd_grad<<<dim3((W + 255) / 256, H, nimg), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->rho, As, s->gxy, s->adeg, s->maxmag2);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "lsd.k_lsd_grad");
   // gxy/adeg/binmap/order/regpts are laid out with stride As per image
   k_lsd_rowhist<<<dim3(H - 1, nimg), 256, 0, cs>>>(s->gxy, s->adeg, As, W, H, s->n_bins, s->maxmag2, s->binmap, s->rowcnt);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "lsd.k_lsd_rowhist");
   k_lsd_binscan<<<nimg, 1024, 0, cs>>>(s->rowcnt, H, s->n_bins, s->binstart, s->nseeds);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "lsd.k_lsd_binscan");
   k_lsd_scatter<<<dim3((H - 1 + 3) / 4, nimg), 128, 0, cs>>>(s->adeg, s->binmap, As, W, H, s->n_bins, s->rowcnt, s->binstart, s->order);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "lsd.k_lsd_scatter");
   k_lsd_grow<<<nimg, 32, 0, cs>>>(s->adeg, As, W, H, s->order, s->nseeds, s->prec, s->min_reg_size, s->regpts,
                                   s->regions, s->max_regions, s->nregions, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "lsd.k_lsd_grow");
   k_lsd_rects<<<dim3((s->max_regions + 127) / 128, nimg), 128, 0, cs>>>(s->gxy, As, W, s->regpts, s->regions, s->max_regions,
                                                                         s->nregions, s->prec, s->scale, s->segs);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "lsd.k_lsd_rects");
   const double min_length = (double)ctx->params.min_line_length * (double)std::min(w, h);
   k_keylines<<<nimg, 1024, 0, cs>>>(s->segs, s->nregions, s->max_regions, w, h, min_length, ctx->params.lsd_nfeatures,
                                     s->kls_all, s->kls, s->max_lines, s->nlines, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "lsd.k_keylines");
   return PLF_OK;
 }
 

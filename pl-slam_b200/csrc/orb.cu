@@ -623,18 +623,24 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
                                          g.w[l], g.h[l], s->rs_tab + s->rs_x_off[l], s->rs_tab + s->rs_y_off[l]);
     PLF_LAUNCH_CHECK(ctx);
   }
+  plf_mark(ctx, "orb.k_resize_exact");
   const int tiles = g.tile_start[g.nlevels];
   k_fast_nms<<<dim3(tiles, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->cand, s->cand_count, s->hist,
                                                  s->overflow);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "orb.k_fast_nms");
   k_select_sort<<<nimg, 1024, 0, cs>>>(g, s->cand, s->cand_count, s->hist, s->kps, s->kp_lxy, s->kp_count, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "orb.k_select_sort");
   k_ic_angle<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->kps, s->kp_lxy, s->kp_count);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "orb.k_ic_angle");
   k_orb_blur7<<<dim3(tiles, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->blur);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "orb.k_orb_blur7");
   k_rbrief<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(s->blur, g, s->kps, s->kp_count, g_dev_pattern, s->desc);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "orb.k_rbrief");
   return PLF_OK;
 }
 

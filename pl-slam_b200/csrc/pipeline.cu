@@ -475,6 +475,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.pt_count, 0, sizeof(int), cs));
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.ls_count, 0, sizeof(int), cs));
   }
+  plf_mark(ctx, "start");
   // --- extraction over 2B images
   if ((st = plf_orb_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
   if ((st = plf_lsd_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
@@ -483,29 +484,38 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   plf_keyline* kls; int* lcnt; int ml;
   plf_lsd_outputs(ctx, &kls, &lcnt, &ml);
   if ((st = plf_launch_blur5_sobel(ctx, s->imgs, w, A, w, h, 2 * B, s->lbd_grad, A))) return st;
+  plf_mark(ctx, "lbd.k_blur5_sobel");
   if ((st = plf_launch_lbd(ctx, s->lbd_grad, A, w, h, 2 * B, kls, lcnt, Ln, s->ldesc_raw, nullptr))) return st;
+  plf_mark(ctx, "lbd.k_lbd");
   // --- stereo association
   PLF_CUDA(ctx, cudaMemsetAsync(s->mcount, 0, (size_t)B * 4 * sizeof(int), cs));
   if ((st = plf_launch_knn2(ctx, s->knn_stereo, 4 * B, std::max(K, Ln)))) return st;
+  plf_mark(ctx, "stereo.k_hamming_knn2");
   if ((st = plf_launch_nnr(ctx, s->nnr_stereo, 2 * B, std::max(K, Ln)))) return st;
+  plf_mark(ctx, "stereo.k_nnr_mutual");
   StereoPrm sp = {P.max_dist_epip, P.min_disp, P.line_horiz_th, P.stereo_overlap_th, P.ls_min_disp_ratio,
                   ctx->cam.fx, ctx->cam.fy, ctx->cam.cx, ctx->cam.cy, ctx->cam.b};
   k_stereo_points<<<B, 1024, 0, cs>>>(kps, odesc, kcnt, K, s->m12, 4 * K, sp, s->fs, 1);
   PLF_LAUNCH_CHECK(ctx);
   k_stereo_lines<<<B, 1024, 0, cs>>>(kls, s->ldesc_raw, lcnt, Ln, s->m12 + K, 4 * K, sp, s->fs, 1);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "stereo.k_stereo_points+lines");
   // --- frame-to-frame tracking + pose (pair k: prev slot k, curr slot k+1; k = 0 uses the carried frame)
   if ((st = plf_launch_knn2(ctx, s->knn_f2f, 4 * B, std::max(K, Ln)))) return st;
+  plf_mark(ctx, "f2f.k_hamming_knn2");
   if ((st = plf_launch_nnr(ctx, s->nnr_f2f, 2 * B, std::max(K, Ln)))) return st;
   k_f2f_build<<<B, 1024, 0, cs>>>(s->fs, 0, K, Ln, s->m12 + 2 * K, s->m12 + 3 * K, 4 * K, s->gnP, s->gnObs, s->gnInlP, s->gnNp,
                                   s->gn_sP, s->gn_eP, s->gn_le, s->gnInlL, s->gnNl);
   PLF_LAUNCH_CHECK(ctx);
+  plf_mark(ctx, "f2f.k_nnr_mutual+k_f2f_build");
   if ((st = plf_launch_gn(ctx, s->gn_probs, B, plf_gn_opts_from_params(P)))) return st;
+  plf_mark(ctx, "gn.k_gn_pose");
   k_finalize<<<(B + 127) / 128, 128, 0, cs>>>(s->gn_out, s->gnNp, s->gnNl, kcnt, lcnt, s->fs, 1, P.min_features,
                                                s->has_prev ? 0 : 1, B, s->results);
   PLF_LAUNCH_CHECK(ctx);
   // carry the last frame
   if ((st = copy_slot(ctx, s, B, 0))) return st;
+  plf_mark(ctx, "k_finalize+carry");
   s->has_prev = true;
   return PLF_OK;
 }

@@ -59,7 +59,53 @@ void* plf_pinned(plf_ctx* ctx, size_t bytes) {
   return ctx->pinned;
 }
 
+void plf_mark(plf_ctx* ctx, const char* name) {
+  if (!ctx->profile) return;
+  if (ctx->prof_used == ctx->prof_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    ctx->prof_ev.push_back(e);
+    ctx->prof_names.emplace_back();
+  }
+  ctx->prof_names[ctx->prof_used] = name;
+  cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream);
+  ctx->prof_used++;
+}
+
 extern "C" {
+
+plf_status plf_profile_enable(plf_ctx* ctx, int on) {
+  if (!ctx) return PLF_ERR_INVALID;
+  ctx->profile = on != 0;
+  ctx->prof_used = 0;
+  return PLF_OK;
+}
+
+// After a plf_batch_run with profiling on: per-stage device time (ms) between consecutive marks.
+// names_buf receives the stage names separated by ';'.  Resets the mark list.
+plf_status plf_profile_read(plf_ctx* ctx, char* names_buf, int buf_len, float* ms, int cap, int* n_out) {
+  if (!ctx || !n_out) return PLF_ERR_INVALID;
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  int n = 0;
+  std::string names;
+  for (size_t i = 1; i < ctx->prof_used; ++i) {
+    if (n < cap && ms) {
+      float t = 0;
+      cudaEventElapsedTime(&t, ctx->prof_ev[i - 1], ctx->prof_ev[i]);
+      ms[n] = t;
+    }
+    names += ctx->prof_names[i];
+    names += ';';
+    ++n;
+  }
+  if (names_buf && buf_len > 0) {
+    strncpy(names_buf, names.c_str(), buf_len - 1);
+    names_buf[buf_len - 1] = 0;
+  }
+  *n_out = n;
+  ctx->prof_used = 0;
+  return PLF_OK;
+}
 
 int plf_abi_version(void) { return PLF_ABI_VERSION; }
 
@@ -179,6 +225,7 @@ void plf_destroy(plf_ctx* ctx) {
   for (auto& b : ctx->scratch)
     if (b.p) cudaFree(b.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  for (auto e : ctx->prof_ev) cudaEventDestroy(e);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

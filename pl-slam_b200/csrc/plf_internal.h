@@ -42,7 +42,14 @@ struct plf_ctx {
   struct LsdState* lsd = nullptr;
   struct LbdState* lbd = nullptr;
   struct PipeState* pipe = nullptr;
+  // optional per-stage timing (plf_profile_enable): events recorded after each kernel of plf_batch_run
+  bool profile = false;
+  std::vector<cudaEvent_t> prof_ev;
+  std::vector<std::string> prof_names;
+  size_t prof_used = 0;
 };
+// Records a timing mark on ctx->stream after the work named `name` (no-op unless profiling is enabled).
+void plf_mark(plf_ctx* ctx, const char* name);
 
 plf_status plf_fail(plf_ctx* ctx, plf_status code, const char* fmt, ...);
 // Ensures scratch slot `slot` holds at least `bytes`; returns device pointer or nullptr (error set).

@@ -405,3 +405,16 @@ class Frontend:
             n = v.n_pt if name.startswith("pt_") or name == "pdesc" else v.n_ls
             out[name] = arr[:n].copy()
         return out
+
+    # -- profiling -------------------------------------------------------------------------------
+    def profile_enable(self, on=True):
+        self._check(self.lib.plf_profile_enable(self._ctx, int(bool(on))), "plf_profile_enable")
+
+    def profile_read(self):
+        """Returns [(stage name, ms)] of the batch_run calls since profiling was enabled / last read."""
+        buf = C.create_string_buffer(16384)
+        ms = (C.c_float * 1024)()
+        n = C.c_int(0)
+        self._check(self.lib.plf_profile_read(self._ctx, buf, 16384, ms, 1024, C.byref(n)), "plf_profile_read")
+        names = buf.value.decode().split(";")[:n.value]
+        return list(zip(names, [ms[i] for i in range(min(n.value, 1024))]))
