@@ -17,7 +17,9 @@ LIB       := $(LIBDIR)/libplslam_b200.so
 ORACLE_SRCS := $(wildcard oracle/*.c)
 ORACLE_LIB  := oracle/_build/liboracle.so
 
-all: $(LIB) oracle
+DEMO      := $(LIBDIR)/vo_demo
+
+all: $(LIB) oracle $(DEMO)
 
 $(OBJDIR)/%.o: pl-slam_b200/csrc/%.cu $(wildcard pl-slam_b200/csrc/*.h) $(wildcard pl-slam_b200/csrc/*.cuh) include/plslam_b200.h
 	@mkdir -p $(OBJDIR)
@@ -26,6 +28,10 @@ $(OBJDIR)/%.o: pl-slam_b200/csrc/%.cu $(wildcard pl-slam_b200/csrc/*.h) $(wildca
 $(LIB): $(OBJS)
 	@mkdir -p $(LIBDIR)
 	$(NVCC) $(ARCH) -shared -cudart static -o $@ $(OBJS)
+
+# C++ host shim demo (the reference's VO loop on the shim classes)
+$(DEMO): pl-slam_b200/cpp/vo_demo.cpp pl-slam_b200/cpp/stvo_shim.h include/plslam_b200.h $(LIB)
+	$(CXX) -O2 -std=c++17 -Wall -Iinclude -Ipl-slam_b200/cpp -o $@ pl-slam_b200/cpp/vo_demo.cpp -L$(LIBDIR) -lplslam_b200 -Wl,-rpath,'$$ORIGIN'
 
 # CPU oracle: plain C, no FMA contraction (mirrors the reference's non-FMA x86-64 build).
 oracle: $(ORACLE_LIB)

@@ -294,6 +294,21 @@ void* plf_batch_device_images(plf_ctx* ctx);
  * app/plslam_dataset.cpp:143, src/keyFrame.cpp:39-53). */
 plf_status plf_get_frame(plf_ctx* ctx, int k, plf_frame_view* view);
 
+/* Host destination for StereoFrameHandler::matched_pt / matched_ls of pair k (src/mapHandler.cpp:770-778 reads
+ * them; fields as written by the in-tree analogue :326-328,:482-487).  Any array may be NULL. */
+typedef struct plf_match_view {
+  int cap_pt, cap_ls;
+  int n_pt, n_ls;
+  double* P;          /* n_pt x 3  PointFeature::P (previous frame) */
+  double* pl_obs;     /* n_pt x 2  PointFeature::pl_obs (current frame) */
+  uint8_t* inlier_pt; /* n_pt      PointFeature::inlier after optimizePose */
+  double* sP;         /* n_ls x 3 */
+  double* eP;         /* n_ls x 3 */
+  double* le_obs;     /* n_ls x 3  LineFeature::le_obs */
+  uint8_t* inlier_ls; /* n_ls */
+} plf_match_view;
+plf_status plf_get_matches(plf_ctx* ctx, int k, plf_match_view* view);
+
 #ifdef __cplusplus
 }
 #endif

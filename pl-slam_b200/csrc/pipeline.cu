@@ -565,4 +565,28 @@ plf_status plf_get_frame(plf_ctx* ctx, int k, plf_frame_view* v) {
   return PLF_OK;
 }
 
+// Frame-to-frame correspondences of pair k of the last batch: what f2fTracking leaves in matched_pt / matched_ls
+// (P / sP,eP from the previous frame, pl_obs / le_obs from the current one, inlier flags after optimizePose).
+plf_status plf_get_matches(plf_ctx* ctx, int k, plf_match_view* v) {
+  if (!ctx || !ctx->pipe || !v || k < 0 || k >= ctx->limits.max_batch)
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_get_matches: bad arguments");
+  PipeState* s = ctx->pipe;
+  const size_t K = s->max_kp, Ln = s->max_ln;
+  cudaStream_t cs = ctx->stream;
+  int np = 0, nl = 0;
+  PLF_CUDA(ctx, cudaMemcpyAsync(&np, s->gnNp + k, 4, cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&nl, s->gnNl + k, 4, cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaStreamSynchronize(cs));
+  v->n_pt = np; v->n_ls = nl;
+  if (np > v->cap_pt || nl > v->cap_ls)
+    return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_get_matches: %d points / %d lines exceed the view capacity", np, nl);
+#define GETM(dst, src, per, n, base) if ((dst) && (n) > 0) PLF_CUDA(ctx, cudaMemcpyAsync((dst), (const char*)(src) + (size_t)k * (base) * (per), (size_t)(n) * (per), cudaMemcpyDeviceToHost, cs))
+  GETM(v->P, s->gnP, 24, np, K); GETM(v->pl_obs, s->gnObs, 16, np, K); GETM(v->inlier_pt, s->gnInlP, 1, np, K);
+  GETM(v->sP, s->gn_sP, 24, nl, Ln); GETM(v->eP, s->gn_eP, 24, nl, Ln); GETM(v->le_obs, s->gn_le, 24, nl, Ln);
+  GETM(v->inlier_ls, s->gnInlL, 1, nl, Ln);
+#undef GETM
+  PLF_CUDA(ctx, cudaStreamSynchronize(cs));
+  return PLF_OK;
+}
+
 }  // extern "C"
