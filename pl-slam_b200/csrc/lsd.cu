@@ -55,6 +55,7 @@ struct LsdState {
   uint8_t* scaled = nullptr;  // [nimg][hs*ws]
   short2* gxy = nullptr;      // [nimg][hs*ws]
   float* adeg = nullptr;      // [nimg][hs*ws]  level-line angle in degrees, LSD_NOTDEF = undefined or used
+  float2* cs = nullptr;       // [nimg][hs*ws]  (cosf, sinf) of float(angle): the region-angle increments, precomputed
   uint16_t* binmap = nullptr; // [nimg][hs*ws]
   int* maxmag2 = nullptr;     // [nimg]
   uint32_t* rowcnt = nullptr; // [nimg][hs][n_bins]
@@ -144,13 +145,15 @@ __device__ __forceinline__ float lsd_fast_atan2(float y, float x) {  // cv::fast
 
 __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int W, int H,
                                                   double rho, size_t stride, short2* __restrict__ gxy,
-                                                  float* __restrict__ adeg, int* __restrict__ maxmag2) {
+                                                  float* __restrict__ adeg, float2* __restrict__ cs,
+                                                  int* __restrict__ maxmag2) {
   const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, im = blockIdx.z;
   int mag2 = -1;
   if (x < W) {
     const size_t o = (size_t)im * stride + (size_t)y * W + x;
     short2 g = make_short2(0, 0);
     float a = LSD_NOTDEF;
+    float2 c2 = make_float2(0.f, 0.f);
     if (x < W - 1 && y < H - 1) {
       const uint8_t* r0 = img + (size_t)im * img_stride + (size_t)y * W + x;
       const uint8_t* r1 = r0 + W;
@@ -162,10 +165,15 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ im
       if (!(norm <= rho)) {
         a = lsd_fast_atan2((float)gx, (float)(-gy));
         mag2 = m2;
+        // region_grow adds cos(float(angle)), sin(float(angle)) (host libm cosf/sinf) for every accepted pixel:
+        // evaluated here, in parallel, with the bit-exact glibc port
+        const float af = (float)((double)a * LSD_DEG2RAD);
+        c2 = make_float2(glibc_cosf(af), glibc_sinf(af));
       }
     }
     gxy[o] = g;
     adeg[o] = a;
+    cs[o] = c2;
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) mag2 = max(mag2, __shfl_xor_sync(0xFFFFFFFFu, mag2, off));
@@ -210,7 +218,18 @@ __global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ row
   uint32_t run = 0;
   if (b < n_bins) {
     uint32_t* c = rowcnt + (size_t)im * H * n_bins + b;
-    for (int y = 0; y < H - 1; ++y) {
+    int y = 0;
+    for (; y + 8 <= H - 1; y += 8) {  // 8 independent loads in flight per thread
+      uint32_t v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = c[(size_t)(y + k) * n_bins];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        c[(size_t)(y + k) * n_bins] = run;
+        run += v[k];
+      }
+    }
+    for (; y < H - 1; ++y) {
       const uint32_t v = c[(size_t)y * n_bins];
       c[(size_t)y * n_bins] = run;
       run += v;
@@ -218,15 +237,20 @@ __global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ row
     tot[b] = run;
   }
   __syncthreads();
-  if (b == 0) {  // 1024-element serial scan: ~1 us, once per image
-    uint32_t acc = 0;
-    for (int k = n_bins - 1; k >= 0; --k) {
-      const uint32_t t = tot[k];
-      binstart[(size_t)im * n_bins + k] = acc;
-      acc += t;
-    }
-    nseeds[im] = (int)acc;
+  // exclusive scan over bins in DESCENDING bin order (Hillis-Steele on the reversed array)
+  __shared__ uint32_t sc[LSD_BINS_MAX];
+  const int rb = n_bins - 1 - b;  // reversed index
+  const uint32_t mine = b < n_bins ? tot[rb] : 0u;   // thread b holds reversed element b = bin (n_bins-1-b)
+  sc[b] = mine;
+  __syncthreads();
+  for (int off = 1; off < 1024; off <<= 1) {
+    const uint32_t v = b >= off ? sc[b - off] : 0u;
+    __syncthreads();
+    sc[b] += v;
+    __syncthreads();
   }
+  if (b < n_bins) binstart[(size_t)im * n_bins + rb] = sc[b] - mine;
+  if (b == n_bins - 1) nseeds[im] = (int)sc[b];
 }
 
 // one warp per (row, image): stable ranks inside the row via match_any, raster order preserved
@@ -280,7 +304,23 @@ __device__ __forceinline__ bool lsd_aligned(float a_deg, double theta, double pr
   return n_theta <= prec;
 }
 
-__global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, size_t stride, int W, int H,
+__device__ __forceinline__ bool lsd_aligned_rad(double a, double theta, double prec) {
+  double n_theta = theta - a;
+  if (n_theta < 0) n_theta = -n_theta;
+  if (n_theta > LSD_3_2_PI) {
+    n_theta -= LSD_2PI;
+    if (n_theta < 0) n_theta = -n_theta;
+  }
+  return n_theta <= prec;
+}
+
+// One warp per image.  Per region point: lanes 0..8 hold the 3x3 neighbourhood's angles, lanes 9..17 the matching
+// (cos, sin) pairs, both fetched one queue entry AHEAD (the loads for point r+1 are in flight while point r is
+// processed; cells accepted meanwhile are patched to "used" in the prefetched registers).  The alignment test of all
+// remaining neighbours runs in parallel across lanes and is repeated after every acceptance, which reproduces the
+// reference's sequential semantics (each test sees the region angle left by the previous acceptance).
+__global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, const float2* __restrict__ cs_all,
+                                                 size_t stride, int W, int H,
                                                  const uint32_t* __restrict__ order_all,
                                                  const int* __restrict__ nseeds, double prec, int min_reg_size,
                                                  uint32_t* __restrict__ regpts_all, uint4* __restrict__ regions_all,
@@ -289,11 +329,14 @@ __global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, s
   __shared__ uint32_t q[LSD_QCAP];
   const int im = blockIdx.x, lane = threadIdx.x;
   float* adeg = adeg_all + (size_t)im * stride;
+  const float2* csm = cs_all + (size_t)im * stride;
   const uint32_t* order = order_all + (size_t)im * stride;
   uint32_t* regpts = regpts_all + (size_t)im * stride;
   uint4* regions = regions_all + (size_t)im * max_regions;
   const int ns = nseeds[im];
-  uint32_t cursor = 0;  // write position in regpts (kept regions only)
+  const int kk = lane < 9 ? lane : (lane < 18 ? lane - 9 : 0);  // neighbour slot served by this lane
+  const int dxk = kk % 3 - 1, dyk = kk / 3 - 1;
+  uint32_t cursor = 0;
   int nreg_out = 0;
   for (int s0 = 0; s0 < ns; s0 += 32) {
     const int si = s0 + lane;
@@ -304,7 +347,6 @@ __global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, s
       const int src = __ffs(pending) - 1;
       const uint32_t sidx = __shfl_sync(0xFFFFFFFFu, seed, src);
       const float sdeg = __shfl_sync(0xFFFFFFFFu, a0, src);
-      // ---- region_grow from this seed ----
       const int sx = sidx % W, sy = sidx / W;
       double reg_angle = (double)sdeg * LSD_DEG2RAD;
       float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
@@ -315,29 +357,50 @@ __global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, s
       }
       __syncwarp();
       uint32_t nreg = 1;
+      // neighbourhood registers of the point being processed (cur_*) and of the next one (pf_*)
+      float pf_a = LSD_NOTDEF;
+      float2 pf_cs = make_float2(0.f, 0.f);
+      int pf_x = 0, pf_y = 0;
+      bool have_pf = false;
       for (uint32_t r = 0; r < nreg; ++r) {
-        // queue entry r: from the shared window when it still holds it, else from global
-        uint32_t pt;
-        if (nreg - r <= LSD_QCAP)  // entries r..nreg-1 all live in the ring
-          pt = q[r % LSD_QCAP];
-        else
-          pt = __ldcg(&regpts[cursor + r]);
-        const int px = pt & 0xFFFF, py = pt >> 16;
-        // lanes 0..8 fetch the 3x3 neighbourhood (row-major: yy outer, xx inner — the reference order)
-        float a = LSD_NOTDEF;
-        int nx = 0, ny = 0;
-        if (lane < 9) {
-          ny = py - 1 + lane / 3;
-          nx = px - 1 + lane % 3;
-          if (nx >= 0 && ny >= 0 && nx < W && ny < H) a = __ldcg(&adeg[(size_t)ny * W + nx]);
+        float cur_a;
+        float2 cur_cs;
+        int cx, cy;
+        if (have_pf) {
+          cur_a = pf_a; cur_cs = pf_cs; cx = pf_x; cy = pf_y;
+        } else {
+          const uint32_t pt = (nreg - r <= LSD_QCAP) ? q[r % LSD_QCAP] : __ldcg(&regpts[cursor + r]);
+          cx = (int)(pt & 0xFFFF) + dxk; cy = (int)(pt >> 16) + dyk;
+          cur_a = LSD_NOTDEF; cur_cs = make_float2(0.f, 0.f);
+          if (lane < 18 && cx >= 0 && cy >= 0 && cx < W && cy < H) {
+            const size_t o = (size_t)cy * W + cx;
+            if (lane < 9) cur_a = __ldcg(&adeg[o]);
+            else cur_cs = __ldg(&csm[o]);
+          }
         }
-        unsigned cand = __ballot_sync(0xFFFFFFFFu, a != LSD_NOTDEF) & 0x1FFu;
-        while (cand) {
-          const int k = __ffs(cand) - 1;
-          cand &= cand - 1;
-          const float ak = __shfl_sync(0xFFFFFFFFu, a, k);
-          if (!lsd_aligned(ak, reg_angle, prec)) continue;
-          const int ax = px - 1 + k % 3, ay = py - 1 + k / 3;
+        // prefetch the neighbourhood of queue entry r+1 (already known) while r is processed
+        have_pf = false;
+        if (r + 1 < nreg) {
+          const uint32_t pt = (nreg - (r + 1) <= LSD_QCAP) ? q[(r + 1) % LSD_QCAP] : __ldcg(&regpts[cursor + r + 1]);
+          pf_x = (int)(pt & 0xFFFF) + dxk; pf_y = (int)(pt >> 16) + dyk;
+          pf_a = LSD_NOTDEF; pf_cs = make_float2(0.f, 0.f);
+          if (lane < 18 && pf_x >= 0 && pf_y >= 0 && pf_x < W && pf_y < H) {
+            const size_t o = (size_t)pf_y * W + pf_x;
+            if (lane < 9) pf_a = __ldcg(&adeg[o]);
+            else pf_cs = __ldg(&csm[o]);
+          }
+          have_pf = true;
+        }
+        const double my_ang = (double)cur_a * LSD_DEG2RAD;
+        unsigned rem = __ballot_sync(0xFFFFFFFFu, lane < 9 && cur_a != LSD_NOTDEF);
+        while (rem) {
+          const bool al = ((rem >> lane) & 1u) && lsd_aligned_rad(my_ang, reg_angle, prec);
+          const unsigned m = __ballot_sync(0xFFFFFFFFu, al);
+          if (!m) break;
+          const int k = __ffs(m) - 1;
+          rem &= ~((2u << k) - 1u);  // k and everything before it have been decided
+          const int ax = __shfl_sync(0xFFFFFFFFu, cx, k), ay = __shfl_sync(0xFFFFFFFFu, cy, k);
+          const float ck = __shfl_sync(0xFFFFFFFFu, cur_cs.x, k + 9), sk = __shfl_sync(0xFFFFFFFFu, cur_cs.y, k + 9);
           const uint32_t packed = ((uint32_t)ay << 16) | (uint32_t)ax;
           if (lane == 0) {
             adeg[(size_t)ay * W + ax] = LSD_NOTDEF;
@@ -345,12 +408,13 @@ __global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, s
             q[nreg % LSD_QCAP] = packed;
           }
           ++nreg;
-          const float af = (float)((double)ak * LSD_DEG2RAD);
-          sumdx = __fadd_rn(sumdx, glibc_cosf(af));
-          sumdy = __fadd_rn(sumdy, glibc_sinf(af));
+          if (have_pf && lane < 9 && pf_x == ax && pf_y == ay) pf_a = LSD_NOTDEF;  // prefetched copy is stale
+          sumdx = __fadd_rn(sumdx, ck);
+          sumdy = __fadd_rn(sumdy, sk);
           reg_angle = (double)lsd_fast_atan2(sumdy, sumdx) * LSD_DEG2RAD;
         }
         __syncwarp();
+        // entry r+1 may only just have been appended: its neighbourhood was not prefetched -> loaded next iteration
       }
       if ((int)nreg >= min_reg_size) {
         if (nreg_out < max_regions) {
@@ -364,7 +428,6 @@ __global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, s
           *overflow = 1;
         }
       }
-      // re-validate the rest of this batch of seeds (the region may have consumed some of them)
       pending &= ~((2u << src) - 1u);
       if (pending) {
         a0 = (pending >> lane) & 1u ? __ldcg(&adeg[seed]) : LSD_NOTDEF;
@@ -561,7 +624,7 @@ __global__ void __launch_bounds__(1024) k_keylines(const float4* __restrict__ se
 
 // ---- host side -------------------------------------------------------------------------------------------------
 static void lsd_release(LsdState* s) {
-  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->gxy); cudaFree(s->adeg); cudaFree(s->binmap);
+  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->gxy); cudaFree(s->adeg); cudaFree(s->cs); cudaFree(s->binmap);
   cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->nseeds); cudaFree(s->order);
   cudaFree(s->regpts); cudaFree(s->regions); cudaFree(s->nregions); cudaFree(s->segs); cudaFree(s->kls);
   cudaFree(s->kls_all); cudaFree(s->nlines); cudaFree(s->overflow); cudaFree(s->rs_tab);
@@ -642,6 +705,7 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg) {
   PLF_CUDA(ctx, cudaMalloc(&s->scaled, As * N));
   PLF_CUDA(ctx, cudaMalloc(&s->gxy, As * N * sizeof(short2)));
   PLF_CUDA(ctx, cudaMalloc(&s->adeg, As * N * sizeof(float)));
+  PLF_CUDA(ctx, cudaMalloc(&s->cs, As * N * sizeof(float2)));
   PLF_CUDA(ctx, cudaMalloc(&s->binmap, As * N * sizeof(uint16_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->maxmag2, N * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->rowcnt, N * s->hs * s->n_bins * sizeof(uint32_t)));
@@ -694,7 +758,7 @@ plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
     scaled_stride = As;
   }
   PLF_CUDA(ctx, cudaMemsetAsync(s->maxmag2, 0xFF, (size_t)nimg * sizeof(int), cs));  // -1
-  k_lsd_grad<<<dim3((W + 255) / 256, H, nimg), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->rho, As, s->gxy, s->adeg, s->maxmag2);
+  k_lsd_grad<<<dim3((W + 255) / 256, H, nimg), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->rho, As, s->gxy, s->adeg, s->cs, s->maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
   // gxy/adeg/binmap/order/regpts are laid out with stride As per image
@@ -707,7 +771,7 @@ plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
   k_lsd_scatter<<<dim3((H - 1 + 3) / 4, nimg), 128, 0, cs>>>(s->adeg, s->binmap, As, W, H, s->n_bins, s->rowcnt, s->binstart, s->order);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_scatter");
-  k_lsd_grow<<<nimg, 32, 0, cs>>>(s->adeg, As, W, H, s->order, s->nseeds, s->prec, s->min_reg_size, s->regpts,
+  k_lsd_grow<<<nimg, 32, 0, cs>>>(s->adeg, s->cs, As, W, H, s->order, s->nseeds, s->prec, s->min_reg_size, s->regpts,
                                   s->regions, s->max_regions, s->nregions, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grow");
