@@ -21,6 +21,7 @@
  */
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -255,6 +256,10 @@ int orc_lsd_detect(const uint8_t* img, int w, int h, double scale, double sigma_
   const size_t min_reg_size = (size_t)(-LOG_NT / log10(p));
   region_point* reg = (region_point*)malloc(sizeof(region_point) * N);
   int nseg = 0, overflow = 0;
+#ifdef LSD_STATS
+  long st_regions = 0, st_points = 0, st_small = 0, st_small_pts = 0, st_defined = 0;
+  for (size_t i = 0; i < N; i++) st_defined += m.angles[i] != NOTDEF;
+#endif
   for (size_t i = 0; i < NP && !overflow; i++) {
     const int sx = ordered[i].x, sy = ordered[i].y;
     const size_t si = (size_t)sy * W + sx;
@@ -288,6 +293,10 @@ int orc_lsd_detect(const uint8_t* img, int w, int h, double scale, double sigma_
           }
         }
     }
+#ifdef LSD_STATS
+    st_regions++; st_points += nreg;
+    if (nreg < min_reg_size) { st_small++; st_small_pts += nreg; }
+#endif
     if (nreg < min_reg_size) continue;
     /* region2rect */
     double x = 0, y = 0, sum = 0;
@@ -328,6 +337,10 @@ int orc_lsd_detect(const uint8_t* img, int w, int h, double scale, double sigma_
     segs[4 * nseg] = (float)x1; segs[4 * nseg + 1] = (float)y1; segs[4 * nseg + 2] = (float)x2; segs[4 * nseg + 3] = (float)y2;
     nseg++;
   }
+#ifdef LSD_STATS
+  fprintf(stderr, "LSD_STATS %dx%d defined=%ld regions=%ld points=%ld small_regions=%ld small_points=%ld kept=%d\n", W, H,
+          st_defined, st_regions, st_points, st_small, st_small_pts, nseg);
+#endif
   free(reg); free(ordered); free(m.angles); free(m.modgrad); free(m.cosa); free(m.sina); free(m.used); free(simg);
   return overflow ? -1 : nseg;
 }
