@@ -434,7 +434,7 @@ plf_gn_opts plf_gn_opts_from_params(const plf_params& p) {
 plf_status plf_launch_gn(plf_ctx* ctx, const GnProblem* d_probs, int nprob, const plf_gn_opts& o) {
   if (nprob <= 0) return PLF_OK;
   GnCam c = {ctx->cam.fx, ctx->cam.fy, ctx->cam.cx, ctx->cam.cy};
-  k_gn_pose<<<nprob, GN_THREADS, 0, ctx->stream>>>(d_probs, c, o);
+  k_gn_pose<<<nprob, GN_THREADS, 0, ctx->cur>>>(d_probs, c, o);
   PLF_LAUNCH_CHECK(ctx);
   return PLF_OK;
 }

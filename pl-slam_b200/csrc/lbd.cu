@@ -103,7 +103,7 @@ plf_status plf_launch_blur5_sobel(plf_ctx* ctx, const uint8_t* imgs, int pitch, 
                                   int w, int h, int nimg, short2* grad, size_t grad_stride) {
   if (nimg <= 0) return PLF_OK;
   dim3 grid((w + LBD_TW - 1) / LBD_TW, (h + LBD_TH - 1) / LBD_TH, nimg);
-  k_blur5_sobel<<<grid, 256, 0, ctx->stream>>>(imgs, pitch, img_stride, w, h, grad, grad_stride);
+  k_blur5_sobel<<<grid, 256, 0, ctx->cur>>>(imgs, pitch, img_stride, w, h, grad, grad_stride);
   PLF_LAUNCH_CHECK(ctx);
   return PLF_OK;
 }
@@ -265,7 +265,7 @@ plf_status plf_launch_lbd(plf_ctx* ctx, const short2* grad, size_t grad_stride, 
   plf_status st = plf_lbd_init(ctx);
   if (st) return st;
   dim3 grid(max_lines, nimg);
-  k_lbd<<<grid, 64, 0, ctx->stream>>>(grad, grad_stride, w, h, kls, counts, max_lines, desc, desc_f);
+  k_lbd<<<grid, 64, 0, ctx->cur>>>(grad, grad_stride, w, h, kls, counts, max_lines, desc, desc_f);
   PLF_LAUNCH_CHECK(ctx);
   return PLF_OK;
 }

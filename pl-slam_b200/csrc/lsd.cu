@@ -722,6 +722,7 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg) {
   PLF_CUDA(ctx, cudaMalloc(&s->overflow, sizeof(int)));
   PLF_CUDA(ctx, cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream));
   if (s->scale != 1.0) {
+    PLF_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lsd_taps, s->taps, sizeof(int) * 16, 0, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<int> tab(2 * (size_t)s->ws + 2 * (size_t)s->hs);
     s->rs_x_off = 0;
     s->rs_y_off = 2 * (size_t)s->ws;
@@ -734,58 +735,84 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg) {
   return PLF_OK;
 }
 
-// LSD + KeyLines on nimg images resident on the device.  Results stay on the device (LsdState).
-plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg) {
-  plf_status st = plf_lsd_prepare(ctx, w, h, nimg);
-  if (st) return st;
+// LSD + KeyLines on images [img0, img0+n) of a batch resident on the device; state must be prepared for >= img0+n
+// images.  Enqueued on ctx->cur; results stay on the device (LsdState).
+plf_status plf_lsd_run_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int img0, int n) {
   LsdState* s = ctx->lsd;
-  cudaStream_t cs = ctx->stream;
+  if (!s || s->w != w || s->h != h || s->nimg < img0 + n)
+    return plf_fail(ctx, PLF_ERR_STATE, "plf_lsd_run_range: state not prepared for this image range");
+  cudaStream_t cs = ctx->cur;
   const int W = s->ws, H = s->hs;
-  const size_t As = (size_t)W * H;
-  const uint8_t* scaled = d_imgs;
+  const size_t As = (size_t)W * H, A = (size_t)w * h, o = (size_t)img0;
+  const uint8_t* imgs = d_imgs + o * img_stride;
+  uint8_t* blur = s->blur + o * A;
+  uint8_t* scaled_buf = s->scaled + o * As;
+  short2* gxy = s->gxy + o * As;
+  float* adeg = s->adeg + o * As;
+  float2* csm = s->cs + o * As;
+  uint16_t* binmap = s->binmap + o * As;
+  int* maxmag2 = s->maxmag2 + o;
+  uint32_t* rowcnt = s->rowcnt + o * H * s->n_bins;
+  uint32_t* binstart = s->binstart + o * s->n_bins;
+  int* nseeds = s->nseeds + o;
+  uint32_t* order = s->order + o * As;
+  uint32_t* regpts = s->regpts + o * As;
+  uint4* regions = s->regions + o * s->max_regions;
+  int* nregions = s->nregions + o;
+  float4* segs = s->segs + o * s->max_regions;
+  plf_keyline* kls = s->kls + o * s->max_lines;
+  plf_keyline* kls_all = s->kls_all + o * s->max_regions;
+  int* nlines = s->nlines + o;
+  plf_status st;
+  const uint8_t* scaled = imgs;
   size_t scaled_stride = img_stride;
   if (s->scale != 1.0) {
-    PLF_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lsd_taps, s->taps, sizeof(int) * 16, 0, cudaMemcpyHostToDevice, cs));
-    dim3 gb((w + BQ_TW - 1) / BQ_TW, (h + BQ_TH - 1) / BQ_TH, nimg);
-    k_blur_q8<<<gb, 256, 0, cs>>>(d_imgs, img_stride, w, w, h, s->ksize / 2, s->blur, (size_t)w * h);
+    dim3 gb((w + BQ_TW - 1) / BQ_TW, (h + BQ_TH - 1) / BQ_TH, n);
+    k_blur_q8<<<gb, 256, 0, cs>>>(imgs, img_stride, w, w, h, s->ksize / 2, blur, A);
     PLF_LAUNCH_CHECK(ctx);
-  plf_mark(ctx, "lsd.k_blur_q8");
-    st = plf_launch_resize_exact(ctx, s->blur, (size_t)w * h, w, h, s->scaled, As, W, H, s->rs_tab + s->rs_x_off,
-                                 s->rs_tab + s->rs_y_off, nimg);
+    plf_mark(ctx, "lsd.k_blur_q8");
+    st = plf_launch_resize_exact(ctx, blur, A, w, h, scaled_buf, As, W, H, s->rs_tab + s->rs_x_off, s->rs_tab + s->rs_y_off, n);
     if (st) return st;
     plf_mark(ctx, "lsd.k_resize_exact");
-    scaled = s->scaled;
+    scaled = scaled_buf;
     scaled_stride = As;
   }
-  PLF_CUDA(ctx, cudaMemsetAsync(s->maxmag2, 0xFF, (size_t)nimg * sizeof(int), cs));  // -1
-  k_lsd_grad<<<dim3((W + 255) / 256, H, nimg), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->rho, As, s->gxy, s->adeg, s->cs, s->maxmag2);
+  PLF_CUDA(ctx, cudaMemsetAsync(maxmag2, 0xFF, (size_t)n * sizeof(int), cs));  // -1
+  k_lsd_grad<<<dim3((W + 255) / 256, H, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->rho, As, gxy, adeg, csm, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
-  // gxy/adeg/binmap/order/regpts are laid out with stride As per image
-  k_lsd_rowhist<<<dim3(H - 1, nimg), 256, 0, cs>>>(s->gxy, s->adeg, As, W, H, s->n_bins, s->maxmag2, s->binmap, s->rowcnt);
+  k_lsd_rowhist<<<dim3(H - 1, n), 256, 0, cs>>>(gxy, adeg, As, W, H, s->n_bins, maxmag2, binmap, rowcnt);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rowhist");
-  k_lsd_binscan<<<nimg, 1024, 0, cs>>>(s->rowcnt, H, s->n_bins, s->binstart, s->nseeds);
+  k_lsd_binscan<<<n, 1024, 0, cs>>>(rowcnt, H, s->n_bins, binstart, nseeds);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_binscan");
-  k_lsd_scatter<<<dim3((H - 1 + 3) / 4, nimg), 128, 0, cs>>>(s->adeg, s->binmap, As, W, H, s->n_bins, s->rowcnt, s->binstart, s->order);
+  k_lsd_scatter<<<dim3((H - 1 + 3) / 4, n), 128, 0, cs>>>(adeg, binmap, As, W, H, s->n_bins, rowcnt, binstart, order);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_scatter");
-  k_lsd_grow<<<nimg, 32, 0, cs>>>(s->adeg, s->cs, As, W, H, s->order, s->nseeds, s->prec, s->min_reg_size, s->regpts,
-                                  s->regions, s->max_regions, s->nregions, s->overflow);
+  k_lsd_grow<<<n, 32, 0, cs>>>(adeg, csm, As, W, H, order, nseeds, s->prec, s->min_reg_size, regpts, regions, s->max_regions,
+                               nregions, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grow");
-  k_lsd_rects<<<dim3((s->max_regions + 127) / 128, nimg), 128, 0, cs>>>(s->gxy, As, W, s->regpts, s->regions, s->max_regions,
-                                                                        s->nregions, s->prec, s->scale, s->segs);
+  k_lsd_rects<<<dim3((s->max_regions + 127) / 128, n), 128, 0, cs>>>(gxy, As, W, regpts, regions, s->max_regions, nregions,
+                                                                     s->prec, s->scale, segs);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rects");
   const double min_length = (double)ctx->params.min_line_length * (double)std::min(w, h);
-  k_keylines<<<nimg, 1024, 0, cs>>>(s->segs, s->nregions, s->max_regions, w, h, min_length, ctx->params.lsd_nfeatures,
-                                    s->kls_all, s->kls, s->max_lines, s->nlines, s->overflow);
+  k_keylines<<<n, 1024, 0, cs>>>(segs, nregions, s->max_regions, w, h, min_length, ctx->params.lsd_nfeatures, kls_all, kls,
+                                 s->max_lines, nlines, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_keylines");
   return PLF_OK;
 }
+
+plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg) {
+  plf_status st = plf_lsd_prepare(ctx, w, h, nimg);
+  if (st) return st;
+  return plf_lsd_run_range(ctx, d_imgs, img_stride, w, h, 0, nimg);
+}
+
+int* plf_lsd_overflow_flag(plf_ctx* ctx) { return ctx->lsd->overflow; }
 
 void plf_lsd_outputs(plf_ctx* ctx, plf_keyline** kls, int** nlines, int* max_lines) {
   LsdState* s = ctx->lsd;

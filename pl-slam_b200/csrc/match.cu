@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(KNN_THREADS) k_hamming_knn2(const KnnProblem* 
 plf_status plf_launch_knn2(plf_ctx* ctx, const KnnProblem* d_probs, int nprob, int max_nq) {
   if (nprob <= 0 || max_nq <= 0) return PLF_OK;
   dim3 grid((max_nq + KNN_QPB - 1) / KNN_QPB, nprob);
-  k_hamming_knn2<<<grid, KNN_THREADS, 0, ctx->stream>>>(d_probs);
+  k_hamming_knn2<<<grid, KNN_THREADS, 0, ctx->cur>>>(d_probs);
   PLF_LAUNCH_CHECK(ctx);
   return PLF_OK;
 }
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_nnr_mutual(const NnrProblem* __restrict
 plf_status plf_launch_nnr(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, int max_n1) {
   if (nprob <= 0 || max_n1 <= 0) return PLF_OK;
   dim3 grid((max_n1 + 255) / 256, nprob);
-  k_nnr_mutual<<<grid, 256, 0, ctx->stream>>>(d_probs);
+  k_nnr_mutual<<<grid, 256, 0, ctx->cur>>>(d_probs);
   PLF_LAUNCH_CHECK(ctx);
   return PLF_OK;
 }

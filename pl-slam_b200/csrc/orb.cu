@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_resize_exact(const uint8_t* __restrict_
 plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_stride, int sw, int sh, uint8_t* dst,
                                    size_t dst_stride, int dw, int dh, const int* tabx, const int* taby, int nimg) {
   dim3 grid((dw + 255) / 256, dh, nimg);
-  k_resize_exact<<<grid, 256, 0, ctx->stream>>>(src, src_stride, sw, sh, dst, dst_stride, dw, dh, tabx, taby);
+  k_resize_exact<<<grid, 256, 0, ctx->cur>>>(src, src_stride, sw, sh, dst, dst_stride, dw, dh, tabx, taby);
   PLF_LAUNCH_CHECK(ctx);
   return PLF_OK;
 }
@@ -168,13 +168,21 @@ __global__ void __launch_bounds__(256) k_fast_nms(const uint8_t* __restrict__ im
     if (gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3) {
       const int cy = sy + 3, cx = sx + 3;  // position in px
       const int v = px[cy][cx];
-      // quick rejection on the 4 compass points (any 9-arc contains at least 2 of them... OpenCV tests pairs)
+      // Quick rejection (as OpenCV's FAST_t): a 9-arc of the 16-ring always contains one pixel of every opposite
+      // pair (k, k+8), so both members of any pair within the threshold band rules the pixel out.
+      const int q0 = v - px[cy + 3][cx], q8 = v - px[cy - 3][cx];
+      bool pd = (q0 > th) | (q8 > th), pb = (q0 < -th) | (q8 < -th);
+      if (!(pd | pb)) { sc[sy][sx] = 0; continue; }
+      const int q4 = v - px[cy][cx + 3], q12 = v - px[cy][cx - 3];
+      pd &= (q4 > th) | (q12 > th);
+      pb &= (q4 < -th) | (q12 < -th);
+      if (!(pd | pb)) { sc[sy][sx] = 0; continue; }
       int d[16];
-      d[0] = v - px[cy + 3][cx];      d[1] = v - px[cy + 3][cx + 1];  d[2] = v - px[cy + 2][cx + 2];
-      d[3] = v - px[cy + 1][cx + 3];  d[4] = v - px[cy][cx + 3];      d[5] = v - px[cy - 1][cx + 3];
-      d[6] = v - px[cy - 2][cx + 2];  d[7] = v - px[cy - 3][cx + 1];  d[8] = v - px[cy - 3][cx];
+      d[0] = q0;                      d[1] = v - px[cy + 3][cx + 1];  d[2] = v - px[cy + 2][cx + 2];
+      d[3] = v - px[cy + 1][cx + 3];  d[4] = q4;                      d[5] = v - px[cy - 1][cx + 3];
+      d[6] = v - px[cy - 2][cx + 2];  d[7] = v - px[cy - 3][cx + 1];  d[8] = q8;
       d[9] = v - px[cy - 3][cx - 1];  d[10] = v - px[cy - 2][cx - 2]; d[11] = v - px[cy - 1][cx - 3];
-      d[12] = v - px[cy][cx - 3];     d[13] = v - px[cy + 1][cx - 3]; d[14] = v - px[cy + 2][cx - 2];
+      d[12] = q12;                    d[13] = v - px[cy + 1][cx - 3]; d[14] = v - px[cy + 2][cx - 2];
       d[15] = v - px[cy + 3][cx - 1];
       uint32_t md = 0, mb = 0;
 #pragma unroll
@@ -612,7 +620,7 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
   if (st) return st;
   OrbState* s = ctx->orb;
   const OrbGeom& g = s->g;
-  cudaStream_t cs = ctx->stream;
+  cudaStream_t cs = ctx->cur;
   PLF_CUDA(ctx, cudaMemsetAsync(s->cand_count, 0, (size_t)nimg * ORB_MAX_LEVELS * sizeof(int), cs));
   PLF_CUDA(ctx, cudaMemsetAsync(s->hist, 0, (size_t)nimg * ORB_MAX_LEVELS * 256 * sizeof(int), cs));
   for (int l = 1; l < g.nlevels; ++l) {
@@ -643,6 +651,8 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
   plf_mark(ctx, "orb.k_rbrief");
   return PLF_OK;
 }
+
+int* plf_orb_overflow_flag(plf_ctx* ctx) { return ctx->orb->overflow; }
 
 // device-side accessors for the pipeline
 void plf_orb_outputs(plf_ctx* ctx, plf_keypoint** kps, uint8_t** desc, int** counts, int* max_kp) {

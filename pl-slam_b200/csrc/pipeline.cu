@@ -23,7 +23,11 @@ struct FrameSlots {  // stereo-valid features per frame slot: [slots][cap]
 struct PipeState {
   int w = 0, h = 0, B = 0, max_kp = 0, max_ln = 0;
   bool has_prev = false;
-  uint8_t* imgs = nullptr;     // [2B][h][w]
+  uint8_t* imgs = nullptr;     // images of the batch being run: = imgs2[run_slot]
+  uint8_t* imgs2[2] = {nullptr, nullptr};  // double-buffered [2B][h][w]: upload of batch i+1 overlaps the run of batch i
+  int up_slot = 0;             // slot written by the last plf_batch_upload
+  cudaStream_t copy = nullptr; // H2D stream
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   short2* lbd_grad = nullptr;  // [2B][h*w]
   uint8_t* ldesc_raw = nullptr;  // [2B][max_ln][32]  LBD of every kept KeyLine
   FrameSlots fs;               // B+1 slots
@@ -62,6 +66,11 @@ extern "C" void plf_pipe_free(plf_ctx* ctx) {
   if (!s) return;
   for (void* p : s->allocs) cudaFree(p);
   if (s->h_results) cudaFreeHost(s->h_results);
+  if (s->copy) { cudaStreamSynchronize(s->copy); cudaStreamDestroy(s->copy); }
+  for (int i = 0; i < 2; ++i) {
+    if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
+    if (s->ev_free[i]) cudaEventDestroy(s->ev_free[i]);
+  }
   delete s;
   ctx->pipe = nullptr;
 }
@@ -343,7 +352,14 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   plf_status st;
 #define PA(ptr, n) if ((st = pipe_alloc(ctx, s, &(ptr), (n)))) return st
   const size_t A = (size_t)w * h, S = (size_t)B + 1;
-  PA(s->imgs, 2 * (size_t)B * A);
+  PA(s->imgs2[0], 2 * (size_t)B * A);
+  PA(s->imgs2[1], 2 * (size_t)B * A);
+  s->imgs = s->imgs2[0];
+  PLF_CUDA(ctx, cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
+    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming));
+  }
   PA(s->lbd_grad, 2 * (size_t)B * A);
   PA(s->ldesc_raw, 2 * (size_t)B * Ln * 32);
   FrameSlots& f = s->fs;
@@ -446,18 +462,29 @@ plf_status plf_batch_upload(plf_ctx* ctx, int B, const uint8_t* left, const uint
   if (st) return st;
   PipeState* s = ctx->pipe;
   const size_t A = (size_t)w * h, hs = (size_t)stride * h;
-  // interleave: device image 2k = left k, 2k+1 = right k
+  // H2D on the copy stream into the slot the GPU is not reading, so the copy of batch i+1 overlaps the run of batch i.
+  // Device layout interleaves the pair: image 2k = left k, 2k+1 = right k.
+  const int slot = s->up_slot ^ 1;
+  uint8_t* dst = s->imgs2[slot];
+  PLF_CUDA(ctx, cudaStreamWaitEvent(s->copy, s->ev_free[slot], 0));  // last run that read this slot has finished with it
   for (int k = 0; k < B; ++k) {
-    PLF_CUDA(ctx, cudaMemcpy2DAsync(s->imgs + (size_t)(2 * k) * A, w, left + k * hs, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
-    PLF_CUDA(ctx, cudaMemcpy2DAsync(s->imgs + (size_t)(2 * k + 1) * A, w, right + k * hs, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+    if (stride == w) {
+      PLF_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)(2 * k) * A, left + k * hs, A, cudaMemcpyHostToDevice, s->copy));
+      PLF_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)(2 * k + 1) * A, right + k * hs, A, cudaMemcpyHostToDevice, s->copy));
+    } else {
+      PLF_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)(2 * k) * A, w, left + k * hs, stride, w, h, cudaMemcpyHostToDevice, s->copy));
+      PLF_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)(2 * k + 1) * A, w, right + k * hs, stride, w, h, cudaMemcpyHostToDevice, s->copy));
+    }
   }
+  PLF_CUDA(ctx, cudaEventRecord(s->ev_up[slot], s->copy));
+  s->up_slot = slot;
   return PLF_OK;
 }
 
 void* plf_batch_device_images(plf_ctx* ctx) {
   if (!ctx) return nullptr;
   if (pipe_prepare(ctx, ctx->cam.width, ctx->cam.height)) return nullptr;
-  return ctx->pipe->imgs;
+  return ctx->pipe->imgs2[ctx->pipe->up_slot];
 }
 
 plf_status plf_batch_run(plf_ctx* ctx, int B) {
@@ -471,20 +498,53 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   const int K = s->max_kp, Ln = s->max_ln;
   cudaStream_t cs = ctx->stream;
   const plf_params& P = ctx->params;
+  const int run_slot = s->up_slot;  // consume the most recently uploaded batch
+  s->imgs = s->imgs2[run_slot];
+  PLF_CUDA(ctx, cudaStreamWaitEvent(cs, s->ev_up[run_slot], 0));
   if (!s->has_prev) {  // initialize(): no previous frame to track against
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.pt_count, 0, sizeof(int), cs));
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.ls_count, 0, sizeof(int), cs));
   }
   plf_mark(ctx, "start");
-  // --- extraction over 2B images
-  if ((st = plf_orb_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
-  if ((st = plf_lsd_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
+  // --- extraction over 2B images.  ORB and LSD are independent; LSD's region growing is latency-bound (one warp per
+  // image) while everything else is bandwidth/ALU-bound, so the batch is forked: ORB (+ the LBD gradient prelude) on one
+  // stream, LSD for 4 groups of pairs on 4 more, so that the growing of one group overlaps the streaming kernels of the
+  // others.  With profiling on, everything stays on the main stream so that the per-kernel marks are meaningful.
   plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
-  plf_orb_outputs(ctx, &kps, &odesc, &kcnt, &mk);
   plf_keyline* kls; int* lcnt; int ml;
-  plf_lsd_outputs(ctx, &kls, &lcnt, &ml);
-  if ((st = plf_launch_blur5_sobel(ctx, s->imgs, w, A, w, h, 2 * B, s->lbd_grad, A))) return st;
-  plf_mark(ctx, "lbd.k_blur5_sobel");
+  const bool forked = !ctx->profile && B >= 4;
+  if (forked) {
+    PLF_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    ctx->cur = ctx->aux[0];
+    PLF_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
+    st = plf_orb_run(ctx, s->imgs, A, w, h, 2 * B);
+    if (!st) st = plf_launch_blur5_sobel(ctx, s->imgs, w, A, w, h, 2 * B, s->lbd_grad, A);
+    if (!st && cudaEventRecord(ctx->ev_join[0], ctx->aux[0]) != cudaSuccess) st = PLF_ERR_CUDA;
+    const int G = 4, per = (B + G - 1) / G;
+    int used = 1;
+    for (int g = 0; g < G && !st; ++g) {
+      const int p0 = g * per, p1 = std::min(B, p0 + per);
+      if (p0 >= p1) break;
+      ctx->cur = ctx->aux[1 + g];
+      if (cudaStreamWaitEvent(ctx->aux[1 + g], ctx->ev_fork, 0) != cudaSuccess) { st = PLF_ERR_CUDA; break; }
+      st = plf_lsd_run_range(ctx, s->imgs, A, w, h, 2 * p0, 2 * (p1 - p0));
+      if (!st && cudaEventRecord(ctx->ev_join[1 + g], ctx->aux[1 + g]) != cudaSuccess) st = PLF_ERR_CUDA;
+      used = 2 + g;
+    }
+    ctx->cur = ctx->stream;
+    if (st) return st == PLF_ERR_CUDA ? plf_fail(ctx, PLF_ERR_CUDA, "plf_batch_run: stream fork failed") : st;
+    for (int i = 0; i < used; ++i) PLF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
+    plf_orb_outputs(ctx, &kps, &odesc, &kcnt, &mk);
+    plf_lsd_outputs(ctx, &kls, &lcnt, &ml);
+  } else {
+    if ((st = plf_orb_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
+    if ((st = plf_lsd_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
+    plf_orb_outputs(ctx, &kps, &odesc, &kcnt, &mk);
+    plf_lsd_outputs(ctx, &kls, &lcnt, &ml);
+    if ((st = plf_launch_blur5_sobel(ctx, s->imgs, w, A, w, h, 2 * B, s->lbd_grad, A))) return st;
+    plf_mark(ctx, "lbd.k_blur5_sobel");
+  }
+  PLF_CUDA(ctx, cudaEventRecord(s->ev_free[run_slot], cs));  // every reader of the image buffer has been enqueued / joined
   if ((st = plf_launch_lbd(ctx, s->lbd_grad, A, w, h, 2 * B, kls, lcnt, Ln, s->ldesc_raw, nullptr))) return st;
   plf_mark(ctx, "lbd.k_lbd");
   // --- stereo association
@@ -525,8 +585,17 @@ plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out) {
     return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_download: bad arguments");
   PipeState* s = ctx->pipe;
   PLF_CUDA(ctx, cudaMemcpyAsync(s->h_results, s->results, sizeof(plf_frame_result) * B, cudaMemcpyDeviceToHost, ctx->stream));
+  int ovf[2] = {0, 0};
+  PLF_CUDA(ctx, cudaMemcpyAsync(&ovf[0], plf_orb_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&ovf[1], plf_lsd_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   memcpy(out, s->h_results, sizeof(plf_frame_result) * B);
+  if (ovf[0] || ovf[1]) {
+    cudaMemsetAsync(plf_orb_overflow_flag(ctx), 0, sizeof(int), ctx->stream);
+    cudaMemsetAsync(plf_lsd_overflow_flag(ctx), 0, sizeof(int), ctx->stream);
+    return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_batch_download: a fixed-capacity buffer overflowed (%s%s); raise plf_limits",
+                    ovf[0] ? "ORB keypoints " : "", ovf[1] ? "LSD segments/lines" : "");
+  }
   return PLF_OK;
 }
 

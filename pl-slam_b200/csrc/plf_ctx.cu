@@ -68,7 +68,7 @@ void plf_mark(plf_ctx* ctx, const char* name) {
     ctx->prof_names.emplace_back();
   }
   ctx->prof_names[ctx->prof_used] = name;
-  cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->stream);
+  cudaEventRecord(ctx->prof_ev[ctx->prof_used], ctx->cur);
   ctx->prof_used++;
 }
 
@@ -162,6 +162,8 @@ void plf_default_limits(plf_limits* l) {
   l->max_lines = 1024;
 }
 
+void plf_destroy(plf_ctx* ctx);
+
 plf_status plf_create(const plf_params* params, const plf_camera* cam, const plf_limits* limits,
                       int device, plf_ctx** out) {
   if (!out) return plf_fail(nullptr, PLF_ERR_INVALID, "plf_create: out is NULL");
@@ -204,6 +206,16 @@ plf_status plf_create(const plf_params* params, const plf_camera* cam, const plf
     delete ctx;
     return plf_fail(nullptr, PLF_ERR_NO_DEVICE, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
+  ctx->cur = ctx->stream;
+  bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int i = 0; i < 5 && ok; ++i) {
+    ok = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  }
+  if (!ok) {
+    plf_destroy(ctx);
+    return plf_fail(nullptr, PLF_ERR_NO_DEVICE, "plf_create: could not create auxiliary streams/events");
+  }
   *out = ctx;
   return PLF_OK;
 }
@@ -226,6 +238,11 @@ void plf_destroy(plf_ctx* ctx) {
     if (b.p) cudaFree(b.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
+  for (int i = 0; i < 5; ++i) {
+    if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); }
+    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

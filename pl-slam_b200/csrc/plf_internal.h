@@ -26,7 +26,10 @@ struct Scratch {
 
 struct plf_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;  // main stream: copies, the serial part of the pipeline, standalone operators
+  cudaStream_t cur = nullptr;     // stream the launch helpers enqueue on (== stream except inside forked sections)
+  cudaStream_t aux[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // fork streams of plf_batch_run
+  cudaEvent_t ev_fork = nullptr, ev_join[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
   plf_params params;
   plf_camera cam;
   plf_limits limits;
@@ -140,4 +143,8 @@ plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_
 // ---- LSD (lsd.cu) --------------------------------------------------------------------------------
 plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg);
 plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg);
+// same, for images [img0, img0+n) of a batch whose state was prepared for >= img0+n images (enqueued on ctx->cur)
+plf_status plf_lsd_run_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int img0, int n);
 void plf_lsd_outputs(plf_ctx* ctx, plf_keyline** kls, int** nlines, int* max_lines);
+int* plf_orb_overflow_flag(plf_ctx* ctx);
+int* plf_lsd_overflow_flag(plf_ctx* ctx);

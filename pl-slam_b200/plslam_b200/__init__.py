@@ -80,6 +80,13 @@ class plf_frame_view(C.Structure):
                 ("ls_angle", C.c_void_p), ("ldesc", C.c_void_p)]
 
 
+RESULT_DTYPE = np.dtype([("DT", np.float64, (4, 4)), ("DT_cov", np.float64, (6, 6)), ("err", np.float64),
+                         ("status", np.int32), ("n_kp_l", np.int32), ("n_kp_r", np.int32), ("n_lines_l", np.int32),
+                         ("n_lines_r", np.int32), ("n_stereo_pt", np.int32), ("n_stereo_ls", np.int32),
+                         ("n_matched_pt", np.int32), ("n_matched_ls", np.int32), ("n_inliers_pt", np.int32),
+                         ("n_inliers_ls", np.int32), ("iters1", np.int32), ("iters2", np.int32)], align=True)
+assert RESULT_DTYPE.itemsize == C.sizeof(plf_frame_result)
+
 RESULT_FIELDS = ["status", "n_kp_l", "n_kp_r", "n_lines_l", "n_lines_r", "n_stereo_pt", "n_stereo_ls", "n_matched_pt",
                  "n_matched_ls", "n_inliers_pt", "n_inliers_ls", "iters1", "iters2"]
 
@@ -384,6 +391,12 @@ class Frontend:
         res = (plf_frame_result * B)()
         self._check(self.lib.plf_batch_download(self._ctx, int(B), res), "plf_batch_download")
         return self._result_dicts(res, B)
+
+    def batch_download_array(self, B):
+        """Same as batch_download but returns one numpy structured array (RESULT_DTYPE) — no per-frame Python objects."""
+        out = np.zeros(B, RESULT_DTYPE)
+        self._check(self.lib.plf_batch_download(self._ctx, int(B), out.ctypes.data_as(C.c_void_p)), "plf_batch_download")
+        return out
 
     @property
     def device_images(self) -> int:
