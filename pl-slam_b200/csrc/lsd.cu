@@ -51,24 +51,25 @@ struct LsdState {
   double scale = 1.2, prec = 0, p = 0, rho = 0;
   int min_reg_size = 0;
   int max_regions = 0, max_lines = 0;
+  bool two_parities = false;
   uint8_t* blur = nullptr;    // [nimg][h*w]
   uint8_t* scaled = nullptr;  // [nimg][hs*ws]
-  short2* gxy = nullptr;      // [nimg][hs*ws]
-  float* adeg = nullptr;      // [nimg][hs*ws]  level-line angle in degrees, LSD_NOTDEF = undefined or used
-  float2* cs = nullptr;       // [nimg][hs*ws]  (cosf, sinf) of float(angle): the region-angle increments, precomputed
+  short2* gxy[2] = {nullptr, nullptr};      // [nimg][hs*ws]
+  float* adeg[2] = {nullptr, nullptr};      // [nimg][hs*ws]  level-line angle in degrees, LSD_NOTDEF = undefined or used
+  float2* cs[2] = {nullptr, nullptr};       // [nimg][hs*ws]  (cosf, sinf) of float(angle): the region-angle increments, precomputed
   uint16_t* binmap = nullptr; // [nimg][hs*ws]
   int* maxmag2 = nullptr;     // [nimg]
   uint32_t* rowcnt = nullptr; // [nimg][hs][n_bins]
   uint32_t* binstart = nullptr; // [nimg][n_bins]
-  int* nseeds = nullptr;      // [nimg]
-  uint32_t* order = nullptr;  // [nimg][hs*ws]
-  uint32_t* regpts = nullptr; // [nimg][hs*ws]
-  uint4* regions = nullptr;   // [nimg][max_regions] {start, count, angle_lo, angle_hi}
-  int* nregions = nullptr;    // [nimg]
-  float4* segs = nullptr;     // [nimg][max_regions]
-  plf_keyline* kls = nullptr; // [nimg][max_lines]  final KeyLines (after top-K)
-  plf_keyline* kls_all = nullptr; // [nimg][max_regions] before top-K
-  int* nlines = nullptr;      // [nimg]
+  int* nseeds[2] = {nullptr, nullptr};      // [nimg]
+  uint32_t* order[2] = {nullptr, nullptr};  // [nimg][hs*ws]
+  uint32_t* regpts[2] = {nullptr, nullptr}; // [nimg][hs*ws]
+  uint4* regions[2] = {nullptr, nullptr};   // [nimg][max_regions] {start, count, angle_lo, angle_hi}
+  int* nregions[2] = {nullptr, nullptr};    // [nimg]
+  float4* segs[2] = {nullptr, nullptr};     // [nimg][max_regions]
+  plf_keyline* kls[2] = {nullptr, nullptr}; // [nimg][max_lines]  final KeyLines (after top-K)
+  plf_keyline* kls_all[2] = {nullptr, nullptr}; // [nimg][max_regions] before top-K
+  int* nlines[2] = {nullptr, nullptr};      // [nimg]
   int* overflow = nullptr;    // [1]
   int* rs_tab = nullptr;      // resize tables
   size_t rs_x_off = 0, rs_y_off = 0;
@@ -624,10 +625,13 @@ __global__ void __launch_bounds__(1024) k_keylines(const float4* __restrict__ se
 
 // ---- host side -------------------------------------------------------------------------------------------------
 static void lsd_release(LsdState* s) {
-  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->gxy); cudaFree(s->adeg); cudaFree(s->cs); cudaFree(s->binmap);
-  cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->nseeds); cudaFree(s->order);
-  cudaFree(s->regpts); cudaFree(s->regions); cudaFree(s->nregions); cudaFree(s->segs); cudaFree(s->kls);
-  cudaFree(s->kls_all); cudaFree(s->nlines); cudaFree(s->overflow); cudaFree(s->rs_tab);
+  for (int p = 0; p < 2; ++p) {
+    cudaFree(s->gxy[p]); cudaFree(s->adeg[p]); cudaFree(s->cs[p]); cudaFree(s->order[p]); cudaFree(s->nseeds[p]);
+    cudaFree(s->regpts[p]); cudaFree(s->regions[p]); cudaFree(s->nregions[p]); cudaFree(s->segs[p]); cudaFree(s->kls[p]);
+    cudaFree(s->kls_all[p]); cudaFree(s->nlines[p]);
+  }
+  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap);
+  cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->overflow); cudaFree(s->rs_tab);
 }
 
 extern "C" void plf_lsd_free(plf_ctx* ctx) {
@@ -660,9 +664,10 @@ static void gaussian_taps_q8(int ksize, double sigma, int* taps) {
   taps[ksize / 2] = 256 - 2 * s;
 }
 
-plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg) {
+plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_parities) {
   LsdState* s = ctx->lsd;
-  if (s && s->w == w && s->h == h && s->nimg >= nimg) return PLF_OK;
+  if (s && s->w == w && s->h == h && s->nimg >= nimg && (s->two_parities || !two_parities)) return PLF_OK;
+  if (s && s->two_parities) two_parities = true;
   if (s) {
     PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     lsd_release(s);
@@ -676,6 +681,7 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg) {
   if (P.lsd_n_bins < 1 || P.lsd_n_bins > LSD_BINS_MAX)
     return plf_fail(ctx, PLF_ERR_INVALID, "LSD: lsd_n_bins must be in [1,%d]", LSD_BINS_MAX);
   s->w = w; s->h = h; s->nimg = nimg;
+  s->two_parities = two_parities;
   s->scale = P.lsd_scale;
   s->n_bins = P.lsd_n_bins;
   s->prec = LSD_PI * P.lsd_ang_th / 180;
@@ -703,22 +709,26 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg) {
   const size_t N = (size_t)nimg, A = (size_t)w * h, As = (size_t)s->ws * s->hs;
   PLF_CUDA(ctx, cudaMalloc(&s->blur, A * N));
   PLF_CUDA(ctx, cudaMalloc(&s->scaled, As * N));
-  PLF_CUDA(ctx, cudaMalloc(&s->gxy, As * N * sizeof(short2)));
-  PLF_CUDA(ctx, cudaMalloc(&s->adeg, As * N * sizeof(float)));
-  PLF_CUDA(ctx, cudaMalloc(&s->cs, As * N * sizeof(float2)));
   PLF_CUDA(ctx, cudaMalloc(&s->binmap, As * N * sizeof(uint16_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->maxmag2, N * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->rowcnt, N * s->hs * s->n_bins * sizeof(uint32_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->binstart, N * s->n_bins * sizeof(uint32_t)));
-  PLF_CUDA(ctx, cudaMalloc(&s->nseeds, N * sizeof(int)));
-  PLF_CUDA(ctx, cudaMalloc(&s->order, As * N * sizeof(uint32_t)));
-  PLF_CUDA(ctx, cudaMalloc(&s->regpts, As * N * sizeof(uint32_t)));
-  PLF_CUDA(ctx, cudaMalloc(&s->regions, N * s->max_regions * sizeof(uint4)));
-  PLF_CUDA(ctx, cudaMalloc(&s->nregions, N * sizeof(int)));
-  PLF_CUDA(ctx, cudaMalloc(&s->segs, N * s->max_regions * sizeof(float4)));
-  PLF_CUDA(ctx, cudaMalloc(&s->kls, N * s->max_lines * sizeof(plf_keyline)));
-  PLF_CUDA(ctx, cudaMalloc(&s->kls_all, N * s->max_regions * sizeof(plf_keyline)));
-  PLF_CUDA(ctx, cudaMalloc(&s->nlines, N * sizeof(int)));
+  // buffers that cross from the pre-grow phase to the grow / match phases exist twice (parity of the batch), so that
+  // batch i+1 can be extracted while batch i is still growing regions; standalone operators use parity 0 only
+  for (int p = 0; p < (s->two_parities ? 2 : 1); ++p) {
+    PLF_CUDA(ctx, cudaMalloc(&s->gxy[p], As * N * sizeof(short2)));
+    PLF_CUDA(ctx, cudaMalloc(&s->adeg[p], As * N * sizeof(float)));
+    PLF_CUDA(ctx, cudaMalloc(&s->cs[p], As * N * sizeof(float2)));
+    PLF_CUDA(ctx, cudaMalloc(&s->nseeds[p], N * sizeof(int)));
+    PLF_CUDA(ctx, cudaMalloc(&s->order[p], As * N * sizeof(uint32_t)));
+    PLF_CUDA(ctx, cudaMalloc(&s->regpts[p], As * N * sizeof(uint32_t)));
+    PLF_CUDA(ctx, cudaMalloc(&s->regions[p], N * s->max_regions * sizeof(uint4)));
+    PLF_CUDA(ctx, cudaMalloc(&s->nregions[p], N * sizeof(int)));
+    PLF_CUDA(ctx, cudaMalloc(&s->segs[p], N * s->max_regions * sizeof(float4)));
+    PLF_CUDA(ctx, cudaMalloc(&s->kls[p], N * s->max_lines * sizeof(plf_keyline)));
+    PLF_CUDA(ctx, cudaMalloc(&s->kls_all[p], N * s->max_regions * sizeof(plf_keyline)));
+    PLF_CUDA(ctx, cudaMalloc(&s->nlines[p], N * sizeof(int)));
+  }
   PLF_CUDA(ctx, cudaMalloc(&s->overflow, sizeof(int)));
   PLF_CUDA(ctx, cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream));
   if (s->scale != 1.0) {
@@ -735,34 +745,29 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg) {
   return PLF_OK;
 }
 
-// LSD + KeyLines on images [img0, img0+n) of a batch resident on the device; state must be prepared for >= img0+n
-// images.  Enqueued on ctx->cur; results stay on the device (LsdState).
-plf_status plf_lsd_run_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int img0, int n) {
+// LSD on images [img0, img0+n) of a batch resident on the device, in two phases so that callers can overlap them with
+// other work: `pre` = blur, resample, gradient and seed ordering (bandwidth-bound), `grow` = region growing, rectangle
+// fit and the KeyLine stage (latency-bound).  `par` selects the buffer set that carries data from pre to grow.
+// State must be prepared for >= img0+n images.  Enqueued on ctx->cur; results stay on the device.
+plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int par, int img0, int n) {
   LsdState* s = ctx->lsd;
-  if (!s || s->w != w || s->h != h || s->nimg < img0 + n)
-    return plf_fail(ctx, PLF_ERR_STATE, "plf_lsd_run_range: state not prepared for this image range");
+  if (!s || s->w != w || s->h != h || s->nimg < img0 + n || (par && !s->two_parities))
+    return plf_fail(ctx, PLF_ERR_STATE, "plf_lsd_pre_range: state not prepared for this image range");
   cudaStream_t cs = ctx->cur;
   const int W = s->ws, H = s->hs;
   const size_t As = (size_t)W * H, A = (size_t)w * h, o = (size_t)img0;
   const uint8_t* imgs = d_imgs + o * img_stride;
   uint8_t* blur = s->blur + o * A;
   uint8_t* scaled_buf = s->scaled + o * As;
-  short2* gxy = s->gxy + o * As;
-  float* adeg = s->adeg + o * As;
-  float2* csm = s->cs + o * As;
+  short2* gxy = s->gxy[par] + o * As;
+  float* adeg = s->adeg[par] + o * As;
+  float2* csm = s->cs[par] + o * As;
   uint16_t* binmap = s->binmap + o * As;
   int* maxmag2 = s->maxmag2 + o;
   uint32_t* rowcnt = s->rowcnt + o * H * s->n_bins;
   uint32_t* binstart = s->binstart + o * s->n_bins;
-  int* nseeds = s->nseeds + o;
-  uint32_t* order = s->order + o * As;
-  uint32_t* regpts = s->regpts + o * As;
-  uint4* regions = s->regions + o * s->max_regions;
-  int* nregions = s->nregions + o;
-  float4* segs = s->segs + o * s->max_regions;
-  plf_keyline* kls = s->kls + o * s->max_lines;
-  plf_keyline* kls_all = s->kls_all + o * s->max_regions;
-  int* nlines = s->nlines + o;
+  int* nseeds = s->nseeds[par] + o;
+  uint32_t* order = s->order[par] + o * As;
   plf_status st;
   const uint8_t* scaled = imgs;
   size_t scaled_stride = img_stride;
@@ -790,6 +795,28 @@ plf_status plf_lsd_run_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
   k_lsd_scatter<<<dim3((H - 1 + 3) / 4, n), 128, 0, cs>>>(adeg, binmap, As, W, H, s->n_bins, rowcnt, binstart, order);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_scatter");
+  return PLF_OK;
+}
+
+plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int n) {
+  LsdState* s = ctx->lsd;
+  if (!s || s->w != w || s->h != h || s->nimg < img0 + n || (par && !s->two_parities))
+    return plf_fail(ctx, PLF_ERR_STATE, "plf_lsd_grow_range: state not prepared for this image range");
+  cudaStream_t cs = ctx->cur;
+  const int W = s->ws, H = s->hs;
+  const size_t As = (size_t)W * H, o = (size_t)img0;
+  short2* gxy = s->gxy[par] + o * As;
+  float* adeg = s->adeg[par] + o * As;
+  float2* csm = s->cs[par] + o * As;
+  int* nseeds = s->nseeds[par] + o;
+  uint32_t* order = s->order[par] + o * As;
+  uint32_t* regpts = s->regpts[par] + o * As;
+  uint4* regions = s->regions[par] + o * s->max_regions;
+  int* nregions = s->nregions[par] + o;
+  float4* segs = s->segs[par] + o * s->max_regions;
+  plf_keyline* kls = s->kls[par] + o * s->max_lines;
+  plf_keyline* kls_all = s->kls_all[par] + o * s->max_regions;
+  int* nlines = s->nlines[par] + o;
   k_lsd_grow<<<n, 32, 0, cs>>>(adeg, csm, As, W, H, order, nseeds, s->prec, s->min_reg_size, regpts, regions, s->max_regions,
                                nregions, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
@@ -807,16 +834,17 @@ plf_status plf_lsd_run_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
 }
 
 plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg) {
-  plf_status st = plf_lsd_prepare(ctx, w, h, nimg);
+  plf_status st = plf_lsd_prepare(ctx, w, h, nimg, false);
   if (st) return st;
-  return plf_lsd_run_range(ctx, d_imgs, img_stride, w, h, 0, nimg);
+  if ((st = plf_lsd_pre_range(ctx, d_imgs, img_stride, w, h, 0, 0, nimg))) return st;
+  return plf_lsd_grow_range(ctx, w, h, 0, 0, nimg);
 }
 
 int* plf_lsd_overflow_flag(plf_ctx* ctx) { return ctx->lsd->overflow; }
 
-void plf_lsd_outputs(plf_ctx* ctx, plf_keyline** kls, int** nlines, int* max_lines) {
+void plf_lsd_outputs(plf_ctx* ctx, int par, plf_keyline** kls, int** nlines, int* max_lines) {
   LsdState* s = ctx->lsd;
-  *kls = s->kls; *nlines = s->nlines; *max_lines = s->max_lines;
+  *kls = s->kls[par]; *nlines = s->nlines[par]; *max_lines = s->max_lines;
 }
 
 static plf_status lsd_check_overflow(plf_ctx* ctx, const char* what) {
@@ -844,13 +872,13 @@ extern "C" plf_status plf_lsd(plf_ctx* ctx, const uint8_t* img, int w, int h, in
   if (st) return st;
   LsdState* s = ctx->lsd;
   int n = 0;
-  PLF_CUDA(ctx, cudaMemcpyAsync(&n, s->nregions, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&n, s->nregions[0], sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   st = lsd_check_overflow(ctx, "plf_lsd");
   if (st) return st;
   *n_out = n;
   if (n > cap) return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_lsd: %d segments > caller capacity %d", n, cap);
   if (n > 0) {
-    PLF_CUDA(ctx, cudaMemcpyAsync(segs, s->segs, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpyAsync(segs, s->segs[0], (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, ctx->stream));
     PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return PLF_OK;
@@ -873,16 +901,16 @@ extern "C" plf_status plf_detect_lines(plf_ctx* ctx, const uint8_t* img, int w, 
   LsdState* s = ctx->lsd;
   st = plf_launch_blur5_sobel(ctx, dimg, w, 0, w, h, 1, dgrad, 0);
   if (st) return st;
-  st = plf_launch_lbd(ctx, dgrad, 0, w, h, 1, s->kls, s->nlines, s->max_lines, ddesc, nullptr);
+  st = plf_launch_lbd(ctx, dgrad, 0, w, h, 1, s->kls[0], s->nlines[0], s->max_lines, ddesc, nullptr);
   if (st) return st;
   int n = 0;
-  PLF_CUDA(ctx, cudaMemcpyAsync(&n, s->nlines, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&n, s->nlines[0], sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   st = lsd_check_overflow(ctx, "plf_detect_lines");
   if (st) return st;
   *n_out = n;
   if (n > cap) return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_detect_lines: %d lines > caller capacity %d", n, cap);
   if (n > 0) {
-    PLF_CUDA(ctx, cudaMemcpyAsync(keylines, s->kls, (size_t)n * sizeof(plf_keyline), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpyAsync(keylines, s->kls[0], (size_t)n * sizeof(plf_keyline), cudaMemcpyDeviceToHost, ctx->stream));
     PLF_CUDA(ctx, cudaMemcpyAsync(desc, ddesc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }

@@ -48,6 +48,7 @@ struct OrbGeom {
 
 struct OrbState {
   int w = 0, h = 0, nimg = 0;
+  bool two_parities = false;
   OrbGeom g;
   uint8_t* pyr = nullptr;    // levels 1..n-1, all images
   uint8_t* blur = nullptr;   // blurred levels 0..n-1
@@ -58,10 +59,10 @@ struct OrbState {
   int* rs_tab = nullptr;
   size_t rs_x_off[ORB_MAX_LEVELS], rs_y_off[ORB_MAX_LEVELS];
   // outputs
-  plf_keypoint* kps = nullptr;  // [nimg][max_kp]
-  short2* kp_lxy = nullptr;     // level coordinates
-  uint8_t* desc = nullptr;      // [nimg][max_kp][32]
-  int* kp_count = nullptr;      // [nimg]
+  plf_keypoint* kps[2] = {nullptr, nullptr};  // [nimg][max_kp]
+  short2* kp_lxy[2] = {nullptr, nullptr};     // level coordinates
+  uint8_t* desc[2] = {nullptr, nullptr};      // [nimg][max_kp][32]
+  int* kp_count[2] = {nullptr, nullptr};      // [nimg]
   int* overflow = nullptr;      // [1]
   float blur_k[7];
 };
@@ -481,9 +482,9 @@ void plf_linear_coeffs_host(int srcsize, int dstsize, double scale, int* ofs, in
 static void orb_release(OrbState* s) {
   if (!s) return;
   cudaFree(s->pyr); cudaFree(s->blur); cudaFree(s->cand); cudaFree(s->cand_count); cudaFree(s->hist);
-  cudaFree(s->rs_tab); cudaFree(s->kps); cudaFree(s->kp_lxy); cudaFree(s->desc); cudaFree(s->kp_count);
-  cudaFree(s->overflow);
-  s->pyr = s->blur = s->desc = nullptr;
+  cudaFree(s->rs_tab); cudaFree(s->overflow);
+  for (int p = 0; p < 2; ++p) { cudaFree(s->kps[p]); cudaFree(s->kp_lxy[p]); cudaFree(s->desc[p]); cudaFree(s->kp_count[p]); }
+  s->pyr = s->blur = nullptr;
 }
 
 extern "C" void plf_orb_free(plf_ctx* ctx) {
@@ -498,9 +499,10 @@ static int8_t* g_dev_pattern = nullptr;  // shared by all contexts on a device (
 static int g_dev_pattern_device = -1;
 
 // (Re)builds the ORB state for images of w x h and up to nimg images per launch.
-plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg) {
+plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_parities) {
   OrbState* s = ctx->orb;
-  if (s && s->w == w && s->h == h && s->nimg >= nimg) return PLF_OK;
+  if (s && s->w == w && s->h == h && s->nimg >= nimg && (s->two_parities || !two_parities)) return PLF_OK;
+  if (s && s->two_parities) two_parities = true;
   if (s) {
     PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     orb_release(s);
@@ -515,6 +517,7 @@ plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg) {
                     "wta_k=%d score=%d patch=%d)", P.orb_nlevels, P.orb_wta_k, P.orb_score, P.orb_patch_size);
   if (w >= 4096 || h >= 4096) return plf_fail(ctx, PLF_ERR_INVALID, "ORB: image larger than 4095 px");
   s->w = w; s->h = h; s->nimg = nimg;
+  s->two_parities = two_parities;
   OrbGeom& g = s->g;
   memset(&g, 0, sizeof g);
   g.nlevels = P.orb_nlevels;
@@ -584,10 +587,12 @@ plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg) {
   PLF_CUDA(ctx, cudaMalloc(&s->cand_count, N * ORB_MAX_LEVELS * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->hist, N * ORB_MAX_LEVELS * 256 * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->rs_tab, std::max<size_t>(tab.size(), 1) * sizeof(int)));
-  PLF_CUDA(ctx, cudaMalloc(&s->kps, N * g.max_kp * sizeof(plf_keypoint)));
-  PLF_CUDA(ctx, cudaMalloc(&s->kp_lxy, N * g.max_kp * sizeof(short2)));
-  PLF_CUDA(ctx, cudaMalloc(&s->desc, N * g.max_kp * 32));
-  PLF_CUDA(ctx, cudaMalloc(&s->kp_count, N * sizeof(int)));
+  for (int p = 0; p < (two_parities ? 2 : 1); ++p) {  // outputs exist per batch parity (read by the match phase of batch i
+    PLF_CUDA(ctx, cudaMalloc(&s->kps[p], N * g.max_kp * sizeof(plf_keypoint)));  // while batch i+1 is being extracted)
+    PLF_CUDA(ctx, cudaMalloc(&s->kp_lxy[p], N * g.max_kp * sizeof(short2)));
+    PLF_CUDA(ctx, cudaMalloc(&s->desc[p], N * g.max_kp * 32));
+    PLF_CUDA(ctx, cudaMalloc(&s->kp_count[p], N * sizeof(int)));
+  }
   PLF_CUDA(ctx, cudaMalloc(&s->overflow, sizeof(int)));
   PLF_CUDA(ctx, cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream));
   if (!tab.empty())
@@ -615,8 +620,8 @@ plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg) {
 }
 
 // Runs ORB on nimg images resident at d_imgs ([nimg][h][w], stride img_stride bytes). Results stay on the device.
-plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg) {
-  plf_status st = plf_orb_prepare(ctx, w, h, nimg);
+plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg, int par) {
+  plf_status st = plf_orb_prepare(ctx, w, h, nimg, par != 0);
   if (st) return st;
   OrbState* s = ctx->orb;
   const OrbGeom& g = s->g;
@@ -637,16 +642,16 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
                                                  s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "orb.k_fast_nms");
-  k_select_sort<<<nimg, 1024, 0, cs>>>(g, s->cand, s->cand_count, s->hist, s->kps, s->kp_lxy, s->kp_count, s->overflow);
+  k_select_sort<<<nimg, 1024, 0, cs>>>(g, s->cand, s->cand_count, s->hist, s->kps[par], s->kp_lxy[par], s->kp_count[par], s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "orb.k_select_sort");
-  k_ic_angle<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->kps, s->kp_lxy, s->kp_count);
+  k_ic_angle<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->kps[par], s->kp_lxy[par], s->kp_count[par]);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "orb.k_ic_angle");
   k_orb_blur7<<<dim3(tiles, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->blur);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "orb.k_orb_blur7");
-  k_rbrief<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(s->blur, g, s->kps, s->kp_count, g_dev_pattern, s->desc);
+  k_rbrief<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(s->blur, g, s->kps[par], s->kp_count[par], g_dev_pattern, s->desc[par]);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "orb.k_rbrief");
   return PLF_OK;
@@ -655,9 +660,9 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
 int* plf_orb_overflow_flag(plf_ctx* ctx) { return ctx->orb->overflow; }
 
 // device-side accessors for the pipeline
-void plf_orb_outputs(plf_ctx* ctx, plf_keypoint** kps, uint8_t** desc, int** counts, int* max_kp) {
+void plf_orb_outputs(plf_ctx* ctx, int par, plf_keypoint** kps, uint8_t** desc, int** counts, int* max_kp) {
   OrbState* s = ctx->orb;
-  *kps = s->kps; *desc = s->desc; *counts = s->kp_count; *max_kp = s->g.max_kp;
+  *kps = s->kps[par]; *desc = s->desc[par]; *counts = s->kp_count[par]; *max_kp = s->g.max_kp;
 }
 
 extern "C" plf_status plf_orb(plf_ctx* ctx, const uint8_t* img, int w, int h, int stride, plf_keypoint* kps,
@@ -668,11 +673,11 @@ extern "C" plf_status plf_orb(plf_ctx* ctx, const uint8_t* img, int w, int h, in
   uint8_t* dimg = (uint8_t*)plf_scratch(ctx, 3, (size_t)w * h);
   if (!dimg) return PLF_ERR_CUDA;
   PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, w, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
-  plf_status st = plf_orb_run(ctx, dimg, (size_t)w * h, w, h, 1);
+  plf_status st = plf_orb_run(ctx, dimg, (size_t)w * h, w, h, 1, 0);
   if (st) return st;
   OrbState* s = ctx->orb;
   int n = 0, ovf = 0;
-  PLF_CUDA(ctx, cudaMemcpyAsync(&n, s->kp_count, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&n, s->kp_count[0], sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PLF_CUDA(ctx, cudaMemcpyAsync(&ovf, s->overflow, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ovf) {
@@ -682,8 +687,8 @@ extern "C" plf_status plf_orb(plf_ctx* ctx, const uint8_t* img, int w, int h, in
   *n_out = n;
   if (n > cap) return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_orb: %d keypoints > caller capacity %d", n, cap);
   if (n > 0) {
-    PLF_CUDA(ctx, cudaMemcpyAsync(kps, s->kps, (size_t)n * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
-    PLF_CUDA(ctx, cudaMemcpyAsync(desc, s->desc, (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpyAsync(kps, s->kps[0], (size_t)n * sizeof(plf_keypoint), cudaMemcpyDeviceToHost, ctx->stream));
+    PLF_CUDA(ctx, cudaMemcpyAsync(desc, s->desc[0], (size_t)n * 32, cudaMemcpyDeviceToHost, ctx->stream));
     PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   }
   return PLF_OK;

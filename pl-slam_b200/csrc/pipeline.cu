@@ -28,24 +28,31 @@ struct PipeState {
   int up_slot = 0;             // slot written by the last plf_batch_upload
   cudaStream_t copy = nullptr; // H2D stream
   cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
-  short2* lbd_grad = nullptr;  // [2B][h*w]
+  short2* lbd_grad[2] = {nullptr, nullptr};  // [parity][2B][h*w]
   uint8_t* ldesc_raw = nullptr;  // [2B][max_ln][32]  LBD of every kept KeyLine
   FrameSlots fs;               // B+1 slots
   // matching scratch
   uint32_t* knn_keys = nullptr;   // [B][8][2][max_kp]
   int32_t* m12 = nullptr;         // [B][4][max_kp]  stereo pts, stereo lines, f2f pts, f2f lines
   int* mcount = nullptr;          // [B][4]
-  KnnProblem* knn_stereo = nullptr;  // [B*4]
+  KnnProblem* knn_stereo[2] = {nullptr, nullptr};  // [parity][B*4]  (read the ORB / LBD outputs of that parity)
   KnnProblem* knn_f2f = nullptr;     // [B*4]
-  NnrProblem* nnr_stereo = nullptr;  // [B*2]
+  NnrProblem* nnr_stereo[2] = {nullptr, nullptr};  // [parity][B*2]
   NnrProblem* nnr_f2f = nullptr;     // [B*2]
   // GN inputs / outputs
   double* gnP = nullptr; double* gnObs = nullptr; uint8_t* gnInlP = nullptr; int* gnNp = nullptr;
   double* gn_sP = nullptr; double* gn_eP = nullptr; double* gn_le = nullptr; uint8_t* gnInlL = nullptr; int* gnNl = nullptr;
   GnProblem* gn_probs = nullptr;
   plf_pose_result* gn_out = nullptr;
-  plf_frame_result* results = nullptr;  // [B] device
-  plf_frame_result* h_results = nullptr;  // pinned host mirror
+  plf_frame_result* results[2] = {nullptr, nullptr};    // [parity][B] device
+  plf_frame_result* h_results[2] = {nullptr, nullptr};  // pinned host mirrors (filled at the end of the match phase)
+  int* h_ovf[2] = {nullptr, nullptr};                   // pinned overflow flags {orb, lsd} per parity
+  // Batches are software-pipelined over three streams: E (extract: ORB, LSD pre-grow, LBD prelude) -> G (LSD region
+  // growing, latency-bound) -> M (LBD, stereo, tracking, pose).  Batch i+1's E phase overlaps batch i's G and M phases;
+  // buffers that cross phases exist per batch parity.  Up to 2 batches may be in flight (run, run, download, ...).
+  cudaEvent_t evE[2] = {nullptr, nullptr}, evG[2] = {nullptr, nullptr}, evM[2] = {nullptr, nullptr};
+  long long seq = 0;            // batches issued
+  int pend_par[2] = {0, 0}, pend_B[2] = {0, 0}, n_pending = 0;
   void* orb_kps_seen = nullptr;  // sub-system output pointers baked into the problem descriptors
   void* lsd_kls_seen = nullptr;
   std::vector<void*> allocs;
@@ -65,7 +72,13 @@ extern "C" void plf_pipe_free(plf_ctx* ctx) {
   PipeState* s = ctx->pipe;
   if (!s) return;
   for (void* p : s->allocs) cudaFree(p);
-  if (s->h_results) cudaFreeHost(s->h_results);
+  for (int i = 0; i < 2; ++i) {
+    if (s->h_results[i]) cudaFreeHost(s->h_results[i]);
+    if (s->h_ovf[i]) cudaFreeHost(s->h_ovf[i]);
+    if (s->evE[i]) cudaEventDestroy(s->evE[i]);
+    if (s->evG[i]) cudaEventDestroy(s->evG[i]);
+    if (s->evM[i]) cudaEventDestroy(s->evM[i]);
+  }
   if (s->copy) { cudaStreamSynchronize(s->copy); cudaStreamDestroy(s->copy); }
   for (int i = 0; i < 2; ++i) {
     if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
@@ -335,12 +348,12 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   if (s && s->w == w && s->h == h) {
     // a standalone operator call on another image size may have rebuilt the ORB / LSD state meanwhile
     plf_status st0;
-    if ((st0 = plf_orb_prepare(ctx, w, h, 2 * s->B))) return st0;
-    if ((st0 = plf_lsd_prepare(ctx, w, h, 2 * s->B))) return st0;
+    if ((st0 = plf_orb_prepare(ctx, w, h, 2 * s->B, true))) return st0;
+    if ((st0 = plf_lsd_prepare(ctx, w, h, 2 * s->B, true))) return st0;
     plf_keypoint* kps0; uint8_t* d0; int* c0; int m0;
-    plf_orb_outputs(ctx, &kps0, &d0, &c0, &m0);
+    plf_orb_outputs(ctx, 0, &kps0, &d0, &c0, &m0);
     plf_keyline* kl0; int* lc0; int ml0;
-    plf_lsd_outputs(ctx, &kl0, &lc0, &ml0);
+    plf_lsd_outputs(ctx, 0, &kl0, &lc0, &ml0);
     if (kps0 == s->orb_kps_seen && kl0 == s->lsd_kls_seen) return PLF_OK;
   }
   if (s) plf_pipe_free(ctx);
@@ -360,7 +373,8 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
     PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
     PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming));
   }
-  PA(s->lbd_grad, 2 * (size_t)B * A);
+  PA(s->lbd_grad[0], 2 * (size_t)B * A);
+  PA(s->lbd_grad[1], 2 * (size_t)B * A);
   PA(s->ldesc_raw, 2 * (size_t)B * Ln * 32);
   FrameSlots& f = s->fs;
   PA(f.pt_pl, S * K); PA(f.pt_disp, S * K); PA(f.pt_P, S * K * 3); PA(f.pt_octave, S * K); PA(f.pdesc, S * K * 32); PA(f.pt_count, S);
@@ -369,27 +383,40 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PA(s->knn_keys, (size_t)B * 8 * 2 * K);
   PA(s->m12, (size_t)B * 4 * K);
   PA(s->mcount, (size_t)B * 4);
-  PA(s->knn_stereo, (size_t)B * 4); PA(s->knn_f2f, (size_t)B * 4); PA(s->nnr_stereo, (size_t)B * 2); PA(s->nnr_f2f, (size_t)B * 2);
+  PA(s->knn_stereo[0], (size_t)B * 4); PA(s->knn_stereo[1], (size_t)B * 4); PA(s->knn_f2f, (size_t)B * 4);
+  PA(s->nnr_stereo[0], (size_t)B * 2); PA(s->nnr_stereo[1], (size_t)B * 2); PA(s->nnr_f2f, (size_t)B * 2);
   PA(s->gnP, (size_t)B * K * 3); PA(s->gnObs, (size_t)B * K * 2); PA(s->gnInlP, (size_t)B * K); PA(s->gnNp, B);
   PA(s->gn_sP, (size_t)B * Ln * 3); PA(s->gn_eP, (size_t)B * Ln * 3); PA(s->gn_le, (size_t)B * Ln * 3); PA(s->gnInlL, (size_t)B * Ln); PA(s->gnNl, B);
-  PA(s->gn_probs, B); PA(s->gn_out, B); PA(s->results, B);
+  PA(s->gn_probs, B); PA(s->gn_out, B); PA(s->results[0], B); PA(s->results[1], B);
 #undef PA
-  PLF_CUDA(ctx, cudaHostAlloc(&s->h_results, sizeof(plf_frame_result) * B, cudaHostAllocDefault));
+  for (int i = 0; i < 2; ++i) {
+    PLF_CUDA(ctx, cudaHostAlloc(&s->h_results[i], sizeof(plf_frame_result) * B, cudaHostAllocDefault));
+    PLF_CUDA(ctx, cudaHostAlloc(&s->h_ovf[i], 2 * sizeof(int), cudaHostAllocDefault));
+    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evE[i], cudaEventDisableTiming));
+    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evG[i], cudaEventDisableTiming));
+    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evM[i], cudaEventDisableTiming));
+  }
   PLF_CUDA(ctx, cudaMemsetAsync(f.pt_count, 0, S * sizeof(int), ctx->stream));
   PLF_CUDA(ctx, cudaMemsetAsync(f.ls_count, 0, S * sizeof(int), ctx->stream));
   // sub-systems sized for 2B images
-  if ((st = plf_orb_prepare(ctx, w, h, 2 * B))) return st;
-  if ((st = plf_lsd_prepare(ctx, w, h, 2 * B))) return st;
+  if ((st = plf_orb_prepare(ctx, w, h, 2 * B, true))) return st;
+  if ((st = plf_lsd_prepare(ctx, w, h, 2 * B, true))) return st;
   // static problem descriptors (pointers never change; counts are read on the device)
-  plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
-  plf_orb_outputs(ctx, &kps, &odesc, &kcnt, &mk);
-  plf_keyline* kls; int* lcnt; int ml;
-  plf_lsd_outputs(ctx, &kls, &lcnt, &ml);
-  s->orb_kps_seen = kps;
-  s->lsd_kls_seen = kls;
-  std::vector<KnnProblem> ks(B * 4), kf(B * 4);
-  std::vector<NnrProblem> ns(B * 2), nf(B * 2);
   const plf_params& P = ctx->params;
+  cudaStream_t cs = ctx->stream;
+  std::vector<KnnProblem> kf(B * 4);
+  std::vector<NnrProblem> nf(B * 2);
+  for (int par = 0; par < 2; ++par) {
+  plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
+  plf_orb_outputs(ctx, par, &kps, &odesc, &kcnt, &mk);
+  plf_keyline* kls; int* lcnt; int ml;
+  plf_lsd_outputs(ctx, par, &kls, &lcnt, &ml);
+  if (par == 0) {
+    s->orb_kps_seen = kps;
+    s->lsd_kls_seen = kls;
+  }
+  std::vector<KnnProblem> ks(B * 4);
+  std::vector<NnrProblem> ns(B * 2);
   for (int k = 0; k < B; ++k) {
     auto key = [&](int prob, int which) { return s->knn_keys + (((size_t)k * 8 + prob) * 2 + which) * K; };
     const uint32_t* dl = (const uint32_t*)(odesc + (size_t)(2 * k) * K * 32);
@@ -418,15 +445,16 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
     nf[2 * k + 1] = {key(6, 0), key(6, 1), key(7, 0), key(7, 1), f.ls_count + k, f.ls_count + k + 1, 0, 0, P.min_ratio_12_l,
                      P.best_lr_matches ? 1 : 0, s->m12 + ((size_t)k * 4 + 3) * K, s->mcount + 4 * k + 3};
   }
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->knn_stereo[par], ks.data(), ks.size() * sizeof(KnnProblem), cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->nnr_stereo[par], ns.data(), ns.size() * sizeof(NnrProblem), cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaStreamSynchronize(cs));
+  }  // par
   std::vector<GnProblem> gp(B);
   for (int k = 0; k < B; ++k)
     gp[k] = {s->gnP + (size_t)k * K * 3, s->gnObs + (size_t)k * K * 2, s->gnInlP + (size_t)k * K, s->gnNp + k, 0,
              s->gn_sP + (size_t)k * Ln * 3, s->gn_eP + (size_t)k * Ln * 3, s->gn_le + (size_t)k * Ln * 3,
              s->gnInlL + (size_t)k * Ln, s->gnNl + k, 0, nullptr, s->gn_out + k};
-  cudaStream_t cs = ctx->stream;
-  PLF_CUDA(ctx, cudaMemcpyAsync(s->knn_stereo, ks.data(), ks.size() * sizeof(KnnProblem), cudaMemcpyHostToDevice, cs));
   PLF_CUDA(ctx, cudaMemcpyAsync(s->knn_f2f, kf.data(), kf.size() * sizeof(KnnProblem), cudaMemcpyHostToDevice, cs));
-  PLF_CUDA(ctx, cudaMemcpyAsync(s->nnr_stereo, ns.data(), ns.size() * sizeof(NnrProblem), cudaMemcpyHostToDevice, cs));
   PLF_CUDA(ctx, cudaMemcpyAsync(s->nnr_f2f, nf.data(), nf.size() * sizeof(NnrProblem), cudaMemcpyHostToDevice, cs));
   PLF_CUDA(ctx, cudaMemcpyAsync(s->gn_probs, gp.data(), gp.size() * sizeof(GnProblem), cudaMemcpyHostToDevice, cs));
   PLF_CUDA(ctx, cudaStreamSynchronize(cs));
@@ -449,7 +477,11 @@ extern "C" {
 
 plf_status plf_reset_sequence(plf_ctx* ctx) {
   if (!ctx) return PLF_ERR_INVALID;
-  if (ctx->pipe) ctx->pipe->has_prev = false;
+  if (ctx->pipe) {
+    if (ctx->pipe->n_pending)
+      return plf_fail(ctx, PLF_ERR_STATE, "plf_reset_sequence: %d batch(es) still in flight; download them first", ctx->pipe->n_pending);
+    ctx->pipe->has_prev = false;
+  }
   return PLF_OK;
 }
 
@@ -494,64 +526,57 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   plf_status st = pipe_prepare(ctx, w, h);
   if (st) return st;
   PipeState* s = ctx->pipe;
+  if (s->n_pending >= 2)
+    return plf_fail(ctx, PLF_ERR_STATE, "plf_batch_run: two batches already in flight; call plf_batch_download first");
   const size_t A = (size_t)w * h;
   const int K = s->max_kp, Ln = s->max_ln;
-  cudaStream_t cs = ctx->stream;
   const plf_params& P = ctx->params;
+  const int par = (int)(s->seq & 1);
   const int run_slot = s->up_slot;  // consume the most recently uploaded batch
+  const uint8_t* imgs = s->imgs2[run_slot];
   s->imgs = s->imgs2[run_slot];
-  PLF_CUDA(ctx, cudaStreamWaitEvent(cs, s->ev_up[run_slot], 0));
+  // With profiling on everything is serialised on the main stream so that the per-kernel marks are meaningful.
+  const bool piped = !ctx->profile;
+  cudaStream_t sM = ctx->stream, sE = piped ? ctx->aux[0] : sM, sG = piped ? ctx->aux[1] : sM;
+  plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
+  plf_keyline* kls; int* lcnt; int ml;
+  plf_orb_outputs(ctx, par, &kps, &odesc, &kcnt, &mk);
+  plf_lsd_outputs(ctx, par, &kls, &lcnt, &ml);
+
+  // ---- E phase: ORB, LSD up to the seed ordering, LBD gradient prelude (all bandwidth / ALU bound) ----
+  ctx->cur = sE;
+  PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->ev_up[run_slot], 0));  // images uploaded
+  PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->evM[par], 0));         // batch i-2 (same parity) no longer reads these buffers
+  plf_mark(ctx, "start");
+  st = plf_orb_run(ctx, imgs, A, w, h, 2 * B, par);
+  if (!st) st = plf_lsd_pre_range(ctx, imgs, A, w, h, par, 0, 2 * B);
+  if (!st) st = plf_launch_blur5_sobel(ctx, imgs, w, A, w, h, 2 * B, s->lbd_grad[par], A);
+  if (st) { ctx->cur = sM; return st; }
+  plf_mark(ctx, "lbd.k_blur5_sobel");
+  PLF_CUDA(ctx, cudaEventRecord(s->evE[par], sE));
+  PLF_CUDA(ctx, cudaEventRecord(s->ev_free[run_slot], sE));  // the image buffer may be overwritten by the next upload
+
+  // ---- G phase: LSD region growing + rectangle fit + KeyLines (latency bound, one warp per image) ----
+  ctx->cur = sG;
+  PLF_CUDA(ctx, cudaStreamWaitEvent(sG, s->evE[par], 0));
+  st = plf_lsd_grow_range(ctx, w, h, par, 0, 2 * B);
+  if (st) { ctx->cur = sM; return st; }
+  PLF_CUDA(ctx, cudaEventRecord(s->evG[par], sG));
+
+  // ---- M phase: LBD, stereo association, frame-to-frame tracking, pose (needs the previous batch's M phase) ----
+  ctx->cur = sM;
+  cudaStream_t cs = sM;
+  PLF_CUDA(ctx, cudaStreamWaitEvent(sM, s->evG[par], 0));
   if (!s->has_prev) {  // initialize(): no previous frame to track against
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.pt_count, 0, sizeof(int), cs));
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.ls_count, 0, sizeof(int), cs));
   }
-  plf_mark(ctx, "start");
-  // --- extraction over 2B images.  ORB and LSD are independent; LSD's region growing is latency-bound (one warp per
-  // image) while everything else is bandwidth/ALU-bound, so the batch is forked: ORB (+ the LBD gradient prelude) on one
-  // stream, LSD for 4 groups of pairs on 4 more, so that the growing of one group overlaps the streaming kernels of the
-  // others.  With profiling on, everything stays on the main stream so that the per-kernel marks are meaningful.
-  plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
-  plf_keyline* kls; int* lcnt; int ml;
-  const bool forked = !ctx->profile && B >= 4;
-  if (forked) {
-    PLF_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    ctx->cur = ctx->aux[0];
-    PLF_CUDA(ctx, cudaStreamWaitEvent(ctx->aux[0], ctx->ev_fork, 0));
-    st = plf_orb_run(ctx, s->imgs, A, w, h, 2 * B);
-    if (!st) st = plf_launch_blur5_sobel(ctx, s->imgs, w, A, w, h, 2 * B, s->lbd_grad, A);
-    if (!st && cudaEventRecord(ctx->ev_join[0], ctx->aux[0]) != cudaSuccess) st = PLF_ERR_CUDA;
-    const int G = 4, per = (B + G - 1) / G;
-    int used = 1;
-    for (int g = 0; g < G && !st; ++g) {
-      const int p0 = g * per, p1 = std::min(B, p0 + per);
-      if (p0 >= p1) break;
-      ctx->cur = ctx->aux[1 + g];
-      if (cudaStreamWaitEvent(ctx->aux[1 + g], ctx->ev_fork, 0) != cudaSuccess) { st = PLF_ERR_CUDA; break; }
-      st = plf_lsd_run_range(ctx, s->imgs, A, w, h, 2 * p0, 2 * (p1 - p0));
-      if (!st && cudaEventRecord(ctx->ev_join[1 + g], ctx->aux[1 + g]) != cudaSuccess) st = PLF_ERR_CUDA;
-      used = 2 + g;
-    }
-    ctx->cur = ctx->stream;
-    if (st) return st == PLF_ERR_CUDA ? plf_fail(ctx, PLF_ERR_CUDA, "plf_batch_run: stream fork failed") : st;
-    for (int i = 0; i < used; ++i) PLF_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[i], 0));
-    plf_orb_outputs(ctx, &kps, &odesc, &kcnt, &mk);
-    plf_lsd_outputs(ctx, &kls, &lcnt, &ml);
-  } else {
-    if ((st = plf_orb_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
-    if ((st = plf_lsd_run(ctx, s->imgs, A, w, h, 2 * B))) return st;
-    plf_orb_outputs(ctx, &kps, &odesc, &kcnt, &mk);
-    plf_lsd_outputs(ctx, &kls, &lcnt, &ml);
-    if ((st = plf_launch_blur5_sobel(ctx, s->imgs, w, A, w, h, 2 * B, s->lbd_grad, A))) return st;
-    plf_mark(ctx, "lbd.k_blur5_sobel");
-  }
-  PLF_CUDA(ctx, cudaEventRecord(s->ev_free[run_slot], cs));  // every reader of the image buffer has been enqueued / joined
-  if ((st = plf_launch_lbd(ctx, s->lbd_grad, A, w, h, 2 * B, kls, lcnt, Ln, s->ldesc_raw, nullptr))) return st;
+  if ((st = plf_launch_lbd(ctx, s->lbd_grad[par], A, w, h, 2 * B, kls, lcnt, Ln, s->ldesc_raw, nullptr))) return st;
   plf_mark(ctx, "lbd.k_lbd");
-  // --- stereo association
   PLF_CUDA(ctx, cudaMemsetAsync(s->mcount, 0, (size_t)B * 4 * sizeof(int), cs));
-  if ((st = plf_launch_knn2(ctx, s->knn_stereo, 4 * B, std::max(K, Ln)))) return st;
+  if ((st = plf_launch_knn2(ctx, s->knn_stereo[par], 4 * B, std::max(K, Ln)))) return st;
   plf_mark(ctx, "stereo.k_hamming_knn2");
-  if ((st = plf_launch_nnr(ctx, s->nnr_stereo, 2 * B, std::max(K, Ln)))) return st;
+  if ((st = plf_launch_nnr(ctx, s->nnr_stereo[par], 2 * B, std::max(K, Ln)))) return st;
   plf_mark(ctx, "stereo.k_nnr_mutual");
   StereoPrm sp = {P.max_dist_epip, P.min_disp, P.line_horiz_th, P.stereo_overlap_th, P.ls_min_disp_ratio,
                   ctx->cam.fx, ctx->cam.fy, ctx->cam.cx, ctx->cam.cy, ctx->cam.b};
@@ -560,7 +585,6 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   k_stereo_lines<<<B, 1024, 0, cs>>>(kls, s->ldesc_raw, lcnt, Ln, s->m12 + K, 4 * K, sp, s->fs, 1);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "stereo.k_stereo_points+lines");
-  // --- frame-to-frame tracking + pose (pair k: prev slot k, curr slot k+1; k = 0 uses the carried frame)
   if ((st = plf_launch_knn2(ctx, s->knn_f2f, 4 * B, std::max(K, Ln)))) return st;
   plf_mark(ctx, "f2f.k_hamming_knn2");
   if ((st = plf_launch_nnr(ctx, s->nnr_f2f, 2 * B, std::max(K, Ln)))) return st;
@@ -571,30 +595,43 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   if ((st = plf_launch_gn(ctx, s->gn_probs, B, plf_gn_opts_from_params(P)))) return st;
   plf_mark(ctx, "gn.k_gn_pose");
   k_finalize<<<(B + 127) / 128, 128, 0, cs>>>(s->gn_out, s->gnNp, s->gnNl, kcnt, lcnt, s->fs, 1, P.min_features,
-                                               s->has_prev ? 0 : 1, B, s->results);
+                                               s->has_prev ? 0 : 1, B, s->results[par]);
   PLF_LAUNCH_CHECK(ctx);
-  // carry the last frame
-  if ((st = copy_slot(ctx, s, B, 0))) return st;
+  if ((st = copy_slot(ctx, s, B, 0))) return st;  // carry the last frame to the next batch
   plf_mark(ctx, "k_finalize+carry");
+  // results + overflow flags to pinned memory as part of this batch's stream work; evM marks them ready
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->h_results[par], s->results[par], sizeof(plf_frame_result) * B, cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&s->h_ovf[par][0], plf_orb_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&s->h_ovf[par][1], plf_lsd_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaEventRecord(s->evM[par], cs));
   s->has_prev = true;
+  s->pend_par[s->n_pending] = par;
+  s->pend_B[s->n_pending] = B;
+  s->n_pending++;
+  s->seq++;
   return PLF_OK;
 }
 
+// Results of the OLDEST batch in flight (FIFO): waits for its match phase only, so a later batch keeps running.
 plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out) {
   if (!ctx || !ctx->pipe || !out || B < 1 || B > ctx->limits.max_batch)
     return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_download: bad arguments");
   PipeState* s = ctx->pipe;
-  PLF_CUDA(ctx, cudaMemcpyAsync(s->h_results, s->results, sizeof(plf_frame_result) * B, cudaMemcpyDeviceToHost, ctx->stream));
-  int ovf[2] = {0, 0};
-  PLF_CUDA(ctx, cudaMemcpyAsync(&ovf[0], plf_orb_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  PLF_CUDA(ctx, cudaMemcpyAsync(&ovf[1], plf_lsd_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  memcpy(out, s->h_results, sizeof(plf_frame_result) * B);
-  if (ovf[0] || ovf[1]) {
+  if (s->n_pending == 0) return plf_fail(ctx, PLF_ERR_STATE, "plf_batch_download: no batch in flight");
+  const int par = s->pend_par[0];
+  if (B != s->pend_B[0])
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_download: B=%d but the oldest batch in flight has %d pairs", B, s->pend_B[0]);
+  PLF_CUDA(ctx, cudaEventSynchronize(s->evM[par]));
+  s->pend_par[0] = s->pend_par[1];
+  s->pend_B[0] = s->pend_B[1];
+  s->n_pending--;
+  memcpy(out, s->h_results[par], sizeof(plf_frame_result) * B);
+  if (s->h_ovf[par][0] || s->h_ovf[par][1]) {
+    const int o0 = s->h_ovf[par][0], o1 = s->h_ovf[par][1];
     cudaMemsetAsync(plf_orb_overflow_flag(ctx), 0, sizeof(int), ctx->stream);
     cudaMemsetAsync(plf_lsd_overflow_flag(ctx), 0, sizeof(int), ctx->stream);
     return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_batch_download: a fixed-capacity buffer overflowed (%s%s); raise plf_limits",
-                    ovf[0] ? "ORB keypoints " : "", ovf[1] ? "LSD segments/lines" : "");
+                    o0 ? "ORB keypoints " : "", o1 ? "LSD segments/lines" : "");
   }
   return PLF_OK;
 }

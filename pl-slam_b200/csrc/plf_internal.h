@@ -133,18 +133,18 @@ plf_gn_opts plf_gn_opts_from_params(const plf_params& p);
 plf_status plf_launch_gn(plf_ctx* ctx, const GnProblem* d_probs, int nprob, const plf_gn_opts& o);
 
 // ---- ORB (orb.cu) --------------------------------------------------------------------------------
-plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg);
-plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg);
-void plf_orb_outputs(plf_ctx* ctx, plf_keypoint** kps, uint8_t** desc, int** counts, int* max_kp);
+plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_parities);
+plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg, int par);
+void plf_orb_outputs(plf_ctx* ctx, int par, plf_keypoint** kps, uint8_t** desc, int** counts, int* max_kp);
 void plf_linear_coeffs_host(int srcsize, int dstsize, double scale, int* ofs, int* c1);
 plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_stride, int sw, int sh, uint8_t* dst,
                                    size_t dst_stride, int dw, int dh, const int* tabx, const int* taby, int nimg);
 
 // ---- LSD (lsd.cu) --------------------------------------------------------------------------------
-plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg);
+plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_parities);
 plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg);
-// same, for images [img0, img0+n) of a batch whose state was prepared for >= img0+n images (enqueued on ctx->cur)
-plf_status plf_lsd_run_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int img0, int n);
-void plf_lsd_outputs(plf_ctx* ctx, plf_keyline** kls, int** nlines, int* max_lines);
+plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int par, int img0, int n);
+plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int n);
+void plf_lsd_outputs(plf_ctx* ctx, int par, plf_keyline** kls, int** nlines, int* max_lines);
 int* plf_orb_overflow_flag(plf_ctx* ctx);
 int* plf_lsd_overflow_flag(plf_ctx* ctx);
