@@ -57,45 +57,47 @@ __global__ void __launch_bounds__(256) k_blur5_sobel(const uint8_t* __restrict__
   short2* out = grad + (size_t)blockIdx.z * grad_stride;
   const int x0 = blockIdx.x * LBD_TW, y0 = blockIdx.y * LBD_TH;
   const int tid = threadIdx.x;
-  // stage raw tile with reflect-101 on load
-  for (int i = tid; i < (LBD_TH + 6) * (LBD_TW + 6); i += 256) {
-    const int ry = i / (LBD_TW + 6), rx = i - ry * (LBD_TW + 6);
-    const int gx = reflect101(x0 - 3 + rx, w), gy = reflect101(y0 - 3 + ry, h);
-    raw[ry][rx] = img[(size_t)gy * pitch + gx];
+  // stage raw tile with reflect-101 on load: one warp per row, lanes along x
+  const int lane = tid & 31, wrp = tid >> 5;
+  const bool interior = x0 >= 3 && x0 + LBD_TW + 3 <= w && y0 >= 3 && y0 + LBD_TH + 3 <= h;
+  for (int ry = wrp; ry < LBD_TH + 6; ry += 8) {
+    const int gy = interior ? y0 - 3 + ry : reflect101(y0 - 3 + ry, h);
+    const uint8_t* row = img + (size_t)gy * pitch;
+    for (int rx = lane; rx < LBD_TW + 6; rx += 32) raw[ry][rx] = row[interior ? x0 - 3 + rx : reflect101(x0 - 3 + rx, w)];
   }
   __syncthreads();
-  // horizontal 5-tap pass for halo-1 columns, all halo-3 rows
-  for (int i = tid; i < (LBD_TH + 6) * (LBD_TW + 2); i += 256) {
-    const int ry = i / (LBD_TW + 2), cx = i - ry * (LBD_TW + 2);
-    const uint8_t* p = &raw[ry][cx];  // taps at coords (x0-1+cx) + {-2..2} = raw offsets cx..cx+4
-    hrow[ry][cx] = (uint16_t)(14 * p[0] + 62 * p[1] + 104 * p[2] + 62 * p[3] + 14 * p[4]);
-  }
+  // horizontal 5-tap pass for halo-1 columns, all halo-3 rows (66 columns: lanes 0..31 take cx, cx+32, and 64/65)
+  for (int ry = wrp; ry < LBD_TH + 6; ry += 8)
+    for (int cx = lane; cx < LBD_TW + 2; cx += 32) {
+      const uint8_t* p = &raw[ry][cx];  // taps at coords (x0-1+cx) + {-2..2} = raw offsets cx..cx+4
+      hrow[ry][cx] = (uint16_t)(14 * p[0] + 62 * p[1] + 104 * p[2] + 62 * p[3] + 14 * p[4]);
+    }
   __syncthreads();
-  // vertical pass -> blurred (halo 1).  Positions whose coordinate lies outside the image are filled below.
-  for (int i = tid; i < (LBD_TH + 2) * (LBD_TW + 2); i += 256) {
-    const int by = i / (LBD_TW + 2), bx = i - by * (LBD_TW + 2);
-    const uint32_t a = 14u * hrow[by][bx] + 62u * hrow[by + 1][bx] + 104u * hrow[by + 2][bx] +
-                       62u * hrow[by + 3][bx] + 14u * hrow[by + 4][bx];
-    const uint32_t v = (a + (1u << 15)) >> 16;
-    blur[by][bx] = (uint8_t)(v > 255 ? 255 : v);
-  }
+  // vertical pass -> blurred (halo 1)
+  for (int by = wrp; by < LBD_TH + 2; by += 8)
+    for (int bx = lane; bx < LBD_TW + 2; bx += 32) {
+      const uint32_t a = 14u * hrow[by][bx] + 62u * hrow[by + 1][bx] + 104u * hrow[by + 2][bx] +
+                         62u * hrow[by + 3][bx] + 14u * hrow[by + 4][bx];
+      const uint32_t v = (a + (1u << 15)) >> 16;
+      blur[by][bx] = (uint8_t)(v > 255 ? 255 : v);
+    }
   __syncthreads();
-  // Sobel's own BORDER_REFLECT_101 acts on the *blurred* image: blurred(-1) = blurred(1) etc.
-  // A raw tile staged with reflect-101 reproduces that only approximately at the border (the blur of
-  // reflected pixels at coordinate -1 equals the blur at coordinate 1 because the 5-tap window is
-  // symmetric and reflect-101 is an even extension) -- it is exact: blur(-1) uses raw(-3..1) =
-  // raw(3,2,1,0,1) which is the mirror image of raw(-1..3) = raw(1,0,1,2,3) used by blur(1). Taps are
-  // symmetric, so the two sums are equal.  No fix-up needed.
-  for (int i = tid; i < LBD_TH * LBD_TW; i += 256) {
-    const int ty = i / LBD_TW, tx = i - ty * LBD_TW;
-    const int gx = x0 + tx, gy = y0 + ty;
-    if (gx >= w || gy >= h) continue;
-    const int a00 = blur[ty][tx], a01 = blur[ty][tx + 1], a02 = blur[ty][tx + 2];
-    const int a10 = blur[ty + 1][tx], a12 = blur[ty + 1][tx + 2];
-    const int a20 = blur[ty + 2][tx], a21 = blur[ty + 2][tx + 1], a22 = blur[ty + 2][tx + 2];
-    const int dx = (a02 - a00) + 2 * (a12 - a10) + (a22 - a20);
-    const int dy = (a20 - a00) + 2 * (a21 - a01) + (a22 - a02);
-    out[(size_t)gy * w + gx] = make_short2((short)dx, (short)dy);
+  // Sobel's own BORDER_REFLECT_101 acts on the *blurred* image (blurred(-1) = blurred(1)).  The raw tile was staged
+  // with reflect-101, and the 5-tap window is symmetric, so blur computed at coordinate -1 from reflected pixels equals
+  // the blur at coordinate 1 exactly (mirror-image taps): no fix-up needed at the image border.
+  const int tx = tid & (LBD_TW - 1), rg = tid >> 6;  // LBD_TW == 64
+  const int gx = x0 + tx;
+  if (gx < w) {
+    for (int ty = rg; ty < LBD_TH; ty += 4) {
+      const int gy = y0 + ty;
+      if (gy >= h) break;
+      const int a00 = blur[ty][tx], a01 = blur[ty][tx + 1], a02 = blur[ty][tx + 2];
+      const int a10 = blur[ty + 1][tx], a12 = blur[ty + 1][tx + 2];
+      const int a20 = blur[ty + 2][tx], a21 = blur[ty + 2][tx + 1], a22 = blur[ty + 2][tx + 2];
+      const int dx = (a02 - a00) + 2 * (a12 - a10) + (a22 - a20);
+      const int dy = (a20 - a00) + 2 * (a21 - a01) + (a22 - a02);
+      out[(size_t)gy * w + gx] = make_short2((short)dx, (short)dy);
+    }
   }
 }
 

@@ -73,6 +73,7 @@ struct LsdState {
   int* overflow = nullptr;    // [1]
   int* rs_tab = nullptr;      // resize tables
   size_t rs_x_off = 0, rs_y_off = 0;
+  float4* grad_lut = nullptr; // [1021*1021] gradient -> {angle, cos, sin}
 };
 
 __constant__ int c_lsd_taps[16];
@@ -98,27 +99,32 @@ __global__ void __launch_bounds__(256) k_blur_q8(const uint8_t* __restrict__ src
   uint8_t* d = dst + (size_t)blockIdx.z * dst_stride;
   const int x0 = blockIdx.x * BQ_TW, y0 = blockIdx.y * BQ_TH, tid = threadIdx.x;
   const int RW = BQ_TW + 2 * r, RH = BQ_TH + 2 * r;
-  for (int i = tid; i < RH * RW; i += 256) {
-    const int ry = i / RW, rx = i - ry * RW;
-    raw[ry][rx] = s[(size_t)lsd_reflect101(y0 - r + ry, h) * pitch + lsd_reflect101(x0 - r + rx, w)];
+  const int lane = tid & 31, wrp = tid >> 5;
+  const bool interior = x0 >= r && x0 + BQ_TW + r <= w && y0 >= r && y0 + BQ_TH + r <= h;
+  for (int ry = wrp; ry < RH; ry += 8) {  // one warp per row, lanes along x
+    const int gy = interior ? y0 - r + ry : lsd_reflect101(y0 - r + ry, h);
+    const uint8_t* row = s + (size_t)gy * pitch;
+    for (int rx = lane; rx < RW; rx += 32) raw[ry][rx] = row[interior ? x0 - r + rx : lsd_reflect101(x0 - r + rx, w)];
   }
   __syncthreads();
   const int ks = 2 * r + 1;
-  for (int i = tid; i < RH * BQ_TW; i += 256) {
-    const int ry = i / BQ_TW, tx = i - ry * BQ_TW;
+  const int tx = tid & (BQ_TW - 1), rg = tid >> 6;  // BQ_TW == 64
+  for (int ry = rg; ry < RH; ry += 4) {
     uint32_t a = 0;
     for (int k = 0; k < ks; ++k) a += (uint32_t)c_lsd_taps[k] * raw[ry][tx + k];
     hrow[ry][tx] = (uint16_t)a;
   }
   __syncthreads();
-  for (int i = tid; i < BQ_TH * BQ_TW; i += 256) {
-    const int ty = i / BQ_TW, tx = i - ty * BQ_TW;
-    const int gx = x0 + tx, gy = y0 + ty;
-    if (gx >= w || gy >= h) continue;
-    uint32_t a = 0;
-    for (int k = 0; k < ks; ++k) a += (uint32_t)c_lsd_taps[k] * hrow[ty + k][tx];
-    const uint32_t v = (a + (1u << 15)) >> 16;
-    d[(size_t)gy * w + gx] = (uint8_t)(v > 255 ? 255 : v);
+  const int gx = x0 + tx;
+  if (gx < w) {
+    for (int ty = rg; ty < BQ_TH; ty += 4) {
+      const int gy = y0 + ty;
+      if (gy >= h) break;
+      uint32_t a = 0;
+      for (int k = 0; k < ks; ++k) a += (uint32_t)c_lsd_taps[k] * hrow[ty + k][tx];
+      const uint32_t v = (a + (1u << 15)) >> 16;
+      d[(size_t)gy * w + gx] = (uint8_t)(v > 255 ? 255 : v);
+    }
   }
 }
 
@@ -144,10 +150,30 @@ __device__ __forceinline__ float lsd_fast_atan2(float y, float x) {  // cv::fast
   return a;
 }
 
+// Gradient lookup table.  The 2x2 gradient (gx, gy) takes 1021 x 1021 integer values; the level-line angle
+// cv::fastAtan2(gx, -gy), the NOTDEF decision (|grad| <= rho) and cosf/sinf of float(angle) are functions of (gx, gy)
+// only.  They are tabulated once per context with exactly the device functions below (16 MB, L2-resident), which turns
+// ~200 dependent instructions per defined pixel into one 16-byte load.  Entry = {angle_deg | NOTDEF, cosf, sinf, 0}.
+#define LSD_LUT_DIM 1021
+__global__ void __launch_bounds__(256) k_lsd_build_lut(double rho, float4* __restrict__ lut) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= LSD_LUT_DIM * LSD_LUT_DIM) return;
+  const int gx = i / LSD_LUT_DIM - 510, gy = i % LSD_LUT_DIM - 510;
+  float4 e = make_float4(LSD_NOTDEF, 0.f, 0.f, 0.f);
+  const double norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
+  if (!(norm <= rho)) {
+    const float a = lsd_fast_atan2((float)gx, (float)(-gy));
+    // region_grow adds cos(float(angle)), sin(float(angle)) (host libm cosf/sinf): bit-exact glibc port
+    const float af = (float)((double)a * LSD_DEG2RAD);
+    e = make_float4(a, glibc_cosf(af), glibc_sinf(af), 0.f);
+  }
+  lut[i] = e;
+}
+
 __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int W, int H,
-                                                  double rho, size_t stride, short2* __restrict__ gxy,
-                                                  float* __restrict__ adeg, float2* __restrict__ cs,
-                                                  int* __restrict__ maxmag2) {
+                                                  const float4* __restrict__ lut, size_t stride,
+                                                  short2* __restrict__ gxy, float* __restrict__ adeg,
+                                                  float2* __restrict__ cs, int* __restrict__ maxmag2) {
   const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, im = blockIdx.z;
   int mag2 = -1;
   if (x < W) {
@@ -161,16 +187,10 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ im
       const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
       const int gx = DA + BC, gy = DA - BC;
       g = make_short2((short)gx, (short)gy);
-      const int m2 = gx * gx + gy * gy;
-      const double norm = sqrt((double)m2 / 4.0);
-      if (!(norm <= rho)) {
-        a = lsd_fast_atan2((float)gx, (float)(-gy));
-        mag2 = m2;
-        // region_grow adds cos(float(angle)), sin(float(angle)) (host libm cosf/sinf) for every accepted pixel:
-        // evaluated here, in parallel, with the bit-exact glibc port
-        const float af = (float)((double)a * LSD_DEG2RAD);
-        c2 = make_float2(glibc_cosf(af), glibc_sinf(af));
-      }
+      const float4 e = __ldg(&lut[(gx + 510) * LSD_LUT_DIM + (gy + 510)]);
+      a = e.x;
+      c2 = make_float2(e.y, e.z);
+      if (a != LSD_NOTDEF) mag2 = gx * gx + gy * gy;
     }
     gxy[o] = g;
     adeg[o] = a;
@@ -632,6 +652,7 @@ static void lsd_release(LsdState* s) {
   }
   cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap);
   cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->overflow); cudaFree(s->rs_tab);
+  cudaFree(s->grad_lut);
 }
 
 extern "C" void plf_lsd_free(plf_ctx* ctx) {
@@ -731,6 +752,10 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   }
   PLF_CUDA(ctx, cudaMalloc(&s->overflow, sizeof(int)));
   PLF_CUDA(ctx, cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream));
+  PLF_CUDA(ctx, cudaMalloc(&s->grad_lut, (size_t)LSD_LUT_DIM * LSD_LUT_DIM * sizeof(float4)));
+  k_lsd_build_lut<<<(LSD_LUT_DIM * LSD_LUT_DIM + 255) / 256, 256, 0, ctx->stream>>>(s->rho, s->grad_lut);
+  PLF_LAUNCH_CHECK(ctx);
+  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (s->scale != 1.0) {
     PLF_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lsd_taps, s->taps, sizeof(int) * 16, 0, cudaMemcpyHostToDevice, ctx->stream));
     std::vector<int> tab(2 * (size_t)s->ws + 2 * (size_t)s->hs);
@@ -783,7 +808,7 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
     scaled_stride = As;
   }
   PLF_CUDA(ctx, cudaMemsetAsync(maxmag2, 0xFF, (size_t)n * sizeof(int), cs));  // -1
-  k_lsd_grad<<<dim3((W + 255) / 256, H, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->rho, As, gxy, adeg, csm, maxmag2);
+  k_lsd_grad<<<dim3((W + 255) / 256, H, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->grad_lut, As, gxy, adeg, csm, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
   k_lsd_rowhist<<<dim3(H - 1, n), 256, 0, cs>>>(gxy, adeg, As, W, H, s->n_bins, maxmag2, binmap, rowcnt);

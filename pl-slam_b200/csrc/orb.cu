@@ -155,45 +155,72 @@ __global__ void __launch_bounds__(256) k_fast_nms(const uint8_t* __restrict__ im
   __shared__ uint8_t px[ORB_TH + 8][ORB_TW + 8];   // halo 4
   __shared__ uint8_t sc[ORB_TH + 2][ORB_TW + 4];   // halo 1 (padded)
   const int tid = threadIdx.x;
-  for (int i = tid; i < (ORB_TH + 8) * (ORB_TW + 8); i += 256) {
-    const int ry = i / (ORB_TW + 8), rx = i - ry * (ORB_TW + 8);
-    const int gx = min(max(x0 - 4 + rx, 0), W - 1), gy = min(max(y0 - 4 + ry, 0), H - 1);
-    px[ry][rx] = src[(size_t)gy * W + gx];
+  {  // stage the tile: one warp per row, lanes along x (no div/mod); coordinates clamped (values outside are never used)
+    const int lane = tid & 31, wrp = tid >> 5;
+    for (int ry = wrp; ry < ORB_TH + 8; ry += 8) {
+      const uint8_t* row = src + (size_t)min(max(y0 - 4 + ry, 0), H - 1) * W;
+      for (int rx = lane; rx < ORB_TW + 8; rx += 32) px[ry][rx] = row[min(max(x0 - 4 + rx, 0), W - 1)];
+    }
   }
   __syncthreads();
   const int th = g.fast_th;
-  for (int i = tid; i < (ORB_TH + 2) * (ORB_TW + 2); i += 256) {
+  // Pass A: cheap rejection for every pixel of the tile (+1 halo).  A 9-arc of the 16-ring always contains one pixel
+  // of every opposite pair (k, k+8) (OpenCV's FAST_t uses the same test), so a pair with both members inside the
+  // threshold band rules the pixel out.  Survivors (a few %) are compacted into a shared list so that pass B runs the
+  // full ring test on dense warps instead of dragging every warp through it.
+  __shared__ unsigned short clist[(ORB_TH + 2) * (ORB_TW + 2)];
+  __shared__ int ccount;
+  if (tid == 0) ccount = 0;
+  __syncthreads();
+  for (int i0 = 0; i0 < (ORB_TH + 2) * (ORB_TW + 2); i0 += 256) {  // uniform trip count: full-warp ballots below
+    const int i = i0 + tid;
+    const bool in_range = i < (ORB_TH + 2) * (ORB_TW + 2);
     const int sy = i / (ORB_TW + 2), sx = i - sy * (ORB_TW + 2);
     const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
-    int score = 0;
-    if (gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3) {
+    bool cand_px = false;
+    if (in_range && gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3) {
       const int cy = sy + 3, cx = sx + 3;  // position in px
       const int v = px[cy][cx];
-      // Quick rejection (as OpenCV's FAST_t): a 9-arc of the 16-ring always contains one pixel of every opposite
-      // pair (k, k+8), so both members of any pair within the threshold band rules the pixel out.
       const int q0 = v - px[cy + 3][cx], q8 = v - px[cy - 3][cx];
       bool pd = (q0 > th) | (q8 > th), pb = (q0 < -th) | (q8 < -th);
-      if (!(pd | pb)) { sc[sy][sx] = 0; continue; }
-      const int q4 = v - px[cy][cx + 3], q12 = v - px[cy][cx - 3];
-      pd &= (q4 > th) | (q12 > th);
-      pb &= (q4 < -th) | (q12 < -th);
-      if (!(pd | pb)) { sc[sy][sx] = 0; continue; }
-      int d[16];
-      d[0] = q0;                      d[1] = v - px[cy + 3][cx + 1];  d[2] = v - px[cy + 2][cx + 2];
-      d[3] = v - px[cy + 1][cx + 3];  d[4] = q4;                      d[5] = v - px[cy - 1][cx + 3];
-      d[6] = v - px[cy - 2][cx + 2];  d[7] = v - px[cy - 3][cx + 1];  d[8] = q8;
-      d[9] = v - px[cy - 3][cx - 1];  d[10] = v - px[cy - 2][cx - 2]; d[11] = v - px[cy - 1][cx - 3];
-      d[12] = q12;                    d[13] = v - px[cy + 1][cx - 3]; d[14] = v - px[cy + 2][cx - 2];
-      d[15] = v - px[cy + 3][cx - 1];
-      uint32_t md = 0, mb = 0;
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        md |= (d[k] > th ? 1u : 0u) << k;   // neighbour darker than centre by more than th
-        mb |= (d[k] < -th ? 1u : 0u) << k;  // brighter
+      if (pd | pb) {
+        const int q4 = v - px[cy][cx + 3], q12 = v - px[cy][cx - 3];
+        pd &= (q4 > th) | (q12 > th);
+        pb &= (q4 < -th) | (q12 < -th);
+        cand_px = pd | pb;
       }
-      if (has_run9(md) || has_run9(mb)) score = fast_corner_score(d);
     }
-    sc[sy][sx] = (uint8_t)score;
+    if (in_range) sc[sy][sx] = 0;
+    const unsigned bal = __ballot_sync(0xFFFFFFFFu, cand_px);
+    if (bal) {
+      const int lane = tid & 31, leader = __ffs(bal) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(&ccount, __popc(bal));
+      base = __shfl_sync(0xFFFFFFFFu, base, leader);
+      if (cand_px) clist[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)i;
+    }
+  }
+  __syncthreads();
+  const int nc = ccount;
+  for (int c = tid; c < nc; c += 256) {
+    const int i = clist[c];
+    const int sy = i / (ORB_TW + 2), sx = i - sy * (ORB_TW + 2);
+    const int cy = sy + 3, cx = sx + 3;
+    const int v = px[cy][cx];
+    int d[16];
+    d[0] = v - px[cy + 3][cx];      d[1] = v - px[cy + 3][cx + 1];  d[2] = v - px[cy + 2][cx + 2];
+    d[3] = v - px[cy + 1][cx + 3];  d[4] = v - px[cy][cx + 3];      d[5] = v - px[cy - 1][cx + 3];
+    d[6] = v - px[cy - 2][cx + 2];  d[7] = v - px[cy - 3][cx + 1];  d[8] = v - px[cy - 3][cx];
+    d[9] = v - px[cy - 3][cx - 1];  d[10] = v - px[cy - 2][cx - 2]; d[11] = v - px[cy - 1][cx - 3];
+    d[12] = v - px[cy][cx - 3];     d[13] = v - px[cy + 1][cx - 3]; d[14] = v - px[cy + 2][cx - 2];
+    d[15] = v - px[cy + 3][cx - 1];
+    uint32_t md = 0, mb = 0;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      md |= (d[k] > th ? 1u : 0u) << k;   // neighbour darker than centre by more than th
+      mb |= (d[k] < -th ? 1u : 0u) << k;  // brighter
+    }
+    if (has_run9(md) || has_run9(mb)) sc[sy][sx] = (uint8_t)fast_corner_score(d);
   }
   __syncthreads();
   for (int i = tid; i < ORB_TH * ORB_TW; i += 256) {
@@ -384,31 +411,37 @@ __global__ void __launch_bounds__(256) k_orb_blur7(const uint8_t* __restrict__ i
   uint8_t* dst = blur + (size_t)img * g.blur_stride + g.blur_off[l];
   __shared__ uint8_t raw[ORB_TH + 6][ORB_TW + 8];
   __shared__ float hrow[ORB_TH + 6][ORB_TW];
-  const int tid = threadIdx.x;
-  for (int i = tid; i < (ORB_TH + 6) * (ORB_TW + 6); i += 256) {
-    const int ry = i / (ORB_TW + 6), rx = i - ry * (ORB_TW + 6);
-    raw[ry][rx] = src[(size_t)orb_reflect101(y0 - 3 + ry, H) * W + orb_reflect101(x0 - 3 + rx, W)];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const bool interior = x0 >= 3 && x0 + ORB_TW + 3 <= W && y0 >= 3 && y0 + ORB_TH + 3 <= H;
+  for (int ry = wrp; ry < ORB_TH + 6; ry += 8) {  // one warp per row, lanes along x
+    const int gy = interior ? y0 - 3 + ry : orb_reflect101(y0 - 3 + ry, H);
+    const uint8_t* row = src + (size_t)gy * W;
+    for (int rx = lane; rx < ORB_TW + 6; rx += 32) raw[ry][rx] = row[interior ? x0 - 3 + rx : orb_reflect101(x0 - 3 + rx, W)];
   }
   __syncthreads();
-  for (int i = tid; i < (ORB_TH + 6) * ORB_TW; i += 256) {
-    const int ry = i / ORB_TW, tx = i - ry * ORB_TW;
+  const int tx = tid & (ORB_TW - 1), rg = tid >> 6;  // ORB_TW == 64: column = low 6 bits, 4 row groups
+  const float k0 = c_blur7[0], k1 = c_blur7[1], k2 = c_blur7[2], k3 = c_blur7[3], k4 = c_blur7[4], k5 = c_blur7[5], k6 = c_blur7[6];
+  for (int ry = rg; ry < ORB_TH + 6; ry += 4) {
     const uint8_t* p = &raw[ry][tx];
-    float a = __fmul_rn(c_blur7[0], (float)p[0]);
-#pragma unroll
-    for (int k = 1; k < 7; ++k) a = __fmaf_rn(c_blur7[k], (float)p[k], a);
+    float a = __fmul_rn(k0, (float)p[0]);
+    a = __fmaf_rn(k1, (float)p[1], a); a = __fmaf_rn(k2, (float)p[2], a); a = __fmaf_rn(k3, (float)p[3], a);
+    a = __fmaf_rn(k4, (float)p[4], a); a = __fmaf_rn(k5, (float)p[5], a); a = __fmaf_rn(k6, (float)p[6], a);
     hrow[ry][tx] = a;
   }
   __syncthreads();
-  for (int i = tid; i < ORB_TH * ORB_TW; i += 256) {
-    const int ty = i / ORB_TW, tx = i - ty * ORB_TW;
-    const int gx = x0 + tx, gy = y0 + ty;
-    if (gx >= W || gy >= H) continue;
-    float a = __fmul_rn(c_blur7[3], hrow[ty + 3][tx]);
-#pragma unroll
-    for (int k = 1; k <= 3; ++k) a = __fmaf_rn(c_blur7[3 + k], __fadd_rn(hrow[ty + 3 + k][tx], hrow[ty + 3 - k][tx]), a);
-    int v = __float2int_rn(a);
-    v = v < 0 ? 0 : (v > 255 ? 255 : v);
-    dst[(size_t)gy * W + gx] = (uint8_t)v;
+  const int gx = x0 + tx;
+  if (gx < W) {
+    for (int ty = rg; ty < ORB_TH; ty += 4) {
+      const int gy = y0 + ty;
+      if (gy >= H) break;
+      float a = __fmul_rn(k3, hrow[ty + 3][tx]);
+      a = __fmaf_rn(k4, __fadd_rn(hrow[ty + 4][tx], hrow[ty + 2][tx]), a);
+      a = __fmaf_rn(k5, __fadd_rn(hrow[ty + 5][tx], hrow[ty + 1][tx]), a);
+      a = __fmaf_rn(k6, __fadd_rn(hrow[ty + 6][tx], hrow[ty][tx]), a);
+      int v = __float2int_rn(a);
+      v = v < 0 ? 0 : (v > 255 ? 255 : v);
+      dst[(size_t)gy * W + gx] = (uint8_t)v;
+    }
   }
 }
 
