@@ -161,7 +161,7 @@ def run_reference(args, rank):
         return
     from oracle import baseline
     cores = os.cpu_count() or 1
-    n = max(8, min(4 * cores, 96))         # bounded sample per step
+    n = max(8, min(4 * cores, 512))        # bounded sample per step: a few waves over all cores
     pool = render_pool(CAM, min(n, 24), seed=0)
     pairs = [pool[i % len(pool)] for i in range(n)]
     for _ in range(args.warmup):
@@ -178,10 +178,27 @@ def run_reference(args, rank):
                 cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
                                   sample=f"{n} pairs/step x {args.steps} steps: cv2 4.13 ORB+LSD+BFMatcher + C LBD/GN, {cores} worker processes"),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
-    print(json.dumps(line))
+    emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The one JSON line goes to the process's original stdout; everything else (NCCL banners, library chatter) was
+    redirected to stderr at start-up."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)           # stdout of this process (and of any library writing to fd 1) -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -333,7 +350,7 @@ def main():
             v, c, dt = cpu_baseline_run(min(n, 24) if n <= 24 else 24, None)
             line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=c, kind="port",
                                         sample="%d rendered pairs of the same stream, one pass (%.1f s): cv2 4.13 ORB+LSD+BFMatcher + C LBD/GN, %d worker processes" % (min(n, 24), dt, c))
-        print(json.dumps(line))
+        emit(line)
     fe.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -101,11 +101,105 @@ __global__ void __launch_bounds__(256) k_blur5_sobel(const uint8_t* __restrict__
   }
 }
 
+// Fast variant: 64x32 outputs per CTA, DP4A row pass (taps 14,62,104,62 | 14 packed as u8), 4-column vertical pass,
+// register-sliding Sobel.  Same integer arithmetic as k_blur5_sobel (bit-identical), ~4x fewer instructions per pixel.
+#define LBF_TW 64
+#define LBF_TH 32
+__global__ void __launch_bounds__(256) k_blur5_sobel_fast(const uint8_t* __restrict__ imgs, int pitch, size_t img_stride,
+                                                           int w, int h, short2* __restrict__ grad, size_t grad_stride) {
+  constexpr int RH = LBF_TH + 6;   // raw rows: halo 3 (blur 2 + sobel 1)
+  constexpr int RP = 76;           // raw row pitch (bytes): 68 blurred columns + 4 taps + word slack, multiple of 4
+  constexpr int BW = 68;           // blurred columns computed (66 needed, rounded to groups of 4)
+  __shared__ __align__(16) uint8_t raw[RH][RP];
+  __shared__ __align__(16) uint16_t hrow[RH][BW];
+  __shared__ __align__(16) uint8_t blur[LBF_TH + 2][BW + 4];
+  const uint8_t* img = imgs + (size_t)blockIdx.z * img_stride;
+  short2* out = grad + (size_t)blockIdx.z * grad_stride;
+  const int x0 = blockIdx.x * LBF_TW, y0 = blockIdx.y * LBF_TH, tid = threadIdx.x;
+  const int lane = tid & 31, wrp = tid >> 5;
+  const bool interior = x0 >= 3 && x0 - 3 + RP <= w && y0 >= 3 && y0 + LBF_TH + 3 <= h;
+  for (int ry = wrp; ry < RH; ry += 8) {
+    const int gy = interior ? y0 - 3 + ry : reflect101(y0 - 3 + ry, h);
+    const uint8_t* row = img + (size_t)gy * pitch;
+    for (int rx = lane; rx < RP; rx += 32) raw[ry][rx] = row[interior ? x0 - 3 + rx : reflect101(x0 - 3 + rx, w)];
+  }
+  __syncthreads();
+  const uint32_t tapsA = 14u | (62u << 8) | (104u << 16) | (62u << 24), tapsB = 14u;
+  // horizontal pass: blurred column b (coordinate x0-1+b) uses raw offsets b..b+4
+  for (int it = tid; it < RH * (BW / 4); it += 256) {
+    const int ry = it / (BW / 4), j = it - ry * (BW / 4);
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(&raw[ry][4 * j]);
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t lo = __byte_perm(w0, w1, 0x3210 + 0x1111 * i);
+      const uint32_t hi = __byte_perm(w1, w2, 0x3210 + 0x1111 * i);
+      o[i] = __dp4a(hi, tapsB, __dp4a(lo, tapsA, 0u));
+    }
+    *reinterpret_cast<uint2*>(&hrow[ry][4 * j]) = make_uint2(o[0] | (o[1] << 16), o[2] | (o[3] << 16));
+  }
+  __syncthreads();
+  // vertical pass -> blurred bytes (rows y0-1 .. y0+32, columns x0-1 .. x0+66)
+  for (int it = tid; it < (LBF_TH + 2) * (BW / 4); it += 256) {
+    const int by = it / (BW / 4), j = it - by * (BW / 4);
+    uint32_t acc[4] = {0, 0, 0, 0};
+    const uint32_t tp[5] = {14u, 62u, 104u, 62u, 14u};
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      const uint2 v = *reinterpret_cast<const uint2*>(&hrow[by + k][4 * j]);
+      acc[0] += tp[k] * (v.x & 0xFFFFu); acc[1] += tp[k] * (v.x >> 16);
+      acc[2] += tp[k] * (v.y & 0xFFFFu); acc[3] += tp[k] * (v.y >> 16);
+    }
+    uint32_t pk = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const uint32_t v = (acc[i] + (1u << 15)) >> 16;
+      pk |= (v > 255 ? 255u : v) << (8 * i);
+    }
+    *reinterpret_cast<uint32_t*>(&blur[by][4 * j]) = pk;
+  }
+  __syncthreads();
+  // Sobel (BORDER_REFLECT_101 on the blurred image is reproduced by the reflect-staged raw tile, see k_blur5_sobel)
+  const int tx = tid & 63, q = tid >> 6;
+  const int gx = x0 + tx;
+  if (gx < w) {
+    int a0[3], a1[3], a2[3];
+    const int by0 = q * 8;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      a0[i] = blur[by0][tx + i];
+      a1[i] = blur[by0 + 1][tx + i];
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) a2[i] = blur[by0 + r + 2][tx + i];
+      const int gy = y0 + by0 + r;
+      if (gy < h) {
+        const int dx = (a0[2] - a0[0]) + 2 * (a1[2] - a1[0]) + (a2[2] - a2[0]);
+        const int dy = (a2[0] - a0[0]) + 2 * (a2[1] - a0[1]) + (a2[2] - a0[2]);
+        out[(size_t)gy * w + gx] = make_short2((short)dx, (short)dy);
+      }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) {
+        a0[i] = a1[i];
+        a1[i] = a2[i];
+      }
+    }
+  }
+}
+
 plf_status plf_launch_blur5_sobel(plf_ctx* ctx, const uint8_t* imgs, int pitch, size_t img_stride,
                                   int w, int h, int nimg, short2* grad, size_t grad_stride) {
   if (nimg <= 0) return PLF_OK;
-  dim3 grid((w + LBD_TW - 1) / LBD_TW, (h + LBD_TH - 1) / LBD_TH, nimg);
-  k_blur5_sobel<<<grid, 256, 0, ctx->cur>>>(imgs, pitch, img_stride, w, h, grad, grad_stride);
+  if (w >= 8 && h >= 8) {
+    dim3 grid((w + LBF_TW - 1) / LBF_TW, (h + LBF_TH - 1) / LBF_TH, nimg);
+    k_blur5_sobel_fast<<<grid, 256, 0, ctx->cur>>>(imgs, pitch, img_stride, w, h, grad, grad_stride);
+  } else {  // tiny images: generic kernel
+    dim3 grid((w + LBD_TW - 1) / LBD_TW, (h + LBD_TH - 1) / LBD_TH, nimg);
+    k_blur5_sobel<<<grid, 256, 0, ctx->cur>>>(imgs, pitch, img_stride, w, h, grad, grad_stride);
+  }
   PLF_LAUNCH_CHECK(ctx);
   return PLF_OK;
 }

@@ -139,72 +139,76 @@ __device__ int fast_corner_score(const int* d /*16*/) {
   return best - 1;
 }
 
+// Tile = 62 x 30 output pixels; scores are needed on a 64 x 32 region (1-px halo for the NMS) and pixels on a 70 x 38
+// region (3-px ring).  All index arithmetic is lane + 32*k / warp + 8*k (no div/mod), every lane is active in every pass.
+#define FN_OW 62
+#define FN_OH 30
 __global__ void __launch_bounds__(256) k_fast_nms(const uint8_t* __restrict__ img0, size_t img0_stride,
-                                                  const uint8_t* __restrict__ pyr, OrbGeom g,
+                                                  const uint8_t* __restrict__ pyr, OrbGeom g, int l, int tiles_x,
                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_count,
                                                   int* __restrict__ hist, int* __restrict__ overflow) {
-  // which level does this tile belong to
-  int l = 0;
-  while (l + 1 < g.nlevels && (int)blockIdx.x >= g.tile_start[l + 1]) ++l;
-  const int t = blockIdx.x - g.tile_start[l];
   const int W = g.w[l], H = g.h[l];
-  const int x0 = (t % g.tiles_x[l]) * ORB_TW, y0 = (t / g.tiles_x[l]) * ORB_TH;
+  const int x0 = (blockIdx.x % tiles_x) * FN_OW, y0 = (blockIdx.x / tiles_x) * FN_OH;
   const int img = blockIdx.y;
   const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride
                                 : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
-  __shared__ uint8_t px[ORB_TH + 8][ORB_TW + 8];   // halo 4
-  __shared__ uint8_t sc[ORB_TH + 2][ORB_TW + 4];   // halo 1 (padded)
-  const int tid = threadIdx.x;
-  {  // stage the tile: one warp per row, lanes along x (no div/mod); coordinates clamped (values outside are never used)
-    const int lane = tid & 31, wrp = tid >> 5;
-    for (int ry = wrp; ry < ORB_TH + 8; ry += 8) {
-      const uint8_t* row = src + (size_t)min(max(y0 - 4 + ry, 0), H - 1) * W;
-      for (int rx = lane; rx < ORB_TW + 8; rx += 32) px[ry][rx] = row[min(max(x0 - 4 + rx, 0), W - 1)];
-    }
+  __shared__ uint8_t px[38][72];   // pixel (x0 - 4 + rx, y0 - 4 + ry)
+  __shared__ uint8_t sc[32][64];   // score of pixel (x0 - 1 + sx, y0 - 1 + sy)
+  __shared__ unsigned short clist[32 * 64];
+  __shared__ int ccount;
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  if (tid == 0) ccount = 0;
+  for (int ry = wrp; ry < 38; ry += 8) {  // coordinates clamped: values outside the image are never used by a valid score
+    const uint8_t* row = src + (size_t)min(max(y0 - 4 + ry, 0), H - 1) * W;
+    for (int rx = lane; rx < 70; rx += 32) px[ry][rx] = row[min(max(x0 - 4 + rx, 0), W - 1)];
   }
   __syncthreads();
   const int th = g.fast_th;
-  // Pass A: cheap rejection for every pixel of the tile (+1 halo).  A 9-arc of the 16-ring always contains one pixel
-  // of every opposite pair (k, k+8) (OpenCV's FAST_t uses the same test), so a pair with both members inside the
-  // threshold band rules the pixel out.  Survivors (a few %) are compacted into a shared list so that pass B runs the
-  // full ring test on dense warps instead of dragging every warp through it.
-  __shared__ unsigned short clist[(ORB_TH + 2) * (ORB_TW + 2)];
-  __shared__ int ccount;
-  if (tid == 0) ccount = 0;
-  __syncthreads();
-  for (int i0 = 0; i0 < (ORB_TH + 2) * (ORB_TW + 2); i0 += 256) {  // uniform trip count: full-warp ballots below
-    const int i = i0 + tid;
-    const bool in_range = i < (ORB_TH + 2) * (ORB_TW + 2);
-    const int sy = i / (ORB_TW + 2), sx = i - sy * (ORB_TW + 2);
-    const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
-    bool cand_px = false;
-    if (in_range && gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3) {
-      const int cy = sy + 3, cx = sx + 3;  // position in px
-      const int v = px[cy][cx];
-      const int q0 = v - px[cy + 3][cx], q8 = v - px[cy - 3][cx];
-      bool pd = (q0 > th) | (q8 > th), pb = (q0 < -th) | (q8 < -th);
-      if (pd | pb) {
-        const int q4 = v - px[cy][cx + 3], q12 = v - px[cy][cx - 3];
-        pd &= (q4 > th) | (q12 > th);
-        pb &= (q4 < -th) | (q12 < -th);
-        cand_px = pd | pb;
+  // Pass A: cheap rejection.  A 9-arc of the 16-ring always contains one pixel of every opposite pair (k, k+8)
+  // (OpenCV's FAST_t uses the same test): a pair with both members inside the threshold band rules the pixel out.
+  // Survivors are compacted so that pass B runs the full ring test on dense warps.
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int sy = wrp + 8 * a;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int sx = lane + 32 * b;
+      const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
+      bool cand_px = false;
+      if (gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3) {
+        const int cy = sy + 3, cx = sx + 3;
+        const int v = px[cy][cx];
+        const int q0 = v - px[cy + 3][cx], q8 = v - px[cy - 3][cx];
+        bool pd = (q0 > th) | (q8 > th), pb = (q0 < -th) | (q8 < -th);
+        if (pd | pb) {
+          const int q4 = v - px[cy][cx + 3], q12 = v - px[cy][cx - 3];
+          pd &= (q4 > th) | (q12 > th);
+          pb &= (q4 < -th) | (q12 < -th);
+          if (pd | pb) {
+            const int q2 = v - px[cy + 2][cx + 2], q10 = v - px[cy - 2][cx - 2];
+            const int q6 = v - px[cy - 2][cx + 2], q14 = v - px[cy + 2][cx - 2];
+            pd &= ((q2 > th) | (q10 > th)) & ((q6 > th) | (q14 > th));
+            pb &= ((q2 < -th) | (q10 < -th)) & ((q6 < -th) | (q14 < -th));
+            cand_px = pd | pb;
+          }
+        }
       }
-    }
-    if (in_range) sc[sy][sx] = 0;
-    const unsigned bal = __ballot_sync(0xFFFFFFFFu, cand_px);
-    if (bal) {
-      const int lane = tid & 31, leader = __ffs(bal) - 1;
-      int base = 0;
-      if (lane == leader) base = atomicAdd(&ccount, __popc(bal));
-      base = __shfl_sync(0xFFFFFFFFu, base, leader);
-      if (cand_px) clist[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)i;
+      sc[sy][sx] = 0;
+      const unsigned bal = __ballot_sync(0xFFFFFFFFu, cand_px);
+      if (bal) {
+        const int leader = __ffs(bal) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&ccount, __popc(bal));
+        base = __shfl_sync(0xFFFFFFFFu, base, leader);
+        if (cand_px) clist[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)(sy * 64 + sx);
+      }
     }
   }
   __syncthreads();
   const int nc = ccount;
   for (int c = tid; c < nc; c += 256) {
     const int i = clist[c];
-    const int sy = i / (ORB_TW + 2), sx = i - sy * (ORB_TW + 2);
+    const int sy = i >> 6, sx = i & 63;
     const int cy = sy + 3, cx = sx + 3;
     const int v = px[cy][cx];
     int d[16];
@@ -223,21 +227,28 @@ __global__ void __launch_bounds__(256) k_fast_nms(const uint8_t* __restrict__ im
     if (has_run9(md) || has_run9(mb)) sc[sy][sx] = (uint8_t)fast_corner_score(d);
   }
   __syncthreads();
-  for (int i = tid; i < ORB_TH * ORB_TW; i += 256) {
-    const int ty = i / ORB_TW, tx = i - ty * ORB_TW;
-    const int gx = x0 + tx, gy = y0 + ty;
-    const int s = sc[ty + 1][tx + 1];
-    if (s == 0) continue;
-    if (gx < g.edge || gx >= W - g.edge || gy < g.edge || gy >= H - g.edge) continue;  // runByImageBorder
-    if (!(s > sc[ty + 1][tx] && s > sc[ty + 1][tx + 2] && s > sc[ty][tx] && s > sc[ty][tx + 1] &&
-          s > sc[ty][tx + 2] && s > sc[ty + 2][tx] && s > sc[ty + 2][tx + 1] && s > sc[ty + 2][tx + 2]))
-      continue;
-    const int slot = atomicAdd(&cand_count[img * ORB_MAX_LEVELS + l], 1);
-    if (slot < g.cand_cap[l])
-      cand[(size_t)img * g.cand_stride + g.cand_off[l] + slot] = ((uint32_t)gy << 20) | ((uint32_t)gx << 8) | (uint32_t)s;
-    else
-      *overflow = 1;
-    atomicAdd(&hist[(img * ORB_MAX_LEVELS + l) * 256 + s], 1);
+  // NMS over the 62 x 30 interior of the score region + border filter + append
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const int sy = wrp + 8 * a;
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int sx = lane + 32 * b;
+      if (sy < 1 || sy > FN_OH || sx < 1 || sx > FN_OW) continue;
+      const int s = sc[sy][sx];
+      if (s == 0) continue;
+      const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
+      if (gx < g.edge || gx >= W - g.edge || gy < g.edge || gy >= H - g.edge) continue;  // runByImageBorder
+      if (!(s > sc[sy][sx - 1] && s > sc[sy][sx + 1] && s > sc[sy - 1][sx - 1] && s > sc[sy - 1][sx] &&
+            s > sc[sy - 1][sx + 1] && s > sc[sy + 1][sx - 1] && s > sc[sy + 1][sx] && s > sc[sy + 1][sx + 1]))
+        continue;
+      const int slot = atomicAdd(&cand_count[img * ORB_MAX_LEVELS + l], 1);
+      if (slot < g.cand_cap[l])
+        cand[(size_t)img * g.cand_stride + g.cand_off[l] + slot] = ((uint32_t)gy << 20) | ((uint32_t)gx << 8) | (uint32_t)s;
+      else
+        *overflow = 1;
+      atomicAdd(&hist[(img * ORB_MAX_LEVELS + l) * 256 + s], 1);
+    }
   }
 }
 
@@ -441,6 +452,70 @@ __global__ void __launch_bounds__(256) k_orb_blur7(const uint8_t* __restrict__ i
       int v = __float2int_rn(a);
       v = v < 0 ? 0 : (v > 255 ? 255 : v);
       dst[(size_t)gy * W + gx] = (uint8_t)v;
+    }
+  }
+}
+
+// Fast variant of k_orb_blur7: 64x32 outputs per CTA; the tile is staged as float once (u8 -> f32 conversion hoisted out
+// of the tap loops), the row pass produces 4 adjacent outputs per thread from 10 floats (same k0*p0, fma(k1,p1,.) ...
+// order), the column pass slides down 8 rows.  Bit-identical to k_orb_blur7.
+#define OBF_TW 64
+#define OBF_TH 32
+__global__ void __launch_bounds__(256) k_orb_blur7_fast(const uint8_t* __restrict__ img0, size_t img0_stride,
+                                                        const uint8_t* __restrict__ pyr, OrbGeom g,
+                                                        uint8_t* __restrict__ blur, int l, int tiles_x) {
+  constexpr int RH = OBF_TH + 6, RP = 72;  // 70 floats needed per row, pitch 72 (16-byte aligned groups of 4)
+  __shared__ __align__(16) float rawf[RH][RP];
+  __shared__ __align__(16) float hrow[RH][OBF_TW];
+  const int W = g.w[l], H = g.h[l];
+  const int x0 = (blockIdx.x % tiles_x) * OBF_TW, y0 = (blockIdx.x / tiles_x) * OBF_TH;
+  const int img = blockIdx.y;
+  const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
+  uint8_t* dst = blur + (size_t)img * g.blur_stride + g.blur_off[l];
+  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const bool interior = x0 >= 3 && x0 - 3 + RP <= W && y0 >= 3 && y0 + OBF_TH + 3 <= H;
+  for (int ry = wrp; ry < RH; ry += 8) {
+    const int gy = interior ? y0 - 3 + ry : orb_reflect101(y0 - 3 + ry, H);
+    const uint8_t* row = src + (size_t)gy * W;
+    for (int rx = lane; rx < RP; rx += 32) rawf[ry][rx] = (float)row[interior ? x0 - 3 + rx : orb_reflect101(x0 - 3 + rx, W)];
+  }
+  __syncthreads();
+  const float k0 = c_blur7[0], k1 = c_blur7[1], k2 = c_blur7[2], k3 = c_blur7[3], k4 = c_blur7[4], k5 = c_blur7[5], k6 = c_blur7[6];
+  for (int it = tid; it < RH * (OBF_TW / 4); it += 256) {
+    const int ry = it >> 4, j = it & 15;
+    const float4 pa = *reinterpret_cast<const float4*>(&rawf[ry][4 * j]);
+    const float4 pb = *reinterpret_cast<const float4*>(&rawf[ry][4 * j + 4]);
+    const float2 pc = *reinterpret_cast<const float2*>(&rawf[ry][4 * j + 8]);
+    const float p[10] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y};
+    float o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float a = __fmul_rn(k0, p[i]);
+      a = __fmaf_rn(k1, p[i + 1], a); a = __fmaf_rn(k2, p[i + 2], a); a = __fmaf_rn(k3, p[i + 3], a);
+      a = __fmaf_rn(k4, p[i + 4], a); a = __fmaf_rn(k5, p[i + 5], a); a = __fmaf_rn(k6, p[i + 6], a);
+      o[i] = a;
+    }
+    *reinterpret_cast<float4*>(&hrow[ry][4 * j]) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  __syncthreads();
+  const int c = tid & 63, q = tid >> 6;
+  const int gx = x0 + c;
+  if (gx < W) {
+    float v[14];
+#pragma unroll
+    for (int k = 0; k < 14; ++k) v[k] = hrow[q * 8 + k][c];
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int gy = y0 + q * 8 + r;
+      if (gy < H) {
+        float a = __fmul_rn(k3, v[r + 3]);
+        a = __fmaf_rn(k4, __fadd_rn(v[r + 4], v[r + 2]), a);
+        a = __fmaf_rn(k5, __fadd_rn(v[r + 5], v[r + 1]), a);
+        a = __fmaf_rn(k6, __fadd_rn(v[r + 6], v[r]), a);
+        int o = __float2int_rn(a);
+        o = o < 0 ? 0 : (o > 255 ? 255 : o);
+        dst[(size_t)gy * W + gx] = (uint8_t)o;
+      }
     }
   }
 }
@@ -671,9 +746,12 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
   }
   plf_mark(ctx, "orb.k_resize_exact");
   const int tiles = g.tile_start[g.nlevels];
-  k_fast_nms<<<dim3(tiles, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->cand, s->cand_count, s->hist,
-                                                 s->overflow);
-  PLF_LAUNCH_CHECK(ctx);
+  for (int l = 0; l < g.nlevels; ++l) {
+    const int tx_ = (g.w[l] + FN_OW - 1) / FN_OW, ty_ = (g.h[l] + FN_OH - 1) / FN_OH;
+    k_fast_nms<<<dim3(tx_ * ty_, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, l, tx_, s->cand, s->cand_count, s->hist,
+                                                      s->overflow);
+    PLF_LAUNCH_CHECK(ctx);
+  }
   plf_mark(ctx, "orb.k_fast_nms");
   k_select_sort<<<nimg, 1024, 0, cs>>>(g, s->cand, s->cand_count, s->hist, s->kps[par], s->kp_lxy[par], s->kp_count[par], s->overflow);
   PLF_LAUNCH_CHECK(ctx);
@@ -681,8 +759,11 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
   k_ic_angle<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->kps[par], s->kp_lxy[par], s->kp_count[par]);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "orb.k_ic_angle");
-  k_orb_blur7<<<dim3(tiles, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->blur);
-  PLF_LAUNCH_CHECK(ctx);
+  for (int l = 0; l < g.nlevels; ++l) {
+    const int tx_ = (g.w[l] + OBF_TW - 1) / OBF_TW, ty_ = (g.h[l] + OBF_TH - 1) / OBF_TH;
+    k_orb_blur7_fast<<<dim3(tx_ * ty_, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->blur, l, tx_);
+    PLF_LAUNCH_CHECK(ctx);
+  }
   plf_mark(ctx, "orb.k_orb_blur7");
   k_rbrief<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(s->blur, g, s->kps[par], s->kp_count[par], g_dev_pattern, s->desc[par]);
   PLF_LAUNCH_CHECK(ctx);
