@@ -55,8 +55,9 @@ struct LsdState {
   uint8_t* blur = nullptr;    // [nimg][h*w]
   uint8_t* scaled = nullptr;  // [nimg][hs*ws]
   short2* gxy[2] = {nullptr, nullptr};      // [nimg][hs*ws]
-  float* adeg[2] = {nullptr, nullptr};      // [nimg][hs*ws]  level-line angle in degrees, LSD_NOTDEF = undefined or used
-  float2* cs[2] = {nullptr, nullptr};       // [nimg][hs*ws]  (cosf, sinf) of float(angle): the region-angle increments, precomputed
+  struct LsdPix* pix[2] = {nullptr, nullptr};  // [nimg][guard + hs*ws]  {angle (rad, f64) | NOTDEF = undefined/used, cosf, sinf}
+  size_t pix_stride = 0;      // entries per image = guard (ws+1, permanently NOTDEF) + hs*ws
+  int m2_min = 0;             // smallest gx^2+gy^2 whose gradient norm exceeds rho (defined pixel)
   uint16_t* binmap = nullptr; // [nimg][hs*ws]
   int* maxmag2 = nullptr;     // [nimg]
   uint32_t* rowcnt = nullptr; // [nimg][hs][n_bins]
@@ -73,7 +74,7 @@ struct LsdState {
   int* overflow = nullptr;    // [1]
   int* rs_tab = nullptr;      // resize tables
   size_t rs_x_off = 0, rs_y_off = 0;
-  float4* grad_lut = nullptr; // [1021*1021] gradient -> {angle, cos, sin}
+  struct LsdPix* grad_lut = nullptr; // [1021*1021] gradient (gx,gy) -> LsdPix
 };
 
 __constant__ int c_lsd_taps[16];
@@ -216,51 +217,68 @@ __device__ __forceinline__ float lsd_fast_atan2(float y, float x) {  // cv::fast
   return a;
 }
 
-// Gradient lookup table.  The 2x2 gradient (gx, gy) takes 1021 x 1021 integer values; the level-line angle
-// cv::fastAtan2(gx, -gy), the NOTDEF decision (|grad| <= rho) and cosf/sinf of float(angle) are functions of (gx, gy)
-// only.  They are tabulated once per context with exactly the device functions below (16 MB, L2-resident), which turns
-// ~200 dependent instructions per defined pixel into one 16-byte load.  Entry = {angle_deg | NOTDEF, cosf, sinf, 0}.
+// Per-pixel record read by the region-growing kernel: one 16-byte load per neighbour.
+struct __align__(16) LsdPix {
+  double a;  // level-line angle in radians (cv::fastAtan2(gx,-gy) * DEG_TO_RADS, as OpenCV stores it) or LSD_NOTDEF_D
+  float c;   // cosf(float(a))  \ the increments region_grow adds to (sumdx, sumdy); host libm semantics
+  float s;   // sinf(float(a))  /  via the glibc port
+};
+#define LSD_NOTDEF_D (-1024.0)
+
+// Gradient lookup table.  The 2x2 gradient (gx, gy) takes 1021 x 1021 integer values; the level-line angle, the NOTDEF
+// decision (|grad| <= rho) and cosf/sinf of float(angle) are functions of (gx, gy) only.  They are tabulated once per
+// context with exactly the device functions used elsewhere (16 MB, L2-resident), which turns ~200 dependent
+// instructions per defined pixel into one 16-byte load.
 #define LSD_LUT_DIM 1021
-__global__ void __launch_bounds__(256) k_lsd_build_lut(double rho, float4* __restrict__ lut) {
+__global__ void __launch_bounds__(256) k_lsd_build_lut(double rho, LsdPix* __restrict__ lut) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= LSD_LUT_DIM * LSD_LUT_DIM) return;
   const int gx = i / LSD_LUT_DIM - 510, gy = i % LSD_LUT_DIM - 510;
-  float4 e = make_float4(LSD_NOTDEF, 0.f, 0.f, 0.f);
+  LsdPix e;
+  e.a = LSD_NOTDEF_D; e.c = 0.f; e.s = 0.f;
   const double norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
   if (!(norm <= rho)) {
-    const float a = lsd_fast_atan2((float)gx, (float)(-gy));
-    // region_grow adds cos(float(angle)), sin(float(angle)) (host libm cosf/sinf): bit-exact glibc port
-    const float af = (float)((double)a * LSD_DEG2RAD);
-    e = make_float4(a, glibc_cosf(af), glibc_sinf(af), 0.f);
+    const float adeg = lsd_fast_atan2((float)gx, (float)(-gy));
+    e.a = (double)adeg * LSD_DEG2RAD;
+    const float af = (float)e.a;  // region_grow: cos(float(angle)), sin(float(angle)) with the host libm -> glibc port
+    e.c = glibc_cosf(af);
+    e.s = glibc_sinf(af);
   }
   lut[i] = e;
 }
 
+__global__ void k_lsd_fill_guard(LsdPix* __restrict__ pix, size_t pix_stride, int guard, int nimg) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= guard * nimg) return;
+  LsdPix e;
+  e.a = LSD_NOTDEF_D; e.c = 0.f; e.s = 0.f;
+  pix[(size_t)(i / guard) * pix_stride + (i % guard)] = e;
+}
+
+// pix points at pixel (0,0) of image 0 (i.e. past the guard); image stride pix_stride.
 __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int W, int H,
-                                                  const float4* __restrict__ lut, size_t stride,
-                                                  short2* __restrict__ gxy, float* __restrict__ adeg,
-                                                  float2* __restrict__ cs, int* __restrict__ maxmag2) {
+                                                  const LsdPix* __restrict__ lut, size_t stride,
+                                                  short2* __restrict__ gxy, LsdPix* __restrict__ pix, size_t pix_stride,
+                                                  int* __restrict__ maxmag2) {
   const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, im = blockIdx.z;
   int mag2 = -1;
   if (x < W) {
-    const size_t o = (size_t)im * stride + (size_t)y * W + x;
+    const int oi = y * W + x;
     short2 g = make_short2(0, 0);
-    float a = LSD_NOTDEF;
-    float2 c2 = make_float2(0.f, 0.f);
+    LsdPix e;
+    e.a = LSD_NOTDEF_D; e.c = 0.f; e.s = 0.f;
     if (x < W - 1 && y < H - 1) {
-      const uint8_t* r0 = img + (size_t)im * img_stride + (size_t)y * W + x;
+      const uint8_t* r0 = img + (size_t)im * img_stride + oi;
       const uint8_t* r1 = r0 + W;
       const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
       const int gx = DA + BC, gy = DA - BC;
       g = make_short2((short)gx, (short)gy);
-      const float4 e = __ldg(&lut[(gx + 510) * LSD_LUT_DIM + (gy + 510)]);
-      a = e.x;
-      c2 = make_float2(e.y, e.z);
-      if (a != LSD_NOTDEF) mag2 = gx * gx + gy * gy;
+      const float4 raw = __ldg(reinterpret_cast<const float4*>(&lut[(gx + 510) * LSD_LUT_DIM + (gy + 510)]));
+      e = *reinterpret_cast<const LsdPix*>(&raw);
+      if (e.a != LSD_NOTDEF_D) mag2 = gx * gx + gy * gy;
     }
-    gxy[o] = g;
-    adeg[o] = a;
-    cs[o] = c2;
+    gxy[(size_t)im * stride + oi] = g;
+    *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + oi]) = *reinterpret_cast<const float4*>(&e);
   }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) mag2 = max(mag2, __shfl_xor_sync(0xFFFFFFFFu, mag2, off));
@@ -274,7 +292,7 @@ __device__ __forceinline__ double lsd_bin_coef(int maxmag2, int n_bins) {
   return max_grad > 0 ? (double)(n_bins - 1) / max_grad : 0.0;
 }
 
-__global__ void __launch_bounds__(256) k_lsd_rowhist(const short2* __restrict__ gxy, const float* __restrict__ adeg,
+__global__ void __launch_bounds__(256) k_lsd_rowhist(const short2* __restrict__ gxy, int m2_min,
                                                      size_t stride, int W, int H, int n_bins,
                                                      const int* __restrict__ maxmag2, uint16_t* __restrict__ binmap,
                                                      uint32_t* __restrict__ rowcnt) {
@@ -285,9 +303,10 @@ __global__ void __launch_bounds__(256) k_lsd_rowhist(const short2* __restrict__ 
   const double coef = lsd_bin_coef(maxmag2[im], n_bins);
   const size_t o = (size_t)im * stride + (size_t)y * W;
   for (int x = threadIdx.x; x < W - 1; x += 256) {
-    if (adeg[o + x] == LSD_NOTDEF) continue;
     const short2 g = gxy[o + x];
-    const double norm = sqrt((double)(g.x * g.x + g.y * g.y) / 4.0);
+    const int m2 = g.x * g.x + g.y * g.y;
+    if (m2 < m2_min) continue;  // undefined level-line angle (norm <= rho): never a seed
+    const double norm = sqrt((double)m2 / 4.0);
     const int b = (int)(norm * coef);
     binmap[o + x] = (uint16_t)b;
     atomicAdd(&hist[b], 1u);
@@ -341,7 +360,7 @@ __global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ row
 }
 
 // one warp per (row, image): stable ranks inside the row via match_any, raster order preserved
-__global__ void __launch_bounds__(128) k_lsd_scatter(const float* __restrict__ adeg, const uint16_t* __restrict__ binmap,
+__global__ void __launch_bounds__(128) k_lsd_scatter(const short2* __restrict__ gxy, int m2_min, const uint16_t* __restrict__ binmap,
                                                      size_t stride, int W, int H, int n_bins,
                                                      const uint32_t* __restrict__ rowcnt,
                                                      const uint32_t* __restrict__ binstart,
@@ -359,7 +378,11 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(const float* __restrict__ a
   uint32_t* ord = order + (size_t)im * stride;
   for (int x0 = 0; x0 < W - 1; x0 += 32) {
     const int x = x0 + lane;
-    const bool valid = x < W - 1 && adeg[o + x] != LSD_NOTDEF;
+    bool valid = false;
+    if (x < W - 1) {
+      const short2 g = gxy[o + x];
+      valid = g.x * g.x + g.y * g.y >= m2_min;
+    }
     const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
     if (valid) {
       const int b = binmap[o + x];
@@ -401,13 +424,20 @@ __device__ __forceinline__ bool lsd_aligned_rad(double a, double theta, double p
   return n_theta <= prec;
 }
 
-// One warp per image.  Per region point: lanes 0..8 hold the 3x3 neighbourhood's angles, lanes 9..17 the matching
-// (cos, sin) pairs, both fetched one queue entry AHEAD (the loads for point r+1 are in flight while point r is
-// processed; cells accepted meanwhile are patched to "used" in the prefetched registers).  The alignment test of all
-// remaining neighbours runs in parallel across lanes and is repeated after every acceptance, which reproduces the
-// reference's sequential semantics (each test sees the region angle left by the previous acceptance).
-__global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, const float2* __restrict__ cs_all,
-                                                 size_t stride, int W, int H,
+__device__ __forceinline__ LsdPix lsd_load_pix(const LsdPix* p) {
+  const float4 raw = __ldcg(reinterpret_cast<const float4*>(p));
+  return *reinterpret_cast<const LsdPix*>(&raw);
+}
+
+// One warp per image.  Pixels are addressed by their linear index i = y*W + x; the 8 neighbours are i + {-W-1 .. W+1}.
+// No bounds tests are needed: the last column and last row of the map are always NOTDEF (ll_angle), so x-1 / x+1 wrap
+// onto NOTDEF pixels, y+1 stays inside, and a guard of W+1 permanently-NOTDEF records precedes pixel 0 for y-1.
+// Per region point: lanes 0..8 hold the 16-byte records of the 3x3 neighbourhood, fetched one queue entry AHEAD (the
+// loads for point r+1 are in flight while point r is processed; cells accepted meanwhile are patched to "used" in the
+// prefetched registers).  The alignment test of all remaining neighbours runs lane-parallel and is repeated after every
+// acceptance, which reproduces the reference's sequential semantics (each test sees the region angle left by the
+// previous acceptance).
+__global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
                                                  const uint32_t* __restrict__ order_all,
                                                  const int* __restrict__ nseeds, double prec, int min_reg_size,
                                                  uint32_t* __restrict__ regpts_all, uint4* __restrict__ regions_all,
@@ -415,93 +445,75 @@ __global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, c
                                                  int* __restrict__ overflow) {
   __shared__ uint32_t q[LSD_QCAP];
   const int im = blockIdx.x, lane = threadIdx.x;
-  float* adeg = adeg_all + (size_t)im * stride;
-  const float2* csm = cs_all + (size_t)im * stride;
+  LsdPix* pix = pix_all + (size_t)im * pix_stride;
   const uint32_t* order = order_all + (size_t)im * stride;
   uint32_t* regpts = regpts_all + (size_t)im * stride;
   uint4* regions = regions_all + (size_t)im * max_regions;
   const int ns = nseeds[im];
-  const int kk = lane < 9 ? lane : (lane < 18 ? lane - 9 : 0);  // neighbour slot served by this lane
-  const int dxk = kk % 3 - 1, dyk = kk / 3 - 1;
+  const int kk = lane < 9 ? lane : 4;                  // neighbour slot served by this lane (lanes >= 9 idle on the centre)
+  const int noff = (kk / 3 - 1) * W + (kk % 3 - 1);   // linear offset of that neighbour (row-major 3x3: reference order)
   uint32_t cursor = 0;
   int nreg_out = 0;
   for (int s0 = 0; s0 < ns; s0 += 32) {
     const int si = s0 + lane;
     const uint32_t seed = si < ns ? order[si] : 0u;
-    float a0 = si < ns ? __ldcg(&adeg[seed]) : LSD_NOTDEF;
-    unsigned pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF);
+    double a0 = si < ns ? __ldcg(&pix[seed].a) : LSD_NOTDEF_D;
+    unsigned pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF_D);
     while (pending) {
       const int src = __ffs(pending) - 1;
       const uint32_t sidx = __shfl_sync(0xFFFFFFFFu, seed, src);
-      const float sdeg = __shfl_sync(0xFFFFFFFFu, a0, src);
-      const int sx = sidx % W, sy = sidx / W;
-      double reg_angle = (double)sdeg * LSD_DEG2RAD;
+      double reg_angle = __shfl_sync(0xFFFFFFFFu, a0, src);
       float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
       if (lane == 0) {
-        adeg[sidx] = LSD_NOTDEF;
-        regpts[cursor] = ((uint32_t)sy << 16) | (uint32_t)sx;
-        q[0] = ((uint32_t)sy << 16) | (uint32_t)sx;
+        pix[sidx].a = LSD_NOTDEF_D;
+        regpts[cursor] = sidx;
+        q[0] = sidx;
       }
       __syncwarp();
       uint32_t nreg = 1;
-      // neighbourhood registers of the point being processed (cur_*) and of the next one (pf_*)
-      float pf_a = LSD_NOTDEF;
-      float2 pf_cs = make_float2(0.f, 0.f);
-      int pf_x = 0, pf_y = 0;
+      LsdPix pf;
+      pf.a = LSD_NOTDEF_D; pf.c = 0.f; pf.s = 0.f;
+      int pf_i = 0;
       bool have_pf = false;
       for (uint32_t r = 0; r < nreg; ++r) {
-        float cur_a;
-        float2 cur_cs;
-        int cx, cy;
+        LsdPix cur;
+        int ci;
         if (have_pf) {
-          cur_a = pf_a; cur_cs = pf_cs; cx = pf_x; cy = pf_y;
+          cur = pf;
+          ci = pf_i;
         } else {
-          const uint32_t pt = (nreg - r <= LSD_QCAP) ? q[r % LSD_QCAP] : __ldcg(&regpts[cursor + r]);
-          cx = (int)(pt & 0xFFFF) + dxk; cy = (int)(pt >> 16) + dyk;
-          cur_a = LSD_NOTDEF; cur_cs = make_float2(0.f, 0.f);
-          if (lane < 18 && cx >= 0 && cy >= 0 && cx < W && cy < H) {
-            const size_t o = (size_t)cy * W + cx;
-            if (lane < 9) cur_a = __ldcg(&adeg[o]);
-            else cur_cs = __ldg(&csm[o]);
-          }
+          const uint32_t pt = (nreg - r <= LSD_QCAP) ? q[r & (LSD_QCAP - 1)] : __ldcg(&regpts[cursor + r]);
+          ci = (int)pt + noff;
+          cur = lsd_load_pix(&pix[ci]);
         }
-        // prefetch the neighbourhood of queue entry r+1 (already known) while r is processed
         have_pf = false;
-        if (r + 1 < nreg) {
-          const uint32_t pt = (nreg - (r + 1) <= LSD_QCAP) ? q[(r + 1) % LSD_QCAP] : __ldcg(&regpts[cursor + r + 1]);
-          pf_x = (int)(pt & 0xFFFF) + dxk; pf_y = (int)(pt >> 16) + dyk;
-          pf_a = LSD_NOTDEF; pf_cs = make_float2(0.f, 0.f);
-          if (lane < 18 && pf_x >= 0 && pf_y >= 0 && pf_x < W && pf_y < H) {
-            const size_t o = (size_t)pf_y * W + pf_x;
-            if (lane < 9) pf_a = __ldcg(&adeg[o]);
-            else pf_cs = __ldg(&csm[o]);
-          }
+        if (r + 1 < nreg) {  // neighbourhood of queue entry r+1, in flight while r is processed
+          const uint32_t pt = (nreg - (r + 1) <= LSD_QCAP) ? q[(r + 1) & (LSD_QCAP - 1)] : __ldcg(&regpts[cursor + r + 1]);
+          pf_i = (int)pt + noff;
+          pf = lsd_load_pix(&pix[pf_i]);
           have_pf = true;
         }
-        const double my_ang = (double)cur_a * LSD_DEG2RAD;
-        unsigned rem = __ballot_sync(0xFFFFFFFFu, lane < 9 && cur_a != LSD_NOTDEF);
+        unsigned rem = __ballot_sync(0xFFFFFFFFu, lane < 9 && cur.a != LSD_NOTDEF_D);
         while (rem) {
-          const bool al = ((rem >> lane) & 1u) && lsd_aligned_rad(my_ang, reg_angle, prec);
+          const bool al = ((rem >> lane) & 1u) && lsd_aligned_rad(cur.a, reg_angle, prec);
           const unsigned m = __ballot_sync(0xFFFFFFFFu, al);
           if (!m) break;
           const int k = __ffs(m) - 1;
           rem &= ~((2u << k) - 1u);  // k and everything before it have been decided
-          const int ax = __shfl_sync(0xFFFFFFFFu, cx, k), ay = __shfl_sync(0xFFFFFFFFu, cy, k);
-          const float ck = __shfl_sync(0xFFFFFFFFu, cur_cs.x, k + 9), sk = __shfl_sync(0xFFFFFFFFu, cur_cs.y, k + 9);
-          const uint32_t packed = ((uint32_t)ay << 16) | (uint32_t)ax;
+          const int ai = __shfl_sync(0xFFFFFFFFu, ci, k);
+          const float ck = __shfl_sync(0xFFFFFFFFu, cur.c, k), sk = __shfl_sync(0xFFFFFFFFu, cur.s, k);
           if (lane == 0) {
-            adeg[(size_t)ay * W + ax] = LSD_NOTDEF;
-            regpts[cursor + nreg] = packed;
-            q[nreg % LSD_QCAP] = packed;
+            pix[ai].a = LSD_NOTDEF_D;
+            regpts[cursor + nreg] = (uint32_t)ai;
+            q[nreg & (LSD_QCAP - 1)] = (uint32_t)ai;
           }
           ++nreg;
-          if (have_pf && lane < 9 && pf_x == ax && pf_y == ay) pf_a = LSD_NOTDEF;  // prefetched copy is stale
+          if (pf_i == ai) pf.a = LSD_NOTDEF_D;  // the prefetched copy of this cell is stale (harmless when !have_pf)
           sumdx = __fadd_rn(sumdx, ck);
           sumdy = __fadd_rn(sumdy, sk);
           reg_angle = (double)lsd_fast_atan2(sumdy, sumdx) * LSD_DEG2RAD;
         }
         __syncwarp();
-        // entry r+1 may only just have been appended: its neighbourhood was not prefetched -> loaded next iteration
       }
       if ((int)nreg >= min_reg_size) {
         if (nreg_out < max_regions) {
@@ -517,8 +529,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(float* __restrict__ adeg_all, c
       }
       pending &= ~((2u << src) - 1u);
       if (pending) {
-        a0 = (pending >> lane) & 1u ? __ldcg(&adeg[seed]) : LSD_NOTDEF;
-        pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF);
+        a0 = (pending >> lane) & 1u ? __ldcg(&pix[seed].a) : LSD_NOTDEF_D;
+        pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF_D);
       }
     }
   }
@@ -549,8 +561,8 @@ __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gx
   double x = 0, y = 0, sum = 0;
   for (int k = 0; k < n; ++k) {
     const uint32_t p = pts[k];
-    const int px = p & 0xFFFF, py = p >> 16;
-    const short2 g = gxy[(size_t)py * W + px];
+    const int py = (int)(p / (uint32_t)W), px = (int)p - py * W;
+    const short2 g = gxy[p];
     const double wgt = sqrt((double)(g.x * g.x + g.y * g.y) / 4.0);
     x += (double)px * wgt;
     y += (double)py * wgt;
@@ -561,8 +573,8 @@ __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gx
   double Ixx = 0, Iyy = 0, Ixy = 0;
   for (int k = 0; k < n; ++k) {
     const uint32_t p = pts[k];
-    const int px = p & 0xFFFF, py = p >> 16;
-    const short2 g = gxy[(size_t)py * W + px];
+    const int py = (int)(p / (uint32_t)W), px = (int)p - py * W;
+    const short2 g = gxy[p];
     const double wgt = sqrt((double)(g.x * g.x + g.y * g.y) / 4.0);
     const double dx = (double)px - x, dy = (double)py - y;
     Ixx += dy * dy * wgt;
@@ -578,7 +590,8 @@ __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gx
   double l_min = 0, l_max = 0;
   for (int k = 0; k < n; ++k) {
     const uint32_t p = pts[k];
-    const double regdx = (double)(p & 0xFFFF) - x, regdy = (double)(p >> 16) - y;
+    const int py = (int)(p / (uint32_t)W), px = (int)p - py * W;
+    const double regdx = (double)px - x, regdy = (double)py - y;
     const double l = regdx * dx + regdy * dy;
     if (l > l_max) l_max = l;
     else if (l < l_min) l_min = l;
@@ -712,7 +725,7 @@ __global__ void __launch_bounds__(1024) k_keylines(const float4* __restrict__ se
 // ---- host side -------------------------------------------------------------------------------------------------
 static void lsd_release(LsdState* s) {
   for (int p = 0; p < 2; ++p) {
-    cudaFree(s->gxy[p]); cudaFree(s->adeg[p]); cudaFree(s->cs[p]); cudaFree(s->order[p]); cudaFree(s->nseeds[p]);
+    cudaFree(s->gxy[p]); cudaFree(s->pix[p]); cudaFree(s->order[p]); cudaFree(s->nseeds[p]);
     cudaFree(s->regpts[p]); cudaFree(s->regions[p]); cudaFree(s->nregions[p]); cudaFree(s->segs[p]); cudaFree(s->kls[p]);
     cudaFree(s->kls_all[p]); cudaFree(s->nlines[p]);
   }
@@ -794,6 +807,9 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   s->max_regions = ctx->limits.max_segments;
   s->max_lines = ctx->limits.max_lines;
   const size_t N = (size_t)nimg, A = (size_t)w * h, As = (size_t)s->ws * s->hs;
+  s->pix_stride = As + (size_t)s->ws + 1;
+  for (s->m2_min = 0; s->m2_min <= 2 * 510 * 510; ++s->m2_min)  // same double expression as the kernels
+    if (!(sqrt((double)s->m2_min / 4.0) <= s->rho)) break;
   PLF_CUDA(ctx, cudaMalloc(&s->blur, A * N));
   PLF_CUDA(ctx, cudaMalloc(&s->scaled, As * N));
   PLF_CUDA(ctx, cudaMalloc(&s->binmap, As * N * sizeof(uint16_t)));
@@ -804,8 +820,9 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   // batch i+1 can be extracted while batch i is still growing regions; standalone operators use parity 0 only
   for (int p = 0; p < (s->two_parities ? 2 : 1); ++p) {
     PLF_CUDA(ctx, cudaMalloc(&s->gxy[p], As * N * sizeof(short2)));
-    PLF_CUDA(ctx, cudaMalloc(&s->adeg[p], As * N * sizeof(float)));
-    PLF_CUDA(ctx, cudaMalloc(&s->cs[p], As * N * sizeof(float2)));
+    PLF_CUDA(ctx, cudaMalloc(&s->pix[p], s->pix_stride * N * sizeof(LsdPix)));
+    k_lsd_fill_guard<<<(int)(((size_t)(s->ws + 1) * N + 255) / 256), 256, 0, ctx->stream>>>(s->pix[p], s->pix_stride, s->ws + 1, (int)N);
+    PLF_LAUNCH_CHECK(ctx);
     PLF_CUDA(ctx, cudaMalloc(&s->nseeds[p], N * sizeof(int)));
     PLF_CUDA(ctx, cudaMalloc(&s->order[p], As * N * sizeof(uint32_t)));
     PLF_CUDA(ctx, cudaMalloc(&s->regpts[p], As * N * sizeof(uint32_t)));
@@ -818,7 +835,7 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   }
   PLF_CUDA(ctx, cudaMalloc(&s->overflow, sizeof(int)));
   PLF_CUDA(ctx, cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream));
-  PLF_CUDA(ctx, cudaMalloc(&s->grad_lut, (size_t)LSD_LUT_DIM * LSD_LUT_DIM * sizeof(float4)));
+  PLF_CUDA(ctx, cudaMalloc(&s->grad_lut, (size_t)LSD_LUT_DIM * LSD_LUT_DIM * sizeof(LsdPix)));
   k_lsd_build_lut<<<(LSD_LUT_DIM * LSD_LUT_DIM + 255) / 256, 256, 0, ctx->stream>>>(s->rho, s->grad_lut);
   PLF_LAUNCH_CHECK(ctx);
   PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -851,8 +868,7 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
   uint8_t* blur = s->blur + o * A;
   uint8_t* scaled_buf = s->scaled + o * As;
   short2* gxy = s->gxy[par] + o * As;
-  float* adeg = s->adeg[par] + o * As;
-  float2* csm = s->cs[par] + o * As;
+  LsdPix* pix = s->pix[par] + o * s->pix_stride + (s->ws + 1);  // pixel (0,0) of the first image of the range
   uint16_t* binmap = s->binmap + o * As;
   int* maxmag2 = s->maxmag2 + o;
   uint32_t* rowcnt = s->rowcnt + o * H * s->n_bins;
@@ -882,16 +898,16 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
     scaled_stride = As;
   }
   PLF_CUDA(ctx, cudaMemsetAsync(maxmag2, 0xFF, (size_t)n * sizeof(int), cs));  // -1
-  k_lsd_grad<<<dim3((W + 255) / 256, H, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->grad_lut, As, gxy, adeg, csm, maxmag2);
+  k_lsd_grad<<<dim3((W + 255) / 256, H, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->grad_lut, As, gxy, pix, s->pix_stride, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
-  k_lsd_rowhist<<<dim3(H - 1, n), 256, 0, cs>>>(gxy, adeg, As, W, H, s->n_bins, maxmag2, binmap, rowcnt);
+  k_lsd_rowhist<<<dim3(H - 1, n), 256, 0, cs>>>(gxy, s->m2_min, As, W, H, s->n_bins, maxmag2, binmap, rowcnt);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rowhist");
   k_lsd_binscan<<<n, 1024, 0, cs>>>(rowcnt, H, s->n_bins, binstart, nseeds);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_binscan");
-  k_lsd_scatter<<<dim3((H - 1 + 3) / 4, n), 128, 0, cs>>>(adeg, binmap, As, W, H, s->n_bins, rowcnt, binstart, order);
+  k_lsd_scatter<<<dim3((H - 1 + 3) / 4, n), 128, 0, cs>>>(gxy, s->m2_min, binmap, As, W, H, s->n_bins, rowcnt, binstart, order);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_scatter");
   return PLF_OK;
@@ -905,8 +921,7 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   const int W = s->ws, H = s->hs;
   const size_t As = (size_t)W * H, o = (size_t)img0;
   short2* gxy = s->gxy[par] + o * As;
-  float* adeg = s->adeg[par] + o * As;
-  float2* csm = s->cs[par] + o * As;
+  LsdPix* pix = s->pix[par] + o * s->pix_stride + (s->ws + 1);
   int* nseeds = s->nseeds[par] + o;
   uint32_t* order = s->order[par] + o * As;
   uint32_t* regpts = s->regpts[par] + o * As;
@@ -916,7 +931,7 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   plf_keyline* kls = s->kls[par] + o * s->max_lines;
   plf_keyline* kls_all = s->kls_all[par] + o * s->max_regions;
   int* nlines = s->nlines[par] + o;
-  k_lsd_grow<<<n, 32, 0, cs>>>(adeg, csm, As, W, H, order, nseeds, s->prec, s->min_reg_size, regpts, regions, s->max_regions,
+  k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, s->min_reg_size, regpts, regions, s->max_regions,
                                nregions, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grow");
