@@ -66,12 +66,6 @@ struct LsdState {
   uint32_t* order[2] = {nullptr, nullptr};  // [nimg][hs*ws]
   uint32_t* regpts[2] = {nullptr, nullptr}; // [nimg][hs*ws]
   uint4* regions[2] = {nullptr, nullptr};   // [nimg][max_regions] {start, count, angle_lo, angle_hi}
-  // connected-component decomposition of the growing (single-buffered: produced and consumed inside the grow phase)
-  uint32_t* lab = nullptr;      // [nimg][hs*ws]  component label (min pixel index) of every defined pixel
-  uint8_t* seed_grp = nullptr;  // [nimg][hs*ws]  group (0..31) of the component each ordered seed belongs to
-  int* grp_count = nullptr;     // [nimg][32]     defined pixels per group (-> region-point segment of each group)
-  uint32_t* reg_rank = nullptr; // [nimg][max_regions] seed rank of each kept region (output order)
-  uint32_t* reg_perm = nullptr; // [nimg][max_regions] regions sorted by seed rank
   int* nregions[2] = {nullptr, nullptr};    // [nimg]
   float4* segs[2] = {nullptr, nullptr};     // [nimg][max_regions]
   plf_keyline* kls[2] = {nullptr, nullptr}; // [nimg][max_lines]  final KeyLines (after top-K)
@@ -435,136 +429,35 @@ __device__ __forceinline__ LsdPix lsd_load_pix(const LsdPix* p) {
   return *reinterpret_cast<const LsdPix*>(&raw);
 }
 
-// ---- connected components of the defined-gradient mask ---------------------------------------------------------
-// Region growing never crosses a pixel whose level-line angle is undefined, so regions that start in different
-// 8-connected components of the defined mask cannot interact: the greedy partition factorises over components.  The
-// components are labelled with a lock-free union-find (label = smallest pixel index), hashed into LSD_GROUPS groups,
-// and each group is grown by its own warp, visiting ITS seeds in the global seed order.  The result is identical to
-// the sequential algorithm; only the order in which regions are emitted differs, and that is restored by ranking the
-// kept regions by the rank of their seed.
-#define LSD_GROUPS 32
-#define LSD_LAB_NONE 0xFFFFFFFFu
-__device__ __forceinline__ int lsd_group_of(uint32_t label) { return (int)((label * 0x9E3779B1u) >> 27); }
-
-__device__ __forceinline__ uint32_t uf_find(const uint32_t* lab, uint32_t x) {
-  uint32_t p = __ldcg(&lab[x]);
-  while (p != x) {
-    x = p;
-    p = __ldcg(&lab[x]);
-  }
-  return x;
-}
-__device__ __forceinline__ void uf_union(uint32_t* lab, uint32_t a, uint32_t b) {
-  for (;;) {
-    a = uf_find(lab, a);
-    b = uf_find(lab, b);
-    if (a == b) return;
-    if (a > b) { const uint32_t t = a; a = b; b = t; }
-    const uint32_t old = atomicMin(&lab[b], a);  // b was a root: hang it under the smaller root
-    if (old == b) return;
-    b = old;                                     // somebody re-parented b meanwhile: unite with its new parent
-  }
-}
-
-__global__ void __launch_bounds__(256) k_lsd_ccl_init(const short2* __restrict__ gxy, int m2_min, size_t stride, int W, int H,
-                                                      uint32_t* __restrict__ lab, int* __restrict__ grp_count,
-                                                      int* __restrict__ nregions) {
-  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, im = blockIdx.z;
-  if (x == 0 && y == 0) {
-    nregions[im] = 0;
-    for (int g = 0; g < LSD_GROUPS; ++g) grp_count[im * LSD_GROUPS + g] = 0;
-  }
-  if (x >= W) return;
-  const size_t o = (size_t)im * stride + (size_t)y * W + x;
-  uint32_t l = LSD_LAB_NONE;
-  if (x < W - 1 && y < H - 1) {
-    const short2 g = gxy[o];
-    if (g.x * g.x + g.y * g.y >= m2_min) l = (uint32_t)(y * W + x);
-  }
-  lab[o] = l;
-}
-
-__global__ void __launch_bounds__(256) k_lsd_ccl_union(size_t stride, int W, int H, uint32_t* __restrict__ lab_all) {
-  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, im = blockIdx.z;
-  if (x >= W - 1 || y >= H - 1) return;
-  uint32_t* lab = lab_all + (size_t)im * stride;
-  const uint32_t i = (uint32_t)(y * W + x);
-  if (__ldcg(&lab[i]) == LSD_LAB_NONE) return;
-  // forward half of the 8-neighbourhood: E, SW, S, SE (last row / column are never defined)
-  if (__ldcg(&lab[i + 1]) != LSD_LAB_NONE) uf_union(lab, i, i + 1);
-  if (x > 0 && __ldcg(&lab[i + W - 1]) != LSD_LAB_NONE) uf_union(lab, i, i + W - 1);
-  if (__ldcg(&lab[i + W]) != LSD_LAB_NONE) uf_union(lab, i, i + W);
-  if (__ldcg(&lab[i + W + 1]) != LSD_LAB_NONE) uf_union(lab, i, i + W + 1);
-}
-
-__global__ void __launch_bounds__(256) k_lsd_ccl_flatten(size_t stride, int W, int H, uint32_t* __restrict__ lab_all,
-                                                         int* __restrict__ grp_count) {
-  __shared__ int hist[LSD_GROUPS];
-  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, im = blockIdx.z;
-  if (threadIdx.x < LSD_GROUPS) hist[threadIdx.x] = 0;
-  __syncthreads();
-  if (x < W - 1 && y < H - 1) {
-    uint32_t* lab = lab_all + (size_t)im * stride;
-    const uint32_t i = (uint32_t)(y * W + x);
-    if (__ldcg(&lab[i]) != LSD_LAB_NONE) {
-      const uint32_t r = uf_find(lab, i);
-      lab[i] = r;  // only ever lowers a label towards its root: concurrent finds stay correct
-      atomicAdd(&hist[lsd_group_of(r)], 1);
-    }
-  }
-  __syncthreads();
-  if (threadIdx.x < LSD_GROUPS && hist[threadIdx.x]) atomicAdd(&grp_count[im * LSD_GROUPS + threadIdx.x], hist[threadIdx.x]);
-}
-
-__global__ void __launch_bounds__(256) k_lsd_seed_groups(const uint32_t* __restrict__ order, const int* __restrict__ nseeds,
-                                                         const uint32_t* __restrict__ lab, size_t stride,
-                                                         uint8_t* __restrict__ seed_grp) {
-  const int im = blockIdx.y;
-  const int si = blockIdx.x * 256 + threadIdx.x;
-  if (si >= nseeds[im]) return;
-  const uint32_t* l = lab + (size_t)im * stride;
-  seed_grp[(size_t)im * stride + si] = (uint8_t)lsd_group_of(uf_find(l, order[(size_t)im * stride + si]));
-}
-
-// One warp per (group, image).  Pixels are addressed by their linear index i = y*W + x; the 8 neighbours are
-// i + {-W-1 .. W+1}.  No bounds tests are needed: the last column and last row of the map are always NOTDEF (ll_angle),
-// so x-1 / x+1 wrap onto NOTDEF pixels, y+1 stays inside, and a guard of W+1 permanently-NOTDEF records precedes pixel 0.
+// One warp per image.  Pixels are addressed by their linear index i = y*W + x; the 8 neighbours are i + {-W-1 .. W+1}.
+// No bounds tests are needed: the last column and last row of the map are always NOTDEF (ll_angle), so x-1 / x+1 wrap
+// onto NOTDEF pixels, y+1 stays inside, and a guard of W+1 permanently-NOTDEF records precedes pixel 0 for y-1.
 // Per region point: lanes 0..8 hold the 16-byte records of the 3x3 neighbourhood, fetched one queue entry AHEAD (the
 // loads for point r+1 are in flight while point r is processed; cells accepted meanwhile are patched to "used" in the
 // prefetched registers).  The alignment test of all remaining neighbours runs lane-parallel and is repeated after every
 // acceptance, which reproduces the reference's sequential semantics (each test sees the region angle left by the
 // previous acceptance).
 __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
-                                                 const uint32_t* __restrict__ order_all, const uint8_t* __restrict__ seed_grp_all,
-                                                 const int* __restrict__ grp_count, const int* __restrict__ nseeds,
-                                                 double prec, int min_reg_size, uint32_t* __restrict__ regpts_all,
-                                                 uint4* __restrict__ regions_all, uint32_t* __restrict__ reg_rank_all,
-                                                 int max_regions, int* __restrict__ nregions, int* __restrict__ overflow) {
+                                                 const uint32_t* __restrict__ order_all,
+                                                 const int* __restrict__ nseeds, double prec, int min_reg_size,
+                                                 uint32_t* __restrict__ regpts_all, uint4* __restrict__ regions_all,
+                                                 int max_regions, int* __restrict__ nregions,
+                                                 int* __restrict__ overflow) {
   __shared__ uint32_t q[LSD_QCAP];
-  const int grp = blockIdx.x, im = blockIdx.y, lane = threadIdx.x;
+  const int im = blockIdx.x, lane = threadIdx.x;
   LsdPix* pix = pix_all + (size_t)im * pix_stride;
   const uint32_t* order = order_all + (size_t)im * stride;
-  const uint8_t* seed_grp = seed_grp_all + (size_t)im * stride;
   uint32_t* regpts = regpts_all + (size_t)im * stride;
   uint4* regions = regions_all + (size_t)im * max_regions;
-  uint32_t* reg_rank = reg_rank_all + (size_t)im * max_regions;
   const int ns = nseeds[im];
-  // this group's segment of the region-point array: exclusive prefix of the per-group pixel counts
-  int cnt = grp_count[im * LSD_GROUPS + lane], incl = cnt;
-#pragma unroll
-  for (int off = 1; off < 32; off <<= 1) {
-    const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-    if (lane >= off) incl += v;
-  }
-  uint32_t cursor = (uint32_t)__shfl_sync(0xFFFFFFFFu, incl - cnt, grp);
-  if (__shfl_sync(0xFFFFFFFFu, cnt, grp) == 0) return;  // no component hashed to this group
   const int kk = lane < 9 ? lane : 4;                  // neighbour slot served by this lane (lanes >= 9 idle on the centre)
   const int noff = (kk / 3 - 1) * W + (kk % 3 - 1);   // linear offset of that neighbour (row-major 3x3: reference order)
+  uint32_t cursor = 0;
+  int nreg_out = 0;
   for (int s0 = 0; s0 < ns; s0 += 32) {
     const int si = s0 + lane;
-    const bool mine = si < ns && seed_grp[si] == grp;
-    const uint32_t seed = mine ? order[si] : 0u;
-    double a0 = mine ? __ldcg(&pix[seed].a) : LSD_NOTDEF_D;
+    const uint32_t seed = si < ns ? order[si] : 0u;
+    double a0 = si < ns ? __ldcg(&pix[seed].a) : LSD_NOTDEF_D;
     unsigned pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF_D);
     while (pending) {
       const int src = __ffs(pending) - 1;
@@ -623,15 +516,12 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
         __syncwarp();
       }
       if ((int)nreg >= min_reg_size) {
-        int slot = 0;
-        if (lane == 0) slot = atomicAdd(&nregions[im], 1);
-        slot = __shfl_sync(0xFFFFFFFFu, slot, 0);
-        if (slot < max_regions) {
+        if (nreg_out < max_regions) {
           if (lane == 0) {
             const unsigned long long bits = (unsigned long long)__double_as_longlong(reg_angle);
-            regions[slot] = make_uint4(cursor, nreg, (uint32_t)bits, (uint32_t)(bits >> 32));
-            reg_rank[slot] = (uint32_t)(s0 + src);
+            regions[nreg_out] = make_uint4(cursor, nreg, (uint32_t)bits, (uint32_t)(bits >> 32));
           }
+          ++nreg_out;
           cursor += nreg;
         } else if (lane == 0) {
           *overflow = 1;
@@ -644,25 +534,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
       }
     }
   }
-}
-
-// Output order = seed order: position of each kept region = number of kept regions with a smaller seed rank.
-__global__ void __launch_bounds__(1024) k_lsd_region_rank(const uint32_t* __restrict__ reg_rank_all, int* __restrict__ nregions,
-                                                          int max_regions, uint32_t* __restrict__ perm_all) {
-  extern __shared__ uint32_t ranks[];
-  const int im = blockIdx.x;
-  const int n = min(nregions[im], max_regions);
-  const uint32_t* rk = reg_rank_all + (size_t)im * max_regions;
-  uint32_t* perm = perm_all + (size_t)im * max_regions;
-  for (int i = threadIdx.x; i < n; i += 1024) ranks[i] = rk[i];
-  __syncthreads();
-  for (int i = threadIdx.x; i < n; i += 1024) {
-    const uint32_t mine = ranks[i];
-    int pos = 0;
-    for (int j = 0; j < n; ++j) pos += ranks[j] < mine;
-    perm[pos] = (uint32_t)i;
-  }
-  if (threadIdx.x == 0) nregions[im] = n;  // clamp (the overflow flag has been raised by the grow kernel)
+  if (lane == 0) nregions[im] = nreg_out;
 }
 
 // ---- rectangle fit -------------------------------------------------------------------------------------------
@@ -676,12 +548,12 @@ __device__ __forceinline__ double lsd_angle_diff(double a, double b) {
 
 __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gxy_all, size_t stride, int W,
                                                    const uint32_t* __restrict__ regpts_all,
-                                                   const uint4* __restrict__ regions_all, const uint32_t* __restrict__ perm_all,
-                                                   int max_regions, const int* __restrict__ nregions, double prec, double scale,
+                                                   const uint4* __restrict__ regions_all, int max_regions,
+                                                   const int* __restrict__ nregions, double prec, double scale,
                                                    float4* __restrict__ segs_all) {
   const int im = blockIdx.y, ri = blockIdx.x * 128 + threadIdx.x;
   if (ri >= nregions[im]) return;
-  const uint4 R = regions_all[(size_t)im * max_regions + perm_all[(size_t)im * max_regions + ri]];
+  const uint4 R = regions_all[(size_t)im * max_regions + ri];
   const uint32_t* pts = regpts_all + (size_t)im * stride + R.x;
   const short2* gxy = gxy_all + (size_t)im * stride;
   const int n = (int)R.y;
@@ -859,8 +731,7 @@ static void lsd_release(LsdState* s) {
   }
   cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap);
   cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->overflow); cudaFree(s->rs_tab);
-  cudaFree(s->grad_lut); cudaFree(s->lab); cudaFree(s->seed_grp); cudaFree(s->grp_count); cudaFree(s->reg_rank);
-  cudaFree(s->reg_perm);
+  cudaFree(s->grad_lut);
 }
 
 extern "C" void plf_lsd_free(plf_ctx* ctx) {
@@ -945,11 +816,6 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   PLF_CUDA(ctx, cudaMalloc(&s->maxmag2, N * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->rowcnt, N * s->hs * s->n_bins * sizeof(uint32_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->binstart, N * s->n_bins * sizeof(uint32_t)));
-  PLF_CUDA(ctx, cudaMalloc(&s->lab, As * N * sizeof(uint32_t)));
-  PLF_CUDA(ctx, cudaMalloc(&s->seed_grp, As * N));
-  PLF_CUDA(ctx, cudaMalloc(&s->grp_count, N * 32 * sizeof(int)));
-  PLF_CUDA(ctx, cudaMalloc(&s->reg_rank, N * s->max_regions * sizeof(uint32_t)));
-  PLF_CUDA(ctx, cudaMalloc(&s->reg_perm, N * s->max_regions * sizeof(uint32_t)));
   // buffers that cross from the pre-grow phase to the grow / match phases exist twice (parity of the batch), so that
   // batch i+1 can be extracted while batch i is still growing regions; standalone operators use parity 0 only
   for (int p = 0; p < (s->two_parities ? 2 : 1); ++p) {
@@ -1065,28 +931,11 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   plf_keyline* kls = s->kls[par] + o * s->max_lines;
   plf_keyline* kls_all = s->kls_all[par] + o * s->max_regions;
   int* nlines = s->nlines[par] + o;
-  uint32_t* lab = s->lab + o * As;
-  uint8_t* seed_grp = s->seed_grp + o * As;
-  int* grp_count = s->grp_count + o * 32;
-  uint32_t* reg_rank = s->reg_rank + o * s->max_regions;
-  uint32_t* reg_perm = s->reg_perm + o * s->max_regions;
-  const dim3 gpx((W + 255) / 256, H, n);
-  k_lsd_ccl_init<<<gpx, 256, 0, cs>>>(gxy, s->m2_min, As, W, H, lab, grp_count, nregions);
-  PLF_LAUNCH_CHECK(ctx);
-  k_lsd_ccl_union<<<gpx, 256, 0, cs>>>(As, W, H, lab);
-  PLF_LAUNCH_CHECK(ctx);
-  k_lsd_ccl_flatten<<<gpx, 256, 0, cs>>>(As, W, H, lab, grp_count);
-  PLF_LAUNCH_CHECK(ctx);
-  k_lsd_seed_groups<<<dim3((unsigned)((As + 255) / 256), n), 256, 0, cs>>>(order, nseeds, lab, As, seed_grp);
-  PLF_LAUNCH_CHECK(ctx);
-  plf_mark(ctx, "lsd.k_lsd_ccl(4 kernels)");
-  k_lsd_grow<<<dim3(LSD_GROUPS, n), 32, 0, cs>>>(pix, s->pix_stride, As, W, order, seed_grp, grp_count, nseeds, s->prec,
-                                                 s->min_reg_size, regpts, regions, reg_rank, s->max_regions, nregions, s->overflow);
+  k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, s->min_reg_size, regpts, regions, s->max_regions,
+                               nregions, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grow");
-  k_lsd_region_rank<<<n, 1024, (size_t)s->max_regions * sizeof(uint32_t), cs>>>(reg_rank, nregions, s->max_regions, reg_perm);
-  PLF_LAUNCH_CHECK(ctx);
-  k_lsd_rects<<<dim3((s->max_regions + 127) / 128, n), 128, 0, cs>>>(gxy, As, W, regpts, regions, reg_perm, s->max_regions, nregions,
+  k_lsd_rects<<<dim3((s->max_regions + 127) / 128, n), 128, 0, cs>>>(gxy, As, W, regpts, regions, s->max_regions, nregions,
                                                                      s->prec, s->scale, segs);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rects");
