@@ -449,6 +449,11 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
   const uint32_t* order = order_all + (size_t)im * stride;
   uint32_t* regpts = regpts_all + (size_t)im * stride;
   uint4* regions = regions_all + (size_t)im * max_regions;
+  // keep the per-image base pointers in registers: without these barriers ptxas re-derives them from (im, stride)
+  // with 64-bit multiplies at every access of the serial loop
+  asm volatile("" : "+l"(pix));
+  asm volatile("" : "+l"(regpts));
+  asm volatile("" : "+l"(regions));
   const int ns = nseeds[im];
   const int kk = lane < 9 ? lane : 4;                  // neighbour slot served by this lane (lanes >= 9 idle on the centre)
   const int noff = (kk / 3 - 1) * W + (kk % 3 - 1);   // linear offset of that neighbour (row-major 3x3: reference order)
