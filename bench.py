@@ -201,10 +201,11 @@ def main():
     os.dup2(2, 1)           # stdout of this process (and of any library writing to fd 1) -> stderr
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLF_BENCH_BATCH", "256")))
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLF_BENCH_BATCH", "768")),
+                    help="stereo pairs per step per GPU (~0.105 GB of HBM each; reduced automatically if it would not fit)")
     ap.add_argument("--pool", type=int, default=24, help="distinct rendered frames (ping-ponged to fill a batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -227,6 +228,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     B = args.batch
+    free_b, _tot = torch.cuda.mem_get_info()
+    fit = int((free_b * 0.85 - 4e9) / 0.105e9)       # every per-pair buffer exists for 2 batches in flight
+    if B > fit:
+        print(f"bench.py: batch {B} -> {max(fit, 8)} (free HBM {free_b / 1e9:.0f} GB)", file=sys.stderr)
+        B = max(fit, 8)
     w, h = CAM["width"], CAM["height"]
     lim = plf.default_limits()
     lim.max_batch = B; lim.max_keypoints = 4096; lim.max_segments = 8192; lim.max_lines = 1024
@@ -326,10 +332,18 @@ def main():
             ktab.append(dict(kernel=name, ms=round(ms, 4), share=round(ms / step_ms, 4) if step_ms else None,
                              algo_gbs=round(gbs, 1) if gbs else None, frac_hbm=round(gbs / peak, 4) if gbs else None))
         dom = max(ktab, key=lambda r: r["ms"]) if ktab else None
+        traffic = None
+        tp = ROOT / "profiles" / "ncu_traffic_per_image.json"      # dram bytes per image from the committed ncu --set full capture
+        if dom and tp.exists():
+            try:
+                per_img = json.loads(tp.read_text()).get(dom["kernel"])
+                traffic = per_img * 2 * B if per_img else None
+            except Exception:
+                traffic = None
         roof = None
         if dom and dom["algo_gbs"]:
             roof = dict(kernel=dom["kernel"], bound="hbm", achieved=dom["algo_gbs"], peak=peak, unit="GB/s",
-                        frac=round(dom["algo_gbs"] / peak, 5), traffic=None, peak_source=peak_src,
+                        frac=round(dom["algo_gbs"] / peak, 5), traffic=traffic, peak_source=peak_src,
                         note=("share of step %.0f%%; region growing is a sequential greedy partition per image: latency-bound, "
                               "reported against HBM for completeness" % (100 * dom["share"])) if "grow" in dom["kernel"] else None)
         whole = dict(algorithmic_bytes_per_pair=ab["pair"], achieved_gbs=round(ab["pair"] * value / 1e9, 1),

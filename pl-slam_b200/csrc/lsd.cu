@@ -257,7 +257,7 @@ __global__ void k_lsd_fill_guard(LsdPix* __restrict__ pix, size_t pix_stride, in
 
 // pix points at pixel (0,0) of image 0 (i.e. past the guard); image stride pix_stride.
 __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int W, int H,
-                                                  const LsdPix* __restrict__ lut, size_t stride,
+                                                  const LsdPix* __restrict__ lut, int m2_min, size_t stride,
                                                   short2* __restrict__ gxy, LsdPix* __restrict__ pix, size_t pix_stride,
                                                   int* __restrict__ maxmag2) {
   const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, im = blockIdx.z;
@@ -273,9 +273,12 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ im
       const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
       const int gx = DA + BC, gy = DA - BC;
       g = make_short2((short)gx, (short)gy);
-      const float4 raw = __ldg(reinterpret_cast<const float4*>(&lut[(gx + 510) * LSD_LUT_DIM + (gy + 510)]));
-      e = *reinterpret_cast<const LsdPix*>(&raw);
-      if (e.a != LSD_NOTDEF_D) mag2 = gx * gx + gy * gy;
+      const int m2 = gx * gx + gy * gy;
+      if (m2 >= m2_min) {  // defined level-line angle (~10 % of the pixels): only these touch the table
+        const float4 raw = __ldg(reinterpret_cast<const float4*>(&lut[(gx + 510) * LSD_LUT_DIM + (gy + 510)]));
+        e = *reinterpret_cast<const LsdPix*>(&raw);
+        mag2 = m2;
+      }
     }
     gxy[(size_t)im * stride + oi] = g;
     *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + oi]) = *reinterpret_cast<const float4*>(&e);
@@ -476,27 +479,36 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
       }
       __syncwarp();
       uint32_t nreg = 1;
-      LsdPix pf;
-      pf.a = LSD_NOTDEF_D; pf.c = 0.f; pf.s = 0.f;
-      int pf_i = 0;
-      bool have_pf = false;
+      // neighbourhood records of queue entries r+1 (pf1) and r+2 (pf2), fetched while earlier entries are processed;
+      // a cell accepted meanwhile is patched to "used" in both prefetched copies
+      LsdPix pf1, pf2;
+      pf1.a = pf2.a = LSD_NOTDEF_D; pf1.c = pf1.s = pf2.c = pf2.s = 0.f;
+      int i1 = -1, i2 = -1;
+      bool have1 = false, have2 = false;
       for (uint32_t r = 0; r < nreg; ++r) {
         LsdPix cur;
         int ci;
-        if (have_pf) {
-          cur = pf;
-          ci = pf_i;
+        if (have1) {
+          cur = pf1;
+          ci = i1;
         } else {
           const uint32_t pt = (nreg - r <= LSD_QCAP) ? q[r & (LSD_QCAP - 1)] : __ldcg(&regpts[cursor + r]);
           ci = (int)pt + noff;
           cur = lsd_load_pix(&pix[ci]);
         }
-        have_pf = false;
-        if (r + 1 < nreg) {  // neighbourhood of queue entry r+1, in flight while r is processed
+        pf1 = pf2; i1 = i2; have1 = have2;
+        have2 = false; i2 = -1;
+        if (!have1 && r + 1 < nreg) {
           const uint32_t pt = (nreg - (r + 1) <= LSD_QCAP) ? q[(r + 1) & (LSD_QCAP - 1)] : __ldcg(&regpts[cursor + r + 1]);
-          pf_i = (int)pt + noff;
-          pf = lsd_load_pix(&pix[pf_i]);
-          have_pf = true;
+          i1 = (int)pt + noff;
+          pf1 = lsd_load_pix(&pix[i1]);
+          have1 = true;
+        }
+        if (r + 2 < nreg) {
+          const uint32_t pt = (nreg - (r + 2) <= LSD_QCAP) ? q[(r + 2) & (LSD_QCAP - 1)] : __ldcg(&regpts[cursor + r + 2]);
+          i2 = (int)pt + noff;
+          pf2 = lsd_load_pix(&pix[i2]);
+          have2 = true;
         }
         unsigned rem = __ballot_sync(0xFFFFFFFFu, lane < 9 && cur.a != LSD_NOTDEF_D);
         while (rem) {
@@ -513,7 +525,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
             q[nreg & (LSD_QCAP - 1)] = (uint32_t)ai;
           }
           ++nreg;
-          if (pf_i == ai) pf.a = LSD_NOTDEF_D;  // the prefetched copy of this cell is stale (harmless when !have_pf)
+          if (i1 == ai) pf1.a = LSD_NOTDEF_D;  // prefetched copies of this cell are stale
+          if (i2 == ai) pf2.a = LSD_NOTDEF_D;
           sumdx = __fadd_rn(sumdx, ck);
           sumdy = __fadd_rn(sumdy, sk);
           reg_angle = (double)lsd_fast_atan2(sumdy, sumdx) * LSD_DEG2RAD;
@@ -903,7 +916,7 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
     scaled_stride = As;
   }
   PLF_CUDA(ctx, cudaMemsetAsync(maxmag2, 0xFF, (size_t)n * sizeof(int), cs));  // -1
-  k_lsd_grad<<<dim3((W + 255) / 256, H, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->grad_lut, As, gxy, pix, s->pix_stride, maxmag2);
+  k_lsd_grad<<<dim3((W + 255) / 256, H, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->grad_lut, s->m2_min, As, gxy, pix, s->pix_stride, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
   k_lsd_rowhist<<<dim3(H - 1, n), 256, 0, cs>>>(gxy, s->m2_min, As, W, H, s->n_bins, maxmag2, binmap, rowcnt);

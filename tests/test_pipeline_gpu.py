@@ -117,3 +117,32 @@ def test_two_batches_in_flight_match_sequential(built):
     for a, b in zip(seq, piped):
         assert a["status"] == b["status"] and a["n_stereo_pt"] == b["n_stereo_pt"] and a["n_inliers_pt"] == b["n_inliers_pt"]
         assert np.array_equal(a["DT"], b["DT"])          # same kernels, same inputs: bit-identical poses
+
+
+def test_trajectory_ate_vs_oracle_and_ground_truth(built):
+    """north_star: trajectory ATE within 1 % of the reference (CPU oracle) on the same synthetic sequence."""
+    cam = dict(plf.KITTI_CAMERA, width=800, height=300, cx=400.0, cy=150.0, fx=520.0, fy=520.0)
+    world = synth.World(seed=5, length=70.0, n_quads=240, n_segs=120, half_width=10.0, half_height=3.5)
+    frames = list(synth.stream(cam, 20, world=world, seed=21, step=0.3))
+    prm = dict(orb_nfeatures=1000, lsd_nfeatures=150)
+    ref = ofe.run_sequence(cam, [(a, b) for a, b, _ in frames], dict(ofe.DEFAULTS, **prm))
+    lim = plf.default_limits(); lim.max_batch = 5
+    got = []
+    with plf.Frontend(camera=cam, limits=lim, **prm) as fe:
+        for s0 in range(0, 20, 5):
+            got += fe.process_batch(np.stack([f[0] for f in frames[s0:s0 + 5]]), np.stack([f[1] for f in frames[s0:s0 + 5]]))
+
+    def chain(dts):
+        T, out = np.eye(4), []
+        for d in dts:
+            T = T @ d
+            out.append(T[:3, 3].copy())
+        return np.array(out)
+    p_gpu, p_ref = chain([g["DT"] for g in got]), chain([r["DT"] for r in ref])
+    T0inv = np.linalg.inv(frames[0][2])
+    p_gt = np.array([(T0inv @ f[2])[:3, 3] for f in frames])
+    ate = lambda p: float(np.sqrt(np.mean(np.sum((p - p_gt) ** 2, axis=1))))
+    ate_gpu, ate_ref = ate(p_gpu), ate(p_ref)
+    assert abs(ate_gpu - ate_ref) <= 0.01 * max(ate_ref, 1e-9)          # within 1 % of the reference's ATE
+    assert np.max(np.linalg.norm(p_gpu - p_ref, axis=1)) < 1e-6          # in fact the trajectories coincide
+    assert ate_gpu < 0.02 * np.linalg.norm(p_gt[-1])                     # and both follow the planted trajectory
