@@ -59,11 +59,12 @@ def kernel_bytes(name, ab, n_kp, m_lines):
         "orb.k_rbrief": 512 * n_kp + 32 * n_kp,
         "lsd.k_blur_q8": 2 * A0,
         "lsd.k_resize_exact": A0 + Ns,
-        "lsd.k_lsd_grad": Ns + 8 * Ns,                            # read scaled u8, write (gx,gy) + angle
-        "lsd.k_lsd_rowhist": 8 * Ns + 2 * Ns,
+        "lsd.k_lsd_grad": Ns + 20 * Ns,                           # read scaled u8, write (gx,gy) 4 B + {angle f64, cos, sin} 16 B
+        "lsd.k_lsd_rowhist": 4 * Ns + 2 * Ns + 4 * 1024 * round(ab["Ns"] ** 0.5),
         "lsd.k_lsd_binscan": 2 * 4 * 1024 * round(ab["Ns"] ** 0.5),
-        "lsd.k_lsd_scatter": 6 * Ns + 4 * Ns,
-        "lsd.k_lsd_grow": 6 * Ns,                                 # read angle + r/w used mask
+        "lsd.k_lsd_scatter": 6 * Ns + 4 * 1024 * round(ab["Ns"] ** 0.5) + 4 * (Ns // 8),
+        "lsd.k_lsd_grow": 6 * Ns,                                 # read angle + r/w used mask (formula kept;
+                                                                  # the 16-byte records actually touched are ~9x that)
         "lsd.k_lsd_rects": 3 * 8 * Ns // 4,
         "lsd.k_keylines": 16 * 1200 + 68 * 1200,
         "lbd.k_blur5_sobel": A0 + 4 * A0,

@@ -283,9 +283,18 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ im
     gxy[(size_t)im * stride + oi] = g;
     *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + oi]) = *reinterpret_cast<const float4*>(&e);
   }
+  // per-image maximum: reduce in the CTA first, and only touch the (single, contended) address when it would grow
+  __shared__ int s_max[8];
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) mag2 = max(mag2, __shfl_xor_sync(0xFFFFFFFFu, mag2, off));
-  if ((threadIdx.x & 31) == 0 && mag2 >= 0) atomicMax(&maxmag2[im], mag2);
+  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mag2;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int m = s_max[0];
+#pragma unroll
+    for (int k = 1; k < 8; ++k) m = max(m, s_max[k]);
+    if (m >= 0 && m > __ldcg(&maxmag2[im])) atomicMax(&maxmag2[im], m);
+  }
 }
 
 // ---- pseudo-ordering (stable counting sort, bins descending) ---------------------------------------------------
