@@ -60,7 +60,7 @@ struct LsdState {
   int m2_min = 0;             // smallest gx^2+gy^2 whose gradient norm exceeds rho (defined pixel)
   uint16_t* binmap = nullptr; // [nimg][hs*ws]
   int* maxmag2 = nullptr;     // [nimg]
-  uint32_t* rowcnt = nullptr; // [nimg][hs][n_bins]
+  uint32_t* rowcnt = nullptr; // [nimg][nchunks][n_bins]  per-chunk bin counts -> prefixes
   uint32_t* binstart = nullptr; // [nimg][n_bins]
   int* nseeds[2] = {nullptr, nullptr};      // [nimg]
   uint32_t* order[2] = {nullptr, nullptr};  // [nimg][hs*ws]
@@ -304,52 +304,50 @@ __device__ __forceinline__ double lsd_bin_coef(int maxmag2, int n_bins) {
   return max_grad > 0 ? (double)(n_bins - 1) / max_grad : 0.0;
 }
 
+// The image is cut into chunks of LSD_CHUNK rows; one CTA histograms a chunk, one warp scatters it (raster order kept).
+#define LSD_CHUNK 16
+#define LSD_BIN_UNDEF 0xFFFFu
 __global__ void __launch_bounds__(256) k_lsd_rowhist(const short2* __restrict__ gxy, int m2_min,
-                                                     size_t stride, int W, int H, int n_bins,
+                                                     size_t stride, int W, int H, int n_bins, int nchunks,
                                                      const int* __restrict__ maxmag2, uint16_t* __restrict__ binmap,
-                                                     uint32_t* __restrict__ rowcnt) {
+                                                     uint32_t* __restrict__ chunkcnt) {
   __shared__ uint32_t hist[LSD_BINS_MAX];
-  const int y = blockIdx.x, im = blockIdx.y;
+  const int ch = blockIdx.x, im = blockIdx.y;
   for (int i = threadIdx.x; i < n_bins; i += 256) hist[i] = 0;
   __syncthreads();
   const double coef = lsd_bin_coef(maxmag2[im], n_bins);
-  const size_t o = (size_t)im * stride + (size_t)y * W;
-  for (int x = threadIdx.x; x < W - 1; x += 256) {
-    const short2 g = gxy[o + x];
-    const int m2 = g.x * g.x + g.y * g.y;
-    if (m2 < m2_min) continue;  // undefined level-line angle (norm <= rho): never a seed
-    const double norm = sqrt((double)m2 / 4.0);
-    const int b = (int)(norm * coef);
-    binmap[o + x] = (uint16_t)b;
-    atomicAdd(&hist[b], 1u);
+  const int y1 = min((ch + 1) * LSD_CHUNK, H - 1);
+  for (int y = ch * LSD_CHUNK; y < y1; ++y) {
+    const size_t o = (size_t)im * stride + (size_t)y * W;
+    for (int x = threadIdx.x; x < W - 1; x += 256) {
+      const short2 g = gxy[o + x];
+      const int m2 = g.x * g.x + g.y * g.y;
+      uint16_t bv = LSD_BIN_UNDEF;  // undefined level-line angle (norm <= rho): never a seed
+      if (m2 >= m2_min) {
+        const double norm = sqrt((double)m2 / 4.0);
+        const int b = (int)(norm * coef);
+        bv = (uint16_t)b;
+        atomicAdd(&hist[b], 1u);
+      }
+      binmap[o + x] = bv;
+    }
   }
   __syncthreads();
-  uint32_t* out = rowcnt + ((size_t)im * H + y) * n_bins;
+  uint32_t* out = chunkcnt + ((size_t)im * nchunks + ch) * n_bins;
   for (int i = threadIdx.x; i < n_bins; i += 256) out[i] = hist[i];
 }
 
-// one block (n_bins threads, <= 1024) per image: per-bin prefix over rows, then start of each bin (bins descending)
-__global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ rowcnt, int H, int n_bins,
+// one block (n_bins threads, <= 1024) per image: per-bin prefix over chunks, then start of each bin (bins descending)
+__global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ chunkcnt, int nchunks, int n_bins,
                                                       uint32_t* __restrict__ binstart, int* __restrict__ nseeds) {
   __shared__ uint32_t tot[LSD_BINS_MAX];
   const int im = blockIdx.x, b = threadIdx.x;
   uint32_t run = 0;
   if (b < n_bins) {
-    uint32_t* c = rowcnt + (size_t)im * H * n_bins + b;
-    int y = 0;
-    for (; y + 8 <= H - 1; y += 8) {  // 8 independent loads in flight per thread
-      uint32_t v[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) v[k] = c[(size_t)(y + k) * n_bins];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        c[(size_t)(y + k) * n_bins] = run;
-        run += v[k];
-      }
-    }
-    for (; y < H - 1; ++y) {
-      const uint32_t v = c[(size_t)y * n_bins];
-      c[(size_t)y * n_bins] = run;
+    uint32_t* c = chunkcnt + (size_t)im * nchunks * n_bins + b;
+    for (int k = 0; k < nchunks; ++k) {
+      const uint32_t v = c[(size_t)k * n_bins];
+      c[(size_t)k * n_bins] = run;
       run += v;
     }
     tot[b] = run;
@@ -371,45 +369,49 @@ __global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ row
   if (b == n_bins - 1) nseeds[im] = (int)sc[b];
 }
 
-// one warp per (row, image): stable ranks inside the row via match_any, raster order preserved
-__global__ void __launch_bounds__(128) k_lsd_scatter(const short2* __restrict__ gxy, int m2_min, const uint16_t* __restrict__ binmap,
-                                                     size_t stride, int W, int H, int n_bins,
-                                                     const uint32_t* __restrict__ rowcnt,
+// one warp per (chunk, image): stable ranks via match_any, raster order preserved; the bin of the next 32 pixels is
+// fetched while the current group is ranked
+__global__ void __launch_bounds__(128) k_lsd_scatter(const uint16_t* __restrict__ binmap, size_t stride, int W, int H,
+                                                     int n_bins, int nchunks, const uint32_t* __restrict__ chunkcnt,
                                                      const uint32_t* __restrict__ binstart,
                                                      uint32_t* __restrict__ order) {
   __shared__ uint32_t cnt[4][LSD_BINS_MAX];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int y = blockIdx.x * 4 + wid, im = blockIdx.y;
-  if (y >= H - 1) return;
+  const int ch = blockIdx.x * 4 + wid, im = blockIdx.y;
+  if (ch >= nchunks) return;
   uint32_t* c = cnt[wid];
-  const uint32_t* rc = rowcnt + ((size_t)im * H + y) * n_bins;
+  const uint32_t* rc = chunkcnt + ((size_t)im * nchunks + ch) * n_bins;
   const uint32_t* bs = binstart + (size_t)im * n_bins;
   for (int i = lane; i < n_bins; i += 32) c[i] = rc[i] + bs[i];
   __syncwarp();
-  const size_t o = (size_t)im * stride + (size_t)y * W;
   uint32_t* ord = order + (size_t)im * stride;
-  for (int x0 = 0; x0 < W - 1; x0 += 32) {
-    const int x = x0 + lane;
-    bool valid = false;
-    if (x < W - 1) {
-      const short2 g = gxy[o + x];
-      valid = g.x * g.x + g.y * g.y >= m2_min;
-    }
-    const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
-    if (valid) {
-      const int b = binmap[o + x];
-      const unsigned peers = __match_any_sync(vm, b);
-      const int rank = __popc(peers & ((1u << lane) - 1));
-      const int leader = __ffs(peers) - 1;
-      uint32_t base = 0;
-      if (lane == leader) {
-        base = c[b];
-        c[b] = base + __popc(peers);
+  const int y1 = min((ch + 1) * LSD_CHUNK, H - 1);
+  const int ngrp = (W - 1 + 31) / 32;
+  for (int y = ch * LSD_CHUNK; y < y1; ++y) {
+    const uint16_t* brow = binmap + (size_t)im * stride + (size_t)y * W;
+    uint16_t nxt = lane < W - 1 ? brow[lane] : (uint16_t)LSD_BIN_UNDEF;
+    for (int gi = 0; gi < ngrp; ++gi) {
+      const int x = gi * 32 + lane;
+      const uint16_t bv = nxt;
+      const int xn = x + 32;
+      nxt = (gi + 1 < ngrp && xn < W - 1) ? brow[xn] : (uint16_t)LSD_BIN_UNDEF;
+      const bool valid = bv != LSD_BIN_UNDEF;
+      const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
+      if (valid) {
+        const int b = bv;
+        const unsigned peers = __match_any_sync(vm, b);
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) {
+          base = c[b];
+          c[b] = base + __popc(peers);
+        }
+        base = __shfl_sync(peers, base, leader);
+        ord[base + rank] = (uint32_t)(y * W + x);
       }
-      base = __shfl_sync(peers, base, leader);
-      ord[base + rank] = (uint32_t)(y * W + x);
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -841,7 +843,7 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   PLF_CUDA(ctx, cudaMalloc(&s->scaled, As * N));
   PLF_CUDA(ctx, cudaMalloc(&s->binmap, As * N * sizeof(uint16_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->maxmag2, N * sizeof(int)));
-  PLF_CUDA(ctx, cudaMalloc(&s->rowcnt, N * s->hs * s->n_bins * sizeof(uint32_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->rowcnt, N * ((s->hs + LSD_CHUNK - 1) / LSD_CHUNK) * s->n_bins * sizeof(uint32_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->binstart, N * s->n_bins * sizeof(uint32_t)));
   // buffers that cross from the pre-grow phase to the grow / match phases exist twice (parity of the batch), so that
   // batch i+1 can be extracted while batch i is still growing regions; standalone operators use parity 0 only
@@ -898,7 +900,8 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
   LsdPix* pix = s->pix[par] + o * s->pix_stride + (s->ws + 1);  // pixel (0,0) of the first image of the range
   uint16_t* binmap = s->binmap + o * As;
   int* maxmag2 = s->maxmag2 + o;
-  uint32_t* rowcnt = s->rowcnt + o * H * s->n_bins;
+  const int nchunks = (H - 1 + LSD_CHUNK - 1) / LSD_CHUNK;
+  uint32_t* rowcnt = s->rowcnt + o * nchunks * s->n_bins;
   uint32_t* binstart = s->binstart + o * s->n_bins;
   int* nseeds = s->nseeds[par] + o;
   uint32_t* order = s->order[par] + o * As;
@@ -928,13 +931,13 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
   k_lsd_grad<<<dim3((W + 255) / 256, H, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->grad_lut, s->m2_min, As, gxy, pix, s->pix_stride, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
-  k_lsd_rowhist<<<dim3(H - 1, n), 256, 0, cs>>>(gxy, s->m2_min, As, W, H, s->n_bins, maxmag2, binmap, rowcnt);
+  k_lsd_rowhist<<<dim3(nchunks, n), 256, 0, cs>>>(gxy, s->m2_min, As, W, H, s->n_bins, nchunks, maxmag2, binmap, rowcnt);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rowhist");
-  k_lsd_binscan<<<n, 1024, 0, cs>>>(rowcnt, H, s->n_bins, binstart, nseeds);
+  k_lsd_binscan<<<n, 1024, 0, cs>>>(rowcnt, nchunks, s->n_bins, binstart, nseeds);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_binscan");
-  k_lsd_scatter<<<dim3((H - 1 + 3) / 4, n), 128, 0, cs>>>(gxy, s->m2_min, binmap, As, W, H, s->n_bins, rowcnt, binstart, order);
+  k_lsd_scatter<<<dim3((nchunks + 3) / 4, n), 128, 0, cs>>>(binmap, As, W, H, s->n_bins, nchunks, rowcnt, binstart, order);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_scatter");
   return PLF_OK;

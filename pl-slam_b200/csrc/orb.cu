@@ -143,8 +143,8 @@ __device__ int fast_corner_score(const int* d /*16*/) {
 // region (3-px ring).  All index arithmetic is lane + 32*k / warp + 8*k (no div/mod), every lane is active in every pass.
 #define FN_OW 62
 #define FN_OH 30
-__global__ void __launch_bounds__(256) k_fast_nms(const uint8_t* __restrict__ img0, size_t img0_stride,
-                                                  const uint8_t* __restrict__ pyr, OrbGeom g, int l, int tiles_x,
+__global__ void __launch_bounds__(256, 6) k_fast_nms(const uint8_t* __restrict__ img0, size_t img0_stride,
+                                                     const uint8_t* __restrict__ pyr, OrbGeom g, int l, int tiles_x,
                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_count,
                                                   int* __restrict__ hist, int* __restrict__ overflow) {
   const int W = g.w[l], H = g.h[l];
@@ -521,24 +521,39 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const uint8_t* __restric
 }
 
 // ---- rBRIEF --------------------------------------------------------------------------------------------
+// One warp per keypoint.  The 37x37 neighbourhood of the (blurred) keypoint that the 512 rotated samples can reach
+// (|offset| <= 18) is first copied to shared memory with row-contiguous loads; the 16 samples of each lane then come
+// from shared memory instead of 16 scattered global sectors.
+#define RB_R 18
+#define RB_D (2 * RB_R + 1)
+#define RB_P 40
 __global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur, OrbGeom g,
                                                 const plf_keypoint* __restrict__ kps,
                                                 const int* __restrict__ kp_count, const int8_t* __restrict__ pattern,
                                                 uint8_t* __restrict__ desc) {
   __shared__ int8_t pat[1024];
+  __shared__ uint8_t patch[8][RB_D][RB_P];
   for (int i = threadIdx.x; i < 1024; i += 256) pat[i] = pattern[i];
   __syncthreads();
   const int img = blockIdx.y;
-  const int ki = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ki = blockIdx.x * 8 + wrp;
   if (ki >= kp_count[img]) return;
   const plf_keypoint kp = kps[(size_t)img * g.max_kp + ki];
   const int l = kp.octave, W = g.w[l];
   const float scale = __fdiv_rn(1.f, g.scale[l]);
   const float angle = __fmul_rn(kp.angle, (float)(3.14159265358979323846 / 180.f));
   const float a = (float)cos((double)angle), b = (float)sin((double)angle);
-  const uint8_t* center = blur + (size_t)img * g.blur_stride + g.blur_off[l] +
-                          (size_t)__float2int_rn(__fmul_rn(kp.y, scale)) * W + __float2int_rn(__fmul_rn(kp.x, scale));
+  const int cyi = __float2int_rn(__fmul_rn(kp.y, scale)), cxi = __float2int_rn(__fmul_rn(kp.x, scale));
+  // keypoints are >= edge (19) pixels inside the level, so the 37x37 window never leaves it
+  const uint8_t* base = blur + (size_t)img * g.blur_stride + g.blur_off[l] + (size_t)(cyi - RB_R) * W + (cxi - RB_R);
+  uint8_t (*P)[RB_P] = patch[wrp];
+  for (int r = 0; r < RB_D; ++r) {
+    const uint8_t* row = base + (size_t)r * W;
+    P[r][lane] = row[lane];
+    if (lane < RB_D - 32) P[r][32 + lane] = row[32 + lane];
+  }
+  __syncwarp();
   unsigned val = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
@@ -548,7 +563,7 @@ __global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur
     const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(qx0, b), __fmul_rn(qy0, a)));
     const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(qx1, a), __fmul_rn(qy1, b)));
     const int iy1 = __float2int_rn(__fadd_rn(__fmul_rn(qx1, b), __fmul_rn(qy1, a)));
-    const int t0 = center[iy0 * W + ix0], t1 = center[iy1 * W + ix1];
+    const int t0 = P[RB_R + iy0][RB_R + ix0], t1 = P[RB_R + iy1][RB_R + ix1];
     val |= (t0 < t1 ? 1u : 0u) << j;
   }
   desc[((size_t)img * g.max_kp + ki) * 32 + lane] = (uint8_t)val;
