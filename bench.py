@@ -44,7 +44,8 @@ def algorithmic_bytes_per_pair(w, h, s=1.2, n_kp=1500, m_lines=200, lbar=90):
     lsd = A0 + 2 * Ns + 8 * Ns + 8 * Ns + 6 * Ns + 16 * m_lines
     lbd = A0 + 4 * A0 + min(4 * A0, 63 * lbar * 4 * m_lines) + 32 * m_lines
     match = 2 * 32 * n_kp + 4 * n_kp + 2 * 32 * m_lines + 4 * m_lines
-    return dict(orb=orb, lsd=lsd, lbd=lbd, match=match, pair=2 * (orb + lsd + lbd) + match, Ns=Ns, A0=A0, S=S, A=A)
+    return dict(orb=orb, lsd=lsd, lbd=lbd, match=match, pair=2 * (orb + lsd + lbd) + match, Ns=Ns, A0=A0, S=S, A=A,
+                chunks=(round(h * s) + 14) // 16)
 
 
 # algorithmic bytes per IMAGE (or per pair where noted) of each kernel, for the per-kernel GB/s table
@@ -60,9 +61,9 @@ def kernel_bytes(name, ab, n_kp, m_lines):
         "lsd.k_blur_q8": 2 * A0,
         "lsd.k_resize_exact": A0 + Ns,
         "lsd.k_lsd_grad": Ns + 20 * Ns,                           # read scaled u8, write (gx,gy) 4 B + {angle f64, cos, sin} 16 B
-        "lsd.k_lsd_rowhist": 4 * Ns + 2 * Ns + 4 * 1024 * round(ab["Ns"] ** 0.5),
-        "lsd.k_lsd_binscan": 2 * 4 * 1024 * round(ab["Ns"] ** 0.5),
-        "lsd.k_lsd_scatter": 6 * Ns + 4 * 1024 * round(ab["Ns"] ** 0.5) + 4 * (Ns // 8),
+        "lsd.k_lsd_rowhist": 4 * Ns + 2 * Ns + 4 * 1024 * ab["chunks"],   # read (gx,gy), write bin map + chunk histograms
+        "lsd.k_lsd_binscan": 2 * 4 * 1024 * ab["chunks"],
+        "lsd.k_lsd_scatter": 2 * Ns + 4 * 1024 * ab["chunks"] + 4 * (Ns // 8),  # read bin map, write the seed list
         "lsd.k_lsd_grow": 6 * Ns,                                 # read angle + r/w used mask (formula kept;
                                                                   # the 16-byte records actually touched are ~9x that)
         "lsd.k_lsd_rects": 3 * 8 * Ns // 4,

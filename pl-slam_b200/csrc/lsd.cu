@@ -55,7 +55,7 @@ struct LsdState {
   uint8_t* blur = nullptr;    // [nimg][h*w]
   uint8_t* scaled = nullptr;  // [nimg][hs*ws]
   short2* gxy[2] = {nullptr, nullptr};      // [nimg][hs*ws]
-  struct LsdPix* pix[2] = {nullptr, nullptr};  // [nimg][guard + hs*ws]  {angle (rad, f64) | NOTDEF = undefined/used, cosf, sinf}
+  struct LsdPix* pix[2] = {nullptr, nullptr};  // [nimg][guard + hs*ws]  {angle (deg, f32) | NOTDEF = undefined/used, cosf, sinf, pad}
   size_t pix_stride = 0;      // entries per image = guard (ws+1, permanently NOTDEF) + hs*ws
   int m2_min = 0;             // smallest gx^2+gy^2 whose gradient norm exceeds rho (defined pixel)
   uint16_t* binmap = nullptr; // [nimg][hs*ws]
@@ -219,11 +219,12 @@ __device__ __forceinline__ float lsd_fast_atan2(float y, float x) {  // cv::fast
 
 // Per-pixel record read by the region-growing kernel: one 16-byte load per neighbour.
 struct __align__(16) LsdPix {
-  double a;  // level-line angle in radians (cv::fastAtan2(gx,-gy) * DEG_TO_RADS, as OpenCV stores it) or LSD_NOTDEF_D
-  float c;   // cosf(float(a))  \ the increments region_grow adds to (sumdx, sumdy); host libm semantics
-  float s;   // sinf(float(a))  /  via the glibc port
+  float a;    // level-line angle in DEGREES exactly as cv::fastAtan2(gx,-gy) returns it (OpenCV stores a * DEG_TO_RADS as
+              // f64; that product is re-formed where the f64 value is needed) or LSD_NOTDEF_F = undefined / used
+  float c, s; // cosf / sinf of float(angle in radians)
+  float pad;
 };
-#define LSD_NOTDEF_D (-1024.0)
+#define LSD_NOTDEF_F (-1024.f)
 
 // Gradient lookup table.  The 2x2 gradient (gx, gy) takes 1021 x 1021 integer values; the level-line angle, the NOTDEF
 // decision (|grad| <= rho) and cosf/sinf of float(angle) are functions of (gx, gy) only.  They are tabulated once per
@@ -235,12 +236,12 @@ __global__ void __launch_bounds__(256) k_lsd_build_lut(double rho, LsdPix* __res
   if (i >= LSD_LUT_DIM * LSD_LUT_DIM) return;
   const int gx = i / LSD_LUT_DIM - 510, gy = i % LSD_LUT_DIM - 510;
   LsdPix e;
-  e.a = LSD_NOTDEF_D; e.c = 0.f; e.s = 0.f;
+  e.a = LSD_NOTDEF_F; e.c = 0.f; e.s = 0.f; e.pad = 0.f;
   const double norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
   if (!(norm <= rho)) {
     const float adeg = lsd_fast_atan2((float)gx, (float)(-gy));
-    e.a = (double)adeg * LSD_DEG2RAD;
-    const float af = (float)e.a;  // region_grow: cos(float(angle)), sin(float(angle)) with the host libm -> glibc port
+    e.a = adeg;
+    const float af = (float)((double)adeg * LSD_DEG2RAD);  // region_grow: cos(float(angle)), sin(float(angle)), host libm -> glibc port
     e.c = glibc_cosf(af);
     e.s = glibc_sinf(af);
   }
@@ -251,7 +252,7 @@ __global__ void k_lsd_fill_guard(LsdPix* __restrict__ pix, size_t pix_stride, in
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= guard * nimg) return;
   LsdPix e;
-  e.a = LSD_NOTDEF_D; e.c = 0.f; e.s = 0.f;
+  e.a = LSD_NOTDEF_F; e.c = 0.f; e.s = 0.f; e.pad = 0.f;
   pix[(size_t)(i / guard) * pix_stride + (i % guard)] = e;
 }
 
@@ -266,7 +267,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ im
     const int oi = y * W + x;
     short2 g = make_short2(0, 0);
     LsdPix e;
-    e.a = LSD_NOTDEF_D; e.c = 0.f; e.s = 0.f;
+    e.a = LSD_NOTDEF_F; e.c = 0.f; e.s = 0.f; e.pad = 0.f;
     if (x < W - 1 && y < H - 1) {
       const uint8_t* r0 = img + (size_t)im * img_stride + oi;
       const uint8_t* r1 = r0 + W;
@@ -438,115 +439,173 @@ __device__ __forceinline__ bool lsd_aligned_rad(double a, double theta, double p
   return n_theta <= prec;
 }
 
+// The warp that grows an image is the only reader and writer of that image's records while the kernel runs, and a CTA
+// never leaves its SM, so L1-cached loads (ld.ca) are coherent with the warp's own stores.
 __device__ __forceinline__ LsdPix lsd_load_pix(const LsdPix* p) {
-  const float4 raw = __ldcg(reinterpret_cast<const float4*>(p));
+  const float4 raw = __ldca(reinterpret_cast<const float4*>(p));
   return *reinterpret_cast<const LsdPix*>(&raw);
 }
+__device__ __forceinline__ void lsd_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
 // One warp per image.  Pixels are addressed by their linear index i = y*W + x; the 8 neighbours are i + {-W-1 .. W+1}.
 // No bounds tests are needed: the last column and last row of the map are always NOTDEF (ll_angle), so x-1 / x+1 wrap
 // onto NOTDEF pixels, y+1 stays inside, and a guard of W+1 permanently-NOTDEF records precedes pixel 0 for y-1.
-// Per region point: lanes 0..8 hold the 16-byte records of the 3x3 neighbourhood, fetched one queue entry AHEAD (the
-// loads for point r+1 are in flight while point r is processed; cells accepted meanwhile are patched to "used" in the
-// prefetched registers).  The alignment test of all remaining neighbours runs lane-parallel and is repeated after every
-// acceptance, which reproduces the reference's sequential semantics (each test sees the region angle left by the
-// previous acceptance).
+// Per region point: lanes 0..8 hold the 16-byte records of the 3x3 neighbourhood, fetched two queue entries AHEAD; cells
+// accepted meanwhile are patched to "used" in the prefetched registers.  The neighbours are decided lane-parallel and
+// re-decided after every acceptance, which reproduces the reference's sequential semantics (each test sees the region
+// angle left by the previous acceptance).
+//
+// Deferred region angle.  The reference recomputes theta_i = fastAtan2(S_i) after every acceptance (S_i = running sum of
+// the members' unit vectors).  Most decisions do not need it: with th = the last angle that WAS evaluated (at sum S_0),
+//   |theta_i - th| <= m_i,   m_0 = 2E + slack,   m_{i+1} = m_i + min(d_k + m_i, prec + E) / |S_0|       (degrees)
+// because adding a unit vector at angle phi to S turns it by at most phi / |S| (tan(delta) = sin(phi) / (|S| + cos(phi))),
+// phi <= d_k + m_i for the accepted cell k, |S_i| never shrinks (every member is within prec + E < 90 deg of S), and
+// E = 0.02 deg bounds the error of the fastAtan2 polynomial (measured maximum 0.0096 deg).  A neighbour whose distance
+// to th is below prec - m_i is aligned under theta_i whatever theta_i is, one above prec + m_i is not; only when the FIRST
+// undecided neighbour falls inside the band is theta_i evaluated (th <- fastAtan2(S_i), m <- m_0), and if it is still
+// inside the (now 0.05 deg) band the reference's own f64 test decides.  The float sums S_i are accumulated in the
+// reference's order either way, so every accepted/rejected decision - and the final angle - is the reference's.
+#define LSD_MARGIN0 0.05f
 __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
                                                  const uint32_t* __restrict__ order_all,
-                                                 const int* __restrict__ nseeds, double prec, int min_reg_size,
-                                                 uint32_t* __restrict__ regpts_all, uint4* __restrict__ regions_all,
-                                                 int max_regions, int* __restrict__ nregions,
-                                                 int* __restrict__ overflow) {
+                                                 const int* __restrict__ nseeds, double prec, float prec_deg,
+                                                 int min_reg_size, uint32_t* __restrict__ regpts_all,
+                                                 uint4* __restrict__ regions_all, int max_regions,
+                                                 int* __restrict__ nregions, int* __restrict__ overflow) {
   __shared__ uint32_t q[LSD_QCAP];
   const int im = blockIdx.x, lane = threadIdx.x;
   LsdPix* pix = pix_all + (size_t)im * pix_stride;
   const uint32_t* order = order_all + (size_t)im * stride;
   uint32_t* regpts = regpts_all + (size_t)im * stride;
   uint4* regions = regions_all + (size_t)im * max_regions;
-  // keep the per-image base pointers in registers: without these barriers ptxas re-derives them from (im, stride)
-  // with 64-bit multiplies at every access of the serial loop
+  // keep the per-image base pointers (and the queue's shared-window address) in registers: without these barriers ptxas
+  // re-derives them with 64-bit multiplies / special-register reads at every access of the serial loop
+  uint32_t qs = (uint32_t)__cvta_generic_to_shared(q);
   asm volatile("" : "+l"(pix));
   asm volatile("" : "+l"(regpts));
   asm volatile("" : "+l"(regions));
+  asm volatile("" : "+r"(qs));
   const int ns = nseeds[im];
   const int kk = lane < 9 ? lane : 4;                  // neighbour slot served by this lane (lanes >= 9 idle on the centre)
   const int noff = (kk / 3 - 1) * W + (kk % 3 - 1);   // linear offset of that neighbour (row-major 3x3: reference order)
+  // look-ahead window fetched into L1/L2 whenever a pixel joins the region: 7 rows x 4 sectors around it (the cells the
+  // next two breadth-first layers will examine), one address per lane
+  const int poff = lane < 28 ? (lane / 4 - 3) * W + (lane % 4) * 2 - 3 : 0;
+  const int pmin = -(W + 1), pmax = (int)pix_stride - (W + 1) - 1;  // records of this image (guard included)
+  // ang_th close to 90 deg would break the "sum never shrinks" argument: fall back to evaluating every angle
+  const float margin0 = prec_deg <= 60.f ? LSD_MARGIN0 : 1e30f;
+  const float dmax = prec_deg + LSD_MARGIN0;
   uint32_t cursor = 0;
   int nreg_out = 0;
+  uint32_t seed_next = lane < ns ? order[lane] : 0u;
   for (int s0 = 0; s0 < ns; s0 += 32) {
     const int si = s0 + lane;
-    const uint32_t seed = si < ns ? order[si] : 0u;
-    double a0 = si < ns ? __ldcg(&pix[seed].a) : LSD_NOTDEF_D;
-    unsigned pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF_D);
+    const uint32_t seed = seed_next;
+    float a0 = si < ns ? __ldcg(&pix[seed].a) : LSD_NOTDEF_F;
+    seed_next = si + 32 < ns ? order[si + 32] : 0u;   // next group of seeds: index now, record into L2 while this group runs
+    if (si + 32 < ns) asm volatile("prefetch.global.L2 [%0];" ::"l"(&pix[seed_next]));
+    unsigned pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF_F);
     while (pending) {
       const int src = __ffs(pending) - 1;
       const uint32_t sidx = __shfl_sync(0xFFFFFFFFu, seed, src);
-      double reg_angle = __shfl_sync(0xFFFFFFFFu, a0, src);
-      float sumdx = (float)cos(reg_angle), sumdy = (float)sin(reg_angle);
+      float th = __shfl_sync(0xFFFFFFFFu, a0, src);      // region angle (degrees) at the last evaluation
+      const double th_seed = (double)th * LSD_DEG2RAD;    // the reference's f64 angle of the seed
+      float sumdx = (float)cos(th_seed), sumdy = (float)sin(th_seed);
+      float margin = margin0, inv0 = 1.02f;               // m_i and an upper bound of 1/|S_0|
+      float lo = prec_deg - margin, hi = prec_deg + margin;
+      bool fresh = true;                                  // th is the reference's current angle
       if (lane == 0) {
-        pix[sidx].a = LSD_NOTDEF_D;
+        pix[sidx].a = LSD_NOTDEF_F;
         regpts[cursor] = sidx;
-        q[0] = sidx;
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(qs), "r"(sidx) : "memory");
       }
+      lsd_prefetch(&pix[min(max((int)sidx + poff, pmin), pmax)]);
       __syncwarp();
       uint32_t nreg = 1;
       // neighbourhood records of queue entries r+1 (pf1) and r+2 (pf2), fetched while earlier entries are processed;
-      // a cell accepted meanwhile is patched to "used" in both prefetched copies
+      // a cell accepted meanwhile is patched to "used" in both prefetched copies (i < pmin: nothing fetched)
       LsdPix pf1, pf2;
-      pf1.a = pf2.a = LSD_NOTDEF_D; pf1.c = pf1.s = pf2.c = pf2.s = 0.f;
-      int i1 = -1, i2 = -1;
-      bool have1 = false, have2 = false;
+      pf1.a = pf2.a = LSD_NOTDEF_F; pf1.c = pf1.s = pf2.c = pf2.s = 0.f;
+      int i1 = pmin - 1, i2 = pmin - 1;
       for (uint32_t r = 0; r < nreg; ++r) {
         LsdPix cur;
         int ci;
-        if (have1) {
+        if (i1 >= pmin) {
           cur = pf1;
           ci = i1;
         } else {
-          const uint32_t pt = (nreg - r <= LSD_QCAP) ? q[r & (LSD_QCAP - 1)] : __ldcg(&regpts[cursor + r]);
+          uint32_t pt;
+          if (nreg - r <= LSD_QCAP) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pt) : "r"(qs + ((r & (LSD_QCAP - 1)) << 2)) : "memory");
+          else pt = __ldcg(&regpts[cursor + r]);
           ci = (int)pt + noff;
           cur = lsd_load_pix(&pix[ci]);
         }
-        pf1 = pf2; i1 = i2; have1 = have2;
-        have2 = false; i2 = -1;
-        if (!have1 && r + 1 < nreg) {
-          const uint32_t pt = (nreg - (r + 1) <= LSD_QCAP) ? q[(r + 1) & (LSD_QCAP - 1)] : __ldcg(&regpts[cursor + r + 1]);
+        pf1 = pf2; i1 = i2;
+        i2 = pmin - 1;
+        if (i1 < pmin && r + 1 < nreg) {
+          uint32_t pt;
+          if (nreg - (r + 1) <= LSD_QCAP) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pt) : "r"(qs + (((r + 1) & (LSD_QCAP - 1)) << 2)) : "memory");
+          else pt = __ldcg(&regpts[cursor + r + 1]);
           i1 = (int)pt + noff;
           pf1 = lsd_load_pix(&pix[i1]);
-          have1 = true;
         }
         if (r + 2 < nreg) {
-          const uint32_t pt = (nreg - (r + 2) <= LSD_QCAP) ? q[(r + 2) & (LSD_QCAP - 1)] : __ldcg(&regpts[cursor + r + 2]);
+          uint32_t pt;
+          if (nreg - (r + 2) <= LSD_QCAP) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pt) : "r"(qs + (((r + 2) & (LSD_QCAP - 1)) << 2)) : "memory");
+          else pt = __ldcg(&regpts[cursor + r + 2]);
           i2 = (int)pt + noff;
           pf2 = lsd_load_pix(&pix[i2]);
-          have2 = true;
         }
-        unsigned rem = __ballot_sync(0xFFFFFFFFu, lane < 9 && cur.a != LSD_NOTDEF_D);
+        unsigned rem = __ballot_sync(0xFFFFFFFFu, lane < 9 && cur.a != LSD_NOTDEF_F);
         while (rem) {
-          const bool al = ((rem >> lane) & 1u) && lsd_aligned_rad(cur.a, reg_angle, prec);
-          const unsigned m = __ballot_sync(0xFFFFFFFFu, al);
-          if (!m) break;
-          const int k = __ffs(m) - 1;
+          float d = fabsf(__fsub_rn(cur.a, th));
+          if (d > 180.f) d = __fsub_rn(360.f, d);
+          const bool mine = (rem >> lane) & 1u;
+          const unsigned mm = __ballot_sync(0xFFFFFFFFu, mine && d <= hi);  // aligned or undecided
+          if (!mm) break;                                                    // everything left is clearly not aligned
+          const int k = __ffs(mm) - 1;
+          const unsigned mi = __ballot_sync(0xFFFFFFFFu, mine && d < lo);   // certainly aligned
+          if (!((mi >> k) & 1u)) {  // the first candidate sits in the band
+            if (!fresh) {
+              th = lsd_fast_atan2(sumdy, sumdx);
+              inv0 = __fmul_rn(rsqrtf(__fadd_rn(__fmul_rn(sumdx, sumdx), __fmul_rn(sumdy, sumdy))), 1.02f);
+              margin = margin0;
+              lo = prec_deg - margin; hi = prec_deg + margin;
+              fresh = true;
+              continue;
+            }
+            const bool ex = lsd_aligned_rad((double)cur.a * LSD_DEG2RAD, (double)th * LSD_DEG2RAD, prec);
+            if (!((__ballot_sync(0xFFFFFFFFu, ex) >> k) & 1u)) {
+              rem &= ~((2u << k) - 1u);  // k rejected by the exact test; the cells before it were clearly not aligned
+              continue;
+            }
+          }
           rem &= ~((2u << k) - 1u);  // k and everything before it have been decided
           const int ai = __shfl_sync(0xFFFFFFFFu, ci, k);
           const float ck = __shfl_sync(0xFFFFFFFFu, cur.c, k), sk = __shfl_sync(0xFFFFFFFFu, cur.s, k);
+          const float dk = __shfl_sync(0xFFFFFFFFu, d, k);
           if (lane == 0) {
-            pix[ai].a = LSD_NOTDEF_D;
+            pix[ai].a = LSD_NOTDEF_F;
             regpts[cursor + nreg] = (uint32_t)ai;
-            q[nreg & (LSD_QCAP - 1)] = (uint32_t)ai;
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(qs + ((nreg & (LSD_QCAP - 1)) << 2)), "r"(ai) : "memory");
           }
           ++nreg;
-          if (i1 == ai) pf1.a = LSD_NOTDEF_D;  // prefetched copies of this cell are stale
-          if (i2 == ai) pf2.a = LSD_NOTDEF_D;
+          lsd_prefetch(&pix[min(max(ai + poff, pmin), pmax)]);
+          if (i1 == ai) pf1.a = LSD_NOTDEF_F;  // prefetched copies of this cell are stale
+          if (i2 == ai) pf2.a = LSD_NOTDEF_F;
           sumdx = __fadd_rn(sumdx, ck);
           sumdy = __fadd_rn(sumdy, sk);
-          reg_angle = (double)lsd_fast_atan2(sumdy, sumdx) * LSD_DEG2RAD;
+          margin = __fmaf_rn(fminf(__fadd_rn(dk, margin), dmax), inv0, margin);
+          lo = prec_deg - margin; hi = prec_deg + margin;
+          fresh = false;
         }
         __syncwarp();
       }
       if ((int)nreg >= min_reg_size) {
         if (nreg_out < max_regions) {
           if (lane == 0) {
+            // region angle handed to the rectangle fit: the seed's own angle for a 1-pixel region, else the angle of the sum
+            const double reg_angle = nreg == 1 ? th_seed : (double)(fresh ? th : lsd_fast_atan2(sumdy, sumdx)) * LSD_DEG2RAD;
             const unsigned long long bits = (unsigned long long)__double_as_longlong(reg_angle);
             regions[nreg_out] = make_uint4(cursor, nreg, (uint32_t)bits, (uint32_t)(bits >> 32));
           }
@@ -558,8 +617,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
       }
       pending &= ~((2u << src) - 1u);
       if (pending) {
-        a0 = (pending >> lane) & 1u ? __ldcg(&pix[seed].a) : LSD_NOTDEF_D;
-        pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF_D);
+        a0 = (pending >> lane) & 1u ? __ldcg(&pix[seed].a) : LSD_NOTDEF_F;
+        pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF_F);
       }
     }
   }
@@ -961,7 +1020,7 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   plf_keyline* kls = s->kls[par] + o * s->max_lines;
   plf_keyline* kls_all = s->kls_all[par] + o * s->max_regions;
   int* nlines = s->nlines[par] + o;
-  k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, s->min_reg_size, regpts, regions, s->max_regions,
+  k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts, regions, s->max_regions,
                                nregions, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grow");
