@@ -441,9 +441,16 @@ __device__ __forceinline__ bool lsd_aligned_rad(double a, double theta, double p
 
 // The warp that grows an image is the only reader and writer of that image's records while the kernel runs, and a CTA
 // never leaves its SM, so L1-cached loads (ld.ca) are coherent with the warp's own stores.
-__device__ __forceinline__ LsdPix lsd_load_pix(const LsdPix* p) {
-  const float4 raw = __ldca(reinterpret_cast<const float4*>(p));
-  return *reinterpret_cast<const LsdPix*>(&raw);
+// Two loads (8 + 4 bytes) rather than one 16-byte load: the 4th word of the record is never used, and ptxas recycled
+// the register it would land in (as a ballot result) while the load was still in flight - a write-after-write wait on
+// the load that cost a quarter of the kernel's time.
+struct LsdRec { float a, c, s; };
+__device__ __forceinline__ LsdRec lsd_load_pix(const LsdPix* p) {
+  const float2 ac = __ldca(reinterpret_cast<const float2*>(p));
+  LsdRec r;
+  r.a = ac.x; r.c = ac.y;
+  r.s = __ldca(&p->s);
+  return r;
 }
 __device__ __forceinline__ void lsd_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
@@ -524,11 +531,11 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
       uint32_t nreg = 1;
       // neighbourhood records of queue entries r+1 (pf1) and r+2 (pf2), fetched while earlier entries are processed;
       // a cell accepted meanwhile is patched to "used" in both prefetched copies (i < pmin: nothing fetched)
-      LsdPix pf1, pf2;
+      LsdRec pf1, pf2;
       pf1.a = pf2.a = LSD_NOTDEF_F; pf1.c = pf1.s = pf2.c = pf2.s = 0.f;
       int i1 = pmin - 1, i2 = pmin - 1;
       for (uint32_t r = 0; r < nreg; ++r) {
-        LsdPix cur;
+        LsdRec cur;
         int ci;
         if (i1 >= pmin) {
           cur = pf1;
