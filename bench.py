@@ -291,6 +291,10 @@ def main():
     dev_ms = e0.elapsed_time(e1)
     launches = fe.launches - l0
     clocks = sampler.stop()
+    try:   # device-clock timeline of the last two (overlapping) batches: [batch][E,G,M][start,end] in ms
+        timeline = [[[round(float(x), 2) for x in ph] for ph in b] for b in fe.debug_timeline()]
+    except Exception:
+        timeline = None
 
     # ---- `e2e`: pinned host buffers -> plf_batch_upload + run + download (+ the pose gather), K steps
     # (software-pipelined like a streaming caller: the H2D of batch i+1 is issued while batch i runs; every step still
@@ -359,7 +363,8 @@ def main():
                                 features_per_frame=stats, tracked_fraction=tracked),
                     e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=2 * B * w * h,
                              d2h_bytes_per_step=B * ctypes.sizeof(plf.plf_frame_result), ms_per_step=e2e_ms / args.steps),
-                    gpu_launches=int(launches), clocks=clocks, roofline=roof, pipeline_vs_hbm=whole, kernels=ktab)
+                    gpu_launches=int(launches), clocks=clocks, roofline=roof, pipeline_vs_hbm=whole,
+                    pipeline_timeline_ms=dict(phases=["E", "G", "M"], last_two_batches=timeline), kernels=ktab)
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = max(8, min(2 * cores, 64))

@@ -309,6 +309,11 @@ typedef struct plf_match_view {
 } plf_match_view;
 plf_status plf_get_matches(plf_ctx* ctx, int k, plf_match_view* view);
 
+/* Debug: device-clock timeline (ms) of the two most recent batches of the software pipeline: for each, the start/end of
+ * the E (extract), G (region growing) and M (match/track/pose) phases relative to the older batch's E start.
+ * No reference counterpart (the reference times whole calls with its Timer, app/plslam_dataset.cpp:126-132). */
+plf_status plf_debug_timeline(plf_ctx* ctx, float out[12]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -143,7 +143,7 @@ __device__ int fast_corner_score(const int* d /*16*/) {
 // region (3-px ring).  All index arithmetic is lane + 32*k / warp + 8*k (no div/mod), every lane is active in every pass.
 #define FN_OW 62
 #define FN_OH 30
-__global__ void __launch_bounds__(256, 6) k_fast_nms(const uint8_t* __restrict__ img0, size_t img0_stride,
+__global__ void __launch_bounds__(256, 5) k_fast_nms(const uint8_t* __restrict__ img0, size_t img0_stride,
                                                      const uint8_t* __restrict__ pyr, OrbGeom g, int l, int tiles_x,
                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_count,
                                                   int* __restrict__ hist, int* __restrict__ overflow) {
@@ -152,15 +152,21 @@ __global__ void __launch_bounds__(256, 6) k_fast_nms(const uint8_t* __restrict__
   const int img = blockIdx.y;
   const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride
                                 : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
-  __shared__ uint8_t px[38][72];   // pixel (x0 - 4 + rx, y0 - 4 + ry)
+  __shared__ __align__(16) uint8_t px[38][72];   // pixel (x0 - 4 + rx, y0 - 4 + ry)
   __shared__ uint8_t sc[32][64];   // score of pixel (x0 - 1 + sx, y0 - 1 + sy)
   __shared__ unsigned short clist[32 * 64];
   __shared__ int ccount;
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   if (tid == 0) ccount = 0;
-  for (int ry = wrp; ry < 38; ry += 8) {  // coordinates clamped: values outside the image are never used by a valid score
-    const uint8_t* row = src + (size_t)min(max(y0 - 4 + ry, 0), H - 1) * W;
-    for (int rx = lane; rx < 70; rx += 32) px[ry][rx] = row[min(max(x0 - 4 + rx, 0), W - 1)];
+  // Stage the tile four pixels at a time (plf_load4).  Rows are clamped to the image; positions outside the image hold
+  // arbitrary in-bounds data - they are never used by a valid score (gx in [3, W-3)).
+  {
+    const plf_span sp = plf_image_span(src, (size_t)W * H);
+    for (int i = tid; i < 38 * 18; i += 256) {
+      const int ry = i / 18, j = i - ry * 18;
+      const uint8_t* p = src + (size_t)min(max(y0 - 4 + ry, 0), H - 1) * W + (x0 - 4 + 4 * j);
+      reinterpret_cast<uint32_t*>(&px[ry][0])[j] = plf_load4(p, sp);
+    }
   }
   __syncthreads();
   const int th = g.fast_th;
@@ -474,10 +480,19 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const uint8_t* __restric
   uint8_t* dst = blur + (size_t)img * g.blur_stride + g.blur_off[l];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const bool interior = x0 >= 3 && x0 - 3 + RP <= W && y0 >= 3 && y0 + OBF_TH + 3 <= H;
-  for (int ry = wrp; ry < RH; ry += 8) {
-    const int gy = interior ? y0 - 3 + ry : orb_reflect101(y0 - 3 + ry, H);
-    const uint8_t* row = src + (size_t)gy * W;
-    for (int rx = lane; rx < RP; rx += 32) rawf[ry][rx] = (float)row[interior ? x0 - 3 + rx : orb_reflect101(x0 - 3 + rx, W)];
+  if (interior) {  // four pixels per step: one unaligned 32-bit read, four conversions, one 16-byte shared store
+    const plf_span sp = plf_image_span(src, (size_t)W * H);
+    for (int i = tid; i < RH * (RP / 4); i += 256) {
+      const int ry = i / (RP / 4), j = i - ry * (RP / 4);
+      const uint32_t v = plf_load4(src + (size_t)(y0 - 3 + ry) * W + (x0 - 3 + 4 * j), sp);
+      *reinterpret_cast<float4*>(&rawf[ry][4 * j]) =
+          make_float4((float)(v & 0xFFu), (float)((v >> 8) & 0xFFu), (float)((v >> 16) & 0xFFu), (float)(v >> 24));
+    }
+  } else {
+    for (int ry = wrp; ry < RH; ry += 8) {
+      const uint8_t* row = src + (size_t)orb_reflect101(y0 - 3 + ry, H) * W;
+      for (int rx = lane; rx < RP; rx += 32) rawf[ry][rx] = (float)row[orb_reflect101(x0 - 3 + rx, W)];
+    }
   }
   __syncthreads();
   const float k0 = c_blur7[0], k1 = c_blur7[1], k2 = c_blur7[2], k3 = c_blur7[3], k4 = c_blur7[4], k5 = c_blur7[5], k6 = c_blur7[6];

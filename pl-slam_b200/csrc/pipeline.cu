@@ -51,6 +51,7 @@ struct PipeState {
   // growing, latency-bound) -> M (LBD, stereo, tracking, pose).  Batch i+1's E phase overlaps batch i's G and M phases;
   // buffers that cross phases exist per batch parity.  Up to 2 batches may be in flight (run, run, download, ...).
   cudaEvent_t evE[2] = {nullptr, nullptr}, evG[2] = {nullptr, nullptr}, evM[2] = {nullptr, nullptr};
+  cudaEvent_t tE0[2] = {nullptr, nullptr}, tG0[2] = {nullptr, nullptr}, tM0[2] = {nullptr, nullptr};  // phase starts (timeline)
   long long seq = 0;            // batches issued
   int pend_par[2] = {0, 0}, pend_B[2] = {0, 0}, n_pending = 0;
   void* orb_kps_seen = nullptr;  // sub-system output pointers baked into the problem descriptors
@@ -78,6 +79,9 @@ extern "C" void plf_pipe_free(plf_ctx* ctx) {
     if (s->evE[i]) cudaEventDestroy(s->evE[i]);
     if (s->evG[i]) cudaEventDestroy(s->evG[i]);
     if (s->evM[i]) cudaEventDestroy(s->evM[i]);
+    if (s->tE0[i]) cudaEventDestroy(s->tE0[i]);
+    if (s->tG0[i]) cudaEventDestroy(s->tG0[i]);
+    if (s->tM0[i]) cudaEventDestroy(s->tM0[i]);
   }
   if (s->copy) { cudaStreamSynchronize(s->copy); cudaStreamDestroy(s->copy); }
   for (int i = 0; i < 2; ++i) {
@@ -392,9 +396,12 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   for (int i = 0; i < 2; ++i) {
     PLF_CUDA(ctx, cudaHostAlloc(&s->h_results[i], sizeof(plf_frame_result) * B, cudaHostAllocDefault));
     PLF_CUDA(ctx, cudaHostAlloc(&s->h_ovf[i], 2 * sizeof(int), cudaHostAllocDefault));
-    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evE[i], cudaEventDisableTiming));
-    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evG[i], cudaEventDisableTiming));
-    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evM[i], cudaEventDisableTiming));
+    PLF_CUDA(ctx, cudaEventCreate(&s->evE[i]));
+    PLF_CUDA(ctx, cudaEventCreate(&s->evG[i]));
+    PLF_CUDA(ctx, cudaEventCreate(&s->evM[i]));
+    PLF_CUDA(ctx, cudaEventCreate(&s->tE0[i]));
+    PLF_CUDA(ctx, cudaEventCreate(&s->tG0[i]));
+    PLF_CUDA(ctx, cudaEventCreate(&s->tM0[i]));
   }
   PLF_CUDA(ctx, cudaMemsetAsync(f.pt_count, 0, S * sizeof(int), ctx->stream));
   PLF_CUDA(ctx, cudaMemsetAsync(f.ls_count, 0, S * sizeof(int), ctx->stream));
@@ -548,6 +555,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->ev_up[run_slot], 0));  // images uploaded
   PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->evM[par], 0));         // batch i-2 (same parity) no longer reads these buffers
   plf_mark(ctx, "start");
+  PLF_CUDA(ctx, cudaEventRecord(s->tE0[par], sE));
   st = plf_orb_run(ctx, imgs, A, w, h, 2 * B, par);
   if (!st) st = plf_lsd_pre_range(ctx, imgs, A, w, h, par, 0, 2 * B);
   if (!st) st = plf_launch_blur5_sobel(ctx, imgs, w, A, w, h, 2 * B, s->lbd_grad[par], A);
@@ -559,6 +567,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   // ---- G phase: LSD region growing + rectangle fit + KeyLines (latency bound, one warp per image) ----
   ctx->cur = sG;
   PLF_CUDA(ctx, cudaStreamWaitEvent(sG, s->evE[par], 0));
+  PLF_CUDA(ctx, cudaEventRecord(s->tG0[par], sG));
   st = plf_lsd_grow_range(ctx, w, h, par, 0, 2 * B);
   if (st) { ctx->cur = sM; return st; }
   PLF_CUDA(ctx, cudaEventRecord(s->evG[par], sG));
@@ -567,6 +576,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   ctx->cur = sM;
   cudaStream_t cs = sM;
   PLF_CUDA(ctx, cudaStreamWaitEvent(sM, s->evG[par], 0));
+  PLF_CUDA(ctx, cudaEventRecord(s->tM0[par], sM));
   if (!s->has_prev) {  // initialize(): no previous frame to track against
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.pt_count, 0, sizeof(int), cs));
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.ls_count, 0, sizeof(int), cs));
@@ -632,6 +642,24 @@ plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out) {
     cudaMemsetAsync(plf_lsd_overflow_flag(ctx), 0, sizeof(int), ctx->stream);
     return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_batch_download: a fixed-capacity buffer overflowed (%s%s); raise plf_limits",
                     o0 ? "ORB keypoints " : "", o1 ? "LSD segments/lines" : "");
+  }
+  return PLF_OK;
+}
+
+// Timeline of the two most recent batches (device clock, ms): for parity p = 0,1 the start and end of the E, G and M
+// phases relative to the earlier of the two E starts.  Call with nothing in flight.
+plf_status plf_debug_timeline(plf_ctx* ctx, float out[12]) {
+  if (!ctx || !ctx->pipe || !out) return plf_fail(ctx, PLF_ERR_INVALID, "plf_debug_timeline: bad arguments");
+  PipeState* s = ctx->pipe;
+  if (s->n_pending) return plf_fail(ctx, PLF_ERR_STATE, "plf_debug_timeline: batches in flight");
+  if (s->seq < 2) return plf_fail(ctx, PLF_ERR_STATE, "plf_debug_timeline: needs two completed batches");
+  PLF_CUDA(ctx, cudaDeviceSynchronize());
+  const int p0 = (int)(s->seq & 1);  // parity of the older of the last two batches
+  cudaEvent_t ref = s->tE0[p0];
+  for (int k = 0; k < 2; ++k) {
+    const int p = k == 0 ? p0 : p0 ^ 1;
+    cudaEvent_t ev[6] = {s->tE0[p], s->evE[p], s->tG0[p], s->evG[p], s->tM0[p], s->evM[p]};
+    for (int j = 0; j < 6; ++j) PLF_CUDA(ctx, cudaEventElapsedTime(&out[k * 6 + j], ref, ev[j]));
   }
   return PLF_OK;
 }

@@ -148,3 +148,25 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
 void plf_lsd_outputs(plf_ctx* ctx, int par, plf_keyline** kls, int** nlines, int* max_lines);
 int* plf_orb_overflow_flag(plf_ctx* ctx);
 int* plf_lsd_overflow_flag(plf_ctx* ctx);
+
+#ifdef __CUDACC__
+// Four consecutive pixels starting at an arbitrary byte address, as two aligned 32-bit loads + a funnel shift (image
+// rows are not 4-byte aligned for odd widths).  Word addresses are clamped to [lo, hi] - the first and last aligned
+// words of the image itself - so a halo word that straddles the image's edge stays inside the allocation (the bytes
+// it then returns lie outside the image and are never used).
+struct plf_span { uintptr_t lo, hi; };
+__device__ __forceinline__ plf_span plf_image_span(const uint8_t* base, size_t bytes) {
+  plf_span s;
+  s.lo = (uintptr_t)base & ~(uintptr_t)3;
+  s.hi = ((uintptr_t)(base + bytes) - 4) & ~(uintptr_t)3;
+  return s;
+}
+__device__ __forceinline__ uint32_t plf_load4(const uint8_t* p, plf_span sp) {
+  const uintptr_t a = (uintptr_t)p & ~(uintptr_t)3;
+  const uintptr_t a0 = a < sp.lo ? sp.lo : (a > sp.hi ? sp.hi : a);
+  const uintptr_t b = a + 4;
+  const uintptr_t a1 = b < sp.lo ? sp.lo : (b > sp.hi ? sp.hi : b);
+  const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(a0)), w1 = __ldg(reinterpret_cast<const uint32_t*>(a1));
+  return __funnelshift_r(w0, w1, 8 * (int)((uintptr_t)p & 3));
+}
+#endif

@@ -340,6 +340,12 @@ class Frontend:
         self._check(st, "plf_debug_sincosf")
         return s, c
 
+    def debug_timeline(self):
+        """Device-clock start/end (ms) of the E, G, M phases of the two most recent batches: array [2, 3, 2]."""
+        out = np.zeros(12, np.float32)
+        self._check(self.lib.plf_debug_timeline(self._ctx, _ptr(out, C.c_float)), "plf_debug_timeline")
+        return out.reshape(2, 3, 2)
+
     # -- batched front-end -----------------------------------------------------------------------
     def reset_sequence(self):
         self._check(self.lib.plf_reset_sequence(self._ctx), "plf_reset_sequence")
