@@ -210,6 +210,7 @@ def main():
                     help="stereo pairs per step per GPU (~0.105 GB of HBM each; reduced automatically if it would not fit)")
     ap.add_argument("--pool", type=int, default=24, help="distinct rendered frames (ping-ponged to fill a batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--overlap-profile", action="store_true", help="also report per-kernel times with two batches in flight")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -320,6 +321,15 @@ def main():
     fe.batch_download_array(B)
     fe.profile_enable(False)
 
+    overlapped = None
+    if args.overlap_profile:   # same marks with the E/G/M pipeline left on: two batches in flight, second batch reported
+        fe.profile_enable(2)
+        fe.batch_run(B); fe.batch_run(B)
+        marks = fe.profile_read()
+        fe.batch_download_array(B); fe.batch_download_array(B)
+        fe.profile_enable(False)
+        overlapped = [(n, round(ms, 3)) for n, ms in marks]
+
     t = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -365,6 +375,8 @@ def main():
                              d2h_bytes_per_step=B * ctypes.sizeof(plf.plf_frame_result), ms_per_step=e2e_ms / args.steps),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, pipeline_vs_hbm=whole,
                     pipeline_timeline_ms=dict(phases=["E", "G", "M"], last_two_batches=timeline), kernels=ktab)
+        if overlapped:
+            line["kernels_overlapped"] = overlapped
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             n = max(8, min(2 * cores, 64))

@@ -40,7 +40,7 @@
 #define LSD_2PI (2 * LSD_PI)
 #define LSD_DEG2RAD (LSD_PI / 180)
 #define LSD_BINS_MAX 1024
-#define LSD_QCAP 1024  // shared-memory window of the region queue (entries)
+#define LSD_QCAP 256   // shared-memory window of the region queue (entries)
 
 struct LsdState {
   int w = 0, h = 0, nimg = 0;
@@ -1155,4 +1155,13 @@ extern "C" plf_status plf_debug_sincosf(plf_ctx* ctx, const float* in, float* s,
   PLF_CUDA(ctx, cudaMemcpyAsync(c, d + 2 * (size_t)n, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
   PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return PLF_OK;
+}
+
+// The region-growing kernel stays resident for tens of milliseconds while the next batch's extraction kernels are
+// co-scheduled on the same SMs.  The L1 / shared-memory split of an SM can only change while it is empty, so the split
+// this kernel is launched with is the one those kernels have to live with: ask for a large shared-memory carve-out
+// (164 KB) so that their CTAs (up to 17 KB of shared memory each) still fit at full occupancy.  Measured: k_orb_blur7 of
+// the overlapped batch 28 ms -> 7 ms, step 83.3 -> 81.9 ms.
+void plf_configure_lsd() {
+  cudaFuncSetAttribute((const void*)k_lsd_grow, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
 }

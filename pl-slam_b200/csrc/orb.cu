@@ -462,16 +462,16 @@ __global__ void __launch_bounds__(256) k_orb_blur7(const uint8_t* __restrict__ i
   }
 }
 
-// Fast variant of k_orb_blur7: 64x32 outputs per CTA; the tile is staged as float once (u8 -> f32 conversion hoisted out
-// of the tap loops), the row pass produces 4 adjacent outputs per thread from 10 floats (same k0*p0, fma(k1,p1,.) ...
+// Fast variant of k_orb_blur7: 64x32 outputs per CTA; the tile is staged as bytes (12 KB of shared memory per CTA in all, so 8 CTAs
+// fit beside co-resident kernels), the row pass produces 4 adjacent outputs per thread from 10 pixels (same k0*p0, fma(k1,p1,.) ...
 // order), the column pass slides down 8 rows.  Bit-identical to k_orb_blur7.
 #define OBF_TW 64
 #define OBF_TH 32
 __global__ void __launch_bounds__(256) k_orb_blur7_fast(const uint8_t* __restrict__ img0, size_t img0_stride,
                                                         const uint8_t* __restrict__ pyr, OrbGeom g,
                                                         uint8_t* __restrict__ blur, int l, int tiles_x) {
-  constexpr int RH = OBF_TH + 6, RP = 72;  // 70 floats needed per row, pitch 72 (16-byte aligned groups of 4)
-  __shared__ __align__(16) float rawf[RH][RP];
+  constexpr int RH = OBF_TH + 6, RP = 72;  // 70 pixels needed per row, pitch 72 (whole 32-bit words)
+  __shared__ __align__(16) uint8_t raw[RH][RP];
   __shared__ __align__(16) float hrow[RH][OBF_TW];
   const int W = g.w[l], H = g.h[l];
   const int x0 = (blockIdx.x % tiles_x) * OBF_TW, y0 = (blockIdx.x / tiles_x) * OBF_TH;
@@ -480,28 +480,27 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const uint8_t* __restric
   uint8_t* dst = blur + (size_t)img * g.blur_stride + g.blur_off[l];
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const bool interior = x0 >= 3 && x0 - 3 + RP <= W && y0 >= 3 && y0 + OBF_TH + 3 <= H;
-  if (interior) {  // four pixels per step: one unaligned 32-bit read, four conversions, one 16-byte shared store
+  if (interior) {  // four pixels per step (plf_load4)
     const plf_span sp = plf_image_span(src, (size_t)W * H);
     for (int i = tid; i < RH * (RP / 4); i += 256) {
       const int ry = i / (RP / 4), j = i - ry * (RP / 4);
-      const uint32_t v = plf_load4(src + (size_t)(y0 - 3 + ry) * W + (x0 - 3 + 4 * j), sp);
-      *reinterpret_cast<float4*>(&rawf[ry][4 * j]) =
-          make_float4((float)(v & 0xFFu), (float)((v >> 8) & 0xFFu), (float)((v >> 16) & 0xFFu), (float)(v >> 24));
+      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4(src + (size_t)(y0 - 3 + ry) * W + (x0 - 3 + 4 * j), sp);
     }
   } else {
     for (int ry = wrp; ry < RH; ry += 8) {
       const uint8_t* row = src + (size_t)orb_reflect101(y0 - 3 + ry, H) * W;
-      for (int rx = lane; rx < RP; rx += 32) rawf[ry][rx] = (float)row[orb_reflect101(x0 - 3 + rx, W)];
+      for (int rx = lane; rx < RP; rx += 32) raw[ry][rx] = row[orb_reflect101(x0 - 3 + rx, W)];
     }
   }
   __syncthreads();
   const float k0 = c_blur7[0], k1 = c_blur7[1], k2 = c_blur7[2], k3 = c_blur7[3], k4 = c_blur7[4], k5 = c_blur7[5], k6 = c_blur7[6];
   for (int it = tid; it < RH * (OBF_TW / 4); it += 256) {
     const int ry = it >> 4, j = it & 15;
-    const float4 pa = *reinterpret_cast<const float4*>(&rawf[ry][4 * j]);
-    const float4 pb = *reinterpret_cast<const float4*>(&rawf[ry][4 * j + 4]);
-    const float2 pc = *reinterpret_cast<const float2*>(&rawf[ry][4 * j + 8]);
-    const float p[10] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w, pc.x, pc.y};
+    const uint32_t* wp = reinterpret_cast<const uint32_t*>(&raw[ry][4 * j]);
+    const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+    const float p[10] = {(float)(w0 & 0xFFu), (float)((w0 >> 8) & 0xFFu), (float)((w0 >> 16) & 0xFFu), (float)(w0 >> 24),
+                         (float)(w1 & 0xFFu), (float)((w1 >> 8) & 0xFFu), (float)((w1 >> 16) & 0xFFu), (float)(w1 >> 24),
+                         (float)(w2 & 0xFFu), (float)((w2 >> 8) & 0xFFu)};
     float o[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {

@@ -543,7 +543,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   const uint8_t* imgs = s->imgs2[run_slot];
   s->imgs = s->imgs2[run_slot];
   // With profiling on everything is serialised on the main stream so that the per-kernel marks are meaningful.
-  const bool piped = !ctx->profile;
+  const bool piped = !ctx->profile || ctx->profile_piped;
   cudaStream_t sM = ctx->stream, sE = piped ? ctx->aux[0] : sM, sG = piped ? ctx->aux[1] : sM;
   plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
   plf_keyline* kls; int* lcnt; int ml;

@@ -2,6 +2,9 @@
 #include <stdarg.h>
 
 #include "plf_internal.h"
+#include <cstdlib>
+#include <cstdio>
+#include <cstring>
 
 static thread_local std::string g_create_err;
 
@@ -77,6 +80,7 @@ extern "C" {
 plf_status plf_profile_enable(plf_ctx* ctx, int on) {
   if (!ctx) return PLF_ERR_INVALID;
   ctx->profile = on != 0;
+  ctx->profile_piped = on == 2;
   ctx->prof_used = 0;
   return PLF_OK;
 }
@@ -85,7 +89,8 @@ plf_status plf_profile_enable(plf_ctx* ctx, int on) {
 // names_buf receives the stage names separated by ';'.  Resets the mark list.
 plf_status plf_profile_read(plf_ctx* ctx, char* names_buf, int buf_len, float* ms, int cap, int* n_out) {
   if (!ctx || !n_out) return PLF_ERR_INVALID;
-  PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->profile_piped) PLF_CUDA(ctx, cudaDeviceSynchronize());
+  else PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   int n = 0;
   std::string names;
   for (size_t i = 1; i < ctx->prof_used; ++i) {
@@ -201,6 +206,8 @@ plf_status plf_create(const plf_params* params, const plf_camera* cam, const plf
     delete ctx;
     return plf_fail(nullptr, PLF_ERR_INVALID, "plf_create: bad camera size or max_batch");
   }
+  plf_configure_lsd();
+  cudaGetLastError();
   e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete ctx;

@@ -47,6 +47,7 @@ struct plf_ctx {
   struct PipeState* pipe = nullptr;
   // optional per-stage timing (plf_profile_enable): events recorded after each kernel of plf_batch_run
   bool profile = false;
+  bool profile_piped = false;  // marks recorded while the E/G/M software pipeline stays enabled (durations under overlap)
   std::vector<cudaEvent_t> prof_ev;
   std::vector<std::string> prof_names;
   size_t prof_used = 0;
@@ -148,6 +149,8 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
 void plf_lsd_outputs(plf_ctx* ctx, int par, plf_keyline** kls, int** nlines, int* max_lines);
 int* plf_orb_overflow_flag(plf_ctx* ctx);
 int* plf_lsd_overflow_flag(plf_ctx* ctx);
+
+void plf_configure_lsd();
 
 #ifdef __CUDACC__
 // Four consecutive pixels starting at an arbitrary byte address, as two aligned 32-bit loads + a funnel shift (image

@@ -427,7 +427,7 @@ class Frontend:
 
     # -- profiling -------------------------------------------------------------------------------
     def profile_enable(self, on=True):
-        self._check(self.lib.plf_profile_enable(self._ctx, int(bool(on))), "plf_profile_enable")
+        self._check(self.lib.plf_profile_enable(self._ctx, int(on)), "plf_profile_enable")  # 2: keep the pipeline on
 
     def profile_read(self):
         """Returns [(stage name, ms)] of the batch_run calls since profiling was enabled / last read."""
