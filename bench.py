@@ -282,11 +282,14 @@ def main():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(ext):
         e0.record(ext)
-        fe.batch_run(B)                       # up to two batches in flight: extraction of batch i+1 overlaps the
-        for _ in range(args.steps - 1):       # latency-bound LSD region growing of batch i (streams E / G / M)
+        depth = min(3, args.steps)             # up to three batches in flight: extraction of batch i+2 / i+1 overlaps the
+        for _ in range(depth):                 # latency-bound LSD region growing and the match phase of batch i
             fe.batch_run(B)
+        for _ in range(args.steps - depth):
             fe.batch_download_array(B)
-        fe.batch_download_array(B)
+            fe.batch_run(B)
+        for _ in range(depth):
+            fe.batch_download_array(B)
         e1.record(ext)
     barrier()
     dev_ms = e0.elapsed_time(e1)
@@ -299,16 +302,17 @@ def main():
 
     # ---- `e2e`: pinned host buffers -> plf_batch_upload + run + download (+ the pose gather), K steps
     # (software-pipelined like a streaming caller: the H2D of batch i+1 is issued while batch i runs; every step still
-    #  uploads its own 2*B images and downloads its own B results inside the timed region)
+    #  uploads its own 2*B images and downloads its own B results inside the timed region; up to 3 batches in flight)
     barrier()
     t0 = time.perf_counter()
-    fe.batch_upload_raw(B, hostL.data_ptr(), hostR.data_ptr())
-    fe.batch_run(B)
-    for i in range(args.steps):
-        if i + 1 < args.steps:
+    issued = done = 0
+    while done < args.steps:
+        while issued < args.steps and issued - done < 3:
             fe.batch_upload_raw(B, hostL.data_ptr(), hostR.data_ptr())
             fe.batch_run(B)
+            issued += 1
         res = fe.batch_download_array(B)
+        done += 1
         gather_poses(res)
     barrier()
     e2e_s = time.perf_counter() - t0

@@ -35,25 +35,32 @@ struct PipeState {
   uint32_t* knn_keys = nullptr;   // [B][8][2][max_kp]
   int32_t* m12 = nullptr;         // [B][4][max_kp]  stereo pts, stereo lines, f2f pts, f2f lines
   int* mcount = nullptr;          // [B][4]
-  KnnProblem* knn_stereo[2] = {nullptr, nullptr};  // [parity][B*4]  (read the ORB / LBD outputs of that parity)
+  // match-phase copies of the extraction outputs (taken right after the LBD kernel, so that the extraction buffers of
+  // this parity are released to batch i+2 early): keypoints, ORB descriptors, KeyLines and their counts for 2B images
+  plf_keypoint* kpsM = nullptr; uint8_t* descM = nullptr; int* kcntM = nullptr;
+  plf_keyline* klsM = nullptr; int* lcntM = nullptr;
+  KnnProblem* knn_stereo = nullptr;  // [B*4]  (read descM / ldesc_raw)
   KnnProblem* knn_f2f = nullptr;     // [B*4]
-  NnrProblem* nnr_stereo[2] = {nullptr, nullptr};  // [parity][B*2]
+  NnrProblem* nnr_stereo = nullptr;  // [B*2]
   NnrProblem* nnr_f2f = nullptr;     // [B*2]
   // GN inputs / outputs
   double* gnP = nullptr; double* gnObs = nullptr; uint8_t* gnInlP = nullptr; int* gnNp = nullptr;
   double* gn_sP = nullptr; double* gn_eP = nullptr; double* gn_le = nullptr; uint8_t* gnInlL = nullptr; int* gnNl = nullptr;
   GnProblem* gn_probs = nullptr;
   plf_pose_result* gn_out = nullptr;
-  plf_frame_result* results[2] = {nullptr, nullptr};    // [parity][B] device
-  plf_frame_result* h_results[2] = {nullptr, nullptr};  // pinned host mirrors (filled at the end of the match phase)
-  int* h_ovf[2] = {nullptr, nullptr};                   // pinned overflow flags {orb, lsd} per parity
+  plf_frame_result* results = nullptr;                  // [B] device
+  plf_frame_result* h_results[3] = {nullptr, nullptr, nullptr};  // pinned host mirrors, ring of PIPE_DEPTH (filled at the end of M)
+  int* h_ovf[3] = {nullptr, nullptr, nullptr};                   // pinned overflow flags {orb, lsd}
   // Batches are software-pipelined over three streams: E (extract: ORB, LSD pre-grow, LBD prelude) -> G (LSD region
-  // growing, latency-bound) -> M (LBD, stereo, tracking, pose).  Batch i+1's E phase overlaps batch i's G and M phases;
-  // buffers that cross phases exist per batch parity.  Up to 2 batches may be in flight (run, run, download, ...).
-  cudaEvent_t evE[2] = {nullptr, nullptr}, evG[2] = {nullptr, nullptr}, evM[2] = {nullptr, nullptr};
-  cudaEvent_t tE0[2] = {nullptr, nullptr}, tG0[2] = {nullptr, nullptr}, tM0[2] = {nullptr, nullptr};  // phase starts (timeline)
+  // growing, latency-bound) -> M (LBD, stereo, tracking, pose).  Buffers that cross E -> G -> M exist per batch parity.
+  // M starts with the LBD kernel and a device copy of the (small) extraction outputs it still needs, then records evX:
+  // from there on batch i+2 may overwrite the parity's extraction buffers, so E(i+2) overlaps the rest of M(i) and
+  // G(i+1).  Up to PIPE_DEPTH = 3 batches may be in flight (run, run, run, download, ...).
+  cudaEvent_t evE[2] = {nullptr, nullptr}, evG[2] = {nullptr, nullptr}, evX[2] = {nullptr, nullptr};
+  cudaEvent_t evM[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t tE0[2] = {nullptr, nullptr}, tG0[2] = {nullptr, nullptr}, tM0[3] = {nullptr, nullptr, nullptr};  // phase starts (timeline)
   long long seq = 0;            // batches issued
-  int pend_par[2] = {0, 0}, pend_B[2] = {0, 0}, n_pending = 0;
+  int pend_slot[3] = {0, 0, 0}, pend_B[3] = {0, 0, 0}, n_pending = 0;
   void* orb_kps_seen = nullptr;  // sub-system output pointers baked into the problem descriptors
   void* lsd_kls_seen = nullptr;
   std::vector<void*> allocs;
@@ -73,15 +80,18 @@ extern "C" void plf_pipe_free(plf_ctx* ctx) {
   PipeState* s = ctx->pipe;
   if (!s) return;
   for (void* p : s->allocs) cudaFree(p);
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     if (s->h_results[i]) cudaFreeHost(s->h_results[i]);
     if (s->h_ovf[i]) cudaFreeHost(s->h_ovf[i]);
+    if (s->evM[i]) cudaEventDestroy(s->evM[i]);
+    if (s->tM0[i]) cudaEventDestroy(s->tM0[i]);
+  }
+  for (int i = 0; i < 2; ++i) {
     if (s->evE[i]) cudaEventDestroy(s->evE[i]);
     if (s->evG[i]) cudaEventDestroy(s->evG[i]);
-    if (s->evM[i]) cudaEventDestroy(s->evM[i]);
+    if (s->evX[i]) cudaEventDestroy(s->evX[i]);
     if (s->tE0[i]) cudaEventDestroy(s->tE0[i]);
     if (s->tG0[i]) cudaEventDestroy(s->tG0[i]);
-    if (s->tM0[i]) cudaEventDestroy(s->tM0[i]);
   }
   if (s->copy) { cudaStreamSynchronize(s->copy); cudaStreamDestroy(s->copy); }
   for (int i = 0; i < 2; ++i) {
@@ -387,21 +397,26 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PA(s->knn_keys, (size_t)B * 8 * 2 * K);
   PA(s->m12, (size_t)B * 4 * K);
   PA(s->mcount, (size_t)B * 4);
-  PA(s->knn_stereo[0], (size_t)B * 4); PA(s->knn_stereo[1], (size_t)B * 4); PA(s->knn_f2f, (size_t)B * 4);
-  PA(s->nnr_stereo[0], (size_t)B * 2); PA(s->nnr_stereo[1], (size_t)B * 2); PA(s->nnr_f2f, (size_t)B * 2);
+  PA(s->knn_stereo, (size_t)B * 4); PA(s->knn_f2f, (size_t)B * 4);
+  PA(s->nnr_stereo, (size_t)B * 2); PA(s->nnr_f2f, (size_t)B * 2);
+  PA(s->kpsM, 2 * (size_t)B * K); PA(s->descM, 2 * (size_t)B * K * 32); PA(s->kcntM, 2 * (size_t)B);
+  PA(s->klsM, 2 * (size_t)B * Ln); PA(s->lcntM, 2 * (size_t)B);
   PA(s->gnP, (size_t)B * K * 3); PA(s->gnObs, (size_t)B * K * 2); PA(s->gnInlP, (size_t)B * K); PA(s->gnNp, B);
   PA(s->gn_sP, (size_t)B * Ln * 3); PA(s->gn_eP, (size_t)B * Ln * 3); PA(s->gn_le, (size_t)B * Ln * 3); PA(s->gnInlL, (size_t)B * Ln); PA(s->gnNl, B);
-  PA(s->gn_probs, B); PA(s->gn_out, B); PA(s->results[0], B); PA(s->results[1], B);
+  PA(s->gn_probs, B); PA(s->gn_out, B); PA(s->results, B);
 #undef PA
-  for (int i = 0; i < 2; ++i) {
+  for (int i = 0; i < 3; ++i) {
     PLF_CUDA(ctx, cudaHostAlloc(&s->h_results[i], sizeof(plf_frame_result) * B, cudaHostAllocDefault));
     PLF_CUDA(ctx, cudaHostAlloc(&s->h_ovf[i], 2 * sizeof(int), cudaHostAllocDefault));
+    PLF_CUDA(ctx, cudaEventCreate(&s->evM[i]));
+    PLF_CUDA(ctx, cudaEventCreate(&s->tM0[i]));
+  }
+  for (int i = 0; i < 2; ++i) {
     PLF_CUDA(ctx, cudaEventCreate(&s->evE[i]));
     PLF_CUDA(ctx, cudaEventCreate(&s->evG[i]));
-    PLF_CUDA(ctx, cudaEventCreate(&s->evM[i]));
+    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evX[i], cudaEventDisableTiming));
     PLF_CUDA(ctx, cudaEventCreate(&s->tE0[i]));
     PLF_CUDA(ctx, cudaEventCreate(&s->tG0[i]));
-    PLF_CUDA(ctx, cudaEventCreate(&s->tM0[i]));
   }
   PLF_CUDA(ctx, cudaMemsetAsync(f.pt_count, 0, S * sizeof(int), ctx->stream));
   PLF_CUDA(ctx, cudaMemsetAsync(f.ls_count, 0, S * sizeof(int), ctx->stream));
@@ -413,15 +428,16 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   cudaStream_t cs = ctx->stream;
   std::vector<KnnProblem> kf(B * 4);
   std::vector<NnrProblem> nf(B * 2);
-  for (int par = 0; par < 2; ++par) {
-  plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
-  plf_orb_outputs(ctx, par, &kps, &odesc, &kcnt, &mk);
-  plf_keyline* kls; int* lcnt; int ml;
-  plf_lsd_outputs(ctx, par, &kls, &lcnt, &ml);
-  if (par == 0) {
-    s->orb_kps_seen = kps;
-    s->lsd_kls_seen = kls;
-  }
+  {
+  plf_keypoint* kps0; uint8_t* odesc0; int* kcnt0; int mk;
+  plf_orb_outputs(ctx, 0, &kps0, &odesc0, &kcnt0, &mk);
+  plf_keyline* kls0; int* lcnt0; int ml;
+  plf_lsd_outputs(ctx, 0, &kls0, &lcnt0, &ml);
+  s->orb_kps_seen = kps0;
+  s->lsd_kls_seen = kls0;
+  uint8_t* odesc = s->descM;
+  int* kcnt = s->kcntM;
+  int* lcnt = s->lcntM;
   std::vector<KnnProblem> ks(B * 4);
   std::vector<NnrProblem> ns(B * 2);
   for (int k = 0; k < B; ++k) {
@@ -452,10 +468,10 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
     nf[2 * k + 1] = {key(6, 0), key(6, 1), key(7, 0), key(7, 1), f.ls_count + k, f.ls_count + k + 1, 0, 0, P.min_ratio_12_l,
                      P.best_lr_matches ? 1 : 0, s->m12 + ((size_t)k * 4 + 3) * K, s->mcount + 4 * k + 3};
   }
-  PLF_CUDA(ctx, cudaMemcpyAsync(s->knn_stereo[par], ks.data(), ks.size() * sizeof(KnnProblem), cudaMemcpyHostToDevice, cs));
-  PLF_CUDA(ctx, cudaMemcpyAsync(s->nnr_stereo[par], ns.data(), ns.size() * sizeof(NnrProblem), cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->knn_stereo, ks.data(), ks.size() * sizeof(KnnProblem), cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->nnr_stereo, ns.data(), ns.size() * sizeof(NnrProblem), cudaMemcpyHostToDevice, cs));
   PLF_CUDA(ctx, cudaStreamSynchronize(cs));
-  }  // par
+  }
   std::vector<GnProblem> gp(B);
   for (int k = 0; k < B; ++k)
     gp[k] = {s->gnP + (size_t)k * K * 3, s->gnObs + (size_t)k * K * 2, s->gnInlP + (size_t)k * K, s->gnNp + k, 0,
@@ -506,11 +522,13 @@ plf_status plf_batch_upload(plf_ctx* ctx, int B, const uint8_t* left, const uint
   const int slot = s->up_slot ^ 1;
   uint8_t* dst = s->imgs2[slot];
   PLF_CUDA(ctx, cudaStreamWaitEvent(s->copy, s->ev_free[slot], 0));  // last run that read this slot has finished with it
-  for (int k = 0; k < B; ++k) {
-    if (stride == w) {
-      PLF_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)(2 * k) * A, left + k * hs, A, cudaMemcpyHostToDevice, s->copy));
-      PLF_CUDA(ctx, cudaMemcpyAsync(dst + (size_t)(2 * k + 1) * A, right + k * hs, A, cudaMemcpyHostToDevice, s->copy));
-    } else {
+  if (stride == w) {
+    // densely packed input: each image is one run of A bytes, so the whole side goes in ONE strided copy
+    // ("rows" = images, destination pitch 2A interleaves left and right)
+    PLF_CUDA(ctx, cudaMemcpy2DAsync(dst, 2 * A, left, A, A, B, cudaMemcpyHostToDevice, s->copy));
+    PLF_CUDA(ctx, cudaMemcpy2DAsync(dst + A, 2 * A, right, A, A, B, cudaMemcpyHostToDevice, s->copy));
+  } else {
+    for (int k = 0; k < B; ++k) {
       PLF_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)(2 * k) * A, w, left + k * hs, stride, w, h, cudaMemcpyHostToDevice, s->copy));
       PLF_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)(2 * k + 1) * A, w, right + k * hs, stride, w, h, cudaMemcpyHostToDevice, s->copy));
     }
@@ -533,12 +551,13 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   plf_status st = pipe_prepare(ctx, w, h);
   if (st) return st;
   PipeState* s = ctx->pipe;
-  if (s->n_pending >= 2)
-    return plf_fail(ctx, PLF_ERR_STATE, "plf_batch_run: two batches already in flight; call plf_batch_download first");
+  if (s->n_pending >= 3)
+    return plf_fail(ctx, PLF_ERR_STATE, "plf_batch_run: three batches already in flight; call plf_batch_download first");
   const size_t A = (size_t)w * h;
   const int K = s->max_kp, Ln = s->max_ln;
   const plf_params& P = ctx->params;
-  const int par = (int)(s->seq & 1);
+  const int par = (int)(s->seq & 1);   // parity of the E -> G -> M hand-off buffers
+  const int rp = (int)(s->seq % 3);    // slot of the result ring
   const int run_slot = s->up_slot;  // consume the most recently uploaded batch
   const uint8_t* imgs = s->imgs2[run_slot];
   s->imgs = s->imgs2[run_slot];
@@ -553,7 +572,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   // ---- E phase: ORB, LSD up to the seed ordering, LBD gradient prelude (all bandwidth / ALU bound) ----
   ctx->cur = sE;
   PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->ev_up[run_slot], 0));  // images uploaded
-  PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->evM[par], 0));         // batch i-2 (same parity) no longer reads these buffers
+  PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->evX[par], 0));         // batch i-2 (same parity) no longer reads these buffers
   plf_mark(ctx, "start");
   PLF_CUDA(ctx, cudaEventRecord(s->tE0[par], sE));
   st = plf_orb_run(ctx, imgs, A, w, h, 2 * B, par);
@@ -576,17 +595,26 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   ctx->cur = sM;
   cudaStream_t cs = sM;
   PLF_CUDA(ctx, cudaStreamWaitEvent(sM, s->evG[par], 0));
-  PLF_CUDA(ctx, cudaEventRecord(s->tM0[par], sM));
+  PLF_CUDA(ctx, cudaEventRecord(s->tM0[rp], sM));
   if (!s->has_prev) {  // initialize(): no previous frame to track against
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.pt_count, 0, sizeof(int), cs));
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.ls_count, 0, sizeof(int), cs));
   }
   if ((st = plf_launch_lbd(ctx, s->lbd_grad[par], A, w, h, 2 * B, kls, lcnt, Ln, s->ldesc_raw, nullptr))) return st;
   plf_mark(ctx, "lbd.k_lbd");
+  // the rest of the match phase works on its own copy of the extraction outputs; evX releases this parity to batch i+2
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->kpsM, kps, sizeof(plf_keypoint) * 2 * (size_t)B * K, cudaMemcpyDeviceToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->descM, odesc, 32 * 2 * (size_t)B * K, cudaMemcpyDeviceToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->kcntM, kcnt, sizeof(int) * 2 * (size_t)B, cudaMemcpyDeviceToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->klsM, kls, sizeof(plf_keyline) * 2 * (size_t)B * Ln, cudaMemcpyDeviceToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->lcntM, lcnt, sizeof(int) * 2 * (size_t)B, cudaMemcpyDeviceToDevice, cs));
+  PLF_CUDA(ctx, cudaEventRecord(s->evX[par], cs));
+  kps = s->kpsM; odesc = s->descM; kcnt = s->kcntM; kls = s->klsM; lcnt = s->lcntM;
+  plf_mark(ctx, "copy extraction outputs");
   PLF_CUDA(ctx, cudaMemsetAsync(s->mcount, 0, (size_t)B * 4 * sizeof(int), cs));
-  if ((st = plf_launch_knn2(ctx, s->knn_stereo[par], 4 * B, std::max(K, Ln)))) return st;
+  if ((st = plf_launch_knn2(ctx, s->knn_stereo, 4 * B, std::max(K, Ln)))) return st;
   plf_mark(ctx, "stereo.k_hamming_knn2");
-  if ((st = plf_launch_nnr(ctx, s->nnr_stereo[par], 2 * B, std::max(K, Ln)))) return st;
+  if ((st = plf_launch_nnr(ctx, s->nnr_stereo, 2 * B, std::max(K, Ln)))) return st;
   plf_mark(ctx, "stereo.k_nnr_mutual");
   StereoPrm sp = {P.max_dist_epip, P.min_disp, P.line_horiz_th, P.stereo_overlap_th, P.ls_min_disp_ratio,
                   ctx->cam.fx, ctx->cam.fy, ctx->cam.cx, ctx->cam.cy, ctx->cam.b};
@@ -605,17 +633,17 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   if ((st = plf_launch_gn(ctx, s->gn_probs, B, plf_gn_opts_from_params(P)))) return st;
   plf_mark(ctx, "gn.k_gn_pose");
   k_finalize<<<(B + 127) / 128, 128, 0, cs>>>(s->gn_out, s->gnNp, s->gnNl, kcnt, lcnt, s->fs, 1, P.min_features,
-                                               s->has_prev ? 0 : 1, B, s->results[par]);
+                                               s->has_prev ? 0 : 1, B, s->results);
   PLF_LAUNCH_CHECK(ctx);
   if ((st = copy_slot(ctx, s, B, 0))) return st;  // carry the last frame to the next batch
   plf_mark(ctx, "k_finalize+carry");
   // results + overflow flags to pinned memory as part of this batch's stream work; evM marks them ready
-  PLF_CUDA(ctx, cudaMemcpyAsync(s->h_results[par], s->results[par], sizeof(plf_frame_result) * B, cudaMemcpyDeviceToHost, cs));
-  PLF_CUDA(ctx, cudaMemcpyAsync(&s->h_ovf[par][0], plf_orb_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, cs));
-  PLF_CUDA(ctx, cudaMemcpyAsync(&s->h_ovf[par][1], plf_lsd_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, cs));
-  PLF_CUDA(ctx, cudaEventRecord(s->evM[par], cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->h_results[rp], s->results, sizeof(plf_frame_result) * B, cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&s->h_ovf[rp][0], plf_orb_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&s->h_ovf[rp][1], plf_lsd_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaEventRecord(s->evM[rp], cs));
   s->has_prev = true;
-  s->pend_par[s->n_pending] = par;
+  s->pend_slot[s->n_pending] = rp;
   s->pend_B[s->n_pending] = B;
   s->n_pending++;
   s->seq++;
@@ -628,12 +656,12 @@ plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out) {
     return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_download: bad arguments");
   PipeState* s = ctx->pipe;
   if (s->n_pending == 0) return plf_fail(ctx, PLF_ERR_STATE, "plf_batch_download: no batch in flight");
-  const int par = s->pend_par[0];
+  const int par = s->pend_slot[0];
   if (B != s->pend_B[0])
     return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_download: B=%d but the oldest batch in flight has %d pairs", B, s->pend_B[0]);
   PLF_CUDA(ctx, cudaEventSynchronize(s->evM[par]));
-  s->pend_par[0] = s->pend_par[1];
-  s->pend_B[0] = s->pend_B[1];
+  s->pend_slot[0] = s->pend_slot[1]; s->pend_slot[1] = s->pend_slot[2];
+  s->pend_B[0] = s->pend_B[1]; s->pend_B[1] = s->pend_B[2];
   s->n_pending--;
   memcpy(out, s->h_results[par], sizeof(plf_frame_result) * B);
   if (s->h_ovf[par][0] || s->h_ovf[par][1]) {
@@ -658,7 +686,8 @@ plf_status plf_debug_timeline(plf_ctx* ctx, float out[12]) {
   cudaEvent_t ref = s->tE0[p0];
   for (int k = 0; k < 2; ++k) {
     const int p = k == 0 ? p0 : p0 ^ 1;
-    cudaEvent_t ev[6] = {s->tE0[p], s->evE[p], s->tG0[p], s->evG[p], s->tM0[p], s->evM[p]};
+    const int r = (int)((s->seq - 2 + k) % 3);
+    cudaEvent_t ev[6] = {s->tE0[p], s->evE[p], s->tG0[p], s->evG[p], s->tM0[r], s->evM[r]};
     for (int j = 0; j < 6; ++j) PLF_CUDA(ctx, cudaEventElapsedTime(&out[k * 6 + j], ref, ev[j]));
   }
   return PLF_OK;

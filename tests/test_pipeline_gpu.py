@@ -89,34 +89,42 @@ def test_pipeline_reset_and_too_few_features(built):
         assert r[0]["status"] == 2
 
 
-def test_two_batches_in_flight_match_sequential(built):
-    """run, run, download, download (software-pipelined use) gives exactly the results of run/download pairs."""
+def test_batches_in_flight_match_sequential(built):
+    """run, run, (run,) download, ... (software-pipelined use, up to three batches in flight) gives exactly the results
+    of run/download pairs."""
     cam = dict(plf.KITTI_CAMERA, width=640, height=360, cx=320.0, cy=180.0, fx=500.0, fy=500.0)
     world = synth.World(seed=4, length=50.0, n_quads=160, n_segs=80, half_width=8.0, half_height=3.5)
-    frames = [(L, R) for L, R, _ in synth.stream(cam, 8, world=world, seed=11, step=0.15)]
+    frames = [(L, R) for L, R, _ in synth.stream(cam, 12, world=world, seed=11, step=0.15)]
     Ls = np.stack([f[0] for f in frames]); Rs = np.stack([f[1] for f in frames])
     lim = plf.default_limits(); lim.max_batch = 2
     with plf.Frontend(camera=cam, limits=lim, orb_nfeatures=700, lsd_nfeatures=150) as fe:
         seq = []
-        for s0 in range(0, 8, 2):
+        for s0 in range(0, 12, 2):
             seq += fe.process_batch(Ls[s0:s0 + 2], Rs[s0:s0 + 2])
-    with plf.Frontend(camera=cam, limits=lim, orb_nfeatures=700, lsd_nfeatures=150) as fe:
-        piped = []
-        fe.batch_upload(Ls[0:2], Rs[0:2]); fe.batch_run(2)
-        for s0 in range(2, 8, 2):
-            fe.batch_upload(Ls[s0:s0 + 2], Rs[s0:s0 + 2]); fe.batch_run(2)
-            piped += list(fe.batch_download_array(2))
-        piped += list(fe.batch_download_array(2))
-        with pytest.raises(plf.PlfError, match="no batch in flight"):
-            fe.batch_download(2)
-        fe.batch_upload(Ls[0:2], Rs[0:2]); fe.batch_run(2); fe.batch_run(2)
-        with pytest.raises(plf.PlfError, match="two batches already in flight"):
-            fe.batch_run(2)
-        fe.batch_download(2); fe.batch_download(2)
-    assert len(piped) == len(seq) == 8
-    for a, b in zip(seq, piped):
-        assert a["status"] == b["status"] and a["n_stereo_pt"] == b["n_stereo_pt"] and a["n_inliers_pt"] == b["n_inliers_pt"]
-        assert np.array_equal(a["DT"], b["DT"])          # same kernels, same inputs: bit-identical poses
+    for depth in (2, 3):
+        with plf.Frontend(camera=cam, limits=lim, orb_nfeatures=700, lsd_nfeatures=150) as fe:
+            piped = []
+            inflight = 0
+            for s0 in range(0, 12, 2):
+                fe.batch_upload(Ls[s0:s0 + 2], Rs[s0:s0 + 2]); fe.batch_run(2)
+                inflight += 1
+                if inflight == depth:
+                    piped += list(fe.batch_download_array(2))
+                    inflight -= 1
+            while inflight:
+                piped += list(fe.batch_download_array(2))
+                inflight -= 1
+            with pytest.raises(plf.PlfError, match="no batch in flight"):
+                fe.batch_download(2)
+            fe.batch_upload(Ls[0:2], Rs[0:2]); fe.batch_run(2); fe.batch_run(2); fe.batch_run(2)
+            with pytest.raises(plf.PlfError, match="three batches already in flight"):
+                fe.batch_run(2)
+            fe.batch_download(2); fe.batch_download(2); fe.batch_download(2)
+        assert len(piped) == len(seq) == 12
+        for a, b in zip(seq, piped):
+            assert a["status"] == b["status"] and a["n_stereo_pt"] == b["n_stereo_pt"] and a["n_inliers_pt"] == b["n_inliers_pt"]
+            assert a["n_stereo_ls"] == b["n_stereo_ls"] and a["n_inliers_ls"] == b["n_inliers_ls"]
+            assert np.array_equal(a["DT"], b["DT"])          # same kernels, same inputs: bit-identical poses
 
 
 def test_trajectory_ate_vs_oracle_and_ground_truth(built):
