@@ -206,8 +206,8 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLF_BENCH_BATCH", "768")),
-                    help="stereo pairs per step per GPU (~0.105 GB of HBM each; reduced automatically if it would not fit)")
+    ap.add_argument("--batch", type=int, default=int(os.environ.get("PLF_BENCH_BATCH", "1536")),
+                    help="stereo pairs per step per GPU (~0.06 GB of HBM each; reduced automatically if it would not fit)")
     ap.add_argument("--pool", type=int, default=24, help="distinct rendered frames (ping-ponged to fill a batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--overlap-profile", action="store_true", help="also report per-kernel times with two batches in flight")
@@ -232,7 +232,7 @@ def main():
 
     B = args.batch
     free_b, _tot = torch.cuda.mem_get_info()
-    fit = int((free_b * 0.85 - 4e9) / 0.105e9)       # every per-pair buffer exists for 2 batches in flight
+    fit = int((free_b * 0.85 - 4e9) / 0.062e9)       # LSD maps once, extraction outputs for 2 batch parities
     if B > fit:
         print(f"bench.py: batch {B} -> {max(fit, 8)} (free HBM {free_b / 1e9:.0f} GB)", file=sys.stderr)
         B = max(fit, 8)
@@ -270,6 +270,8 @@ def main():
         last = fe.process_batch(hostL.numpy(), hostR.numpy())
         gather_poses(last)
     barrier()
+    free_after, _tot = torch.cuda.mem_get_info(local_rank)
+    print(f"bench.py: HBM in use after warm-up {(_tot - free_after) / 1e9:.1f} GB ({(_tot - free_after) / 1e6 / B:.1f} MB per pair)", file=sys.stderr)
     stats = {k: float(np.mean([r[k] for r in last[1:]])) for k in ("n_kp_l", "n_lines_l", "n_stereo_pt", "n_stereo_ls", "n_matched_pt", "n_matched_ls", "n_inliers_pt", "n_inliers_ls")}
     tracked = float(np.mean([r["status"] == 0 for r in last[1:]]))
 

@@ -1043,6 +1043,7 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rects");
   const double min_length = (double)ctx->params.min_line_length * (double)std::min(w, h);
+  if (ctx->lsd_keylines_wait) PLF_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->lsd_keylines_wait, 0));
   k_keylines<<<n, 1024, 0, cs>>>(segs, nregions, s->max_regions, w, h, min_length, ctx->params.lsd_nfeatures, kls_all, kls,
                                  s->max_lines, nlines, s->overflow);
   PLF_LAUNCH_CHECK(ctx);

@@ -27,7 +27,7 @@ struct PipeState {
   uint8_t* imgs2[2] = {nullptr, nullptr};  // double-buffered [2B][h][w]: upload of batch i+1 overlaps the run of batch i
   int up_slot = 0;             // slot written by the last plf_batch_upload
   cudaStream_t copy = nullptr; // H2D stream
-  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_free2[2] = {nullptr, nullptr};
   short2* lbd_grad[2] = {nullptr, nullptr};  // [parity][2B][h*w]
   uint8_t* ldesc_raw = nullptr;  // [2B][max_ln][32]  LBD of every kept KeyLine
   FrameSlots fs;               // B+1 slots
@@ -97,6 +97,7 @@ extern "C" void plf_pipe_free(plf_ctx* ctx) {
   for (int i = 0; i < 2; ++i) {
     if (s->ev_up[i]) cudaEventDestroy(s->ev_up[i]);
     if (s->ev_free[i]) cudaEventDestroy(s->ev_free[i]);
+    if (s->ev_free2[i]) cudaEventDestroy(s->ev_free2[i]);
   }
   delete s;
   ctx->pipe = nullptr;
@@ -363,7 +364,7 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
     // a standalone operator call on another image size may have rebuilt the ORB / LSD state meanwhile
     plf_status st0;
     if ((st0 = plf_orb_prepare(ctx, w, h, 2 * s->B, true))) return st0;
-    if ((st0 = plf_lsd_prepare(ctx, w, h, 2 * s->B, true))) return st0;
+    if ((st0 = plf_lsd_prepare(ctx, w, h, 2 * s->B, false))) return st0;
     plf_keypoint* kps0; uint8_t* d0; int* c0; int m0;
     plf_orb_outputs(ctx, 0, &kps0, &d0, &c0, &m0);
     plf_keyline* kl0; int* lc0; int ml0;
@@ -386,6 +387,7 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   for (int i = 0; i < 2; ++i) {
     PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_up[i], cudaEventDisableTiming));
     PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_free[i], cudaEventDisableTiming));
+    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->ev_free2[i], cudaEventDisableTiming));
   }
   PA(s->lbd_grad[0], 2 * (size_t)B * A);
   PA(s->lbd_grad[1], 2 * (size_t)B * A);
@@ -422,7 +424,7 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PLF_CUDA(ctx, cudaMemsetAsync(f.ls_count, 0, S * sizeof(int), ctx->stream));
   // sub-systems sized for 2B images
   if ((st = plf_orb_prepare(ctx, w, h, 2 * B, true))) return st;
-  if ((st = plf_lsd_prepare(ctx, w, h, 2 * B, true))) return st;
+  if ((st = plf_lsd_prepare(ctx, w, h, 2 * B, false))) return st;
   // static problem descriptors (pointers never change; counts are read on the device)
   const plf_params& P = ctx->params;
   cudaStream_t cs = ctx->stream;
@@ -521,7 +523,8 @@ plf_status plf_batch_upload(plf_ctx* ctx, int B, const uint8_t* left, const uint
   // Device layout interleaves the pair: image 2k = left k, 2k+1 = right k.
   const int slot = s->up_slot ^ 1;
   uint8_t* dst = s->imgs2[slot];
-  PLF_CUDA(ctx, cudaStreamWaitEvent(s->copy, s->ev_free[slot], 0));  // last run that read this slot has finished with it
+  PLF_CUDA(ctx, cudaStreamWaitEvent(s->copy, s->ev_free[slot], 0));   // the last run that read this slot has finished with it
+  PLF_CUDA(ctx, cudaStreamWaitEvent(s->copy, s->ev_free2[slot], 0));  // (ORB / LBD prelude on one stream, LSD on another)
   if (stride == w) {
     // densely packed input: each image is one run of A bytes, so the whole side goes in ONE strided copy
     // ("rows" = images, destination pitch 2A interleaves left and right)
@@ -567,27 +570,35 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
   plf_keyline* kls; int* lcnt; int ml;
   plf_orb_outputs(ctx, par, &kps, &odesc, &kcnt, &mk);
-  plf_lsd_outputs(ctx, par, &kls, &lcnt, &ml);
+  plf_lsd_outputs(ctx, 0, &kls, &lcnt, &ml);
 
-  // ---- E phase: ORB, LSD up to the seed ordering, LBD gradient prelude (all bandwidth / ALU bound) ----
+  // ---- E phase: ORB + LBD gradient prelude (bandwidth / ALU bound); outputs per batch parity ----
   ctx->cur = sE;
   PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->ev_up[run_slot], 0));  // images uploaded
   PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->evX[par], 0));         // batch i-2 (same parity) no longer reads these buffers
   plf_mark(ctx, "start");
   PLF_CUDA(ctx, cudaEventRecord(s->tE0[par], sE));
   st = plf_orb_run(ctx, imgs, A, w, h, 2 * B, par);
-  if (!st) st = plf_lsd_pre_range(ctx, imgs, A, w, h, par, 0, 2 * B);
   if (!st) st = plf_launch_blur5_sobel(ctx, imgs, w, A, w, h, 2 * B, s->lbd_grad[par], A);
   if (st) { ctx->cur = sM; return st; }
   plf_mark(ctx, "lbd.k_blur5_sobel");
   PLF_CUDA(ctx, cudaEventRecord(s->evE[par], sE));
   PLF_CUDA(ctx, cudaEventRecord(s->ev_free[run_slot], sE));  // the image buffer may be overwritten by the next upload
 
-  // ---- G phase: LSD region growing + rectangle fit + KeyLines (latency bound, one warp per image) ----
+  // ---- G phase: the whole LSD chain on one stream - blur / resize / gradient / seed ordering, then region growing
+  // (latency bound, one warp per image), rectangle fit and KeyLines.  Its per-pixel maps exist ONCE (no batch parity:
+  // they are 2/3 of the pipeline's memory, and the batch size - the number of images the latency-bound growing kernel
+  // keeps in flight - is what they would cost), so LSD(i+1) starts when LSD(i) ends; ORB(i+1), ORB(i+2) and M(i) fill
+  // the SMs meanwhile. ----
   ctx->cur = sG;
-  PLF_CUDA(ctx, cudaStreamWaitEvent(sG, s->evE[par], 0));
+  PLF_CUDA(ctx, cudaStreamWaitEvent(sG, s->ev_up[run_slot], 0));
   PLF_CUDA(ctx, cudaEventRecord(s->tG0[par], sG));
-  st = plf_lsd_grow_range(ctx, w, h, par, 0, 2 * B);
+  st = plf_lsd_pre_range(ctx, imgs, A, w, h, 0, 0, 2 * B);
+  if (st) { ctx->cur = sM; return st; }
+  PLF_CUDA(ctx, cudaEventRecord(s->ev_free2[run_slot], sG));
+  ctx->lsd_keylines_wait = piped ? s->evX[par ^ 1] : nullptr;  // batch i-1's match phase has copied its KeyLines
+  st = plf_lsd_grow_range(ctx, w, h, 0, 0, 2 * B);
+  ctx->lsd_keylines_wait = nullptr;
   if (st) { ctx->cur = sM; return st; }
   PLF_CUDA(ctx, cudaEventRecord(s->evG[par], sG));
 
@@ -595,6 +606,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   ctx->cur = sM;
   cudaStream_t cs = sM;
   PLF_CUDA(ctx, cudaStreamWaitEvent(sM, s->evG[par], 0));
+  PLF_CUDA(ctx, cudaStreamWaitEvent(sM, s->evE[par], 0));
   PLF_CUDA(ctx, cudaEventRecord(s->tM0[rp], sM));
   if (!s->has_prev) {  // initialize(): no previous frame to track against
     PLF_CUDA(ctx, cudaMemsetAsync(s->fs.pt_count, 0, sizeof(int), cs));
