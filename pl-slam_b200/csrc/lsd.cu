@@ -55,6 +55,7 @@ struct LsdState {
   uint8_t* blur = nullptr;    // [nimg][h*w]
   uint8_t* scaled = nullptr;  // [nimg][hs*ws]
   short2* gxy[2] = {nullptr, nullptr};      // [nimg][hs*ws]
+  struct LsdPix* pix_raw[2] = {nullptr, nullptr};  // allocation (pix + look-ahead slack on both sides)
   struct LsdPix* pix[2] = {nullptr, nullptr};  // [nimg][guard + hs*ws]  {angle (deg, f32) | NOTDEF = undefined/used, cosf, sinf, pad}
   size_t pix_stride = 0;      // entries per image = guard (ws+1, permanently NOTDEF) + hs*ws
   int m2_min = 0;             // smallest gx^2+gy^2 whose gradient norm exceeds rho (defined pixel)
@@ -505,7 +506,9 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
   // look-ahead window fetched into L1/L2 whenever a pixel joins the region: 7 rows x 4 sectors around it (the cells the
   // next two breadth-first layers will examine), one address per lane
   const int poff = lane < 28 ? (lane / 4 - 3) * W + (lane % 4) * 2 - 3 : 0;
-  const int pmin = -(W + 1), pmax = (int)pix_stride - (W + 1) - 1;  // records of this image (guard included)
+  const int pmin = -(W + 1);  // first record of this image (the guard); smaller values mean "nothing fetched"
+  const char* const pb = reinterpret_cast<const char*>(pix);
+  const int l0 = lane == 0 ? 1 : 0;
   // ang_th close to 90 deg would break the "sum never shrinks" argument: fall back to evaluating every angle
   const float margin0 = prec_deg <= 60.f ? LSD_MARGIN0 : 1e30f;
   const float dmax = prec_deg + LSD_MARGIN0;
@@ -533,7 +536,7 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
         regpts[cursor] = sidx;
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(qs), "r"(sidx) : "memory");
       }
-      lsd_prefetch(&pix[min(max((int)sidx + poff, pmin), pmax)]);
+      lsd_prefetch(pb + (long long)((int)sidx + poff) * 16);
       __syncwarp();
       uint32_t nreg = 1;
       // neighbourhood records of queue entries r+1 (pf1) and r+2 (pf2), fetched while earlier entries are processed;
@@ -552,7 +555,8 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
           if (nreg - r <= LSD_QCAP) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pt) : "r"(qs + ((r & (LSD_QCAP - 1)) << 2)) : "memory");
           else pt = __ldcg(&regpts[cursor + r]);
           ci = (int)pt + noff;
-          cur = lsd_load_pix(&pix[ci]);
+          asm volatile("" : "+r"(ci));  // keep the index 32-bit: one IMAD.WIDE forms the address
+          cur = lsd_load_pix(reinterpret_cast<const LsdPix*>(pb + (long long)ci * 16));
         }
         pf1 = pf2; i1 = i2;
         i2 = pmin - 1;
@@ -561,14 +565,16 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
           if (nreg - (r + 1) <= LSD_QCAP) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pt) : "r"(qs + (((r + 1) & (LSD_QCAP - 1)) << 2)) : "memory");
           else pt = __ldcg(&regpts[cursor + r + 1]);
           i1 = (int)pt + noff;
-          pf1 = lsd_load_pix(&pix[i1]);
+          asm volatile("" : "+r"(i1));
+          pf1 = lsd_load_pix(reinterpret_cast<const LsdPix*>(pb + (long long)i1 * 16));
         }
         if (r + 2 < nreg) {
           uint32_t pt;
           if (nreg - (r + 2) <= LSD_QCAP) asm volatile("ld.shared.u32 %0, [%1];" : "=r"(pt) : "r"(qs + (((r + 2) & (LSD_QCAP - 1)) << 2)) : "memory");
           else pt = __ldcg(&regpts[cursor + r + 2]);
           i2 = (int)pt + noff;
-          pf2 = lsd_load_pix(&pix[i2]);
+          asm volatile("" : "+r"(i2));
+          pf2 = lsd_load_pix(reinterpret_cast<const LsdPix*>(pb + (long long)i2 * 16));
         }
         unsigned rem = __ballot_sync(0xFFFFFFFFu, lane < 9 && cur.a != LSD_NOTDEF_F);
         while (rem) {
@@ -588,7 +594,9 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
               fresh = true;
               continue;
             }
-            const bool ex = lsd_aligned_rad((double)cur.a * LSD_DEG2RAD, (double)th * LSD_DEG2RAD, prec);
+            float av = cur.a;
+            asm volatile("" : "+f"(av));  // the f64 form of the angle is only needed here: keep it out of the hot loop
+            const bool ex = lsd_aligned_rad((double)av * LSD_DEG2RAD, (double)th * LSD_DEG2RAD, prec);
             if (!((__ballot_sync(0xFFFFFFFFu, ex) >> k) & 1u)) {
               rem &= ~((2u << k) - 1u);  // k rejected by the exact test; the cells before it were clearly not aligned
               continue;
@@ -598,13 +606,15 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
           const int ai = __shfl_sync(0xFFFFFFFFu, ci, k);
           const float ck = __shfl_sync(0xFFFFFFFFu, cur.c, k), sk = __shfl_sync(0xFFFFFFFFu, cur.s, k);
           const float dk = __shfl_sync(0xFFFFFFFFu, d, k);
-          if (lane == 0) {
-            pix[ai].a = LSD_NOTDEF_F;
-            regpts[cursor + nreg] = (uint32_t)ai;
-            asm volatile("st.shared.u32 [%0], %1;" ::"r"(qs + ((nreg & (LSD_QCAP - 1)) << 2)), "r"(ai) : "memory");
-          }
+          // lane 0 marks the cell used and appends it to the region / the queue (predicated: no divergent branch)
+          asm volatile(
+              "{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %0, 0;\n\t"
+              "@p st.global.f32 [%1], %2;\n\t@p st.global.u32 [%3], %4;\n\t@p st.shared.u32 [%5], %4;\n\t}"
+              ::"r"(l0), "l"(pb + (long long)ai * 16), "f"(LSD_NOTDEF_F), "l"(regpts + (cursor + nreg)), "r"(ai),
+                "r"(qs + ((nreg & (LSD_QCAP - 1)) << 2))
+              : "memory");
           ++nreg;
-          lsd_prefetch(&pix[min(max(ai + poff, pmin), pmax)]);
+          lsd_prefetch(pb + (long long)(ai + poff) * 16);
           if (i1 == ai) pf1.a = LSD_NOTDEF_F;  // prefetched copies of this cell are stale
           if (i2 == ai) pf2.a = LSD_NOTDEF_F;
           sumdx = __fadd_rn(sumdx, ck);
@@ -827,7 +837,7 @@ __global__ void __launch_bounds__(1024) k_keylines(const float4* __restrict__ se
 // ---- host side -------------------------------------------------------------------------------------------------
 static void lsd_release(LsdState* s) {
   for (int p = 0; p < 2; ++p) {
-    cudaFree(s->gxy[p]); cudaFree(s->pix[p]); cudaFree(s->order[p]); cudaFree(s->nseeds[p]);
+    cudaFree(s->gxy[p]); cudaFree(s->pix_raw[p]); cudaFree(s->order[p]); cudaFree(s->nseeds[p]);
     cudaFree(s->regpts[p]); cudaFree(s->regions[p]); cudaFree(s->nregions[p]); cudaFree(s->segs[p]); cudaFree(s->kls[p]);
     cudaFree(s->kls_all[p]); cudaFree(s->nlines[p]);
   }
@@ -922,7 +932,10 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   // batch i+1 can be extracted while batch i is still growing regions; standalone operators use parity 0 only
   for (int p = 0; p < (s->two_parities ? 2 : 1); ++p) {
     PLF_CUDA(ctx, cudaMalloc(&s->gxy[p], As * N * sizeof(short2)));
-    PLF_CUDA(ctx, cudaMalloc(&s->pix[p], s->pix_stride * N * sizeof(LsdPix)));
+    // 3 rows + 8 records of slack on both sides: the growing kernel's look-ahead prefetches need no clamping
+    const size_t pad = 3 * (size_t)s->ws + 8;
+    PLF_CUDA(ctx, cudaMalloc(&s->pix_raw[p], (s->pix_stride * N + 2 * pad) * sizeof(LsdPix)));
+    s->pix[p] = s->pix_raw[p] + pad;
     k_lsd_fill_guard<<<(int)(((size_t)(s->ws + 1) * N + 255) / 256), 256, 0, ctx->stream>>>(s->pix[p], s->pix_stride, s->ws + 1, (int)N);
     PLF_LAUNCH_CHECK(ctx);
     PLF_CUDA(ctx, cudaMalloc(&s->nseeds[p], N * sizeof(int)));
