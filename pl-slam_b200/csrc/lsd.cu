@@ -55,6 +55,7 @@ struct LsdState {
   uint8_t* blur = nullptr;    // [nimg][h*w]
   uint8_t* scaled = nullptr;  // [nimg][hs*ws]
   short2* gxy[2] = {nullptr, nullptr};      // [nimg][hs*ws]
+  uint32_t* rect_perm = nullptr;  // [nimg][max_regions] regions in size-class order (k_lsd_rect_order)
   struct LsdPix* pix_raw[2] = {nullptr, nullptr};  // allocation (pix + look-ahead slack on both sides)
   struct LsdPix* pix[2] = {nullptr, nullptr};  // [nimg][guard + hs*ws]  {angle (deg, f32) | NOTDEF = undefined/used, cosf, sinf, pad}
   size_t pix_stride = 0;      // entries per image = guard (ws+1, permanently NOTDEF) + hs*ws
@@ -658,13 +659,38 @@ __device__ __forceinline__ double lsd_angle_diff(double a, double b) {
   return diff;
 }
 
+// The rectangle fit runs one THREAD per region (three sequential f64 passes over its points, in the reference's
+// order), so a warp takes as long as its largest region; region sizes span 17 .. several thousand pixels in detection
+// order.  k_lsd_rect_order permutes each image's regions into power-of-two size classes, largest first, so that the 32
+// regions of a warp have similar lengths (outputs stay indexed by the original region number).
+#define LSD_SIZE_BINS 20
+__global__ void __launch_bounds__(256) k_lsd_rect_order(const uint4* __restrict__ regions_all, int max_regions,
+                                                        const int* __restrict__ nregions, uint32_t* __restrict__ perm_all) {
+  __shared__ int cnt[LSD_SIZE_BINS], pos[LSD_SIZE_BINS];
+  const int im = blockIdx.x, n = min(nregions[im], max_regions);
+  const uint4* regions = regions_all + (size_t)im * max_regions;
+  uint32_t* perm = perm_all + (size_t)im * max_regions;
+  if (threadIdx.x < LSD_SIZE_BINS) cnt[threadIdx.x] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) atomicAdd(&cnt[min(31 - __clz((int)regions[i].y | 1), LSD_SIZE_BINS - 1)], 1);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int b = LSD_SIZE_BINS - 1; b >= 0; --b) { pos[b] = run; run += cnt[b]; }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256)
+    perm[atomicAdd(&pos[min(31 - __clz((int)regions[i].y | 1), LSD_SIZE_BINS - 1)], 1)] = (uint32_t)i;
+}
+
 __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gxy_all, size_t stride, int W,
                                                    const uint32_t* __restrict__ regpts_all,
                                                    const uint4* __restrict__ regions_all, int max_regions,
-                                                   const int* __restrict__ nregions, double prec, double scale,
-                                                   float4* __restrict__ segs_all) {
-  const int im = blockIdx.y, ri = blockIdx.x * 128 + threadIdx.x;
-  if (ri >= nregions[im]) return;
+                                                   const int* __restrict__ nregions, const uint32_t* __restrict__ perm_all,
+                                                   double prec, double scale, float4* __restrict__ segs_all) {
+  const int im = blockIdx.y, slot = blockIdx.x * 128 + threadIdx.x;
+  if (slot >= nregions[im]) return;
+  const int ri = (int)perm_all[(size_t)im * max_regions + slot];
   const uint4 R = regions_all[(size_t)im * max_regions + ri];
   const uint32_t* pts = regpts_all + (size_t)im * stride + R.x;
   const short2* gxy = gxy_all + (size_t)im * stride;
@@ -841,7 +867,7 @@ static void lsd_release(LsdState* s) {
     cudaFree(s->regpts[p]); cudaFree(s->regions[p]); cudaFree(s->nregions[p]); cudaFree(s->segs[p]); cudaFree(s->kls[p]);
     cudaFree(s->kls_all[p]); cudaFree(s->nlines[p]);
   }
-  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap);
+  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap); cudaFree(s->rect_perm);
   cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->overflow); cudaFree(s->rs_tab);
   cudaFree(s->grad_lut);
 }
@@ -922,9 +948,10 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   s->pix_stride = As + (size_t)s->ws + 1;
   for (s->m2_min = 0; s->m2_min <= 2 * 510 * 510; ++s->m2_min)  // same double expression as the kernels
     if (!(sqrt((double)s->m2_min / 4.0) <= s->rho)) break;
-  PLF_CUDA(ctx, cudaMalloc(&s->blur, A * N));
-  PLF_CUDA(ctx, cudaMalloc(&s->scaled, As * N));
+  PLF_CUDA(ctx, cudaMalloc(&s->blur, A * N + 64));      // + slack: plf_load4 may read the aligned word that holds the
+  PLF_CUDA(ctx, cudaMalloc(&s->scaled, As * N + 64));   // last byte of the last image
   PLF_CUDA(ctx, cudaMalloc(&s->binmap, As * N * sizeof(uint16_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->rect_perm, N * s->max_regions * sizeof(uint32_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->maxmag2, N * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->rowcnt, N * ((s->hs + LSD_CHUNK - 1) / LSD_CHUNK) * s->n_bins * sizeof(uint32_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->binstart, N * s->n_bins * sizeof(uint32_t)));
@@ -1051,8 +1078,11 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
                                nregions, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grow");
+  uint32_t* perm = s->rect_perm + o * s->max_regions;
+  k_lsd_rect_order<<<n, 256, 0, cs>>>(regions, s->max_regions, nregions, perm);
+  PLF_LAUNCH_CHECK(ctx);
   k_lsd_rects<<<dim3((s->max_regions + 127) / 128, n), 128, 0, cs>>>(gxy, As, W, regpts, regions, s->max_regions, nregions,
-                                                                     s->prec, s->scale, segs);
+                                                                     perm, s->prec, s->scale, segs);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rects");
   const double min_length = (double)ctx->params.min_line_length * (double)std::min(w, h);

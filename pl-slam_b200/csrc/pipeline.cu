@@ -69,7 +69,7 @@ struct PipeState {
 template <typename T>
 static plf_status pipe_alloc(plf_ctx* ctx, PipeState* s, T** p, size_t n) {
   void* q = nullptr;
-  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 256));
+  cudaError_t e = cudaMalloc(&q, std::max<size_t>(n * sizeof(T), 256) + 64);  // + slack for plf_load4 (see plf_image_span)
   if (e != cudaSuccess) return plf_fail(ctx, PLF_ERR_CUDA, "pipeline cudaMalloc(%zu): %s", n * sizeof(T), cudaGetErrorString(e));
   *p = (T*)q;
   s->allocs.push_back(q);

@@ -32,7 +32,7 @@ void* plf_scratch(plf_ctx* ctx, int slot, size_t bytes) {
   }
   size_t want = bytes < 4096 ? 4096 : bytes;
   want = (want + 255) & ~size_t(255);
-  cudaError_t e = cudaMalloc(&b.p, want);
+  cudaError_t e = cudaMalloc(&b.p, want + 64);  // + slack for plf_load4 (see plf_image_span)
   if (e != cudaSuccess) {
     plf_fail(ctx, PLF_ERR_CUDA, "cudaMalloc(%zu) scratch slot %d: %s", want, slot,
              cudaGetErrorString(e));

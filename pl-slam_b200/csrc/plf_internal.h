@@ -155,14 +155,15 @@ void plf_configure_lsd();
 
 #ifdef __CUDACC__
 // Four consecutive pixels starting at an arbitrary byte address, as two aligned 32-bit loads + a funnel shift (image
-// rows are not 4-byte aligned for odd widths).  Word addresses are clamped to [lo, hi] - the first and last aligned
-// words of the image itself - so a halo word that straddles the image's edge stays inside the allocation (the bytes
-// it then returns lie outside the image and are never used).
+// rows are not 4-byte aligned for odd widths).  Word addresses are clamped to [lo, hi] - the aligned words that hold
+// the first and the last byte of the image - so a halo word beyond the image's edge stays inside the allocation (the
+// bytes it then returns lie outside the image and are never used).  The word at hi may extend up to 3 bytes past the
+// image: every image buffer is allocated with 64 bytes of slack for that.
 struct plf_span { uintptr_t lo, hi; };
 __device__ __forceinline__ plf_span plf_image_span(const uint8_t* base, size_t bytes) {
   plf_span s;
   s.lo = (uintptr_t)base & ~(uintptr_t)3;
-  s.hi = ((uintptr_t)(base + bytes) - 4) & ~(uintptr_t)3;
+  s.hi = ((uintptr_t)(base + bytes) - 1) & ~(uintptr_t)3;
   return s;
 }
 __device__ __forceinline__ uint32_t plf_load4(const uint8_t* p, plf_span sp) {
