@@ -210,7 +210,7 @@ def main():
                     help="stereo pairs per step per GPU (~0.06 GB of HBM each; reduced automatically if it would not fit)")
     ap.add_argument("--pool", type=int, default=24, help="distinct rendered frames (ping-ponged to fill a batch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--overlap-profile", action="store_true", help="also report per-kernel times with two batches in flight")
+    ap.add_argument("--overlap-profile", action="store_true", help="also report per-kernel times measured with two batches in flight (overlapped)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -282,8 +282,12 @@ plf_status plf_reset_sequence(plf_ctx* ctx);
 plf_status plf_process_batch(plf_ctx* ctx, int B, const uint8_t* left, const uint8_t* right, int stride,
                              plf_frame_result* out);
 
-/* The three phases of plf_process_batch, for callers that keep images resident in HBM:
- * upload (H2D) -> run (all kernels, asynchronous on plf_stream) -> download (D2H of the B results + sync). */
+/* The three phases of plf_process_batch, for streaming callers and callers that keep images resident in HBM:
+ * upload (asynchronous H2D into the image slot the GPU is not reading) -> run (all kernels, asynchronous; consumes the
+ * most recent upload) -> download (waits for the OLDEST batch in flight and returns its B results).
+ * Batches are software-pipelined on the device: up to THREE may be in flight (run, run, run, download, run, ...);
+ * a fourth plf_batch_run returns PLF_ERR_STATE.  Results are identical to run/download pairs.  plf_get_frame /
+ * plf_get_matches refer to the batch most recently RUN, so call them with a single batch in flight. */
 plf_status plf_batch_upload(plf_ctx* ctx, int B, const uint8_t* left, const uint8_t* right, int stride);
 plf_status plf_batch_run(plf_ctx* ctx, int B);
 plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out);
