@@ -212,7 +212,7 @@ plf_status plf_launch_blur5_sobel(plf_ctx* ctx, const uint8_t* imgs, int pitch, 
 }
 
 // One CTA per (image, line slot).  kls: [nimg][max_lines]; counts: [nimg]; desc: [nimg][max_lines][32].
-__global__ void __launch_bounds__(64) k_lbd(const short2* __restrict__ grad, size_t grad_stride, int w,
+__global__ void __launch_bounds__(64, 12) k_lbd(const short2* __restrict__ grad, size_t grad_stride, int w,
                                             int h, const plf_keyline* __restrict__ kls,
                                             const int* __restrict__ counts, int max_lines,
                                             uint8_t* __restrict__ desc, float* __restrict__ desc_f) {

@@ -37,8 +37,9 @@ __global__ void __launch_bounds__(KNN_THREADS) k_hamming_knn2(const KnnProblem* 
   const int qi = q0 + (threadIdx.x / KNN_SPLIT);
   const bool active = qi < nq;
   uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+  const int row = active ? (P.qlist ? P.qlist[qi] : qi) : 0;
   if (active) {
-    const uint4* qp = reinterpret_cast<const uint4*>(P.q) + 2 * (size_t)qi;
+    const uint4* qp = reinterpret_cast<const uint4*>(P.q) + 2 * (size_t)row;
     qa = qp[0];
     qb = qp[1];
   }
@@ -67,8 +68,8 @@ __global__ void __launch_bounds__(KNN_THREADS) k_hamming_knn2(const KnnProblem* 
     best = nb;
   }
   if (active && sub == 0) {
-    P.best[qi] = best;
-    P.second[qi] = second;
+    P.best[row] = best;
+    P.second[row] = second;
   }
 }
 
@@ -107,6 +108,31 @@ __global__ void __launch_bounds__(256) k_nnr_mutual(const NnrProblem* __restrict
   if (i < n1) P.matches12[i] = m;
   const unsigned ball = __ballot_sync(0xFFFFFFFFu, m >= 0);
   if ((threadIdx.x & 31) == 0 && ball && P.count) atomicAdd(P.count, __popc(ball));
+}
+
+// The mutual check of k_nnr_mutual reads the reverse 2-NN only at rows that are the accepted best match of some query;
+// this kernel lists those rows (each once, any order) so the reverse kNN runs on them alone.
+__global__ void __launch_bounds__(256) k_nnr_mark(const NnrProblem* __restrict__ probs, int* __restrict__ flags,
+                                                  int* __restrict__ qlist, int* __restrict__ qcount, int stride) {
+  const NnrProblem P = probs[blockIdx.y];
+  const int n1 = P.n1_ptr ? *P.n1_ptr : P.n1;
+  const int n2 = P.n2_ptr ? *P.n2_ptr : P.n2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n1 || n2 <= 0 || !P.best_lr) return;
+  const uint32_t b = P.best12[i], s = P.second12[i];
+  if (!nnr_accept(b, s, P.nnr)) return;
+  const int m = (int)(b & 0xFFFFu);
+  if (atomicExch(&flags[(size_t)blockIdx.y * stride + m], 1) == 0)
+    qlist[(size_t)blockIdx.y * stride + atomicAdd(&qcount[blockIdx.y], 1)] = m;
+}
+
+plf_status plf_launch_nnr_mark(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, int max_n1, int* flags, int* qlist,
+                               int* qcount, int stride) {
+  if (nprob <= 0 || max_n1 <= 0) return PLF_OK;
+  dim3 grid((max_n1 + 255) / 256, nprob);
+  k_nnr_mark<<<grid, 256, 0, ctx->cur>>>(d_probs, flags, qlist, qcount, stride);
+  PLF_LAUNCH_CHECK(ctx);
+  return PLF_OK;
 }
 
 plf_status plf_launch_nnr(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, int max_n1) {

@@ -39,7 +39,8 @@ struct PipeState {
   // this parity are released to batch i+2 early): keypoints, ORB descriptors, KeyLines and their counts for 2B images
   plf_keypoint* kpsM = nullptr; uint8_t* descM = nullptr; int* kcntM = nullptr;
   plf_keyline* klsM = nullptr; int* lcntM = nullptr;
-  KnnProblem* knn_stereo = nullptr;  // [B*4]  (read descM / ldesc_raw)
+  KnnProblem* knn_stereo = nullptr;  // [B*4]: [0,2B) forward L->R (points, lines per pair), [2B,4B) reverse R->L on listed rows
+  int* rev_flags = nullptr; int* rev_list = nullptr; int* rev_count = nullptr;  // [2B][max_kp], [2B][max_kp], [2B]
   KnnProblem* knn_f2f = nullptr;     // [B*4]
   NnrProblem* nnr_stereo = nullptr;  // [B*2]
   NnrProblem* nnr_f2f = nullptr;     // [B*2]
@@ -401,6 +402,7 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PA(s->mcount, (size_t)B * 4);
   PA(s->knn_stereo, (size_t)B * 4); PA(s->knn_f2f, (size_t)B * 4);
   PA(s->nnr_stereo, (size_t)B * 2); PA(s->nnr_f2f, (size_t)B * 2);
+  PA(s->rev_flags, 2 * (size_t)B * K); PA(s->rev_list, 2 * (size_t)B * K); PA(s->rev_count, 2 * (size_t)B);
   PA(s->kpsM, 2 * (size_t)B * K); PA(s->descM, 2 * (size_t)B * K * 32); PA(s->kcntM, 2 * (size_t)B);
   PA(s->klsM, 2 * (size_t)B * Ln); PA(s->lcntM, 2 * (size_t)B);
   PA(s->gnP, (size_t)B * K * 3); PA(s->gnObs, (size_t)B * K * 2); PA(s->gnInlP, (size_t)B * K); PA(s->gnNp, B);
@@ -448,10 +450,11 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
     const uint32_t* dr = (const uint32_t*)(odesc + (size_t)(2 * k + 1) * K * 32);
     const uint32_t* ll = (const uint32_t*)(s->ldesc_raw + (size_t)(2 * k) * Ln * 32);
     const uint32_t* lr = (const uint32_t*)(s->ldesc_raw + (size_t)(2 * k + 1) * Ln * 32);
-    ks[4 * k + 0] = {dl, dr, kcnt + 2 * k, kcnt + 2 * k + 1, 0, 0, key(0, 0), key(0, 1)};
-    ks[4 * k + 1] = {dr, dl, kcnt + 2 * k + 1, kcnt + 2 * k, 0, 0, key(1, 0), key(1, 1)};
-    ks[4 * k + 2] = {ll, lr, lcnt + 2 * k, lcnt + 2 * k + 1, 0, 0, key(2, 0), key(2, 1)};
-    ks[4 * k + 3] = {lr, ll, lcnt + 2 * k + 1, lcnt + 2 * k, 0, 0, key(3, 0), key(3, 1)};
+    // forward problems (all left rows), then reverse problems restricted to the right rows the mutual check will read
+    ks[2 * k + 0] = {dl, dr, kcnt + 2 * k, kcnt + 2 * k + 1, 0, 0, key(0, 0), key(0, 1), nullptr};
+    ks[2 * k + 1] = {ll, lr, lcnt + 2 * k, lcnt + 2 * k + 1, 0, 0, key(2, 0), key(2, 1), nullptr};
+    ks[2 * B + 2 * k + 0] = {dr, dl, s->rev_count + 2 * k, kcnt + 2 * k, 0, 0, key(1, 0), key(1, 1), s->rev_list + (size_t)(2 * k) * K};
+    ks[2 * B + 2 * k + 1] = {lr, ll, s->rev_count + 2 * k + 1, lcnt + 2 * k, 0, 0, key(3, 0), key(3, 1), s->rev_list + (size_t)(2 * k + 1) * K};
     ns[2 * k + 0] = {key(0, 0), key(0, 1), key(1, 0), key(1, 1), kcnt + 2 * k, kcnt + 2 * k + 1, 0, 0, P.min_ratio_12_p,
                      P.best_lr_matches ? 1 : 0, s->m12 + ((size_t)k * 4 + 0) * K, s->mcount + 4 * k + 0};
     ns[2 * k + 1] = {key(2, 0), key(2, 1), key(3, 0), key(3, 1), lcnt + 2 * k, lcnt + 2 * k + 1, 0, 0, P.min_ratio_12_l,
@@ -624,7 +627,15 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   kps = s->kpsM; odesc = s->descM; kcnt = s->kcntM; kls = s->klsM; lcnt = s->lcntM;
   plf_mark(ctx, "copy extraction outputs");
   PLF_CUDA(ctx, cudaMemsetAsync(s->mcount, 0, (size_t)B * 4 * sizeof(int), cs));
-  if ((st = plf_launch_knn2(ctx, s->knn_stereo, 4 * B, std::max(K, Ln)))) return st;
+  // L->R 2-NN for every left feature; R->L only for the right features that are somebody's accepted best match
+  // (k_nnr_mutual reads nothing else of the reverse direction): the same matches for ~2/3 of the popcounts
+  if ((st = plf_launch_knn2(ctx, s->knn_stereo, 2 * B, std::max(K, Ln)))) return st;
+  if (P.best_lr_matches) {
+    PLF_CUDA(ctx, cudaMemsetAsync(s->rev_flags, 0, 2 * (size_t)B * K * sizeof(int), cs));
+    PLF_CUDA(ctx, cudaMemsetAsync(s->rev_count, 0, 2 * (size_t)B * sizeof(int), cs));
+    if ((st = plf_launch_nnr_mark(ctx, s->nnr_stereo, 2 * B, std::max(K, Ln), s->rev_flags, s->rev_list, s->rev_count, K))) return st;
+    if ((st = plf_launch_knn2(ctx, s->knn_stereo + 2 * B, 2 * B, std::max(K, Ln)))) return st;
+  }
   plf_mark(ctx, "stereo.k_hamming_knn2");
   if ((st = plf_launch_nnr(ctx, s->nnr_stereo, 2 * B, std::max(K, Ln)))) return st;
   plf_mark(ctx, "stereo.k_nnr_mutual");

@@ -89,6 +89,7 @@ struct KnnProblem {
   int nq, nt;
   uint32_t* best;    // [nq] packed (dist << 16 | idx), 0xFFFFFFFF if none
   uint32_t* second;  // [nq]
+  const int* qlist;  // optional: the query rows to process (nq / *nq_ptr = its length); results stored at best[row]
 };
 // Launches the kNN kernel over `nprob` problems (device array), max_nq = upper bound of nq.
 plf_status plf_launch_knn2(plf_ctx* ctx, const KnnProblem* d_probs, int nprob, int max_nq);
@@ -107,6 +108,10 @@ struct NnrProblem {
   int* count;          // device counter (accumulated with atomicAdd; caller zeroes)
 };
 plf_status plf_launch_nnr(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, int max_n1);
+// Marks, per problem, the train rows that are the NNR-accepted best match of some query: the only rows whose reverse
+// 2-NN the mutual-consistency check will read.  flags/qlist: [nprob][stride] (flags zeroed by the caller), qcount: [nprob].
+plf_status plf_launch_nnr_mark(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, int max_n1, int* flags, int* qlist,
+                               int* qcount, int stride);
 
 // ---- LBD (lbd.cu) ------------------------------------------------------------------------------
 plf_status plf_launch_blur5_sobel(plf_ctx* ctx, const uint8_t* imgs, int pitch, size_t img_stride,
