@@ -126,6 +126,16 @@ plf_status plf_hamming_knn2(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8
 plf_status plf_match(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2, int n2, float nnr,
                      int best_lr, int32_t* matches_12, int* n_matches);
 
+/* Landmark descriptor maintenance, batched.  Replaces the body of MapPoint::updateAverageDescDir and
+ * MapLine::updateAverageDescDir (src/mapFeatures.cpp:51-93, 121-163), called on every observation add (:48, :118).
+ * desc: the observed descriptors of all landmarks, concatenated, [offsets[n_landmarks]][32] (host); landmark l owns
+ * rows offsets[l] .. offsets[l+1]-1 (2 .. 64 of them); dirs: the matching observation directions [.][3] f64, or NULL.
+ * med_idx[l] = index WITHIN landmark l of the descriptor the reference would copy into med_desc (smallest element at
+ * position int(1 + 0.5 (n-1)) of its sorted distance row, first on ties); med_dir[l] = mean direction (sum in
+ * observation order / n; the reference's accumulator is uninitialised, :88-90 - zero here, deliberately). */
+plf_status plf_median_descriptors(plf_ctx* ctx, const uint8_t* desc, const int* offsets, const double* dirs,
+                                  int n_landmarks, int* med_idx, double* med_dir);
+
 /* ------------------------------------------------------------------------------------------------
  * Point features
  * ---------------------------------------------------------------------------------------------- */

@@ -234,3 +234,99 @@ extern "C" plf_status plf_match(plf_ctx* ctx, const uint8_t* d1, int n1, const u
   if (n_matches) *n_matches = hcount;
   return PLF_OK;
 }
+
+// ---- landmark descriptor maintenance ---------------------------------------------------------
+// MapPoint::updateAverageDescDir / MapLine::updateAverageDescDir (src/mapFeatures.cpp:51-93, 121-163): among the n
+// descriptors observed for a landmark, the representative is the one whose sorted row of Hamming distances to all of
+// them (its own 0 included) has the smallest element at position int(1 + 0.5 (n - 1)); ties keep the first.  The mean
+// observation direction is the plain f64 sum in observation order divided by n (the reference accumulates into an
+// uninitialised Vector3d, :88-90 / :158-160 - started from zero here, deliberately).
+// One warp per landmark.  Distances d(i,j) (<= 256) go to shared memory; the k-th smallest of row i is found by rank
+// counting under the (value, column) order, which is what std::sort's result looks like position-wise.
+#define MED_MAX_OBS 64
+__global__ void __launch_bounds__(128) k_median_desc(const uint32_t* __restrict__ desc, const int* __restrict__ offsets,
+                                                     const double* __restrict__ dirs, int n_landmarks,
+                                                     int* __restrict__ med_idx, double* __restrict__ med_dir) {
+  __shared__ unsigned short dist[4][MED_MAX_OBS][MED_MAX_OBS + 1];
+  const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = blockIdx.x * 4 + wrp;
+  if (L >= n_landmarks) return;
+  const int o = offsets[L], n = offsets[L + 1] - o;
+  if (n <= 0 || n > MED_MAX_OBS) {
+    if (lane == 0) med_idx[L] = n <= 0 ? -1 : -2;  // -2: more observations than one warp pass handles
+    return;
+  }
+  unsigned short (*D)[MED_MAX_OBS + 1] = dist[wrp];
+  const uint4* dp = reinterpret_cast<const uint4*>(desc) + 2 * (size_t)o;
+  for (int pr = lane; pr < n * n; pr += 32) {
+    const int i = pr / n, j = pr - i * n;
+    const uint4 a0 = dp[2 * i], a1 = dp[2 * i + 1], b0 = dp[2 * j], b1 = dp[2 * j + 1];
+    D[i][j] = (unsigned short)hamming256(a0, a1, b0, b1);
+  }
+  __syncwarp();
+  const int k = (int)(1 + 0.5 * (n - 1));  // position read by the reference; k <= n - 1 for n >= 2
+  unsigned best = 0xFFFFFFFFu;             // (median << 16 | row): smallest median, first row on ties
+  for (int i = lane; i < n; i += 32) {
+    int med = 0;
+    if (k < n) {
+      for (int j = 0; j < n; ++j) {
+        const int v = D[i][j];
+        int rank = 0;
+        for (int m = 0; m < n; ++m) {
+          const int u = D[i][m];
+          rank += (u < v || (u == v && m < j)) ? 1 : 0;
+        }
+        if (rank == k) med = v;
+      }
+    }
+    best = min(best, ((unsigned)med << 16) | (unsigned)i);
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) best = min(best, __shfl_xor_sync(0xFFFFFFFFu, best, off));
+  if (lane == 0) {
+    med_idx[L] = (int)(best & 0xFFFFu);
+    if (dirs && med_dir) {
+      double sx = 0.0, sy = 0.0, sz = 0.0;
+      for (int i = 0; i < n; ++i) {
+        sx += dirs[3 * (size_t)(o + i)]; sy += dirs[3 * (size_t)(o + i) + 1]; sz += dirs[3 * (size_t)(o + i) + 2];
+      }
+      med_dir[3 * (size_t)L] = sx / n; med_dir[3 * (size_t)L + 1] = sy / n; med_dir[3 * (size_t)L + 2] = sz / n;
+    }
+  }
+}
+
+extern "C" plf_status plf_median_descriptors(plf_ctx* ctx, const uint8_t* desc, const int* offsets, const double* dirs,
+                                             int n_landmarks, int* med_idx, double* med_dir) {
+  if (!ctx) return PLF_ERR_INVALID;
+  if (n_landmarks < 0 || (n_landmarks > 0 && (!desc || !offsets || !med_idx)))
+    return plf_fail(ctx, PLF_ERR_INVALID, "plf_median_descriptors: bad arguments");
+  if (n_landmarks == 0) return PLF_OK;
+  const int total = offsets[n_landmarks];
+  if (offsets[0] != 0 || total < 0) return plf_fail(ctx, PLF_ERR_INVALID, "plf_median_descriptors: offsets must start at 0 and be non-decreasing");
+  for (int l = 0; l < n_landmarks; ++l) {
+    const int n = offsets[l + 1] - offsets[l];
+    if (n < 0) return plf_fail(ctx, PLF_ERR_INVALID, "plf_median_descriptors: offsets must be non-decreasing");
+    if (n == 1) return plf_fail(ctx, PLF_ERR_INVALID, "plf_median_descriptors: landmark %d has one observation (the reference reads past its row, src/mapFeatures.cpp:76; a landmark's first observation sets med_desc directly, :25-38)", l);
+    if (n > MED_MAX_OBS) return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_median_descriptors: landmark %d has %d observations (max %d)", l, n, MED_MAX_OBS);
+  }
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  const size_t bd = align256((size_t)total * 32), bo = align256((size_t)(n_landmarks + 1) * 4),
+               br = align256((size_t)total * 24), bi = align256((size_t)n_landmarks * 4), bm = align256((size_t)n_landmarks * 24);
+  uint8_t* base = (uint8_t*)plf_scratch(ctx, 0, bd + bo + br + bi + bm);
+  if (!base) return PLF_ERR_CUDA;
+  uint8_t* dd = base; int* dofs = (int*)(base + bd); double* ddir = (double*)(base + bd + bo);
+  int* didx = (int*)(base + bd + bo + br); double* dmed = (double*)(base + bd + bo + br + bi);
+  cudaStream_t cs = ctx->stream;
+  if (total > 0) PLF_CUDA(ctx, cudaMemcpyAsync(dd, desc, (size_t)total * 32, cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(dofs, offsets, (size_t)(n_landmarks + 1) * 4, cudaMemcpyHostToDevice, cs));
+  const bool want_dir = dirs && med_dir;
+  if (want_dir && total > 0) PLF_CUDA(ctx, cudaMemcpyAsync(ddir, dirs, (size_t)total * 24, cudaMemcpyHostToDevice, cs));
+  ctx->cur = cs;
+  k_median_desc<<<(n_landmarks + 3) / 4, 128, 0, cs>>>((const uint32_t*)dd, dofs, want_dir ? ddir : nullptr, n_landmarks, didx,
+                                                       want_dir ? dmed : nullptr);
+  PLF_LAUNCH_CHECK(ctx);
+  PLF_CUDA(ctx, cudaMemcpyAsync(med_idx, didx, (size_t)n_landmarks * 4, cudaMemcpyDeviceToHost, cs));
+  if (want_dir) PLF_CUDA(ctx, cudaMemcpyAsync(med_dir, dmed, (size_t)n_landmarks * 24, cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaStreamSynchronize(cs));
+  return PLF_OK;
+}

@@ -236,6 +236,23 @@ class Frontend:
         self._check(st, "plf_match")
         return m, cnt.value
 
+    def median_descriptors(self, desc, offsets, dirs=None):
+        """MapPoint/MapLine::updateAverageDescDir over many landmarks: (med_idx int32[L], med_dir f64[L,3] or None)."""
+        desc = _u8(desc).reshape(-1, DESC_BYTES)
+        offsets = np.ascontiguousarray(offsets, np.int32)
+        L = len(offsets) - 1
+        idx = np.full(max(L, 0), -1, np.int32)
+        md = None
+        dp = None
+        if dirs is not None:
+            dirs = np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+            md = np.zeros((max(L, 0), 3), np.float64)
+            dp = _ptr(dirs, C.c_double)
+        st = self.lib.plf_median_descriptors(self._ctx, _ptr(desc, C.c_uint8), _ptr(offsets, C.c_int), dp, L,
+                                             _ptr(idx, C.c_int), _ptr(md, C.c_double) if md is not None else None)
+        self._check(st, "plf_median_descriptors")
+        return idx, md
+
     # -- line descriptor -------------------------------------------------------------------------
     def lbd_gradients(self, img):
         """BinaryDescriptor::computeSobel: returns (dx, dy) int16 of the 5x5-blurred image."""

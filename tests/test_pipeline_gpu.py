@@ -76,6 +76,32 @@ def test_pipeline_euroc_shape_stream(built):
     compare(ref, got, feats)
 
 
+def corridor_world(n_segs=450, seed=3):
+    """Lines-dominant scene: long low-contrast 3-D segments running along the corridor (few crossings, ends mostly
+    outside the view), no textured quads."""
+    world = synth.World(seed=21, length=90.0, n_quads=0, n_segs=0)
+    rng = np.random.default_rng(seed)
+    segs = []
+    for _ in range(n_segs):
+        x = rng.choice([-1, 1]) * rng.uniform(1.0, 12.0); y = rng.uniform(-4, 4)
+        z0 = rng.uniform(1.0, 30.0); z1 = z0 + rng.uniform(15, 60)
+        g = float(90 + rng.choice([-1, 1]) * rng.uniform(24, 32))
+        segs.append((np.array([x, y, z0]), np.array([x + rng.normal(0, 0.05), y + rng.normal(0, 0.05), z1]), g, int(rng.integers(2, 4))))
+    world.segs = segs
+    return world
+
+
+def test_pipeline_low_texture_stream(built):
+    """BASELINE config 5 shape: lines-dominant frames (< 200 ORB keypoints kept, > 400 LSD lines with
+    lsd_nfeatures = 0 = keep all) - stresses LBD and the line rows of the pose Jacobian."""
+    cam = plf.KITTI_CAMERA
+    frames = list(synth.stream(cam, 3, world=corridor_world(), seed=17, noise=2))
+    ref, got, feats = run_both(cam, frames, 3, orb_nfeatures=150, lsd_nfeatures=0)
+    assert all(g["n_kp_l"] < 200 for g in got) and all(g["n_lines_l"] > 400 for g in got)
+    assert got[1]["status"] == 0 and got[1]["n_inliers_ls"] > got[1]["n_inliers_pt"]
+    compare(ref, got, feats)
+
+
 def test_pipeline_reset_and_too_few_features(built):
     cam = dict(plf.KITTI_CAMERA, width=320, height=200, cx=160.0, cy=100.0)
     lim = plf.default_limits(); lim.max_batch = 2
