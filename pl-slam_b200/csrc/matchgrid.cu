@@ -1,0 +1,217 @@
+// Windowed greedy matcher: stvo-pl `matchGrid` (points and lines overloads) over a `GridStructure`, as pl-slam calls it
+// at src/mapHandler.cpp:251-271 (points), :382-418 (lines), :580-591, :686-706.
+//
+// stvo-pl is not on disk: the semantics restate SURVEY Appendix A.3 and the published sources from memory (see
+// oracle/matchgrid.py for the full statement; "parity unpinned").  Candidates are visited in ascending index order
+// (stvo-pl iterates a std::unordered_set, whose order is implementation-defined and only matters for ties).
+//
+// The reference loop is sequential over the queries: with best_lr_matches a candidate i2 counts for query i1 only if
+// d(i1,i2) beats the smallest distance any EARLIER query achieved on i2.  That is an exclusive prefix-minimum down each
+// column of the (query x train) candidate matrix, so the work splits into
+//   k_mg_columns : one thread per train feature walks the queries in order, evaluates the candidate predicate (window
+//                  test; for lines, Bresenham cells within the window of each other + direction gate), computes the
+//                  Hamming distance of the candidates and writes d or "not considered" to a dense u16 matrix;
+//   k_mg_rows    : one thread per query scans its row in ascending train index with the reference's strict '<' updates,
+//                  applies the f32 ratio test and records matches_12; matches_21 comes from the column pass;
+//   k_mg_mutual  : drops i1 unless matches_21[matches_12[i1]] == i1, counts the matches.
+#include "plf_internal.h"
+
+#define MG_NONE 0xFFFFu
+
+struct MgGrid { int cols, rows, w_lo, w_hi, h_lo, h_hi; };
+
+__device__ __forceinline__ int mg_hamming(const uint4* a, const uint4* b) {
+  const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
+  return __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+         __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+}
+
+// GridStructure::get window around cell (cx, cy), clipped to the grid: is cell (x, y) - already known to be inside the
+// grid - returned?
+__device__ __forceinline__ bool mg_in_window(const MgGrid& g, int cx, int cy, int x, int y) {
+  return x >= max(0, cx - g.w_lo) && x < min(g.cols, cx + g.w_hi + 1) && y >= max(0, cy - g.h_lo) &&
+         y < min(g.rows, cy + g.h_hi + 1);
+}
+
+// 8-connected Bresenham walk over the cells of (x1,y1)-(x2,y2), end points included (used as a set).
+struct MgLine {
+  bool steep; int x, x_end, y, dx, dy, err, ystep;
+  __device__ void start(int x1, int y1, int x2, int y2) {
+    steep = abs(y2 - y1) > abs(x2 - x1);
+    if (steep) { int t = x1; x1 = y1; y1 = t; t = x2; x2 = y2; y2 = t; }
+    if (x1 > x2) { int t = x1; x1 = x2; x2 = t; t = y1; y1 = y2; y2 = t; }
+    dx = x2 - x1; dy = abs(y2 - y1); err = dx / 2; ystep = y1 < y2 ? 1 : -1; y = y1; x = x1; x_end = x2;
+  }
+  __device__ bool next(int* cx, int* cy) {
+    if (x > x_end) return false;
+    *cx = steep ? y : x; *cy = steep ? x : y;
+    err -= dy;
+    if (err < 0) { y += ystep; err += dx; }
+    ++x;
+    return true;
+  }
+};
+
+// lines: is some registered (in-grid) cell of train line t inside the window of some cell of query line q?
+__device__ bool mg_lines_near(const MgGrid& g, const int* q, const int* t) {
+  MgLine lq; lq.start(q[0], q[1], q[2], q[3]);
+  int cx, cy;
+  while (lq.next(&cx, &cy)) {
+    const int x0 = max(0, cx - g.w_lo), x1 = min(g.cols, cx + g.w_hi + 1), y0 = max(0, cy - g.h_lo), y1 = min(g.rows, cy + g.h_hi + 1);
+    if (x0 >= x1 || y0 >= y1) continue;
+    MgLine lt; lt.start(t[0], t[1], t[2], t[3]);
+    int x, y;
+    while (lt.next(&x, &y))
+      if (x >= x0 && x < x1 && y >= y0 && y < y1) return true;  // (inside the window implies inside the grid)
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(128) k_mg_columns(MgGrid g, int is_lines, const int* __restrict__ q_geo,
+                                                    const int* __restrict__ t_geo, const double* __restrict__ t_dir,
+                                                    double line_sim_th, const uint32_t* __restrict__ d1, int n1,
+                                                    const uint32_t* __restrict__ d2, int n2, int best_lr,
+                                                    unsigned short* __restrict__ D, int* __restrict__ m21) {
+  const int i2 = blockIdx.x * 128 + threadIdx.x;
+  if (i2 >= n2) return;
+  const uint4* b = reinterpret_cast<const uint4*>(d2) + 2 * (size_t)i2;
+  int tg[4] = {0, 0, 0, 0};
+  bool t_ok = true;
+  double tdx = 0, tdy = 0;
+  if (is_lines) {
+    for (int k = 0; k < 4; ++k) tg[k] = t_geo[4 * i2 + k];
+    tdx = t_dir[2 * i2]; tdy = t_dir[2 * i2 + 1];
+  } else {
+    tg[0] = t_geo[2 * i2]; tg[1] = t_geo[2 * i2 + 1];
+    t_ok = tg[0] >= 0 && tg[0] < g.cols && tg[1] >= 0 && tg[1] < g.rows;  // grid.at() outside the grid: never returned
+  }
+  int run = 0x7FFFFFFF, who = -1;
+  for (int i1 = 0; i1 < n1; ++i1) {
+    bool cand = t_ok;
+    if (cand) {
+      if (is_lines) {
+        const int* q = q_geo + 4 * i1;
+        cand = mg_lines_near(g, q, tg);
+        if (cand) {  // direction gate, before the distance (and before the best-so-far record) as in the reference
+          double vx = (double)(q[2] - q[0]), vy = (double)(q[3] - q[1]);
+          const double nrm = sqrt(vx * vx + vy * vy);
+          vx /= nrm; vy /= nrm;  // unguarded like the reference's normalize(): 0/0 = NaN fails the '<' below -> kept
+          if (fabs(vx * tdx + vy * tdy) < line_sim_th) cand = false;
+        }
+      } else {
+        cand = mg_in_window(g, q_geo[2 * i1], q_geo[2 * i1 + 1], tg[0], tg[1]);
+      }
+    }
+    unsigned short out = MG_NONE;
+    if (cand) {
+      const int d = mg_hamming(reinterpret_cast<const uint4*>(d1) + 2 * (size_t)i1, b);
+      if (best_lr) {
+        if (d < run) { run = d; who = i1; out = (unsigned short)d; }
+      } else {
+        out = (unsigned short)d;
+      }
+    }
+    D[(size_t)i1 * n2 + i2] = out;
+  }
+  m21[i2] = who;
+}
+
+__global__ void __launch_bounds__(128) k_mg_rows(const unsigned short* __restrict__ D, int n1, int n2, float nnr,
+                                                 int32_t* __restrict__ m12) {
+  const int i1 = blockIdx.x * 128 + threadIdx.x;
+  if (i1 >= n1) return;
+  int best_d = 0x7FFFFFFF, best_d2 = 0x7FFFFFFF, best_idx = -1;
+  const unsigned short* row = D + (size_t)i1 * n2;
+  for (int i2 = 0; i2 < n2; ++i2) {
+    const int d = row[i2];
+    if (d == MG_NONE) continue;
+    if (d < best_d) { best_d2 = best_d; best_d = d; best_idx = i2; }
+    else if (d < best_d2) best_d2 = d;
+  }
+  // `best_d < best_d2 * nnr`: int * float -> f32 product, int -> f32 comparison (INT_MAX when there is one candidate)
+  m12[i1] = ((float)best_d < __fmul_rn((float)best_d2, nnr)) ? best_idx : -1;
+}
+
+__global__ void __launch_bounds__(128) k_mg_mutual(int32_t* __restrict__ m12, const int* __restrict__ m21, int n1,
+                                                   int best_lr, int* __restrict__ count) {
+  const int i1 = blockIdx.x * 128 + threadIdx.x;
+  bool ok = false;
+  if (i1 < n1) {
+    const int i2 = m12[i1];
+    ok = i2 >= 0;
+    if (ok && best_lr && m21[i2] != i1) { m12[i1] = -1; ok = false; }
+  }
+  const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(count, __popc(bal));
+}
+
+static size_t mg_align(size_t x) { return (x + 255) & ~size_t(255); }
+
+static plf_status mg_run(plf_ctx* ctx, const char* who, int is_lines, const int* q_geo, const uint8_t* d1, int n1,
+                         const int* t_geo, const double* t_dir, const uint8_t* d2, int n2, int cols, int rows,
+                         plf_grid_window w, float nnr, double line_sim_th, int best_lr, int32_t* matches_12, int* n_matches) {
+  if (!ctx) return PLF_ERR_INVALID;
+  if (n_matches) *n_matches = 0;
+  if (n1 < 0 || n2 < 0 || n1 > 8192 || n2 > 8192 || cols <= 0 || rows <= 0 || cols > 4096 || rows > 4096 ||
+      (n1 > 0 && (!q_geo || !d1 || !matches_12)) || (n2 > 0 && (!t_geo || !d2 || (is_lines && !t_dir))))
+    return plf_fail(ctx, PLF_ERR_INVALID, "%s: bad arguments (n1=%d, n2=%d, each <= 8192; grid %dx%d)", who, n1, n2, cols, rows);
+  if (n1 == 0) return PLF_OK;
+  if (n2 == 0) {
+    for (int i = 0; i < n1; ++i) matches_12[i] = -1;
+    return PLF_OK;
+  }
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  const int gq = is_lines ? 4 : 2;
+  const size_t bq = mg_align((size_t)n1 * gq * 4), bt = mg_align((size_t)n2 * gq * 4), bdir = mg_align((size_t)n2 * 16),
+               b1 = mg_align((size_t)n1 * 32), b2 = mg_align((size_t)n2 * 32), bD = mg_align((size_t)n1 * n2 * 2),
+               bm12 = mg_align((size_t)n1 * 4), bm21 = mg_align((size_t)n2 * 4);
+  uint8_t* base = (uint8_t*)plf_scratch(ctx, 0, bq + bt + bdir + b1 + b2 + bD + bm12 + bm21 + 256);
+  if (!base) return PLF_ERR_CUDA;
+  uint8_t* p = base;
+  int* dq = (int*)p; p += bq;
+  int* dt = (int*)p; p += bt;
+  double* ddir = (double*)p; p += bdir;
+  uint8_t* dd1 = p; p += b1;
+  uint8_t* dd2 = p; p += b2;
+  unsigned short* D = (unsigned short*)p; p += bD;
+  int32_t* dm12 = (int32_t*)p; p += bm12;
+  int* dm21 = (int*)p; p += bm21;
+  int* dcount = (int*)p;
+  cudaStream_t cs = ctx->stream;
+  ctx->cur = cs;
+  PLF_CUDA(ctx, cudaMemcpyAsync(dq, q_geo, (size_t)n1 * gq * 4, cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(dt, t_geo, (size_t)n2 * gq * 4, cudaMemcpyHostToDevice, cs));
+  if (is_lines) PLF_CUDA(ctx, cudaMemcpyAsync(ddir, t_dir, (size_t)n2 * 16, cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(dd1, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(dd2, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(int), cs));
+  const MgGrid g = {cols, rows, w.width_lo, w.width_hi, w.height_lo, w.height_hi};
+  k_mg_columns<<<(n2 + 127) / 128, 128, 0, cs>>>(g, is_lines, dq, dt, ddir, line_sim_th, (const uint32_t*)dd1, n1,
+                                                 (const uint32_t*)dd2, n2, best_lr ? 1 : 0, D, dm21);
+  PLF_LAUNCH_CHECK(ctx);
+  k_mg_rows<<<(n1 + 127) / 128, 128, 0, cs>>>(D, n1, n2, nnr, dm12);
+  PLF_LAUNCH_CHECK(ctx);
+  k_mg_mutual<<<(n1 + 127) / 128, 128, 0, cs>>>(dm12, dm21, n1, best_lr ? 1 : 0, dcount);
+  PLF_LAUNCH_CHECK(ctx);
+  int cnt = 0;
+  PLF_CUDA(ctx, cudaMemcpyAsync(matches_12, dm12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(&cnt, dcount, sizeof(int), cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaStreamSynchronize(cs));
+  if (n_matches) *n_matches = cnt;
+  return PLF_OK;
+}
+
+extern "C" plf_status plf_match_grid_points(plf_ctx* ctx, const int* q_cell, const uint8_t* d1, int n1, const int* t_cell,
+                                            const uint8_t* d2, int n2, int grid_cols, int grid_rows, plf_grid_window w,
+                                            float nnr, int best_lr, int32_t* matches_12, int* n_matches) {
+  return mg_run(ctx, "plf_match_grid_points", 0, q_cell, d1, n1, t_cell, nullptr, d2, n2, grid_cols, grid_rows, w, nnr, 0.0,
+                best_lr, matches_12, n_matches);
+}
+
+extern "C" plf_status plf_match_grid_lines(plf_ctx* ctx, const int* q_line, const uint8_t* d1, int n1, const int* t_line,
+                                           const double* t_dir, const uint8_t* d2, int n2, int grid_cols, int grid_rows,
+                                           plf_grid_window w, float nnr, double line_sim_th, int best_lr,
+                                           int32_t* matches_12, int* n_matches) {
+  return mg_run(ctx, "plf_match_grid_lines", 1, q_line, d1, n1, t_line, t_dir, d2, n2, grid_cols, grid_rows, w, nnr,
+                line_sim_th, best_lr, matches_12, n_matches);
+}
