@@ -133,24 +133,26 @@ plf_status plf_match(plf_ctx* ctx, const uint8_t* d1, int n1, const uint8_t* d2,
  * restated from SURVEY Appendix A.3 (oracle/matchgrid.py, "parity unpinned"); candidates are visited in ascending index
  * order where stvo-pl iterates an unordered_set.
  * All coordinates are integer GRID cells (x in [0, grid_cols), y in [0, grid_rows)), i.e. what the reference obtains by
- * scaling pixels with inv_width = GRID_COLS / width, inv_height = GRID_ROWS / height and truncating to int:
- *   points: q_cell [n1][2] = cells of the projected query points (pj_points), t_cell [n2][2] = the cell each train
- *           feature was pushed into with grid.at(x, y) (outside the grid: never a candidate);
- *   lines:  q_line [n1][4], t_line [n2][4] = (x1, y1, x2, y2) end-point cells - the query is looked up, and the train
- *           line registered, in the Bresenham cells between them (getLineCoords) - and t_dir [n2][2] = directions2.
+ * scaling pixels with inv_width = GRID_COLS / width, inv_height = GRID_ROWS / height and truncating to int.
+ *   The GridStructure is passed as it is held - per cell, the list of train indices pushed into it with
+ *   grid.at(x, y).push_back(idx): cell (x, y) owns cell_items[cell_start[x * grid_rows + y] .. cell_start[.. + 1]);
+ *   a train line appears in every cell of its getLineCoords() walk; indices outside [0, n2) are ignored.
+ *   points: q_cell [n1][2] = cells of the projected query points (pj_points);
+ *   lines:  q_line [n1][4] = (x1, y1, x2, y2) end-point cells of the projected query lines (looked up along their
+ *           Bresenham walk), t_dir [n2][2] = directions2.
  * Query order matters: with best_lr a candidate counts for query i only if it beats every earlier query's distance to
  * it.  matches_12[i] = j or -1; *n_matches = the reference's return value.  n1, n2 <= 8192. */
 typedef struct plf_grid_window {
   int width_lo, width_hi;    /* GridWindow::width  (first, second) */
   int height_lo, height_hi;  /* GridWindow::height (first, second) */
 } plf_grid_window;
-plf_status plf_match_grid_points(plf_ctx* ctx, const int* q_cell, const uint8_t* d1, int n1, const int* t_cell,
-                                 const uint8_t* d2, int n2, int grid_cols, int grid_rows, plf_grid_window w, float nnr,
-                                 int best_lr, int32_t* matches_12, int* n_matches);
-plf_status plf_match_grid_lines(plf_ctx* ctx, const int* q_line, const uint8_t* d1, int n1, const int* t_line,
-                                const double* t_dir, const uint8_t* d2, int n2, int grid_cols, int grid_rows,
-                                plf_grid_window w, float nnr, double line_sim_th, int best_lr, int32_t* matches_12,
-                                int* n_matches);
+plf_status plf_match_grid_points(plf_ctx* ctx, const int* q_cell, const uint8_t* d1, int n1, const int* cell_start,
+                                 const int* cell_items, const uint8_t* d2, int n2, int grid_cols, int grid_rows,
+                                 plf_grid_window w, float nnr, int best_lr, int32_t* matches_12, int* n_matches);
+plf_status plf_match_grid_lines(plf_ctx* ctx, const int* q_line, const uint8_t* d1, int n1, const int* cell_start,
+                                const int* cell_items, const double* t_dir, const uint8_t* d2, int n2, int grid_cols,
+                                int grid_rows, plf_grid_window w, float nnr, double line_sim_th, int best_lr,
+                                int32_t* matches_12, int* n_matches);
 
 /* Landmark descriptor maintenance, batched.  Replaces the body of MapPoint::updateAverageDescDir and
  * MapLine::updateAverageDescDir (src/mapFeatures.cpp:51-93, 121-163), called on every observation add (:48, :118).

@@ -83,44 +83,89 @@ def _greedy(n1, n2, cand_fn, d1, d2, nnr, best_lr):
     return m12, matches
 
 
-def match_grid_points(q_cell, d1, t_cell, d2, cols, rows, w, nnr, best_lr=True):
-    """q_cell [n1,2], t_cell [n2,2] integer grid coordinates (x, y); w = (width.first, width.second, height.first,
-    height.second)."""
-    q_cell = np.asarray(q_cell, np.int64).reshape(-1, 2); t_cell = np.asarray(t_cell, np.int64).reshape(-1, 2)
-    n1, n2 = len(q_cell), len(t_cell)
-    in_grid = (t_cell[:, 0] >= 0) & (t_cell[:, 0] < cols) & (t_cell[:, 1] >= 0) & (t_cell[:, 1] < rows)
+class Grid:
+    """GridStructure: rows x cols lists of train indices; at(x, y).push_back(idx) outside the grid goes to a bin that is
+    never returned."""
+
+    def __init__(self, rows, cols):
+        self.rows, self.cols = int(rows), int(cols)
+        self.cells = [[[] for _ in range(self.rows)] for _ in range(self.cols)]
+
+    def push(self, x, y, idx):
+        x, y = int(x), int(y)
+        if 0 <= x < self.cols and 0 <= y < self.rows:
+            self.cells[x][y].append(int(idx))
+
+    def get(self, x, y, w):
+        x0, x1, y0, y1 = _window(int(x), int(y), w, self.cols, self.rows)
+        out = set()
+        for xx in range(x0, x1):
+            for yy in range(y0, y1):
+                out.update(self.cells[xx][yy])
+        return out
+
+    def csr(self):
+        """(cell_start int32[cols*rows+1], cell_items int32[]) with cell (x, y) at index x*rows + y - the C ABI's form."""
+        start, items = [0], []
+        for x in range(self.cols):
+            for y in range(self.rows):
+                items += self.cells[x][y]
+                start.append(len(items))
+        return np.asarray(start, np.int32), np.asarray(items, np.int32)
+
+
+def grid_from_points(t_cell, rows, cols):
+    """src/mapHandler.cpp:260-264: every train point is pushed into the cell of its (scaled, truncated) position."""
+    g = Grid(rows, cols)
+    for idx, (x, y) in enumerate(np.asarray(t_cell, np.int64).reshape(-1, 2)):
+        g.push(x, y, idx)
+    return g
+
+
+def grid_from_lines(t_line, rows, cols):
+    """src/mapHandler.cpp:398-411: every train line is pushed into each cell of its getLineCoords() walk."""
+    g = Grid(rows, cols)
+    for idx, ln in enumerate(np.asarray(t_line, np.int64).reshape(-1, 4)):
+        for (x, y) in bresenham(*ln):
+            g.push(x, y, idx)
+    return g
+
+
+def match_grid_points(q_cell, d1, grid, d2, w, nnr, best_lr=True):
+    """q_cell [n1,2] integer grid coordinates (x, y); grid: Grid over the train features; w = (width.first,
+    width.second, height.first, height.second)."""
+    q_cell = np.asarray(q_cell, np.int64).reshape(-1, 2)
+    n1, n2 = len(q_cell), len(d2)
 
     def cand(i1):
-        x0, x1, y0, y1 = _window(int(q_cell[i1, 0]), int(q_cell[i1, 1]), w, cols, rows)
-        ok = in_grid & (t_cell[:, 0] >= x0) & (t_cell[:, 0] < x1) & (t_cell[:, 1] >= y0) & (t_cell[:, 1] < y1)
-        return np.nonzero(ok)[0]
+        return sorted(i2 for i2 in grid.get(q_cell[i1, 0], q_cell[i1, 1], w) if 0 <= i2 < n2)
 
     return _greedy(n1, n2, cand, d1, d2, nnr, best_lr)
 
 
-def match_grid_lines(q_line, d1, t_line, t_dir, d2, cols, rows, w, nnr, line_sim_th, best_lr=True):
-    """q_line [n1,4], t_line [n2,4]: integer grid coordinates (x1, y1, x2, y2); t_dir [n2,2]: the train lines' unit
-    directions (directions2)."""
-    q_line = np.asarray(q_line, np.int64).reshape(-1, 4); t_line = np.asarray(t_line, np.int64).reshape(-1, 4)
+def match_grid_lines(q_line, d1, grid, t_dir, d2, w, nnr, line_sim_th, best_lr=True):
+    """q_line [n1,4]: integer grid coordinates (x1, y1, x2, y2) of the projected query lines; grid: Grid over the train
+    lines; t_dir [n2,2]: the train lines' unit directions (directions2)."""
+    q_line = np.asarray(q_line, np.int64).reshape(-1, 4)
     t_dir = np.asarray(t_dir, np.float64).reshape(-1, 2)
-    n1, n2 = len(q_line), len(t_line)
-    occ = np.zeros((n2, cols, rows), bool)         # cells each train line is registered in
-    for i2 in range(n2):
-        for (x, y) in bresenham(*t_line[i2]):
-            if 0 <= x < cols and 0 <= y < rows:
-                occ[i2, x, y] = True
+    n1, n2 = len(q_line), len(d2)
 
     def cand(i1):
-        hit = np.zeros(n2, bool)
+        c = set()
         for (x, y) in bresenham(*q_line[i1]):
-            x0, x1, y0, y1 = _window(x, y, w, cols, rows)
-            if x0 < x1 and y0 < y1:
-                hit |= occ[:, x0:x1, y0:y1].any(axis=(1, 2))
+            c |= grid.get(x, y, w)
         vx, vy = float(q_line[i1, 2] - q_line[i1, 0]), float(q_line[i1, 3] - q_line[i1, 1])
         with np.errstate(invalid="ignore", divide="ignore"):
             nrm = np.sqrt(np.float64(vx * vx + vy * vy))     # normalize(v) is unguarded: a query whose end points share
             vx, vy = np.float64(vx) / nrm, np.float64(vy) / nrm  # a cell gives 0/0 = NaN, and NaN < th is false -> kept
-            dots = np.abs(vx * t_dir[:, 0] + vy * t_dir[:, 1])
-        return np.nonzero(hit & ~(dots < line_sim_th))[0]
+        out = []
+        for i2 in sorted(c):
+            if not (0 <= i2 < n2):
+                continue
+            with np.errstate(invalid="ignore"):
+                if abs(vx * t_dir[i2, 0] + vy * t_dir[i2, 1]) < line_sim_th:
+                    continue
+            out.append(i2)
+        return out
 
     return _greedy(n1, n2, cand, d1, d2, nnr, best_lr)

@@ -398,4 +398,97 @@ inline int match(plf_ctx* ctx, const DescMat& d1, const DescMat& d2, float nnr, 
   return n;
 }
 
+// ---- stvo-pl gridStructure.h / matching.h: the windowed matcher pl-slam uses when SlamConfig::fastMatching() ----------
+// (src/mapHandler.cpp:251-271 points, :382-418 lines; also :580-591, :686-706).  Cell coordinates are ints: callers scale
+// pixels by inv_width = GRID_COLS / width, inv_height = GRID_ROWS / height and the pair<double,double> -> pair<int,int>
+// conversion truncates.  [UPSTREAM-RECALL]: restated from SURVEY Appendix A.3, see oracle/matchgrid.py.
+#define GRID_ROWS 48
+#define GRID_COLS 36
+typedef std::pair<int, int> point_2d;
+typedef std::pair<point_2d, point_2d> line_2d;
+
+struct GridWindow {
+  std::pair<int, int> width, height;
+};
+
+inline void normalize(std::pair<double, double>& v) {  // unguarded, as upstream
+  const double m = std::sqrt(v.first * v.first + v.second * v.second);
+  v.first /= m;
+  v.second /= m;
+}
+
+// cells of the 8-connected line between two cells, end points included
+inline void getLineCoords(double x1d, double y1d, double x2d, double y2d, std::list<point_2d>& line_coords) {
+  line_coords.clear();
+  int x1 = (int)x1d, y1 = (int)y1d, x2 = (int)x2d, y2 = (int)y2d;
+  const bool steep = std::abs(y2 - y1) > std::abs(x2 - x1);
+  if (steep) { std::swap(x1, y1); std::swap(x2, y2); }
+  if (x1 > x2) { std::swap(x1, x2); std::swap(y1, y2); }
+  const int dx = x2 - x1, dy = std::abs(y2 - y1), ystep = y1 < y2 ? 1 : -1;
+  int err = dx / 2, y = y1;
+  for (int x = x1; x <= x2; ++x) {
+    line_coords.emplace_back(steep ? y : x, steep ? x : y);
+    err -= dy;
+    if (err < 0) { y += ystep; err += dx; }
+  }
+}
+
+class GridStructure {
+ public:
+  int rows, cols;
+  GridStructure(int rows_, int cols_) : rows(rows_), cols(cols_), grid(cols_, std::vector<std::list<int>>(rows_)) {
+    if (rows_ <= 0 || cols_ <= 0) throw std::runtime_error("[GridStructure] invalid dimension");
+  }
+  std::list<int>& at(int x, int y) { return (x >= 0 && x < cols && y >= 0 && y < rows) ? grid[x][y] : out_of_bounds; }
+  void clear() { for (auto& c : grid) for (auto& l : c) l.clear(); }
+  // the C ABI's form: cell (x, y) owns items[start[x*rows+y] .. start[x*rows+y+1])
+  void flatten(std::vector<int>& start, std::vector<int>& items) const {
+    start.assign(1, 0); items.clear();
+    for (int x = 0; x < cols; ++x)
+      for (int y = 0; y < rows; ++y) {
+        items.insert(items.end(), grid[x][y].begin(), grid[x][y].end());
+        start.push_back((int)items.size());
+      }
+  }
+ private:
+  std::vector<std::vector<std::list<int>>> grid;
+  std::list<int> out_of_bounds;
+};
+
+inline int matchGrid(plf_ctx* ctx, const std::vector<point_2d>& points, const DescMat& d1, const GridStructure& grid,
+                     const DescMat& d2, const GridWindow& w, std::vector<int>& matches_12, float nnr, bool best_lr = true) {
+  if ((int)points.size() != d1.rows) throw std::runtime_error("[matchGrid] each point needs a corresponding descriptor!");
+  std::vector<int> q; q.reserve(2 * points.size());
+  for (const auto& p : points) { q.push_back(p.first); q.push_back(p.second); }
+  std::vector<int> start, items;
+  grid.flatten(start, items);
+  matches_12.assign(d1.rows, -1);
+  int n = 0;
+  const plf_grid_window gw = {w.width.first, w.width.second, w.height.first, w.height.second};
+  if (plf_match_grid_points(ctx, q.data(), d1.data.data(), d1.rows, start.data(), items.data(), d2.data.data(), d2.rows,
+                            grid.cols, grid.rows, gw, nnr, best_lr ? 1 : 0, matches_12.data(), &n) != PLF_OK)
+    throw std::runtime_error(std::string("[matchGrid] ") + plf_last_error(ctx));
+  return n;
+}
+
+inline int matchGrid(plf_ctx* ctx, const std::vector<line_2d>& lines, const DescMat& d1, const GridStructure& grid,
+                     const DescMat& d2, const std::vector<std::pair<double, double>>& directions2, const GridWindow& w,
+                     std::vector<int>& matches_12, float nnr, double line_sim_th, bool best_lr = true) {
+  if ((int)lines.size() != d1.rows) throw std::runtime_error("[matchGrid] each line needs a corresponding descriptor!");
+  if ((int)directions2.size() != d2.rows) throw std::runtime_error("[matchGrid] each train line needs a direction!");
+  std::vector<int> q; q.reserve(4 * lines.size());
+  for (const auto& l : lines) { q.push_back(l.first.first); q.push_back(l.first.second); q.push_back(l.second.first); q.push_back(l.second.second); }
+  std::vector<double> dir; dir.reserve(2 * directions2.size());
+  for (const auto& v : directions2) { dir.push_back(v.first); dir.push_back(v.second); }
+  std::vector<int> start, items;
+  grid.flatten(start, items);
+  matches_12.assign(d1.rows, -1);
+  int n = 0;
+  const plf_grid_window gw = {w.width.first, w.width.second, w.height.first, w.height.second};
+  if (plf_match_grid_lines(ctx, q.data(), d1.data.data(), d1.rows, start.data(), items.data(), dir.data(), d2.data.data(),
+                           d2.rows, grid.cols, grid.rows, gw, nnr, line_sim_th, best_lr ? 1 : 0, matches_12.data(), &n) != PLF_OK)
+    throw std::runtime_error(std::string("[matchGrid] ") + plf_last_error(ctx));
+  return n;
+}
+
 }  // namespace StVO

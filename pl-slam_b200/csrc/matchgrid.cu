@@ -8,13 +8,17 @@
 // The reference loop is sequential over the queries: with best_lr_matches a candidate i2 counts for query i1 only if
 // d(i1,i2) beats the smallest distance any EARLIER query achieved on i2.  That is an exclusive prefix-minimum down each
 // column of the (query x train) candidate matrix, so the work splits into
-//   k_mg_columns : one thread per train feature walks the queries in order, evaluates the candidate predicate (window
-//                  test; for lines, Bresenham cells within the window of each other + direction gate), computes the
-//                  Hamming distance of the candidates and writes d or "not considered" to a dense u16 matrix;
+//   k_mg_columns : one thread per train feature walks the queries in order, evaluates the candidate predicate (is one
+//                  of the grid cells the feature was pushed into inside the GridStructure::get window of the query's
+//                  cell - for lines: of one of the query's Bresenham cells - plus, for lines, the direction gate),
+//                  computes the Hamming distance of the candidates and writes d or "not considered" to a dense u16
+//                  matrix (the grid arrives as cell -> items lists, the host wrapper inverts it to item -> cells);
 //   k_mg_rows    : one thread per query scans its row in ascending train index with the reference's strict '<' updates,
 //                  applies the f32 ratio test and records matches_12; matches_21 comes from the column pass;
 //   k_mg_mutual  : drops i1 unless matches_21[matches_12[i1]] == i1, counts the matches.
 #include "plf_internal.h"
+#include <algorithm>
+#include <vector>
 
 #define MG_NONE 0xFFFFu
 
@@ -52,46 +56,39 @@ struct MgLine {
   }
 };
 
-// lines: is some registered (in-grid) cell of train line t inside the window of some cell of query line q?
-__device__ bool mg_lines_near(const MgGrid& g, const int* q, const int* t) {
-  MgLine lq; lq.start(q[0], q[1], q[2], q[3]);
-  int cx, cy;
-  while (lq.next(&cx, &cy)) {
-    const int x0 = max(0, cx - g.w_lo), x1 = min(g.cols, cx + g.w_hi + 1), y0 = max(0, cy - g.h_lo), y1 = min(g.rows, cy + g.h_hi + 1);
-    if (x0 >= x1 || y0 >= y1) continue;
-    MgLine lt; lt.start(t[0], t[1], t[2], t[3]);
-    int x, y;
-    while (lt.next(&x, &y))
-      if (x >= x0 && x < x1 && y >= y0 && y < y1) return true;  // (inside the window implies inside the grid)
+// is one of the cells (packed x * rows + y) the train feature sits in returned by get(cx, cy, w)?
+__device__ __forceinline__ bool mg_cells_in_window(const MgGrid& g, int cx, int cy, const int* cells, int nc) {
+  const int x0 = max(0, cx - g.w_lo), x1 = min(g.cols, cx + g.w_hi + 1), y0 = max(0, cy - g.h_lo), y1 = min(g.rows, cy + g.h_hi + 1);
+  if (x0 >= x1 || y0 >= y1) return false;
+  for (int k = 0; k < nc; ++k) {
+    const int x = cells[k] / g.rows, y = cells[k] - x * g.rows;
+    if (x >= x0 && x < x1 && y >= y0 && y < y1) return true;
   }
   return false;
 }
 
 __global__ void __launch_bounds__(128) k_mg_columns(MgGrid g, int is_lines, const int* __restrict__ q_geo,
-                                                    const int* __restrict__ t_geo, const double* __restrict__ t_dir,
-                                                    double line_sim_th, const uint32_t* __restrict__ d1, int n1,
+                                                    const int* __restrict__ t_cell_start, const int* __restrict__ t_cells,
+                                                    const double* __restrict__ t_dir, double line_sim_th,
+                                                    const uint32_t* __restrict__ d1, int n1,
                                                     const uint32_t* __restrict__ d2, int n2, int best_lr,
                                                     unsigned short* __restrict__ D, int* __restrict__ m21) {
   const int i2 = blockIdx.x * 128 + threadIdx.x;
   if (i2 >= n2) return;
   const uint4* b = reinterpret_cast<const uint4*>(d2) + 2 * (size_t)i2;
-  int tg[4] = {0, 0, 0, 0};
-  bool t_ok = true;
+  const int* cells = t_cells + t_cell_start[i2];
+  const int nc = t_cell_start[i2 + 1] - t_cell_start[i2];  // 0: the feature is in no cell of the grid -> never a candidate
   double tdx = 0, tdy = 0;
-  if (is_lines) {
-    for (int k = 0; k < 4; ++k) tg[k] = t_geo[4 * i2 + k];
-    tdx = t_dir[2 * i2]; tdy = t_dir[2 * i2 + 1];
-  } else {
-    tg[0] = t_geo[2 * i2]; tg[1] = t_geo[2 * i2 + 1];
-    t_ok = tg[0] >= 0 && tg[0] < g.cols && tg[1] >= 0 && tg[1] < g.rows;  // grid.at() outside the grid: never returned
-  }
+  if (is_lines) { tdx = t_dir[2 * i2]; tdy = t_dir[2 * i2 + 1]; }
   int run = 0x7FFFFFFF, who = -1;
   for (int i1 = 0; i1 < n1; ++i1) {
-    bool cand = t_ok;
-    if (cand) {
+    bool cand = false;
+    if (nc > 0) {
       if (is_lines) {
         const int* q = q_geo + 4 * i1;
-        cand = mg_lines_near(g, q, tg);
+        MgLine lq; lq.start(q[0], q[1], q[2], q[3]);
+        int cx, cy;
+        while (!cand && lq.next(&cx, &cy)) cand = mg_cells_in_window(g, cx, cy, cells, nc);
         if (cand) {  // direction gate, before the distance (and before the best-so-far record) as in the reference
           double vx = (double)(q[2] - q[0]), vy = (double)(q[3] - q[1]);
           const double nrm = sqrt(vx * vx + vy * vy);
@@ -99,7 +96,7 @@ __global__ void __launch_bounds__(128) k_mg_columns(MgGrid g, int is_lines, cons
           if (fabs(vx * tdx + vy * tdy) < line_sim_th) cand = false;
         }
       } else {
-        cand = mg_in_window(g, q_geo[2 * i1], q_geo[2 * i1 + 1], tg[0], tg[1]);
+        cand = mg_cells_in_window(g, q_geo[2 * i1], q_geo[2 * i1 + 1], cells, nc);
       }
     }
     unsigned short out = MG_NONE;
@@ -148,28 +145,44 @@ __global__ void __launch_bounds__(128) k_mg_mutual(int32_t* __restrict__ m12, co
 static size_t mg_align(size_t x) { return (x + 255) & ~size_t(255); }
 
 static plf_status mg_run(plf_ctx* ctx, const char* who, int is_lines, const int* q_geo, const uint8_t* d1, int n1,
-                         const int* t_geo, const double* t_dir, const uint8_t* d2, int n2, int cols, int rows,
-                         plf_grid_window w, float nnr, double line_sim_th, int best_lr, int32_t* matches_12, int* n_matches) {
+                         const int* cell_start, const int* cell_items, const double* t_dir, const uint8_t* d2, int n2,
+                         int cols, int rows, plf_grid_window w, float nnr, double line_sim_th, int best_lr,
+                         int32_t* matches_12, int* n_matches) {
   if (!ctx) return PLF_ERR_INVALID;
   if (n_matches) *n_matches = 0;
-  if (n1 < 0 || n2 < 0 || n1 > 8192 || n2 > 8192 || cols <= 0 || rows <= 0 || cols > 4096 || rows > 4096 ||
-      (n1 > 0 && (!q_geo || !d1 || !matches_12)) || (n2 > 0 && (!t_geo || !d2 || (is_lines && !t_dir))))
+  if (n1 < 0 || n2 < 0 || n1 > 8192 || n2 > 8192 || cols <= 0 || rows <= 0 || cols > 4096 || rows > 4096 || !cell_start ||
+      (n1 > 0 && (!q_geo || !d1 || !matches_12)) || (n2 > 0 && (!d2 || (is_lines && !t_dir))))
     return plf_fail(ctx, PLF_ERR_INVALID, "%s: bad arguments (n1=%d, n2=%d, each <= 8192; grid %dx%d)", who, n1, n2, cols, rows);
+  const int ncell = cols * rows, nitems = cell_start[ncell];
+  if (cell_start[0] != 0 || nitems < 0 || (nitems > 0 && !cell_items))
+    return plf_fail(ctx, PLF_ERR_INVALID, "%s: cell_start must start at 0 and be non-decreasing", who);
   if (n1 == 0) return PLF_OK;
-  if (n2 == 0) {
-    for (int i = 0; i < n1; ++i) matches_12[i] = -1;
-    return PLF_OK;
+  for (int i = 0; i < n1; ++i) matches_12[i] = -1;
+  if (n2 == 0) return PLF_OK;
+  // invert the grid: cell -> items (what GridStructure holds) to item -> cells (what a per-feature thread scans);
+  // items outside [0, n2) are dropped as the reference's `if (i2 < 0 || i2 >= desc2.rows) continue;` does
+  std::vector<int> tstart(n2 + 1, 0);
+  for (int c = 0; c < ncell; ++c) {
+    if (cell_start[c + 1] < cell_start[c]) return plf_fail(ctx, PLF_ERR_INVALID, "%s: cell_start must be non-decreasing", who);
+    for (int k = cell_start[c]; k < cell_start[c + 1]; ++k)
+      if (cell_items[k] >= 0 && cell_items[k] < n2) tstart[cell_items[k] + 1]++;
   }
+  for (int i = 0; i < n2; ++i) tstart[i + 1] += tstart[i];
+  std::vector<int> tcells(std::max(tstart[n2], 1)), fill(tstart.begin(), tstart.end() - 1);
+  for (int c = 0; c < ncell; ++c)
+    for (int k = cell_start[c]; k < cell_start[c + 1]; ++k)
+      if (cell_items[k] >= 0 && cell_items[k] < n2) tcells[fill[cell_items[k]]++] = c;  // cell id = x * rows + y
   PLF_CUDA(ctx, cudaSetDevice(ctx->device));
   const int gq = is_lines ? 4 : 2;
-  const size_t bq = mg_align((size_t)n1 * gq * 4), bt = mg_align((size_t)n2 * gq * 4), bdir = mg_align((size_t)n2 * 16),
-               b1 = mg_align((size_t)n1 * 32), b2 = mg_align((size_t)n2 * 32), bD = mg_align((size_t)n1 * n2 * 2),
-               bm12 = mg_align((size_t)n1 * 4), bm21 = mg_align((size_t)n2 * 4);
-  uint8_t* base = (uint8_t*)plf_scratch(ctx, 0, bq + bt + bdir + b1 + b2 + bD + bm12 + bm21 + 256);
+  const size_t bq = mg_align((size_t)n1 * gq * 4), bts = mg_align((size_t)(n2 + 1) * 4), btc = mg_align(tcells.size() * 4),
+               bdir = mg_align((size_t)n2 * 16), b1 = mg_align((size_t)n1 * 32), b2 = mg_align((size_t)n2 * 32),
+               bD = mg_align((size_t)n1 * n2 * 2), bm12 = mg_align((size_t)n1 * 4), bm21 = mg_align((size_t)n2 * 4);
+  uint8_t* base = (uint8_t*)plf_scratch(ctx, 0, bq + bts + btc + bdir + b1 + b2 + bD + bm12 + bm21 + 256);
   if (!base) return PLF_ERR_CUDA;
   uint8_t* p = base;
   int* dq = (int*)p; p += bq;
-  int* dt = (int*)p; p += bt;
+  int* dts = (int*)p; p += bts;
+  int* dtc = (int*)p; p += btc;
   double* ddir = (double*)p; p += bdir;
   uint8_t* dd1 = p; p += b1;
   uint8_t* dd2 = p; p += b2;
@@ -180,13 +193,14 @@ static plf_status mg_run(plf_ctx* ctx, const char* who, int is_lines, const int*
   cudaStream_t cs = ctx->stream;
   ctx->cur = cs;
   PLF_CUDA(ctx, cudaMemcpyAsync(dq, q_geo, (size_t)n1 * gq * 4, cudaMemcpyHostToDevice, cs));
-  PLF_CUDA(ctx, cudaMemcpyAsync(dt, t_geo, (size_t)n2 * gq * 4, cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(dts, tstart.data(), (size_t)(n2 + 1) * 4, cudaMemcpyHostToDevice, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(dtc, tcells.data(), tcells.size() * 4, cudaMemcpyHostToDevice, cs));
   if (is_lines) PLF_CUDA(ctx, cudaMemcpyAsync(ddir, t_dir, (size_t)n2 * 16, cudaMemcpyHostToDevice, cs));
   PLF_CUDA(ctx, cudaMemcpyAsync(dd1, d1, (size_t)n1 * 32, cudaMemcpyHostToDevice, cs));
   PLF_CUDA(ctx, cudaMemcpyAsync(dd2, d2, (size_t)n2 * 32, cudaMemcpyHostToDevice, cs));
   PLF_CUDA(ctx, cudaMemsetAsync(dcount, 0, sizeof(int), cs));
   const MgGrid g = {cols, rows, w.width_lo, w.width_hi, w.height_lo, w.height_hi};
-  k_mg_columns<<<(n2 + 127) / 128, 128, 0, cs>>>(g, is_lines, dq, dt, ddir, line_sim_th, (const uint32_t*)dd1, n1,
+  k_mg_columns<<<(n2 + 127) / 128, 128, 0, cs>>>(g, is_lines, dq, dts, dtc, ddir, line_sim_th, (const uint32_t*)dd1, n1,
                                                  (const uint32_t*)dd2, n2, best_lr ? 1 : 0, D, dm21);
   PLF_LAUNCH_CHECK(ctx);
   k_mg_rows<<<(n1 + 127) / 128, 128, 0, cs>>>(D, n1, n2, nnr, dm12);
@@ -196,22 +210,22 @@ static plf_status mg_run(plf_ctx* ctx, const char* who, int is_lines, const int*
   int cnt = 0;
   PLF_CUDA(ctx, cudaMemcpyAsync(matches_12, dm12, (size_t)n1 * 4, cudaMemcpyDeviceToHost, cs));
   PLF_CUDA(ctx, cudaMemcpyAsync(&cnt, dcount, sizeof(int), cudaMemcpyDeviceToHost, cs));
-  PLF_CUDA(ctx, cudaStreamSynchronize(cs));
+  PLF_CUDA(ctx, cudaStreamSynchronize(cs));  // (the host vectors above are pageable: their copies completed at enqueue)
   if (n_matches) *n_matches = cnt;
   return PLF_OK;
 }
 
-extern "C" plf_status plf_match_grid_points(plf_ctx* ctx, const int* q_cell, const uint8_t* d1, int n1, const int* t_cell,
-                                            const uint8_t* d2, int n2, int grid_cols, int grid_rows, plf_grid_window w,
-                                            float nnr, int best_lr, int32_t* matches_12, int* n_matches) {
-  return mg_run(ctx, "plf_match_grid_points", 0, q_cell, d1, n1, t_cell, nullptr, d2, n2, grid_cols, grid_rows, w, nnr, 0.0,
-                best_lr, matches_12, n_matches);
+extern "C" plf_status plf_match_grid_points(plf_ctx* ctx, const int* q_cell, const uint8_t* d1, int n1, const int* cell_start,
+                                            const int* cell_items, const uint8_t* d2, int n2, int grid_cols, int grid_rows,
+                                            plf_grid_window w, float nnr, int best_lr, int32_t* matches_12, int* n_matches) {
+  return mg_run(ctx, "plf_match_grid_points", 0, q_cell, d1, n1, cell_start, cell_items, nullptr, d2, n2, grid_cols, grid_rows, w,
+                nnr, 0.0, best_lr, matches_12, n_matches);
 }
 
-extern "C" plf_status plf_match_grid_lines(plf_ctx* ctx, const int* q_line, const uint8_t* d1, int n1, const int* t_line,
-                                           const double* t_dir, const uint8_t* d2, int n2, int grid_cols, int grid_rows,
-                                           plf_grid_window w, float nnr, double line_sim_th, int best_lr,
-                                           int32_t* matches_12, int* n_matches) {
-  return mg_run(ctx, "plf_match_grid_lines", 1, q_line, d1, n1, t_line, t_dir, d2, n2, grid_cols, grid_rows, w, nnr,
-                line_sim_th, best_lr, matches_12, n_matches);
+extern "C" plf_status plf_match_grid_lines(plf_ctx* ctx, const int* q_line, const uint8_t* d1, int n1, const int* cell_start,
+                                           const int* cell_items, const double* t_dir, const uint8_t* d2, int n2,
+                                           int grid_cols, int grid_rows, plf_grid_window w, float nnr, double line_sim_th,
+                                           int best_lr, int32_t* matches_12, int* n_matches) {
+  return mg_run(ctx, "plf_match_grid_lines", 1, q_line, d1, n1, cell_start, cell_items, t_dir, d2, n2, grid_cols, grid_rows, w,
+                nnr, line_sim_th, best_lr, matches_12, n_matches);
 }

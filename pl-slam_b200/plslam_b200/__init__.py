@@ -124,10 +124,11 @@ def load_library() -> C.CDLL:
     lib.plf_stream.restype = C.c_void_p
     lib.plf_stream.argtypes = [C.c_void_p]
     _pi, _pu8 = C.POINTER(C.c_int), C.POINTER(C.c_uint8)
-    lib.plf_match_grid_points.argtypes = [C.c_void_p, _pi, _pu8, C.c_int, _pi, _pu8, C.c_int, C.c_int, C.c_int,
+    lib.plf_match_grid_points.argtypes = [C.c_void_p, _pi, _pu8, C.c_int, _pi, _pi, _pu8, C.c_int, C.c_int, C.c_int,
                                           plf_grid_window, C.c_float, C.c_int, C.POINTER(C.c_int32), _pi]
-    lib.plf_match_grid_lines.argtypes = [C.c_void_p, _pi, _pu8, C.c_int, _pi, C.POINTER(C.c_double), _pu8, C.c_int, C.c_int,
-                                         C.c_int, plf_grid_window, C.c_float, C.c_double, C.c_int, C.POINTER(C.c_int32), _pi]
+    lib.plf_match_grid_lines.argtypes = [C.c_void_p, _pi, _pu8, C.c_int, _pi, _pi, C.POINTER(C.c_double), _pu8, C.c_int,
+                                         C.c_int, C.c_int, plf_grid_window, C.c_float, C.c_double, C.c_int,
+                                         C.POINTER(C.c_int32), _pi]
     lib.plf_destroy.restype = None
     lib.plf_destroy.argtypes = [C.c_void_p]
     lib.plf_batch_device_images.restype = C.c_void_p
@@ -245,29 +246,33 @@ class Frontend:
         self._check(st, "plf_match")
         return m, cnt.value
 
-    def match_grid_points(self, q_cell, d1, t_cell, d2, cols, rows, w, nnr, best_lr=True):
-        """stvo-pl matchGrid (points): cells int32 [n,2]; w = (width.first, width.second, height.first, height.second)."""
-        q = np.ascontiguousarray(q_cell, np.int32).reshape(-1, 2); t = np.ascontiguousarray(t_cell, np.int32).reshape(-1, 2)
+    def match_grid_points(self, q_cell, d1, cell_start, cell_items, d2, cols, rows, w, nnr, best_lr=True):
+        """stvo-pl matchGrid (points): q_cell int32 [n1,2]; the GridStructure as (cell_start, cell_items), cell (x, y) at
+        x*rows + y; w = (width.first, width.second, height.first, height.second)."""
+        q = np.ascontiguousarray(q_cell, np.int32).reshape(-1, 2)
+        cs = np.ascontiguousarray(cell_start, np.int32); ci = np.ascontiguousarray(cell_items, np.int32)
         d1 = _u8(d1).reshape(-1, DESC_BYTES); d2 = _u8(d2).reshape(-1, DESC_BYTES)
         m = np.full(len(q), -1, np.int32)
         cnt = C.c_int(0)
-        st = self.lib.plf_match_grid_points(self._ctx, _ptr(q, C.c_int), _ptr(d1, C.c_uint8), len(q), _ptr(t, C.c_int),
-                                            _ptr(d2, C.c_uint8), len(t), int(cols), int(rows), plf_grid_window(*[int(v) for v in w]),
-                                            C.c_float(nnr), int(bool(best_lr)), _ptr(m, C.c_int32), C.byref(cnt))
+        st = self.lib.plf_match_grid_points(self._ctx, _ptr(q, C.c_int), _ptr(d1, C.c_uint8), len(q), _ptr(cs, C.c_int),
+                                            _ptr(ci, C.c_int), _ptr(d2, C.c_uint8), len(d2), int(cols), int(rows),
+                                            plf_grid_window(*[int(v) for v in w]), C.c_float(nnr), int(bool(best_lr)),
+                                            _ptr(m, C.c_int32), C.byref(cnt))
         self._check(st, "plf_match_grid_points")
         return m, cnt.value
 
-    def match_grid_lines(self, q_line, d1, t_line, t_dir, d2, cols, rows, w, nnr, line_sim_th, best_lr=True):
-        """stvo-pl matchGrid (lines): end-point cells int32 [n,4], directions2 f64 [n2,2]."""
-        q = np.ascontiguousarray(q_line, np.int32).reshape(-1, 4); t = np.ascontiguousarray(t_line, np.int32).reshape(-1, 4)
+    def match_grid_lines(self, q_line, d1, cell_start, cell_items, t_dir, d2, cols, rows, w, nnr, line_sim_th, best_lr=True):
+        """stvo-pl matchGrid (lines): q_line int32 [n1,4] end-point cells, grid as above, directions2 f64 [n2,2]."""
+        q = np.ascontiguousarray(q_line, np.int32).reshape(-1, 4)
+        cs = np.ascontiguousarray(cell_start, np.int32); ci = np.ascontiguousarray(cell_items, np.int32)
         td = np.ascontiguousarray(t_dir, np.float64).reshape(-1, 2)
         d1 = _u8(d1).reshape(-1, DESC_BYTES); d2 = _u8(d2).reshape(-1, DESC_BYTES)
         m = np.full(len(q), -1, np.int32)
         cnt = C.c_int(0)
-        st = self.lib.plf_match_grid_lines(self._ctx, _ptr(q, C.c_int), _ptr(d1, C.c_uint8), len(q), _ptr(t, C.c_int),
-                                           _ptr(td, C.c_double), _ptr(d2, C.c_uint8), len(t), int(cols), int(rows),
-                                           plf_grid_window(*[int(v) for v in w]), C.c_float(nnr), C.c_double(line_sim_th),
-                                           int(bool(best_lr)), _ptr(m, C.c_int32), C.byref(cnt))
+        st = self.lib.plf_match_grid_lines(self._ctx, _ptr(q, C.c_int), _ptr(d1, C.c_uint8), len(q), _ptr(cs, C.c_int),
+                                           _ptr(ci, C.c_int), _ptr(td, C.c_double), _ptr(d2, C.c_uint8), len(d2), int(cols),
+                                           int(rows), plf_grid_window(*[int(v) for v in w]), C.c_float(nnr),
+                                           C.c_double(line_sim_th), int(bool(best_lr)), _ptr(m, C.c_int32), C.byref(cnt))
         self._check(st, "plf_match_grid_lines")
         return m, cnt.value
 

@@ -25,8 +25,10 @@ def test_points_vs_oracle(fe, seed, n1, n2, ws, best_lr):
     q = np.stack([rng.integers(-2, COLS + 2, n1), rng.integers(-2, ROWS + 2, n1)], 1)
     t = np.stack([rng.integers(-1, COLS + 1, n2), rng.integers(-1, ROWS + 1, n2)], 1)
     w = (ws, ws, ws, ws)
-    ref, nref = mg.match_grid_points(q, d1, t, d2, COLS, ROWS, w, 0.9, best_lr)
-    got, ngot = fe.match_grid_points(q, d1, t, d2, COLS, ROWS, w, 0.9, best_lr)
+    grid = mg.grid_from_points(t, ROWS, COLS)
+    grid.push(3, 3, n2 + 5); grid.push(4, 4, -1)                  # stray indices are ignored (i2 < 0 || i2 >= desc2.rows)
+    ref, nref = mg.match_grid_points(q, d1, grid, d2, w, 0.9, best_lr)
+    got, ngot = fe.match_grid_points(q, d1, *grid.csr(), d2, COLS, ROWS, w, 0.9, best_lr)
     assert ngot == nref and np.array_equal(got, ref)
     assert nref > 0
 
@@ -49,8 +51,9 @@ def test_lines_vs_oracle(fe, best_lr):
     nrm = np.linalg.norm(td, axis=1, keepdims=True)
     td = np.where(nrm > 0, td / np.maximum(nrm, 1e-300), np.array([[1.0, 0.0]]))
     w = (1, 1, 1, 1)
-    ref, nref = mg.match_grid_lines(ql, d1, tl, td, d2, COLS, ROWS, w, 0.9, 0.75, best_lr)
-    got, ngot = fe.match_grid_lines(ql, d1, tl, td, d2, COLS, ROWS, w, 0.9, 0.75, best_lr)
+    grid = mg.grid_from_lines(tl, ROWS, COLS)
+    ref, nref = mg.match_grid_lines(ql, d1, grid, td, d2, w, 0.9, 0.75, best_lr)
+    got, ngot = fe.match_grid_lines(ql, d1, *grid.csr(), td, d2, COLS, ROWS, w, 0.9, 0.75, best_lr)
     assert ngot == nref and np.array_equal(got, ref)
     assert nref > 0
 
@@ -58,9 +61,13 @@ def test_lines_vs_oracle(fe, best_lr):
 def test_edge_cases(fe):
     rng = np.random.default_rng(0)
     d = rng.integers(0, 256, (5, 32), dtype=np.uint8)
-    m, n = fe.match_grid_points(np.zeros((0, 2)), d[:0], np.zeros((5, 2)), d, COLS, ROWS, (1, 1, 1, 1), 0.9)
+    g5 = mg.grid_from_points(np.zeros((5, 2)), ROWS, COLS).csr()
+    g0 = mg.Grid(ROWS, COLS).csr()
+    m, n = fe.match_grid_points(np.zeros((0, 2)), d[:0], *g5, d, COLS, ROWS, (1, 1, 1, 1), 0.9)
     assert len(m) == 0 and n == 0
-    m, n = fe.match_grid_points(np.zeros((5, 2)), d, np.zeros((0, 2)), d[:0], COLS, ROWS, (1, 1, 1, 1), 0.9)
+    m, n = fe.match_grid_points(np.zeros((5, 2)), d, *g0, d[:0], COLS, ROWS, (1, 1, 1, 1), 0.9)
+    assert list(m) == [-1] * 5 and n == 0
+    m, n = fe.match_grid_points(np.zeros((5, 2)), d, *g0, d, COLS, ROWS, (1, 1, 1, 1), 0.9)     # empty grid: no candidates
     assert list(m) == [-1] * 5 and n == 0
     with pytest.raises(plf.PlfError, match="bad arguments"):
-        fe.match_grid_points(np.zeros((5, 2)), d, np.zeros((5, 2)), d, 0, ROWS, (1, 1, 1, 1), 0.9)
+        fe.match_grid_points(np.zeros((5, 2)), d, *g5, d, 0, ROWS, (1, 1, 1, 1), 0.9)
