@@ -119,10 +119,9 @@ __global__ void __launch_bounds__(256) k_blur5_sobel_fast(const uint8_t* __restr
   const int lane = tid & 31, wrp = tid >> 5;
   const bool interior = x0 >= 3 && x0 - 3 + RP <= w && y0 >= 3 && y0 + LBF_TH + 3 <= h;
   if (interior) {  // four pixels per step (plf_load4)
-    const plf_span sp = plf_image_span(img, (size_t)pitch * h);
     for (int i = tid; i < RH * (RP / 4); i += 256) {
       const int ry = i / (RP / 4), j = i - ry * (RP / 4);
-      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4(img + (size_t)(y0 - 3 + ry) * pitch + (x0 - 3 + 4 * j), sp);
+      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4_fast(img + (size_t)(y0 - 3 + ry) * pitch + (x0 - 3 + 4 * j));
     }
   } else {
     for (int ry = wrp; ry < RH; ry += 8) {

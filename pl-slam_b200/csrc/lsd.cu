@@ -154,10 +154,9 @@ __global__ void __launch_bounds__(256) k_blur_q8_fast(const uint8_t* __restrict_
   const int lane = tid & 31, wrp = tid >> 5;
   const bool interior = x0 >= R && x0 + RP - R <= w && y0 >= R && y0 + BF_TH + R <= h;
   if (interior) {  // four pixels per step (plf_load4)
-    const plf_span sp = plf_image_span(s, (size_t)pitch * h);
     for (int i = tid; i < RH * (RP / 4); i += 256) {
       const int ry = i / (RP / 4), j = i - ry * (RP / 4);
-      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4(s + (size_t)(y0 - R + ry) * pitch + (x0 - R + 4 * j), sp);
+      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4_fast(s + (size_t)(y0 - R + ry) * pitch + (x0 - R + 4 * j));
     }
   } else {
     for (int ry = wrp; ry < RH; ry += 8) {

@@ -108,7 +108,6 @@ __global__ void __launch_bounds__(256) k_resize_exact4(const uint8_t* __restrict
   const int y = blockIdx.y * 4 + threadIdx.y;
   if (x >= dw || y >= dh) return;
   const uint8_t* s = src + (size_t)blockIdx.z * src_stride;
-  const plf_span sp = plf_image_span(s, (size_t)sw * sh);
   const int oy = taby[y], cy = taby[dh + y];
   int ox[4], cx[4];
 #pragma unroll
@@ -117,10 +116,12 @@ __global__ void __launch_bounds__(256) k_resize_exact4(const uint8_t* __restrict
     ox[i] = tabx[xi];
     cx[i] = tabx[dw + xi];
   }
+  // source bytes ox[0] .. ox[0]+7 of rows oy and oy+1.  The second row is clamped to the image (its weight cy is 0
+  // there), so every byte wanted lies inside the image or within 7 bytes of its end: unclamped loads (allocation slack).
   const uint8_t* r0 = s + (size_t)oy * sw + ox[0];
-  const uint8_t* r1 = r0 + sw;
-  const unsigned long long a = (unsigned long long)plf_load4(r0, sp) | ((unsigned long long)plf_load4(r0 + 4, sp) << 32);
-  const unsigned long long b = (unsigned long long)plf_load4(r1, sp) | ((unsigned long long)plf_load4(r1 + 4, sp) << 32);
+  const uint8_t* r1 = oy + 1 < sh ? r0 + sw : r0;
+  const unsigned long long a = (unsigned long long)plf_load4_fast(r0) | ((unsigned long long)plf_load4_fast(r0 + 4) << 32);
+  const unsigned long long b = (unsigned long long)plf_load4_fast(r1) | ((unsigned long long)plf_load4_fast(r1 + 4) << 32);
   uint8_t* d = dst + (size_t)blockIdx.z * dst_stride + (size_t)y * dw + x;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -201,7 +202,12 @@ __global__ void __launch_bounds__(256, 5) k_fast_nms(const uint8_t* __restrict__
   if (tid == 0) ccount = 0;
   // Stage the tile four pixels at a time (plf_load4).  Rows are clamped to the image; positions outside the image hold
   // arbitrary in-bounds data - they are never used by a valid score (gx in [3, W-3)).
-  {
+  if (x0 >= 4 && x0 + 68 <= W && y0 >= 4 && y0 + 34 <= H) {  // tile + halo inside the image: no clamps
+    for (int i = tid; i < 38 * 18; i += 256) {
+      const int ry = i / 18, j = i - ry * 18;
+      reinterpret_cast<uint32_t*>(&px[ry][0])[j] = plf_load4_fast(src + (size_t)(y0 - 4 + ry) * W + (x0 - 4 + 4 * j));
+    }
+  } else {
     const plf_span sp = plf_image_span(src, (size_t)W * H);
     for (int i = tid; i < 38 * 18; i += 256) {
       const int ry = i / 18, j = i - ry * 18;
@@ -522,10 +528,9 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const uint8_t* __restric
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   const bool interior = x0 >= 3 && x0 - 3 + RP <= W && y0 >= 3 && y0 + OBF_TH + 3 <= H;
   if (interior) {  // four pixels per step (plf_load4)
-    const plf_span sp = plf_image_span(src, (size_t)W * H);
     for (int i = tid; i < RH * (RP / 4); i += 256) {
       const int ry = i / (RP / 4), j = i - ry * (RP / 4);
-      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4(src + (size_t)(y0 - 3 + ry) * W + (x0 - 3 + 4 * j), sp);
+      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4_fast(src + (size_t)(y0 - 3 + ry) * W + (x0 - 3 + 4 * j));
     }
   } else {
     for (int ry = wrp; ry < RH; ry += 8) {
@@ -586,9 +591,9 @@ __global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur
                                                 const plf_keypoint* __restrict__ kps,
                                                 const int* __restrict__ kp_count, const int8_t* __restrict__ pattern,
                                                 uint8_t* __restrict__ desc) {
-  __shared__ int8_t pat[1024];
+  __shared__ __align__(16) int8_t pat[1024];
   __shared__ __align__(16) uint8_t patch[8][RB_D][RB_P];
-  for (int i = threadIdx.x; i < 1024; i += 256) pat[i] = pattern[i];
+  reinterpret_cast<uint32_t*>(pat)[threadIdx.x] = reinterpret_cast<const uint32_t*>(pattern)[threadIdx.x];  // 1024 B
   __syncthreads();
   const int img = blockIdx.y;
   const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -604,13 +609,12 @@ __global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur
   const uint8_t* base = blur + (size_t)img * g.blur_stride + g.blur_off[l] + (size_t)(cyi - RB_R) * W + (cxi - RB_R);
   uint8_t (*P)[RB_P] = patch[wrp];
   {  // 37 rows x 10 words, four pixels per load step (plf_load4): 12 steps per lane instead of 74 byte loads
-    const uint8_t* lvl = blur + (size_t)img * g.blur_stride + g.blur_off[l];
-    const plf_span sp = plf_image_span(lvl, (size_t)W * g.h[l]);
+    // (keypoints are >= 19 pixels inside the level: rows y-18 .. y+18 and columns x-18 .. x+21 are inside the image)
     uint32_t* Pw = reinterpret_cast<uint32_t*>(&P[0][0]);
 #pragma unroll 4
     for (int i = lane; i < RB_D * (RB_P / 4); i += 32) {
       const int r = i / (RB_P / 4), j = i - r * (RB_P / 4);
-      Pw[i] = plf_load4(base + (size_t)r * W + 4 * j, sp);
+      Pw[i] = plf_load4_fast(base + (size_t)r * W + 4 * j);
     }
   }
   __syncwarp();

@@ -179,4 +179,11 @@ __device__ __forceinline__ uint32_t plf_load4(const uint8_t* p, plf_span sp) {
   const uint32_t w0 = __ldg(reinterpret_cast<const uint32_t*>(a0)), w1 = __ldg(reinterpret_cast<const uint32_t*>(a1));
   return __funnelshift_r(w0, w1, 8 * (int)((uintptr_t)p & 3));
 }
+// The same without the clamps, for callers whose four bytes are known to lie inside the image: the two aligned words
+// then reach at most 3 bytes before the first / after the last of them, i.e. stay inside the image or - at its very end
+// - inside the 64 bytes of slack every image buffer is allocated with.
+__device__ __forceinline__ uint32_t plf_load4_fast(const uint8_t* p) {
+  const uint32_t* a = reinterpret_cast<const uint32_t*>((uintptr_t)p & ~(uintptr_t)3);
+  return __funnelshift_r(__ldg(a), __ldg(a + 1), 8 * (int)((uintptr_t)p & 3));
+}
 #endif
