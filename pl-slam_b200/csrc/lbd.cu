@@ -279,44 +279,46 @@ __global__ void __launch_bounds__(64, 12) k_lbd(const short2* __restrict__ grad,
     bandv[b][q] = acc;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  // Mean / standard deviation per band (:1253-1280), the two L2 normalisations (:1283-1315), the 0.4 clamp (:1322-1328)
+  // and the final L2 normalisation (:1331-1341).  The element-wise parts (36 sqrtf, scalings, clamp) run on all
+  // threads; only the three sums, whose f32 order is part of the result, stay sequential on thread 0.
+  __shared__ float s_scale[2];
+  {
     const float invN2 = (float)(1.0 / (LBD_WB * 2.0)), invN3 = (float)(1.0 / (LBD_WB * 3.0));
-    for (int b = 0; b < LBD_NB; ++b) {
+    for (int e = threadIdx.x; e < 36; e += 64) {   // e = band * 4 + q, q: pgdL, ngdL, pgdO, ngdO
+      const int b = e >> 2, q = e & 3;
       const float invN = (b == 0 || b == LBD_NB - 1) ? invN2 : invN3;
-      const int d = b * 8;
-      float t = __fmul_rn(bandv[b][0], invN);
-      des[d] = t;
-      des[d + 4] = sqrtf(__fsub_rn(__fmul_rn(bandv[b][2], invN), __fmul_rn(t, t)));
-      t = __fmul_rn(bandv[b][1], invN);
-      des[d + 1] = t;
-      des[d + 5] = sqrtf(__fsub_rn(__fmul_rn(bandv[b][3], invN), __fmul_rn(t, t)));
-      t = __fmul_rn(bandv[b][4], invN);
-      des[d + 2] = t;
-      des[d + 6] = sqrtf(__fsub_rn(__fmul_rn(bandv[b][6], invN), __fmul_rn(t, t)));
-      t = __fmul_rn(bandv[b][5], invN);
-      des[d + 3] = t;
-      des[d + 7] = sqrtf(__fsub_rn(__fmul_rn(bandv[b][7], invN), __fmul_rn(t, t)));
+      const int src = q < 2 ? q : q + 2;           // bandv column of the sum (0, 1, 4, 5); its square sum is at +2
+      const float t = __fmul_rn(bandv[b][src], invN);
+      des[b * 8 + q] = t;
+      des[b * 8 + 4 + q] = sqrtf(__fsub_rn(__fmul_rn(bandv[b][src + 2], invN), __fmul_rn(t, t)));
     }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     float tempM = 0.f, tempS = 0.f;
     for (int b = 0; b < LBD_NB; ++b) {
       const float* v = des + 8 * b;
       for (int k = 0; k < 4; ++k) tempM = __fadd_rn(tempM, __fmul_rn(v[k], v[k]));
       for (int k = 4; k < 8; ++k) tempS = __fadd_rn(tempS, __fmul_rn(v[k], v[k]));
     }
-    tempM = __fdiv_rn(1.0f, sqrtf(tempM));
-    tempS = __fdiv_rn(1.0f, sqrtf(tempS));
-    for (int b = 0; b < LBD_NB; ++b) {
-      float* v = des + 8 * b;
-      for (int k = 0; k < 4; ++k) v[k] = __fmul_rn(v[k], tempM);
-      for (int k = 4; k < 8; ++k) v[k] = __fmul_rn(v[k], tempS);
-    }
-    for (int i = 0; i < 72; ++i)
-      if ((double)des[i] > 0.4) des[i] = (float)0.4;
+    s_scale[0] = __fdiv_rn(1.0f, sqrtf(tempM));
+    s_scale[1] = __fdiv_rn(1.0f, sqrtf(tempS));
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 72; i += 64) {
+    float v = __fmul_rn(des[i], s_scale[(i & 7) < 4 ? 0 : 1]);
+    if ((double)v > 0.4) v = (float)0.4;
+    des[i] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     float t = 0.f;
     for (int i = 0; i < 72; ++i) t = __fadd_rn(t, __fmul_rn(des[i], des[i]));
-    t = __fdiv_rn(1.0f, sqrtf(t));
-    for (int i = 0; i < 72; ++i) des[i] = __fmul_rn(des[i], t);
+    s_scale[0] = __fdiv_rn(1.0f, sqrtf(t));
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 72; i += 64) des[i] = __fmul_rn(des[i], s_scale[0]);
   __syncthreads();
   uint8_t* o = desc + ((size_t)img * max_lines + li) * 32;
   if (threadIdx.x < 32) {

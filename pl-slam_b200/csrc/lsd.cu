@@ -265,32 +265,43 @@ __global__ void k_lsd_fill_guard(LsdPix* __restrict__ pix, size_t pix_stride, in
 }
 
 // pix points at pixel (0,0) of image 0 (i.e. past the guard); image stride pix_stride.
+// One thread produces the same column of TWO consecutive rows: 6 independent byte loads (3 source rows) and up to 2
+// table loads in flight per thread instead of a 4-load + 1-load chain per pixel, stores still coalesced row by row.
 __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int W, int H,
                                                   const LsdPix* __restrict__ lut, int m2_min, size_t stride,
                                                   short2* __restrict__ gxy, LsdPix* __restrict__ pix, size_t pix_stride,
                                                   int* __restrict__ maxmag2) {
-  const int x = blockIdx.x * 256 + threadIdx.x, y = blockIdx.y, im = blockIdx.z;
+  const int x = blockIdx.x * 256 + threadIdx.x, y0 = blockIdx.y * 2, im = blockIdx.z;
   int mag2 = -1;
   if (x < W) {
-    const int oi = y * W + x;
-    short2 g = make_short2(0, 0);
-    LsdPix e;
-    e.a = LSD_NOTDEF_F; e.c = 0.f; e.s = 0.f; e.pad = 0.f;
-    if (x < W - 1 && y < H - 1) {
-      const uint8_t* r0 = img + (size_t)im * img_stride + oi;
-      const uint8_t* r1 = r0 + W;
-      const int DA = (int)r1[1] - (int)r0[0], BC = (int)r0[1] - (int)r1[0];
-      const int gx = DA + BC, gy = DA - BC;
-      g = make_short2((short)gx, (short)gy);
-      const int m2 = gx * gx + gy * gy;
-      if (m2 >= m2_min) {  // defined level-line angle (~10 % of the pixels): only these touch the table
-        const float4 raw = __ldg(reinterpret_cast<const float4*>(&lut[(gx + 510) * LSD_LUT_DIM + (gy + 510)]));
-        e = *reinterpret_cast<const LsdPix*>(&raw);
-        mag2 = m2;
-      }
+    const uint8_t* p = img + (size_t)im * img_stride + (size_t)y0 * W + x;
+    const bool xin = x < W - 1, r0ok = xin && y0 < H - 1, r1ok = xin && y0 + 1 < H - 1;
+    int a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0;
+    if (r0ok) { a0 = p[0]; a1 = p[1]; b0 = p[W]; b1 = p[W + 1]; }
+    if (r1ok) { c0 = p[2 * W]; c1 = p[2 * W + 1]; }
+    short2 g[2] = {make_short2(0, 0), make_short2(0, 0)};
+    int li[2] = {-1, -1};
+    if (r0ok) {
+      const int DA = b1 - a0, BC = a1 - b0, gx = DA + BC, gy = DA - BC, m2 = gx * gx + gy * gy;
+      g[0] = make_short2((short)gx, (short)gy);
+      if (m2 >= m2_min) { li[0] = (gx + 510) * LSD_LUT_DIM + (gy + 510); mag2 = m2; }  // defined angle (~10 % of the pixels)
     }
-    gxy[(size_t)im * stride + oi] = g;
-    *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + oi]) = *reinterpret_cast<const float4*>(&e);
+    if (r1ok) {
+      const int DA = c1 - b0, BC = b1 - c0, gx = DA + BC, gy = DA - BC, m2 = gx * gx + gy * gy;
+      g[1] = make_short2((short)gx, (short)gy);
+      if (m2 >= m2_min) { li[1] = (gx + 510) * LSD_LUT_DIM + (gy + 510); mag2 = max(mag2, m2); }
+    }
+    float4 e[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      e[r] = li[r] >= 0 ? __ldg(reinterpret_cast<const float4*>(&lut[li[r]])) : make_float4(LSD_NOTDEF_F, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < 2; ++r)
+      if (y0 + r < H) {
+        const size_t oi = (size_t)(y0 + r) * W + x;
+        gxy[(size_t)im * stride + oi] = g[r];
+        *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + oi]) = e[r];
+      }
   }
   // per-image maximum: reduce in the CTA first, and only touch the (single, contended) address when it would grow
   __shared__ int s_max[8];
@@ -1040,7 +1051,7 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
     scaled_stride = As;
   }
   PLF_CUDA(ctx, cudaMemsetAsync(maxmag2, 0xFF, (size_t)n * sizeof(int), cs));  // -1
-  k_lsd_grad<<<dim3((W + 255) / 256, H, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->grad_lut, s->m2_min, As, gxy, pix, s->pix_stride, maxmag2);
+  k_lsd_grad<<<dim3((W + 255) / 256, (H + 1) / 2, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->grad_lut, s->m2_min, As, gxy, pix, s->pix_stride, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
   k_lsd_rowhist<<<dim3(nchunks, n), 256, 0, cs>>>(gxy, s->m2_min, As, W, H, s->n_bins, nchunks, maxmag2, binmap, rowcnt);
