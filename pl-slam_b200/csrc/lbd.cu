@@ -6,15 +6,18 @@
 // packing :401-412 over combinations :74-107).
 //
 // Kernels
-//   k_blur5_sobel  u8 image -> interleaved int16 (dx,dy) gradient map.  One 64x16 tile per CTA staged in
-//                  shared memory with a 3-pixel BORDER_REFLECT_101 halo; the 5x5 sigma-1 blur is OpenCV's
-//                  CV_8U fixed-point path (Q8.8 taps 14,62,104,62,14; one rounding), Sobel is exact integer.
-//                  HBM traffic: 1 B/px read + 4 B/px written (the algorithmic minimum for this stage).
+//   k_blur5_sobel_fast
+//                  u8 image -> interleaved int16 (dx,dy) gradient map.  One 64x32 tile per CTA staged by 32-bit words
+//                  in shared memory with a 3-pixel BORDER_REFLECT_101 halo; the 5x5 sigma-1 blur is OpenCV's
+//                  CV_8U fixed-point path (Q8.8 taps 14,62,104,62,14; DP4A row pass, one rounding), Sobel is exact
+//                  integer.  HBM traffic: 1 B/px read + 4 B/px written (the algorithmic minimum for this stage).
+//                  (k_blur5_sobel: generic variant for tiny images)
 //   k_lbd          one CTA (64 threads) per line.  Bit-exactness fixes the mapping: thread h
 //                  (0..62) replays the h row-steps of the LSR origin in f32, then walks its row serially with
 //                  the reference's repeated f32 additions and sequential f32 row sums; 72 threads-worth of band
-//                  accumulators are then evaluated in row order by the same threads; one thread finishes the
-//                  three normalisations and 32 byte-compares.  No tree/shuffle reductions on this path.
+//                  accumulators are then evaluated in row order by the same threads; the three normalisations keep their
+//                  sums sequential on one thread (their f32 order is part of the result) and run everything
+//                  element-wise on all threads; 32 byte-compares pack the bits.  No tree/shuffle reductions.
 // All float arithmetic is unfused (--fmad=false) in the reference's source order.
 #include "plf_internal.h"
 

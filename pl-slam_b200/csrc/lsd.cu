@@ -11,24 +11,27 @@
 // inside a bin) -> greedy region growing -> rectangle fit.  No NFA validation runs at refine 0.
 //
 // Kernels
-//   k_blur_q8        separable Q8.8 Gaussian (tile in shared memory), one rounding
-//   k_resize_exact   (orb.cu) INTER_LINEAR_EXACT resample to scale
-//   k_lsd_grad       2x2 gradient -> (gx,gy) int16 pair + level-line angle (cv::fastAtan2, degrees, f32) per pixel,
-//                    per-image max of |grad|^2
+//   k_blur_q8_fast   separable Q8.8 Gaussian (word-staged tile in shared memory, DP4A row pass), one rounding
+//                    (k_blur_q8: generic variant for tiny images)
+//   k_resize_exact4  (orb.cu) INTER_LINEAR_EXACT resample to scale
+//   k_lsd_grad       2x2 gradient -> (gx,gy) int16 pair + the 16-byte record {angle (cv::fastAtan2, degrees, f32),
+//                    cosf, sinf} fetched from a table keyed by (gx,gy); per-image max of |grad|^2
 //   k_lsd_rowhist / k_lsd_binscan / k_lsd_scatter
 //                    stable counting sort of the defined pixels by magnitude bin (descending), raster order inside a
 //                    bin == OpenCV's ordered_points
 //   k_lsd_grow       region growing.  The algorithm is a sequential greedy partition (each accepted pixel updates the
 //                    region angle that the next test uses, and regions compete through the `used` map), so it is run by
-//                    ONE WARP PER IMAGE with many images in flight: lanes 0..8 fetch the 3x3 neighbourhood of the
-//                    current region point in one memory round trip, the 9 alignment tests are then replayed in the
-//                    reference order; the seed scan looks 32 seeds ahead per round trip.  `used` is folded into the
-//                    angle map (a used pixel gets the NOTDEF sentinel; both are rejected identically).
-//   k_lsd_rects      one thread per region: weighted centroid, inertia-matrix angle, extent — sequential fp64 sums in
-//                    region order (bit-exact with the CPU loop)
+//                    ONE WARP PER IMAGE with thousands of images in flight: lanes 0..8 hold the 3x3 neighbourhood
+//                    records of the current region point (fetched two queue entries ahead, L1-resident through a
+//                    look-ahead prefetch), the alignment tests run lane-parallel in the reference order, and the
+//                    region angle is only evaluated when a decision depends on it (see the kernel's comment; bit-exact).
+//                    `used` is folded into the angle (a used pixel gets the NOTDEF sentinel).
+//   k_lsd_rect_order / k_lsd_rects
+//                    one thread per region, regions permuted into size classes: weighted centroid, inertia-matrix
+//                    angle, extent - sequential fp64 sums in region order (bit-exact with the CPU loop)
 //   k_keylines       clamp + length filter + KeyLine fill with ordered compaction, optional top-K by response
-// Roofline: gradient / ordering / blur stream each map once (HBM-bound when batched); region growing is
-// latency-bound by construction and is reported as time, not as a roofline fraction.
+// Roofline: the gradient kernel is bound by its HBM writes (4.7 TB/s); region growing is latency-bound by construction
+// and is reported as time, not as a roofline fraction; the rest in DESIGN.md §4.
 #include <float.h>
 
 #include "glibc_sincosf.cuh"
@@ -436,18 +439,6 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(const uint16_t* __restrict_
 }
 
 // ---- region growing ----------------------------------------------------------------------------------------
-__device__ __forceinline__ bool lsd_aligned(float a_deg, double theta, double prec) {
-  if (a_deg == LSD_NOTDEF) return false;
-  const double a = (double)a_deg * LSD_DEG2RAD;
-  double n_theta = theta - a;
-  if (n_theta < 0) n_theta = -n_theta;
-  if (n_theta > LSD_3_2_PI) {
-    n_theta -= LSD_2PI;
-    if (n_theta < 0) n_theta = -n_theta;
-  }
-  return n_theta <= prec;
-}
-
 __device__ __forceinline__ bool lsd_aligned_rad(double a, double theta, double prec) {
   double n_theta = theta - a;
   if (n_theta < 0) n_theta = -n_theta;

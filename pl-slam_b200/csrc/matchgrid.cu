@@ -30,13 +30,6 @@ __device__ __forceinline__ int mg_hamming(const uint4* a, const uint4* b) {
          __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
 }
 
-// GridStructure::get window around cell (cx, cy), clipped to the grid: is cell (x, y) - already known to be inside the
-// grid - returned?
-__device__ __forceinline__ bool mg_in_window(const MgGrid& g, int cx, int cy, int x, int y) {
-  return x >= max(0, cx - g.w_lo) && x < min(g.cols, cx + g.w_hi + 1) && y >= max(0, cy - g.h_lo) &&
-         y < min(g.rows, cy + g.h_hi + 1);
-}
-
 // 8-connected Bresenham walk over the cells of (x1,y1)-(x2,y2), end points included (used as a set).
 struct MgLine {
   bool steep; int x, x_end, y, dx, dy, err, ystep;

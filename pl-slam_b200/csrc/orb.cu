@@ -7,18 +7,22 @@
 // INTER_LINEAR_EXACT and the float sepFilter2D Gaussian), pinned integer-for-integer against cv2 4.13 by oracle/orb.c.
 //
 // Kernels (all gridded [tile or feature, image]; one launch covers every image of the batch)
-//   k_resize_exact   pyramid level l from level l-1: Q8.8 x Q8.8 bilinear, one rounding (bit-exact INTER_LINEAR_EXACT)
-//   k_fast_nms       FAST-9/16 corner score + 3x3 non-max suppression + border filter on a 64x16 tile staged in
-//                    shared memory (halo 4); survivors are appended to a per-(image,level) candidate list and a
-//                    256-bin response histogram
+//   k_resize_exact4  pyramid level l from level l-1: Q8.8 x Q8.8 bilinear, one rounding (bit-exact INTER_LINEAR_EXACT),
+//                    four outputs per thread from two unaligned 32-bit reads per source row (k_resize_exact: scalar
+//                    variant for scale factors above 1.9)
+//   k_fast_nms       FAST-9/16 corner score + 3x3 non-max suppression + border filter on a 62x30 tile staged in
+//                    shared memory by 32-bit words (halo 4): 4-pair rejection, survivors compacted, full ring + score
+//                    on dense warps; corners are appended to a per-(image,level) candidate list and a 256-bin
+//                    response histogram
 //   k_select_sort    KeyPointsFilter::retainBest: per-level response threshold from the histogram (n-th largest,
 //                    ties kept), compaction, in-shared-memory bitonic sort to the canonical (octave, y, x) order
 //   k_ic_angle       intensity-centroid orientation: integer moments over the 31-px circular patch, one warp per
 //                    keypoint, cv::fastAtan2 polynomial
-//   k_orb_blur7      7x7 sigma-2 Gaussian in float with FMA (OpenCV takes its sepFilter2D path for the pyramid ROI)
-//   k_rbrief         256 rotated pair tests, one warp per keypoint (lane = descriptor byte)
-// Roofline: every kernel streams u8 maps once (HBM-bound when batched); per-image algorithmic bytes are
-// A0 + 2*sum(A_k>=1) + 2*S + 56*N.
+//   k_orb_blur7_fast 7x7 sigma-2 Gaussian in float with FMA (OpenCV takes its sepFilter2D path for the pyramid ROI), 64x32
+//                    outputs per CTA, 4 per thread (k_orb_blur7: generic variant for tiny images)
+//   k_rbrief         256 rotated pair tests from a 37x37 shared-memory patch, one warp per keypoint (lane = byte)
+// Per-image algorithmic bytes are A0 + 2*sum(A_k>=1) + 2*S + 56*N; what bounds each kernel (issue rate,
+// latency - none is HBM-bound) is measured in profiles/r01_ncu_full_final_summary.txt and tabulated in DESIGN.md §4.
 #include "orb_pattern.h"
 #include "plf_internal.h"
 

@@ -214,11 +214,8 @@ plf_status plf_create(const plf_params* params, const plf_camera* cam, const plf
     return plf_fail(nullptr, PLF_ERR_NO_DEVICE, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
   ctx->cur = ctx->stream;
-  bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-  for (int i = 0; i < 5 && ok; ++i) {
-    ok = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess &&
-         cudaEventCreateWithFlags(&ctx->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
-  }
+  bool ok = true;
+  for (int i = 0; i < 2 && ok; ++i) ok = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess;
   if (!ok) {
     plf_destroy(ctx);
     return plf_fail(nullptr, PLF_ERR_NO_DEVICE, "plf_create: could not create auxiliary streams/events");
@@ -245,11 +242,8 @@ void plf_destroy(plf_ctx* ctx) {
     if (b.p) cudaFree(b.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
-  for (int i = 0; i < 5; ++i) {
+  for (int i = 0; i < 2; ++i)
     if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); }
-    if (ctx->ev_join[i]) cudaEventDestroy(ctx->ev_join[i]);
-  }
-  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
