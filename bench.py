@@ -75,7 +75,7 @@ def kernel_bytes(name, ab, n_kp, m_lines):
 
 
 def render_pool(cam, n, seed):
-    from oracle import synth
+    from plslam_b200 import synth      # input generator (not the oracle)
     world = synth.World(seed=7 + seed)
     return [(L, R) for (L, R, _) in synth.stream(cam, n, world=world, seed=42 + seed)]
 

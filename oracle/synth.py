@@ -1,173 +1,4 @@
-"""Seeded synthetic stereo imagery.  TEST / BENCH INFRASTRUCTURE ONLY.
-
-scene_pair(): the C1 "plumbing" pair — filled random-gray rectangles + thin lines on gray 90, 3x3
-sigma-0.8 blur, +-3 uniform noise, right image = left shifted by a constant disparity.
-Stream rendering (planted SE(3) trajectory through a 3-D world of textured quads and segments) is in
-world_* below.  Drawing uses cv2 (python OpenCV is part of the image on both the build container and
-the GPU box); everything is deterministic given the seed.
-"""
-import cv2
-import numpy as np
-
-
-def scene_pair(w=1242, h=375, seed=1, n_rect=220, n_lines=120, disparity=20, noise=3):
-    rng = np.random.default_rng(seed)
-    W = w + disparity
-    img = np.full((h, W), 90, np.uint8)
-    for _ in range(n_rect):
-        x0 = int(rng.integers(-40, W)); y0 = int(rng.integers(-40, h))
-        rw = int(rng.integers(12, 160)); rh = int(rng.integers(10, 110))
-        g = int(rng.integers(20, 236))
-        cv2.rectangle(img, (x0, y0), (x0 + rw, y0 + rh), g, -1)
-    for _ in range(n_lines):
-        p0 = (int(rng.integers(0, W)), int(rng.integers(0, h)))
-        ang = rng.uniform(0, np.pi); L = rng.uniform(30, 300)
-        p1 = (int(p0[0] + L * np.cos(ang)), int(p0[1] + L * np.sin(ang)))
-        cv2.line(img, p0, p1, int(rng.integers(0, 256)), int(rng.integers(1, 3)), cv2.LINE_8)
-    img = cv2.GaussianBlur(img, (3, 3), 0.8)
-    def noisy(a, r):
-        n = r.integers(-noise, noise + 1, a.shape)
-        return np.clip(a.astype(np.int16) + n, 0, 255).astype(np.uint8)
-    left = noisy(img[:, 0:w], rng)                       # x_left = x_right + disparity
-    right = noisy(img[:, disparity:disparity + w], rng)
-    return np.ascontiguousarray(left), np.ascontiguousarray(right)
-
-
-# ---- synthetic correspondences for the pose optimiser (planted pose) ---------------
-def project(cam, P):
-    P = np.asarray(P, np.float64)
-    return np.stack([cam["cx"] + cam["fx"] * P[:, 0] / P[:, 2], cam["cy"] + cam["fy"] * P[:, 1] / P[:, 2]], 1)
-
-
-def gn_problem(cam, n_pts=300, n_lines=80, seed=0, x_true=None, px_noise=0.3, outlier_frac=0.1):
-    """3-D points / segments in the previous camera frame + their observations in the current frame under a
-    planted increment T_true (current <- previous), with pixel noise and gross outliers."""
-    from oracle import clib
-    rng = np.random.default_rng(seed)
-    if x_true is None:
-        x_true = np.array([0.05, -0.02, 0.9, 0.01, -0.03, 0.005])
-    T = clib.expmap_se3(x_true)
-    def rand_pts(n):
-        z = rng.uniform(4, 40, n)
-        u = rng.uniform(30, cam["width"] - 30, n); v = rng.uniform(20, cam["height"] - 20, n)
-        return np.stack([(u - cam["cx"]) * z / cam["fx"], (v - cam["cy"]) * z / cam["fy"], z], 1)
-    P = rand_pts(n_pts)
-    Pc = P @ T[:3, :3].T + T[:3, 3]
-    obs = project(cam, Pc) + rng.normal(0, px_noise, (n_pts, 2))
-    n_out = int(outlier_frac * n_pts)
-    obs[:n_out] += rng.uniform(-60, 60, (n_out, 2))
-    sP = rand_pts(n_lines)
-    eP = sP + rng.normal(0, 1.0, (n_lines, 3)) * np.array([1.5, 1.0, 0.5])
-    eP[:, 2] = np.maximum(eP[:, 2], 2.0)
-    sp = project(cam, sP @ T[:3, :3].T + T[:3, 3]) + rng.normal(0, px_noise, (n_lines, 2))
-    ep = project(cam, eP @ T[:3, :3].T + T[:3, 3]) + rng.normal(0, px_noise, (n_lines, 2))
-    n_outl = int(outlier_frac * n_lines)
-    sp[:n_outl] += rng.uniform(-40, 40, (n_outl, 2))
-    sph = np.concatenate([sp, np.ones((n_lines, 1))], 1); eph = np.concatenate([ep, np.ones((n_lines, 1))], 1)
-    le = np.cross(sph, eph)
-    le = le / np.sqrt(le[:, 0:1] ** 2 + le[:, 1:2] ** 2)      # le = (sp x ep) / ||(le0, le1)||  
-    return dict(P=P, obs=obs, sP=sP, eP=eP, le=le, T_true=T, x_true=np.asarray(x_true, np.float64))
-
-
-# ---- synthetic stereo streams with a planted SE(3) trajectory ------------------------------
-class World:
-    """Fronto-parallel textured quads (random-checker albedo) + 3-D line segments along a corridor in +z."""
-
-    def __init__(self, seed=7, length=120.0, n_quads=260, n_segs=140, albedo_sigma=60.0, cells=4,
-                 half_width=14.0, half_height=4.5):
-        rng = np.random.default_rng(seed)
-        self.quads = []   # (centre xyz, half sizes, cell grays [cells x cells])
-        for _ in range(n_quads):
-            z = rng.uniform(4.0, length)
-            side = rng.choice([-1.0, 1.0])
-            x = side * rng.uniform(1.2, half_width)
-            y = rng.uniform(-half_height, half_height * 0.6)
-            hw, hh = rng.uniform(0.4, 2.2), rng.uniform(0.3, 1.6)
-            base = rng.uniform(40, 215)
-            g = np.clip(base + rng.normal(0, albedo_sigma, (cells, cells)), 5, 250)
-            self.quads.append((np.array([x, y, z]), hw, hh, g))
-        self.segs = []
-        for _ in range(n_segs):
-            z = rng.uniform(4.0, length)
-            x = rng.uniform(-half_width, half_width); y = rng.uniform(-half_height, half_height)
-            d = rng.normal(0, 1, 3) * np.array([2.0, 1.2, 0.3])
-            self.segs.append((np.array([x, y, z]), np.array([x, y, z]) + d, float(rng.uniform(10, 245)), int(rng.integers(1, 3))))
-        self.cells = cells
-
-
-def _project(cam, Pc):
-    return np.stack([cam["cx"] + cam["fx"] * Pc[:, 0] / Pc[:, 2], cam["cy"] + cam["fy"] * Pc[:, 1] / Pc[:, 2]], 1)
-
-
-def render_view(world, cam, T_cw, x_offset=0.0, noise_rng=None, noise=3, bg=90):
-    """Renders one camera view. T_cw: camera <- world (4x4). x_offset: camera-frame x shift (right eye = +b)."""
-    w, h = cam["width"], cam["height"]
-    img = np.full((h, w), bg, np.uint8)
-    R, t = T_cw[:3, :3], T_cw[:3, 3].copy()
-    t[0] -= x_offset
-    items = []
-    for (c, hw, hh, g) in world.quads:
-        zc = (R @ c + t)[2]
-        if 1.0 < zc < 90.0:
-            items.append((zc, 0, (c, hw, hh, g)))
-    for (a, b, gray, th) in world.segs:
-        za, zb = (R @ a + t)[2], (R @ b + t)[2]
-        if za > 1.0 and zb > 1.0 and min(za, zb) < 90.0:
-            items.append((max(za, zb), 1, (a, b, gray, th)))
-    items.sort(key=lambda it: -it[0])     # painter's algorithm: far to near
-    SH = 4
-    for _, kind, it in items:
-        if kind == 0:
-            c, hw, hh, g = it
-            n = g.shape[0]
-            xs = np.linspace(-hw, hw, n + 1); ys = np.linspace(-hh, hh, n + 1)
-            gx, gy = np.meshgrid(xs, ys)
-            Pw = np.stack([c[0] + gx.ravel(), c[1] + gy.ravel(), np.full(gx.size, c[2])], 1)
-            Pc = Pw @ R.T + t
-            if (Pc[:, 2] < 0.5).any():
-                continue
-            uv = _project(cam, Pc).reshape(n + 1, n + 1, 2)
-            if uv[..., 0].max() < -50 or uv[..., 0].min() > w + 50 or uv[..., 1].max() < -50 or uv[..., 1].min() > h + 50:
-                continue
-            for i in range(n):
-                for j in range(n):
-                    poly = np.array([uv[i, j], uv[i, j + 1], uv[i + 1, j + 1], uv[i + 1, j]])
-                    cv2.fillConvexPoly(img, np.round(poly * (1 << SH)).astype(np.int32), int(g[i, j]), cv2.LINE_AA, SH)
-        else:
-            a, b, gray, th = it
-            Pc = np.stack([a, b]) @ R.T + t
-            uv = _project(cam, Pc)
-            if np.abs(uv).max() > 1e5:
-                continue
-            p0 = tuple(int(v) for v in np.round(uv[0] * (1 << SH))); p1 = tuple(int(v) for v in np.round(uv[1] * (1 << SH)))
-            cv2.line(img, p0, p1, int(gray), th, cv2.LINE_AA, SH)
-    img = cv2.GaussianBlur(img, (3, 3), 0.8)
-    if noise_rng is not None and noise > 0:
-        img = np.clip(img.astype(np.int16) + noise_rng.integers(-noise, noise + 1, img.shape), 0, 255).astype(np.uint8)
-    return img
-
-
-def trajectory(n_frames, seed=42, step=0.4, yaw_deg=0.6, lateral=0.02):
-    """Planted camera poses T_wc (world <- camera): forward motion with small yaw / lateral jitter."""
-    from oracle import clib
-    rng = np.random.default_rng(seed)
-    T = np.eye(4)
-    out = [T.copy()]
-    for _ in range(n_frames - 1):
-        x = np.array([rng.normal(0, lateral), rng.normal(0, lateral * 0.5), step * rng.uniform(0.8, 1.2),
-                      np.deg2rad(rng.normal(0, yaw_deg * 0.3)), np.deg2rad(rng.normal(0, yaw_deg)), np.deg2rad(rng.normal(0, yaw_deg * 0.2))])
-        T = T @ clib.expmap_se3(x)
-        out.append(T.copy())
-    return out
-
-
-def stream(cam, n_frames, world=None, seed=42, traj=None, noise=3, **traj_kw):
-    """Yields (left, right, T_wc) for a planted trajectory.  Right camera is offset by the baseline along +x."""
-    world = world or World()
-    traj = traj or trajectory(n_frames, seed=seed, **traj_kw)
-    rng = np.random.default_rng(seed + 1000)
-    for T_wc in traj:
-        T_cw = np.linalg.inv(T_wc)
-        L = render_view(world, cam, T_cw, 0.0, rng, noise)
-        Rr = render_view(world, cam, T_cw, cam["b"], rng, noise)
-        yield L, Rr, T_wc
+"""The synthetic-input generator moved to the package (pl-slam_b200/plslam_b200/synth.py): it is data generation, not
+part of the oracle.  Kept as an alias for the tests that import it from here."""
+from plslam_b200.synth import *  # noqa: F401,F403
+from plslam_b200.synth import World, expmap_se3, gn_problem, project, render_view, scene_pair, stream, trajectory  # noqa: F401
