@@ -57,21 +57,55 @@ def _extract_one(idx):
     return ofe.extract_stereo(cam, L, R, prm, orb_fn, lines_fn, match_cv2)
 
 
+class Workers:
+    """A pool of worker processes (fork) that outlives one run(): forking and joining 128 processes costs seconds, which
+    must not be charged to every timed step of the baseline."""
+
+    def __init__(self, cam, pairs, prm=None, threads=None, cv_threads=1):
+        import multiprocessing as mp
+
+        import cv2
+        self.prm = dict(ofe.DEFAULTS, **(prm or {}))
+        self.threads = max(1, min(threads or os.cpu_count() or 1, len(pairs)))
+        cv2.setNumThreads(cv_threads)
+        _G.update(cam=cam, pairs=pairs, prm=self.prm)   # inherited by the forked workers
+        self.cam, self.pairs = cam, pairs
+        self.pool = mp.get_context("fork").Pool(self.threads) if self.threads > 1 else None
+
+    def extract(self, n=None):
+        idx = range(len(self.pairs) if n is None else n)
+        if self.pool is None:
+            return [_extract_one(i) for i in idx]
+        return self.pool.map(_extract_one, idx, chunksize=1)
+
+    def run(self, n=None):
+        """One pass over the first n pairs as one sequence: extraction + stereo association spread over the workers,
+        then frame-to-frame tracking and pose refinement sequentially, as the reference's loop does."""
+        import time
+        t0 = time.perf_counter()
+        frames = self.extract(n)
+        t1 = time.perf_counter()
+        pairs = self.pairs if n is None else self.pairs[:n]
+        res = ofe.run_sequence(self.cam, pairs, self.prm, match_fn=match_cv2, frames=frames)
+        self.last_split = (t1 - t0, time.perf_counter() - t1)   # (parallel extraction, sequential tracking + pose) seconds
+        return res
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.close()
+            self.pool.join()
+            self.pool = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
 def run(cam, pairs, prm=None, threads=None, cv_threads=1):
     """Processes the stereo pairs as one sequence.  Extraction + stereo association of the frames are independent
     and are spread over `threads` worker processes (fork; default = all host cores); frame-to-frame tracking and
     the pose refinement then run sequentially, as the reference's loop does.  Returns (results, cores used)."""
-    import multiprocessing as mp
-
-    import cv2
-    prm = dict(ofe.DEFAULTS, **(prm or {}))
-    threads = max(1, min(threads or os.cpu_count() or 1, len(pairs)))
-    cv2.setNumThreads(cv_threads)
-    _G.update(cam=cam, pairs=pairs, prm=prm)
-    if threads <= 1:
-        frames = [_extract_one(i) for i in range(len(pairs))]
-    else:
-        with mp.get_context("fork").Pool(threads) as pool:
-            frames = pool.map(_extract_one, range(len(pairs)), chunksize=1)
-    res = ofe.run_sequence(cam, pairs, prm, match_fn=match_cv2, frames=frames)
-    return res, threads
+    with Workers(cam, pairs, prm, threads, cv_threads) as w:
+        return w.run(), w.threads
