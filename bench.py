@@ -166,7 +166,7 @@ def run_reference(args, rank):
     if rank != 0:
         return
     from oracle import baseline
-    cores = os.cpu_count() or 1
+    cores = baseline.effective_cores()     # affinity mask capped by the cgroup CPU quota, if any
     n = max(8, min(4 * cores, 512))        # bounded sample per step: a few waves over all cores
     pool = render_pool(CAM, min(n, 24), seed=0)
     pairs = [pool[i % len(pool)] for i in range(n)]
@@ -184,8 +184,9 @@ def run_reference(args, rank):
                 ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="u8/f32/f64",
                 data="synthetic", impl="reference",
                 config=dict(workload=WORKLOAD, pairs_per_step=n, **PRM),
-                cpu_baseline=dict(value=v, unit=UNIT, cores=cores, kind="port",
-                                  sample=f"{n} pairs/step x {args.steps} steps: cv2 4.13 ORB+LSD+BFMatcher + C LBD/GN, {cores} worker processes"),
+                cpu_baseline=dict(value=v, unit=UNIT, cores=w.threads, kind="port", host_cpus=os.cpu_count(),
+                                  sample=f"{n} pairs/step x {args.steps} steps: cv2 4.13 ORB+LSD+BFMatcher + C LBD/GN, {w.threads} worker processes"
+                                         f" ({os.cpu_count()} CPUs visible); last step {w.last_split[0]:.2f} s extraction + {w.last_split[1]:.2f} s sequential tracking/pose"),
                 e2e=dict(value=v, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     emit(line)
 
@@ -391,11 +392,11 @@ def main():
         if overlapped:
             line["kernels_overlapped"] = overlapped
         if world == 1 and not args.no_cpu_baseline:
-            cores = os.cpu_count() or 1
-            n = max(8, min(2 * cores, 64))
-            v, c, dt = cpu_baseline_run(min(n, 24) if n <= 24 else 24, None)
-            line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=c, kind="port",
-                                        sample="%d rendered pairs of the same stream, one pass (%.1f s): cv2 4.13 ORB+LSD+BFMatcher + C LBD/GN, %d worker processes" % (min(n, 24), dt, c))
+            n_cpu = 48                         # ~12 s of single-core CPU work (0.25 s per pair)
+            v, c, dt = cpu_baseline_run(n_cpu, None)
+            line["cpu_baseline"] = dict(value=v, unit=UNIT, cores=c, kind="port", host_cpus=os.cpu_count(),
+                                        sample="%d rendered pairs of the same stream, one pass (%.1f s): cv2 4.13 ORB+LSD+BFMatcher + C LBD/GN, "
+                                               "%d worker processes (%d CPUs visible)" % (n_cpu, dt, c, os.cpu_count()))
         emit(line)
     fe.close()
     if dist is not None:

@@ -57,6 +57,31 @@ def _extract_one(idx):
     return ofe.extract_stereo(cam, L, R, prm, orb_fn, lines_fn, match_cv2)
 
 
+def effective_cores():
+    """Host cores this process can actually use: the affinity mask, capped by a cgroup CPU quota when there is one (a
+    GPU slot of a shared box shows all of the node's CPUs in os.cpu_count() but is scheduled on a fraction of them)."""
+    try:
+        n = len(os.sched_getaffinity(0))
+    except Exception:
+        n = os.cpu_count() or 1
+    quota = None
+    try:                                                    # cgroup v2
+        q, p = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            quota = float(q) / float(p)
+    except Exception:
+        try:                                                # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            p = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0 and p > 0:
+                quota = q / p
+        except Exception:
+            pass
+    if quota is not None:
+        n = max(1, min(n, int(quota + 0.5)))
+    return n
+
+
 def _worker_init(cv_threads):
     """One thread per worker process: without this every numpy / BLAS call inside 128 workers starts its own 128-thread
     pool (measured on the 64-core box: 2.9 s per pair and process instead of 0.25 s)."""
@@ -80,7 +105,7 @@ class Workers:
 
         import cv2
         self.prm = dict(ofe.DEFAULTS, **(prm or {}))
-        self.threads = max(1, min(threads or os.cpu_count() or 1, len(pairs)))
+        self.threads = max(1, min(threads or effective_cores(), len(pairs)))
         cv2.setNumThreads(cv_threads)
         _G.update(cam=cam, pairs=pairs, prm=self.prm)   # inherited by the forked workers
         self.cam, self.pairs = cam, pairs
