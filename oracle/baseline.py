@@ -82,20 +82,6 @@ def effective_cores():
     return n
 
 
-def _worker_init(cv_threads):
-    """One thread per worker process: without this every numpy / BLAS call inside 128 workers starts its own 128-thread
-    pool (measured on the 64-core box: 2.9 s per pair and process instead of 0.25 s)."""
-    import cv2
-    cv2.setNumThreads(cv_threads)
-    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
-        os.environ[k] = "1"
-    try:
-        from threadpoolctl import threadpool_limits
-        _G["_tp"] = threadpool_limits(limits=1)     # kept alive for the life of the worker
-    except Exception:
-        pass
-
-
 class Workers:
     """A pool of worker processes (fork) that outlives one run(): forking and joining 128 processes costs seconds, which
     must not be charged to every timed step of the baseline."""
@@ -106,10 +92,10 @@ class Workers:
         import cv2
         self.prm = dict(ofe.DEFAULTS, **(prm or {}))
         self.threads = max(1, min(threads or effective_cores(), len(pairs)))
-        cv2.setNumThreads(cv_threads)
-        _G.update(cam=cam, pairs=pairs, prm=self.prm)   # inherited by the forked workers
+        cv2.setNumThreads(cv_threads)                   # one OpenCV thread per worker (inherited by the fork); measured on the
+        _G.update(cam=cam, pairs=pairs, prm=self.prm)   # box, BLAS / OpenMP thread limits make no difference to this path
         self.cam, self.pairs = cam, pairs
-        self.pool = mp.get_context("fork").Pool(self.threads, initializer=_worker_init, initargs=(cv_threads,)) if self.threads > 1 else None
+        self.pool = mp.get_context("fork").Pool(self.threads) if self.threads > 1 else None
 
     def extract(self, n=None):
         idx = range(len(self.pairs) if n is None else n)
