@@ -23,7 +23,13 @@
  *   - sqrt resolves to std::sqrt(float) (cv namespace has `using std::sqrt`), so 1/sqrt(x) is a
  *     float division.
  * The reference itself is built with -O3 -march=native (CMakeLists.txt:27), i.e. its FMA behaviour
- * depends on the build host; parity for this piece is against this restatement ("parity unpinned").
+ * depends on the build host.
+ * PINNED: the vendored sources themselves are compiled, unmodified, into oracle/_ref/liblinedesc_ref.so
+ * (oracle/ref_build/, -ffp-contract=off) and tests/test_refbin_pin.py checks orc_lbd_compute bit-for-bit
+ * against BinaryDescriptor::compute, and orc_keylines_from_segments field-for-field against
+ * LSDDetectorC::detect.  One difference was found that way and is kept on purpose until the CUDA side can
+ * follow: in the C++ build the KeyLine angle `atan2(float, float)` resolves to glibc's atan2f, not to the
+ * f64 atan2 rounded to f32 used here (1 ulp apart on ~10 % of the lines).
  */
 #include <math.h>
 #include <stdint.h>

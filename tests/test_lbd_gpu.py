@@ -71,3 +71,17 @@ def test_lbd_edge_cases(fe):
     flat = np.full((120, 160), 77, np.uint8)
     d = fe.lbd(flat, kl)
     assert np.array_equal(d, clib.lbd_compute(flat, kl)) and (d == 0).all()
+
+
+def test_lbd_equals_vendored_reference_code(fe):
+    """CUDA LBD vs the reference's own BinaryDescriptor::compute (vendored sources compiled unmodified into
+    oracle/_ref/liblinedesc_ref.so, see oracle/refbin.py): bit-exact descriptors."""
+    from oracle import refbin
+    if not refbin.available():
+        pytest.skip("oracle/_ref/liblinedesc_ref.so not present")
+    L, R = synth.scene_pair()
+    for img in (L, R):
+        kl = clib.keylines_from_segments(clib.lsd(img), 1242, 375, 0.025 * 375)
+        kl["class_id"] = np.arange(len(kl), dtype=np.int32)
+        assert len(kl) > 300
+        assert np.array_equal(fe.lbd(img, kl), refbin.lbd(img, kl))
