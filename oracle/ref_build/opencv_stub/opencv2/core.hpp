@@ -356,7 +356,14 @@ inline Mat operator/(const Mat&, double) { plf_stub_abort("Mat / s"); }
 inline void add(InputArray, InputArray, OutputArray, InputArray = _InputArray(), int = -1) { plf_stub_abort("cv::add"); }
 inline void compare(InputArray, InputArray, OutputArray, int) { plf_stub_abort("cv::compare"); }
 inline double norm(InputArray, int = NORM_L2, InputArray = _InputArray()) { plf_stub_abort("cv::norm"); }
-inline double norm(InputArray, InputArray, int = NORM_L2, InputArray = _InputArray()) { plf_stub_abort("cv::norm"); }
+inline double norm(InputArray a_, InputArray b_, int type = NORM_L2, InputArray = _InputArray()) {
+  Mat a = a_.getMat(), b = b_.getMat();   // functional for what src/mapFeatures.cpp:63,133 calls: NORM_HAMMING on CV_8U rows
+  if (type != NORM_HAMMING || a.depth() != CV_8U || a.type() != b.type() || a.rows != b.rows || a.cols != b.cols) plf_stub_abort("cv::norm (only NORM_HAMMING on CV_8U)");
+  int d = 0;
+  for (int r = 0; r < a.rows; ++r)
+    for (int c = 0; c < a.cols * a.channels(); ++c) d += __builtin_popcount((unsigned)(a.ptr(r)[c] ^ b.ptr(r)[c]));
+  return (double)d;
+}
 inline int countNonZero(InputArray) { plf_stub_abort("cv::countNonZero"); }
 }  // namespace cv
 #endif

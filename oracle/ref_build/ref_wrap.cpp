@@ -7,6 +7,7 @@
 // restatements of oracle/*.c, so what these functions add over the oracle is exactly the vendored code.
 #include <vector>
 
+#include "precomp_custom.hpp"   // (brings in bitops_custom.hpp: the reference's own popcount distance, :83-96)
 #include "line_descriptor_custom.hpp"
 extern "C" {
 #include "oracle.h"
@@ -69,4 +70,9 @@ extern "C" int ref_lbd(const uint8_t* img, int w, int h, const orc_keyline* kls,
     fprintf(stderr, "ref_lbd: %s\n", e.what());
     return -1;
   }
+}
+
+// cv::line_descriptor::match(P, Q, codelb): the Hamming primitive of the reference (src/bitops_custom.hpp:83-96)
+extern "C" int ref_hamming(const uint8_t* p, const uint8_t* q, int nbytes) {
+  return cv::line_descriptor::match((UINT8*)p, (UINT8*)q, nbytes);
 }

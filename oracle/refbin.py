@@ -1,5 +1,6 @@
 """TEST INFRASTRUCTURE.  ctypes access to oracle/_ref/liblinedesc_ref.so: the reference's own vendored
-3rdparty/line_descriptor (LSDDetectorC::detect, BinaryDescriptor::compute), compiled UNMODIFIED from /root/reference by
+3rdparty/line_descriptor (LSDDetectorC::detect, BinaryDescriptor::compute) and src/mapFeatures.cpp (MapPoint), compiled
+UNMODIFIED from /root/reference by
 oracle/ref_build/Makefile against a stand-in for the OpenCV API whose primitives on this path are the cv2-pinned
 restatements of oracle/*.c.  Used only to pin oracle/lbd.c (KeyLine stage + LBD) against the shipped reference code.
 The library is built where /root/reference exists and travels to the GPU box; available() is False otherwise."""
@@ -44,6 +45,26 @@ def lib():
         _lib.ref_keylines.restype = C.c_int
         _lib.ref_lbd.restype = C.c_int
     return _lib
+
+
+def hamming(a, b):
+    """cv::line_descriptor::match(P, Q, codelb) of the vendored bitops_custom.hpp:83-96."""
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return int(lib().ref_hamming(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), a.size))
+
+
+def median_descriptor(desc, dirs):
+    """PLSLAM::MapPoint (src/mapFeatures.cpp) fed the observations one by one: (index of the observation whose
+    descriptor is med_desc, med_obs_dir under the stand-in's zero-initialised accumulator)."""
+    desc = np.ascontiguousarray(desc, np.uint8).reshape(-1, 32)
+    dirs = np.ascontiguousarray(dirs, np.float64).reshape(-1, 3)
+    idx = C.c_int(-1)
+    md = np.zeros(3, np.float64)
+    r = lib().ref_median_descriptor(desc.ctypes.data_as(C.c_void_p), len(desc), dirs.ctypes.data_as(C.c_void_p), C.byref(idx),
+                                    md.ctypes.data_as(C.c_void_p))
+    if r != 0:
+        raise RuntimeError("ref_median_descriptor failed")
+    return idx.value, md
 
 
 def keylines(img, scale_arg=1, num_octaves=1, refine=0, scale=1.2, sigma_scale=0.6, quant=2.0, ang_th=22.5, log_eps=1.0,

@@ -54,3 +54,40 @@ def test_keyline_stage_equals_vendored_lsd_detector():
         assert np.array_equal(mine["angle"], np.arctan2(dy.astype(np.float64), dx.astype(np.float64)).astype(np.float32))
         ulp = np.abs(ref["angle"].view(np.int32).astype(np.int64) - mine["angle"].view(np.int32).astype(np.int64))
         assert ulp.max() <= 1 and 0 < (ulp > 0).mean() < 0.3
+
+
+def test_median_descriptor_equals_reference_mappoint():
+    """PLSLAM::MapPoint::updateAverageDescDir (src/mapFeatures.cpp:51-93, compiled unmodified) picks the same
+    observation as oracle/mapfeatures.py for every landmark, ties included."""
+    from oracle import mapfeatures as mf
+    rng = np.random.default_rng(5)
+    for trial in range(300):
+        n = int(rng.integers(2, 40))
+        if trial % 3 == 0:      # few distinct descriptors: many equal distances and equal medians
+            base = rng.integers(0, 256, (3, 32), dtype=np.uint8)
+            desc = base[rng.integers(0, 3, n)]
+        else:                   # noisy copies of one descriptor
+            proto = rng.integers(0, 256, 32, dtype=np.uint8)
+            desc = (proto[None, :] ^ np.packbits(rng.random((n, 256)) < 0.08, axis=1)).astype(np.uint8)
+        dirs = rng.normal(0, 1, (n, 3))
+        ri, rd = refbin.median_descriptor(desc, dirs)
+        oi, od = mf.median_descriptor(desc, dirs)
+        assert ri == oi, (trial, n)
+        assert np.array_equal(rd, od)      # (under the stand-in's zero-initialised accumulator, see eigen_stub)
+
+
+def test_hamming_primitive_equals_reference_bitops():
+    """oracle/matching.py's distance == cv::line_descriptor::match (src/bitops_custom.hpp:83-96) on 32-byte rows and
+    on lengths that exercise its byte-LUT tail."""
+    from oracle import matching as om
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 256, (200, 32), dtype=np.uint8); b = rng.integers(0, 256, (200, 32), dtype=np.uint8)
+    d = om.hamming_matrix(a, b) if hasattr(om, "hamming_matrix") else None
+    for i in range(200):
+        ref = refbin.hamming(a[i], b[i])
+        assert ref == int(np.unpackbits(a[i] ^ b[i]).sum())
+        if d is not None:
+            assert ref == int(d[i, i])
+    for n in (1, 7, 16, 17, 31, 33):
+        x = rng.integers(0, 256, n, dtype=np.uint8); y = rng.integers(0, 256, n, dtype=np.uint8)
+        assert refbin.hamming(x, y) == int(np.unpackbits(x ^ y).sum())
