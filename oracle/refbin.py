@@ -53,6 +53,14 @@ def hamming(a, b):
     return int(lib().ref_hamming(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), a.size))
 
 
+def forb_distance(a, b):
+    """DBoW2::FORB::distance (3rdparty/DBoW2/src/DBoW2/FORB.cpp:78-101) on two 32-byte rows."""
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    f = lib().ref_forb_distance
+    f.restype = C.c_double
+    return float(f(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)))
+
+
 def median_descriptor(desc, dirs):
     """PLSLAM::MapPoint (src/mapFeatures.cpp) fed the observations one by one: (index of the observation whose
     descriptor is med_desc, med_obs_dir under the stand-in's zero-initialised accumulator)."""

@@ -88,6 +88,7 @@ def test_hamming_primitive_equals_reference_bitops():
         assert ref == int(np.unpackbits(a[i] ^ b[i]).sum())
         if d is not None:
             assert ref == int(d[i, i])
+        assert refbin.forb_distance(a[i], b[i]) == ref          # DBoW2::FORB::distance agrees as well
     for n in (1, 7, 16, 17, 31, 33):
         x = rng.integers(0, 256, n, dtype=np.uint8); y = rng.integers(0, 256, n, dtype=np.uint8)
         assert refbin.hamming(x, y) == int(np.unpackbits(x ^ y).sum())
