@@ -117,45 +117,53 @@ def sequential(ang, order):
     return out, steps
 
 
-def speculative(ang, order, M):
+def speculative(ang, order, M, R=None):
+    """M workers, a reorder buffer of R >= M regions (a worker that finishes a region leaves it in the buffer until it
+    can commit and starts the next one)."""
+    R = R or M
     H, W = len(ang), len(ang[0])
     used = [[False] * W for _ in range(H)]
-    rob, out = [], []
+    rob, out = [], []                      # rob entries: [region, non_speculative]
     nxt, ticks, work, retries, dropped = 0, 0, 0, 0, 0
     seed_owner = {}
     while True:
-        # dispatch: fill the window with the next seeds that are unused in the committed map
-        while len(rob) < M and nxt < len(order):
+        # dispatch: fill the buffer with the next seeds that are unused in the committed map
+        while len(rob) < R and nxt < len(order):
             s = order[nxt]
             if not used[s[1]][s[0]]:
-                R = Region(nxt, s, ang); rob.append([R, False]); seed_owner[s] = nxt    # [region, non_speculative]
+                rob.append([Region(nxt, s, ang), False]); seed_owner[s] = nxt
             nxt += 1
         if not rob:
             break
         ticks += 1
-        for ent in rob:
-            R = ent[0]
-            if not R.done():
-                R.step(ang, used, W, H, None if ent[1] else seed_owner); work += 1
+        busy = 0
+        for ent in rob:                    # the M oldest unfinished regions run this tick
+            Rg = ent[0]
+            if not Rg.done():
+                Rg.step(ang, used, W, H, None if ent[1] else seed_owner); work += 1
+                busy += 1
+                if busy == M:
+                    break
         # in-order commit
         while rob and rob[0][0].done():
-            R, exact = rob[0]
-            if used[R.seed[1]][R.seed[0]]:
-                rob.pop(0); seed_owner.pop(R.seed, None); dropped += 1
+            Rg, exact = rob[0]
+            if used[Rg.seed[1]][Rg.seed[0]]:
+                rob.pop(0); seed_owner.pop(Rg.seed, None); dropped += 1
                 continue
-            if not exact and (R.aborted or any(used[y][x] for (x, y) in R.pts)):
+            if not exact and (Rg.aborted or any(used[y][x] for (x, y) in Rg.pts)):
                 retries += 1
-                rob[0] = [Region(R.k, R.seed, ang), True]      # every earlier region is committed: this run is exact
+                rob[0] = [Region(Rg.k, Rg.seed, ang), True]     # every earlier region is committed: this run is exact
                 break
-            for (x, y) in R.pts:
+            for (x, y) in Rg.pts:
                 used[y][x] = True
-            out.append((R.k, R.pts)); rob.pop(0); seed_owner.pop(R.seed, None)
+            out.append((Rg.k, Rg.pts)); rob.pop(0); seed_owner.pop(Rg.seed, None)
     return out, dict(ticks=ticks, work=work, retries=retries, dropped=dropped)
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workers", default="4,8,16,32,64")
+    ap.add_argument("--rob", type=int, default=1, help="reorder-buffer entries per worker")
     ap.add_argument("--scale", type=float, default=1.2)
     ap.add_argument("--crop", default="", help="w,h crop of the bench frame (the pure-Python simulation is slow)")
     args = ap.parse_args()
@@ -172,9 +180,9 @@ def main():
     sizes = sorted((len(p) for _, p in ref), reverse=True)
     print(f"image {L.shape[1]}x{L.shape[0]}: {len(order)} seeds, {len(ref)} regions, sequential chain {seq_steps} region points; largest regions {sizes[:5]}")
     for M in (int(v) for v in args.workers.split(",")):
-        out, st = speculative(ang, order, M)
+        out, st = speculative(ang, order, M, M * args.rob)
         ok = out == ref
-        print(f"M={M:3d}: identical={ok}  makespan {st['ticks']} steps (x{seq_steps / st['ticks']:.2f} vs sequential), work {st['work']} (x{st['work'] / seq_steps:.2f}), "
+        print(f"M={M:3d} (buffer {M * args.rob}): identical={ok}  makespan {st['ticks']} steps (x{seq_steps / st['ticks']:.2f} vs sequential), work {st['work']} (x{st['work'] / seq_steps:.2f}), "
               f"re-executions {st['retries']}, dropped duplicates {st['dropped']}")
         assert ok, "speculative result differs from the sequential one"
 
