@@ -8,7 +8,51 @@
 
 #include "stvo_shim.h"
 
+// The fast-matching branch of MapHandler::matchKF2KFPoints / matchKF2KFLines (src/mapHandler.cpp:251-271, :382-418)
+// written against the shim: grid filled with grid.at(x, y).push_back(idx), GridWindow of +-ws cells, matchGrid.
+// `vo_demo --grid-selftest` runs it on the features of one synthetic frame against themselves (every feature must then
+// find itself) - a build-time check that the overloads instantiate and a usage example for INTEGRATION.md.
+static int grid_selftest(StVO::StereoFrameHandler* h, const StVO::StereoFrame* fr, float nnr) {
+  using namespace StVO;
+  const double inv_w = GRID_COLS / (double)fr->cam->getWidth(), inv_h = GRID_ROWS / (double)fr->cam->getHeight();
+  std::vector<point_2d> pj_points;
+  GridStructure grid(GRID_ROWS, GRID_COLS);
+  for (size_t idx = 0; idx < fr->stereo_pt.size(); ++idx) {
+    const PointFeature* pt = fr->stereo_pt[idx];
+    pj_points.push_back(std::make_pair((int)(pt->pl[0] * inv_w), (int)(pt->pl[1] * inv_h)));
+    grid.at((int)(pt->pl[0] * inv_w), (int)(pt->pl[1] * inv_h)).push_back((int)idx);
+  }
+  GridWindow w;
+  w.width = std::make_pair(1, 1);
+  w.height = std::make_pair(1, 1);
+  std::vector<int> m12;
+  const int np = matchGrid(h->ctx(), pj_points, fr->pdesc_l, grid, fr->pdesc_l, w, m12, nnr);
+  int self = 0;
+  for (size_t i = 0; i < m12.size(); ++i) self += m12[i] == (int)i;
+  std::vector<line_2d> pj_lines;
+  std::vector<std::pair<double, double>> directions(fr->stereo_ls.size());
+  GridStructure lgrid(GRID_ROWS, GRID_COLS);
+  std::list<point_2d> cells;
+  for (size_t idx = 0; idx < fr->stereo_ls.size(); ++idx) {
+    const LineFeature* ls = fr->stereo_ls[idx];
+    std::pair<double, double>& v = directions[idx];
+    v = std::make_pair((ls->epl[0] - ls->spl[0]) * inv_w, (ls->epl[1] - ls->spl[1]) * inv_h);
+    normalize(v);
+    getLineCoords(ls->spl[0] * inv_w, ls->spl[1] * inv_h, ls->epl[0] * inv_w, ls->epl[1] * inv_h, cells);
+    for (const point_2d& p : cells) lgrid.at(p.first, p.second).push_back((int)idx);
+    pj_lines.push_back(std::make_pair(std::make_pair((int)(ls->spl[0] * inv_w), (int)(ls->spl[1] * inv_h)),
+                                      std::make_pair((int)(ls->epl[0] * inv_w), (int)(ls->epl[1] * inv_h))));
+  }
+  std::vector<int> l12;
+  const int nl = matchGrid(h->ctx(), pj_lines, fr->ldesc_l, lgrid, fr->ldesc_l, directions, w, l12, nnr, 0.75);
+  std::printf("grid-selftest points %zu matched %d self %d lines %zu matched %d\n", fr->stereo_pt.size(), np, self,
+              fr->stereo_ls.size(), nl);
+  return 0;
+}
+
 int main(int argc, char** argv) {
+  bool grid_test = false;
+  if (argc >= 2 && std::string(argv[argc - 1]) == "--grid-selftest") { grid_test = true; --argc; }
   if (argc < 2) {
     std::fprintf(stderr, "usage: %s frames.bin [orb_nfeatures lsd_nfeatures]\n", argv[0]);
     return 1;
@@ -34,6 +78,7 @@ int main(int argc, char** argv) {
       if (frame_counter == 0) {
         StVO_->initialize(img_l, img_r, 0);                                             // app:115
         cur = StVO_->prev_frame;
+        if (grid_test) return grid_selftest(StVO_, cur, prm.min_ratio_12_p);
       } else {
         StVO_->insertStereoPair(img_l, img_r, frame_counter);                           // app:127
         StVO_->optimizePose();                                                          // app:128
