@@ -376,8 +376,9 @@ def main():
                         frac=round(dom["algo_gbs"] / peak, 5), traffic=traffic, peak_source=peak_src,
                         note=("share of step %.0f%%; region growing is a sequential greedy partition per image: latency-bound, "
                               "reported against HBM for completeness" % (100 * dom["share"])) if "grow" in dom["kernel"] else None)
-        whole = dict(algorithmic_bytes_per_pair=ab["pair"], achieved_gbs=round(ab["pair"] * value / 1e9, 1),
-                     frac_hbm=round(ab["pair"] * value / 1e9 / peak, 4))
+        # PER-GPU figures: `value` is the whole-job aggregate over `world` ranks, the peak is one GPU's
+        whole = dict(algorithmic_bytes_per_pair=ab["pair"], per="gpu", achieved_gbs=round(ab["pair"] * value / world / 1e9, 1),
+                     frac_hbm=round(ab["pair"] * value / world / 1e9 / peak, 4))
         line = dict(metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
                     ms_per_step=dev_ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype="u8/f32/f64", data="synthetic",

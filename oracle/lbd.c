@@ -18,8 +18,9 @@
  *
  * Floating-point conventions mirrored (compile with -ffp-contract=off):
  *   - float expressions are evaluated in float in source order, no FMA contraction;
- *   - cos/sin/atan2/round resolve to the double C functions (the translation unit only includes
- *     <cmath>; the float argument is promoted) and the result is narrowed on assignment;
+ *   - cos/sin/round resolve to the double C functions (the translation unit only includes
+ *     <cmath>; the float argument is promoted) and the result is narrowed on assignment; the KeyLine
+ *     angle's atan2(float, float) resolves to the float overload, i.e. glibc's atan2f;
  *   - sqrt resolves to std::sqrt(float) (cv namespace has `using std::sqrt`), so 1/sqrt(x) is a
  *     float division.
  * The reference itself is built with -O3 -march=native (CMakeLists.txt:27), i.e. its FMA behaviour
@@ -27,9 +28,8 @@
  * PINNED: the vendored sources themselves are compiled, unmodified, into oracle/_ref/liblinedesc_ref.so
  * (oracle/ref_build/, -ffp-contract=off) and tests/test_refbin_pin.py checks orc_lbd_compute bit-for-bit
  * against BinaryDescriptor::compute, and orc_keylines_from_segments field-for-field against
- * LSDDetectorC::detect.  One difference was found that way and is kept on purpose until the CUDA side can
- * follow: in the C++ build the KeyLine angle `atan2(float, float)` resolves to glibc's atan2f, not to the
- * f64 atan2 rounded to f32 used here (1 ulp apart on ~10 % of the lines).
+ * LSDDetectorC::detect - every field, including `angle` (glibc atan2f; the CUDA kernel carries a bit-exact
+ * port of it, pl-slam_b200/csrc/glibc_atan2f.cuh).
  */
 #include <math.h>
 #include <stdint.h>
@@ -311,7 +311,9 @@ int orc_keylines_from_segments(const float* segs, int m, int w, int h, double mi
     int x1 = cv_round_f(e[0]), y1 = cv_round_f(e[1]), x2 = cv_round_f(e[2]), y2 = cv_round_f(e[3]);
     int adx = abs(x2 - x1), ady = abs(y2 - y1);
     kl.numOfPixels = (adx > ady ? adx : ady) + 1;
-    kl.angle = (float)atan2((double)(kl.endPointY - kl.startPointY), (double)(kl.endPointX - kl.startPointX));
+    /* `atan2(float, float)` at :286 resolves to the float overload = glibc atan2f in the reference's C++ build
+     * (established by compiling the vendored source, oracle/ref_build; tests/test_refbin_pin.py) */
+    kl.angle = atan2f(kl.endPointY - kl.startPointY, kl.endPointX - kl.startPointX);
     kl.class_id = ++class_counter;
     kl.octave = 0;
     kl.size = (kl.endPointX - kl.startPointX) * (kl.endPointY - kl.startPointY);

@@ -91,6 +91,10 @@ inline double det6(Matrix6d a) {  // LU with partial pivoting
 
 }  // namespace plf
 
+// stvo-pl gridStructure.h [UPSTREAM-RECALL, SURVEY A.2]: 48 x 64 matching grid
+#define STVO_GRID_ROWS 48
+#define STVO_GRID_COLS 64
+
 namespace StVO {
 
 using plf::Matrix4d;
@@ -162,8 +166,10 @@ class StereoFrame {
  public:
   StereoFrame(const plf::Image& img_l_, const plf::Image& img_r_, int idx, PinholeStereoCamera* cam_)
       : frame_idx(idx), img_l(img_l_), img_r(img_r_), cam(cam_) {
-    inv_width = 1.0 / cam->getWidth();
-    inv_height = 1.0 / cam->getHeight();
+    // grid-cell scales, as the reference uses them (src/mapHandler.cpp:256,263,404-408: `pl(0) * curr_frame->inv_width`
+    // feeds GridStructure::at / matchGrid): stvo-pl sets GRID_COLS / width and GRID_ROWS / height  [UPSTREAM-RECALL]
+    inv_width = STVO_GRID_COLS / static_cast<double>(cam->getWidth());
+    inv_height = STVO_GRID_ROWS / static_cast<double>(cam->getHeight());
   }
   ~StereoFrame() {
     for (auto* p : stereo_pt) delete p;
@@ -402,8 +408,8 @@ inline int match(plf_ctx* ctx, const DescMat& d1, const DescMat& d2, float nnr, 
 // (src/mapHandler.cpp:251-271 points, :382-418 lines; also :580-591, :686-706).  Cell coordinates are ints: callers scale
 // pixels by inv_width = GRID_COLS / width, inv_height = GRID_ROWS / height and the pair<double,double> -> pair<int,int>
 // conversion truncates.  [UPSTREAM-RECALL]: restated from SURVEY Appendix A.3, see oracle/matchgrid.py.
-#define GRID_ROWS 48
-#define GRID_COLS 36
+#define GRID_ROWS STVO_GRID_ROWS
+#define GRID_COLS STVO_GRID_COLS
 typedef std::pair<int, int> point_2d;
 typedef std::pair<point_2d, point_2d> line_2d;
 

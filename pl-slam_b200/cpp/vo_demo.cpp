@@ -14,7 +14,7 @@
 // find itself) - a build-time check that the overloads instantiate and a usage example for INTEGRATION.md.
 static int grid_selftest(StVO::StereoFrameHandler* h, const StVO::StereoFrame* fr, float nnr) {
   using namespace StVO;
-  const double inv_w = GRID_COLS / (double)fr->cam->getWidth(), inv_h = GRID_ROWS / (double)fr->cam->getHeight();
+  const double inv_w = fr->inv_width, inv_h = fr->inv_height;  // = GRID_COLS / width, GRID_ROWS / height
   std::vector<point_2d> pj_points;
   GridStructure grid(GRID_ROWS, GRID_COLS);
   for (size_t idx = 0; idx < fr->stereo_pt.size(); ++idx) {

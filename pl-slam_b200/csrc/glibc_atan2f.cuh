@@ -3,11 +3,12 @@
 // --fmad=false) and for the host (gcc -ffp-contract=off).
 //
 // Why: compiling the reference's vendored LSDDetector_custom.cpp (oracle/ref_build) showed that the KeyLine angle
-// `atan2(endY - startY, endX - startX)` on float operands (:286) resolves to atan2f in the C++ build, while
-// k_keylines and oracle/lbd.c compute the f64 atan2 and narrow it (1 ulp apart on ~10 % of the lines).  CUDA's
+// `atan2(endY - startY, endX - startX)` on float operands (:286) resolves to atan2f in the C++ build, which is 1 ulp
+// away from the narrowed f64 atan2 on ~10 % of the lines (what round 1 computed).  CUDA's
 // atan2f is not glibc's, so bit-exactness needs this port.  It is verified bit-for-bit against libm on the host
-// (tests/test_glibc_atan2f_port.py; 60 M inputs offline); it is NOT yet wired into k_keylines - that switch has to be
-// validated on a GPU together with the oracle's switch to atan2f.
+// (tests/test_glibc_atan2f_port.py; 60 M inputs offline) and is what k_keylines (lsd.cu) calls; the oracle's
+// orc_keylines_from_segments calls the host libm atan2f, and tests/test_refbin_pin.py requires every KeyLine field of
+// the oracle to equal the reference's own compiled LSDDetector_custom.cpp.
 #pragma once
 #ifdef __CUDACC__
 #define PLF_LIBM_FN __device__ __forceinline__

@@ -34,6 +34,7 @@
 // and is reported as time, not as a roofline fraction; the rest in DESIGN.md §4.
 #include <float.h>
 
+#include "glibc_atan2f.cuh"
 #include "glibc_sincosf.cuh"
 #include "plf_internal.h"
 
@@ -780,7 +781,8 @@ __global__ void __launch_bounds__(1024) k_keylines(const float4* __restrict__ se
         kl.lineLength = (float)length;
         const int x1 = __float2int_rn(e.x), y1 = __float2int_rn(e.y), x2 = __float2int_rn(e.z), y2 = __float2int_rn(e.w);
         kl.numOfPixels = max(abs(x2 - x1), abs(y2 - y1)) + 1;  // LineIterator(8-connected).count
-        kl.angle = (float)atan2((double)__fsub_rn(kl.endPointY, kl.startPointY), (double)__fsub_rn(kl.endPointX, kl.startPointX));
+        // atan2(float, float) at LSDDetector_custom.cpp:286 is glibc's atan2f in the reference build (bit-exact port)
+        kl.angle = glibc_atan2f(__fsub_rn(kl.endPointY, kl.startPointY), __fsub_rn(kl.endPointX, kl.startPointX));
         kl.octave = 0;
         kl.size = __fmul_rn(__fsub_rn(kl.endPointX, kl.startPointX), __fsub_rn(kl.endPointY, kl.startPointY));
         kl.response = __fdiv_rn(kl.lineLength, (float)max(w, h));

@@ -52,6 +52,7 @@ struct PipeState {
   plf_frame_result* results = nullptr;                  // [B] device
   plf_frame_result* h_results[3] = {nullptr, nullptr, nullptr};  // pinned host mirrors, ring of PIPE_DEPTH (filled at the end of M)
   int* h_ovf[3] = {nullptr, nullptr, nullptr};                   // pinned overflow flags {orb, lsd}
+  int* d_ovf = nullptr;         // [3][2] per-batch snapshots of the two global overflow flags (taken at the end of E and G)
   // Batches are software-pipelined over three streams: E (extract: ORB, LSD pre-grow, LBD prelude) -> G (LSD region
   // growing, latency-bound) -> M (LBD, stereo, tracking, pose).  Buffers that cross E -> G -> M exist per batch parity.
   // M starts with the LBD kernel and a device copy of the (small) extraction outputs it still needs, then records evX:
@@ -408,6 +409,7 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PA(s->gnP, (size_t)B * K * 3); PA(s->gnObs, (size_t)B * K * 2); PA(s->gnInlP, (size_t)B * K); PA(s->gnNp, B);
   PA(s->gn_sP, (size_t)B * Ln * 3); PA(s->gn_eP, (size_t)B * Ln * 3); PA(s->gn_le, (size_t)B * Ln * 3); PA(s->gnInlL, (size_t)B * Ln); PA(s->gnNl, B);
   PA(s->gn_probs, B); PA(s->gn_out, B); PA(s->results, B);
+  PA(s->d_ovf, 6);
 #undef PA
   for (int i = 0; i < 3; ++i) {
     PLF_CUDA(ctx, cudaHostAlloc(&s->h_results[i], sizeof(plf_frame_result) * B, cudaHostAllocDefault));
@@ -585,6 +587,10 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   if (!st) st = plf_launch_blur5_sobel(ctx, imgs, w, A, w, h, 2 * B, s->lbd_grad[par], A);
   if (st) { ctx->cur = sM; return st; }
   plf_mark(ctx, "lbd.k_blur5_sobel");
+  // this batch's ORB overflow flag: snapshot + clear on the E stream, so that a flag raised by batch i+1's extraction is
+  // not reported on batch i's download
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->d_ovf + 2 * rp, plf_orb_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToDevice, sE));
+  PLF_CUDA(ctx, cudaMemsetAsync(plf_orb_overflow_flag(ctx), 0, sizeof(int), sE));
   PLF_CUDA(ctx, cudaEventRecord(s->evE[par], sE));
   PLF_CUDA(ctx, cudaEventRecord(s->ev_free[run_slot], sE));  // the image buffer may be overwritten by the next upload
 
@@ -603,6 +609,8 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   st = plf_lsd_grow_range(ctx, w, h, 0, 0, 2 * B);
   ctx->lsd_keylines_wait = nullptr;
   if (st) { ctx->cur = sM; return st; }
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->d_ovf + 2 * rp + 1, plf_lsd_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToDevice, sG));
+  PLF_CUDA(ctx, cudaMemsetAsync(plf_lsd_overflow_flag(ctx), 0, sizeof(int), sG));
   PLF_CUDA(ctx, cudaEventRecord(s->evG[par], sG));
 
   // ---- M phase: LBD, stereo association, frame-to-frame tracking, pose (needs the previous batch's M phase) ----
@@ -634,7 +642,9 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
     PLF_CUDA(ctx, cudaMemsetAsync(s->rev_flags, 0, 2 * (size_t)B * K * sizeof(int), cs));
     PLF_CUDA(ctx, cudaMemsetAsync(s->rev_count, 0, 2 * (size_t)B * sizeof(int), cs));
     if ((st = plf_launch_nnr_mark(ctx, s->nnr_stereo, 2 * B, std::max(K, Ln), s->rev_flags, s->rev_list, s->rev_count, K))) return st;
-    if ((st = plf_launch_knn2(ctx, s->knn_stereo + 2 * B, 2 * B, std::max(K, Ln)))) return st;
+    // the reverse problems are laid out after the forward problems of ALL max_batch pairs (pipe_prepare), not of this
+    // call's B pairs: a partial batch (B < max_batch) must still start at 2 * max_batch
+    if ((st = plf_launch_knn2(ctx, s->knn_stereo + 2 * s->B, 2 * B, std::max(K, Ln)))) return st;
   }
   plf_mark(ctx, "stereo.k_hamming_knn2");
   if ((st = plf_launch_nnr(ctx, s->nnr_stereo, 2 * B, std::max(K, Ln)))) return st;
@@ -662,8 +672,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   plf_mark(ctx, "k_finalize+carry");
   // results + overflow flags to pinned memory as part of this batch's stream work; evM marks them ready
   PLF_CUDA(ctx, cudaMemcpyAsync(s->h_results[rp], s->results, sizeof(plf_frame_result) * B, cudaMemcpyDeviceToHost, cs));
-  PLF_CUDA(ctx, cudaMemcpyAsync(&s->h_ovf[rp][0], plf_orb_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, cs));
-  PLF_CUDA(ctx, cudaMemcpyAsync(&s->h_ovf[rp][1], plf_lsd_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->h_ovf[rp], s->d_ovf + 2 * rp, 2 * sizeof(int), cudaMemcpyDeviceToHost, cs));
   PLF_CUDA(ctx, cudaEventRecord(s->evM[rp], cs));
   s->has_prev = true;
   s->pend_slot[s->n_pending] = rp;
@@ -689,8 +698,6 @@ plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out) {
   memcpy(out, s->h_results[par], sizeof(plf_frame_result) * B);
   if (s->h_ovf[par][0] || s->h_ovf[par][1]) {
     const int o0 = s->h_ovf[par][0], o1 = s->h_ovf[par][1];
-    cudaMemsetAsync(plf_orb_overflow_flag(ctx), 0, sizeof(int), ctx->stream);
-    cudaMemsetAsync(plf_lsd_overflow_flag(ctx), 0, sizeof(int), ctx->stream);
     return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_batch_download: a fixed-capacity buffer overflowed (%s%s); raise plf_limits",
                     o0 ? "ORB keypoints " : "", o1 ? "LSD segments/lines" : "");
   }

@@ -85,3 +85,31 @@ def test_lbd_equals_vendored_reference_code(fe):
         kl["class_id"] = np.arange(len(kl), dtype=np.int32)
         assert len(kl) > 300
         assert np.array_equal(fe.lbd(img, kl), refbin.lbd(img, kl))
+
+
+def test_cuda_lines_end_to_end_equal_vendored_reference_code(built):
+    """The whole CUDA line path (LSD -> KeyLine stage -> LBD, one call: plf_detect_lines) against the reference's own
+    LSDDetectorC::detect + BinaryDescriptor::compute compiled unmodified (oracle/_ref): every KeyLine field - `angle`
+    (glibc atan2f, LSDDetector_custom.cpp:286) included - and every descriptor bit, end to end, nothing of the oracle's
+    restatement in between."""
+    import plslam_b200 as plf
+    from oracle import refbin
+    if not refbin.available():
+        pytest.skip("oracle/_ref/liblinedesc_ref.so not present")
+    L, R = synth.scene_pair()
+    E = synth.scene_pair(w=752, h=480, seed=9)[0]
+    S = next(iter(synth.stream(plf.KITTI_CAMERA, 1, world=synth.World(seed=7), seed=42)))[1]
+    n_ulp = 0
+    for img in (L, R, E, S):
+        h, w = img.shape
+        cam = dict(plf.KITTI_CAMERA, width=w, height=h)
+        with plf.Frontend(camera=cam, lsd_nfeatures=0) as fe:          # keep every line, detection order
+            kl, desc = fe.detect_lines(img)
+        ref_kl = refbin.keylines(img, min_length=float(np.float32(0.025)) * min(w, h))
+        assert len(kl) == len(ref_kl) > 150
+        for f in ref_kl.dtype.names:
+            assert np.array_equal(kl[f].view(np.int32), ref_kl[f].view(np.int32)), f
+        assert np.array_equal(desc, refbin.lbd(img, ref_kl))
+        dy = ref_kl["endPointY"] - ref_kl["startPointY"]; dx = ref_kl["endPointX"] - ref_kl["startPointX"]
+        n_ulp += int((ref_kl["angle"] != np.arctan2(dy.astype(np.float64), dx.astype(np.float64)).astype(np.float32)).sum())
+    assert n_ulp > 0      # the lines do include cases where atan2f and the narrowed f64 atan2 differ

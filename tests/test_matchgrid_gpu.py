@@ -6,7 +6,7 @@ import plslam_b200 as plf
 from oracle import matchgrid as mg
 
 pytestmark = pytest.mark.gpu
-COLS, ROWS = 36, 48
+COLS, ROWS = 64, 48   # stvo-pl GRID_COLS x GRID_ROWS
 
 
 def _descs(rng, n, protos=None, flip=0.1):

@@ -1,0 +1,129 @@
+"""GPU parity tests of the batched front-end in the MEASURED configuration: full-resolution frames,
+large batches (B >= 32), hundreds of frames, three batches in flight - features and matches bit-equal, pose within 1e-4
+on the se(3) log against oracle/frontend.py; and partial batches (B < max_batch)."""
+import multiprocessing as mp
+import os
+
+import numpy as np
+import pytest
+
+import plslam_b200 as plf
+from oracle import clib, synth
+from oracle import frontend as ofe
+from test_pipeline_gpu import check_frame, compare, corridor_world, rel, POSE_REL_TOL
+
+pytestmark = pytest.mark.gpu
+
+_G = {}
+
+
+def _extract(i):
+    L, R, _ = _G["frames"][i]
+    return ofe.extract_stereo(_G["cam"], L, R, _G["prm"])
+
+
+def oracle_sequence(cam, frames, prm):
+    """oracle/frontend.py over the whole stream; the per-frame extraction (independent) is spread over the host cores."""
+    prm = dict(ofe.DEFAULTS, **prm)
+    _G.update(cam=cam, frames=frames, prm=prm)
+    ncpu = max(1, min(len(os.sched_getaffinity(0)), 32, len(frames)))
+    if ncpu > 1:
+        with mp.get_context("fork").Pool(ncpu) as pool:
+            ex = pool.map(_extract, range(len(frames)), chunksize=1)
+    else:
+        ex = [_extract(i) for i in range(len(frames))]
+    return ofe.run_sequence(cam, [(a, b) for a, b, _ in frames], prm, frames=ex)
+
+
+def gpu_sequential(cam, frames, B, max_batch, **kw):
+    lim = plf.default_limits(); lim.max_batch = max_batch
+    got, feats = [], []
+    with plf.Frontend(camera=cam, limits=lim, **kw) as fe:
+        for s0 in range(0, len(frames), B):
+            chunk = frames[s0:s0 + B]
+            got += fe.process_batch(np.stack([c[0] for c in chunk]), np.stack([c[1] for c in chunk]))
+            feats += [fe.get_frame(k) for k in range(len(chunk))]
+    return got, feats
+
+
+def gpu_pipelined(cam, frames, B, depth, **kw):
+    """run, run, run, download, run, ... : `depth` batches in flight."""
+    lim = plf.default_limits(); lim.max_batch = B
+    out, inflight = [], []
+    with plf.Frontend(camera=cam, limits=lim, **kw) as fe:
+        for s0 in range(0, len(frames), B):
+            chunk = frames[s0:s0 + B]
+            fe.batch_upload(np.stack([c[0] for c in chunk]), np.stack([c[1] for c in chunk]))
+            fe.batch_run(len(chunk))
+            inflight.append(len(chunk))
+            if len(inflight) == depth:
+                out += list(fe.batch_download_array(inflight.pop(0)))
+        while inflight:
+            out += list(fe.batch_download_array(inflight.pop(0)))
+    return out
+
+
+def assert_same_results(seq, piped):
+    assert len(seq) == len(piped)
+    for k, (a, b) in enumerate(zip(seq, piped)):
+        for f in plf.RESULT_FIELDS:
+            assert a[f] == b[f], (k, f)
+        assert np.array_equal(a["DT"], b["DT"]) and np.array_equal(a["DT_cov"], b["DT_cov"]), k
+
+
+def test_partial_batches_match_oracle(built):
+    """max_batch = 4 but calls of 3 and 2 pairs (the last chunk of any sequence is such a call): the reverse (R->L)
+    stereo problems must be found at their max_batch-based offset (pipeline.cu)."""
+    cam = dict(plf.KITTI_CAMERA, width=640, height=360, cx=320.0, cy=180.0, fx=500.0, fy=500.0)
+    world = synth.World(seed=4, length=50.0, n_quads=160, n_segs=80, half_width=8.0, half_height=3.5)
+    frames = list(synth.stream(cam, 5, world=world, seed=11, step=0.15))
+    prm = dict(orb_nfeatures=700, lsd_nfeatures=150)
+    ref = oracle_sequence(cam, frames, prm)
+    got, feats = gpu_sequential(cam, frames, 3, 4, **prm)
+    compare(ref, got, feats)
+    assert any(r["status"] == 0 and len(r["res"]["inlier_pt"]) > 50 for r in ref)
+
+
+def test_bench_configuration_large_batches_in_flight(built):
+    """The bench's own regime: 1242x375, orb 1500 / lsd 200, B = 64, 192 frames.  (1) sequential calls: every frame's
+    stereo features bit-equal to the oracle, matches / inliers equal, pose <= 1e-4; (2) the same stream with three
+    batches in flight: results bit-identical to (1)."""
+    cam = plf.KITTI_CAMERA
+    frames = list(synth.stream(cam, 192))
+    prm = dict(orb_nfeatures=1500, lsd_nfeatures=200)
+    ref = oracle_sequence(cam, frames, prm)
+    got, feats = gpu_sequential(cam, frames, 64, 64, **prm)
+    compare(ref, got, feats)
+    assert sum(r["status"] == 0 for r in ref) == 191
+    piped = gpu_pipelined(cam, frames, 64, 3, **prm)
+    assert_same_results(got, piped)
+    # the planted trajectory is recovered over the whole stream
+    T = np.eye(4)
+    for g in got:
+        T = T @ g["DT"]
+    T_true = np.linalg.inv(frames[0][2]) @ frames[-1][2]
+    assert np.linalg.norm(T[:3, 3] - T_true[:3, 3]) < 0.05 * np.linalg.norm(T_true[:3, 3])
+
+
+def test_euroc_shape_32_frames_in_flight(built):
+    """BASELINE configs[2] shape at batch 16, 32 frames, sequential vs oracle and three in flight vs sequential."""
+    cam = plf.EUROC_CAMERA
+    world = synth.World(seed=8, length=40.0, n_quads=220, n_segs=120, half_width=5.0, half_height=3.0)
+    frames = list(synth.stream(cam, 32, world=world, seed=43, step=0.08, yaw_deg=0.8))
+    prm = dict(orb_nfeatures=1200, lsd_nfeatures=300)
+    ref = oracle_sequence(cam, frames, prm)
+    got, feats = gpu_sequential(cam, frames, 16, 16, **prm)
+    compare(ref, got, feats)
+    assert_same_results(got, gpu_pipelined(cam, frames, 8, 3, **prm))
+
+
+def test_low_texture_32_frames_in_flight(built):
+    """BASELINE configs[4] shape (lines-dominant) at batch 16, 32 frames."""
+    cam = plf.KITTI_CAMERA
+    frames = list(synth.stream(cam, 32, world=corridor_world(), seed=17, noise=2))
+    prm = dict(orb_nfeatures=150, lsd_nfeatures=0)
+    ref = oracle_sequence(cam, frames, prm)
+    got, feats = gpu_sequential(cam, frames, 16, 16, **prm)
+    compare(ref, got, feats)
+    assert all(g["n_lines_l"] > 400 for g in got)
+    assert_same_results(got, gpu_pipelined(cam, frames, 8, 3, **prm))

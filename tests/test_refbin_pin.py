@@ -34,12 +34,13 @@ def test_lbd_descriptor_equals_vendored_binary_descriptor():
 
 
 def test_keyline_stage_equals_vendored_lsd_detector():
-    """LSDDetectorC::detect (LSDDetector_custom.cpp:218-324) == orc_keylines_from_segments on every field except
-    `angle`, where the reference build resolves atan2(float, float) to glibc's atan2f while the restatement (and the
-    CUDA kernel) round the f64 atan2 to f32: a 1-ulp difference on ~10 % of the lines (deviations)."""
+    """LSDDetectorC::detect (LSDDetector_custom.cpp:218-324) == orc_keylines_from_segments on EVERY field, `angle`
+    included: the reference build resolves atan2(float, float) at :286 to glibc's atan2f, and so does the restatement
+    (round 1 narrowed the f64 atan2 instead: 1 ulp off on ~10 % of the lines)."""
     libm = C.CDLL("libm.so.6")
     libm.atan2f.restype = C.c_float
     libm.atan2f.argtypes = [C.c_float, C.c_float]
+    n_diff_f64 = 0
     for img in images():
         h, w = img.shape
         minlen = float(np.float32(0.025)) * min(w, h)
@@ -47,13 +48,11 @@ def test_keyline_stage_equals_vendored_lsd_detector():
         mine = clib.keylines_from_segments(clib.lsd(img), w, h, minlen)
         assert len(ref) == len(mine) > 150
         for f in ref.dtype.names:
-            if f != "angle":
-                assert np.array_equal(ref[f], mine[f]), f
+            assert np.array_equal(ref[f].view(np.int32), mine[f].view(np.int32)), f
         dy = ref["endPointY"] - ref["startPointY"]; dx = ref["endPointX"] - ref["startPointX"]
         assert np.array_equal(ref["angle"], np.array([libm.atan2f(float(y), float(x)) for y, x in zip(dy, dx)], np.float32))
-        assert np.array_equal(mine["angle"], np.arctan2(dy.astype(np.float64), dx.astype(np.float64)).astype(np.float32))
-        ulp = np.abs(ref["angle"].view(np.int32).astype(np.int64) - mine["angle"].view(np.int32).astype(np.int64))
-        assert ulp.max() <= 1 and 0 < (ulp > 0).mean() < 0.3
+        n_diff_f64 += int((ref["angle"] != np.arctan2(dy.astype(np.float64), dx.astype(np.float64)).astype(np.float32)).sum())
+    assert n_diff_f64 > 0   # the inputs do exercise the atan2f-vs-narrowed-atan2 distinction
 
 
 def test_median_descriptor_equals_reference_mappoint():
