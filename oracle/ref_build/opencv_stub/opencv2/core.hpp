@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <limits>
 #include <memory>
 #include <sstream>
 #include <stdexcept>
@@ -294,6 +295,8 @@ class FileNode {
  public:
   FileNode operator[](const char*) const { return FileNode(); }
   FileNode operator[](const String&) const { return FileNode(); }
+  FileNode operator[](int) const { return FileNode(); }
+  size_t size() const { return 0; }
   bool empty() const { return true; }
   bool isNone() const { return true; }
   operator int() const { return 0; }

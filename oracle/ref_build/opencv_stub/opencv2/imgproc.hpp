@@ -20,6 +20,11 @@ inline void pyrDown(InputArray, OutputArray, const Size& = Size(), int = BORDER_
 inline void resize(InputArray, OutputArray, Size, double = 0, double = 0, int = INTER_LINEAR) { plf_stub_abort("cv::resize"); }
 inline void cvtColor(InputArray, OutputArray, int, int = 0) { plf_stub_abort("cv::cvtColor"); }
 inline double threshold(InputArray, OutputArray, double, double, int) { plf_stub_abort("cv::threshold"); }
+// drawing + the OpenCV-1 colour codes (src/keyFrame.cpp:86-127 plotKeyFrame, only has to compile: tests/test_shim_compile.py)
+#define CV_GRAY2BGR 8
+#define CV_BGRA2BGR 1
+inline void circle(InputOutputArray, Point, int, const Scalar&, int = 1, int = 8, int = 0) { plf_stub_abort("cv::circle"); }
+inline void line(InputOutputArray, Point, Point, const Scalar&, int = 1, int = 8, int = 0) { plf_stub_abort("cv::line"); }
 
 class LineIterator {
  public:

@@ -30,11 +30,22 @@ struct Image {  // view of an 8-bit single-channel image (cv::Mat CV_8UC1: data,
   int cols = 0, rows = 0, step = 0;
 };
 
+// Fixed-size f64 matrix / vector with the Eigen accessors pl-slam uses on stvo-pl's types: (r, c), (i), [i], Identity(),
+// Zero().  Vectors are R x 1.
 template <int R, int C>
 struct Mat {
   std::array<double, R * C> v{};
+  Mat() = default;
+  Mat(double a, double b) { static_assert(R * C == 2, "2-vector"); v[0] = a; v[1] = b; }
+  Mat(double a, double b, double c) { static_assert(R * C == 3, "3-vector"); v[0] = a; v[1] = b; v[2] = c; }
   double& operator()(int r, int c) { return v[r * C + c]; }
   double operator()(int r, int c) const { return v[r * C + c]; }
+  double& operator()(int i) { return v[i]; }
+  double operator()(int i) const { return v[i]; }
+  double& operator[](int i) { return v[i]; }
+  double operator[](int i) const { return v[i]; }
+  double* data() { return v.data(); }
+  const double* data() const { return v.data(); }
   static Mat Identity() {
     Mat m;
     for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) = 1.0;
@@ -43,11 +54,12 @@ struct Mat {
   static Mat Zero() { return Mat(); }
   bool operator==(const Mat& o) const { return v == o.v; }
 };
+using Matrix3d = Mat<3, 3>;
 using Matrix4d = Mat<4, 4>;
 using Matrix6d = Mat<6, 6>;
-using Vector2d = std::array<double, 2>;
-using Vector3d = std::array<double, 3>;
-using Vector6d = std::array<double, 6>;
+using Vector2d = Mat<2, 1>;
+using Vector3d = Mat<3, 1>;
+using Vector6d = Mat<6, 1>;
 
 inline Matrix4d operator*(const Matrix4d& a, const Matrix4d& b) {
   Matrix4d c;
@@ -89,6 +101,60 @@ inline double det6(Matrix6d a) {  // LU with partial pivoting
   return det;
 }
 
+// stvo-pl auxiliar.h se(3) helpers on the host (x = [t; w]); the device versions are plf_se3.
+inline Matrix4d expmap_se3(const Vector6d& x) {
+  Matrix4d T = Matrix4d::Identity();
+  const double wx = x(3), wy = x(4), wz = x(5), th = std::sqrt(wx * wx + wy * wy + wz * wz);
+  if (th < 1e-6) {
+    for (int i = 0; i < 3; ++i) T(i, 3) = x(i);
+    return T;
+  }
+  const double s[3][3] = {{0, -wz / th, wy / th}, {wz / th, 0, -wx / th}, {-wy / th, wx / th, 0}};
+  double s2[3][3];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j) s2[i][j] = s[i][0] * s[0][j] + s[i][1] * s[1][j] + s[i][2] * s[2][j];
+  const double a = std::sin(th), b = 1.0 - std::cos(th), c = (1.0 - std::cos(th)) / th, d = (th - std::sin(th)) / th;
+  for (int i = 0; i < 3; ++i) {
+    double t = 0;
+    for (int j = 0; j < 3; ++j) {
+      T(i, j) = (i == j ? 1.0 : 0.0) + s[i][j] * a + s2[i][j] * b;
+      t += ((i == j ? 1.0 : 0.0) + s[i][j] * c + s2[i][j] * d) * x(j);
+    }
+    T(i, 3) = t;
+  }
+  return T;
+}
+
+inline Vector6d logmap_se3(const Matrix4d& T) {
+  Vector6d x;
+  double c = (T(0, 0) + T(1, 1) + T(2, 2) - 1.0) / 2.0;
+  c = c > 1 ? 1 : (c < -1 ? -1 : c);
+  const double th = std::acos(c);
+  double w[3] = {0, 0, 0};
+  if (th >= 1e-6) {
+    const double k = th / (2.0 * std::sin(th));
+    w[0] = k * (T(2, 1) - T(1, 2)); w[1] = k * (T(0, 2) - T(2, 0)); w[2] = k * (T(1, 0) - T(0, 1));
+  }
+  const double t[3] = {T(0, 3), T(1, 3), T(2, 3)};
+  if (th < 1e-6) {
+    for (int i = 0; i < 3; ++i) { x(i) = t[i]; x(3 + i) = w[i]; }
+    return x;
+  }
+  // V^-1 = I - 0.5 [w]x + (1/th^2)(1 - (th sin th) / (2 (1 - cos th))) [w]x^2
+  const double W[3][3] = {{0, -w[2], w[1]}, {w[2], 0, -w[0]}, {-w[1], w[0], 0}};
+  const double kk = (1.0 - th * std::sin(th) / (2.0 * (1.0 - std::cos(th)))) / (th * th);
+  for (int i = 0; i < 3; ++i) {
+    double r = 0;
+    for (int j = 0; j < 3; ++j) {
+      double w2 = W[i][0] * W[0][j] + W[i][1] * W[1][j] + W[i][2] * W[2][j];
+      r += ((i == j ? 1.0 : 0.0) - 0.5 * W[i][j] + kk * w2) * t[j];
+    }
+    x(i) = r;
+    x(3 + i) = w[i];
+  }
+  return x;
+}
+
 }  // namespace plf
 
 // stvo-pl gridStructure.h [UPSTREAM-RECALL, SURVEY A.2]: 48 x 64 matching grid
@@ -97,11 +163,23 @@ inline double det6(Matrix6d a) {  // LU with partial pivoting
 
 namespace StVO {
 
+using plf::Matrix3d;
 using plf::Matrix4d;
 using plf::Matrix6d;
 using plf::Vector2d;
 using plf::Vector3d;
 using plf::Vector6d;
+using plf::expmap_se3;
+using plf::inverse_se3;
+using plf::logmap_se3;
+// The image type of StereoFrame::img_l / img_r and of initialize / insertStereoPair: cv::Mat in a build that has OpenCV
+// (define STVO_SHIM_WITH_OPENCV after including <opencv2/core.hpp>; the shim reads data / cols / rows / step only),
+// the plf::Image view otherwise.
+#ifdef STVO_SHIM_WITH_OPENCV
+typedef cv::Mat Image;
+#else
+typedef plf::Image Image;
+#endif
 
 // stvo-pl PinholeStereoCamera (uses: app/plslam_dataset.cpp:84,97; src/mapHandler.cpp:255,551,1384-1385,3344)
 class PinholeStereoCamera {
@@ -164,7 +242,7 @@ struct DescMat {
 // stvo-pl StereoFrame: the fields KeyFrame deep-copies (src/keyFrame.cpp:39-53)
 class StereoFrame {
  public:
-  StereoFrame(const plf::Image& img_l_, const plf::Image& img_r_, int idx, PinholeStereoCamera* cam_)
+  StereoFrame(const Image& img_l_, const Image& img_r_, int idx, PinholeStereoCamera* cam_)
       : frame_idx(idx), img_l(img_l_), img_r(img_r_), cam(cam_) {
     // grid-cell scales, as the reference uses them (src/mapHandler.cpp:256,263,404-408: `pl(0) * curr_frame->inv_width`
     // feeds GridStructure::at / matchGrid): stvo-pl sets GRID_COLS / width and GRID_ROWS / height  [UPSTREAM-RECALL]
@@ -179,7 +257,7 @@ class StereoFrame {
   StereoFrame& operator=(const StereoFrame&) = delete;
 
   int frame_idx;
-  plf::Image img_l, img_r;
+  Image img_l, img_r;
   Matrix4d Tfw = Matrix4d::Identity(), DT = Matrix4d::Identity();
   Matrix6d Tfw_cov = Matrix6d::Zero(), DT_cov = Matrix6d::Zero();
   double err_norm = -1;
@@ -211,7 +289,7 @@ class StereoFrameHandler {
   }
 
   // app/plslam_dataset.cpp:115
-  void initialize(const plf::Image& img_l, const plf::Image& img_r, int idx) {
+  void initialize(const Image& img_l, const Image& img_r, int idx) {
     check(plf_reset_sequence(ctx_));
     delete prev_frame;
     prev_frame = run_frame(img_l, img_r, idx);
@@ -230,7 +308,7 @@ class StereoFrameHandler {
   }
 
   // app/plslam_dataset.cpp:127 — extraction, stereo association and frame-to-frame tracking
-  void insertStereoPair(const plf::Image& img_l, const plf::Image& img_r, int idx) {
+  void insertStereoPair(const Image& img_l, const Image& img_r, int idx) {
     if (!prev_frame) throw std::runtime_error("[StereoFrameHandler] insertStereoPair before initialize");
     delete curr_frame;
     curr_frame = run_frame(img_l, img_r, idx);
@@ -317,10 +395,10 @@ class StereoFrameHandler {
     if (st != PLF_OK) throw std::runtime_error(std::string("[StereoFrameHandler] ") + plf_last_error(ctx_));
   }
 
-  StereoFrame* run_frame(const plf::Image& l, const plf::Image& r, int idx) {
-    if (l.cols != cam->getWidth() || l.rows != cam->getHeight() || r.cols != l.cols || r.rows != l.rows || l.step != r.step)
+  StereoFrame* run_frame(const Image& l, const Image& r, int idx) {
+    if (l.cols != cam->getWidth() || l.rows != cam->getHeight() || r.cols != l.cols || r.rows != l.rows || (size_t)l.step != (size_t)r.step)
       throw std::runtime_error("[StereoFrameHandler] image size does not match the camera");
-    check(plf_process_batch(ctx_, 1, l.data, r.data, l.step, &last_));
+    check(plf_process_batch(ctx_, 1, l.data, r.data, (int)(size_t)l.step, &last_));
     auto* f = new StereoFrame(l, r, idx, cam);
     const int K = lim_.max_keypoints, Ln = lim_.max_lines;
     std::vector<double> pl(2 * (size_t)K), disp(K), P(3 * (size_t)K), spl(2 * (size_t)Ln), epl(2 * (size_t)Ln), sd(Ln), ed(Ln),

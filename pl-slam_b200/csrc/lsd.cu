@@ -33,6 +33,7 @@
 // Roofline: the gradient kernel is bound by its HBM writes (4.7 TB/s); region growing is latency-bound by construction
 // and is reported as time, not as a roofline fraction; the rest in DESIGN.md §4.
 #include <float.h>
+#include <stdlib.h>
 
 #include "glibc_atan2f.cuh"
 #include "glibc_sincosf.cuh"
@@ -652,6 +653,186 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
   if (lane == 0) nregions[im] = nreg_out;
 }
 
+// ---- region growing, one THREAD per image ------------------------------------------------------------------------
+// The warp-per-image kernel above is bound by its per-point dependent chain: ~116 warp instructions per region point, a
+// quarter of them cross-lane (VOTE / SHFL at 13-25 cycles each) - ~1000 cycles per point, 82.7 k points per KITTI frame,
+// whatever the batch size.  The algorithm has no intra-image parallelism to offer, so this kernel
+// removes the cross-lane traffic instead: ONE THREAD grows one image, with everything in its own registers - the 8
+// neighbour records (8 independent 16-byte loads), the reference's row-major decision order as straight-line code, the
+// same deferred-angle bounds (identical arithmetic, so identical decisions).  LANES images share a warp (LANES threads
+// per CTA), which divides the issue slots per point by LANES; the threads of a warp diverge freely (seed scan vs.
+// growing, different acceptance slots) and only ever wait for their own loads.
+//   * queue: per-thread ring of LSD_TQCAP entries in shared memory (the region's points, re-read in order), global
+//     memory (regpts, which is the output anyway) beyond that;
+//   * look-ahead: when a pixel joins the region the records its own 3x3 pass will read (PF_R rows around it) are
+//     prefetched into L1, so the dependent loads of the pass are L1 hits;
+//   * seed scan: 8 seeds per step, their indices loaded two steps and their records prefetched one step ahead.
+#define LSD_TQCAP 128
+template <int LANES, int PF_R, int PF_C>
+__global__ void __launch_bounds__(LANES) k_lsd_grow_t(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
+                                                       const uint32_t* __restrict__ order_all,
+                                                       const int* __restrict__ nseeds, int nimg, double prec,
+                                                       float prec_deg, int min_reg_size,
+                                                       uint32_t* __restrict__ regpts_all, uint4* __restrict__ regions_all,
+                                                       int max_regions, int* __restrict__ nregions,
+                                                       int* __restrict__ overflow) {
+  __shared__ uint32_t q_all[LANES][LSD_TQCAP];
+  const int im = blockIdx.x * LANES + threadIdx.x;
+  if (im >= nimg) return;
+  uint32_t* const q = q_all[threadIdx.x];
+  LsdPix* const pix = pix_all + (size_t)im * pix_stride;
+  const char* const pb = reinterpret_cast<const char*>(pix);
+  const uint32_t* const order = order_all + (size_t)im * stride;
+  uint32_t* const regpts = regpts_all + (size_t)im * stride;
+  uint4* const regions = regions_all + (size_t)im * max_regions;
+  const int ns = nseeds[im];
+  const int noff[8] = {-W - 1, -W, -W + 1, -1, 1, W - 1, W, W + 1};  // the reference's row-major 3x3 order, centre skipped
+  const float margin0 = prec_deg <= 60.f ? LSD_MARGIN0 : 1e30f;
+  const float dmax = prec_deg + LSD_MARGIN0;
+  // seed scan state: the seed order is consumed in groups of 8.  gA = the group being examined (position sbase), gB and
+  // gC = the next two groups, whose records are already being prefetched, gD = the group after those (indices loaded,
+  // records not yet requested): record prefetches run two groups, index loads three groups ahead of the examination.
+  uint32_t gA[8], gB[8], gC[8], gD[8];
+  int sbase = 0, gpos = 0;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    gA[j] = j < ns ? __ldg(&order[j]) : 0u;
+    gB[j] = 8 + j < ns ? __ldg(&order[8 + j]) : 0u;
+    gC[j] = 16 + j < ns ? __ldg(&order[16 + j]) : 0u;
+    gD[j] = 24 + j < ns ? __ldg(&order[24 + j]) : 0u;
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < ns) lsd_prefetch(&pix[gA[j]]);
+    if (8 + j < ns) lsd_prefetch(&pix[gB[j]]);
+    if (16 + j < ns) lsd_prefetch(&pix[gC[j]]);
+  }
+  uint32_t cursor = 0;
+  int nreg_out = 0;
+  // region state
+  bool active = false, fresh = true;
+  uint32_t r = 0, nreg = 0;
+  float th = 0.f, sumdx = 0.f, sumdy = 0.f, margin = 0.f, inv0 = 1.02f, lo = 0.f, hi = 0.f;
+  double th_seed = 0.0;
+  for (;;) {
+    if (!active) {
+      if (sbase >= ns) break;
+      // examine the seeds gpos.. of the current group (their records were prefetched a step ago; they are re-read after
+      // every region, which may have used some of them)
+      float a8[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a8[j] = (j >= gpos && sbase + j < ns) ? __ldca(&pix[gA[j]].a) : LSD_NOTDEF_F;
+      int hit = -1;
+#pragma unroll
+      for (int j = 7; j >= 0; --j)
+        if (a8[j] != LSD_NOTDEF_F) hit = j;
+      if (hit < 0) {  // next group
+        sbase += 8;
+        gpos = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          gA[j] = gB[j];
+          gB[j] = gC[j];
+          gC[j] = gD[j];
+          gD[j] = sbase + 24 + j < ns ? __ldg(&order[sbase + 24 + j]) : 0u;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          if (sbase + 16 + j < ns) lsd_prefetch(&pix[gC[j]]);
+        if (sbase + 96 < ns) asm volatile("prefetch.global.L2 [%0];" ::"l"(&order[sbase + 96]));
+        continue;
+      }
+      uint32_t sidx = gA[0];
+      float a0 = a8[0];
+#pragma unroll
+      for (int j = 1; j < 8; ++j)
+        if (hit == j) { sidx = gA[j]; a0 = a8[j]; }
+      gpos = hit + 1;
+      // region_grow: seed
+      th = a0;
+      th_seed = (double)th * LSD_DEG2RAD;
+      margin = margin0; inv0 = 1.02f;
+      lo = prec_deg - margin; hi = prec_deg + margin;
+      fresh = true;
+      pix[sidx].a = LSD_NOTDEF_F;
+      regpts[cursor] = sidx;
+      q[0] = sidx;
+      r = 0; nreg = 1;
+      active = true;
+#pragma unroll
+      for (int dr = -PF_R; dr <= PF_R; ++dr)
+#pragma unroll
+        for (int dc = -PF_C; dc <= PF_C; dc += 2) lsd_prefetch(pb + (long long)((int)sidx + dr * W + dc) * 16);
+      continue;
+    }
+    // ---- one region point: its 3x3 neighbourhood in the reference's order ----
+    const uint32_t pt = (nreg - r <= LSD_TQCAP) ? q[r & (LSD_TQCAP - 1)] : __ldcg(&regpts[cursor + r]);
+    float4 rec[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) rec[k] = __ldca(reinterpret_cast<const float4*>(pb + (long long)((int)pt + noff[k]) * 16));
+    const uint32_t nreg0 = nreg;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float a = rec[k].x;
+      if (a == LSD_NOTDEF_F) continue;
+      float d = fabsf(__fsub_rn(a, th));
+      if (d > 180.f) d = __fsub_rn(360.f, d);
+      if (d > hi) continue;  // clearly not aligned whatever the exact region angle is
+      if (!(d < lo)) {       // inside the band: the decision needs the exact angle
+        if (!fresh) {
+          th = lsd_fast_atan2(sumdy, sumdx);
+          inv0 = __fmul_rn(rsqrtf(__fadd_rn(__fmul_rn(sumdx, sumdx), __fmul_rn(sumdy, sumdy))), 1.02f);
+          margin = margin0;
+          lo = prec_deg - margin; hi = prec_deg + margin;
+          fresh = true;
+          d = fabsf(__fsub_rn(a, th));
+          if (d > 180.f) d = __fsub_rn(360.f, d);
+          if (d > hi) continue;
+        }
+        if (!(d < lo) && !lsd_aligned_rad((double)a * LSD_DEG2RAD, (double)th * LSD_DEG2RAD, prec)) continue;
+      }
+      // accepted: mark used, append to the region / the queue, update the running sums and the bound
+      const int ai = (int)pt + noff[k];
+      *reinterpret_cast<float*>(const_cast<char*>(pb) + (long long)ai * 16) = LSD_NOTDEF_F;
+      regpts[cursor + nreg] = (uint32_t)ai;
+      q[nreg & (LSD_TQCAP - 1)] = (uint32_t)ai;
+      if (nreg == 1) {  // first member: the seed's own unit vector (f64 cos / sin, as the reference)
+        sumdx = (float)cos(th_seed);
+        sumdy = (float)sin(th_seed);
+      }
+      ++nreg;
+      sumdx = __fadd_rn(sumdx, rec[k].y);
+      sumdy = __fadd_rn(sumdy, rec[k].z);
+      margin = __fmaf_rn(fminf(__fadd_rn(d, margin), dmax), inv0, margin);
+      lo = prec_deg - margin; hi = prec_deg + margin;
+      fresh = false;
+    }
+    // look-ahead for the pixels that joined: the rows their own pass will read
+    for (uint32_t j = nreg0; j < nreg; ++j) {
+      const int p = (int)q[j & (LSD_TQCAP - 1)];
+#pragma unroll
+      for (int dr = -PF_R; dr <= PF_R; ++dr)
+#pragma unroll
+        for (int dc = -PF_C; dc <= PF_C; dc += 2) lsd_prefetch(pb + (long long)(p + dr * W + dc) * 16);
+    }
+    if (++r == nreg) {  // region complete
+      if ((int)nreg >= min_reg_size) {
+        if (nreg_out < max_regions) {
+          const double reg_angle = nreg == 1 ? th_seed : (double)(fresh ? th : lsd_fast_atan2(sumdy, sumdx)) * LSD_DEG2RAD;
+          const unsigned long long bits = (unsigned long long)__double_as_longlong(reg_angle);
+          regions[nreg_out] = make_uint4(cursor, nreg, (uint32_t)bits, (uint32_t)(bits >> 32));
+          ++nreg_out;
+          cursor += nreg;
+        } else {
+          *overflow = 1;
+        }
+      }
+      active = false;
+    }
+  }
+  nregions[im] = nreg_out;
+}
+
 // ---- rectangle fit -------------------------------------------------------------------------------------------
 __device__ __forceinline__ double lsd_angle_diff(double a, double b) {
   double diff = a - b;
@@ -1077,8 +1258,35 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   plf_keyline* kls = s->kls[par] + o * s->max_lines;
   plf_keyline* kls_all = s->kls_all[par] + o * s->max_regions;
   int* nlines = s->nlines[par] + o;
-  k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts, regions, s->max_regions,
-                               nregions, s->overflow);
+  // PLF_GROW = "warp" selects the round-1 warp-per-image kernel (kept for A/B measurements); default: thread per image.
+  // PLF_GROW_CFG = "<lanes><pf_r><pf_c>" picks one of the compiled look-ahead variants (tuning).
+  static const int grow_mode = [] {
+    const char* e = getenv("PLF_GROW");
+    if (e && !strcmp(e, "warp")) return -1;
+    const char* c = getenv("PLF_GROW_CFG");
+    return c ? atoi(c) : 821;
+  }();
+#define GROW_T(L, R, C)                                                                                                  \
+  k_lsd_grow_t<L, R, C><<<(n + L - 1) / L, L, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, n, s->prec,             \
+                                                       (float)(s->p * 180.0), s->min_reg_size, regpts, regions,          \
+                                                       s->max_regions, nregions, s->overflow)
+  switch (grow_mode) {
+    case -1:
+      k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
+                                   regions, s->max_regions, nregions, s->overflow);
+      break;
+    case 411: GROW_T(4, 1, 1); break;
+    case 421: GROW_T(4, 2, 1); break;
+    case 423: GROW_T(4, 2, 3); break;
+    case 433: GROW_T(4, 3, 3); break;
+    case 811: GROW_T(8, 1, 1); break;
+    case 823: GROW_T(8, 2, 3); break;
+    case 833: GROW_T(8, 3, 3); break;
+    case 1621: GROW_T(16, 2, 1); break;
+    case 3221: GROW_T(32, 2, 1); break;
+    default: GROW_T(8, 2, 1); break;
+  }
+#undef GROW_T
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grow");
   uint32_t* perm = s->rect_perm + o * s->max_regions;
