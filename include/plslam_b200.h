@@ -268,6 +268,45 @@ plf_status plf_gn_pose(plf_ctx* ctx, const plf_gn_opts* opts, const double* P, c
                        const double* le_obs, uint8_t* inlier_ls, int nl, const double* T_init,
                        plf_pose_result* out);
 
+/* Relative pose between two keyframes.  Replaces MapHandler::isLoopClosure (src/mapHandler.cpp:3192-3300:
+ * match() on the points :3223 and on the lines :3249 of kf0 / kf1, the inlier-ratio pre-condition :3277-3299) followed by
+ * MapHandler::computeRelativePoseRobustGN (:3566-3957: two-stage robust GN from identity with the chi2 gate in between,
+ * both stages stopping on DBL_EPSILON; acceptance tests residual / covariance eigenvalue / translation / rotation
+ * :3875-3906; pose_inc = logmap_se3(inverse_se3(expmap_se3(x_inc))) :3951).  max_iters / max_iters_ref, min_ratio_12_*,
+ * has_points / has_lines, best_lr_matches and homog_th come from the ctx params (SlamConfig inherits them). */
+typedef struct plf_lc_params {
+  double lc_res;          /* SlamConfig::lcRes()  src/slamConfig.cpp:73  (config_euroc.yaml:116: 1.5) */
+  double lc_unc;          /* lcUnc  :74   maximum largest eigenvalue of H^-1 */
+  double lc_inl;          /* lcInl  :75   (evaluated but overridden by the reference, mapHandler.cpp:3900) */
+  double lc_trs;          /* lcTrs  :76 */
+  double lc_rot;          /* lcRot  :77   degrees */
+  double lc_inlier_ratio; /* lcInlierRatio :83, percent */
+} plf_lc_params;
+typedef struct plf_lc_keyframe {  /* the stereo-valid features of a KeyFrame's frame (host arrays) */
+  int n_pt, n_ls;
+  const uint8_t* pdesc; /* n_pt x 32  stereo_frame->pdesc_l */
+  const double* P;      /* n_pt x 3   stereo_pt[i]->P   (read for kf0) */
+  const double* pl;     /* n_pt x 2   stereo_pt[i]->pl  (read for kf1) */
+  const uint8_t* ldesc; /* n_ls x 32 */
+  const double* sP;     /* n_ls x 3   (kf0) */
+  const double* eP;     /* n_ls x 3   (kf0) */
+  const double* le;     /* n_ls x 3   stereo_ls[i]->le (kf1) */
+} plf_lc_keyframe;
+typedef struct plf_lc_result {
+  int accepted;        /* the reference's return value */
+  int estimated;       /* 0: stopped at the inlier-ratio pre-condition */
+  int common_pt, common_ls;
+  int n_pt, n_ls;      /* inlier correspondences written to pt_pairs / ls_pairs (accepted only) */
+  double inl_ratio_pt, inl_ratio_ls;
+  double err, max_cov_eig, ratio_inliers, t, r;
+  double x_inc[6];     /* logmap_se3(T_inc) */
+  double pose_inc[6];  /* accepted only */
+} plf_lc_result;
+/* pt_pairs / ls_pairs: (i1 in kf0, i2 in kf1) per surviving correspondence, capacity cap_* pairs (may be NULL). */
+plf_status plf_loop_closure_pose(plf_ctx* ctx, const plf_lc_params* lc, const plf_lc_keyframe* kf0,
+                                 const plf_lc_keyframe* kf1, plf_lc_result* out, int32_t* pt_pairs, int cap_pt,
+                                 int32_t* ls_pairs, int cap_ls);
+
 /* se(3) helpers of stvo-pl auxiliar.h used throughout src/mapHandler.cpp (e.g. :137-142,:3439,:3558):
  * op 0 = expmap_se3 (in: 6 = [t; w], out: 16 row-major), op 1 = logmap_se3 (in: 16, out: 6). */
 plf_status plf_se3(plf_ctx* ctx, int op, const double* in, double* out);
@@ -329,6 +368,12 @@ plf_status plf_process_batch(plf_ctx* ctx, int B, const uint8_t* left, const uin
 plf_status plf_batch_upload(plf_ctx* ctx, int B, const uint8_t* left, const uint8_t* right, int stride);
 plf_status plf_batch_run(plf_ctx* ctx, int B);
 plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out);
+/* Poses of the OLDEST batch in flight, device to device: dst_device[B][16] f64 (DT, row-major) is filled on `stream`
+ * (a cudaStream_t of the caller; NULL = an internal stream, synchronised before returning) behind that batch's match
+ * phase - the buffer a multi-GPU caller passes to its NCCL pose all-gather on the same stream (the reference
+ * has no counterpart: app/plslam_dataset.cpp:148-154 reads curr_frame->Tfw on the host).  The batch stays in flight
+ * until plf_batch_download. */
+plf_status plf_batch_device_poses(plf_ctx* ctx, int B, double* dst_device, void* stream);
 /* Device buffer [2*max_batch][h][w] read by plf_batch_run (image 2k = left k, 2k+1 = right k). */
 void* plf_batch_device_images(plf_ctx* ctx);
 

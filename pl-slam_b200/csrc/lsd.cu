@@ -677,15 +677,17 @@ __global__ void __launch_bounds__(LANES) k_lsd_grow_t(LsdPix* __restrict__ pix_a
                                                        int max_regions, int* __restrict__ nregions,
                                                        int* __restrict__ overflow) {
   __shared__ uint32_t q_all[LANES][LSD_TQCAP];
-  const int im = blockIdx.x * LANES + threadIdx.x;
-  if (im >= nimg) return;
+  const unsigned wmask = __activemask();   // the LANES threads of this (partial) warp
+  const int im_raw = blockIdx.x * LANES + threadIdx.x;
+  const bool valid = im_raw < nimg;
+  const int im = valid ? im_raw : 0;       // threads past the last image idle through the loop (they must keep converging)
   uint32_t* const q = q_all[threadIdx.x];
   LsdPix* const pix = pix_all + (size_t)im * pix_stride;
   const char* const pb = reinterpret_cast<const char*>(pix);
   const uint32_t* const order = order_all + (size_t)im * stride;
   uint32_t* const regpts = regpts_all + (size_t)im * stride;
   uint4* const regions = regions_all + (size_t)im * max_regions;
-  const int ns = nseeds[im];
+  const int ns = valid ? nseeds[im] : 0;
   const int noff[8] = {-W - 1, -W, -W + 1, -1, 1, W - 1, W, W + 1};  // the reference's row-major 3x3 order, centre skipped
   const float margin0 = prec_deg <= 60.f ? LSD_MARGIN0 : 1e30f;
   const float dmax = prec_deg + LSD_MARGIN0;
@@ -710,15 +712,19 @@ __global__ void __launch_bounds__(LANES) k_lsd_grow_t(LsdPix* __restrict__ pix_a
   uint32_t cursor = 0;
   int nreg_out = 0;
   // region state
-  bool active = false, fresh = true;
+  bool done = ns <= 0, active = false, fresh = true;
   uint32_t r = 0, nreg = 0;
   float th = 0.f, sumdx = 0.f, sumdy = 0.f, margin = 0.f, inv0 = 1.02f, lo = 0.f, hi = 0.f;
   double th_seed = 0.0;
+  // The threads of a warp must meet again at the top of every step: each then executes either the scan step or the growing
+  // step, the threads in the same kind of step in lockstep.  (Without the explicit convergence point the threads drift apart
+  // after the first divergent branch and the warp executes them one after the other: measured 3x slower than one warp
+  // per image.)
   for (;;) {
-    if (!active) {
-      if (sbase >= ns) break;
-      // examine the seeds gpos.. of the current group (their records were prefetched a step ago; they are re-read after
-      // every region, which may have used some of them)
+    if (__all_sync(wmask, done)) break;
+    if (!done && !active) {
+      // ---- seed scan: the seeds gpos.. of the current group (their records were prefetched two groups ago; they are
+      // re-read after every region, which may have used some of them)
       float a8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) a8[j] = (j >= gpos && sbase + j < ns) ? __ldca(&pix[gA[j]].a) : LSD_NOTDEF_F;
@@ -729,108 +735,121 @@ __global__ void __launch_bounds__(LANES) k_lsd_grow_t(LsdPix* __restrict__ pix_a
       if (hit < 0) {  // next group
         sbase += 8;
         gpos = 0;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          gA[j] = gB[j];
-          gB[j] = gC[j];
-          gC[j] = gD[j];
-          gD[j] = sbase + 24 + j < ns ? __ldg(&order[sbase + 24 + j]) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          if (sbase + 16 + j < ns) lsd_prefetch(&pix[gC[j]]);
-        if (sbase + 96 < ns) asm volatile("prefetch.global.L2 [%0];" ::"l"(&order[sbase + 96]));
-        continue;
-      }
-      uint32_t sidx = gA[0];
-      float a0 = a8[0];
-#pragma unroll
-      for (int j = 1; j < 8; ++j)
-        if (hit == j) { sidx = gA[j]; a0 = a8[j]; }
-      gpos = hit + 1;
-      // region_grow: seed
-      th = a0;
-      th_seed = (double)th * LSD_DEG2RAD;
-      margin = margin0; inv0 = 1.02f;
-      lo = prec_deg - margin; hi = prec_deg + margin;
-      fresh = true;
-      pix[sidx].a = LSD_NOTDEF_F;
-      regpts[cursor] = sidx;
-      q[0] = sidx;
-      r = 0; nreg = 1;
-      active = true;
-#pragma unroll
-      for (int dr = -PF_R; dr <= PF_R; ++dr)
-#pragma unroll
-        for (int dc = -PF_C; dc <= PF_C; dc += 2) lsd_prefetch(pb + (long long)((int)sidx + dr * W + dc) * 16);
-      continue;
-    }
-    // ---- one region point: its 3x3 neighbourhood in the reference's order ----
-    const uint32_t pt = (nreg - r <= LSD_TQCAP) ? q[r & (LSD_TQCAP - 1)] : __ldcg(&regpts[cursor + r]);
-    float4 rec[8];
-#pragma unroll
-    for (int k = 0; k < 8; ++k) rec[k] = __ldca(reinterpret_cast<const float4*>(pb + (long long)((int)pt + noff[k]) * 16));
-    const uint32_t nreg0 = nreg;
-#pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const float a = rec[k].x;
-      if (a == LSD_NOTDEF_F) continue;
-      float d = fabsf(__fsub_rn(a, th));
-      if (d > 180.f) d = __fsub_rn(360.f, d);
-      if (d > hi) continue;  // clearly not aligned whatever the exact region angle is
-      if (!(d < lo)) {       // inside the band: the decision needs the exact angle
-        if (!fresh) {
-          th = lsd_fast_atan2(sumdy, sumdx);
-          inv0 = __fmul_rn(rsqrtf(__fadd_rn(__fmul_rn(sumdx, sumdx), __fmul_rn(sumdy, sumdy))), 1.02f);
-          margin = margin0;
-          lo = prec_deg - margin; hi = prec_deg + margin;
-          fresh = true;
-          d = fabsf(__fsub_rn(a, th));
-          if (d > 180.f) d = __fsub_rn(360.f, d);
-          if (d > hi) continue;
-        }
-        if (!(d < lo) && !lsd_aligned_rad((double)a * LSD_DEG2RAD, (double)th * LSD_DEG2RAD, prec)) continue;
-      }
-      // accepted: mark used, append to the region / the queue, update the running sums and the bound
-      const int ai = (int)pt + noff[k];
-      *reinterpret_cast<float*>(const_cast<char*>(pb) + (long long)ai * 16) = LSD_NOTDEF_F;
-      regpts[cursor + nreg] = (uint32_t)ai;
-      q[nreg & (LSD_TQCAP - 1)] = (uint32_t)ai;
-      if (nreg == 1) {  // first member: the seed's own unit vector (f64 cos / sin, as the reference)
-        sumdx = (float)cos(th_seed);
-        sumdy = (float)sin(th_seed);
-      }
-      ++nreg;
-      sumdx = __fadd_rn(sumdx, rec[k].y);
-      sumdy = __fadd_rn(sumdy, rec[k].z);
-      margin = __fmaf_rn(fminf(__fadd_rn(d, margin), dmax), inv0, margin);
-      lo = prec_deg - margin; hi = prec_deg + margin;
-      fresh = false;
-    }
-    // look-ahead for the pixels that joined: the rows their own pass will read
-    for (uint32_t j = nreg0; j < nreg; ++j) {
-      const int p = (int)q[j & (LSD_TQCAP - 1)];
-#pragma unroll
-      for (int dr = -PF_R; dr <= PF_R; ++dr)
-#pragma unroll
-        for (int dc = -PF_C; dc <= PF_C; dc += 2) lsd_prefetch(pb + (long long)(p + dr * W + dc) * 16);
-    }
-    if (++r == nreg) {  // region complete
-      if ((int)nreg >= min_reg_size) {
-        if (nreg_out < max_regions) {
-          const double reg_angle = nreg == 1 ? th_seed : (double)(fresh ? th : lsd_fast_atan2(sumdy, sumdx)) * LSD_DEG2RAD;
-          const unsigned long long bits = (unsigned long long)__double_as_longlong(reg_angle);
-          regions[nreg_out] = make_uint4(cursor, nreg, (uint32_t)bits, (uint32_t)(bits >> 32));
-          ++nreg_out;
-          cursor += nreg;
+        if (sbase >= ns) {
+          done = true;
         } else {
-          *overflow = 1;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            gA[j] = gB[j];
+            gB[j] = gC[j];
+            gC[j] = gD[j];
+            gD[j] = sbase + 24 + j < ns ? __ldg(&order[sbase + 24 + j]) : 0u;
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (sbase + 16 + j < ns) lsd_prefetch(&pix[gC[j]]);
+          if (sbase + 96 < ns) asm volatile("prefetch.global.L2 [%0];" ::"l"(&order[sbase + 96]));
         }
+      } else {
+        uint32_t sidx = gA[0];
+        float a0 = a8[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j)
+          if (hit == j) { sidx = gA[j]; a0 = a8[j]; }
+        gpos = hit + 1;
+        // region_grow: seed
+        th = a0;
+        th_seed = (double)th * LSD_DEG2RAD;
+        margin = margin0; inv0 = 1.02f;
+        lo = prec_deg - margin; hi = prec_deg + margin;
+        fresh = true;
+        pix[sidx].a = LSD_NOTDEF_F;
+        regpts[cursor] = sidx;
+        q[0] = sidx;
+        r = 0; nreg = 1;
+        active = true;
+#pragma unroll
+        for (int dr = -PF_R; dr <= PF_R; ++dr)
+#pragma unroll
+          for (int dc = -PF_C; dc <= PF_C; dc += 2) lsd_prefetch(pb + (long long)((int)sidx + dr * W + dc) * 16);
       }
-      active = false;
+    } else if (!done) {
+      // ---- one region point: its 3x3 neighbourhood in the reference's order ----
+      const uint32_t pt = (nreg - r <= LSD_TQCAP) ? q[r & (LSD_TQCAP - 1)] : __ldcg(&regpts[cursor + r]);
+      float4 rec[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) rec[k] = __ldca(reinterpret_cast<const float4*>(pb + (long long)((int)pt + noff[k]) * 16));
+      // distances to the last evaluated region angle, all eight at once: th only changes on the (rare) re-evaluation
+      // below, which recomputes the distances of the slots still to come
+      float d8[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float d = fabsf(__fsub_rn(rec[k].x, th));
+        if (d > 180.f) d = __fsub_rn(360.f, d);
+        d8[k] = rec[k].x == LSD_NOTDEF_F ? 1e30f : d;   // NOTDEF (undefined or used): never aligned
+      }
+      const uint32_t nreg0 = nreg;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (d8[k] > hi) continue;  // clearly not aligned whatever the exact region angle is (or NOTDEF)
+        if (!(d8[k] < lo)) {       // inside the band: the decision needs the exact angle
+          if (!fresh) {
+            th = lsd_fast_atan2(sumdy, sumdx);
+            inv0 = __fmul_rn(rsqrtf(__fadd_rn(__fmul_rn(sumdx, sumdx), __fmul_rn(sumdy, sumdy))), 1.02f);
+            margin = margin0;
+            lo = prec_deg - margin; hi = prec_deg + margin;
+            fresh = true;
+#pragma unroll
+            for (int kk = k; kk < 8; ++kk) {
+              float d = fabsf(__fsub_rn(rec[kk].x, th));
+              if (d > 180.f) d = __fsub_rn(360.f, d);
+              d8[kk] = rec[kk].x == LSD_NOTDEF_F ? 1e30f : d;
+            }
+            if (d8[k] > hi) continue;
+          }
+          if (!(d8[k] < lo) && !lsd_aligned_rad((double)rec[k].x * LSD_DEG2RAD, (double)th * LSD_DEG2RAD, prec)) continue;
+        }
+        // accepted: mark used, append to the region / the queue, update the running sums and the bound
+        const int ai = (int)pt + noff[k];
+        *reinterpret_cast<float*>(const_cast<char*>(pb) + (long long)ai * 16) = LSD_NOTDEF_F;
+        regpts[cursor + nreg] = (uint32_t)ai;
+        q[nreg & (LSD_TQCAP - 1)] = (uint32_t)ai;
+        if (nreg == 1) {  // first member: the seed's own unit vector (f64 cos / sin, as the reference)
+          sumdx = (float)cos(th_seed);
+          sumdy = (float)sin(th_seed);
+        }
+        ++nreg;
+        sumdx = __fadd_rn(sumdx, rec[k].y);
+        sumdy = __fadd_rn(sumdy, rec[k].z);
+        margin = __fmaf_rn(fminf(__fadd_rn(d8[k], margin), dmax), inv0, margin);
+        lo = prec_deg - margin; hi = prec_deg + margin;
+        fresh = false;
+      }
+      // look-ahead for the pixels that joined: the rows their own pass will read
+      for (uint32_t j = nreg0; j < nreg; ++j) {
+        const int p = (int)q[j & (LSD_TQCAP - 1)];
+#pragma unroll
+        for (int dr = -PF_R; dr <= PF_R; ++dr)
+#pragma unroll
+          for (int dc = -PF_C; dc <= PF_C; dc += 2) lsd_prefetch(pb + (long long)(p + dr * W + dc) * 16);
+      }
+      if (++r == nreg) {  // region complete
+        if ((int)nreg >= min_reg_size) {
+          if (nreg_out < max_regions) {
+            const double reg_angle = nreg == 1 ? th_seed : (double)(fresh ? th : lsd_fast_atan2(sumdy, sumdx)) * LSD_DEG2RAD;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(reg_angle);
+            regions[nreg_out] = make_uint4(cursor, nreg, (uint32_t)bits, (uint32_t)(bits >> 32));
+            ++nreg_out;
+            cursor += nreg;
+          } else {
+            *overflow = 1;
+          }
+        }
+        active = false;
+      }
     }
   }
-  nregions[im] = nreg_out;
+  if (valid) nregions[im] = nreg_out;
 }
 
 // ---- rectangle fit -------------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ struct PipeState {
   double* gn_sP = nullptr; double* gn_eP = nullptr; double* gn_le = nullptr; uint8_t* gnInlL = nullptr; int* gnNl = nullptr;
   GnProblem* gn_probs = nullptr;
   plf_pose_result* gn_out = nullptr;
-  plf_frame_result* results = nullptr;                  // [B] device
+  plf_frame_result* results = nullptr;                  // [3][B] device, ring indexed like h_results (plf_batch_device_poses reads it)
   plf_frame_result* h_results[3] = {nullptr, nullptr, nullptr};  // pinned host mirrors, ring of PIPE_DEPTH (filled at the end of M)
   int* h_ovf[3] = {nullptr, nullptr, nullptr};                   // pinned overflow flags {orb, lsd}
   int* d_ovf = nullptr;         // [3][2] per-batch snapshots of the two global overflow flags (taken at the end of E and G)
@@ -408,13 +408,15 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PA(s->klsM, 2 * (size_t)B * Ln); PA(s->lcntM, 2 * (size_t)B);
   PA(s->gnP, (size_t)B * K * 3); PA(s->gnObs, (size_t)B * K * 2); PA(s->gnInlP, (size_t)B * K); PA(s->gnNp, B);
   PA(s->gn_sP, (size_t)B * Ln * 3); PA(s->gn_eP, (size_t)B * Ln * 3); PA(s->gn_le, (size_t)B * Ln * 3); PA(s->gnInlL, (size_t)B * Ln); PA(s->gnNl, B);
-  PA(s->gn_probs, B); PA(s->gn_out, B); PA(s->results, B);
+  PA(s->gn_probs, B); PA(s->gn_out, B); PA(s->results, 3 * (size_t)B);
   PA(s->d_ovf, 6);
 #undef PA
   for (int i = 0; i < 3; ++i) {
     PLF_CUDA(ctx, cudaHostAlloc(&s->h_results[i], sizeof(plf_frame_result) * B, cudaHostAllocDefault));
     PLF_CUDA(ctx, cudaHostAlloc(&s->h_ovf[i], 2 * sizeof(int), cudaHostAllocDefault));
-    PLF_CUDA(ctx, cudaEventCreate(&s->evM[i]));
+    // timing enabled (plf_debug_timeline) + blocking sync: a host thread waiting in plf_batch_download sleeps instead of
+    // spinning (8 ranks spinning on a box that gives the job a fraction of its CPUs was the round-1 scaling suspect)
+    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evM[i], cudaEventBlockingSync));
     PLF_CUDA(ctx, cudaEventCreate(&s->tM0[i]));
   }
   for (int i = 0; i < 2; ++i) {
@@ -666,12 +668,12 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   if ((st = plf_launch_gn(ctx, s->gn_probs, B, plf_gn_opts_from_params(P)))) return st;
   plf_mark(ctx, "gn.k_gn_pose");
   k_finalize<<<(B + 127) / 128, 128, 0, cs>>>(s->gn_out, s->gnNp, s->gnNl, kcnt, lcnt, s->fs, 1, P.min_features,
-                                               s->has_prev ? 0 : 1, B, s->results);
+                                               s->has_prev ? 0 : 1, B, s->results + (size_t)rp * s->B);
   PLF_LAUNCH_CHECK(ctx);
   if ((st = copy_slot(ctx, s, B, 0))) return st;  // carry the last frame to the next batch
   plf_mark(ctx, "k_finalize+carry");
   // results + overflow flags to pinned memory as part of this batch's stream work; evM marks them ready
-  PLF_CUDA(ctx, cudaMemcpyAsync(s->h_results[rp], s->results, sizeof(plf_frame_result) * B, cudaMemcpyDeviceToHost, cs));
+  PLF_CUDA(ctx, cudaMemcpyAsync(s->h_results[rp], s->results + (size_t)rp * s->B, sizeof(plf_frame_result) * B, cudaMemcpyDeviceToHost, cs));
   PLF_CUDA(ctx, cudaMemcpyAsync(s->h_ovf[rp], s->d_ovf + 2 * rp, 2 * sizeof(int), cudaMemcpyDeviceToHost, cs));
   PLF_CUDA(ctx, cudaEventRecord(s->evM[rp], cs));
   s->has_prev = true;
@@ -701,6 +703,25 @@ plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out) {
     return plf_fail(ctx, PLF_ERR_CAPACITY, "plf_batch_download: a fixed-capacity buffer overflowed (%s%s); raise plf_limits",
                     o0 ? "ORB keypoints " : "", o1 ? "LSD segments/lines" : "");
   }
+  return PLF_OK;
+}
+
+// Device-resident poses of the OLDEST batch in flight: copies DT (16 f64, row-major) of its B frames into the caller's
+// DEVICE buffer dst[B][16] on the CALLER's stream, behind that batch's end-of-match-phase event - what a multi-GPU
+// caller hands to its NCCL all-gather (issued on the same stream) without a host round trip and without queueing behind
+// the later batches already enqueued on the library's own streams.  Does not retire the batch.
+plf_status plf_batch_device_poses(plf_ctx* ctx, int B, double* dst_device, void* stream) {
+  if (!ctx || !ctx->pipe || !dst_device || B < 1) return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_device_poses: bad arguments");
+  PipeState* s = ctx->pipe;
+  if (s->n_pending == 0) return plf_fail(ctx, PLF_ERR_STATE, "plf_batch_device_poses: no batch in flight");
+  if (B != s->pend_B[0]) return plf_fail(ctx, PLF_ERR_INVALID, "plf_batch_device_poses: B=%d but the oldest batch has %d pairs", B, s->pend_B[0]);
+  const int rp = s->pend_slot[0];
+  cudaStream_t cs = stream ? (cudaStream_t)stream : s->copy;
+  PLF_CUDA(ctx, cudaSetDevice(ctx->device));
+  PLF_CUDA(ctx, cudaStreamWaitEvent(cs, s->evM[rp], 0));
+  PLF_CUDA(ctx, cudaMemcpy2DAsync(dst_device, 16 * sizeof(double), s->results + (size_t)rp * s->B, sizeof(plf_frame_result),
+                                  16 * sizeof(double), B, cudaMemcpyDeviceToDevice, cs));
+  if (!stream) PLF_CUDA(ctx, cudaStreamSynchronize(cs));
   return PLF_OK;
 }
 

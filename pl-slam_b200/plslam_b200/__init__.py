@@ -84,6 +84,23 @@ class plf_frame_view(C.Structure):
                 ("ls_angle", C.c_void_p), ("ldesc", C.c_void_p)]
 
 
+class plf_lc_params(C.Structure):
+    _fields_ = [("lc_res", C.c_double), ("lc_unc", C.c_double), ("lc_inl", C.c_double), ("lc_trs", C.c_double),
+                ("lc_rot", C.c_double), ("lc_inlier_ratio", C.c_double)]
+
+
+class plf_lc_keyframe(C.Structure):
+    _fields_ = [("n_pt", C.c_int), ("n_ls", C.c_int), ("pdesc", C.c_void_p), ("P", C.c_void_p), ("pl", C.c_void_p),
+                ("ldesc", C.c_void_p), ("sP", C.c_void_p), ("eP", C.c_void_p), ("le", C.c_void_p)]
+
+
+class plf_lc_result(C.Structure):
+    _fields_ = [("accepted", C.c_int), ("estimated", C.c_int), ("common_pt", C.c_int), ("common_ls", C.c_int),
+                ("n_pt", C.c_int), ("n_ls", C.c_int), ("inl_ratio_pt", C.c_double), ("inl_ratio_ls", C.c_double),
+                ("err", C.c_double), ("max_cov_eig", C.c_double), ("ratio_inliers", C.c_double), ("t", C.c_double),
+                ("r", C.c_double), ("x_inc", C.c_double * 6), ("pose_inc", C.c_double * 6)]
+
+
 RESULT_DTYPE = np.dtype([("DT", np.float64, (4, 4)), ("DT_cov", np.float64, (6, 6)), ("err", np.float64),
                          ("status", np.int32), ("n_kp_l", np.int32), ("n_kp_r", np.int32), ("n_lines_l", np.int32),
                          ("n_lines_r", np.int32), ("n_stereo_pt", np.int32), ("n_stereo_ls", np.int32),
@@ -338,6 +355,38 @@ class Frontend:
                     err=out.err, iters=(out.iters1, out.iters2), inlier_pt=ip, inlier_ls=il,
                     n_inliers=(out.n_inliers_pt, out.n_inliers_ls))
 
+    def loop_closure_pose(self, kf0, kf1, lc=None):
+        """MapHandler::isLoopClosure + computeRelativePoseRobustGN (src/mapHandler.cpp:3192-3300, :3566-3957).
+        kf0 / kf1: dicts with pdesc, P, pl, ldesc, sP, eP, le (numpy); lc: dict of the lc_* thresholds."""
+        d = dict(lc_res=1.0, lc_unc=0.01, lc_inl=0.3, lc_trs=1.5, lc_rot=35.0, lc_inlier_ratio=30.0)
+        d.update(lc or {})
+        lcp = plf_lc_params(**d)
+        keep = []
+
+        def kf(k):
+            f = plf_lc_keyframe()
+            pd = _u8(k["pdesc"]).reshape(-1, 32); ld = _u8(k["ldesc"]).reshape(-1, 32)
+            arrs = dict(pdesc=pd, ldesc=ld)
+            for name, cols in (("P", 3), ("pl", 2), ("sP", 3), ("eP", 3), ("le", 3)):
+                arrs[name] = np.ascontiguousarray(k[name], np.float64).reshape(-1, cols)
+            f.n_pt, f.n_ls = len(pd), len(ld)
+            for name, a in arrs.items():
+                keep.append(a)
+                setattr(f, name, a.ctypes.data if a.size else None)
+            return f
+        k0, k1 = kf(kf0), kf(kf1)
+        cap_p, cap_l = max(k0.n_pt, 1), max(k0.n_ls, 1)
+        pp = np.full((cap_p, 2), -1, np.int32); lp = np.full((cap_l, 2), -1, np.int32)
+        out = plf_lc_result()
+        st = self.lib.plf_loop_closure_pose(self._ctx, C.byref(lcp), C.byref(k0), C.byref(k1), C.byref(out),
+                                            _ptr(pp, C.c_int32), cap_p, _ptr(lp, C.c_int32), cap_l)
+        self._check(st, "plf_loop_closure_pose")
+        r = {f: getattr(out, f) for f, _ in plf_lc_result._fields_ if f not in ("x_inc", "pose_inc")}
+        r["accepted"] = bool(out.accepted); r["estimated"] = bool(out.estimated)
+        r["x_inc"] = np.array(out.x_inc); r["pose_inc"] = np.array(out.pose_inc)
+        r["pt_pairs"] = pp[:out.n_pt].copy(); r["ls_pairs"] = lp[:out.n_ls].copy()
+        return r
+
     def expmap_se3(self, x):
         x = np.ascontiguousarray(x, np.float64).reshape(6)
         T = np.zeros(16)
@@ -460,6 +509,11 @@ class Frontend:
         out = np.zeros(B, RESULT_DTYPE)
         self._check(self.lib.plf_batch_download(self._ctx, int(B), out.ctypes.data_as(C.c_void_p)), "plf_batch_download")
         return out
+
+    def batch_device_poses(self, B, dst_device_ptr, stream=0):
+        """DT [B,16] f64 of the oldest batch in flight -> caller's device buffer, on the caller's CUDA stream."""
+        self._check(self.lib.plf_batch_device_poses(self._ctx, int(B), C.c_void_p(int(dst_device_ptr)), C.c_void_p(int(stream))),
+                    "plf_batch_device_poses")
 
     @property
     def device_images(self) -> int:

@@ -76,19 +76,7 @@ def test_pipeline_euroc_shape_stream(built):
     compare(ref, got, feats)
 
 
-def corridor_world(n_segs=450, seed=3):
-    """Lines-dominant scene: long low-contrast 3-D segments running along the corridor (few crossings, ends mostly
-    outside the view), no textured quads."""
-    world = synth.World(seed=21, length=90.0, n_quads=0, n_segs=0)
-    rng = np.random.default_rng(seed)
-    segs = []
-    for _ in range(n_segs):
-        x = rng.choice([-1, 1]) * rng.uniform(1.0, 12.0); y = rng.uniform(-4, 4)
-        z0 = rng.uniform(1.0, 30.0); z1 = z0 + rng.uniform(15, 60)
-        g = float(90 + rng.choice([-1, 1]) * rng.uniform(24, 32))
-        segs.append((np.array([x, y, z0]), np.array([x + rng.normal(0, 0.05), y + rng.normal(0, 0.05), z1]), g, int(rng.integers(2, 4))))
-    world.segs = segs
-    return world
+corridor_world = synth.corridor_world   # lines-dominant scene (now part of the input generator: bench.py --config lowtex)
 
 
 def test_pipeline_low_texture_stream(built):
