@@ -1277,13 +1277,11 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   plf_keyline* kls = s->kls[par] + o * s->max_lines;
   plf_keyline* kls_all = s->kls_all[par] + o * s->max_regions;
   int* nlines = s->nlines[par] + o;
-  // PLF_GROW = "warp" selects the round-1 warp-per-image kernel (kept for A/B measurements); default: thread per image.
+  // default: the warp-per-image kernel; PLF_GROW_CFG selects a thread-per-image variant (A/B measurements).
   // PLF_GROW_CFG = "<lanes><pf_r><pf_c>" picks one of the compiled look-ahead variants (tuning).
   static const int grow_mode = [] {
-    const char* e = getenv("PLF_GROW");
-    if (e && !strcmp(e, "warp")) return -1;
     const char* c = getenv("PLF_GROW_CFG");
-    return c ? atoi(c) : 821;
+    return c ? atoi(c) : -1;   // measured on B200 (3072 images): warp 49.7 ms, thread-per-image 146 (4 lanes) .. 230 ms (16 lanes)
   }();
 #define GROW_T(L, R, C)                                                                                                  \
   k_lsd_grow_t<L, R, C><<<(n + L - 1) / L, L, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, n, s->prec,             \
@@ -1294,6 +1292,10 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
       k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
                                    regions, s->max_regions, nregions, s->overflow);
       break;
+    case 111: GROW_T(1, 1, 1); break;
+    case 121: GROW_T(1, 2, 1); break;
+    case 211: GROW_T(2, 1, 1); break;
+    case 221: GROW_T(2, 2, 1); break;
     case 411: GROW_T(4, 1, 1); break;
     case 421: GROW_T(4, 2, 1); break;
     case 423: GROW_T(4, 2, 3); break;
