@@ -62,6 +62,14 @@ typedef struct plf_params {
   int lsd_nfeatures, lsd_refine;
   double lsd_scale, lsd_sigma_scale, lsd_quant, lsd_ang_th, lsd_log_eps, lsd_density_th; /* LSDOptions: double */
   int lsd_n_bins;
+  /* matching strategy (config_euroc.yaml:55-57 `matching_strategy`, `matching_s_ws`, `matching_f2f_ws`).
+   * 0 (default here): descriptor-only association - stereo and frame-to-frame matches come from match() (brute-force
+   * NNR + mutual).  != 0 (the reference configs select 3): windowed - stereo association runs matchGrid() over the
+   * 48 x 64 GridStructure of the right image with the window (matching_s_ws, 0) x (0, 0); frame-to-frame tracking
+   * follows the in-tree analogue's control flow (src/mapHandler.cpp:247-278, :379-425): matchGrid() in a
+   * +-matching_f2f_ws window around the projected feature, match() when fewer than min_pt_matches / min_ls_matches
+   * (src/slamConfig.cpp:85-86) survive. */
+  int matching_strategy, matching_s_ws, matching_f2f_ws, min_pt_matches, min_ls_matches;
 } plf_params;
 
 /* Rectified pinhole stereo rig (stvo-pl PinholeStereoCamera; schema

@@ -39,7 +39,12 @@ DEFAULTS = dict(  # config/config/config_euroc.yaml:9-77
     best_lr_matches=True, max_dist_epip=1.0, min_disp=1.0, min_ratio_12_p=0.9, line_sim_th=0.75,
     stereo_overlap_th=0.75, f2f_overlap_th=0.75, min_line_length=0.025, line_horiz_th=0.1, min_ratio_12_l=0.9,
     ls_min_disp_ratio=0.7, homog_th=1e-7, min_features=10, max_iters=5, max_iters_ref=10, min_error=1e-7,
-    min_error_change=1e-7, orb_nfeatures=800, orb_nlevels=4, orb_fast_th=20, lsd_nfeatures=300)
+    min_error_change=1e-7, orb_nfeatures=800, orb_nlevels=4, orb_fast_th=20, lsd_nfeatures=300,
+    # matching strategy (config_euroc.yaml:55-57; 0 = descriptor only, the default of this library; the reference
+    # configs select 3 = windowed) and the fall-back thresholds of the in-tree analogue (src/slamConfig.cpp:85-86)
+    matching_strategy=0, matching_s_ws=10, matching_f2f_ws=3, min_pt_matches=10, min_ls_matches=6)
+
+GRID_ROWS, GRID_COLS = 48, 64   # stvo-pl gridStructure.h
 
 
 def f32(x):
@@ -90,8 +95,53 @@ class Frame:
     ldesc: np.ndarray = field(default_factory=lambda: np.zeros((0, 32), np.uint8))
 
 
+def grid_scales(cam):
+    """StereoFrame::inv_width / inv_height = GRID_COLS / width, GRID_ROWS / height (f64)."""
+    return GRID_COLS / float(cam["width"]), GRID_ROWS / float(cam["height"])
+
+
+def _cell(v):
+    """double -> int conversion of a scaled coordinate (C++ truncation toward zero)."""
+    return np.trunc(np.asarray(v, np.float64)).astype(np.int64)
+
+
+def grid_match_points(cam, q_xy, d1, t_xy, d2, w, nnr, best_lr):
+    """matchGrid (points): queries / train features at pixel positions q_xy / t_xy (f64 [n,2])."""
+    from oracle import matchgrid as mg
+    iw, ih = grid_scales(cam)
+    q_xy = np.asarray(q_xy, np.float64).reshape(-1, 2)
+    t_xy = np.asarray(t_xy, np.float64).reshape(-1, 2)
+    q_cell = np.stack([_cell(q_xy[:, 0] * iw), _cell(q_xy[:, 1] * ih)], 1)
+    t_cell = np.stack([_cell(t_xy[:, 0] * iw), _cell(t_xy[:, 1] * ih)], 1)
+    return mg.match_grid_points(q_cell, d1, mg.grid_from_points(t_cell, GRID_ROWS, GRID_COLS), d2, w, nnr, best_lr)
+
+
+def grid_match_lines(cam, q_se, d1, t_se, d2, w, nnr, line_sim_th, best_lr):
+    """matchGrid (lines): q_se / t_se = [n,4] pixel end points (sx, sy, ex, ey), f64.  Train directions are the
+    normalised scaled deltas ((ex - sx) inv_width, (ey - sy) inv_height) (src/mapHandler.cpp:402-404)."""
+    from oracle import matchgrid as mg
+    iw, ih = grid_scales(cam)
+    sc = np.array([iw, ih, iw, ih])
+    q_se = np.asarray(q_se, np.float64).reshape(-1, 4)
+    t_se = np.asarray(t_se, np.float64).reshape(-1, 4)
+    q_line, t_line = _cell(q_se * sc), _cell(t_se * sc)
+    vx, vy = (t_se[:, 2] - t_se[:, 0]) * iw, (t_se[:, 3] - t_se[:, 1]) * ih
+    with np.errstate(invalid="ignore", divide="ignore"):
+        nrm = np.sqrt(vx * vx + vy * vy)
+        t_dir = np.stack([vx / nrm, vy / nrm], 1)
+    return mg.match_grid_lines(q_line, d1, mg.grid_from_lines(t_line, GRID_ROWS, GRID_COLS), t_dir, d2, w, nnr,
+                               float(np.float32(line_sim_th)), best_lr)
+
+
 def stereo_points(cam, kp_l, desc_l, kp_r, desc_r, prm, match_fn=None):
-    m12, _ = (match_fn or om.match)(desc_l, desc_r, prm["min_ratio_12_p"], prm["best_lr_matches"])
+    if prm.get("matching_strategy", 0) and match_fn is None:
+        # stvo-pl matchStereoPoints: window (matching_s_ws, 0) x (0, 0) left of / on the query's cell (A.2)
+        q = np.stack([kp_l["x"].astype(np.float64), kp_l["y"].astype(np.float64)], 1)
+        t = np.stack([kp_r["x"].astype(np.float64), kp_r["y"].astype(np.float64)], 1)
+        m12, _ = grid_match_points(cam, q, desc_l, t, desc_r, (int(prm["matching_s_ws"]), 0, 0, 0), prm["min_ratio_12_p"],
+                                   prm["best_lr_matches"])
+    else:
+        m12, _ = (match_fn or om.match)(desc_l, desc_r, prm["min_ratio_12_p"], prm["best_lr_matches"])
     pl, disp, P, octv, rows = [], [], [], [], []
     for i, j in enumerate(m12):
         if j < 0:
@@ -107,8 +157,16 @@ def stereo_points(cam, kp_l, desc_l, kp_r, desc_r, prm, match_fn=None):
             np.array(octv, np.int32), desc_l[rows].reshape(n, 32))
 
 
+def _kl_se(kl):
+    return np.stack([kl["startPointX"], kl["startPointY"], kl["endPointX"], kl["endPointY"]], 1).astype(np.float64)
+
+
 def stereo_lines(cam, kl_l, desc_l, kl_r, desc_r, prm, match_fn=None):
-    m12, _ = (match_fn or om.match)(desc_l, desc_r, prm["min_ratio_12_l"], prm["best_lr_matches"])
+    if prm.get("matching_strategy", 0) and match_fn is None:
+        m12, _ = grid_match_lines(cam, _kl_se(kl_l), desc_l, _kl_se(kl_r), desc_r, (int(prm["matching_s_ws"]), 0, 0, 0),
+                                  prm["min_ratio_12_l"], prm["line_sim_th"], prm["best_lr_matches"])
+    else:
+        m12, _ = (match_fn or om.match)(desc_l, desc_r, prm["min_ratio_12_l"], prm["best_lr_matches"])
     out = dict(spl=[], epl=[], sdisp=[], edisp=[], sP=[], eP=[], le=[], angle=[], rows=[])
     for i, j in enumerate(m12):
         if j < 0:
@@ -165,12 +223,49 @@ def _orb_c(img, prm):
     return clib.orb(img, prm["orb_nfeatures"], 1.2, prm["orb_nlevels"], 19, 31, prm["orb_fast_th"])
 
 
-def track(prev: Frame, curr: Frame, prm, match_fn=None):
-    """f2fTracking: brute-force NNR + mutual match of the stereo-valid descriptors (A.2), building the GN rows."""
-    mp, _ = (match_fn or om.match)(prev.pdesc, curr.pdesc, prm["min_ratio_12_p"], prm["best_lr_matches"])
+def projection(cam, P):
+    """PinholeStereoCamera::projection (A.4)."""
+    P = np.asarray(P, np.float64).reshape(-1, 3)
+    return np.stack([cam["cx"] + cam["fx"] * P[:, 0] / P[:, 2], cam["cy"] + cam["fy"] * P[:, 1] / P[:, 2]], 1)
+
+
+def track_matches(cam, prev: Frame, curr: Frame, prm, match_fn=None):
+    """The two matches_12 vectors of f2fTracking.  matching_strategy 0: match() on the stereo-valid descriptors (A.2).
+    Otherwise the control flow of the in-tree analogue (src/mapHandler.cpp:247-278, :379-425) with DT = identity
+    (use_motion_model false): the previous frame's 3-D features are projected, matched in a +-matching_f2f_ws window of
+    the current frame's grid, and match() takes over when fewer than min_pt_matches / min_ls_matches survive (both
+    frames holding more features than that).  Projected lines are scaled to grid units like the points (the analogue
+    leaves them in pixels, :395, which empties the window; not reproduced)."""
+    mfn = match_fn or om.match
+    if not prm.get("matching_strategy", 0) or match_fn is not None:
+        mp, _ = mfn(prev.pdesc, curr.pdesc, prm["min_ratio_12_p"], prm["best_lr_matches"])
+        ml, _ = mfn(prev.ldesc, curr.ldesc, prm["min_ratio_12_l"], prm["best_lr_matches"])
+        return mp, ml
+    ws = int(prm["matching_f2f_ws"])
+    w = (ws, ws, ws, ws)
+    mp, ml = np.full(len(prev.pdesc), -1, np.int32), np.full(len(prev.ldesc), -1, np.int32)
+    if len(prev.pdesc) and len(curr.pdesc):
+        mp, n = grid_match_points(cam, projection(cam, prev.pt_P), prev.pdesc, curr.pt_pl, curr.pdesc, w,
+                                  prm["min_ratio_12_p"], prm["best_lr_matches"])
+        k = int(prm["min_pt_matches"])
+        if len(curr.pdesc) > k and len(prev.pdesc) > k and n < k:
+            mp, _ = om.match(prev.pdesc, curr.pdesc, prm["min_ratio_12_p"], prm["best_lr_matches"])
+    if len(prev.ldesc) and len(curr.ldesc):
+        q = np.concatenate([projection(cam, prev.ls_sP), projection(cam, prev.ls_eP)], 1)
+        t = np.concatenate([curr.ls_spl, curr.ls_epl], 1)
+        ml, n = grid_match_lines(cam, q, prev.ldesc, t, curr.ldesc, w, prm["min_ratio_12_l"], prm["line_sim_th"],
+                                 prm["best_lr_matches"])
+        k = int(prm["min_ls_matches"])
+        if len(curr.ldesc) > k and len(prev.ldesc) > k and n < k:
+            ml, _ = om.match(prev.ldesc, curr.ldesc, prm["min_ratio_12_l"], prm["best_lr_matches"])
+    return mp, ml
+
+
+def track(prev: Frame, curr: Frame, prm, match_fn=None, cam=None):
+    """f2fTracking: the two matches_12 vectors (track_matches), then the GN rows."""
+    mp, ml = track_matches(cam, prev, curr, prm, match_fn)
     ip = np.nonzero(mp >= 0)[0]
     P, obs = prev.pt_P[ip], curr.pt_pl[mp[ip]]
-    ml, _ = (match_fn or om.match)(prev.ldesc, curr.ldesc, prm["min_ratio_12_l"], prm["best_lr_matches"])
     il = np.nonzero(ml >= 0)[0]
     sP, eP, le = prev.ls_sP[il], prev.ls_eP[il], curr.ls_le[ml[il]]
     return dict(P=P, obs=obs, sP=sP, eP=eP, le=le, mp=mp, ml=ml)
@@ -196,7 +291,7 @@ def run_sequence(cam, pairs, prm=None, orb_fn=None, lines_fn=None, match_fn=None
         if prev is None:
             DT, status, res = np.eye(4), 2, None      # initialize(): first frame
         else:
-            tr = track(prev, cur, prm, match_fn)
+            tr = track(prev, cur, prm, match_fn, cam=cam)
             DT, res, status = optimize_pose(cam, tr, prm)
         Tfw = Tfw @ DT
         out.append(dict(DT=DT, Tfw=Tfw.copy(), status=status, n_pt=len(cur.pt_pl), n_ls=len(cur.ls_spl), res=res, frame=cur))

@@ -20,6 +20,7 @@
 //                  element-wise on all threads; 32 byte-compares pack the bits.  No tree/shuffle reductions.
 // All float arithmetic is unfused (--fmad=false) in the reference's source order.
 #include "plf_internal.h"
+#include "plf_tma.cuh"
 
 #define LBD_TW 64
 #define LBD_TH 16
@@ -27,8 +28,13 @@
 #define LBD_WB 7
 #define LBD_ROWS 63
 
+plf_status plf_lbd_init(plf_ctx* ctx);
+
 struct LbdState {
-  int dummy;
+  // cached tensor maps of the source images of k_blur5_sobel_fast (the pipeline alternates between two upload buffers)
+  const void* tm_src[2] = {nullptr, nullptr};
+  CUtensorMap tm[2];
+  size_t tm_stride = 0; int tm_pitch = 0, tm_w = 0, tm_h = 0, tm_nimg = 0;
 };
 
 __constant__ float c_gaussL[21];  // (float)gaussCoefL_[i]
@@ -104,34 +110,29 @@ __global__ void __launch_bounds__(256) k_blur5_sobel(const uint8_t* __restrict__
   }
 }
 
-// Fast variant: 64x32 outputs per CTA, DP4A row pass (taps 14,62,104,62 | 14 packed as u8), 4-column vertical pass,
-// register-sliding Sobel.  Same integer arithmetic as k_blur5_sobel (bit-identical), ~4x fewer instructions per pixel.
+// Fast variant: 64x32 outputs per CTA, the (tile + halo) box staged by ONE TMA bulk-tensor copy (plf_tma.cuh; border CTAs
+// rebuild BORDER_REFLECT_101 inside shared memory), DP4A row pass (taps 14,62,104,62 | 14 packed as u8), 4-column vertical
+// pass, register-sliding Sobel.  Same integer arithmetic as k_blur5_sobel (bit-identical), ~4x fewer instructions per pixel.
 #define LBF_TW 64
 #define LBF_TH 32
-__global__ void __launch_bounds__(256) k_blur5_sobel_fast(const uint8_t* __restrict__ imgs, int pitch, size_t img_stride,
-                                                           int w, int h, short2* __restrict__ grad, size_t grad_stride) {
+__global__ void __launch_bounds__(256) k_blur5_sobel_fast(const __grid_constant__ CUtensorMap tmap, int w, int h,
+                                                           short2* __restrict__ grad, size_t grad_stride) {
   constexpr int RH = LBF_TH + 6;   // raw rows: halo 3 (blur 2 + sobel 1)
-  constexpr int RP = 76;           // raw row pitch (bytes): 68 blurred columns + 4 taps + word slack, multiple of 4
+  constexpr int RP = 80;           // TMA box width (bytes, multiple of 16)
+  constexpr int NEED = 76;         // columns read: 68 blurred columns + 4 taps + word slack
   constexpr int BW = 68;           // blurred columns computed (66 needed, rounded to groups of 4)
-  __shared__ __align__(16) uint8_t raw[RH][RP];
+  __shared__ __align__(128) uint8_t raw[RH][RP];
   __shared__ __align__(16) uint16_t hrow[RH][BW];
   __shared__ __align__(16) uint8_t blur[LBF_TH + 2][BW + 4];
-  const uint8_t* img = imgs + (size_t)blockIdx.z * img_stride;
+  __shared__ __align__(8) uint64_t bar;
   short2* out = grad + (size_t)blockIdx.z * grad_stride;
   const int x0 = blockIdx.x * LBF_TW, y0 = blockIdx.y * LBF_TH, tid = threadIdx.x;
-  const int lane = tid & 31, wrp = tid >> 5;
-  const bool interior = x0 >= 3 && x0 - 3 + RP <= w && y0 >= 3 && y0 + LBF_TH + 3 <= h;
-  if (interior) {  // four pixels per step (plf_load4)
-    for (int i = tid; i < RH * (RP / 4); i += 256) {
-      const int ry = i / (RP / 4), j = i - ry * (RP / 4);
-      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4_fast(img + (size_t)(y0 - 3 + ry) * pitch + (x0 - 3 + 4 * j));
-    }
-  } else {
-    for (int ry = wrp; ry < RH; ry += 8) {
-      const uint8_t* row = img + (size_t)reflect101(y0 - 3 + ry, h) * pitch;
-      for (int rx = lane; rx < RP; rx += 32) raw[ry][rx] = row[reflect101(x0 - 3 + rx, w)];
-    }
-  }
+  if (tid == 0) plf_mbar_init(&bar);
+  __syncthreads();
+  if (tid == 0) plf_tma_load_3d(&raw[0][0], &tmap, x0 - 3, y0 - 3, (int)blockIdx.z, &bar, RH * RP);
+  plf_mbar_wait(&bar, 0);
+  if (!(x0 >= 3 && x0 - 3 + NEED <= w && y0 >= 3 && y0 + LBF_TH + 3 <= h))   // border tile: BORDER_REFLECT_101 in place
+    plf_tma_reflect_fix<RH, RP>(raw, x0 - 3, y0 - 3, w, h, NEED);
   __syncthreads();
   const uint32_t tapsA = 14u | (62u << 8) | (104u << 16) | (62u << 24), tapsB = 14u;
   // horizontal pass: blurred column b (coordinate x0-1+b) uses raw offsets b..b+4
@@ -202,10 +203,25 @@ __global__ void __launch_bounds__(256) k_blur5_sobel_fast(const uint8_t* __restr
 plf_status plf_launch_blur5_sobel(plf_ctx* ctx, const uint8_t* imgs, int pitch, size_t img_stride,
                                   int w, int h, int nimg, short2* grad, size_t grad_stride) {
   if (nimg <= 0) return PLF_OK;
-  if (w >= 8 && h >= 8) {
+  if (w >= 8 && h >= 8 && (pitch & 15) == 0 && (img_stride & 15) == 0 && ((uintptr_t)imgs & 15) == 0) {
+    plf_status st0 = plf_lbd_init(ctx);
+    if (st0) return st0;
+    LbdState* s = ctx->lbd;
+    if (s->tm_stride != img_stride || s->tm_pitch != pitch || s->tm_w != w || s->tm_h != h || s->tm_nimg < nimg) {
+      s->tm_src[0] = s->tm_src[1] = nullptr;
+      s->tm_stride = img_stride; s->tm_pitch = pitch; s->tm_w = w; s->tm_h = h; s->tm_nimg = nimg;
+    }
+    int slot = -1;
+    for (int k = 0; k < 2; ++k) if (s->tm_src[k] == imgs) slot = k;
+    if (slot < 0) {
+      slot = s->tm_src[0] ? (s->tm_src[1] ? 0 : 1) : 0;
+      if (!plf_tma_encode_u8(&s->tm[slot], imgs, w, h, s->tm_nimg, pitch, img_stride ? img_stride : (size_t)pitch * h, 80, LBF_TH + 6))
+        return plf_fail(ctx, PLF_ERR_CUDA, "LBD: cuTensorMapEncodeTiled failed (pitch %d, stride %zu)", pitch, img_stride);
+      s->tm_src[slot] = imgs;
+    }
     dim3 grid((w + LBF_TW - 1) / LBF_TW, (h + LBF_TH - 1) / LBF_TH, nimg);
-    k_blur5_sobel_fast<<<grid, 256, 0, ctx->cur>>>(imgs, pitch, img_stride, w, h, grad, grad_stride);
-  } else {  // tiny images: generic kernel
+    k_blur5_sobel_fast<<<grid, 256, 0, ctx->cur>>>(s->tm[slot], w, h, grad, grad_stride);
+  } else {  // tiny images / unpadded rows: generic kernel
     dim3 grid((w + LBD_TW - 1) / LBD_TW, (h + LBD_TH - 1) / LBD_TH, nimg);
     k_blur5_sobel<<<grid, 256, 0, ctx->cur>>>(imgs, pitch, img_stride, w, h, grad, grad_stride);
   }
@@ -389,11 +405,12 @@ extern "C" plf_status plf_lbd_gradients(plf_ctx* ctx, const uint8_t* img, int w,
   if (!ctx || !img || !dxdy || w < 2 || h < 2 || stride < w)
     return plf_fail(ctx, PLF_ERR_INVALID, "plf_lbd_gradients: bad arguments");
   PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t ib = al256((size_t)w * h), gb = al256((size_t)w * h * 4);
+  const int pitch = plf_pitch16(w);
+  const size_t ib = al256((size_t)pitch * h), gb = al256((size_t)w * h * 4);
   uint8_t* base = (uint8_t*)plf_scratch(ctx, 1, ib + gb);
   if (!base) return PLF_ERR_CUDA;
-  PLF_CUDA(ctx, cudaMemcpy2DAsync(base, w, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
-  plf_status st = plf_launch_blur5_sobel(ctx, base, w, 0, w, h, 1, (short2*)(base + ib), 0);
+  PLF_CUDA(ctx, cudaMemcpy2DAsync(base, pitch, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  plf_status st = plf_launch_blur5_sobel(ctx, base, pitch, (size_t)pitch * h, w, h, 1, (short2*)(base + ib), 0);
   if (st) return st;
   PLF_CUDA(ctx, cudaMemcpyAsync(dxdy, base + ib, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream));
   PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -411,7 +428,8 @@ extern "C" plf_status plf_lbd(plf_ctx* ctx, const uint8_t* img, int w, int h, in
   if (n > 32767)
     return plf_fail(ctx, PLF_ERR_INVALID, "plf_lbd: %d lines (reference numOfFinalLine is a short, :1029)", n);
   PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t ib = al256((size_t)w * h), gb = al256((size_t)w * h * 4),
+  const int pitch = plf_pitch16(w);
+  const size_t ib = al256((size_t)pitch * h), gb = al256((size_t)w * h * 4),
                kb = al256((size_t)n * sizeof(plf_keyline)), db = al256((size_t)n * 32),
                fb = al256((size_t)n * 72 * 4);
   uint8_t* base = (uint8_t*)plf_scratch(ctx, 1, ib + gb + kb + db + fb + 256);
@@ -422,10 +440,10 @@ extern "C" plf_status plf_lbd(plf_ctx* ctx, const uint8_t* img, int w, int h, in
   uint8_t* ddesc = base + ib + gb + kb;
   float* dfl = (float*)(base + ib + gb + kb + db);
   int* dcount = (int*)(base + ib + gb + kb + db + fb);
-  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, w, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, pitch, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
   PLF_CUDA(ctx, cudaMemcpyAsync(dkl, keylines, (size_t)n * sizeof(plf_keyline), cudaMemcpyHostToDevice, ctx->stream));
   PLF_CUDA(ctx, cudaMemcpyAsync(dcount, &n, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
-  plf_status st = plf_launch_blur5_sobel(ctx, dimg, w, 0, w, h, 1, dgrad, 0);
+  plf_status st = plf_launch_blur5_sobel(ctx, dimg, pitch, (size_t)pitch * h, w, h, 1, dgrad, 0);
   if (st) return st;
   st = plf_launch_lbd(ctx, dgrad, 0, w, h, 1, dkl, dcount, n, ddesc, desc_float ? dfl : nullptr);
   if (st) return st;

@@ -38,6 +38,7 @@
 #include "glibc_atan2f.cuh"
 #include "glibc_sincosf.cuh"
 #include "plf_internal.h"
+#include "plf_tma.cuh"
 
 #define LSD_NOTDEF (-1024.0f)
 #define LSD_PI 3.1415926535897932384626433832795
@@ -57,8 +58,12 @@ struct LsdState {
   int min_reg_size = 0;
   int max_regions = 0, max_lines = 0;
   bool two_parities = false;
-  uint8_t* blur = nullptr;    // [nimg][h*w]
-  uint8_t* scaled = nullptr;  // [nimg][hs*ws]
+  uint8_t* blur = nullptr;    // [nimg][h][bp]   bp = plf_pitch16(w)
+  uint8_t* scaled = nullptr;  // [nimg][hs][sp]  sp = plf_pitch16(ws)
+  int bp = 0, sp = 0;
+  const void* tm_src[2] = {nullptr, nullptr};   // source buffers the cached tensor maps were encoded for
+  CUtensorMap tm_blur[2];
+  size_t tm_stride = 0; int tm_pitch = 0, tm_nimg = 0;
   short2* gxy[2] = {nullptr, nullptr};      // [nimg][hs*ws]
   uint32_t* rect_perm = nullptr;  // [nimg][max_regions] regions in size-class order (k_lsd_rect_order)
   struct LsdPix* pix_raw[2] = {nullptr, nullptr};  // allocation (pix + look-ahead slack on both sides)
@@ -82,6 +87,7 @@ struct LsdState {
   int* rs_tab = nullptr;      // resize tables
   size_t rs_x_off = 0, rs_y_off = 0;
   struct LsdPix* grad_lut = nullptr; // [1021*1021] gradient (gx,gy) -> LsdPix
+  float2* seed_lut = nullptr;        // [1021*1021] gradient (gx,gy) -> unit vector of a region seed
 };
 
 __constant__ int c_lsd_taps[16];
@@ -100,7 +106,7 @@ __device__ __forceinline__ int lsd_reflect101(int i, int n) {
 #define BQ_TH 16
 #define BQ_R 7
 __global__ void __launch_bounds__(256) k_blur_q8(const uint8_t* __restrict__ src, size_t src_stride, int pitch,
-                                                 int w, int h, int r, uint8_t* __restrict__ dst, size_t dst_stride) {
+                                                 int w, int h, int r, uint8_t* __restrict__ dst, size_t dst_stride, int dpitch) {
   __shared__ uint8_t raw[BQ_TH + 2 * BQ_R][BQ_TW + 2 * BQ_R + 2];
   __shared__ uint16_t hrow[BQ_TH + 2 * BQ_R][BQ_TW];
   const uint8_t* s = src + (size_t)blockIdx.z * src_stride;
@@ -131,12 +137,13 @@ __global__ void __launch_bounds__(256) k_blur_q8(const uint8_t* __restrict__ src
       uint32_t a = 0;
       for (int k = 0; k < ks; ++k) a += (uint32_t)c_lsd_taps[k] * hrow[ty + k][tx];
       const uint32_t v = (a + (1u << 15)) >> 16;
-      d[(size_t)gy * w + gx] = (uint8_t)(v > 255 ? 255 : v);
+      d[(size_t)gy * dpitch + gx] = (uint8_t)(v > 255 ? 255 : v);
     }
   }
 }
 
-// Fast path for KS <= 8 taps (7x7 at the reference's scale 1.2 / 0.8): 64x32 output tile, DP4A row pass.
+// Fast path for KS <= 8 taps (7x7 at the reference's scale 1.2 / 0.8): 64x32 output tile staged by ONE TMA bulk-tensor
+// copy (plf_tma.cuh; border CTAs rebuild BORDER_REFLECT_101 inside shared memory), DP4A row pass.
 //   row pass : a thread produces 4 adjacent outputs of one row from three aligned 32-bit words of the staged tile;
 //              the KS byte window of each output is assembled with PRMT (byte_perm) and reduced with two DP4As against
 //              the packed u8 taps (taps <= 255, products summed exactly in 32 bits, result < 2^16);
@@ -145,30 +152,24 @@ __global__ void __launch_bounds__(256) k_blur_q8(const uint8_t* __restrict__ src
 #define BF_TW 64
 #define BF_TH 32
 template <int KS>
-__global__ void __launch_bounds__(256) k_blur_q8_fast(const uint8_t* __restrict__ src, size_t src_stride, int pitch, int w,
-                                                      int h, uint32_t tapsA, uint32_t tapsB, uint8_t* __restrict__ dst,
-                                                      size_t dst_stride) {
+__global__ void __launch_bounds__(256) k_blur_q8_fast(const __grid_constant__ CUtensorMap tmap, int z0, int w, int h,
+                                                      uint32_t tapsA, uint32_t tapsB, uint8_t* __restrict__ dst,
+                                                      size_t dst_stride, int dpitch) {
   constexpr int R = KS / 2;
   constexpr int RH = BF_TH + 2 * R;
-  constexpr int RP = ((BF_TW + 2 * R + 3) / 4) * 4 + 4;  // row pitch in bytes, multiple of 4, 4 spare
-  __shared__ __align__(16) uint8_t raw[RH][RP];
+  constexpr int RP = 80;     // TMA box width (bytes, multiple of 16)
+  constexpr int NEED = 72;   // columns the row pass reads (64 outputs + 2R taps, whole 32-bit words)
+  __shared__ __align__(128) uint8_t raw[RH][RP];
   __shared__ __align__(16) uint16_t hrow[RH][BF_TW];
-  const uint8_t* s = src + (size_t)blockIdx.z * src_stride;
+  __shared__ __align__(8) uint64_t bar;
   uint8_t* d = dst + (size_t)blockIdx.z * dst_stride;
   const int x0 = blockIdx.x * BF_TW, y0 = blockIdx.y * BF_TH, tid = threadIdx.x;
-  const int lane = tid & 31, wrp = tid >> 5;
-  const bool interior = x0 >= R && x0 + RP - R <= w && y0 >= R && y0 + BF_TH + R <= h;
-  if (interior) {  // four pixels per step (plf_load4)
-    for (int i = tid; i < RH * (RP / 4); i += 256) {
-      const int ry = i / (RP / 4), j = i - ry * (RP / 4);
-      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4_fast(s + (size_t)(y0 - R + ry) * pitch + (x0 - R + 4 * j));
-    }
-  } else {
-    for (int ry = wrp; ry < RH; ry += 8) {
-      const uint8_t* row = s + (size_t)lsd_reflect101(y0 - R + ry, h) * pitch;
-      for (int rx = lane; rx < RP; rx += 32) raw[ry][rx] = row[lsd_reflect101(x0 - R + rx, w)];
-    }
-  }
+  if (tid == 0) plf_mbar_init(&bar);
+  __syncthreads();
+  if (tid == 0) plf_tma_load_3d(&raw[0][0], &tmap, x0 - R, y0 - R, z0 + (int)blockIdx.z, &bar, RH * RP);
+  plf_mbar_wait(&bar, 0);
+  if (!(x0 >= R && x0 - R + NEED <= w && y0 >= R && y0 + BF_TH + R <= h))   // border tile: BORDER_REFLECT_101 in place
+    plf_tma_reflect_fix<RH, RP>(raw, x0 - R, y0 - R, w, h, NEED);
   __syncthreads();
   for (int it = tid; it < RH * (BF_TW / 4); it += 256) {
     const int ry = it >> 4, j = it & 15;  // BF_TW / 4 == 16 groups per row
@@ -202,7 +203,7 @@ __global__ void __launch_bounds__(256) k_blur_q8_fast(const uint8_t* __restrict_
 #pragma unroll
         for (int k = 0; k < KS; ++k) a += t[k] * v[r + k];
         const uint32_t o = (a + (1u << 15)) >> 16;
-        d[(size_t)gy * w + gx] = (uint8_t)(o > 255 ? 255 : o);
+        d[(size_t)gy * dpitch + gx] = (uint8_t)(o > 255 ? 255 : o);
       }
     }
   }
@@ -234,8 +235,8 @@ __device__ __forceinline__ float lsd_fast_atan2(float y, float x) {  // cv::fast
 struct __align__(16) LsdPix {
   float a;    // level-line angle in DEGREES exactly as cv::fastAtan2(gx,-gy) returns it (OpenCV stores a * DEG_TO_RADS as
               // f64; that product is re-formed where the f64 value is needed) or LSD_NOTDEF_F = undefined / used
+  uint32_t li; // index of the pixel's gradient in the (gx,gy) tables: the seed's unit vector is fetched from lut_seed[li]
   float c, s; // cosf / sinf of float(angle in radians)
-  float pad;
 };
 #define LSD_NOTDEF_F (-1024.f)
 
@@ -244,12 +245,14 @@ struct __align__(16) LsdPix {
 // context with exactly the device functions used elsewhere (16 MB, L2-resident), which turns ~200 dependent
 // instructions per defined pixel into one 16-byte load.
 #define LSD_LUT_DIM 1021
-__global__ void __launch_bounds__(256) k_lsd_build_lut(double rho, LsdPix* __restrict__ lut) {
+// lut_seed: the unit vector region_grow starts its sums from, float(cos(angle)), float(sin(angle)) of the f64 angle.
+__global__ void __launch_bounds__(256) k_lsd_build_lut(double rho, LsdPix* __restrict__ lut, float2* __restrict__ lut_seed) {
   const int i = blockIdx.x * 256 + threadIdx.x;
   if (i >= LSD_LUT_DIM * LSD_LUT_DIM) return;
   const int gx = i / LSD_LUT_DIM - 510, gy = i % LSD_LUT_DIM - 510;
   LsdPix e;
-  e.a = LSD_NOTDEF_F; e.c = 0.f; e.s = 0.f; e.pad = 0.f;
+  e.a = LSD_NOTDEF_F; e.c = 0.f; e.s = 0.f; e.li = (uint32_t)i;
+  float2 sv = make_float2(0.f, 0.f);
   const double norm = sqrt((double)(gx * gx + gy * gy) / 4.0);
   if (!(norm <= rho)) {
     const float adeg = lsd_fast_atan2((float)gx, (float)(-gy));
@@ -257,33 +260,36 @@ __global__ void __launch_bounds__(256) k_lsd_build_lut(double rho, LsdPix* __res
     const float af = (float)((double)adeg * LSD_DEG2RAD);  // region_grow: cos(float(angle)), sin(float(angle)), host libm -> glibc port
     e.c = glibc_cosf(af);
     e.s = glibc_sinf(af);
+    const double ad = (double)adeg * LSD_DEG2RAD;
+    sv = make_float2((float)cos(ad), (float)sin(ad));
   }
   lut[i] = e;
+  lut_seed[i] = sv;
 }
 
 __global__ void k_lsd_fill_guard(LsdPix* __restrict__ pix, size_t pix_stride, int guard, int nimg) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= guard * nimg) return;
   LsdPix e;
-  e.a = LSD_NOTDEF_F; e.c = 0.f; e.s = 0.f; e.pad = 0.f;
+  e.a = LSD_NOTDEF_F; e.c = 0.f; e.s = 0.f; e.li = 0u;
   pix[(size_t)(i / guard) * pix_stride + (i % guard)] = e;
 }
 
 // pix points at pixel (0,0) of image 0 (i.e. past the guard); image stride pix_stride.
 // One thread produces the same column of TWO consecutive rows: 6 independent byte loads (3 source rows) and up to 2
 // table loads in flight per thread instead of a 4-load + 1-load chain per pixel, stores still coalesced row by row.
-__global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int W, int H,
+__global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int IP, int W, int H,
                                                   const LsdPix* __restrict__ lut, int m2_min, size_t stride,
                                                   short2* __restrict__ gxy, LsdPix* __restrict__ pix, size_t pix_stride,
                                                   int* __restrict__ maxmag2) {
   const int x = blockIdx.x * 256 + threadIdx.x, y0 = blockIdx.y * 2, im = blockIdx.z;
   int mag2 = -1;
   if (x < W) {
-    const uint8_t* p = img + (size_t)im * img_stride + (size_t)y0 * W + x;
+    const uint8_t* p = img + (size_t)im * img_stride + (size_t)y0 * IP + x;   // IP = row pitch of the image
     const bool xin = x < W - 1, r0ok = xin && y0 < H - 1, r1ok = xin && y0 + 1 < H - 1;
     int a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0;
-    if (r0ok) { a0 = p[0]; a1 = p[1]; b0 = p[W]; b1 = p[W + 1]; }
-    if (r1ok) { c0 = p[2 * W]; c1 = p[2 * W + 1]; }
+    if (r0ok) { a0 = p[0]; a1 = p[1]; b0 = p[IP]; b1 = p[IP + 1]; }
+    if (r1ok) { c0 = p[2 * IP]; c1 = p[2 * IP + 1]; }
     short2 g[2] = {make_short2(0, 0), make_short2(0, 0)};
     int li[2] = {-1, -1};
     if (r0ok) {
@@ -453,15 +459,15 @@ __device__ __forceinline__ bool lsd_aligned_rad(double a, double theta, double p
 
 // The warp that grows an image is the only reader and writer of that image's records while the kernel runs, and a CTA
 // never leaves its SM, so L1-cached loads (ld.ca) are coherent with the warp's own stores.
-// Two loads (8 + 4 bytes) rather than one 16-byte load: the 4th word of the record is never used, and ptxas recycled
+// Two loads (4 + 8 bytes) rather than one 16-byte load: the 2nd word of the record is not used here, and ptxas recycled
 // the register it would land in (as a ballot result) while the load was still in flight - a write-after-write wait on
 // the load that cost a quarter of the kernel's time.
 struct LsdRec { float a, c, s; };
 __device__ __forceinline__ LsdRec lsd_load_pix(const LsdPix* p) {
-  const float2 ac = __ldca(reinterpret_cast<const float2*>(p));
+  const float2 cs = __ldca(reinterpret_cast<const float2*>(&p->c));
   LsdRec r;
-  r.a = ac.x; r.c = ac.y;
-  r.s = __ldca(&p->s);
+  r.a = __ldca(&p->a);
+  r.c = cs.x; r.s = cs.y;
   return r;
 }
 __device__ __forceinline__ void lsd_prefetch(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
@@ -653,191 +659,177 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
   if (lane == 0) nregions[im] = nreg_out;
 }
 
-// ---- region growing, one THREAD per image ------------------------------------------------------------------------
-// The warp-per-image kernel above is bound by its per-point dependent chain: ~116 warp instructions per region point, a
-// quarter of them cross-lane (VOTE / SHFL at 13-25 cycles each) - ~1000 cycles per point, 82.7 k points per KITTI frame,
-// whatever the batch size.  The algorithm has no intra-image parallelism to offer, so this kernel
-// removes the cross-lane traffic instead: ONE THREAD grows one image, with everything in its own registers - the 8
-// neighbour records (8 independent 16-byte loads), the reference's row-major decision order as straight-line code, the
-// same deferred-angle bounds (identical arithmetic, so identical decisions).  LANES images share a warp (LANES threads
-// per CTA), which divides the issue slots per point by LANES; the threads of a warp diverge freely (seed scan vs.
-// growing, different acceptance slots) and only ever wait for their own loads.
-//   * queue: per-thread ring of LSD_TQCAP entries in shared memory (the region's points, re-read in order), global
-//     memory (regpts, which is the output anyway) beyond that;
-//   * look-ahead: when a pixel joins the region the records its own 3x3 pass will read (PF_R rows around it) are
-//     prefetched into L1, so the dependent loads of the pass are L1 hits;
-//   * seed scan: 8 seeds per step, their indices loaded two steps and their records prefetched one step ahead.
-#define LSD_TQCAP 128
-template <int LANES, int PF_R, int PF_C>
-__global__ void __launch_bounds__(LANES) k_lsd_grow_t(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
-                                                       const uint32_t* __restrict__ order_all,
-                                                       const int* __restrict__ nseeds, int nimg, double prec,
-                                                       float prec_deg, int min_reg_size,
-                                                       uint32_t* __restrict__ regpts_all, uint4* __restrict__ regions_all,
-                                                       int max_regions, int* __restrict__ nregions,
-                                                       int* __restrict__ overflow) {
-  __shared__ uint32_t q_all[LANES][LSD_TQCAP];
-  const unsigned wmask = __activemask();   // the LANES threads of this (partial) warp
-  const int im_raw = blockIdx.x * LANES + threadIdx.x;
-  const bool valid = im_raw < nimg;
-  const int im = valid ? im_raw : 0;       // threads past the last image idle through the loop (they must keep converging)
-  uint32_t* const q = q_all[threadIdx.x];
+// ---- region growing, LANE per image with helper lanes ("grow_s") ---------------------------------------------------
+// The warp-per-image kernel above spends ~116 warp instructions per region point, a quarter of them cross-lane (VOTE /
+// SHFL on the dependent chain): ~1000 cycles per point, 82.6 k points per KITTI frame, and at 3072 images it also holds
+// half of the SMs' issue slots.  Here ONE LANE grows one image with the whole decision chain in its own registers (8
+// neighbour records, the reference's row-major order as straight-line code, the same deferred-angle bounds - identical
+// arithmetic, identical decisions), LG images per warp.  The lanes stay in lockstep: every iteration of the main loop
+// is  [scan step, if some grower needs its next seed]  ->  [one region point per grower]  ->  [look-ahead prefetch],
+// with the warp converged between the parts.  The other lanes are HELPERS, 7 per grower (lanes 7g..7g+6):
+//   * seed scan: the 7 lanes examine 7 consecutive seeds of the grower's order list at once (ballot + first-hit), and
+//     keep the records of the seeds two steps ahead and the order list itself flowing into L1;
+//   * look-ahead: after every step the 7 lanes prefetch a 7-row x 4-sector window around each pixel that joined the
+//     grower's region (the cells the next two breadth-first layers will examine), one row per lane - the grower's own
+//     loads are then L1 hits.
+// No f64 trigonometry in the loop: the seed's unit vector (float(cos(double angle)), as the reference forms it) comes from
+// a second table keyed by the gradient (lut_seed, index carried in the record), fetched when the region starts.
+#define LSD_SQCAP 256
+__device__ __noinline__ float lsd_region_angle(float sumdy, float sumdx) { return lsd_fast_atan2(sumdy, sumdx); }
+__device__ __noinline__ bool lsd_aligned_exact(float a_deg, float th_deg, double prec) {
+  return lsd_aligned_rad((double)a_deg * LSD_DEG2RAD, (double)th_deg * LSD_DEG2RAD, prec);
+}
+// distance between two level-line angles in degrees, as the reference folds it (d > 180 -> 360 - d).  NOTDEF (-1024) on
+// either side lands far above any threshold without a separate test: |a - th| >= 664 and |360 - |a - th|| >= 304.
+__device__ __forceinline__ float lsd_dist_deg(float a, float th) {
+  const float d = fabsf(__fsub_rn(a, th));
+  return fminf(d, fabsf(__fsub_rn(360.f, d)));
+}
+
+template <int LG>
+__global__ void __launch_bounds__(32) k_lsd_grow_s(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
+                                                   const uint32_t* __restrict__ order_all, const int* __restrict__ nseeds,
+                                                   int nimg, const float2* __restrict__ lut_seed, double prec,
+                                                   float prec_deg, int min_reg_size, uint32_t* __restrict__ regpts_all,
+                                                   uint4* __restrict__ regions_all, int max_regions,
+                                                   int* __restrict__ nregions, int* __restrict__ overflow) {
+  __shared__ uint32_t q_all[LG][LSD_SQCAP];
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x;
+  const bool grower = lane < LG;
+  // ---- this lane as a grower: image blockIdx.x * LG + lane
+  const int im_raw = blockIdx.x * LG + lane;
+  const bool gvalid = grower && im_raw < nimg;
+  const int im = gvalid ? im_raw : 0;
   LsdPix* const pix = pix_all + (size_t)im * pix_stride;
-  const char* const pb = reinterpret_cast<const char*>(pix);
-  const uint32_t* const order = order_all + (size_t)im * stride;
+  char* const pb = reinterpret_cast<char*>(pix);
   uint32_t* const regpts = regpts_all + (size_t)im * stride;
   uint4* const regions = regions_all + (size_t)im * max_regions;
-  const int ns = valid ? nseeds[im] : 0;
+  uint32_t* const q = q_all[grower ? lane : 0];
+  const int ns = gvalid ? nseeds[im] : 0;
+  // ---- this lane as a helper of group hg = lane / 7 (row hj - 3 of the look-ahead window, seed hj of the scan group)
+  const int hg = lane / 7, hj = lane - 7 * hg;
+  const bool helper = lane < 28 && hg < LG && blockIdx.x * LG + hg < nimg;
+  const int him = helper ? blockIdx.x * LG + hg : 0;
+  const char* const hpb = reinterpret_cast<const char*>(pix_all + (size_t)him * pix_stride);
+  const uint32_t* const horder = order_all + (size_t)him * stride;
+  const int hns = helper ? nseeds[him] : 0;
+  const uint32_t* const hq = q_all[helper ? hg : 0];
+  const int hrow = (hj - 3) * W - 3;   // first record of this helper's window row, relative to the centre pixel
+
   const int noff[8] = {-W - 1, -W, -W + 1, -1, 1, W - 1, W, W + 1};  // the reference's row-major 3x3 order, centre skipped
-  const float margin0 = prec_deg <= 60.f ? LSD_MARGIN0 : 1e30f;
+  const float margin0 = prec_deg <= 60.f ? LSD_MARGIN0 : 1e30f;   // ang_th near 90 deg: evaluate every angle (see k_lsd_grow)
   const float dmax = prec_deg + LSD_MARGIN0;
-  // seed scan state: the seed order is consumed in groups of 8.  gA = the group being examined (position sbase), gB and
-  // gC = the next two groups, whose records are already being prefetched, gD = the group after those (indices loaded,
-  // records not yet requested): record prefetches run two groups, index loads three groups ahead of the examination.
-  uint32_t gA[8], gB[8], gC[8], gD[8];
-  int sbase = 0, gpos = 0;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    gA[j] = j < ns ? __ldg(&order[j]) : 0u;
-    gB[j] = 8 + j < ns ? __ldg(&order[8 + j]) : 0u;
-    gC[j] = 16 + j < ns ? __ldg(&order[16 + j]) : 0u;
-    gD[j] = 24 + j < ns ? __ldg(&order[24 + j]) : 0u;
-  }
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    if (j < ns) lsd_prefetch(&pix[gA[j]]);
-    if (8 + j < ns) lsd_prefetch(&pix[gB[j]]);
-    if (16 + j < ns) lsd_prefetch(&pix[gC[j]]);
-  }
-  uint32_t cursor = 0;
+  enum { SCAN = 0, GROW = 1, DONE = 2 };
+  int mode = gvalid && ns > 0 ? SCAN : DONE;
+  int spos = 0;                 // next position of the seed order to examine
+  uint32_t cursor = 0;          // first free entry of regpts
   int nreg_out = 0;
-  // region state
-  bool done = ns <= 0, active = false, fresh = true;
   uint32_t r = 0, nreg = 0;
-  float th = 0.f, sumdx = 0.f, sumdy = 0.f, margin = 0.f, inv0 = 1.02f, lo = 0.f, hi = 0.f;
-  double th_seed = 0.0;
-  // The threads of a warp must meet again at the top of every step: each then executes either the scan step or the growing
-  // step, the threads in the same kind of step in lockstep.  (Without the explicit convergence point the threads drift apart
-  // after the first divergent branch and the warp executes them one after the other: measured 3x slower than one warp
-  // per image.)
+  float th = 0.f, a_seed = 0.f, sumdx = 0.f, sumdy = 0.f, margin = 0.f, inv0 = 1.02f, lo = 0.f, hi = 0.f;
+  bool fresh = true;
+
   for (;;) {
-    if (__all_sync(wmask, done)) break;
-    if (!done && !active) {
-      // ---- seed scan: the seeds gpos.. of the current group (their records were prefetched two groups ago; they are
-      // re-read after every region, which may have used some of them)
-      float a8[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a8[j] = (j >= gpos && sbase + j < ns) ? __ldca(&pix[gA[j]].a) : LSD_NOTDEF_F;
-      int hit = -1;
-#pragma unroll
-      for (int j = 7; j >= 0; --j)
-        if (a8[j] != LSD_NOTDEF_F) hit = j;
-      if (hit < 0) {  // next group
-        sbase += 8;
-        gpos = 0;
-        if (sbase >= ns) {
-          done = true;
+    const unsigned live = __ballot_sync(FULL, mode != DONE);
+    if (!live) break;
+    // ---------------- seed scan (whole warp, for the groups whose grower is between regions) ----------------
+    if (__ballot_sync(FULL, mode == SCAN)) {
+      const int g_spos = __shfl_sync(FULL, spos, hg & 3);
+      const int g_mode = __shfl_sync(FULL, mode, hg & 3);
+      const bool act = helper && g_mode == SCAN;
+      const int pos = g_spos + hj;
+      uint32_t sidx = 0;
+      float a = LSD_NOTDEF_F;
+      if (act && pos < hns) {
+        sidx = __ldg(&horder[pos]);
+        a = __ldca(reinterpret_cast<const float*>(hpb + (size_t)sidx * 16));
+        if (pos + 14 < hns) lsd_prefetch(hpb + (size_t)__ldg(&horder[pos + 14]) * 16);   // record of the seed two steps ahead
+        if (hj == 0 && pos + 64 < hns) lsd_prefetch(&horder[pos + 64]);                    // the order list itself
+      }
+      const unsigned hits = __ballot_sync(FULL, a != LSD_NOTDEF_F);
+      int src = 0;
+      bool start = false;
+      if (grower && mode == SCAN) {
+        const unsigned f = (hits >> (7 * lane)) & 0x7Fu;
+        if (f) {
+          const int jj = __ffs(f) - 1;
+          src = 7 * lane + jj;
+          spos += jj + 1;
+          start = true;
         } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            gA[j] = gB[j];
-            gB[j] = gC[j];
-            gC[j] = gD[j];
-            gD[j] = sbase + 24 + j < ns ? __ldg(&order[sbase + 24 + j]) : 0u;
-          }
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (sbase + 16 + j < ns) lsd_prefetch(&pix[gC[j]]);
-          if (sbase + 96 < ns) asm volatile("prefetch.global.L2 [%0];" ::"l"(&order[sbase + 96]));
+          spos += 7;
+          if (spos >= ns) mode = DONE;
         }
-      } else {
-        uint32_t sidx = gA[0];
-        float a0 = a8[0];
-#pragma unroll
-        for (int j = 1; j < 8; ++j)
-          if (hit == j) { sidx = gA[j]; a0 = a8[j]; }
-        gpos = hit + 1;
-        // region_grow: seed
-        th = a0;
-        th_seed = (double)th * LSD_DEG2RAD;
+      }
+      const uint32_t s_sidx = __shfl_sync(FULL, sidx, src);
+      const float s_a = __shfl_sync(FULL, a, src);
+      if (start) {  // region_grow: the seed
+        const uint32_t li = __ldca(reinterpret_cast<const uint32_t*>(pb + (size_t)s_sidx * 16 + 4));
+        const float2 sv = __ldg(&lut_seed[li]);     // float(cos(double angle)), float(sin(double angle))
+        *reinterpret_cast<float*>(pb + (size_t)s_sidx * 16) = LSD_NOTDEF_F;
+        regpts[cursor] = s_sidx;
+        q[0] = s_sidx;
+        r = 0; nreg = 1;
+        th = s_a; a_seed = s_a;
+        sumdx = sv.x; sumdy = sv.y;
         margin = margin0; inv0 = 1.02f;
         lo = prec_deg - margin; hi = prec_deg + margin;
         fresh = true;
-        pix[sidx].a = LSD_NOTDEF_F;
-        regpts[cursor] = sidx;
-        q[0] = sidx;
-        r = 0; nreg = 1;
-        active = true;
-#pragma unroll
-        for (int dr = -PF_R; dr <= PF_R; ++dr)
-#pragma unroll
-          for (int dc = -PF_C; dc <= PF_C; dc += 2) lsd_prefetch(pb + (long long)((int)sidx + dr * W + dc) * 16);
+        mode = GROW;
       }
-    } else if (!done) {
-      // ---- one region point: its 3x3 neighbourhood in the reference's order ----
-      const uint32_t pt = (nreg - r <= LSD_TQCAP) ? q[r & (LSD_TQCAP - 1)] : __ldcg(&regpts[cursor + r]);
+      // look-ahead window of the new seeds, by the helpers of their groups
+      const uint32_t st = __shfl_sync(FULL, start ? s_sidx : 0xFFFFFFFFu, hg & 3);
+      if (helper && st != 0xFFFFFFFFu) {
+        const char* p = hpb + ((long long)(int)st + hrow) * 16;
+        lsd_prefetch(p); lsd_prefetch(p + 32); lsd_prefetch(p + 64); lsd_prefetch(p + 96);
+      }
+    }
+    // ---------------- one region point per grower: its 3x3 neighbourhood in the reference's order ----------------
+    const uint32_t nreg0 = nreg;
+    if (mode == GROW) {
+      const uint32_t pt = (nreg - r <= LSD_SQCAP) ? q[r & (LSD_SQCAP - 1)] : __ldcg(&regpts[cursor + r]);
       float4 rec[8];
 #pragma unroll
       for (int k = 0; k < 8; ++k) rec[k] = __ldca(reinterpret_cast<const float4*>(pb + (long long)((int)pt + noff[k]) * 16));
-      // distances to the last evaluated region angle, all eight at once: th only changes on the (rare) re-evaluation
-      // below, which recomputes the distances of the slots still to come
       float d8[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        float d = fabsf(__fsub_rn(rec[k].x, th));
-        if (d > 180.f) d = __fsub_rn(360.f, d);
-        d8[k] = rec[k].x == LSD_NOTDEF_F ? 1e30f : d;   // NOTDEF (undefined or used): never aligned
-      }
-      const uint32_t nreg0 = nreg;
+      for (int k = 0; k < 8; ++k) d8[k] = lsd_dist_deg(rec[k].x, th);
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
-        if (d8[k] > hi) continue;  // clearly not aligned whatever the exact region angle is (or NOTDEF)
-        if (!(d8[k] < lo)) {       // inside the band: the decision needs the exact angle
-          if (!fresh) {
-            th = lsd_fast_atan2(sumdy, sumdx);
-            inv0 = __fmul_rn(rsqrtf(__fadd_rn(__fmul_rn(sumdx, sumdx), __fmul_rn(sumdy, sumdy))), 1.02f);
-            margin = margin0;
-            lo = prec_deg - margin; hi = prec_deg + margin;
-            fresh = true;
+        if (d8[k] <= hi) {              // aligned or undecided (clearly not aligned, used and undefined cells fall through)
+          bool acc = d8[k] < lo;        // certainly aligned whatever the exact region angle is
+          if (!acc) {                   // inside the band: the decision needs the exact angle
+            if (!fresh) {
+              th = lsd_region_angle(sumdy, sumdx);
+              inv0 = __fmul_rn(rsqrtf(__fadd_rn(__fmul_rn(sumdx, sumdx), __fmul_rn(sumdy, sumdy))), 1.02f);
+              margin = margin0;
+              lo = prec_deg - margin; hi = prec_deg + margin;
+              fresh = true;
 #pragma unroll
-            for (int kk = k; kk < 8; ++kk) {
-              float d = fabsf(__fsub_rn(rec[kk].x, th));
-              if (d > 180.f) d = __fsub_rn(360.f, d);
-              d8[kk] = rec[kk].x == LSD_NOTDEF_F ? 1e30f : d;
+              for (int kk = k; kk < 8; ++kk) d8[kk] = lsd_dist_deg(rec[kk].x, th);
             }
-            if (d8[k] > hi) continue;
+            if (d8[k] <= hi) acc = d8[k] < lo || lsd_aligned_exact(rec[k].x, th, prec);
           }
-          if (!(d8[k] < lo) && !lsd_aligned_rad((double)rec[k].x * LSD_DEG2RAD, (double)th * LSD_DEG2RAD, prec)) continue;
+          if (acc) {  // mark used, append to the region / the queue, update the running sums and the bound
+            const int ai = (int)pt + noff[k];
+            *reinterpret_cast<float*>(pb + (long long)ai * 16) = LSD_NOTDEF_F;
+            regpts[cursor + nreg] = (uint32_t)ai;
+            q[nreg & (LSD_SQCAP - 1)] = (uint32_t)ai;
+            ++nreg;
+            sumdx = __fadd_rn(sumdx, rec[k].z);
+            sumdy = __fadd_rn(sumdy, rec[k].w);
+            margin = __fmaf_rn(fminf(__fadd_rn(d8[k], margin), dmax), inv0, margin);
+            lo = prec_deg - margin; hi = prec_deg + margin;
+            fresh = false;
+          }
         }
-        // accepted: mark used, append to the region / the queue, update the running sums and the bound
-        const int ai = (int)pt + noff[k];
-        *reinterpret_cast<float*>(const_cast<char*>(pb) + (long long)ai * 16) = LSD_NOTDEF_F;
-        regpts[cursor + nreg] = (uint32_t)ai;
-        q[nreg & (LSD_TQCAP - 1)] = (uint32_t)ai;
-        if (nreg == 1) {  // first member: the seed's own unit vector (f64 cos / sin, as the reference)
-          sumdx = (float)cos(th_seed);
-          sumdy = (float)sin(th_seed);
-        }
-        ++nreg;
-        sumdx = __fadd_rn(sumdx, rec[k].y);
-        sumdy = __fadd_rn(sumdy, rec[k].z);
-        margin = __fmaf_rn(fminf(__fadd_rn(d8[k], margin), dmax), inv0, margin);
-        lo = prec_deg - margin; hi = prec_deg + margin;
-        fresh = false;
-      }
-      // look-ahead for the pixels that joined: the rows their own pass will read
-      for (uint32_t j = nreg0; j < nreg; ++j) {
-        const int p = (int)q[j & (LSD_TQCAP - 1)];
-#pragma unroll
-        for (int dr = -PF_R; dr <= PF_R; ++dr)
-#pragma unroll
-          for (int dc = -PF_C; dc <= PF_C; dc += 2) lsd_prefetch(pb + (long long)(p + dr * W + dc) * 16);
       }
       if (++r == nreg) {  // region complete
         if ((int)nreg >= min_reg_size) {
           if (nreg_out < max_regions) {
-            const double reg_angle = nreg == 1 ? th_seed : (double)(fresh ? th : lsd_fast_atan2(sumdy, sumdx)) * LSD_DEG2RAD;
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(reg_angle);
+            // nreg >= min_reg_size > 1: the angle of the sum (the seed's own angle only matters for 1-pixel regions)
+            const float ang = nreg == 1 ? a_seed : (fresh ? th : lsd_region_angle(sumdy, sumdx));
+            const unsigned long long bits = (unsigned long long)__double_as_longlong((double)ang * LSD_DEG2RAD);
             regions[nreg_out] = make_uint4(cursor, nreg, (uint32_t)bits, (uint32_t)(bits >> 32));
             ++nreg_out;
             cursor += nreg;
@@ -845,11 +837,26 @@ __global__ void __launch_bounds__(LANES) k_lsd_grow_t(LsdPix* __restrict__ pix_a
             *overflow = 1;
           }
         }
-        active = false;
+        mode = spos < ns ? SCAN : DONE;
+      }
+    }
+    __syncwarp(FULL);
+    // ---------------- look-ahead for the pixels that joined, by the helpers ----------------
+    {
+      const int cnt = (int)(nreg - nreg0);   // 0 for helpers-only lanes and for growers that did not grow
+      const int g_cnt = __shfl_sync(FULL, cnt, hg & 3);
+      const uint32_t g_n0 = __shfl_sync(FULL, nreg0, hg & 3);
+      const int maxc = __reduce_max_sync(FULL, helper ? g_cnt : 0);
+      for (int j = 0; j < maxc; ++j) {
+        if (helper && j < g_cnt) {
+          const uint32_t ai = hq[(g_n0 + j) & (LSD_SQCAP - 1)];
+          const char* p = hpb + ((long long)(int)ai + hrow) * 16;
+          lsd_prefetch(p); lsd_prefetch(p + 32); lsd_prefetch(p + 64); lsd_prefetch(p + 96);
+        }
       }
     }
   }
-  if (valid) nregions[im] = nreg_out;
+  if (gvalid) nregions[im] = nreg_out;
 }
 
 // ---- rectangle fit -------------------------------------------------------------------------------------------
@@ -1072,7 +1079,7 @@ static void lsd_release(LsdState* s) {
   }
   cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap); cudaFree(s->rect_perm);
   cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->overflow); cudaFree(s->rs_tab);
-  cudaFree(s->grad_lut);
+  cudaFree(s->grad_lut); cudaFree(s->seed_lut);
 }
 
 extern "C" void plf_lsd_free(plf_ctx* ctx) {
@@ -1147,12 +1154,13 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   s->min_reg_size = (int)(size_t)(-LOG_NT / log10(s->p));
   s->max_regions = ctx->limits.max_segments;
   s->max_lines = ctx->limits.max_lines;
-  const size_t N = (size_t)nimg, A = (size_t)w * h, As = (size_t)s->ws * s->hs;
+  s->bp = plf_pitch16(w); s->sp = plf_pitch16(s->ws);
+  const size_t N = (size_t)nimg, A = (size_t)s->bp * h, As = (size_t)s->ws * s->hs, Asp = (size_t)s->sp * s->hs;
   s->pix_stride = As + (size_t)s->ws + 1;
   for (s->m2_min = 0; s->m2_min <= 2 * 510 * 510; ++s->m2_min)  // same double expression as the kernels
     if (!(sqrt((double)s->m2_min / 4.0) <= s->rho)) break;
   PLF_CUDA(ctx, cudaMalloc(&s->blur, A * N + 64));      // + slack: plf_load4 may read the aligned word that holds the
-  PLF_CUDA(ctx, cudaMalloc(&s->scaled, As * N + 64));   // last byte of the last image
+  PLF_CUDA(ctx, cudaMalloc(&s->scaled, Asp * N + 64));  // last byte of the last image
   PLF_CUDA(ctx, cudaMalloc(&s->binmap, As * N * sizeof(uint16_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->rect_perm, N * s->max_regions * sizeof(uint32_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->maxmag2, N * sizeof(int)));
@@ -1181,7 +1189,8 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   PLF_CUDA(ctx, cudaMalloc(&s->overflow, sizeof(int)));
   PLF_CUDA(ctx, cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream));
   PLF_CUDA(ctx, cudaMalloc(&s->grad_lut, (size_t)LSD_LUT_DIM * LSD_LUT_DIM * sizeof(LsdPix)));
-  k_lsd_build_lut<<<(LSD_LUT_DIM * LSD_LUT_DIM + 255) / 256, 256, 0, ctx->stream>>>(s->rho, s->grad_lut);
+  PLF_CUDA(ctx, cudaMalloc(&s->seed_lut, (size_t)LSD_LUT_DIM * LSD_LUT_DIM * sizeof(float2)));
+  k_lsd_build_lut<<<(LSD_LUT_DIM * LSD_LUT_DIM + 255) / 256, 256, 0, ctx->stream>>>(s->rho, s->grad_lut, s->seed_lut);
   PLF_LAUNCH_CHECK(ctx);
   PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (s->scale != 1.0) {
@@ -1202,16 +1211,16 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
 // other work: `pre` = blur, resample, gradient and seed ordering (bandwidth-bound), `grow` = region growing, rectangle
 // fit and the KeyLine stage (latency-bound).  `par` selects the buffer set that carries data from pre to grow.
 // State must be prepared for >= img0+n images.  Enqueued on ctx->cur; results stay on the device.
-plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int par, int img0, int n) {
+plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int pitch, int w, int h, int par, int img0, int n) {
   LsdState* s = ctx->lsd;
   if (!s || s->w != w || s->h != h || s->nimg < img0 + n || (par && !s->two_parities))
     return plf_fail(ctx, PLF_ERR_STATE, "plf_lsd_pre_range: state not prepared for this image range");
   cudaStream_t cs = ctx->cur;
   const int W = s->ws, H = s->hs;
-  const size_t As = (size_t)W * H, A = (size_t)w * h, o = (size_t)img0;
+  const size_t As = (size_t)W * H, A = (size_t)s->bp * h, Asp = (size_t)s->sp * H, o = (size_t)img0;
   const uint8_t* imgs = d_imgs + o * img_stride;
   uint8_t* blur = s->blur + o * A;
-  uint8_t* scaled_buf = s->scaled + o * As;
+  uint8_t* scaled_buf = s->scaled + o * Asp;
   short2* gxy = s->gxy[par] + o * As;
   LsdPix* pix = s->pix[par] + o * s->pix_stride + (s->ws + 1);  // pixel (0,0) of the first image of the range
   uint16_t* binmap = s->binmap + o * As;
@@ -1224,27 +1233,42 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
   plf_status st;
   const uint8_t* scaled = imgs;
   size_t scaled_stride = img_stride;
+  int scaled_pitch = pitch;
   if (s->scale != 1.0) {
     if (s->ksize == 7 || s->ksize == 5) {
+      // tensor map of the source images (two cached slots: the pipeline alternates between its two upload buffers)
+      if (s->tm_stride != img_stride || s->tm_pitch != pitch || s->tm_nimg < img0 + n) {
+        s->tm_src[0] = s->tm_src[1] = nullptr;
+        s->tm_stride = img_stride; s->tm_pitch = pitch; s->tm_nimg = std::max(s->nimg, img0 + n);
+      }
+      int slot = -1;
+      for (int k = 0; k < 2; ++k) if (s->tm_src[k] == d_imgs) slot = k;
+      if (slot < 0) {
+        slot = s->tm_src[0] ? (s->tm_src[1] ? 0 : 1) : 0;
+        if (!plf_tma_encode_u8(&s->tm_blur[slot], d_imgs, w, h, s->tm_nimg, pitch, img_stride, 80, BF_TH + s->ksize - 1))
+          return plf_fail(ctx, PLF_ERR_CUDA, "LSD: cuTensorMapEncodeTiled failed for the source images (pitch %d, stride %zu)", pitch, img_stride);
+        s->tm_src[slot] = d_imgs;
+      }
       uint32_t tA = 0, tB = 0;
       for (int k = 0; k < s->ksize; ++k) (k < 4 ? tA : tB) |= (uint32_t)s->taps[k] << (8 * (k & 3));
       dim3 gf((w + BF_TW - 1) / BF_TW, (h + BF_TH - 1) / BF_TH, n);
-      if (s->ksize == 7) k_blur_q8_fast<7><<<gf, 256, 0, cs>>>(imgs, img_stride, w, w, h, tA, tB, blur, A);
-      else k_blur_q8_fast<5><<<gf, 256, 0, cs>>>(imgs, img_stride, w, w, h, tA, tB, blur, A);
+      if (s->ksize == 7) k_blur_q8_fast<7><<<gf, 256, 0, cs>>>(s->tm_blur[slot], img0, w, h, tA, tB, blur, A, s->bp);
+      else k_blur_q8_fast<5><<<gf, 256, 0, cs>>>(s->tm_blur[slot], img0, w, h, tA, tB, blur, A, s->bp);
     } else {
       dim3 gb((w + BQ_TW - 1) / BQ_TW, (h + BQ_TH - 1) / BQ_TH, n);
-      k_blur_q8<<<gb, 256, 0, cs>>>(imgs, img_stride, w, w, h, s->ksize / 2, blur, A);
+      k_blur_q8<<<gb, 256, 0, cs>>>(imgs, img_stride, pitch, w, h, s->ksize / 2, blur, A, s->bp);
     }
     PLF_LAUNCH_CHECK(ctx);
     plf_mark(ctx, "lsd.k_blur_q8");
-    st = plf_launch_resize_exact(ctx, blur, A, w, h, scaled_buf, As, W, H, s->rs_tab + s->rs_x_off, s->rs_tab + s->rs_y_off, n);
+    st = plf_launch_resize_exact(ctx, blur, A, s->bp, w, h, scaled_buf, Asp, s->sp, W, H, s->rs_tab + s->rs_x_off, s->rs_tab + s->rs_y_off, n);
     if (st) return st;
     plf_mark(ctx, "lsd.k_resize_exact");
     scaled = scaled_buf;
-    scaled_stride = As;
+    scaled_stride = Asp;
+    scaled_pitch = s->sp;
   }
   PLF_CUDA(ctx, cudaMemsetAsync(maxmag2, 0xFF, (size_t)n * sizeof(int), cs));  // -1
-  k_lsd_grad<<<dim3((W + 255) / 256, (H + 1) / 2, n), 256, 0, cs>>>(scaled, scaled_stride, W, H, s->grad_lut, s->m2_min, As, gxy, pix, s->pix_stride, maxmag2);
+  k_lsd_grad<<<dim3((W + 255) / 256, (H + 1) / 2, n), 256, 0, cs>>>(scaled, scaled_stride, scaled_pitch, W, H, s->grad_lut, s->m2_min, As, gxy, pix, s->pix_stride, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
   k_lsd_rowhist<<<dim3(nchunks, n), 256, 0, cs>>>(gxy, s->m2_min, As, W, H, s->n_bins, nchunks, maxmag2, binmap, rowcnt);
@@ -1277,37 +1301,26 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   plf_keyline* kls = s->kls[par] + o * s->max_lines;
   plf_keyline* kls_all = s->kls_all[par] + o * s->max_regions;
   int* nlines = s->nlines[par] + o;
-  // default: the warp-per-image kernel; PLF_GROW_CFG selects a thread-per-image variant (A/B measurements).
-  // PLF_GROW_CFG = "<lanes><pf_r><pf_c>" picks one of the compiled look-ahead variants (tuning).
+  // PLF_GROW_CFG: 0 = the warp-per-image kernel, 1..4 = k_lsd_grow_s with that many images per warp (A/B measurements).
   static const int grow_mode = [] {
     const char* c = getenv("PLF_GROW_CFG");
-    return c ? atoi(c) : -1;   // measured on B200 (3072 images): warp 49.7 ms, thread-per-image 146 (4 lanes) .. 230 ms (16 lanes)
+    return c ? atoi(c) : 0;
   }();
-#define GROW_T(L, R, C)                                                                                                  \
-  k_lsd_grow_t<L, R, C><<<(n + L - 1) / L, L, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, n, s->prec,             \
-                                                       (float)(s->p * 180.0), s->min_reg_size, regpts, regions,          \
-                                                       s->max_regions, nregions, s->overflow)
+#define GROW_S(L)                                                                                                        \
+  k_lsd_grow_s<L><<<(n + L - 1) / L, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, n, s->seed_lut, s->prec,     \
+                                                  (float)(s->p * 180.0), s->min_reg_size, regpts, regions,               \
+                                                  s->max_regions, nregions, s->overflow)
   switch (grow_mode) {
-    case -1:
+    case 1: GROW_S(1); break;
+    case 2: GROW_S(2); break;
+    case 3: GROW_S(3); break;
+    case 4: GROW_S(4); break;
+    default:
       k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
                                    regions, s->max_regions, nregions, s->overflow);
       break;
-    case 111: GROW_T(1, 1, 1); break;
-    case 121: GROW_T(1, 2, 1); break;
-    case 211: GROW_T(2, 1, 1); break;
-    case 221: GROW_T(2, 2, 1); break;
-    case 411: GROW_T(4, 1, 1); break;
-    case 421: GROW_T(4, 2, 1); break;
-    case 423: GROW_T(4, 2, 3); break;
-    case 433: GROW_T(4, 3, 3); break;
-    case 811: GROW_T(8, 1, 1); break;
-    case 823: GROW_T(8, 2, 3); break;
-    case 833: GROW_T(8, 3, 3); break;
-    case 1621: GROW_T(16, 2, 1); break;
-    case 3221: GROW_T(32, 2, 1); break;
-    default: GROW_T(8, 2, 1); break;
   }
-#undef GROW_T
+#undef GROW_S
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grow");
   uint32_t* perm = s->rect_perm + o * s->max_regions;
@@ -1326,10 +1339,10 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   return PLF_OK;
 }
 
-plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg) {
+plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int pitch, int w, int h, int nimg) {
   plf_status st = plf_lsd_prepare(ctx, w, h, nimg, false);
   if (st) return st;
-  if ((st = plf_lsd_pre_range(ctx, d_imgs, img_stride, w, h, 0, 0, nimg))) return st;
+  if ((st = plf_lsd_pre_range(ctx, d_imgs, img_stride, pitch, w, h, 0, 0, nimg))) return st;
   return plf_lsd_grow_range(ctx, w, h, 0, 0, nimg);
 }
 
@@ -1358,10 +1371,11 @@ extern "C" plf_status plf_lsd(plf_ctx* ctx, const uint8_t* img, int w, int h, in
   if (!ctx || !img || !n_out || w < 3 || h < 3 || stride < w || cap < 0 || (cap > 0 && !segs))
     return plf_fail(ctx, PLF_ERR_INVALID, "plf_lsd: bad arguments");
   PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-  uint8_t* dimg = (uint8_t*)plf_scratch(ctx, 4, (size_t)w * h);
+  const int pitch = plf_pitch16(w);
+  uint8_t* dimg = (uint8_t*)plf_scratch(ctx, 4, (size_t)pitch * h);
   if (!dimg) return PLF_ERR_CUDA;
-  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, w, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
-  plf_status st = plf_lsd_run(ctx, dimg, (size_t)w * h, w, h, 1);
+  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, pitch, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  plf_status st = plf_lsd_run(ctx, dimg, (size_t)pitch * h, pitch, w, h, 1);
   if (st) return st;
   LsdState* s = ctx->lsd;
   int n = 0;
@@ -1382,17 +1396,18 @@ extern "C" plf_status plf_detect_lines(plf_ctx* ctx, const uint8_t* img, int w, 
   if (!ctx || !img || !n_out || w < 3 || h < 3 || stride < w || cap < 0 || (cap > 0 && (!keylines || !desc)))
     return plf_fail(ctx, PLF_ERR_INVALID, "plf_detect_lines: bad arguments");
   PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-  const size_t A = ((size_t)w * h + 255) & ~size_t(255);
+  const int pitch = plf_pitch16(w);
+  const size_t A = ((size_t)pitch * h + 255) & ~size_t(255);
   uint8_t* base = (uint8_t*)plf_scratch(ctx, 4, A + A * 4 + (size_t)ctx->limits.max_lines * 32 + 256);
   if (!base) return PLF_ERR_CUDA;
   uint8_t* dimg = base;
   short2* dgrad = (short2*)(base + A);
   uint8_t* ddesc = base + A + A * 4;
-  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, w, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
-  plf_status st = plf_lsd_run(ctx, dimg, (size_t)w * h, w, h, 1);
+  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, pitch, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  plf_status st = plf_lsd_run(ctx, dimg, (size_t)pitch * h, pitch, w, h, 1);
   if (st) return st;
   LsdState* s = ctx->lsd;
-  st = plf_launch_blur5_sobel(ctx, dimg, w, 0, w, h, 1, dgrad, 0);
+  st = plf_launch_blur5_sobel(ctx, dimg, pitch, (size_t)pitch * h, w, h, 1, dgrad, 0);
   if (st) return st;
   st = plf_launch_lbd(ctx, dgrad, 0, w, h, 1, s->kls[0], s->nlines[0], s->max_lines, ddesc, nullptr);
   if (st) return st;

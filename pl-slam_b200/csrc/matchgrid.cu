@@ -22,7 +22,6 @@
 
 #define MG_NONE 0xFFFFu
 
-struct MgGrid { int cols, rows, w_lo, w_hi, h_lo, h_hi; };
 
 __device__ __forceinline__ int mg_hamming(const uint4* a, const uint4* b) {
   const uint4 a0 = a[0], a1 = a[1], b0 = b[0], b1 = b[1];
@@ -221,4 +220,163 @@ extern "C" plf_status plf_match_grid_lines(plf_ctx* ctx, const int* q_line, cons
                                            int best_lr, int32_t* matches_12, int* n_matches) {
   return mg_run(ctx, "plf_match_grid_lines", 1, q_line, d1, n1, cell_start, cell_items, t_dir, d2, n2, grid_cols, grid_rows, w,
                 nnr, line_sim_th, best_lr, matches_12, n_matches);
+}
+
+// =====================================================================================================================
+// Batched, device-resident form used by plf_batch_run when plf_params.matching_strategy != 0:
+// the same three passes over MANY problems at once (grid.y = problem), with the geometry produced on the device from
+// the frame's own feature arrays - no host hop.  A problem's arrays are addressed base + problem * stride.
+//   k_mgb_qmask   (lines) per query line: bit mask over the grid cells of "some cell of the query's Bresenham walk has
+//                 this cell inside its GridStructure::get window" (the window dilation of the walk)
+//   k_mgb_columns one thread per train feature: candidate test (points: its cell inside the query's window; lines: one of
+//                 its own Bresenham cells set in the query's mask, then the direction gate), Hamming distance, exclusive
+//                 prefix-minimum down the column (best_lr_matches), dense u16 row-major matrix D
+//   k_mgb_rows / k_mgb_mutual: as k_mg_rows / k_mg_mutual
+// D costs 2 * K * K bytes per problem, so the problems are processed in chunks that share one scratch buffer.
+#define MGB_MASK_WORDS 128   // >= cols * rows / 32 for the 64 x 48 grid (96 words)
+
+__global__ void __launch_bounds__(128) k_mgb_qmask(MgbArgs a, int p0) {
+  const int pl = blockIdx.y, p = p0 + pl;
+  const int i1 = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int n1 = min(a.n1[(size_t)p * a.n1_stride], a.K);
+  if (i1 >= n1) return;
+  uint32_t* m = a.qmask + ((size_t)pl * a.K + i1) * MGB_MASK_WORDS;
+  for (int k = lane; k < MGB_MASK_WORDS; k += 32) m[k] = 0u;
+  __syncwarp();
+  const int* q = a.q_geo + ((size_t)p * a.K + i1) * 4;
+  MgLine lq; lq.start(q[0], q[1], q[2], q[3]);
+  int cx, cy;
+  const MgGrid& g = a.g;
+  while (lq.next(&cx, &cy)) {   // warp-uniform walk; the window's cells are spread over the lanes
+    const int x0 = max(0, cx - g.w_lo), x1 = min(g.cols, cx + g.w_hi + 1), y0 = max(0, cy - g.h_lo), y1 = min(g.rows, cy + g.h_hi + 1);
+    const int nx = x1 - x0, ny = y1 - y0;
+    if (nx <= 0 || ny <= 0) continue;
+    for (int k = lane; k < nx * ny; k += 32) {
+      const int c = (x0 + k / ny) * g.rows + (y0 + k % ny);
+      atomicOr(&m[c >> 5], 1u << (c & 31));
+    }
+  }
+}
+
+template <int IS_LINES>
+__global__ void __launch_bounds__(128) k_mgb_columns(MgbArgs a, int p0) {
+  const int pl = blockIdx.y, p = p0 + pl;
+  const int i2 = blockIdx.x * 128 + threadIdx.x;
+  const int n1 = min(a.n1[(size_t)p * a.n1_stride], a.K), n2 = min(a.n2[(size_t)p * a.n2_stride], a.K);
+  if (i2 >= n2) return;
+  const MgGrid& g = a.g;
+  const uint4* b = reinterpret_cast<const uint4*>(a.d2 + (size_t)p * a.d2_stride) + 2 * (size_t)i2;
+  const uint4* q1 = reinterpret_cast<const uint4*>(a.d1 + (size_t)p * a.d1_stride);
+  const int* tg = a.t_geo + ((size_t)p * a.K + i2) * (IS_LINES ? 4 : 2);
+  const int* qg = a.q_geo + (size_t)p * a.K * (IS_LINES ? 4 : 2);
+  unsigned short* D = a.D + (size_t)pl * a.K * a.K;
+  int tx = 0, ty = 0, t4[4] = {0, 0, 0, 0};
+  double tdx = 0, tdy = 0;
+  bool t_in = false;
+  if (IS_LINES) {
+    t4[0] = tg[0]; t4[1] = tg[1]; t4[2] = tg[2]; t4[3] = tg[3];
+    tdx = a.t_dir[((size_t)p * a.K + i2) * 2]; tdy = a.t_dir[((size_t)p * a.K + i2) * 2 + 1];
+  } else {
+    tx = tg[0]; ty = tg[1];
+    t_in = tx >= 0 && tx < g.cols && ty >= 0 && ty < g.rows;   // pushed outside the grid: never returned
+  }
+  int run = 0x7FFFFFFF, who = -1;
+  for (int i1 = 0; i1 < n1; ++i1) {
+    bool cand = false;
+    if (IS_LINES) {
+      const uint32_t* m = a.qmask + ((size_t)pl * a.K + i1) * MGB_MASK_WORDS;
+      MgLine lt; lt.start(t4[0], t4[1], t4[2], t4[3]);
+      int cx, cy;
+      while (!cand && lt.next(&cx, &cy)) {
+        if (cx < 0 || cx >= g.cols || cy < 0 || cy >= g.rows) continue;   // a cell outside the grid is never returned
+        const int c = cx * g.rows + cy;
+        cand = (m[c >> 5] >> (c & 31)) & 1u;
+      }
+      if (cand) {
+        const int* q = qg + 4 * i1;
+        double vx = (double)(q[2] - q[0]), vy = (double)(q[3] - q[1]);
+        const double nrm = sqrt(vx * vx + vy * vy);
+        vx /= nrm; vy /= nrm;
+        if (fabs(vx * tdx + vy * tdy) < a.line_sim_th) cand = false;
+      }
+    } else if (t_in) {
+      const int qx = qg[2 * i1], qy = qg[2 * i1 + 1];
+      cand = tx >= qx - g.w_lo && tx <= qx + g.w_hi && ty >= qy - g.h_lo && ty <= qy + g.h_hi;
+    }
+    unsigned short out = MG_NONE;
+    if (cand) {
+      const int d = mg_hamming(q1 + 2 * (size_t)i1, b);
+      if (a.best_lr) {
+        if (d < run) { run = d; who = i1; out = (unsigned short)d; }
+      } else {
+        out = (unsigned short)d;
+      }
+    }
+    D[(size_t)i1 * a.K + i2] = out;
+  }
+  a.m21[(size_t)pl * a.K + i2] = who;
+}
+
+__global__ void __launch_bounds__(128) k_mgb_rows(MgbArgs a, int p0) {
+  const int pl = blockIdx.y, p = p0 + pl;
+  const int i1 = blockIdx.x * 128 + threadIdx.x;
+  const int n1 = min(a.n1[(size_t)p * a.n1_stride], a.K), n2 = min(a.n2[(size_t)p * a.n2_stride], a.K);
+  if (i1 >= n1) return;
+  int best_d = 0x7FFFFFFF, best_d2 = 0x7FFFFFFF, best_idx = -1;
+  const unsigned short* row = a.D + (size_t)pl * a.K * a.K + (size_t)i1 * a.K;
+  for (int i2 = 0; i2 < n2; ++i2) {
+    const int d = row[i2];
+    if (d == MG_NONE) continue;
+    if (d < best_d) { best_d2 = best_d; best_d = d; best_idx = i2; }
+    else if (d < best_d2) best_d2 = d;
+  }
+  a.m12[(size_t)p * a.m12_stride + i1] = ((float)best_d < __fmul_rn((float)best_d2, a.nnr)) ? best_idx : -1;
+}
+
+__global__ void __launch_bounds__(128) k_mgb_mutual(MgbArgs a, int p0) {
+  const int pl = blockIdx.y, p = p0 + pl;
+  const int i1 = blockIdx.x * 128 + threadIdx.x;
+  const int n1 = min(a.n1[(size_t)p * a.n1_stride], a.K);
+  bool ok = false;
+  if (i1 < n1) {
+    int32_t* m12 = a.m12 + (size_t)p * a.m12_stride;
+    const int i2 = m12[i1];
+    ok = i2 >= 0;
+    if (ok && a.best_lr && a.m21[(size_t)pl * a.K + i2] != i1) { m12[i1] = -1; ok = false; }
+  }
+  const unsigned bal = __ballot_sync(0xFFFFFFFFu, ok);
+  if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&a.count[(size_t)p * a.count_stride], __popc(bal));
+}
+
+// Runs nprob windowed matching problems.  scratch: MGB scratch of the context (slot 9), sized here.
+plf_status plf_launch_match_grid_batch(plf_ctx* ctx, MgbArgs a, int nprob, int max_n) {
+  if (nprob <= 0) return PLF_OK;
+  if (a.g.cols * a.g.rows > 32 * MGB_MASK_WORDS) return plf_fail(ctx, PLF_ERR_INVALID, "match grid: %dx%d cells exceed the mask", a.g.cols, a.g.rows);
+  const int K = a.K;
+  const size_t perD = (size_t)K * K * 2, perM = a.is_lines ? (size_t)K * MGB_MASK_WORDS * 4 : 0, per21 = (size_t)K * 4;
+  const size_t per = mg_align(perD) + mg_align(perM) + mg_align(per21);
+  int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)nprob, (size_t(1) << 31) / per));   // <= 2 GB of scratch
+  uint8_t* base = (uint8_t*)plf_scratch(ctx, 9, per * chunk);
+  if (!base) return PLF_ERR_CUDA;
+  a.D = (unsigned short*)base;
+  a.qmask = (uint32_t*)(base + mg_align(perD) * chunk);
+  a.m21 = (int*)(base + (mg_align(perD) + mg_align(perM)) * chunk);
+  cudaStream_t cs = ctx->cur;
+  const int gx = (max_n + 127) / 128;
+  for (int p0 = 0; p0 < nprob; p0 += chunk) {
+    const int np = std::min(chunk, nprob - p0);
+    if (a.is_lines) {
+      k_mgb_qmask<<<dim3((max_n + 3) / 4, np), 128, 0, cs>>>(a, p0);
+      PLF_LAUNCH_CHECK(ctx);
+      k_mgb_columns<1><<<dim3(gx, np), 128, 0, cs>>>(a, p0);
+    } else {
+      k_mgb_columns<0><<<dim3(gx, np), 128, 0, cs>>>(a, p0);
+    }
+    PLF_LAUNCH_CHECK(ctx);
+    k_mgb_rows<<<dim3(gx, np), 128, 0, cs>>>(a, p0);
+    PLF_LAUNCH_CHECK(ctx);
+    k_mgb_mutual<<<dim3(gx, np), 128, 0, cs>>>(a, p0);
+    PLF_LAUNCH_CHECK(ctx);
+  }
+  return PLF_OK;
 }

@@ -25,6 +25,7 @@
 // latency - none is HBM-bound) is measured in profiles/r01_ncu_full_final_summary.txt and tabulated in DESIGN.md §4.
 #include "orb_pattern.h"
 #include "plf_internal.h"
+#include "plf_tma.cuh"
 
 #define ORB_MAX_LEVELS 8
 #define ORB_TW 64
@@ -34,6 +35,8 @@
 struct OrbGeom {
   int nlevels;
   int w[ORB_MAX_LEVELS], h[ORB_MAX_LEVELS];
+  int pitch[ORB_MAX_LEVELS];        // row pitch (bytes, multiple of 16) of level l; level 0 = the caller's image pitch
+  int bpitch[ORB_MAX_LEVELS];       // row pitch of the blurred level l
   float scale[ORB_MAX_LEVELS];
   int nfeat[ORB_MAX_LEVELS];
   int umax[20];
@@ -69,6 +72,13 @@ struct OrbState {
   int* kp_count[2] = {nullptr, nullptr};      // [nimg]
   int* overflow = nullptr;      // [1]
   float blur_k[7];
+  // TMA descriptors (plf_tma.cuh): halo boxes of the FAST tile (80 x 38) and of the blur tile (80 x 38) per level; level 0
+  // is the caller's image buffer (re-encoded when its address changes - the pipeline alternates between two)
+  CUtensorMap tm_fast[ORB_MAX_LEVELS], tm_blur[ORB_MAX_LEVELS];
+  const void* tm_src0[2] = {nullptr, nullptr};   // image buffers the cached level-0 maps were encoded for
+  CUtensorMap tm_fast0[2], tm_blur0[2];
+  size_t tm_stride0 = 0; int tm_pitch0 = 0, tm_nimg0 = 0;
+  bool tma_ok = false;
 };
 
 __constant__ float c_blur7[7];
@@ -84,8 +94,8 @@ __device__ __forceinline__ int orb_reflect101(int i, int n) {
 
 // ---- pyramid ---------------------------------------------------------------------------------------
 // tab layout per level: [ox(dw) | cx(dw) | oy(dh) | cy(dh)]
-__global__ void __launch_bounds__(256) k_resize_exact(const uint8_t* __restrict__ src, size_t src_stride, int sw,
-                                                      int sh, uint8_t* __restrict__ dst, size_t dst_stride, int dw,
+__global__ void __launch_bounds__(256) k_resize_exact(const uint8_t* __restrict__ src, size_t src_stride, int sp, int sw,
+                                                      int sh, uint8_t* __restrict__ dst, size_t dst_stride, int dp, int dw,
                                                       int dh, const int* __restrict__ tabx,
                                                       const int* __restrict__ taby) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,19 +103,19 @@ __global__ void __launch_bounds__(256) k_resize_exact(const uint8_t* __restrict_
   if (x >= dw) return;
   const uint8_t* s = src + (size_t)blockIdx.z * src_stride;
   const int ox = tabx[x], cx = tabx[dw + x], oy = taby[y], cy = taby[dh + y];
-  const uint8_t* r0 = s + (size_t)oy * sw + ox;
-  const uint8_t* r1 = r0 + sw;
+  const uint8_t* r0 = s + (size_t)oy * sp + ox;
+  const uint8_t* r1 = r0 + sp;
   const uint32_t h0 = r0[0] * (256 - cx) + r0[1] * cx;
   const uint32_t h1 = r1[0] * (256 - cx) + r1[1] * cx;
   const uint32_t v = (h0 * (256 - cy) + h1 * cy + 32768u) >> 16;
-  dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dw + x] = (uint8_t)(v > 255 ? 255 : v);
+  dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dp + x] = (uint8_t)(v > 255 ? 255 : v);
 }
 
 // Four adjacent outputs per thread.  For scale factors up to 2 the four outputs read source columns ox0 .. ox0+7 at
 // most, i.e. two 32-bit words per source row (plf_load4), from which each output takes its byte pair with a shift.
 // Same integer arithmetic as k_resize_exact (bit-identical), about half the instructions per pixel.
-__global__ void __launch_bounds__(256) k_resize_exact4(const uint8_t* __restrict__ src, size_t src_stride, int sw,
-                                                       int sh, uint8_t* __restrict__ dst, size_t dst_stride, int dw,
+__global__ void __launch_bounds__(256) k_resize_exact4(const uint8_t* __restrict__ src, size_t src_stride, int sp, int sw,
+                                                       int sh, uint8_t* __restrict__ dst, size_t dst_stride, int dp, int dw,
                                                        int dh, const int* __restrict__ tabx,
                                                        const int* __restrict__ taby) {
   const int x = (blockIdx.x * 64 + threadIdx.x) * 4;  // block = 64 x 4 threads = 256 x 4 outputs
@@ -122,11 +132,12 @@ __global__ void __launch_bounds__(256) k_resize_exact4(const uint8_t* __restrict
   }
   // source bytes ox[0] .. ox[0]+7 of rows oy and oy+1.  The second row is clamped to the image (its weight cy is 0
   // there), so every byte wanted lies inside the image or within 7 bytes of its end: unclamped loads (allocation slack).
-  const uint8_t* r0 = s + (size_t)oy * sw + ox[0];
-  const uint8_t* r1 = oy + 1 < sh ? r0 + sw : r0;
+  const uint8_t* r0 = s + (size_t)oy * sp + ox[0];
+  const uint8_t* r1 = oy + 1 < sh ? r0 + sp : r0;
   const unsigned long long a = (unsigned long long)plf_load4_fast(r0) | ((unsigned long long)plf_load4_fast(r0 + 4) << 32);
   const unsigned long long b = (unsigned long long)plf_load4_fast(r1) | ((unsigned long long)plf_load4_fast(r1 + 4) << 32);
-  uint8_t* d = dst + (size_t)blockIdx.z * dst_stride + (size_t)y * dw + x;
+  uint8_t* d = dst + (size_t)blockIdx.z * dst_stride + (size_t)y * dp + x;
+  uint32_t pk = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     const int sft = 8 * (ox[i] - ox[0]);
@@ -134,18 +145,20 @@ __global__ void __launch_bounds__(256) k_resize_exact4(const uint8_t* __restrict
     const uint32_t h0 = (pa & 0xFFu) * (256 - cx[i]) + ((pa >> 8) & 0xFFu) * cx[i];
     const uint32_t h1 = (pb & 0xFFu) * (256 - cx[i]) + ((pb >> 8) & 0xFFu) * cx[i];
     const uint32_t v = (h0 * (256 - cy) + h1 * cy + 32768u) >> 16;
-    if (x + i < dw) d[i] = (uint8_t)(v > 255 ? 255 : v);
+    pk |= (v > 255 ? 255u : v) << (8 * i);
   }
+  // rows are 16-byte aligned (pitch) and x is a multiple of 4: one 32-bit store (bytes past dw land in the row's padding)
+  *reinterpret_cast<uint32_t*>(d) = pk;
 }
 
-plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_stride, int sw, int sh, uint8_t* dst,
-                                   size_t dst_stride, int dw, int dh, const int* tabx, const int* taby, int nimg) {
+plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_stride, int sp, int sw, int sh, uint8_t* dst,
+                                   size_t dst_stride, int dp, int dw, int dh, const int* tabx, const int* taby, int nimg) {
   if ((double)sw <= 1.9 * (double)dw) {  // four outputs span at most 3 * 1.9 + 2 < 8 source columns
     dim3 grid((dw + 255) / 256, (dh + 3) / 4, nimg);
-    k_resize_exact4<<<grid, dim3(64, 4), 0, ctx->cur>>>(src, src_stride, sw, sh, dst, dst_stride, dw, dh, tabx, taby);
+    k_resize_exact4<<<grid, dim3(64, 4), 0, ctx->cur>>>(src, src_stride, sp, sw, sh, dst, dst_stride, dp, dw, dh, tabx, taby);
   } else {
     dim3 grid((dw + 255) / 256, dh, nimg);
-    k_resize_exact<<<grid, 256, 0, ctx->cur>>>(src, src_stride, sw, sh, dst, dst_stride, dw, dh, tabx, taby);
+    k_resize_exact<<<grid, 256, 0, ctx->cur>>>(src, src_stride, sp, sw, sh, dst, dst_stride, dp, dw, dh, tabx, taby);
   }
   PLF_LAUNCH_CHECK(ctx);
   return PLF_OK;
@@ -189,37 +202,27 @@ __device__ int fast_corner_score(const int* d /*16*/) {
 // region (3-px ring).  All index arithmetic is lane + 32*k / warp + 8*k (no div/mod), every lane is active in every pass.
 #define FN_OW 62
 #define FN_OH 30
-__global__ void __launch_bounds__(256, 5) k_fast_nms(const uint8_t* __restrict__ img0, size_t img0_stride,
-                                                     const uint8_t* __restrict__ pyr, OrbGeom g, int l, int tiles_x,
+__global__ void __launch_bounds__(256, 5) k_fast_nms(const __grid_constant__ CUtensorMap tmap, OrbGeom g, int l, int tiles_x,
                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_count,
                                                   int* __restrict__ hist, int* __restrict__ overflow) {
   const int W = g.w[l], H = g.h[l];
   const int x0 = (blockIdx.x % tiles_x) * FN_OW, y0 = (blockIdx.x / tiles_x) * FN_OH;
   const int img = blockIdx.y;
-  const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride
-                                : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
-  __shared__ __align__(16) uint8_t px[38][72];   // pixel (x0 - 4 + rx, y0 - 4 + ry)
+  __shared__ __align__(128) uint8_t px[38][80];   // pixel (x0 - 4 + rx, y0 - 4 + ry): the TMA box (80 x 38 bytes)
   __shared__ uint8_t sc[32][64];   // score of pixel (x0 - 1 + sx, y0 - 1 + sy)
   __shared__ unsigned short clist[32 * 64];
   __shared__ int ccount;
+  __shared__ __align__(8) uint64_t bar;
   const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  if (tid == 0) ccount = 0;
-  // Stage the tile four pixels at a time (plf_load4).  Rows are clamped to the image; positions outside the image hold
-  // arbitrary in-bounds data - they are never used by a valid score (gx in [3, W-3)).
-  if (x0 >= 4 && x0 + 68 <= W && y0 >= 4 && y0 + 34 <= H) {  // tile + halo inside the image: no clamps
-    for (int i = tid; i < 38 * 18; i += 256) {
-      const int ry = i / 18, j = i - ry * 18;
-      reinterpret_cast<uint32_t*>(&px[ry][0])[j] = plf_load4_fast(src + (size_t)(y0 - 4 + ry) * W + (x0 - 4 + 4 * j));
-    }
-  } else {
-    const plf_span sp = plf_image_span(src, (size_t)W * H);
-    for (int i = tid; i < 38 * 18; i += 256) {
-      const int ry = i / 18, j = i - ry * 18;
-      const uint8_t* p = src + (size_t)min(max(y0 - 4 + ry, 0), H - 1) * W + (x0 - 4 + 4 * j);
-      reinterpret_cast<uint32_t*>(&px[ry][0])[j] = plf_load4(p, sp);
-    }
+  if (tid == 0) {
+    ccount = 0;
+    plf_mbar_init(&bar);
   }
   __syncthreads();
+  // The tile + halo arrives as ONE bulk-tensor copy (TMA).  Positions outside the image come back as zeros - they are
+  // never used by a valid score (gx in [3, W-3), gy in [3, H-3)).
+  if (tid == 0) plf_tma_load_3d(&px[0][0], &tmap, x0 - 4, y0 - 4, img, &bar, 38 * 80);
+  plf_mbar_wait(&bar, 0);
   const int th = g.fast_th;
   // Pass A: cheap rejection.  A 9-arc of the 16-ring always contains one pixel of every opposite pair (k, k+8)
   // (OpenCV's FAST_t uses the same test): a pair with both members inside the threshold band rules the pixel out.
@@ -436,7 +439,7 @@ __global__ void __launch_bounds__(256) k_ic_angle(const uint8_t* __restrict__ im
   plf_keypoint* kp = &kps[(size_t)img * g.max_kp + ki];
   const int l = kp->octave;
   const short2 p = kp_lxy[(size_t)img * g.max_kp + ki];
-  const int W = g.w[l];
+  const int W = g.pitch[l];   // row pitch
   const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride
                                 : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
   const uint8_t* center = src + (size_t)p.y * W + p.x;
@@ -465,83 +468,28 @@ __global__ void __launch_bounds__(256) k_ic_angle(const uint8_t* __restrict__ im
 // ---- descriptor-stage blur -----------------------------------------------------------------------------
 // float row pass (sequential, FMA), symmetric float column pass (FMA), round-half-even saturate: OpenCV's sepFilter2D
 // path for the pyramid ROI on FMA-capable hosts (see oracle/orb.c orc_orb_blur7).
-__global__ void __launch_bounds__(256) k_orb_blur7(const uint8_t* __restrict__ img0, size_t img0_stride,
-                                                   const uint8_t* __restrict__ pyr, OrbGeom g,
-                                                   uint8_t* __restrict__ blur) {
-  int l = 0;
-  while (l + 1 < g.nlevels && (int)blockIdx.x >= g.tile_start[l + 1]) ++l;
-  const int t = blockIdx.x - g.tile_start[l];
-  const int W = g.w[l], H = g.h[l];
-  const int x0 = (t % g.tiles_x[l]) * ORB_TW, y0 = (t / g.tiles_x[l]) * ORB_TH;
-  const int img = blockIdx.y;
-  const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride
-                                : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
-  uint8_t* dst = blur + (size_t)img * g.blur_stride + g.blur_off[l];
-  __shared__ uint8_t raw[ORB_TH + 6][ORB_TW + 8];
-  __shared__ float hrow[ORB_TH + 6][ORB_TW];
-  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const bool interior = x0 >= 3 && x0 + ORB_TW + 3 <= W && y0 >= 3 && y0 + ORB_TH + 3 <= H;
-  for (int ry = wrp; ry < ORB_TH + 6; ry += 8) {  // one warp per row, lanes along x
-    const int gy = interior ? y0 - 3 + ry : orb_reflect101(y0 - 3 + ry, H);
-    const uint8_t* row = src + (size_t)gy * W;
-    for (int rx = lane; rx < ORB_TW + 6; rx += 32) raw[ry][rx] = row[interior ? x0 - 3 + rx : orb_reflect101(x0 - 3 + rx, W)];
-  }
-  __syncthreads();
-  const int tx = tid & (ORB_TW - 1), rg = tid >> 6;  // ORB_TW == 64: column = low 6 bits, 4 row groups
-  const float k0 = c_blur7[0], k1 = c_blur7[1], k2 = c_blur7[2], k3 = c_blur7[3], k4 = c_blur7[4], k5 = c_blur7[5], k6 = c_blur7[6];
-  for (int ry = rg; ry < ORB_TH + 6; ry += 4) {
-    const uint8_t* p = &raw[ry][tx];
-    float a = __fmul_rn(k0, (float)p[0]);
-    a = __fmaf_rn(k1, (float)p[1], a); a = __fmaf_rn(k2, (float)p[2], a); a = __fmaf_rn(k3, (float)p[3], a);
-    a = __fmaf_rn(k4, (float)p[4], a); a = __fmaf_rn(k5, (float)p[5], a); a = __fmaf_rn(k6, (float)p[6], a);
-    hrow[ry][tx] = a;
-  }
-  __syncthreads();
-  const int gx = x0 + tx;
-  if (gx < W) {
-    for (int ty = rg; ty < ORB_TH; ty += 4) {
-      const int gy = y0 + ty;
-      if (gy >= H) break;
-      float a = __fmul_rn(k3, hrow[ty + 3][tx]);
-      a = __fmaf_rn(k4, __fadd_rn(hrow[ty + 4][tx], hrow[ty + 2][tx]), a);
-      a = __fmaf_rn(k5, __fadd_rn(hrow[ty + 5][tx], hrow[ty + 1][tx]), a);
-      a = __fmaf_rn(k6, __fadd_rn(hrow[ty + 6][tx], hrow[ty][tx]), a);
-      int v = __float2int_rn(a);
-      v = v < 0 ? 0 : (v > 255 ? 255 : v);
-      dst[(size_t)gy * W + gx] = (uint8_t)v;
-    }
-  }
-}
-
-// Fast variant of k_orb_blur7: 64x32 outputs per CTA; the tile is staged as bytes (12 KB of shared memory per CTA in all, so 8 CTAs
-// fit beside co-resident kernels), the row pass produces 4 adjacent outputs per thread from 10 pixels (same k0*p0, fma(k1,p1,.) ...
-// order), the column pass slides down 8 rows.  Bit-identical to k_orb_blur7.
+// 64x32 outputs per CTA; the (tile + halo) box is staged by ONE TMA bulk-tensor copy (13 KB of shared memory per CTA in all, so
+// 8 CTAs fit beside co-resident kernels; border CTAs rebuild BORDER_REFLECT_101 inside shared memory), the row pass produces 4
+// adjacent outputs per thread from 10 pixels (k0*p0, fma(k1,p1,.) ... order), the column pass slides down 8 rows.
 #define OBF_TW 64
 #define OBF_TH 32
-__global__ void __launch_bounds__(256) k_orb_blur7_fast(const uint8_t* __restrict__ img0, size_t img0_stride,
-                                                        const uint8_t* __restrict__ pyr, OrbGeom g,
+__global__ void __launch_bounds__(256) k_orb_blur7_fast(const __grid_constant__ CUtensorMap tmap, OrbGeom g,
                                                         uint8_t* __restrict__ blur, int l, int tiles_x) {
-  constexpr int RH = OBF_TH + 6, RP = 72;  // 70 pixels needed per row, pitch 72 (whole 32-bit words)
-  __shared__ __align__(16) uint8_t raw[RH][RP];
+  constexpr int RH = OBF_TH + 6, RP = 80, NEED = 72;  // 70 pixels needed per row (72: whole words); box pitch 80
+  __shared__ __align__(128) uint8_t raw[RH][RP];
   __shared__ __align__(16) float hrow[RH][OBF_TW];
-  const int W = g.w[l], H = g.h[l];
+  __shared__ __align__(8) uint64_t bar;
+  const int W = g.w[l], H = g.h[l], BP = g.bpitch[l];
   const int x0 = (blockIdx.x % tiles_x) * OBF_TW, y0 = (blockIdx.x / tiles_x) * OBF_TH;
   const int img = blockIdx.y;
-  const uint8_t* src = (l == 0) ? img0 + (size_t)img * img0_stride : pyr + (size_t)img * g.pyr_stride + g.pyr_off[l];
   uint8_t* dst = blur + (size_t)img * g.blur_stride + g.blur_off[l];
-  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-  const bool interior = x0 >= 3 && x0 - 3 + RP <= W && y0 >= 3 && y0 + OBF_TH + 3 <= H;
-  if (interior) {  // four pixels per step (plf_load4)
-    for (int i = tid; i < RH * (RP / 4); i += 256) {
-      const int ry = i / (RP / 4), j = i - ry * (RP / 4);
-      reinterpret_cast<uint32_t*>(&raw[ry][0])[j] = plf_load4_fast(src + (size_t)(y0 - 3 + ry) * W + (x0 - 3 + 4 * j));
-    }
-  } else {
-    for (int ry = wrp; ry < RH; ry += 8) {
-      const uint8_t* row = src + (size_t)orb_reflect101(y0 - 3 + ry, H) * W;
-      for (int rx = lane; rx < RP; rx += 32) raw[ry][rx] = row[orb_reflect101(x0 - 3 + rx, W)];
-    }
-  }
+  const int tid = threadIdx.x;
+  if (tid == 0) plf_mbar_init(&bar);
+  __syncthreads();
+  if (tid == 0) plf_tma_load_3d(&raw[0][0], &tmap, x0 - 3, y0 - 3, img, &bar, RH * RP);
+  plf_mbar_wait(&bar, 0);
+  if (!(x0 >= 3 && x0 - 3 + NEED <= W && y0 >= 3 && y0 + OBF_TH + 3 <= H))   // border tile: BORDER_REFLECT_101 in place
+    plf_tma_reflect_fix<RH, RP>(raw, x0 - 3, y0 - 3, W, H, NEED);
   __syncthreads();
   const float k0 = c_blur7[0], k1 = c_blur7[1], k2 = c_blur7[2], k3 = c_blur7[3], k4 = c_blur7[4], k5 = c_blur7[5], k6 = c_blur7[6];
   for (int it = tid; it < RH * (OBF_TW / 4); it += 256) {
@@ -578,7 +526,7 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const uint8_t* __restric
         a = __fmaf_rn(k6, __fadd_rn(v[r + 6], v[r]), a);
         int o = __float2int_rn(a);
         o = o < 0 ? 0 : (o > 255 ? 255 : o);
-        dst[(size_t)gy * W + gx] = (uint8_t)o;
+        dst[(size_t)gy * BP + gx] = (uint8_t)o;
       }
     }
   }
@@ -604,7 +552,7 @@ __global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur
   const int ki = blockIdx.x * 8 + wrp;
   if (ki >= kp_count[img]) return;
   const plf_keypoint kp = kps[(size_t)img * g.max_kp + ki];
-  const int l = kp.octave, W = g.w[l];
+  const int l = kp.octave, W = g.bpitch[l];   // row pitch of the blurred level
   const float scale = __fdiv_rn(1.f, g.scale[l]);
   const float angle = __fmul_rn(kp.angle, (float)(3.14159265358979323846 / 180.f));
   const float a = (float)cos((double)angle), b = (float)sin((double)angle);
@@ -727,7 +675,8 @@ plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
     if (g.w[l] < 2 * g.edge + 8 || g.h[l] < 2 * g.edge + 8)
       return plf_fail(ctx, PLF_ERR_INVALID, "ORB: level %d (%dx%d) too small for edge threshold %d", l, g.w[l],
                       g.h[l], g.edge);
-    const size_t a = ((size_t)g.w[l] * g.h[l] + 255) & ~size_t(255);
+    g.pitch[l] = g.bpitch[l] = plf_pitch16(g.w[l]);   // level 0's source pitch is the caller's (set per run)
+    const size_t a = ((size_t)g.pitch[l] * g.h[l] + 255) & ~size_t(255);
     if (l >= 1) { g.pyr_off[l] = pyr; pyr += a; }
     g.blur_off[l] = blur; blur += a;
     g.cand_cap[l] = (int)std::min<size_t>((size_t)g.w[l] * g.h[l] / 9 + 64, 32768);
@@ -807,31 +756,53 @@ plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
     g_dev_pattern_device = ctx->device;
   }
   PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  // tensor maps of the pyramid levels (fixed addresses); level 0 = the caller's image buffer, encoded per run
+  s->tm_src0[0] = s->tm_src0[1] = nullptr;
+  for (int l = 1; l < g.nlevels; ++l) {
+    if (!plf_tma_encode_u8(&s->tm_fast[l], s->pyr + g.pyr_off[l], g.w[l], g.h[l], nimg, g.pitch[l], g.pyr_stride, 80, 38) ||
+        !plf_tma_encode_u8(&s->tm_blur[l], s->pyr + g.pyr_off[l], g.w[l], g.h[l], nimg, g.pitch[l], g.pyr_stride, 80, OBF_TH + 6))
+      return plf_fail(ctx, PLF_ERR_CUDA, "ORB: cuTensorMapEncodeTiled failed for pyramid level %d", l);
+  }
   return PLF_OK;
 }
 
-// Runs ORB on nimg images resident at d_imgs ([nimg][h][w], stride img_stride bytes). Results stay on the device.
-plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg, int par) {
+// Runs ORB on nimg images resident at d_imgs ([nimg][h][pitch], pitch a multiple of 16, stride img_stride bytes).
+// Results stay on the device.
+plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int pitch, int w, int h, int nimg, int par) {
   plf_status st = plf_orb_prepare(ctx, w, h, nimg, par != 0);
   if (st) return st;
   OrbState* s = ctx->orb;
-  const OrbGeom& g = s->g;
+  OrbGeom g = s->g;
+  g.pitch[0] = pitch;
   cudaStream_t cs = ctx->cur;
+  // level-0 tensor maps: two cached slots (the pipeline alternates between its two upload buffers)
+  int slot = -1;
+  if (s->tm_stride0 != img_stride || s->tm_pitch0 != pitch || s->tm_nimg0 < nimg) {
+    s->tm_src0[0] = s->tm_src0[1] = nullptr;
+    s->tm_stride0 = img_stride; s->tm_pitch0 = pitch; s->tm_nimg0 = nimg;
+  }
+  for (int k = 0; k < 2; ++k) if (s->tm_src0[k] == d_imgs) slot = k;
+  if (slot < 0) {
+    slot = s->tm_src0[0] ? (s->tm_src0[1] ? 0 : 1) : 0;
+    if (!plf_tma_encode_u8(&s->tm_fast0[slot], d_imgs, w, h, s->tm_nimg0, pitch, img_stride, 80, 38) ||
+        !plf_tma_encode_u8(&s->tm_blur0[slot], d_imgs, w, h, s->tm_nimg0, pitch, img_stride, 80, OBF_TH + 6))
+      return plf_fail(ctx, PLF_ERR_CUDA, "ORB: cuTensorMapEncodeTiled failed for the source images (pitch %d, stride %zu)", pitch, img_stride);
+    s->tm_src0[slot] = d_imgs;
+  }
   PLF_CUDA(ctx, cudaMemsetAsync(s->cand_count, 0, (size_t)nimg * ORB_MAX_LEVELS * sizeof(int), cs));
   PLF_CUDA(ctx, cudaMemsetAsync(s->hist, 0, (size_t)nimg * ORB_MAX_LEVELS * 256 * sizeof(int), cs));
   for (int l = 1; l < g.nlevels; ++l) {
     const uint8_t* src = (l == 1) ? d_imgs : s->pyr + g.pyr_off[l - 1];
     const size_t sstride = (l == 1) ? img_stride : g.pyr_stride;
-    st = plf_launch_resize_exact(ctx, src, sstride, g.w[l - 1], g.h[l - 1], s->pyr + g.pyr_off[l], g.pyr_stride, g.w[l],
-                                 g.h[l], s->rs_tab + s->rs_x_off[l], s->rs_tab + s->rs_y_off[l], nimg);
+    st = plf_launch_resize_exact(ctx, src, sstride, g.pitch[l - 1], g.w[l - 1], g.h[l - 1], s->pyr + g.pyr_off[l], g.pyr_stride,
+                                 g.pitch[l], g.w[l], g.h[l], s->rs_tab + s->rs_x_off[l], s->rs_tab + s->rs_y_off[l], nimg);
     if (st) return st;
   }
   plf_mark(ctx, "orb.k_resize_exact");
-  const int tiles = g.tile_start[g.nlevels];
   for (int l = 0; l < g.nlevels; ++l) {
     const int tx_ = (g.w[l] + FN_OW - 1) / FN_OW, ty_ = (g.h[l] + FN_OH - 1) / FN_OH;
-    k_fast_nms<<<dim3(tx_ * ty_, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, l, tx_, s->cand, s->cand_count, s->hist,
-                                                      s->overflow);
+    k_fast_nms<<<dim3(tx_ * ty_, nimg), 256, 0, cs>>>(l == 0 ? s->tm_fast0[slot] : s->tm_fast[l], g, l, tx_, s->cand, s->cand_count,
+                                                      s->hist, s->overflow);
     PLF_LAUNCH_CHECK(ctx);
   }
   plf_mark(ctx, "orb.k_fast_nms");
@@ -843,7 +814,7 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
   plf_mark(ctx, "orb.k_ic_angle");
   for (int l = 0; l < g.nlevels; ++l) {
     const int tx_ = (g.w[l] + OBF_TW - 1) / OBF_TW, ty_ = (g.h[l] + OBF_TH - 1) / OBF_TH;
-    k_orb_blur7_fast<<<dim3(tx_ * ty_, nimg), 256, 0, cs>>>(d_imgs, img_stride, s->pyr, g, s->blur, l, tx_);
+    k_orb_blur7_fast<<<dim3(tx_ * ty_, nimg), 256, 0, cs>>>(l == 0 ? s->tm_blur0[slot] : s->tm_blur[l], g, s->blur, l, tx_);
     PLF_LAUNCH_CHECK(ctx);
   }
   plf_mark(ctx, "orb.k_orb_blur7");
@@ -866,10 +837,11 @@ extern "C" plf_status plf_orb(plf_ctx* ctx, const uint8_t* img, int w, int h, in
   if (!ctx || !img || !n_out || w < 8 || h < 8 || stride < w || cap < 0 || (cap > 0 && (!kps || !desc)))
     return plf_fail(ctx, PLF_ERR_INVALID, "plf_orb: bad arguments");
   PLF_CUDA(ctx, cudaSetDevice(ctx->device));
-  uint8_t* dimg = (uint8_t*)plf_scratch(ctx, 3, (size_t)w * h);
+  const int pitch = plf_pitch16(w);
+  uint8_t* dimg = (uint8_t*)plf_scratch(ctx, 3, (size_t)pitch * h);
   if (!dimg) return PLF_ERR_CUDA;
-  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, w, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
-  plf_status st = plf_orb_run(ctx, dimg, (size_t)w * h, w, h, 1, 0);
+  PLF_CUDA(ctx, cudaMemcpy2DAsync(dimg, pitch, img, stride, w, h, cudaMemcpyHostToDevice, ctx->stream));
+  plf_status st = plf_orb_run(ctx, dimg, (size_t)pitch * h, pitch, w, h, 1, 0);
   if (st) return st;
   OrbState* s = ctx->orb;
   int n = 0, ovf = 0;

@@ -13,6 +13,7 @@
 // images [2B][H][W] (2k = left, 2k+1 = right) -> ORB / LSD / LBD over 2B images -> per-pair kernels.  The last
 // frame's stereo features are carried to the next call (slot 0).
 #include "plf_internal.h"
+#include "plf_tma.cuh"
 
 struct FrameSlots {  // stereo-valid features per frame slot: [slots][cap]
   double2* pt_pl; double* pt_disp; double* pt_P; int* pt_octave; uint8_t* pdesc; int* pt_count;
@@ -22,9 +23,10 @@ struct FrameSlots {  // stereo-valid features per frame slot: [slots][cap]
 
 struct PipeState {
   int w = 0, h = 0, B = 0, max_kp = 0, max_ln = 0;
+  int pitch = 0;               // row pitch of the device images: plf_pitch16(w) (16-byte rows: every halo tile is a legal TMA box)
   bool has_prev = false;
   uint8_t* imgs = nullptr;     // images of the batch being run: = imgs2[run_slot]
-  uint8_t* imgs2[2] = {nullptr, nullptr};  // double-buffered [2B][h][w]: upload of batch i+1 overlaps the run of batch i
+  uint8_t* imgs2[2] = {nullptr, nullptr};  // double-buffered [2B][h][pitch]: upload of batch i+1 overlaps the run of batch i
   int up_slot = 0;             // slot written by the last plf_batch_upload
   cudaStream_t copy = nullptr; // H2D stream
   cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_free2[2] = {nullptr, nullptr};
@@ -53,6 +55,13 @@ struct PipeState {
   plf_frame_result* h_results[3] = {nullptr, nullptr, nullptr};  // pinned host mirrors, ring of PIPE_DEPTH (filled at the end of M)
   int* h_ovf[3] = {nullptr, nullptr, nullptr};                   // pinned overflow flags {orb, lsd}
   int* d_ovf = nullptr;         // [3][2] per-batch snapshots of the two global overflow flags (taken at the end of E and G)
+  // windowed matching (plf_params.matching_strategy != 0): grid geometry of the four problem kinds per pair
+  // (0 stereo points, 1 stereo lines, 2 f2f points, 3 f2f lines), train-line directions, f2f grid results and counts
+  int* mg_q[4] = {nullptr, nullptr, nullptr, nullptr};
+  int* mg_t[4] = {nullptr, nullptr, nullptr, nullptr};
+  double* mg_dir[2] = {nullptr, nullptr};   // [B][Ln][2]: stereo lines, f2f lines
+  int32_t* m12g = nullptr;                  // [B][2][K]  f2f matchGrid results (points, lines)
+  int* mgcount = nullptr;                   // [B][2]
   // Batches are software-pipelined over three streams: E (extract: ORB, LSD pre-grow, LBD prelude) -> G (LSD region
   // growing, latency-bound) -> M (LBD, stereo, tracking, pose).  Buffers that cross E -> G -> M exist per batch parity.
   // M starts with the LBD kernel and a device copy of the (small) extraction outputs it still needs, then records evX:
@@ -360,6 +369,83 @@ __global__ void k_finalize(const plf_pose_result* __restrict__ gn, const int* __
   out[k] = r;
 }
 
+// ---- windowed matching: grid geometry on the device (oracle/frontend.py grid_match_points / grid_match_lines) ----
+#define PLF_GRID_ROWS 48   // stvo-pl gridStructure.h
+#define PLF_GRID_COLS 64
+__device__ __forceinline__ int mg_cell(double v) { return (int)v; }   // double -> int as in C++ (truncation)
+
+// stereo: queries = left key points / KeyLines of pair k (image 2k), train = the right ones (image 2k+1)
+__global__ void __launch_bounds__(256) k_mg_geom_stereo(const plf_keypoint* __restrict__ kps, const int* __restrict__ kcnt, int K,
+                                                        const plf_keyline* __restrict__ kls, const int* __restrict__ lcnt, int Ln,
+                                                        double iw, double ih, int* __restrict__ qp, int* __restrict__ tp,
+                                                        int* __restrict__ ql, int* __restrict__ tl, double* __restrict__ tdir) {
+  const int img = blockIdx.y, k = img >> 1, right = img & 1, i = blockIdx.x * 256 + threadIdx.x;
+  if (i < min(kcnt[img], K)) {
+    const plf_keypoint kp = kps[(size_t)img * K + i];
+    int* d = (right ? tp : qp) + ((size_t)k * K + i) * 2;
+    d[0] = mg_cell((double)kp.x * iw);
+    d[1] = mg_cell((double)kp.y * ih);
+  }
+  if (i < min(lcnt[img], Ln)) {
+    const plf_keyline kl = kls[(size_t)img * Ln + i];
+    const double sx = kl.startPointX, sy = kl.startPointY, ex = kl.endPointX, ey = kl.endPointY;
+    int* d = (right ? tl : ql) + ((size_t)k * Ln + i) * 4;
+    d[0] = mg_cell(sx * iw); d[1] = mg_cell(sy * ih); d[2] = mg_cell(ex * iw); d[3] = mg_cell(ey * ih);
+    if (right) {
+      const double vx = (ex - sx) * iw, vy = (ey - sy) * ih, nrm = sqrt(vx * vx + vy * vy);
+      tdir[((size_t)k * Ln + i) * 2] = vx / nrm;        // unguarded like the reference's normalize()
+      tdir[((size_t)k * Ln + i) * 2 + 1] = vy / nrm;
+    }
+  }
+}
+
+// frame-to-frame: queries = the previous frame's 3-D features projected with DT = identity (slot k), train = the
+// current frame's image features (slot k+1)
+__global__ void __launch_bounds__(256) k_mg_geom_f2f(FrameSlots fs, int K, int Ln, StereoPrm c, double iw, double ih,
+                                                     int* __restrict__ qp, int* __restrict__ tp, int* __restrict__ ql,
+                                                     int* __restrict__ tl, double* __restrict__ tdir) {
+  const int k = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  const int ps = k, cs = k + 1;
+  if (i < min(fs.pt_count[ps], K)) {
+    const double* P = fs.pt_P + 3 * ((size_t)ps * K + i);
+    const double u = c.cx + c.fx * P[0] / P[2], v = c.cy + c.fy * P[1] / P[2];   // PinholeStereoCamera::projection
+    qp[((size_t)k * K + i) * 2] = mg_cell(u * iw);
+    qp[((size_t)k * K + i) * 2 + 1] = mg_cell(v * ih);
+  }
+  if (i < min(fs.pt_count[cs], K)) {
+    const double2 p = fs.pt_pl[(size_t)cs * K + i];
+    tp[((size_t)k * K + i) * 2] = mg_cell(p.x * iw);
+    tp[((size_t)k * K + i) * 2 + 1] = mg_cell(p.y * ih);
+  }
+  if (i < min(fs.ls_count[ps], Ln)) {
+    const double* S = fs.ls_sP + 3 * ((size_t)ps * Ln + i);
+    const double* E = fs.ls_eP + 3 * ((size_t)ps * Ln + i);
+    int* d = ql + ((size_t)k * Ln + i) * 4;
+    d[0] = mg_cell((c.cx + c.fx * S[0] / S[2]) * iw); d[1] = mg_cell((c.cy + c.fy * S[1] / S[2]) * ih);
+    d[2] = mg_cell((c.cx + c.fx * E[0] / E[2]) * iw); d[3] = mg_cell((c.cy + c.fy * E[1] / E[2]) * ih);
+  }
+  if (i < min(fs.ls_count[cs], Ln)) {
+    const double2 sp = fs.ls_spl[(size_t)cs * Ln + i], ep = fs.ls_epl[(size_t)cs * Ln + i];
+    int* d = tl + ((size_t)k * Ln + i) * 4;
+    d[0] = mg_cell(sp.x * iw); d[1] = mg_cell(sp.y * ih); d[2] = mg_cell(ep.x * iw); d[3] = mg_cell(ep.y * ih);
+    const double vx = (ep.x - sp.x) * iw, vy = (ep.y - sp.y) * ih, nrm = sqrt(vx * vx + vy * vy);
+    tdir[((size_t)k * Ln + i) * 2] = vx / nrm;
+    tdir[((size_t)k * Ln + i) * 2 + 1] = vy / nrm;
+  }
+}
+
+// src/mapHandler.cpp:274-278 / :421-425: keep the windowed result unless both frames hold more than `kmin` features and
+// fewer than `kmin` matches survived - then the brute-force match() result (already in m12) stands.
+__global__ void __launch_bounds__(256) k_mg_select(const int32_t* __restrict__ m12g, const int* __restrict__ mgcount,
+                                                   const int* __restrict__ cnt, int cap, int K, int which, int kmin,
+                                                   int32_t* __restrict__ m12) {
+  const int k = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  const int n1 = min(cnt[k], cap), n2 = min(cnt[k + 1], cap);
+  if (i >= n1) return;
+  const bool fall_back = n2 > kmin && n1 > kmin && mgcount[2 * k + which] < kmin;
+  if (!fall_back) m12[((size_t)k * 4 + 2 + which) * K + i] = m12g[((size_t)k * 2 + which) * K + i];
+}
+
 static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PipeState* s = ctx->pipe;
   if (s && s->w == w && s->h == h) {
@@ -379,11 +465,12 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   if (Ln > K || K > 65535)
     return plf_fail(ctx, PLF_ERR_INVALID, "limits: need max_lines <= max_keypoints <= 65535 (got %d, %d)", Ln, K);
   s->w = w; s->h = h; s->B = B; s->max_kp = K; s->max_ln = Ln;
+  s->pitch = plf_pitch16(w);
   plf_status st;
 #define PA(ptr, n) if ((st = pipe_alloc(ctx, s, &(ptr), (n)))) return st
-  const size_t A = (size_t)w * h, S = (size_t)B + 1;
-  PA(s->imgs2[0], 2 * (size_t)B * A);
-  PA(s->imgs2[1], 2 * (size_t)B * A);
+  const size_t A = (size_t)w * h, AP = (size_t)s->pitch * h, S = (size_t)B + 1;
+  PA(s->imgs2[0], 2 * (size_t)B * AP);
+  PA(s->imgs2[1], 2 * (size_t)B * AP);
   s->imgs = s->imgs2[0];
   PLF_CUDA(ctx, cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
@@ -410,6 +497,15 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PA(s->gn_sP, (size_t)B * Ln * 3); PA(s->gn_eP, (size_t)B * Ln * 3); PA(s->gn_le, (size_t)B * Ln * 3); PA(s->gnInlL, (size_t)B * Ln); PA(s->gnNl, B);
   PA(s->gn_probs, B); PA(s->gn_out, B); PA(s->results, 3 * (size_t)B);
   PA(s->d_ovf, 6);
+  if (ctx->params.matching_strategy) {
+    PA(s->mg_q[0], (size_t)B * K * 2); PA(s->mg_t[0], (size_t)B * K * 2);
+    PA(s->mg_q[1], (size_t)B * Ln * 4); PA(s->mg_t[1], (size_t)B * Ln * 4);
+    PA(s->mg_q[2], (size_t)B * K * 2); PA(s->mg_t[2], (size_t)B * K * 2);
+    PA(s->mg_q[3], (size_t)B * Ln * 4); PA(s->mg_t[3], (size_t)B * Ln * 4);
+    PA(s->mg_dir[0], (size_t)B * Ln * 2); PA(s->mg_dir[1], (size_t)B * Ln * 2);
+    PA(s->m12g, (size_t)B * 2 * K);
+    PA(s->mgcount, (size_t)B * 2);
+  }
 #undef PA
   for (int i = 0; i < 3; ++i) {
     PLF_CUDA(ctx, cudaHostAlloc(&s->h_results[i], sizeof(plf_frame_result) * B, cudaHostAllocDefault));
@@ -525,23 +621,22 @@ plf_status plf_batch_upload(plf_ctx* ctx, int B, const uint8_t* left, const uint
   plf_status st = pipe_prepare(ctx, w, h);
   if (st) return st;
   PipeState* s = ctx->pipe;
-  const size_t A = (size_t)w * h, hs = (size_t)stride * h;
+  const size_t A = (size_t)s->pitch * h;
   // H2D on the copy stream into the slot the GPU is not reading, so the copy of batch i+1 overlaps the run of batch i.
-  // Device layout interleaves the pair: image 2k = left k, 2k+1 = right k.
+  // Device layout interleaves the pair: image 2k = left k, 2k+1 = right k; rows are padded to a 16-byte pitch.
   const int slot = s->up_slot ^ 1;
   uint8_t* dst = s->imgs2[slot];
   PLF_CUDA(ctx, cudaStreamWaitEvent(s->copy, s->ev_free[slot], 0));   // the last run that read this slot has finished with it
   PLF_CUDA(ctx, cudaStreamWaitEvent(s->copy, s->ev_free2[slot], 0));  // (ORB / LBD prelude on one stream, LSD on another)
-  if (stride == w) {
-    // densely packed input: each image is one run of A bytes, so the whole side goes in ONE strided copy
-    // ("rows" = images, destination pitch 2A interleaves left and right)
-    PLF_CUDA(ctx, cudaMemcpy2DAsync(dst, 2 * A, left, A, A, B, cudaMemcpyHostToDevice, s->copy));
-    PLF_CUDA(ctx, cudaMemcpy2DAsync(dst + A, 2 * A, right, A, A, B, cudaMemcpyHostToDevice, s->copy));
-  } else {
-    for (int k = 0; k < B; ++k) {
-      PLF_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)(2 * k) * A, w, left + k * hs, stride, w, h, cudaMemcpyHostToDevice, s->copy));
-      PLF_CUDA(ctx, cudaMemcpy2DAsync(dst + (size_t)(2 * k + 1) * A, w, right + k * hs, stride, w, h, cudaMemcpyHostToDevice, s->copy));
-    }
+  // one 3-D copy per side: rows of w bytes, h rows per image, B images; the destination "height" of 2h rows skips the
+  // other side's image of each pair
+  for (int side = 0; side < 2; ++side) {
+    cudaMemcpy3DParms cp = {};
+    cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(side ? right : left), (size_t)stride, (size_t)w, (size_t)h);
+    cp.dstPtr = make_cudaPitchedPtr(dst + (size_t)side * A, (size_t)s->pitch, (size_t)w, 2 * (size_t)h);
+    cp.extent = make_cudaExtent((size_t)w, (size_t)h, (size_t)B);
+    cp.kind = cudaMemcpyHostToDevice;
+    PLF_CUDA(ctx, cudaMemcpy3DAsync(&cp, s->copy));
   }
   PLF_CUDA(ctx, cudaEventRecord(s->ev_up[slot], s->copy));
   s->up_slot = slot;
@@ -563,7 +658,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   PipeState* s = ctx->pipe;
   if (s->n_pending >= 3)
     return plf_fail(ctx, PLF_ERR_STATE, "plf_batch_run: three batches already in flight; call plf_batch_download first");
-  const size_t A = (size_t)w * h;
+  const size_t A = (size_t)w * h, AP = (size_t)s->pitch * h;   // dense maps / padded images
   const int K = s->max_kp, Ln = s->max_ln;
   const plf_params& P = ctx->params;
   const int par = (int)(s->seq & 1);   // parity of the E -> G -> M hand-off buffers
@@ -585,8 +680,8 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   PLF_CUDA(ctx, cudaStreamWaitEvent(sE, s->evX[par], 0));         // batch i-2 (same parity) no longer reads these buffers
   plf_mark(ctx, "start");
   PLF_CUDA(ctx, cudaEventRecord(s->tE0[par], sE));
-  st = plf_orb_run(ctx, imgs, A, w, h, 2 * B, par);
-  if (!st) st = plf_launch_blur5_sobel(ctx, imgs, w, A, w, h, 2 * B, s->lbd_grad[par], A);
+  st = plf_orb_run(ctx, imgs, AP, s->pitch, w, h, 2 * B, par);
+  if (!st) st = plf_launch_blur5_sobel(ctx, imgs, s->pitch, AP, w, h, 2 * B, s->lbd_grad[par], A);
   if (st) { ctx->cur = sM; return st; }
   plf_mark(ctx, "lbd.k_blur5_sobel");
   // this batch's ORB overflow flag: snapshot + clear on the E stream, so that a flag raised by batch i+1's extraction is
@@ -604,7 +699,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   ctx->cur = sG;
   PLF_CUDA(ctx, cudaStreamWaitEvent(sG, s->ev_up[run_slot], 0));
   PLF_CUDA(ctx, cudaEventRecord(s->tG0[par], sG));
-  st = plf_lsd_pre_range(ctx, imgs, A, w, h, 0, 0, 2 * B);
+  st = plf_lsd_pre_range(ctx, imgs, AP, s->pitch, w, h, 0, 0, 2 * B);
   if (st) { ctx->cur = sM; return st; }
   PLF_CUDA(ctx, cudaEventRecord(s->ev_free2[run_slot], sG));
   ctx->lsd_keylines_wait = piped ? s->evX[par ^ 1] : nullptr;  // batch i-1's match phase has copied its KeyLines
@@ -637,6 +732,30 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   kps = s->kpsM; odesc = s->descM; kcnt = s->kcntM; kls = s->klsM; lcnt = s->lcntM;
   plf_mark(ctx, "copy extraction outputs");
   PLF_CUDA(ctx, cudaMemsetAsync(s->mcount, 0, (size_t)B * 4 * sizeof(int), cs));
+  const double mg_iw = PLF_GRID_COLS / (double)w, mg_ih = PLF_GRID_ROWS / (double)h;   // StereoFrame::inv_width / inv_height
+  MgbArgs mga = {};
+  if (P.matching_strategy) {
+    // stereo association through matchGrid(): window (matching_s_ws, 0) x (0, 0) over the right image's grid
+    k_mg_geom_stereo<<<dim3((std::max(K, Ln) + 255) / 256, 2 * B), 256, 0, cs>>>(kps, kcnt, K, kls, lcnt, Ln, mg_iw, mg_ih, s->mg_q[0],
+                                                                                 s->mg_t[0], s->mg_q[1], s->mg_t[1], s->mg_dir[0]);
+    PLF_LAUNCH_CHECK(ctx);
+    mga.g = {PLF_GRID_COLS, PLF_GRID_ROWS, P.matching_s_ws, 0, 0, 0};
+    mga.best_lr = P.best_lr_matches ? 1 : 0;
+    mga.line_sim_th = (double)P.line_sim_th;
+    mga.is_lines = 0; mga.K = K; mga.nnr = P.min_ratio_12_p;
+    mga.q_geo = s->mg_q[0]; mga.t_geo = s->mg_t[0]; mga.t_dir = nullptr;
+    mga.d1 = odesc; mga.d1_stride = 2 * (size_t)K * 32; mga.d2 = odesc + (size_t)K * 32; mga.d2_stride = 2 * (size_t)K * 32;
+    mga.n1 = kcnt; mga.n1_stride = 2; mga.n2 = kcnt + 1; mga.n2_stride = 2;
+    mga.m12 = s->m12; mga.m12_stride = 4 * (size_t)K; mga.count = s->mcount; mga.count_stride = 4;
+    if ((st = plf_launch_match_grid_batch(ctx, mga, B, K))) return st;
+    mga.is_lines = 1; mga.K = Ln; mga.nnr = P.min_ratio_12_l;
+    mga.q_geo = s->mg_q[1]; mga.t_geo = s->mg_t[1]; mga.t_dir = s->mg_dir[0];
+    mga.d1 = s->ldesc_raw; mga.d1_stride = 2 * (size_t)Ln * 32; mga.d2 = s->ldesc_raw + (size_t)Ln * 32; mga.d2_stride = 2 * (size_t)Ln * 32;
+    mga.n1 = lcnt; mga.n2 = lcnt + 1;
+    mga.m12 = s->m12 + K; mga.count = s->mcount + 1;
+    if ((st = plf_launch_match_grid_batch(ctx, mga, B, Ln))) return st;
+    plf_mark(ctx, "stereo.k_mgb (matchGrid)");
+  } else {
   // L->R 2-NN for every left feature; R->L only for the right features that are somebody's accepted best match
   // (k_nnr_mutual reads nothing else of the reverse direction): the same matches for ~2/3 of the popcounts
   if ((st = plf_launch_knn2(ctx, s->knn_stereo, 2 * B, std::max(K, Ln)))) return st;
@@ -651,6 +770,7 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   plf_mark(ctx, "stereo.k_hamming_knn2");
   if ((st = plf_launch_nnr(ctx, s->nnr_stereo, 2 * B, std::max(K, Ln)))) return st;
   plf_mark(ctx, "stereo.k_nnr_mutual");
+  }
   StereoPrm sp = {P.max_dist_epip, P.min_disp, P.line_horiz_th, P.stereo_overlap_th, P.ls_min_disp_ratio,
                   ctx->cam.fx, ctx->cam.fy, ctx->cam.cx, ctx->cam.cy, ctx->cam.b};
   k_stereo_points<<<B, 1024, 0, cs>>>(kps, odesc, kcnt, K, s->m12, 4 * K, sp, s->fs, 1);
@@ -661,6 +781,33 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   if ((st = plf_launch_knn2(ctx, s->knn_f2f, 4 * B, std::max(K, Ln)))) return st;
   plf_mark(ctx, "f2f.k_hamming_knn2");
   if ((st = plf_launch_nnr(ctx, s->nnr_f2f, 2 * B, std::max(K, Ln)))) return st;
+  if (P.matching_strategy) {
+    // frame-to-frame: matchGrid() in a +-matching_f2f_ws window around the projected feature; the match() result above
+    // stands where the window search found fewer than min_pt_matches / min_ls_matches
+    PLF_CUDA(ctx, cudaMemsetAsync(s->mgcount, 0, (size_t)B * 2 * sizeof(int), cs));
+    k_mg_geom_f2f<<<dim3((std::max(K, Ln) + 255) / 256, B), 256, 0, cs>>>(s->fs, K, Ln, sp, mg_iw, mg_ih, s->mg_q[2], s->mg_t[2],
+                                                                          s->mg_q[3], s->mg_t[3], s->mg_dir[1]);
+    PLF_LAUNCH_CHECK(ctx);
+    const int ws = P.matching_f2f_ws;
+    mga.g = {PLF_GRID_COLS, PLF_GRID_ROWS, ws, ws, ws, ws};
+    mga.is_lines = 0; mga.K = K; mga.nnr = P.min_ratio_12_p;
+    mga.q_geo = s->mg_q[2]; mga.t_geo = s->mg_t[2]; mga.t_dir = nullptr;
+    mga.d1 = s->fs.pdesc; mga.d1_stride = (size_t)K * 32; mga.d2 = s->fs.pdesc + (size_t)K * 32; mga.d2_stride = (size_t)K * 32;
+    mga.n1 = s->fs.pt_count; mga.n1_stride = 1; mga.n2 = s->fs.pt_count + 1; mga.n2_stride = 1;
+    mga.m12 = s->m12g; mga.m12_stride = 2 * (size_t)K; mga.count = s->mgcount; mga.count_stride = 2;
+    if ((st = plf_launch_match_grid_batch(ctx, mga, B, K))) return st;
+    mga.is_lines = 1; mga.K = Ln; mga.nnr = P.min_ratio_12_l;
+    mga.q_geo = s->mg_q[3]; mga.t_geo = s->mg_t[3]; mga.t_dir = s->mg_dir[1];
+    mga.d1 = s->fs.ldesc; mga.d1_stride = (size_t)Ln * 32; mga.d2 = s->fs.ldesc + (size_t)Ln * 32; mga.d2_stride = (size_t)Ln * 32;
+    mga.n1 = s->fs.ls_count; mga.n2 = s->fs.ls_count + 1;
+    mga.m12 = s->m12g + K; mga.count = s->mgcount + 1;
+    if ((st = plf_launch_match_grid_batch(ctx, mga, B, Ln))) return st;
+    k_mg_select<<<dim3((K + 255) / 256, B), 256, 0, cs>>>(s->m12g, s->mgcount, s->fs.pt_count, K, K, 0, P.min_pt_matches, s->m12);
+    PLF_LAUNCH_CHECK(ctx);
+    k_mg_select<<<dim3((Ln + 255) / 256, B), 256, 0, cs>>>(s->m12g, s->mgcount, s->fs.ls_count, Ln, K, 1, P.min_ls_matches, s->m12);
+    PLF_LAUNCH_CHECK(ctx);
+    plf_mark(ctx, "f2f.k_mgb (matchGrid)");
+  }
   k_f2f_build<<<B, 1024, 0, cs>>>(s->fs, 0, K, Ln, s->m12 + 2 * K, s->m12 + 3 * K, 4 * K, s->gnP, s->gnObs, s->gnInlP, s->gnNp,
                                   s->gn_sP, s->gn_eP, s->gn_le, s->gnInlL, s->gnNl);
   PLF_LAUNCH_CHECK(ctx);

@@ -158,6 +158,11 @@ void plf_default_params(plf_params* p) {
   p->lsd_log_eps = 1.0;
   p->lsd_density_th = 0.6;
   p->lsd_n_bins = 1024;
+  p->matching_strategy = 0;
+  p->matching_s_ws = 10;
+  p->matching_f2f_ws = 3;
+  p->min_pt_matches = 10;
+  p->min_ls_matches = 6;
 }
 
 void plf_default_limits(plf_limits* l) {

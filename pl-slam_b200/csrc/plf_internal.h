@@ -112,6 +112,28 @@ plf_status plf_launch_nnr(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, in
 plf_status plf_launch_nnr_mark(plf_ctx* ctx, const NnrProblem* d_probs, int nprob, int max_n1, int* flags, int* qlist,
                                int* qcount, int stride);
 
+// ---- windowed greedy matcher, batched device-resident form (matchgrid.cu) ------------------------------------
+struct MgGrid { int cols, rows, w_lo, w_hi, h_lo, h_hi; };
+struct MgbArgs {
+  MgGrid g;
+  int is_lines, K, best_lr;
+  float nnr;
+  double line_sim_th;
+  const int* q_geo;      // [P][K][2|4]  query cells (points) / integer end points in grid units (lines)
+  const int* t_geo;      // [P][K][2|4]
+  const double* t_dir;   // [P][K][2] (lines) unit directions of the train lines
+  const uint8_t* d1; size_t d1_stride;   // descriptor rows of problem p: d1 + p * d1_stride
+  const uint8_t* d2; size_t d2_stride;
+  const int* n1; int n1_stride;          // counts: n1[p * n1_stride]
+  const int* n2; int n2_stride;
+  unsigned short* D;     // scratch (set by the launcher)
+  uint32_t* qmask;
+  int* m21;
+  int32_t* m12; size_t m12_stride;       // output rows of problem p: m12 + p * m12_stride
+  int* count; int count_stride;          // matches of problem p (accumulated; zeroed by the caller)
+};
+plf_status plf_launch_match_grid_batch(plf_ctx* ctx, MgbArgs a, int nprob, int max_n);
+
 // ---- LBD (lbd.cu) ------------------------------------------------------------------------------
 plf_status plf_launch_blur5_sobel(plf_ctx* ctx, const uint8_t* imgs, int pitch, size_t img_stride,
                                   int w, int h, int nimg, short2* grad, size_t grad_stride);
@@ -140,16 +162,16 @@ plf_status plf_launch_gn(plf_ctx* ctx, const GnProblem* d_probs, int nprob, cons
 
 // ---- ORB (orb.cu) --------------------------------------------------------------------------------
 plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_parities);
-plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg, int par);
+plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int pitch, int w, int h, int nimg, int par);
 void plf_orb_outputs(plf_ctx* ctx, int par, plf_keypoint** kps, uint8_t** desc, int** counts, int* max_kp);
 void plf_linear_coeffs_host(int srcsize, int dstsize, double scale, int* ofs, int* c1);
-plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_stride, int sw, int sh, uint8_t* dst,
-                                   size_t dst_stride, int dw, int dh, const int* tabx, const int* taby, int nimg);
+plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_stride, int sp, int sw, int sh, uint8_t* dst,
+                                   size_t dst_stride, int dp, int dw, int dh, const int* tabx, const int* taby, int nimg);
 
 // ---- LSD (lsd.cu) --------------------------------------------------------------------------------
 plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_parities);
-plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int nimg);
-plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int w, int h, int par, int img0, int n);
+plf_status plf_lsd_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int pitch, int w, int h, int nimg);
+plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, int pitch, int w, int h, int par, int img0, int n);
 plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int n);
 void plf_lsd_outputs(plf_ctx* ctx, int par, plf_keyline** kls, int** nlines, int* max_lines);
 int* plf_orb_overflow_flag(plf_ctx* ctx);

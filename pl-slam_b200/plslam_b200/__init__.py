@@ -40,6 +40,8 @@ class plf_params(C.Structure):
         ("lsd_scale", C.c_double), ("lsd_sigma_scale", C.c_double), ("lsd_quant", C.c_double),
         ("lsd_ang_th", C.c_double), ("lsd_log_eps", C.c_double), ("lsd_density_th", C.c_double),
         ("lsd_n_bins", C.c_int),
+        ("matching_strategy", C.c_int), ("matching_s_ws", C.c_int), ("matching_f2f_ws", C.c_int),
+        ("min_pt_matches", C.c_int), ("min_ls_matches", C.c_int),
     ]
 
 

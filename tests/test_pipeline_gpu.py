@@ -29,7 +29,9 @@ def run_both(cam, frames, B, **prm_over):
     prm = dict(ofe.DEFAULTS, **prm_over)
     ref = ofe.run_sequence(cam, [(a, b) for a, b, _ in frames], prm)
     lim = plf.default_limits(); lim.max_batch = B
-    kw = {k: v for k, v in prm_over.items() if k in ("orb_nfeatures", "lsd_nfeatures", "max_iters", "max_iters_ref", "min_features")}
+    kw = {k: v for k, v in prm_over.items() if k in ("orb_nfeatures", "lsd_nfeatures", "max_iters", "max_iters_ref", "min_features",
+                                                     "matching_strategy", "matching_s_ws", "matching_f2f_ws", "min_pt_matches",
+                                                     "min_ls_matches")}
     got, feats = [], []
     with plf.Frontend(camera=cam, limits=lim, **kw) as fe:
         for s0 in range(0, len(frames), B):
@@ -73,6 +75,38 @@ def test_pipeline_euroc_shape_stream(built):
     world = synth.World(seed=8, length=40.0, n_quads=220, n_segs=120, half_width=5.0, half_height=3.0)
     frames = list(synth.stream(cam, 4, world=world, seed=43, step=0.08, yaw_deg=0.8))
     ref, got, feats = run_both(cam, frames, 1, orb_nfeatures=1200, lsd_nfeatures=300)
+    compare(ref, got, feats)
+
+
+@pytest.mark.parametrize("shape", ["kitti", "euroc", "lowtex"])
+def test_pipeline_windowed_matching_strategy(built, shape):
+    """plf_params.matching_strategy = 3 (the reference configs, config_euroc.yaml:55-57): stereo association through
+    matchGrid() with the (matching_s_ws, 0) x (0, 0) window, frame-to-frame tracking through matchGrid() in a
+    +-matching_f2f_ws window with the match() fall-back of src/mapHandler.cpp:274-278 - features, matches and poses
+    equal to the oracle's (oracle/frontend.py track_matches / grid_match_*), all on the device."""
+    if shape == "kitti":
+        cam, frames, over, B = plf.KITTI_CAMERA, list(synth.stream(plf.KITTI_CAMERA, 5)), dict(orb_nfeatures=1500, lsd_nfeatures=200), 3
+    elif shape == "euroc":
+        cam = plf.EUROC_CAMERA
+        world = synth.World(seed=8, length=40.0, n_quads=220, n_segs=120, half_width=5.0, half_height=3.0)
+        frames, over, B = list(synth.stream(cam, 4, world=world, seed=43, step=0.08, yaw_deg=0.8)), dict(orb_nfeatures=1200, lsd_nfeatures=300), 2
+    else:
+        cam = plf.KITTI_CAMERA
+        frames, over, B = list(synth.stream(cam, 3, world=synth.corridor_world(), seed=17, noise=2)), dict(orb_nfeatures=150, lsd_nfeatures=0), 3
+    ref, got, feats = run_both(cam, frames, B, matching_strategy=3, **over)
+    compare(ref, got, feats)
+    ref0 = ofe.run_sequence(cam, [(a, b) for a, b, _ in frames[:2]], dict(ofe.DEFAULTS, **over))
+    assert (ref[1]["n_pt"], ref[1]["n_ls"]) != (ref0[1]["n_pt"], ref0[1]["n_ls"])   # the strategy does change the association
+
+
+def test_pipeline_windowed_matching_fallback(built):
+    """A window of 0 cells with a large min_pt_matches forces the match() fall-back for points while lines keep the
+    window result (min_ls_matches = 0)."""
+    cam = dict(plf.KITTI_CAMERA, width=640, height=360, cx=320.0, cy=180.0, fx=500.0, fy=500.0)
+    world = synth.World(seed=4, length=50.0, n_quads=160, n_segs=80, half_width=8.0, half_height=3.5)
+    frames = list(synth.stream(cam, 4, world=world, seed=9, step=0.9))     # large motion: the 0-cell window loses most points
+    ref, got, feats = run_both(cam, frames, 2, orb_nfeatures=800, lsd_nfeatures=150, matching_strategy=3, matching_f2f_ws=0,
+                               min_pt_matches=500, min_ls_matches=0)
     compare(ref, got, feats)
 
 
