@@ -126,7 +126,7 @@ __global__ void __launch_bounds__(256) k_blur5_sobel_fast(const __grid_constant_
   __shared__ __align__(16) uint8_t blur[LBF_TH + 2][BW + 4];
   __shared__ __align__(8) uint64_t bar;
   short2* out = grad + (size_t)blockIdx.z * grad_stride;
-  const int x0 = blockIdx.x * LBF_TW, y0 = blockIdx.y * LBF_TH, tid = threadIdx.x;
+  const int x0 = blockIdx.x * LBF_TW - 13, y0 = blockIdx.y * LBF_TH, tid = threadIdx.x;   // x0 - 3 on a 16-byte boundary (TMA)
   if (tid == 0) plf_mbar_init(&bar);
   __syncthreads();
   if (tid == 0) plf_tma_load_3d(&raw[0][0], &tmap, x0 - 3, y0 - 3, (int)blockIdx.z, &bar, RH * RP);
@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(256) k_blur5_sobel_fast(const __grid_constant_
   // Sobel (BORDER_REFLECT_101 on the blurred image is reproduced by the reflect-staged raw tile, see k_blur5_sobel)
   const int tx = tid & 63, q = tid >> 6;
   const int gx = x0 + tx;
-  if (gx < w) {
+  if (gx >= 0 && gx < w) {
     int a0[3], a1[3], a2[3];
     const int by0 = q * 8;
 #pragma unroll
@@ -219,7 +219,7 @@ plf_status plf_launch_blur5_sobel(plf_ctx* ctx, const uint8_t* imgs, int pitch, 
         return plf_fail(ctx, PLF_ERR_CUDA, "LBD: cuTensorMapEncodeTiled failed (pitch %d, stride %zu)", pitch, img_stride);
       s->tm_src[slot] = imgs;
     }
-    dim3 grid((w + LBF_TW - 1) / LBF_TW, (h + LBF_TH - 1) / LBF_TH, nimg);
+    dim3 grid(plf_tma_tiles_x(w, 3), (h + LBF_TH - 1) / LBF_TH, nimg);
     k_blur5_sobel_fast<<<grid, 256, 0, ctx->cur>>>(s->tm[slot], w, h, grad, grad_stride);
   } else {  // tiny images / unpadded rows: generic kernel
     dim3 grid((w + LBD_TW - 1) / LBD_TW, (h + LBD_TH - 1) / LBD_TH, nimg);

@@ -163,7 +163,7 @@ __global__ void __launch_bounds__(256) k_blur_q8_fast(const __grid_constant__ CU
   __shared__ __align__(16) uint16_t hrow[RH][BF_TW];
   __shared__ __align__(8) uint64_t bar;
   uint8_t* d = dst + (size_t)blockIdx.z * dst_stride;
-  const int x0 = blockIdx.x * BF_TW, y0 = blockIdx.y * BF_TH, tid = threadIdx.x;
+  const int x0 = blockIdx.x * BF_TW - (16 - R), y0 = blockIdx.y * BF_TH, tid = threadIdx.x;   // x0 - R on a 16-byte boundary (TMA)
   if (tid == 0) plf_mbar_init(&bar);
   __syncthreads();
   if (tid == 0) plf_tma_load_3d(&raw[0][0], &tmap, x0 - R, y0 - R, z0 + (int)blockIdx.z, &bar, RH * RP);
@@ -188,7 +188,7 @@ __global__ void __launch_bounds__(256) k_blur_q8_fast(const __grid_constant__ CU
   __syncthreads();
   const int c = tid & 63, q = tid >> 6;
   const int gx = x0 + c;
-  if (gx < w) {
+  if (gx >= 0 && gx < w) {
     uint32_t t[KS];
 #pragma unroll
     for (int k = 0; k < KS; ++k) t[k] = k < 4 ? ((tapsA >> (8 * k)) & 0xFFu) : ((tapsB >> (8 * (k - 4))) & 0xFFu);
@@ -1251,7 +1251,7 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
       }
       uint32_t tA = 0, tB = 0;
       for (int k = 0; k < s->ksize; ++k) (k < 4 ? tA : tB) |= (uint32_t)s->taps[k] << (8 * (k & 3));
-      dim3 gf((w + BF_TW - 1) / BF_TW, (h + BF_TH - 1) / BF_TH, n);
+      dim3 gf(plf_tma_tiles_x(w, s->ksize / 2), (h + BF_TH - 1) / BF_TH, n);
       if (s->ksize == 7) k_blur_q8_fast<7><<<gf, 256, 0, cs>>>(s->tm_blur[slot], img0, w, h, tA, tB, blur, A, s->bp);
       else k_blur_q8_fast<5><<<gf, 256, 0, cs>>>(s->tm_blur[slot], img0, w, h, tA, tB, blur, A, s->bp);
     } else {

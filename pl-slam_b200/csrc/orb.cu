@@ -72,7 +72,7 @@ struct OrbState {
   int* kp_count[2] = {nullptr, nullptr};      // [nimg]
   int* overflow = nullptr;      // [1]
   float blur_k[7];
-  // TMA descriptors (plf_tma.cuh): halo boxes of the FAST tile (80 x 38) and of the blur tile (80 x 38) per level; level 0
+  // TMA descriptors (plf_tma.cuh): halo boxes of the FAST tile (96 x 38) and of the blur tile (80 x 38) per level; level 0
   // is the caller's image buffer (re-encoded when its address changes - the pipeline alternates between two)
   CUtensorMap tm_fast[ORB_MAX_LEVELS], tm_blur[ORB_MAX_LEVELS];
   const void* tm_src0[2] = {nullptr, nullptr};   // image buffers the cached level-0 maps were encoded for
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(256, 5) k_fast_nms(const __grid_constant__ CUt
   const int W = g.w[l], H = g.h[l];
   const int x0 = (blockIdx.x % tiles_x) * FN_OW, y0 = (blockIdx.x / tiles_x) * FN_OH;
   const int img = blockIdx.y;
-  __shared__ __align__(128) uint8_t px[38][80];   // pixel (x0 - 4 + rx, y0 - 4 + ry): the TMA box (80 x 38 bytes)
+  __shared__ __align__(128) uint8_t pxb[38][96];  // the TMA box (96 x 38 bytes) from the 16-byte boundary at or below x0 - 4
   __shared__ uint8_t sc[32][64];   // score of pixel (x0 - 1 + sx, y0 - 1 + sy)
   __shared__ unsigned short clist[32 * 64];
   __shared__ int ccount;
@@ -221,7 +221,10 @@ __global__ void __launch_bounds__(256, 5) k_fast_nms(const __grid_constant__ CUt
   __syncthreads();
   // The tile + halo arrives as ONE bulk-tensor copy (TMA).  Positions outside the image come back as zeros - they are
   // never used by a valid score (gx in [3, W-3), gy in [3, H-3)).
-  if (tid == 0) plf_tma_load_3d(&px[0][0], &tmap, x0 - 4, y0 - 4, img, &bar, 38 * 80);
+  const int xs = (x0 - 4) & ~15;   // (two's complement: also the boundary below a negative origin)
+  if (tid == 0) plf_tma_load_3d(&pxb[0][0], &tmap, xs, y0 - 4, img, &bar, 38 * 96);
+  // px[ry][rx] = pixel (x0 - 4 + rx, y0 - 4 + ry)
+  const uint8_t (*px)[96] = reinterpret_cast<const uint8_t (*)[96]>(&pxb[0][(x0 - 4) - xs]);
   plf_mbar_wait(&bar, 0);
   const int th = g.fast_th;
   // Pass A: cheap rejection.  A 9-arc of the 16-ring always contains one pixel of every opposite pair (k, k+8)
@@ -480,7 +483,7 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const __grid_constant__ 
   __shared__ __align__(16) float hrow[RH][OBF_TW];
   __shared__ __align__(8) uint64_t bar;
   const int W = g.w[l], H = g.h[l], BP = g.bpitch[l];
-  const int x0 = (blockIdx.x % tiles_x) * OBF_TW, y0 = (blockIdx.x / tiles_x) * OBF_TH;
+  const int x0 = (blockIdx.x % tiles_x) * OBF_TW - 13, y0 = (blockIdx.x / tiles_x) * OBF_TH;   // x0 - 3 on a 16-byte boundary (TMA)
   const int img = blockIdx.y;
   uint8_t* dst = blur + (size_t)img * g.blur_stride + g.blur_off[l];
   const int tid = threadIdx.x;
@@ -512,7 +515,7 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const __grid_constant__ 
   __syncthreads();
   const int c = tid & 63, q = tid >> 6;
   const int gx = x0 + c;
-  if (gx < W) {
+  if (gx >= 0 && gx < W) {
     float v[14];
 #pragma unroll
     for (int k = 0; k < 14; ++k) v[k] = hrow[q * 8 + k][c];
@@ -759,7 +762,7 @@ plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   // tensor maps of the pyramid levels (fixed addresses); level 0 = the caller's image buffer, encoded per run
   s->tm_src0[0] = s->tm_src0[1] = nullptr;
   for (int l = 1; l < g.nlevels; ++l) {
-    if (!plf_tma_encode_u8(&s->tm_fast[l], s->pyr + g.pyr_off[l], g.w[l], g.h[l], nimg, g.pitch[l], g.pyr_stride, 80, 38) ||
+    if (!plf_tma_encode_u8(&s->tm_fast[l], s->pyr + g.pyr_off[l], g.w[l], g.h[l], nimg, g.pitch[l], g.pyr_stride, 96, 38) ||
         !plf_tma_encode_u8(&s->tm_blur[l], s->pyr + g.pyr_off[l], g.w[l], g.h[l], nimg, g.pitch[l], g.pyr_stride, 80, OBF_TH + 6))
       return plf_fail(ctx, PLF_ERR_CUDA, "ORB: cuTensorMapEncodeTiled failed for pyramid level %d", l);
   }
@@ -784,7 +787,7 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
   for (int k = 0; k < 2; ++k) if (s->tm_src0[k] == d_imgs) slot = k;
   if (slot < 0) {
     slot = s->tm_src0[0] ? (s->tm_src0[1] ? 0 : 1) : 0;
-    if (!plf_tma_encode_u8(&s->tm_fast0[slot], d_imgs, w, h, s->tm_nimg0, pitch, img_stride, 80, 38) ||
+    if (!plf_tma_encode_u8(&s->tm_fast0[slot], d_imgs, w, h, s->tm_nimg0, pitch, img_stride, 96, 38) ||
         !plf_tma_encode_u8(&s->tm_blur0[slot], d_imgs, w, h, s->tm_nimg0, pitch, img_stride, 80, OBF_TH + 6))
       return plf_fail(ctx, PLF_ERR_CUDA, "ORB: cuTensorMapEncodeTiled failed for the source images (pitch %d, stride %zu)", pitch, img_stride);
     s->tm_src0[slot] = d_imgs;
@@ -813,7 +816,7 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "orb.k_ic_angle");
   for (int l = 0; l < g.nlevels; ++l) {
-    const int tx_ = (g.w[l] + OBF_TW - 1) / OBF_TW, ty_ = (g.h[l] + OBF_TH - 1) / OBF_TH;
+    const int tx_ = plf_tma_tiles_x(g.w[l], 3), ty_ = (g.h[l] + OBF_TH - 1) / OBF_TH;
     k_orb_blur7_fast<<<dim3(tx_ * ty_, nimg), 256, 0, cs>>>(l == 0 ? s->tm_blur0[slot] : s->tm_blur[l], g, s->blur, l, tx_);
     PLF_LAUNCH_CHECK(ctx);
   }

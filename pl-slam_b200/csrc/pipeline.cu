@@ -27,6 +27,7 @@ struct PipeState {
   bool has_prev = false;
   uint8_t* imgs = nullptr;     // images of the batch being run: = imgs2[run_slot]
   uint8_t* imgs2[2] = {nullptr, nullptr};  // double-buffered [2B][h][pitch]: upload of batch i+1 overlaps the run of batch i
+  uint8_t* stage = nullptr;    // dense [2B][h][w] landing buffer of the H2D copy (one contiguous DMA per side), repacked to the padded pitch on the device
   int up_slot = 0;             // slot written by the last plf_batch_upload
   cudaStream_t copy = nullptr; // H2D stream
   cudaEvent_t ev_up[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr}, ev_free2[2] = {nullptr, nullptr};
@@ -68,6 +69,8 @@ struct PipeState {
   // from there on batch i+2 may overwrite the parity's extraction buffers, so E(i+2) overlaps the rest of M(i) and
   // G(i+1).  Up to PIPE_DEPTH = 3 batches may be in flight (run, run, run, download, ...).
   cudaEvent_t evE[2] = {nullptr, nullptr}, evG[2] = {nullptr, nullptr}, evX[2] = {nullptr, nullptr};
+  cudaEvent_t evP[2] = {nullptr, nullptr};   // end of the LSD pre-grow phase (stream P)
+  bool lsd2 = false;            // LSD hand-off buffers exist per batch parity: pre-grow of batch i+1 overlaps the growing of batch i
   cudaEvent_t evM[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t tE0[2] = {nullptr, nullptr}, tG0[2] = {nullptr, nullptr}, tM0[3] = {nullptr, nullptr, nullptr};  // phase starts (timeline)
   long long seq = 0;            // batches issued
@@ -101,6 +104,7 @@ extern "C" void plf_pipe_free(plf_ctx* ctx) {
     if (s->evE[i]) cudaEventDestroy(s->evE[i]);
     if (s->evG[i]) cudaEventDestroy(s->evG[i]);
     if (s->evX[i]) cudaEventDestroy(s->evX[i]);
+    if (s->evP[i]) cudaEventDestroy(s->evP[i]);
     if (s->tE0[i]) cudaEventDestroy(s->tE0[i]);
     if (s->tG0[i]) cudaEventDestroy(s->tG0[i]);
   }
@@ -446,13 +450,25 @@ __global__ void __launch_bounds__(256) k_mg_select(const int32_t* __restrict__ m
   if (!fall_back) m12[((size_t)k * 4 + 2 + which) * K + i] = m12g[((size_t)k * 2 + which) * K + i];
 }
 
+// The LSD hand-off maps (gradient, record, seed order, region points: 28 bytes per scaled pixel) exist once or per batch
+// parity (PLF_LSD_PARITIES = 2).  Per parity the pre-grow chain of batch i+1 (blur, resample, gradient, seed ordering) runs
+// on its own stream while batch i is still growing regions, which takes the pre-grow kernels off the LSD chain.  Measured on
+// B200 (B = 1536, KITTI shape): 121.0 ms per step with two parities (157 GB) against 118.7 ms with one copy (97 GB) - the
+// step is bound by the SMs' total issue work, not by the chain (the E phase stretches from 36 ms alone to 88 ms while it
+// shares the SMs with the growing kernel), so the default stays ONE copy and the memory is left to the batch size.
+static bool lsd_want_two_parities(const plf_ctx* ctx, int w, int h, int nimg) {
+  (void)ctx; (void)w; (void)h; (void)nimg;
+  const char* e = getenv("PLF_LSD_PARITIES");
+  return e && atoi(e) >= 2;
+}
+
 static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PipeState* s = ctx->pipe;
   if (s && s->w == w && s->h == h) {
     // a standalone operator call on another image size may have rebuilt the ORB / LSD state meanwhile
     plf_status st0;
     if ((st0 = plf_orb_prepare(ctx, w, h, 2 * s->B, true))) return st0;
-    if ((st0 = plf_lsd_prepare(ctx, w, h, 2 * s->B, false))) return st0;
+    if ((st0 = plf_lsd_prepare(ctx, w, h, 2 * s->B, s->lsd2))) return st0;
     plf_keypoint* kps0; uint8_t* d0; int* c0; int m0;
     plf_orb_outputs(ctx, 0, &kps0, &d0, &c0, &m0);
     plf_keyline* kl0; int* lc0; int ml0;
@@ -471,6 +487,7 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   const size_t A = (size_t)w * h, AP = (size_t)s->pitch * h, S = (size_t)B + 1;
   PA(s->imgs2[0], 2 * (size_t)B * AP);
   PA(s->imgs2[1], 2 * (size_t)B * AP);
+  if (s->pitch != w) PA(s->stage, 2 * (size_t)B * A);
   s->imgs = s->imgs2[0];
   PLF_CUDA(ctx, cudaStreamCreateWithFlags(&s->copy, cudaStreamNonBlocking));
   for (int i = 0; i < 2; ++i) {
@@ -519,6 +536,7 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
     PLF_CUDA(ctx, cudaEventCreate(&s->evE[i]));
     PLF_CUDA(ctx, cudaEventCreate(&s->evG[i]));
     PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evX[i], cudaEventDisableTiming));
+    PLF_CUDA(ctx, cudaEventCreateWithFlags(&s->evP[i], cudaEventDisableTiming));
     PLF_CUDA(ctx, cudaEventCreate(&s->tE0[i]));
     PLF_CUDA(ctx, cudaEventCreate(&s->tG0[i]));
   }
@@ -526,7 +544,8 @@ static plf_status pipe_prepare(plf_ctx* ctx, int w, int h) {
   PLF_CUDA(ctx, cudaMemsetAsync(f.ls_count, 0, S * sizeof(int), ctx->stream));
   // sub-systems sized for 2B images
   if ((st = plf_orb_prepare(ctx, w, h, 2 * B, true))) return st;
-  if ((st = plf_lsd_prepare(ctx, w, h, 2 * B, false))) return st;
+  s->lsd2 = lsd_want_two_parities(ctx, w, h, 2 * B);
+  if ((st = plf_lsd_prepare(ctx, w, h, 2 * B, s->lsd2))) return st;
   // static problem descriptors (pointers never change; counts are read on the device)
   const plf_params& P = ctx->params;
   cudaStream_t cs = ctx->stream;
@@ -628,15 +647,28 @@ plf_status plf_batch_upload(plf_ctx* ctx, int B, const uint8_t* left, const uint
   uint8_t* dst = s->imgs2[slot];
   PLF_CUDA(ctx, cudaStreamWaitEvent(s->copy, s->ev_free[slot], 0));   // the last run that read this slot has finished with it
   PLF_CUDA(ctx, cudaStreamWaitEvent(s->copy, s->ev_free2[slot], 0));  // (ORB / LBD prelude on one stream, LSD on another)
-  // one 3-D copy per side: rows of w bytes, h rows per image, B images; the destination "height" of 2h rows skips the
-  // other side's image of each pair
-  for (int side = 0; side < 2; ++side) {
-    cudaMemcpy3DParms cp = {};
-    cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(side ? right : left), (size_t)stride, (size_t)w, (size_t)h);
-    cp.dstPtr = make_cudaPitchedPtr(dst + (size_t)side * A, (size_t)s->pitch, (size_t)w, 2 * (size_t)h);
-    cp.extent = make_cudaExtent((size_t)w, (size_t)h, (size_t)B);
-    cp.kind = cudaMemcpyHostToDevice;
-    PLF_CUDA(ctx, cudaMemcpy3DAsync(&cp, s->copy));
+  const size_t A0 = (size_t)w * h;
+  if (stride == w && s->stage) {
+    // densely packed input: ONE contiguous H2D copy per side into the dense landing buffer ("rows" = images, pitch 2 A0
+    // interleaves left and right), then a device-to-device 2-D copy widens the rows to the 16-byte pitch (the DMA engines
+    // move 1242-byte rows from host memory at a fraction of the contiguous rate: measured 8.9 k vs 12.7 k pairs/s end to end)
+    PLF_CUDA(ctx, cudaMemcpy2DAsync(s->stage, 2 * A0, left, A0, A0, B, cudaMemcpyHostToDevice, s->copy));
+    PLF_CUDA(ctx, cudaMemcpy2DAsync(s->stage + A0, 2 * A0, right, A0, A0, B, cudaMemcpyHostToDevice, s->copy));
+    PLF_CUDA(ctx, cudaMemcpy2DAsync(dst, (size_t)s->pitch, s->stage, (size_t)w, (size_t)w, 2 * (size_t)B * h, cudaMemcpyDeviceToDevice, s->copy));
+  } else if (stride == w) {   // pitch == w: the dense layout is the device layout
+    PLF_CUDA(ctx, cudaMemcpy2DAsync(dst, 2 * A, left, A, A, B, cudaMemcpyHostToDevice, s->copy));
+    PLF_CUDA(ctx, cudaMemcpy2DAsync(dst + A, 2 * A, right, A, A, B, cudaMemcpyHostToDevice, s->copy));
+  } else {
+    // strided input: one 3-D copy per side (rows of w bytes, h rows per image, B images; the destination "height" of 2h
+    // rows skips the other side's image of each pair)
+    for (int side = 0; side < 2; ++side) {
+      cudaMemcpy3DParms cp = {};
+      cp.srcPtr = make_cudaPitchedPtr(const_cast<uint8_t*>(side ? right : left), (size_t)stride, (size_t)w, (size_t)h);
+      cp.dstPtr = make_cudaPitchedPtr(dst + (size_t)side * A, (size_t)s->pitch, (size_t)w, 2 * (size_t)h);
+      cp.extent = make_cudaExtent((size_t)w, (size_t)h, (size_t)B);
+      cp.kind = cudaMemcpyHostToDevice;
+      PLF_CUDA(ctx, cudaMemcpy3DAsync(&cp, s->copy));
+    }
   }
   PLF_CUDA(ctx, cudaEventRecord(s->ev_up[slot], s->copy));
   s->up_slot = slot;
@@ -669,10 +701,13 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   // With profiling on everything is serialised on the main stream so that the per-kernel marks are meaningful.
   const bool piped = !ctx->profile || ctx->profile_piped;
   cudaStream_t sM = ctx->stream, sE = piped ? ctx->aux[0] : sM, sG = piped ? ctx->aux[1] : sM;
+  const bool lsd2 = s->lsd2;
+  cudaStream_t sP = (piped && lsd2) ? ctx->aux[2] : sG;   // LSD pre-grow chain: own stream when its outputs exist per parity
+  const int lp = lsd2 ? par : 0;                         // parity of the LSD hand-off buffers
   plf_keypoint* kps; uint8_t* odesc; int* kcnt; int mk;
   plf_keyline* kls; int* lcnt; int ml;
   plf_orb_outputs(ctx, par, &kps, &odesc, &kcnt, &mk);
-  plf_lsd_outputs(ctx, 0, &kls, &lcnt, &ml);
+  plf_lsd_outputs(ctx, lp, &kls, &lcnt, &ml);
 
   // ---- E phase: ORB + LBD gradient prelude (bandwidth / ALU bound); outputs per batch parity ----
   ctx->cur = sE;
@@ -691,19 +726,24 @@ plf_status plf_batch_run(plf_ctx* ctx, int B) {
   PLF_CUDA(ctx, cudaEventRecord(s->evE[par], sE));
   PLF_CUDA(ctx, cudaEventRecord(s->ev_free[run_slot], sE));  // the image buffer may be overwritten by the next upload
 
-  // ---- G phase: the whole LSD chain on one stream - blur / resize / gradient / seed ordering, then region growing
-  // (latency bound, one warp per image), rectangle fit and KeyLines.  Its per-pixel maps exist ONCE (no batch parity:
-  // they are 2/3 of the pipeline's memory, and the batch size - the number of images the latency-bound growing kernel
-  // keeps in flight - is what they would cost), so LSD(i+1) starts when LSD(i) ends; ORB(i+1), ORB(i+2) and M(i) fill
-  // the SMs meanwhile. ----
-  ctx->cur = sG;
-  PLF_CUDA(ctx, cudaStreamWaitEvent(sG, s->ev_up[run_slot], 0));
-  PLF_CUDA(ctx, cudaEventRecord(s->tG0[par], sG));
-  st = plf_lsd_pre_range(ctx, imgs, AP, s->pitch, w, h, 0, 0, 2 * B);
+  // ---- P / G phases: the LSD chain.  P = blur / resize / gradient / seed ordering (bandwidth-bound), G = region growing
+  // (latency bound, one warp per image), rectangle fit and KeyLines.  With the hand-off maps per batch parity (lsd2) P runs
+  // on its own stream: P(i+1) overlaps G(i), and the chain on the critical path is G alone; with one copy (the maps are
+  // 2/3 of the pipeline's memory) P and G share a stream and LSD(i+1) starts when LSD(i) ends. ----
+  ctx->cur = sP;
+  PLF_CUDA(ctx, cudaStreamWaitEvent(sP, s->ev_up[run_slot], 0));
+  if (lsd2) PLF_CUDA(ctx, cudaStreamWaitEvent(sP, s->evG[par], 0));   // batch i-2 (same parity) has finished growing / fitting on these maps
+  PLF_CUDA(ctx, cudaEventRecord(s->tG0[par], sP));
+  st = plf_lsd_pre_range(ctx, imgs, AP, s->pitch, w, h, lp, 0, 2 * B);
   if (st) { ctx->cur = sM; return st; }
-  PLF_CUDA(ctx, cudaEventRecord(s->ev_free2[run_slot], sG));
-  ctx->lsd_keylines_wait = piped ? s->evX[par ^ 1] : nullptr;  // batch i-1's match phase has copied its KeyLines
-  st = plf_lsd_grow_range(ctx, w, h, 0, 0, 2 * B);
+  PLF_CUDA(ctx, cudaEventRecord(s->ev_free2[run_slot], sP));
+  PLF_CUDA(ctx, cudaEventRecord(s->evP[par], sP));
+  ctx->cur = sG;
+  PLF_CUDA(ctx, cudaStreamWaitEvent(sG, s->evP[par], 0));
+  // the KeyLine outputs are overwritten: the match phase that read them last (batch i-2 with two parities, batch i-1 with one)
+  // has taken its copy
+  ctx->lsd_keylines_wait = piped ? s->evX[lsd2 ? par : par ^ 1] : nullptr;
+  st = plf_lsd_grow_range(ctx, w, h, lp, 0, 2 * B);
   ctx->lsd_keylines_wait = nullptr;
   if (st) { ctx->cur = sM; return st; }
   PLF_CUDA(ctx, cudaMemcpyAsync(s->d_ovf + 2 * rp + 1, plf_lsd_overflow_flag(ctx), sizeof(int), cudaMemcpyDeviceToDevice, sG));

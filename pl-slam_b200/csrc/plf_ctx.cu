@@ -220,7 +220,7 @@ plf_status plf_create(const plf_params* params, const plf_camera* cam, const plf
   }
   ctx->cur = ctx->stream;
   bool ok = true;
-  for (int i = 0; i < 2 && ok; ++i) ok = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 3 && ok; ++i) ok = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess;
   if (!ok) {
     plf_destroy(ctx);
     return plf_fail(nullptr, PLF_ERR_NO_DEVICE, "plf_create: could not create auxiliary streams/events");
@@ -247,7 +247,7 @@ void plf_destroy(plf_ctx* ctx) {
     if (b.p) cudaFree(b.p);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   for (auto e : ctx->prof_ev) cudaEventDestroy(e);
-  for (int i = 0; i < 2; ++i)
+  for (int i = 0; i < 3; ++i)
     if (ctx->aux[i]) { cudaStreamSynchronize(ctx->aux[i]); cudaStreamDestroy(ctx->aux[i]); }
   cudaStreamDestroy(ctx->stream);
   delete ctx;

@@ -28,7 +28,7 @@ struct plf_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;  // main stream: copies, the serial part of the pipeline, standalone operators
   cudaStream_t cur = nullptr;     // stream the launch helpers enqueue on (== stream except inside forked sections)
-  cudaStream_t aux[2] = {nullptr, nullptr};  // streams of the extraction (E) and LSD (G) phases of plf_batch_run
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};  // streams of the extraction (E), LSD growing (G) and LSD pre-grow (P) phases of plf_batch_run
   cudaEvent_t lsd_keylines_wait = nullptr;  // if set: plf_lsd_grow_range waits for it before it overwrites the KeyLine outputs
   plf_params params;
   plf_camera cam;

@@ -4,7 +4,11 @@
 // any halo tile of any image of a batch a legal box of a 3-D tensor map {x: width, y: height, z: image} with strides
 // {1, pitch, image stride}.  One elected thread issues ONE bulk-tensor copy per CTA (SASS: UTMALDG.3D) that lands the
 // (tile + halo) box in shared memory and signals an mbarrier with the byte count; the other threads only wait on the
-// barrier - no per-thread address arithmetic, no funnel shifts, no st.shared.  Elements of the box that lie outside the
+// barrier - no per-thread address arithmetic, no funnel shifts, no st.shared.  The hardware wants the box to START on a
+// 16-byte boundary of global memory (measured on B200: any other x origin faults with "illegal instruction"; y and z are
+// free because the strides are multiples of 16), so the tile grids are shifted: a kernel whose tile needs columns from
+// x0 - R places its tiles at x0 = 64 * bx - (16 - R) (plf_tma_x0), or loads a wider box from the aligned address below
+// its origin and indexes it with the remainder (FAST).  Elements of the box that lie outside the
 // image come back as zeros; kernels that need BORDER_REFLECT_101 patch those cells from the in-image part of the same
 // tile (plf_tma_reflect_fix: shared memory -> shared memory, border CTAs only).
 #pragma once
@@ -13,6 +17,8 @@
 #include <stdint.h>
 
 static inline int plf_pitch16(int w) { return (w + 15) & ~15; }
+// number of 64-column tiles when the tile grid is shifted left by (16 - R) columns (see above)
+static inline int plf_tma_tiles_x(int w, int R) { return (w + (16 - R) + 63) / 64; }
 
 // Host: tensor map over nimg images of w x h bytes, row pitch `pitch`, image stride `img_stride` (both multiples of
 // 16), box = box_w x box_h x 1 (box_w a multiple of 16).  The driver entry point is resolved through the runtime so

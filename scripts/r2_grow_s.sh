@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
+build/tma_probe | tail -12
 # 1. TMA-staged tile kernels + padded pitches with the default (warp) growing kernel: whole GPU suite + bench
 unset PLF_GROW_CFG
 ( time timeout 900 python -m pytest tests -m gpu -x -q ) > gpurun_out/r2_tma_gputests.log 2>&1
