@@ -199,9 +199,21 @@ __device__ int fast_corner_score(const int* d /*16*/) {
 }
 
 // Tile = 62 x 30 output pixels; scores are needed on a 64 x 32 region (1-px halo for the NMS) and pixels on a 70 x 38
-// region (3-px ring).  All index arithmetic is lane + 32*k / warp + 8*k (no div/mod), every lane is active in every pass.
+// region (3-px ring), which arrives as one TMA box (96 x 38 bytes from the 16-byte boundary at or below x0 - 4).
+//   pass A  rejection, FOUR pixels per step on the aligned 32-bit words of the box: |v - p0| and |v - p8| of four adjacent
+//           centres are two VABSDIFF4 on the words of rows y-3 / y / y+3, and "some difference exceeds the threshold" is a
+//           3-instruction SWAR compare - a 9-arc of the 16-ring always contains one pixel of every opposite pair (k, k+8)
+//           (OpenCV's FAST_t uses the same test), so a group whose four bytes all fail is dropped after ~5 instructions per
+//           pixel; the surviving bytes go through the pairs (4,12), (2,10), (6,14) one pixel at a time and are compacted;
+//   pass B  full ring test + exact cornerScore on the compacted candidates (dense warps);
+//   NMS     3x3 strict maximum + border filter + append, over the candidates only (nothing else has a score).
 #define FN_OW 62
 #define FN_OH 30
+// bit 7 of every byte of d that is greater than th (bytes are unsigned; k7 = (0x7f - (th & 0x7f)) * 0x01010101)
+__device__ __forceinline__ uint32_t fast_gt4(uint32_t d, uint32_t k7, bool th_small) {
+  const uint32_t low = (d & 0x7f7f7f7fu) + k7;           // bit 7 <=> (d & 0x7f) > (th & 0x7f); no carry crosses a byte
+  return (th_small ? (low | d) : (low & d)) & 0x80808080u;
+}
 __global__ void __launch_bounds__(256, 5) k_fast_nms(const __grid_constant__ CUtensorMap tmap, OrbGeom g, int l, int tiles_x,
                                                   uint32_t* __restrict__ cand, int* __restrict__ cand_count,
                                                   int* __restrict__ hist, int* __restrict__ overflow) {
@@ -209,65 +221,63 @@ __global__ void __launch_bounds__(256, 5) k_fast_nms(const __grid_constant__ CUt
   const int x0 = (blockIdx.x % tiles_x) * FN_OW, y0 = (blockIdx.x / tiles_x) * FN_OH;
   const int img = blockIdx.y;
   __shared__ __align__(128) uint8_t pxb[38][96];  // the TMA box (96 x 38 bytes) from the 16-byte boundary at or below x0 - 4
-  __shared__ uint8_t sc[32][64];   // score of pixel (x0 - 1 + sx, y0 - 1 + sy)
+  __shared__ __align__(16) uint8_t sc[32][64];    // score of pixel (x0 - 1 + sx, y0 - 1 + sy)
   __shared__ unsigned short clist[32 * 64];
   __shared__ int ccount;
   __shared__ __align__(8) uint64_t bar;
-  const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  const int tid = threadIdx.x;
   if (tid == 0) {
     ccount = 0;
     plf_mbar_init(&bar);
   }
+  reinterpret_cast<uint2*>(&sc[0][0])[tid] = make_uint2(0u, 0u);   // 256 x 8 bytes = the whole score tile
   __syncthreads();
   // The tile + halo arrives as ONE bulk-tensor copy (TMA).  Positions outside the image come back as zeros - they are
   // never used by a valid score (gx in [3, W-3), gy in [3, H-3)).
   const int xs = (x0 - 4) & ~15;   // (two's complement: also the boundary below a negative origin)
   if (tid == 0) plf_tma_load_3d(&pxb[0][0], &tmap, xs, y0 - 4, img, &bar, 38 * 96);
+  const int boxoff = (x0 - 4) - xs;   // box column of pixel x0 - 4
   // px[ry][rx] = pixel (x0 - 4 + rx, y0 - 4 + ry)
-  const uint8_t (*px)[96] = reinterpret_cast<const uint8_t (*)[96]>(&pxb[0][(x0 - 4) - xs]);
-  plf_mbar_wait(&bar, 0);
+  const uint8_t (*px)[96] = reinterpret_cast<const uint8_t (*)[96]>(&pxb[0][boxoff]);
   const int th = g.fast_th;
-  // Pass A: cheap rejection.  A 9-arc of the 16-ring always contains one pixel of every opposite pair (k, k+8)
-  // (OpenCV's FAST_t uses the same test): a pair with both members inside the threshold band rules the pixel out.
-  // Survivors are compacted so that pass B runs the full ring test on dense warps.
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int sy = wrp + 8 * a;
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int sx = lane + 32 * b;
-      const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
-      bool cand_px = false;
-      if (gx >= 3 && gx < W - 3 && gy >= 3 && gy < H - 3) {
-        const int cy = sy + 3, cx = sx + 3;
-        const int v = px[cy][cx];
-        const int q0 = v - px[cy + 3][cx], q8 = v - px[cy - 3][cx];
-        bool pd = (q0 > th) | (q8 > th), pb = (q0 < -th) | (q8 < -th);
-        if (pd | pb) {
-          const int q4 = v - px[cy][cx + 3], q12 = v - px[cy][cx - 3];
-          pd &= (q4 > th) | (q12 > th);
-          pb &= (q4 < -th) | (q12 < -th);
-          if (pd | pb) {
-            const int q2 = v - px[cy + 2][cx + 2], q10 = v - px[cy - 2][cx - 2];
-            const int q6 = v - px[cy - 2][cx + 2], q14 = v - px[cy + 2][cx - 2];
-            pd &= ((q2 > th) | (q10 > th)) & ((q6 > th) | (q14 > th));
-            pb &= ((q2 < -th) | (q10 < -th)) & ((q6 < -th) | (q14 < -th));
-            cand_px = pd | pb;
-          }
-        }
-      }
-      sc[sy][sx] = 0;
-      const unsigned bal = __ballot_sync(0xFFFFFFFFu, cand_px);
-      if (bal) {
-        const int leader = __ffs(bal) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&ccount, __popc(bal));
-        base = __shfl_sync(0xFFFFFFFFu, base, leader);
-        if (cand_px) clist[base + __popc(bal & ((1u << lane) - 1))] = (unsigned short)(sy * 64 + sx);
+  const uint32_t k7 = (uint32_t)(0x7f - (th & 0x7f)) * 0x01010101u;
+  const bool th_small = th < 128;
+  plf_mbar_wait(&bar, 0);
+  // ---- pass A: score pixel (sy, sx) sits at box row sy + 3, box column c_first + sx
+  const int c_first = boxoff + 3, w_first = c_first >> 2, nwords = ((c_first + 63) >> 2) - w_first + 1;   // 16 or 17 words
+  for (int gi = tid; gi < 32 * 17; gi += 256) {
+    const int sy = gi / 17, wi = gi - sy * 17;
+    const int gy = y0 - 1 + sy;
+    if (wi >= nwords || gy < 3 || gy >= H - 3) continue;
+    const int wcol = w_first + wi;
+    const uint32_t wc = reinterpret_cast<const uint32_t*>(&pxb[sy + 3][0])[wcol];
+    const uint32_t wd = reinterpret_cast<const uint32_t*>(&pxb[sy + 6][0])[wcol];   // ring pixel 0: (x, y + 3)
+    const uint32_t wu = reinterpret_cast<const uint32_t*>(&pxb[sy][0])[wcol];       // ring pixel 8: (x, y - 3)
+    uint32_t t = fast_gt4(__vabsdiffu4(wc, wd), k7, th_small) | fast_gt4(__vabsdiffu4(wc, wu), k7, th_small);
+    while (t) {
+      const int b = (__ffs(t) - 1) >> 3;   // byte whose pair (0, 8) does not rule it out
+      t &= ~(0x80u << (8 * b));
+      const int sx = 4 * wcol + b - c_first;
+      const int gx = x0 - 1 + sx;
+      if (sx < 0 || sx >= 64 || gx < 3 || gx >= W - 3) continue;
+      const int cy = sy + 3, cx = sx + 3;
+      const int v = (wc >> (8 * b)) & 0xFF;
+      const int q0 = v - (int)((wd >> (8 * b)) & 0xFF), q8 = v - (int)((wu >> (8 * b)) & 0xFF);
+      bool pd = (q0 > th) | (q8 > th), pb = (q0 < -th) | (q8 < -th);
+      const int q4 = v - px[cy][cx + 3], q12 = v - px[cy][cx - 3];
+      pd &= (q4 > th) | (q12 > th);
+      pb &= (q4 < -th) | (q12 < -th);
+      if (pd | pb) {
+        const int q2 = v - px[cy + 2][cx + 2], q10 = v - px[cy - 2][cx - 2];
+        const int q6 = v - px[cy - 2][cx + 2], q14 = v - px[cy + 2][cx - 2];
+        pd &= ((q2 > th) | (q10 > th)) & ((q6 > th) | (q14 > th));
+        pb &= ((q2 < -th) | (q10 < -th)) & ((q6 < -th) | (q14 < -th));
+        if (pd | pb) clist[atomicAdd(&ccount, 1)] = (unsigned short)(sy * 64 + sx);
       }
     }
   }
   __syncthreads();
+  // ---- pass B: full ring test + score on the candidates
   const int nc = ccount;
   for (int c = tid; c < nc; c += 256) {
     const int i = clist[c];
@@ -290,28 +300,24 @@ __global__ void __launch_bounds__(256, 5) k_fast_nms(const __grid_constant__ CUt
     if (has_run9(md) || has_run9(mb)) sc[sy][sx] = (uint8_t)fast_corner_score(d);
   }
   __syncthreads();
-  // NMS over the 62 x 30 interior of the score region + border filter + append
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    const int sy = wrp + 8 * a;
-#pragma unroll
-    for (int b = 0; b < 2; ++b) {
-      const int sx = lane + 32 * b;
-      if (sy < 1 || sy > FN_OH || sx < 1 || sx > FN_OW) continue;
-      const int s = sc[sy][sx];
-      if (s == 0) continue;
-      const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
-      if (gx < g.edge || gx >= W - g.edge || gy < g.edge || gy >= H - g.edge) continue;  // runByImageBorder
-      if (!(s > sc[sy][sx - 1] && s > sc[sy][sx + 1] && s > sc[sy - 1][sx - 1] && s > sc[sy - 1][sx] &&
-            s > sc[sy - 1][sx + 1] && s > sc[sy + 1][sx - 1] && s > sc[sy + 1][sx] && s > sc[sy + 1][sx + 1]))
-        continue;
-      const int slot = atomicAdd(&cand_count[img * ORB_MAX_LEVELS + l], 1);
-      if (slot < g.cand_cap[l])
-        cand[(size_t)img * g.cand_stride + g.cand_off[l] + slot] = ((uint32_t)gy << 20) | ((uint32_t)gx << 8) | (uint32_t)s;
-      else
-        *overflow = 1;
-      atomicAdd(&hist[(img * ORB_MAX_LEVELS + l) * 256 + s], 1);
-    }
+  // ---- NMS over the 62 x 30 interior of the score region + border filter + append: only candidates carry a score
+  for (int c = tid; c < nc; c += 256) {
+    const int i = clist[c];
+    const int sy = i >> 6, sx = i & 63;
+    if (sy < 1 || sy > FN_OH || sx < 1 || sx > FN_OW) continue;
+    const int s = sc[sy][sx];
+    if (s == 0) continue;
+    const int gx = x0 - 1 + sx, gy = y0 - 1 + sy;
+    if (gx < g.edge || gx >= W - g.edge || gy < g.edge || gy >= H - g.edge) continue;  // runByImageBorder
+    if (!(s > sc[sy][sx - 1] && s > sc[sy][sx + 1] && s > sc[sy - 1][sx - 1] && s > sc[sy - 1][sx] &&
+          s > sc[sy - 1][sx + 1] && s > sc[sy + 1][sx - 1] && s > sc[sy + 1][sx] && s > sc[sy + 1][sx + 1]))
+      continue;
+    const int slot = atomicAdd(&cand_count[img * ORB_MAX_LEVELS + l], 1);
+    if (slot < g.cand_cap[l])
+      cand[(size_t)img * g.cand_stride + g.cand_off[l] + slot] = ((uint32_t)gy << 20) | ((uint32_t)gx << 8) | (uint32_t)s;
+    else
+      *overflow = 1;
+    atomicAdd(&hist[(img * ORB_MAX_LEVELS + l) * 256 + s], 1);
   }
 }
 
