@@ -276,6 +276,51 @@ plf_status plf_gn_pose(plf_ctx* ctx, const plf_gn_opts* opts, const double* P, c
                        const double* le_obs, uint8_t* inlier_ls, int nl, const double* T_init,
                        plf_pose_result* out);
 
+/* Local bundle adjustment.  Replaces MapHandler::levMarquardtOptimizationLBA (src/mapHandler.cpp:1332-1989),
+ * the numerical core of MapHandler::localBundleAdjustment (:1220-1330): Levenberg-Marquardt over the local keyframes'
+ * poses, the local 3-D points and the local 3-D segments with Cauchy-weighted residuals, solved on the device through the
+ * Schur complement on the landmarks.  The caller (MapHandler) assembles the lists exactly as :1224-1319 does:
+ *   kf_pose  [n_kf][6]  x_kf_w of the local keyframes (se(3) vectors [t; w]), in / out
+ *   pt       [n_pt][3]  point3D of the local map points, in / out;   ls [n_ls][6]  line3D (start | end), in / out
+ *   fixed_T  [n_fixed][16]  T_kf_w (row-major) of the keyframes that observe local landmarks but are not optimised
+ *   observations, grouped per landmark in ascending local landmark index (obs_aux(1), :1257,:1298):
+ *     *_obs_lm   local landmark index          *_obs_kf  local keyframe index (obs_aux(4)), or -1 - k for fixed_T[k]
+ *     pt_obs_xy [.][2] observed pixel          ls_obs_le [.][3] observed (normalised) line equation
+ *   pt_moved / ls_moved (may be NULL): 1 where the landmark moved by more than 0.01 - the reference then clears its
+ *     inlier flag (:1826-1851).
+ * opts: lambda / lambda_k / max_iters = SlamConfig::lambdaLbaLM / lambdaLbaK / maxItersLba (src/slamConfig.cpp:64-66);
+ * ref_quirks = 1 reproduces four oddities of the reference as written (oracle/lba.c lists them with their lines),
+ * 0 follows its evident intent.  Returns PLF_ERR_INVALID for an empty problem (the reference returns -1, :1324-1328). */
+typedef struct plf_lba_opts {
+  double lambda, lambda_k;
+  int max_iters;
+  double homog_th, min_error, min_error_change;
+  int ref_quirks;
+} plf_lba_opts;
+typedef struct plf_lba_problem {
+  int n_kf, n_pt, n_ls, n_fixed;
+  double* kf_pose;
+  double* pt;
+  double* ls;
+  const double* fixed_T;
+  int n_pt_obs;
+  const int* pt_obs_lm;
+  const int* pt_obs_kf;
+  const double* pt_obs_xy;
+  int n_ls_obs;
+  const int* ls_obs_lm;
+  const int* ls_obs_kf;
+  const double* ls_obs_le;
+  uint8_t* pt_moved;
+  uint8_t* ls_moved;
+} plf_lba_problem;
+typedef struct plf_lba_result {
+  int iters;     /* value of the reference's loop counter at exit */
+  double err;    /* last normalised weighted error */
+  double lambda; /* final damping */
+} plf_lba_result;
+plf_status plf_local_ba(plf_ctx* ctx, const plf_lba_opts* opts, const plf_lba_problem* problem, plf_lba_result* out);
+
 /* Relative pose between two keyframes.  Replaces MapHandler::isLoopClosure (src/mapHandler.cpp:3192-3300:
  * match() on the points :3223 and on the lines :3249 of kf0 / kf1, the inlier-ratio pre-condition :3277-3299) followed by
  * MapHandler::computeRelativePoseRobustGN (:3566-3957: two-stage robust GN from identity with the chi2 gate in between,

@@ -183,3 +183,44 @@ def lsd(img, scale=1.2, sigma_scale=0.6, quant=2.0, ang_th=22.5, n_bins=1024, or
     if n < 0:
         raise RuntimeError("lsd oracle: capacity exceeded")
     return segs[:n].copy()
+
+
+class _LbaOpts(C.Structure):
+    _fields_ = [("lambda_", C.c_double), ("lambda_k", C.c_double), ("max_iters", C.c_int), ("homog_th", C.c_double),
+                ("min_error", C.c_double), ("min_error_change", C.c_double), ("ref_quirks", C.c_int)]
+
+
+class _LbaResult(C.Structure):
+    _fields_ = [("iters", C.c_int), ("err", C.c_double), ("lambda_", C.c_double)]
+
+
+def lba_opts(lambda_=1e-5, lambda_k=10.0, max_iters=15, homog_th=1e-7, min_error=1e-7, min_error_change=1e-7, ref_quirks=1):
+    """Defaults: src/slamConfig.cpp:64-66 (lambda_lba_lm, lambda_lba_k, max_iters_lba), config_euroc.yaml:45,49-50."""
+    return dict(lambda_=lambda_, lambda_k=lambda_k, max_iters=max_iters, homog_th=homog_th, min_error=min_error,
+                min_error_change=min_error_change, ref_quirks=ref_quirks)
+
+
+def local_ba(cam, prob, opts=None):
+    """MapHandler::levMarquardtOptimizationLBA (oracle/lba.c).  prob: dict with kf_pose [nkf,6], pt [npt,3], ls [nls,6],
+    fixed_T [nf,4,4], pt_obs_lm / pt_obs_kf / pt_obs_xy, ls_obs_lm / ls_obs_kf / ls_obs_le (kf < 0: fixed keyframe -1-k)."""
+    o = _LbaOpts(**(opts or lba_opts()))
+    c = orc_camera(**{k: cam[k] for k in ("width", "height", "fx", "fy", "cx", "cy", "b")})
+    kf = np.ascontiguousarray(prob["kf_pose"], np.float64).reshape(-1, 6)
+    pt = np.ascontiguousarray(prob["pt"], np.float64).reshape(-1, 3)
+    ls = np.ascontiguousarray(prob["ls"], np.float64).reshape(-1, 6)
+    X = np.concatenate([kf.ravel(), pt.ravel(), ls.ravel()]).astype(np.float64)
+    fT = np.ascontiguousarray(prob.get("fixed_T", np.zeros((0, 4, 4))), np.float64).reshape(-1, 16)
+    i32 = lambda k: np.ascontiguousarray(prob[k], np.int32).ravel()
+    f64 = lambda k: np.ascontiguousarray(prob[k], np.float64).ravel()
+    po_lm, po_kf, po_xy = i32("pt_obs_lm"), i32("pt_obs_kf"), f64("pt_obs_xy")
+    lo_lm, lo_kf, lo_le = i32("ls_obs_lm"), i32("ls_obs_kf"), f64("ls_obs_le")
+    pm, lm = np.zeros(max(len(pt), 1), np.uint8), np.zeros(max(len(ls), 1), np.uint8)
+    res = _LbaResult()
+    f = lib().orc_local_ba
+    f.restype = C.c_int
+    rc = f(C.byref(c), C.byref(o), len(kf), len(pt), len(ls), _p(X), len(fT), _p(fT), len(po_lm), _p(po_lm), _p(po_kf), _p(po_xy),
+           len(lo_lm), _p(lo_lm), _p(lo_kf), _p(lo_le), _p(pm), _p(lm), C.byref(res))
+    nk, npt = 6 * len(kf), 3 * len(pt)
+    return dict(rc=rc, kf_pose=X[:nk].reshape(-1, 6), pt=X[nk:nk + npt].reshape(-1, 3), ls=X[nk + npt:].reshape(-1, 6),
+                pt_moved=pm[:len(pt)].astype(bool), ls_moved=lm[:len(ls)].astype(bool), iters=res.iters, err=res.err,
+                lambda_=res.lambda_)

@@ -74,4 +74,20 @@ int orc_inverse6(const double* A, double* Ainv);
 void orc_gn_pose(const orc_camera* cam, const orc_gn_opts* o, const double* P, const double* obs, uint8_t* inl_p,
                  int np, const double* sP, const double* eP, const double* le, uint8_t* inl_l, int nl,
                  const double* T_init, orc_pose_result* out);
+
+/* ---- local bundle adjustment (oracle/lba.c; src/mapHandler.cpp:1332-1989) ---- */
+typedef struct orc_lba_opts {
+  double lambda;           /* SlamConfig::lambdaLbaLM  (src/slamConfig.cpp:64: 0.00001) */
+  double lambda_k;         /* SlamConfig::lambdaLbaK   (:65: 10) */
+  int max_iters;           /* SlamConfig::maxItersLba  (:66: 15) */
+  double homog_th;         /* SlamConfig::homogTh */
+  double min_error;        /* Config::minError */
+  double min_error_change; /* Config::minErrorChange */
+  int ref_quirks;          /* 1: reproduce the reference as written (see lba.c), 0: the evident intent */
+} orc_lba_opts;
+typedef struct orc_lba_result { int iters; double err; double lambda; } orc_lba_result;
+int orc_local_ba(const orc_camera* cam, const orc_lba_opts* o, int nkf, int npt, int nls, double* X, int n_fixed,
+                 const double* fixed_T, int npo, const int* po_lm, const int* po_kf, const double* po_xy, int nlo,
+                 const int* lo_lm, const int* lo_kf, const double* lo_le, uint8_t* pt_moved, uint8_t* ls_moved,
+                 orc_lba_result* out);
 #endif

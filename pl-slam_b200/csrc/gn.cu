@@ -16,6 +16,7 @@
 #include <float.h>
 
 #include "plf_internal.h"
+#include "plf_se3.cuh"
 
 #define GN_THREADS 128
 #define GN_NACC 29  // 21 (H upper) + 6 (g) + e + N
@@ -74,92 +75,6 @@ __device__ __forceinline__ void gn_add_row(double* acc, const double* J, double 
 }
 
 // ---- small dense helpers (single thread) ---------------------------------------------------------
-__device__ void d_skew(const double* w, double* S) {
-  S[0] = 0; S[1] = -w[2]; S[2] = w[1];
-  S[3] = w[2]; S[4] = 0; S[5] = -w[0];
-  S[6] = -w[1]; S[7] = w[0]; S[8] = 0;
-}
-__device__ void d_mul3(const double* A, const double* B, double* C) {
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < 3; ++j)
-      C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
-}
-
-// T <- T * inverse_se3(expmap_se3(x)),  x = [t; w]
-__device__ void d_update_pose(double* T, const double* x) {
-  double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {x[0], x[1], x[2]};
-  const double* w = x + 3;
-  const double theta = sqrt(w[0] * w[0] + w[1] * w[1] + w[2] * w[2]);
-  if (!(theta < 0.000001)) {
-    double s[9], s2[9], V[9];
-    d_skew(w, s);
-    for (int i = 0; i < 9; ++i) s[i] /= theta;
-    d_mul3(s, s, s2);
-    const double sn = sin(theta), cs = cos(theta);
-    for (int i = 0; i < 9; ++i) {
-      const double I = (i % 4 == 0) ? 1.0 : 0.0;
-      R[i] = I + s[i] * sn + s2[i] * (1.0 - cs);
-      V[i] = I + s[i] * (1.0 - cs) / theta + s2[i] * (theta - sn) / theta;
-    }
-    const double t0 = t[0], t1 = t[1], t2 = t[2];
-    for (int i = 0; i < 3; ++i) t[i] = V[3 * i] * t0 + V[3 * i + 1] * t1 + V[3 * i + 2] * t2;
-  }
-  // E^-1 = [R^T, -R^T t]
-  double Ei[16];
-  for (int i = 0; i < 3; ++i) {
-    for (int j = 0; j < 3; ++j) Ei[4 * i + j] = R[3 * j + i];
-    Ei[4 * i + 3] = -(R[i] * t[0] + R[3 + i] * t[1] + R[6 + i] * t[2]);
-  }
-  Ei[12] = Ei[13] = Ei[14] = 0;
-  Ei[15] = 1;
-  double out[16];
-  for (int i = 0; i < 4; ++i)
-    for (int j = 0; j < 4; ++j) {
-      double a = 0;
-      for (int k = 0; k < 4; ++k) a += T[4 * i + k] * Ei[4 * k + j];
-      out[4 * i + j] = a;
-    }
-  for (int i = 0; i < 16; ++i) T[i] = out[i];
-}
-
-__device__ void d_logmap(const double* T, double* x) {
-  double V[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, w[3] = {0, 0, 0};
-  const double Vt[3] = {T[3], T[7], T[11]};
-  double cosine = (T[0] + T[5] + T[10] - 1.0) / 2.0;
-  cosine = cosine > 1.0 ? 1.0 : (cosine < -1.0 ? -1.0 : cosine);
-  double sine = sqrt(1.0 - cosine * cosine);
-  sine = sine > 1.0 ? 1.0 : sine;
-  const double theta = acos(cosine);
-  if (theta > 0.000001) {
-    const double k = theta / (2.0 * sine);
-    w[0] = k * (T[9] - T[6]);
-    w[1] = k * (T[2] - T[8]);
-    w[2] = k * (T[4] - T[1]);
-    double s[9], s2[9];
-    d_skew(w, s);
-    for (int i = 0; i < 9; ++i) s[i] /= theta;
-    d_mul3(s, s, s2);
-    for (int i = 0; i < 9; ++i) {
-      const double I = (i % 4 == 0) ? 1.0 : 0.0;
-      V[i] = I + s[i] * (1.0 - cosine) / theta + s2[i] * (theta - sine) / theta;
-    }
-  }
-  const double det = V[0] * (V[4] * V[8] - V[5] * V[7]) - V[1] * (V[3] * V[8] - V[5] * V[6]) +
-                     V[2] * (V[3] * V[7] - V[4] * V[6]);
-  const double id = 1.0 / det;
-  const double Vi[9] = {(V[4] * V[8] - V[5] * V[7]) * id, (V[2] * V[7] - V[1] * V[8]) * id,
-                        (V[1] * V[5] - V[2] * V[4]) * id, (V[5] * V[6] - V[3] * V[8]) * id,
-                        (V[0] * V[8] - V[2] * V[6]) * id, (V[2] * V[3] - V[0] * V[5]) * id,
-                        (V[3] * V[7] - V[4] * V[6]) * id, (V[1] * V[6] - V[0] * V[7]) * id,
-                        (V[0] * V[4] - V[1] * V[3]) * id};
-  for (int i = 0; i < 3; ++i) x[i] = Vi[3 * i] * Vt[0] + Vi[3 * i + 1] * Vt[1] + Vi[3 * i + 2] * Vt[2];
-  x[3] = w[0];
-  x[4] = w[1];
-  x[5] = w[2];
-}
-
-// Column-pivoting Householder QR solve of the 6x6 system H x = g (Eigen ColPivHouseholderQR semantics:
-// rank-revealing, rank-deficient directions get 0).
 __device__ void d_colpiv_qr_solve6(const double* Hin, const double* gin, double* x) {
   const int n = 6;
   double A[36], b[6], Rd[6];

@@ -55,6 +55,23 @@ class plf_limits(C.Structure):
                 ("max_lines", C.c_int)]
 
 
+class plf_lba_opts(C.Structure):
+    _fields_ = [("lambda_", C.c_double), ("lambda_k", C.c_double), ("max_iters", C.c_int), ("homog_th", C.c_double),
+                ("min_error", C.c_double), ("min_error_change", C.c_double), ("ref_quirks", C.c_int)]
+
+
+class plf_lba_problem(C.Structure):
+    _fields_ = [("n_kf", C.c_int), ("n_pt", C.c_int), ("n_ls", C.c_int), ("n_fixed", C.c_int),
+                ("kf_pose", C.c_void_p), ("pt", C.c_void_p), ("ls", C.c_void_p), ("fixed_T", C.c_void_p),
+                ("n_pt_obs", C.c_int), ("pt_obs_lm", C.c_void_p), ("pt_obs_kf", C.c_void_p), ("pt_obs_xy", C.c_void_p),
+                ("n_ls_obs", C.c_int), ("ls_obs_lm", C.c_void_p), ("ls_obs_kf", C.c_void_p), ("ls_obs_le", C.c_void_p),
+                ("pt_moved", C.c_void_p), ("ls_moved", C.c_void_p)]
+
+
+class plf_lba_result(C.Structure):
+    _fields_ = [("iters", C.c_int), ("err", C.c_double), ("lambda_", C.c_double)]
+
+
 class plf_grid_window(C.Structure):
     _fields_ = [("width_lo", C.c_int), ("width_hi", C.c_int), ("height_lo", C.c_int), ("height_hi", C.c_int)]
 
@@ -388,6 +405,26 @@ class Frontend:
         r["x_inc"] = np.array(out.x_inc); r["pose_inc"] = np.array(out.pose_inc)
         r["pt_pairs"] = pp[:out.n_pt].copy(); r["ls_pairs"] = lp[:out.n_ls].copy()
         return r
+
+    def local_ba(self, prob, lambda_=1e-5, lambda_k=10.0, max_iters=15, homog_th=1e-7, min_error=1e-7,
+                 min_error_change=1e-7, ref_quirks=1):
+        """MapHandler::levMarquardtOptimizationLBA on the device (plf_local_ba; src/mapHandler.cpp:1332-1989).
+        prob: dict as produced by synth.lba_problem (kf_pose, pt, ls, fixed_T, pt_obs_*, ls_obs_*)."""
+        f64 = lambda a, c: np.ascontiguousarray(a, np.float64).reshape(-1, c).copy()
+        i32 = lambda a: np.ascontiguousarray(a, np.int32).ravel().copy()
+        kf, pt, ls = f64(prob["kf_pose"], 6), f64(prob["pt"], 3), f64(prob["ls"], 6)
+        fT = np.ascontiguousarray(prob.get("fixed_T", np.zeros((0, 4, 4))), np.float64).reshape(-1, 16).copy()
+        po_lm, po_kf, po_xy = i32(prob["pt_obs_lm"]), i32(prob["pt_obs_kf"]), f64(prob["pt_obs_xy"], 2)
+        lo_lm, lo_kf, lo_le = i32(prob["ls_obs_lm"]), i32(prob["ls_obs_kf"]), f64(prob["ls_obs_le"], 3)
+        pm, lm = np.zeros(max(len(pt), 1), np.uint8), np.zeros(max(len(ls), 1), np.uint8)
+        ad = lambda a: a.ctypes.data if a.size else None
+        p = plf_lba_problem(len(kf), len(pt), len(ls), len(fT), ad(kf), ad(pt), ad(ls), ad(fT), len(po_lm), ad(po_lm), ad(po_kf),
+                            ad(po_xy), len(lo_lm), ad(lo_lm), ad(lo_kf), ad(lo_le), ad(pm), ad(lm))
+        o = plf_lba_opts(lambda_, lambda_k, max_iters, homog_th, min_error, min_error_change, int(ref_quirks))
+        res = plf_lba_result()
+        self._check(self.lib.plf_local_ba(self._ctx, C.byref(o), C.byref(p), C.byref(res)), "plf_local_ba")
+        return dict(kf_pose=kf, pt=pt, ls=ls, pt_moved=pm[:len(pt)].astype(bool), ls_moved=lm[:len(ls)].astype(bool),
+                    iters=res.iters, err=res.err, lambda_=res.lambda_)
 
     def expmap_se3(self, x):
         x = np.ascontiguousarray(x, np.float64).reshape(6)

@@ -211,3 +211,72 @@ def stream(cam, n_frames, world=None, seed=42, traj=None, noise=3, **traj_kw):
         L = render_view(world, cam, T_cw, 0.0, rng, noise)
         Rr = render_view(world, cam, T_cw, cam["b"], rng, noise)
         yield L, Rr, T_wc
+
+
+# ---- synthetic local-map problems for the bundle adjustment ------------------------------------
+def _logmap_se3(T):
+    """logmap_se3, numpy; x = [t; w]."""
+    R, t = T[:3, :3], T[:3, 3]
+    c = min(1.0, max(-1.0, (np.trace(R) - 1.0) / 2.0))
+    theta = math.acos(c)
+    w = np.zeros(3)
+    V = np.eye(3)
+    if theta > 1e-6:
+        sn = math.sqrt(max(0.0, 1.0 - c * c))
+        W = (R - R.T) * (theta / (2.0 * sn))
+        w = np.array([W[2, 1], W[0, 2], W[1, 0]])
+        s = np.array([[0.0, -w[2], w[1]], [w[2], 0.0, -w[0]], [-w[1], w[0], 0.0]]) / theta
+        V = np.eye(3) + s * (1.0 - c) / theta + (s @ s) * (theta - sn) / theta
+    return np.concatenate([np.linalg.solve(V, t), w])
+
+
+def lba_problem(cam, n_kf=4, n_fixed=2, n_pt=120, n_ls=40, seed=0, px_noise=0.3, pose_noise=0.01, lm_noise=0.02):
+    """A local map as MapHandler::localBundleAdjustment assembles it (src/mapHandler.cpp:1220-1330): n_kf local keyframes
+    (optimised) + n_fixed fixed ones along a forward trajectory, point and line landmarks in front of them, every landmark
+    observed by the keyframes that see it (observations grouped per landmark, as the reference builds its lists).  Poses
+    are T_kf_w (keyframe -> world) as se(3) vectors; the returned initial values are perturbed copies of the truth."""
+    rng = np.random.default_rng(seed)
+    poses = []
+    for i in range(n_kf + n_fixed):
+        x = np.array([0.05 * rng.standard_normal(), 0.02 * rng.standard_normal(), 0.8 * i, 0.01 * rng.standard_normal(),
+                      0.03 * rng.standard_normal(), 0.005 * rng.standard_normal()])
+        poses.append(expmap_se3(x))
+    fixed_T = np.stack(poses[:n_fixed]) if n_fixed else np.zeros((0, 4, 4))
+    local_T = poses[n_fixed:]
+
+    def rand_world(n):
+        z = rng.uniform(6, 40, n) + 0.8 * (n_kf + n_fixed)
+        u = rng.uniform(60, cam["width"] - 60, n); v = rng.uniform(40, cam["height"] - 40, n)
+        return np.stack([(u - cam["cx"]) * (z - 4) / cam["fx"], (v - cam["cy"]) * (z - 4) / cam["fy"], z], 1)
+
+    def view(T_kf_w, Pw):
+        Ti = np.linalg.inv(T_kf_w)
+        Pc = Pw @ Ti[:3, :3].T + Ti[:3, 3]
+        uv = np.stack([cam["cx"] + cam["fx"] * Pc[:, 0] / Pc[:, 2], cam["cy"] + cam["fy"] * Pc[:, 1] / Pc[:, 2]], 1)
+        ok = (Pc[:, 2] > 1.0) & (uv[:, 0] > 0) & (uv[:, 0] < cam["width"]) & (uv[:, 1] > 0) & (uv[:, 1] < cam["height"])
+        return uv, ok
+
+    pt = rand_world(n_pt)
+    a = rand_world(n_ls)
+    ls = np.concatenate([a, a + rng.uniform(-2.0, 2.0, (n_ls, 3)) * np.array([1.0, 0.5, 0.3])], 1)
+    all_T = [(-1 - k, fixed_T[k]) for k in range(n_fixed)] + [(k, local_T[k]) for k in range(n_kf)]
+    po_lm, po_kf, po_xy, lo_lm, lo_kf, lo_le = [], [], [], [], [], []
+    # (a landmark nobody observes would leave a zero block in the Hessian: the first keyframe always keeps its observation)
+    for j in range(n_pt):
+        for i, (kf, T) in enumerate(all_T):
+            uv, ok = view(T, pt[j:j + 1])
+            if i == 0 or (ok[0] and rng.uniform() < 0.8):
+                po_lm.append(j); po_kf.append(kf); po_xy.append(uv[0] + px_noise * rng.standard_normal(2))
+    for j in range(n_ls):
+        for i, (kf, T) in enumerate(all_T):
+            s, oks = view(T, ls[j:j + 1, :3]); e, oke = view(T, ls[j:j + 1, 3:])
+            if i == 0 or (oks[0] and oke[0] and rng.uniform() < 0.8):
+                sp = np.append(s[0] + px_noise * rng.standard_normal(2), 1.0); ep = np.append(e[0] + px_noise * rng.standard_normal(2), 1.0)
+                le = np.cross(sp, ep)
+                lo_lm.append(j); lo_kf.append(kf); lo_le.append(le / math.sqrt(le[0] * le[0] + le[1] * le[1]))
+    kf_true = np.stack([_logmap_se3(T) for T in local_T]) if n_kf else np.zeros((0, 6))
+    return dict(kf_pose=kf_true + pose_noise * rng.standard_normal(kf_true.shape), pt=pt + lm_noise * rng.standard_normal(pt.shape),
+                ls=ls + lm_noise * rng.standard_normal(ls.shape), fixed_T=fixed_T,
+                pt_obs_lm=np.array(po_lm, np.int32), pt_obs_kf=np.array(po_kf, np.int32), pt_obs_xy=np.array(po_xy).reshape(-1, 2),
+                ls_obs_lm=np.array(lo_lm, np.int32), ls_obs_kf=np.array(lo_kf, np.int32), ls_obs_le=np.array(lo_le).reshape(-1, 3),
+                truth=dict(kf_pose=kf_true, pt=pt, ls=ls))
