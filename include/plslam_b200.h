@@ -47,13 +47,16 @@ typedef struct plf_params {
   int has_points, has_lines, best_lr_matches;
   /* point tracking (config_euroc.yaml:22-25) */
   float max_dist_epip, min_disp, min_ratio_12_p;
-  /* line tracking (config_euroc.yaml:27-34) */
+  /* line tracking (config_euroc.yaml:27-34).  line_sim_th: direction gate of the windowed matcher (matching_strategy != 0
+   * and plf_match_grid_lines).  f2f_overlap_th: carried for API parity, IGNORED (stvo-pl's matchF2FLines does not gate on
+   * overlap in the version pl-slam builds against). */
   float line_sim_th, stereo_overlap_th, f2f_overlap_th, min_line_length, line_horiz_th,
       min_ratio_12_l, ls_min_disp_ratio;
   /* optimiser (config_euroc.yaml:43-51) */
   double homog_th;
   int min_features, max_iters, max_iters_ref;
-  double min_error, min_error_change, inlier_k;
+  double min_error, min_error_change, inlier_k; /* inlier_k: IGNORED - the outlier gate is the in-tree twin's chi2 threshold
+                                                   sqrt(7.815) (src/mapHandler.cpp:3460,3479), not stvo-pl's MAD-scaled inlier_k */
   /* ORB (config_euroc.yaml:59-67) */
   int orb_nfeatures;
   float orb_scale_factor;
@@ -427,7 +430,8 @@ plf_status plf_batch_download(plf_ctx* ctx, int B, plf_frame_result* out);
  * has no counterpart: app/plslam_dataset.cpp:148-154 reads curr_frame->Tfw on the host).  The batch stays in flight
  * until plf_batch_download. */
 plf_status plf_batch_device_poses(plf_ctx* ctx, int B, double* dst_device, void* stream);
-/* Device buffer [2*max_batch][h][w] read by plf_batch_run (image 2k = left k, 2k+1 = right k). */
+/* Device buffer [2*max_batch][h][pitch] read by plf_batch_run (image 2k = left k, 2k+1 = right k), pitch = width rounded up
+ * to a multiple of 16 bytes (every halo tile of every image is then a legal TMA box). */
 void* plf_batch_device_images(plf_ctx* ctx);
 
 /* Stereo-valid features of frame k of the last batch (what `new KeyFrame(StVO->curr_frame)` deep-copies,
