@@ -37,15 +37,21 @@ EUROC = dict(width=752, height=480, fx=458.654, fy=457.296, cx=367.215, cy=248.3
 CONFIGS = {
     "kitti": dict(cam=KITTI, prm=dict(orb_nfeatures=1500, lsd_nfeatures=200),
                   workload="kitti00_shape_synthetic_stream_1242x375_orb1500_lsd200_tracking", batch=1536, lbar=90,
-                  world=lambda seed: dict(seed=7 + seed), stream=lambda seed: dict(seed=42 + seed)),
+                  world=lambda seed: dict(seed=7), stream=lambda seed: dict(seed=42 + seed)),
     "euroc": dict(cam=EUROC, prm=dict(orb_nfeatures=1200, lsd_nfeatures=300, max_iters=5, max_iters_ref=10),
                   workload="euroc_mh_shape_synthetic_stream_752x480_orb1200_lsd300_full_frontend_pose_refine", batch=1536, lbar=80,
-                  world=lambda seed: dict(seed=8 + seed, length=40.0, n_quads=220, n_segs=120, half_width=5.0, half_height=3.0),
+                  world=lambda seed: dict(seed=8, length=40.0, n_quads=220, n_segs=120, half_width=5.0, half_height=3.0),
                   stream=lambda seed: dict(seed=43 + seed, step=0.08, yaw_deg=0.8)),
     "lowtex": dict(cam=KITTI, prm=dict(orb_nfeatures=150, lsd_nfeatures=0),
                    workload="low_texture_lines_dominant_synthetic_stream_1242x375_orb150_lsd_all", batch=1536, lbar=120,
                    world=None, stream=lambda seed: dict(seed=17 + seed, noise=2)),
 }
+# Sequences of different ranks (BASELINE config 4: one independent sequence per GPU) are independent TRAJECTORIES (stream seed +
+# rank: own motion, own image noise) through the SAME synthetic world.  Weak scaling wants equal work per GPU: with one world
+# per rank (the first round-2 measurement, profiles/r02_scale_n8_heterogeneous.json) the scene content made the summed kernel
+# time of a step range from 124 to 158 ms across the 8 ranks (region growing 45 .. 69 ms), and because the ranks meet at the
+# per-step pose all-gather the whole job ran at the pace of the heaviest sequence - 0.78 "efficiency" that measured the
+# scenes, not the system.
 CFG = CONFIGS["kitti"]
 CAM, PRM, WORKLOAD = CFG["cam"], CFG["prm"], CFG["workload"]
 
@@ -445,7 +451,10 @@ def main():
                                 rendered_frames=args.pool,
                                 l2="per-step working set %.0f MB (images + pyramids + LSD maps) >> 126 MB L2" % (B * 36.0 * w * h / 465750),
                                 features_per_frame=stats, tracked_fraction=tracked,
-                                exchange="device-resident pose copy (+ one NCCL all-gather when n_gpus > 1) per step, inside both timed regions"),
+                                exchange="device-resident pose copy (+ one NCCL all-gather when n_gpus > 1) per step, inside both timed regions",
+                                sequences="one independent trajectory per rank (stream seed + rank) through the same synthetic world: equal work per GPU",
+                                rank_serial_kernel_ms=[round(min(r["serial_kernel_ms"] for r in per_rank), 1),
+                                                       round(max(r["serial_kernel_ms"] for r in per_rank), 1)]),
                     e2e=dict(value=e2e_v, unit=UNIT, h2d_bytes_per_step=2 * B * w * h,
                              d2h_bytes_per_step=B * ctypes.sizeof(plf.plf_frame_result), ms_per_step=e2e_ms / args.steps),
                     gpu_launches=int(launches), clocks=clocks, roofline=roof, pipeline_vs_hbm=whole,

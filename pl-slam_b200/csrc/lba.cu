@@ -463,7 +463,8 @@ extern "C" plf_status plf_local_ba(plf_ctx* ctx, const plf_lba_opts* opts, const
   // ---- first pass on the map's values (:1352-1541), lambda *= Hmax (:1543-1550), first step applied unconditionally
   if ((st = build(0))) return st;
   double err = h_scal[0];
-  if (q) err /= (double)(0 + 0);   // (q1) :1541
+  volatile int never_incremented = 0;   // Npt_obs + Nls_obs of the reference
+  if (q) err /= (double)never_incremented;   // (q1) :1541
   else err /= (double)nobs;
   double Hmax;
   { unsigned long long bits; memcpy(&bits, &h_scal[2], 8); memcpy(&Hmax, &bits, 8); }

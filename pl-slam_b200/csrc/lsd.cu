@@ -491,7 +491,7 @@ __device__ __forceinline__ void lsd_prefetch(const void* p) { asm volatile("pref
 // inside the (now 0.05 deg) band the reference's own f64 test decides.  The float sums S_i are accumulated in the
 // reference's order either way, so every accepted/rejected decision - and the final angle - is the reference's.
 #define LSD_MARGIN0 0.05f
-__global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
+__device__ __forceinline__ void lsd_grow_body(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
                                                  const uint32_t* __restrict__ order_all,
                                                  const int* __restrict__ nseeds, double prec, float prec_deg,
                                                  int min_reg_size, uint32_t* __restrict__ regpts_all,
@@ -658,6 +658,16 @@ __global__ void __launch_bounds__(32) k_lsd_grow(LsdPix* __restrict__ pix_all, s
   }
   if (lane == 0) nregions[im] = nreg_out;
 }
+
+#define LSD_GROW_ARGS LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W, const uint32_t* __restrict__ order_all, \
+    const int* __restrict__ nseeds, double prec, float prec_deg, int min_reg_size, uint32_t* __restrict__ regpts_all,              \
+    uint4* __restrict__ regions_all, int max_regions, int* __restrict__ nregions, int* __restrict__ overflow
+#define LSD_GROW_PASS pix_all, pix_stride, stride, W, order_all, nseeds, prec, prec_deg, min_reg_size, regpts_all, regions_all, max_regions, nregions, overflow
+__global__ void __launch_bounds__(32) k_lsd_grow(LSD_GROW_ARGS) { lsd_grow_body(LSD_GROW_PASS); }
+// register-capped variants (PLF_GROW_CFG = 40 / 48): the kernel is resident for tens of milliseconds with one warp per image,
+// and what it leaves of the register file is what the co-scheduled tile kernels get
+__global__ void __maxnreg__(40) k_lsd_grow_r40(LSD_GROW_ARGS) { lsd_grow_body(LSD_GROW_PASS); }
+__global__ void __maxnreg__(48) k_lsd_grow_r48(LSD_GROW_ARGS) { lsd_grow_body(LSD_GROW_PASS); }
 
 // ---- region growing, LANE per image with helper lanes ("grow_s") ---------------------------------------------------
 // The warp-per-image kernel above spends ~116 warp instructions per region point, a quarter of them cross-lane (VOTE /
@@ -1315,6 +1325,14 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
     case 2: GROW_S(2); break;
     case 3: GROW_S(3); break;
     case 4: GROW_S(4); break;
+    case 40:
+      k_lsd_grow_r40<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
+                                       regions, s->max_regions, nregions, s->overflow);
+      break;
+    case 48:
+      k_lsd_grow_r48<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
+                                       regions, s->max_regions, nregions, s->overflow);
+      break;
     default:
       k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
                                    regions, s->max_regions, nregions, s->overflow);
@@ -1455,4 +1473,6 @@ extern "C" plf_status plf_debug_sincosf(plf_ctx* ctx, const float* in, float* s,
 // the overlapped batch 28 ms -> 7 ms, step 83.3 -> 81.9 ms.
 void plf_configure_lsd() {
   cudaFuncSetAttribute((const void*)k_lsd_grow, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
+  cudaFuncSetAttribute((const void*)k_lsd_grow_r40, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
+  cudaFuncSetAttribute((const void*)k_lsd_grow_r48, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
 }
