@@ -915,28 +915,52 @@ __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gx
   const short2* gxy = gxy_all + (size_t)im * stride;
   const int n = (int)R.y;
   const double reg_angle = __longlong_as_double((long long)(((unsigned long long)R.w << 32) | R.z));
+  // The sums run in the region's point order (bit-exact with the CPU loop); what is batched is the LOADS: the point
+  // indices and the gradients of 8 points are fetched before their terms are added, so the dependent pts[k] -> gxy[p]
+  // round trips overlap instead of serialising (the thread is otherwise one L2 / DRAM latency per point).
+  constexpr int PF = 8;
   double x = 0, y = 0, sum = 0;
-  for (int k = 0; k < n; ++k) {
-    const uint32_t p = pts[k];
-    const int py = (int)(p / (uint32_t)W), px = (int)p - py * W;
-    const short2 g = gxy[p];
-    const double wgt = sqrt((double)(g.x * g.x + g.y * g.y) / 4.0);
-    x += (double)px * wgt;
-    y += (double)py * wgt;
-    sum += wgt;
+  for (int k0 = 0; k0 < n; k0 += PF) {
+    uint32_t pp[PF];
+    short2 gg[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) pp[j] = k0 + j < n ? pts[k0 + j] : 0u;
+#pragma unroll
+    for (int j = 0; j < PF; ++j) gg[j] = k0 + j < n ? gxy[pp[j]] : make_short2(0, 0);
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      if (k0 + j < n) {
+        const uint32_t p = pp[j];
+        const int py = (int)(p / (uint32_t)W), px = (int)p - py * W;
+        const double wgt = sqrt((double)(gg[j].x * gg[j].x + gg[j].y * gg[j].y) / 4.0);
+        x += (double)px * wgt;
+        y += (double)py * wgt;
+        sum += wgt;
+      }
+    }
   }
   x /= sum;
   y /= sum;
   double Ixx = 0, Iyy = 0, Ixy = 0;
-  for (int k = 0; k < n; ++k) {
-    const uint32_t p = pts[k];
-    const int py = (int)(p / (uint32_t)W), px = (int)p - py * W;
-    const short2 g = gxy[p];
-    const double wgt = sqrt((double)(g.x * g.x + g.y * g.y) / 4.0);
-    const double dx = (double)px - x, dy = (double)py - y;
-    Ixx += dy * dy * wgt;
-    Iyy += dx * dx * wgt;
-    Ixy -= dx * dy * wgt;
+  for (int k0 = 0; k0 < n; k0 += PF) {
+    uint32_t pp[PF];
+    short2 gg[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) pp[j] = k0 + j < n ? pts[k0 + j] : 0u;
+#pragma unroll
+    for (int j = 0; j < PF; ++j) gg[j] = k0 + j < n ? gxy[pp[j]] : make_short2(0, 0);
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      if (k0 + j < n) {
+        const uint32_t p = pp[j];
+        const int py = (int)(p / (uint32_t)W), px = (int)p - py * W;
+        const double wgt = sqrt((double)(gg[j].x * gg[j].x + gg[j].y * gg[j].y) / 4.0);
+        const double dx = (double)px - x, dy = (double)py - y;
+        Ixx += dy * dy * wgt;
+        Iyy += dx * dx * wgt;
+        Ixy -= dx * dy * wgt;
+      }
+    }
   }
   const double lambda = 0.5 * (Ixx + Iyy - sqrt((Ixx - Iyy) * (Ixx - Iyy) + 4.0 * Ixy * Ixy));
   double theta = (fabs(Ixx) > fabs(Iyy)) ? (double)lsd_fast_atan2((float)(lambda - Ixx), (float)Ixy)
@@ -945,13 +969,21 @@ __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gx
   if (lsd_angle_diff(theta, reg_angle) > prec) theta += LSD_PI;
   const double dx = cos(theta), dy = sin(theta);
   double l_min = 0, l_max = 0;
-  for (int k = 0; k < n; ++k) {
-    const uint32_t p = pts[k];
-    const int py = (int)(p / (uint32_t)W), px = (int)p - py * W;
-    const double regdx = (double)px - x, regdy = (double)py - y;
-    const double l = regdx * dx + regdy * dy;
-    if (l > l_max) l_max = l;
-    else if (l < l_min) l_min = l;
+  for (int k0 = 0; k0 < n; k0 += PF) {
+    uint32_t pp[PF];
+#pragma unroll
+    for (int j = 0; j < PF; ++j) pp[j] = k0 + j < n ? pts[k0 + j] : 0u;
+#pragma unroll
+    for (int j = 0; j < PF; ++j) {
+      if (k0 + j < n) {
+        const uint32_t p = pp[j];
+        const int py = (int)(p / (uint32_t)W), px = (int)p - py * W;
+        const double regdx = (double)px - x, regdy = (double)py - y;
+        const double l = regdx * dx + regdy * dy;
+        if (l > l_max) l_max = l;
+        else if (l < l_min) l_min = l;
+      }
+    }
   }
   double x1 = x + l_min * dx, y1 = y + l_min * dy, x2 = x + l_max * dx, y2 = y + l_max * dy;
   x1 += 0.5; y1 += 0.5; x2 += 0.5; y2 += 0.5;
