@@ -492,7 +492,7 @@ __device__ __forceinline__ void lsd_prefetch(const void* p) { asm volatile("pref
 // reference's order either way, so every accepted/rejected decision - and the final angle - is the reference's.
 #define LSD_MARGIN0 0.05f
 __device__ __forceinline__ void lsd_grow_body(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
-                                                 const uint32_t* __restrict__ order_all,
+                                                 const uint32_t* __restrict__ order_all, const float2* __restrict__ lut_seed,
                                                  const int* __restrict__ nseeds, double prec, float prec_deg,
                                                  int min_reg_size, uint32_t* __restrict__ regpts_all,
                                                  uint4* __restrict__ regions_all, int max_regions,
@@ -528,7 +528,12 @@ __device__ __forceinline__ void lsd_grow_body(LsdPix* __restrict__ pix_all, size
   for (int s0 = 0; s0 < ns; s0 += 32) {
     const int si = s0 + lane;
     const uint32_t seed = seed_next;
-    float a0 = si < ns ? __ldcg(&pix[seed].a) : LSD_NOTDEF_F;
+    // angle + index of the seed's gradient in the (gx,gy) tables: the region's sums start from lut_seed[li] =
+    // (float(cos(double angle)), float(sin(double angle))) - tabulated once per context with the very expressions this
+    // kernel used to evaluate per region (130 f64 instructions at 10 k region starts per frame: 15 % of the kernel)
+    const uint2 ali = si < ns ? __ldcg(reinterpret_cast<const uint2*>(&pix[seed])) : make_uint2(__float_as_uint(LSD_NOTDEF_F), 0u);
+    float a0 = __uint_as_float(ali.x);
+    const uint32_t seed_li = ali.y;
     seed_next = si + 32 < ns ? order[si + 32] : 0u;   // next group of seeds: index now, record into L2 while this group runs
     if (si + 32 < ns) asm volatile("prefetch.global.L2 [%0];" ::"l"(&pix[seed_next]));
     unsigned pending = __ballot_sync(0xFFFFFFFFu, a0 != LSD_NOTDEF_F);
@@ -537,7 +542,8 @@ __device__ __forceinline__ void lsd_grow_body(LsdPix* __restrict__ pix_all, size
       const uint32_t sidx = __shfl_sync(0xFFFFFFFFu, seed, src);
       float th = __shfl_sync(0xFFFFFFFFu, a0, src);      // region angle (degrees) at the last evaluation
       const double th_seed = (double)th * LSD_DEG2RAD;    // the reference's f64 angle of the seed
-      float sumdx = (float)cos(th_seed), sumdy = (float)sin(th_seed);
+      const float2 sv = __ldg(&lut_seed[__shfl_sync(0xFFFFFFFFu, seed_li, src)]);
+      float sumdx = sv.x, sumdy = sv.y;                   // = (float)cos(th_seed), (float)sin(th_seed)
       float margin = margin0, inv0 = 1.02f;               // m_i and an upper bound of 1/|S_0|
       float lo = prec_deg - margin, hi = prec_deg + margin;
       bool fresh = true;                                  // th is the reference's current angle
@@ -660,9 +666,9 @@ __device__ __forceinline__ void lsd_grow_body(LsdPix* __restrict__ pix_all, size
 }
 
 #define LSD_GROW_ARGS LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W, const uint32_t* __restrict__ order_all, \
-    const int* __restrict__ nseeds, double prec, float prec_deg, int min_reg_size, uint32_t* __restrict__ regpts_all,              \
+    const float2* __restrict__ lut_seed, const int* __restrict__ nseeds, double prec, float prec_deg, int min_reg_size, uint32_t* __restrict__ regpts_all,              \
     uint4* __restrict__ regions_all, int max_regions, int* __restrict__ nregions, int* __restrict__ overflow
-#define LSD_GROW_PASS pix_all, pix_stride, stride, W, order_all, nseeds, prec, prec_deg, min_reg_size, regpts_all, regions_all, max_regions, nregions, overflow
+#define LSD_GROW_PASS pix_all, pix_stride, stride, W, order_all, lut_seed, nseeds, prec, prec_deg, min_reg_size, regpts_all, regions_all, max_regions, nregions, overflow
 __global__ void __launch_bounds__(32) k_lsd_grow(LSD_GROW_ARGS) { lsd_grow_body(LSD_GROW_PASS); }
 // register-capped variants (PLF_GROW_CFG = 40 / 48): the kernel is resident for tens of milliseconds with one warp per image,
 // and what it leaves of the register file is what the co-scheduled tile kernels get
@@ -1358,15 +1364,15 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
     case 3: GROW_S(3); break;
     case 4: GROW_S(4); break;
     case 40:
-      k_lsd_grow_r40<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
+      k_lsd_grow_r40<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, s->seed_lut, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
                                        regions, s->max_regions, nregions, s->overflow);
       break;
     case 48:
-      k_lsd_grow_r48<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
+      k_lsd_grow_r48<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, s->seed_lut, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
                                        regions, s->max_regions, nregions, s->overflow);
       break;
     default:
-      k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
+      k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, s->seed_lut, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
                                    regions, s->max_regions, nregions, s->overflow);
       break;
   }
