@@ -103,6 +103,21 @@ def test_bench_configuration_large_batches_in_flight(built):
         T = T @ g["DT"]
     T_true = np.linalg.inv(frames[0][2]) @ frames[-1][2]
     assert np.linalg.norm(T[:3, 3] - T_true[:3, 3]) < 0.05 * np.linalg.norm(T_true[:3, 3])
+    # north-star: trajectory ATE within 1 % of the reference path's on the same sequence.  Absolute trajectory error (RMSE
+    # of the positions of the chained poses against the planted trajectory, first frames aligned) of the GPU and of the
+    # oracle trajectory, and the RMSE between the two trajectories themselves.
+    def positions(dts):
+        Tc, out = np.eye(4), []
+        for D in dts:
+            Tc = Tc @ D
+            out.append(Tc[:3, 3].copy())
+        return np.array(out)
+    p_gpu, p_ref = positions([g["DT"] for g in got]), positions([r["DT"] for r in ref])
+    T0i = np.linalg.inv(frames[0][2])
+    p_gt = np.array([(T0i @ f[2])[:3, 3] for f in frames])
+    ate_gpu = np.sqrt(np.mean(np.sum((p_gpu - p_gt) ** 2, 1))); ate_ref = np.sqrt(np.mean(np.sum((p_ref - p_gt) ** 2, 1)))
+    assert abs(ate_gpu - ate_ref) <= 0.01 * ate_ref
+    assert np.sqrt(np.mean(np.sum((p_gpu - p_ref) ** 2, 1))) <= 1e-4 * np.linalg.norm(p_gt[-1])
 
 
 def test_euroc_shape_32_frames_in_flight(built):
