@@ -11,11 +11,11 @@
 // inside a bin) -> greedy region growing -> rectangle fit.  No NFA validation runs at refine 0.
 //
 // Kernels
-//   k_blur_q8_fast   separable Q8.8 Gaussian (word-staged tile in shared memory, DP4A row pass), one rounding
+//   k_blur_q8_fast   separable Q8.8 Gaussian (tile + halo staged by one TMA bulk-tensor copy, DP4A row pass), one rounding
 //                    (k_blur_q8: generic variant for tiny images)
 //   k_resize_exact4  (orb.cu) INTER_LINEAR_EXACT resample to scale
-//   k_lsd_grad       2x2 gradient -> (gx,gy) int16 pair + the 16-byte record {angle (cv::fastAtan2, degrees, f32),
-//                    cosf, sinf} fetched from a table keyed by (gx,gy); per-image max of |grad|^2
+//   k_lsd_grad       2x2 gradient -> (gx,gy) int16 pair + the 16-byte record {angle (cv::fastAtan2, degrees, f32), table
+//                    index, cosf, sinf} fetched from a table keyed by (gx,gy); per-image max of |grad|^2
 //   k_lsd_rowhist / k_lsd_binscan / k_lsd_scatter
 //                    stable counting sort of the defined pixels by magnitude bin (descending), raster order inside a
 //                    bin == OpenCV's ordered_points
@@ -670,210 +670,6 @@ __device__ __forceinline__ void lsd_grow_body(LsdPix* __restrict__ pix_all, size
     uint4* __restrict__ regions_all, int max_regions, int* __restrict__ nregions, int* __restrict__ overflow
 #define LSD_GROW_PASS pix_all, pix_stride, stride, W, order_all, lut_seed, nseeds, prec, prec_deg, min_reg_size, regpts_all, regions_all, max_regions, nregions, overflow
 __global__ void __launch_bounds__(32) k_lsd_grow(LSD_GROW_ARGS) { lsd_grow_body(LSD_GROW_PASS); }
-// register-capped variants (PLF_GROW_CFG = 40 / 48): the kernel is resident for tens of milliseconds with one warp per image,
-// and what it leaves of the register file is what the co-scheduled tile kernels get
-__global__ void __maxnreg__(40) k_lsd_grow_r40(LSD_GROW_ARGS) { lsd_grow_body(LSD_GROW_PASS); }
-__global__ void __maxnreg__(48) k_lsd_grow_r48(LSD_GROW_ARGS) { lsd_grow_body(LSD_GROW_PASS); }
-
-// ---- region growing, LANE per image with helper lanes ("grow_s") ---------------------------------------------------
-// The warp-per-image kernel above spends ~116 warp instructions per region point, a quarter of them cross-lane (VOTE /
-// SHFL on the dependent chain): ~1000 cycles per point, 82.6 k points per KITTI frame, and at 3072 images it also holds
-// half of the SMs' issue slots.  Here ONE LANE grows one image with the whole decision chain in its own registers (8
-// neighbour records, the reference's row-major order as straight-line code, the same deferred-angle bounds - identical
-// arithmetic, identical decisions), LG images per warp.  The lanes stay in lockstep: every iteration of the main loop
-// is  [scan step, if some grower needs its next seed]  ->  [one region point per grower]  ->  [look-ahead prefetch],
-// with the warp converged between the parts.  The other lanes are HELPERS, 7 per grower (lanes 7g..7g+6):
-//   * seed scan: the 7 lanes examine 7 consecutive seeds of the grower's order list at once (ballot + first-hit), and
-//     keep the records of the seeds two steps ahead and the order list itself flowing into L1;
-//   * look-ahead: after every step the 7 lanes prefetch a 7-row x 4-sector window around each pixel that joined the
-//     grower's region (the cells the next two breadth-first layers will examine), one row per lane - the grower's own
-//     loads are then L1 hits.
-// No f64 trigonometry in the loop: the seed's unit vector (float(cos(double angle)), as the reference forms it) comes from
-// a second table keyed by the gradient (lut_seed, index carried in the record), fetched when the region starts.
-#define LSD_SQCAP 256
-__device__ __noinline__ float lsd_region_angle(float sumdy, float sumdx) { return lsd_fast_atan2(sumdy, sumdx); }
-__device__ __noinline__ bool lsd_aligned_exact(float a_deg, float th_deg, double prec) {
-  return lsd_aligned_rad((double)a_deg * LSD_DEG2RAD, (double)th_deg * LSD_DEG2RAD, prec);
-}
-// distance between two level-line angles in degrees, as the reference folds it (d > 180 -> 360 - d).  NOTDEF (-1024) on
-// either side lands far above any threshold without a separate test: |a - th| >= 664 and |360 - |a - th|| >= 304.
-__device__ __forceinline__ float lsd_dist_deg(float a, float th) {
-  const float d = fabsf(__fsub_rn(a, th));
-  return fminf(d, fabsf(__fsub_rn(360.f, d)));
-}
-
-template <int LG>
-__global__ void __launch_bounds__(32) k_lsd_grow_s(LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
-                                                   const uint32_t* __restrict__ order_all, const int* __restrict__ nseeds,
-                                                   int nimg, const float2* __restrict__ lut_seed, double prec,
-                                                   float prec_deg, int min_reg_size, uint32_t* __restrict__ regpts_all,
-                                                   uint4* __restrict__ regions_all, int max_regions,
-                                                   int* __restrict__ nregions, int* __restrict__ overflow) {
-  __shared__ uint32_t q_all[LG][LSD_SQCAP];
-  const unsigned FULL = 0xFFFFFFFFu;
-  const int lane = threadIdx.x;
-  const bool grower = lane < LG;
-  // ---- this lane as a grower: image blockIdx.x * LG + lane
-  const int im_raw = blockIdx.x * LG + lane;
-  const bool gvalid = grower && im_raw < nimg;
-  const int im = gvalid ? im_raw : 0;
-  LsdPix* const pix = pix_all + (size_t)im * pix_stride;
-  char* const pb = reinterpret_cast<char*>(pix);
-  uint32_t* const regpts = regpts_all + (size_t)im * stride;
-  uint4* const regions = regions_all + (size_t)im * max_regions;
-  uint32_t* const q = q_all[grower ? lane : 0];
-  const int ns = gvalid ? nseeds[im] : 0;
-  // ---- this lane as a helper of group hg = lane / 7 (row hj - 3 of the look-ahead window, seed hj of the scan group)
-  const int hg = lane / 7, hj = lane - 7 * hg;
-  const bool helper = lane < 28 && hg < LG && blockIdx.x * LG + hg < nimg;
-  const int him = helper ? blockIdx.x * LG + hg : 0;
-  const char* const hpb = reinterpret_cast<const char*>(pix_all + (size_t)him * pix_stride);
-  const uint32_t* const horder = order_all + (size_t)him * stride;
-  const int hns = helper ? nseeds[him] : 0;
-  const uint32_t* const hq = q_all[helper ? hg : 0];
-  const int hrow = (hj - 3) * W - 3;   // first record of this helper's window row, relative to the centre pixel
-
-  const int noff[8] = {-W - 1, -W, -W + 1, -1, 1, W - 1, W, W + 1};  // the reference's row-major 3x3 order, centre skipped
-  const float margin0 = prec_deg <= 60.f ? LSD_MARGIN0 : 1e30f;   // ang_th near 90 deg: evaluate every angle (see k_lsd_grow)
-  const float dmax = prec_deg + LSD_MARGIN0;
-  enum { SCAN = 0, GROW = 1, DONE = 2 };
-  int mode = gvalid && ns > 0 ? SCAN : DONE;
-  int spos = 0;                 // next position of the seed order to examine
-  uint32_t cursor = 0;          // first free entry of regpts
-  int nreg_out = 0;
-  uint32_t r = 0, nreg = 0;
-  float th = 0.f, a_seed = 0.f, sumdx = 0.f, sumdy = 0.f, margin = 0.f, inv0 = 1.02f, lo = 0.f, hi = 0.f;
-  bool fresh = true;
-
-  for (;;) {
-    const unsigned live = __ballot_sync(FULL, mode != DONE);
-    if (!live) break;
-    // ---------------- seed scan (whole warp, for the groups whose grower is between regions) ----------------
-    if (__ballot_sync(FULL, mode == SCAN)) {
-      const int g_spos = __shfl_sync(FULL, spos, hg & 3);
-      const int g_mode = __shfl_sync(FULL, mode, hg & 3);
-      const bool act = helper && g_mode == SCAN;
-      const int pos = g_spos + hj;
-      uint32_t sidx = 0;
-      float a = LSD_NOTDEF_F;
-      if (act && pos < hns) {
-        sidx = __ldg(&horder[pos]);
-        a = __ldca(reinterpret_cast<const float*>(hpb + (size_t)sidx * 16));
-        if (pos + 14 < hns) lsd_prefetch(hpb + (size_t)__ldg(&horder[pos + 14]) * 16);   // record of the seed two steps ahead
-        if (hj == 0 && pos + 64 < hns) lsd_prefetch(&horder[pos + 64]);                    // the order list itself
-      }
-      const unsigned hits = __ballot_sync(FULL, a != LSD_NOTDEF_F);
-      int src = 0;
-      bool start = false;
-      if (grower && mode == SCAN) {
-        const unsigned f = (hits >> (7 * lane)) & 0x7Fu;
-        if (f) {
-          const int jj = __ffs(f) - 1;
-          src = 7 * lane + jj;
-          spos += jj + 1;
-          start = true;
-        } else {
-          spos += 7;
-          if (spos >= ns) mode = DONE;
-        }
-      }
-      const uint32_t s_sidx = __shfl_sync(FULL, sidx, src);
-      const float s_a = __shfl_sync(FULL, a, src);
-      if (start) {  // region_grow: the seed
-        const uint32_t li = __ldca(reinterpret_cast<const uint32_t*>(pb + (size_t)s_sidx * 16 + 4));
-        const float2 sv = __ldg(&lut_seed[li]);     // float(cos(double angle)), float(sin(double angle))
-        *reinterpret_cast<float*>(pb + (size_t)s_sidx * 16) = LSD_NOTDEF_F;
-        regpts[cursor] = s_sidx;
-        q[0] = s_sidx;
-        r = 0; nreg = 1;
-        th = s_a; a_seed = s_a;
-        sumdx = sv.x; sumdy = sv.y;
-        margin = margin0; inv0 = 1.02f;
-        lo = prec_deg - margin; hi = prec_deg + margin;
-        fresh = true;
-        mode = GROW;
-      }
-      // look-ahead window of the new seeds, by the helpers of their groups
-      const uint32_t st = __shfl_sync(FULL, start ? s_sidx : 0xFFFFFFFFu, hg & 3);
-      if (helper && st != 0xFFFFFFFFu) {
-        const char* p = hpb + ((long long)(int)st + hrow) * 16;
-        lsd_prefetch(p); lsd_prefetch(p + 32); lsd_prefetch(p + 64); lsd_prefetch(p + 96);
-      }
-    }
-    // ---------------- one region point per grower: its 3x3 neighbourhood in the reference's order ----------------
-    const uint32_t nreg0 = nreg;
-    if (mode == GROW) {
-      const uint32_t pt = (nreg - r <= LSD_SQCAP) ? q[r & (LSD_SQCAP - 1)] : __ldcg(&regpts[cursor + r]);
-      float4 rec[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) rec[k] = __ldca(reinterpret_cast<const float4*>(pb + (long long)((int)pt + noff[k]) * 16));
-      float d8[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) d8[k] = lsd_dist_deg(rec[k].x, th);
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        if (d8[k] <= hi) {              // aligned or undecided (clearly not aligned, used and undefined cells fall through)
-          bool acc = d8[k] < lo;        // certainly aligned whatever the exact region angle is
-          if (!acc) {                   // inside the band: the decision needs the exact angle
-            if (!fresh) {
-              th = lsd_region_angle(sumdy, sumdx);
-              inv0 = __fmul_rn(rsqrtf(__fadd_rn(__fmul_rn(sumdx, sumdx), __fmul_rn(sumdy, sumdy))), 1.02f);
-              margin = margin0;
-              lo = prec_deg - margin; hi = prec_deg + margin;
-              fresh = true;
-#pragma unroll
-              for (int kk = k; kk < 8; ++kk) d8[kk] = lsd_dist_deg(rec[kk].x, th);
-            }
-            if (d8[k] <= hi) acc = d8[k] < lo || lsd_aligned_exact(rec[k].x, th, prec);
-          }
-          if (acc) {  // mark used, append to the region / the queue, update the running sums and the bound
-            const int ai = (int)pt + noff[k];
-            *reinterpret_cast<float*>(pb + (long long)ai * 16) = LSD_NOTDEF_F;
-            regpts[cursor + nreg] = (uint32_t)ai;
-            q[nreg & (LSD_SQCAP - 1)] = (uint32_t)ai;
-            ++nreg;
-            sumdx = __fadd_rn(sumdx, rec[k].z);
-            sumdy = __fadd_rn(sumdy, rec[k].w);
-            margin = __fmaf_rn(fminf(__fadd_rn(d8[k], margin), dmax), inv0, margin);
-            lo = prec_deg - margin; hi = prec_deg + margin;
-            fresh = false;
-          }
-        }
-      }
-      if (++r == nreg) {  // region complete
-        if ((int)nreg >= min_reg_size) {
-          if (nreg_out < max_regions) {
-            // nreg >= min_reg_size > 1: the angle of the sum (the seed's own angle only matters for 1-pixel regions)
-            const float ang = nreg == 1 ? a_seed : (fresh ? th : lsd_region_angle(sumdy, sumdx));
-            const unsigned long long bits = (unsigned long long)__double_as_longlong((double)ang * LSD_DEG2RAD);
-            regions[nreg_out] = make_uint4(cursor, nreg, (uint32_t)bits, (uint32_t)(bits >> 32));
-            ++nreg_out;
-            cursor += nreg;
-          } else {
-            *overflow = 1;
-          }
-        }
-        mode = spos < ns ? SCAN : DONE;
-      }
-    }
-    __syncwarp(FULL);
-    // ---------------- look-ahead for the pixels that joined, by the helpers ----------------
-    {
-      const int cnt = (int)(nreg - nreg0);   // 0 for helpers-only lanes and for growers that did not grow
-      const int g_cnt = __shfl_sync(FULL, cnt, hg & 3);
-      const uint32_t g_n0 = __shfl_sync(FULL, nreg0, hg & 3);
-      const int maxc = __reduce_max_sync(FULL, helper ? g_cnt : 0);
-      for (int j = 0; j < maxc; ++j) {
-        if (helper && j < g_cnt) {
-          const uint32_t ai = hq[(g_n0 + j) & (LSD_SQCAP - 1)];
-          const char* p = hpb + ((long long)(int)ai + hrow) * 16;
-          lsd_prefetch(p); lsd_prefetch(p + 32); lsd_prefetch(p + 64); lsd_prefetch(p + 96);
-        }
-      }
-    }
-  }
-  if (gvalid) nregions[im] = nreg_out;
-}
 
 // ---- rectangle fit -------------------------------------------------------------------------------------------
 __device__ __forceinline__ double lsd_angle_diff(double a, double b) {
@@ -1349,34 +1145,10 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   plf_keyline* kls = s->kls[par] + o * s->max_lines;
   plf_keyline* kls_all = s->kls_all[par] + o * s->max_regions;
   int* nlines = s->nlines[par] + o;
-  // PLF_GROW_CFG: 0 = the warp-per-image kernel, 1..4 = k_lsd_grow_s with that many images per warp (A/B measurements).
-  static const int grow_mode = [] {
-    const char* c = getenv("PLF_GROW_CFG");
-    return c ? atoi(c) : 0;
-  }();
-#define GROW_S(L)                                                                                                        \
-  k_lsd_grow_s<L><<<(n + L - 1) / L, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, nseeds, n, s->seed_lut, s->prec,     \
-                                                  (float)(s->p * 180.0), s->min_reg_size, regpts, regions,               \
-                                                  s->max_regions, nregions, s->overflow)
-  switch (grow_mode) {
-    case 1: GROW_S(1); break;
-    case 2: GROW_S(2); break;
-    case 3: GROW_S(3); break;
-    case 4: GROW_S(4); break;
-    case 40:
-      k_lsd_grow_r40<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, s->seed_lut, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
-                                       regions, s->max_regions, nregions, s->overflow);
-      break;
-    case 48:
-      k_lsd_grow_r48<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, s->seed_lut, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
-                                       regions, s->max_regions, nregions, s->overflow);
-      break;
-    default:
-      k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, s->seed_lut, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
-                                   regions, s->max_regions, nregions, s->overflow);
-      break;
-  }
-#undef GROW_S
+  // (round-2 experiments - thread / lane per image, register-capped and unrolled variants, an angle-map layout - were all
+  // bit-exact and slower; their measurements are under profiles/, DESIGN.md section 5 has the table)
+  k_lsd_grow<<<n, 32, 0, cs>>>(pix, s->pix_stride, As, W, order, s->seed_lut, nseeds, s->prec, (float)(s->p * 180.0), s->min_reg_size, regpts,
+                               regions, s->max_regions, nregions, s->overflow);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grow");
   uint32_t* perm = s->rect_perm + o * s->max_regions;
@@ -1511,6 +1283,4 @@ extern "C" plf_status plf_debug_sincosf(plf_ctx* ctx, const float* in, float* s,
 // the overlapped batch 28 ms -> 7 ms, step 83.3 -> 81.9 ms.
 void plf_configure_lsd() {
   cudaFuncSetAttribute((const void*)k_lsd_grow, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
-  cudaFuncSetAttribute((const void*)k_lsd_grow_r40, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
-  cudaFuncSetAttribute((const void*)k_lsd_grow_r48, cudaFuncAttributePreferredSharedMemoryCarveout, 72);
 }

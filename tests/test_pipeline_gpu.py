@@ -202,3 +202,35 @@ def test_trajectory_ate_vs_oracle_and_ground_truth(built):
     assert abs(ate_gpu - ate_ref) <= 0.01 * max(ate_ref, 1e-9)          # within 1 % of the reference's ATE
     assert np.max(np.linalg.norm(p_gpu - p_ref, axis=1)) < 1e-6          # in fact the trajectories coincide
     assert ate_gpu < 0.02 * np.linalg.norm(p_gt[-1])                     # and both follow the planted trajectory
+
+
+def test_lsd_maps_per_batch_parity(built, monkeypatch):
+    """PLF_LSD_PARITIES=2: the LSD hand-off maps exist per batch parity and the pre-grow chain runs on its own stream
+    (pre-grow of batch i+1 under the growing of batch i).  Same results as the default single-copy pipeline, sequentially
+    and with three batches in flight."""
+    cam = dict(plf.KITTI_CAMERA, width=640, height=360, cx=320.0, cy=180.0, fx=500.0, fy=500.0)
+    world = synth.World(seed=4, length=50.0, n_quads=160, n_segs=80, half_width=8.0, half_height=3.5)
+    frames = list(synth.stream(cam, 8, world=world, seed=21, step=0.12))
+    Ls, Rs = np.stack([f[0] for f in frames]), np.stack([f[1] for f in frames])
+
+    def run(in_flight):
+        lim = plf.default_limits(); lim.max_batch = 2
+        out = []
+        with plf.Frontend(camera=cam, limits=lim, orb_nfeatures=700, lsd_nfeatures=150) as fe:
+            pend = 0
+            for s0 in range(0, 8, 2):
+                fe.batch_upload(Ls[s0:s0 + 2], Rs[s0:s0 + 2]); fe.batch_run(2); pend += 1
+                if pend == in_flight:
+                    out += list(fe.batch_download_array(2)); pend -= 1
+            while pend:
+                out += list(fe.batch_download_array(2)); pend -= 1
+        return out
+    monkeypatch.delenv("PLF_LSD_PARITIES", raising=False)
+    base = run(1)
+    monkeypatch.setenv("PLF_LSD_PARITIES", "2")
+    for depth in (1, 3):
+        got = run(depth)
+        for a, b in zip(base, got):
+            for f in plf.RESULT_FIELDS:
+                assert a[f] == b[f], f
+            assert np.array_equal(a["DT"], b["DT"])
