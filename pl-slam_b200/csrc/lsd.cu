@@ -267,12 +267,16 @@ __global__ void __launch_bounds__(256) k_lsd_build_lut(double rho, LsdPix* __res
   lut_seed[i] = sv;
 }
 
-__global__ void k_lsd_fill_guard(LsdPix* __restrict__ pix, size_t pix_stride, int guard, int nimg) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= guard * nimg) return;
+// Every record of the map (guards included) starts as "undefined".  From then on the map returns to that state by itself:
+// the growing kernel visits every defined pixel - as a seed or as a member of a region - and marks it used (= NOTDEF), so
+// when a batch's region growing has finished, all records of its images read NOTDEF again.  The gradient kernel therefore
+// writes records for the DEFINED pixels only (~12 % of them): 6.5 instead of 13.4 MB of DRAM writes per image.
+__global__ void k_lsd_fill_notdef(LsdPix* __restrict__ pix, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
   LsdPix e;
   e.a = LSD_NOTDEF_F; e.c = 0.f; e.s = 0.f; e.li = 0u;
-  pix[(size_t)(i / guard) * pix_stride + (i % guard)] = e;
+  pix[i] = e;
 }
 
 // pix points at pixel (0,0) of image 0 (i.e. past the guard); image stride pix_stride.
@@ -311,7 +315,7 @@ __global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ im
       if (y0 + r < H) {
         const size_t oi = (size_t)(y0 + r) * W + x;
         gxy[(size_t)im * stride + oi] = g[r];
-        *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + oi]) = e[r];
+        if (li[r] >= 0) *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + oi]) = e[r];   // undefined pixels already read NOTDEF (see k_lsd_fill_notdef)
       }
   }
   // per-image maximum: reduce in the CTA first, and only touch the (single, contended) address when it would grow
@@ -1018,7 +1022,10 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
     const size_t pad = 3 * (size_t)s->ws + 8;
     PLF_CUDA(ctx, cudaMalloc(&s->pix_raw[p], (s->pix_stride * N + 2 * pad) * sizeof(LsdPix)));
     s->pix[p] = s->pix_raw[p] + pad;
-    k_lsd_fill_guard<<<(int)(((size_t)(s->ws + 1) * N + 255) / 256), 256, 0, ctx->stream>>>(s->pix[p], s->pix_stride, s->ws + 1, (int)N);
+    {
+      const size_t nrec = s->pix_stride * N + 2 * pad;
+      k_lsd_fill_notdef<<<(unsigned)((nrec + 255) / 256), 256, 0, ctx->stream>>>(s->pix_raw[p], nrec);
+    }
     PLF_LAUNCH_CHECK(ctx);
     PLF_CUDA(ctx, cudaMalloc(&s->nseeds[p], N * sizeof(int)));
     PLF_CUDA(ctx, cudaMalloc(&s->order[p], As * N * sizeof(uint32_t)));
