@@ -70,7 +70,9 @@ struct LsdState {
   struct LsdPix* pix[2] = {nullptr, nullptr};  // [nimg][guard + hs*ws]  {angle (deg, f32) | NOTDEF = undefined/used, cosf, sinf, pad}
   size_t pix_stride = 0;      // entries per image = guard (ws+1, permanently NOTDEF) + hs*ws
   int m2_min = 0;             // smallest gx^2+gy^2 whose gradient norm exceeds rho (defined pixel)
-  uint16_t* binmap = nullptr; // [nimg][hs*ws]
+  uint16_t* binmap = nullptr; // [nimg][hs*ws]  bins of the chunks' compact seed lists (chunk c's list starts at c * LSD_CHUNK * ws)
+  uint32_t* seedlist = nullptr; // [nimg][hs*ws] pixel indices of the same lists
+  int* chunkn = nullptr;      // [nimg][nchunks] list lengths
   int* maxmag2 = nullptr;     // [nimg]
   uint32_t* rowcnt = nullptr; // [nimg][nchunks][n_bins]  per-chunk bin counts -> prefixes
   uint32_t* binstart = nullptr; // [nimg][n_bins]
@@ -339,37 +341,79 @@ __device__ __forceinline__ double lsd_bin_coef(int maxmag2, int n_bins) {
   return max_grad > 0 ? (double)(n_bins - 1) / max_grad : 0.0;
 }
 
-// The image is cut into chunks of LSD_CHUNK rows; one CTA histograms a chunk, one warp scatters it (raster order kept).
+// The image is cut into chunks of LSD_CHUNK rows; one CTA histograms a chunk and compacts its DEFINED pixels (~12 %) into a
+// raster-ordered list (pixel index, bin) stored at the chunk's own offset of two per-image arrays (a chunk can never
+// overflow the space of its own pixels); one warp then scatters the chunk's list - 8 times fewer steps than walking a
+// dense bin map, and no dense map to write and read back.
 #define LSD_CHUNK 16
-#define LSD_BIN_UNDEF 0xFFFFu
 __global__ void __launch_bounds__(256) k_lsd_rowhist(const short2* __restrict__ gxy, int m2_min,
                                                      size_t stride, int W, int H, int n_bins, int nchunks,
-                                                     const int* __restrict__ maxmag2, uint16_t* __restrict__ binmap,
+                                                     const int* __restrict__ maxmag2, uint32_t* __restrict__ list_idx,
+                                                     uint16_t* __restrict__ list_bin, int* __restrict__ chunkn,
                                                      uint32_t* __restrict__ chunkcnt) {
   __shared__ uint32_t hist[LSD_BINS_MAX];
-  const int ch = blockIdx.x, im = blockIdx.y;
-  for (int i = threadIdx.x; i < n_bins; i += 256) hist[i] = 0;
+  __shared__ int wcnt[2][8];
+  const int ch = blockIdx.x, im = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+  for (int i = tid; i < n_bins; i += 256) hist[i] = 0;
   __syncthreads();
   const double coef = lsd_bin_coef(maxmag2[im], n_bins);
   const int y1 = min((ch + 1) * LSD_CHUNK, H - 1);
+  const size_t lo = (size_t)im * stride + (size_t)ch * LSD_CHUNK * W;   // this chunk's slice of the list arrays
+  int base = 0, it = 0;
+  // a thread owns RH_E consecutive pixels of the row (its entries stay in raster order), so a row of up to 256 * RH_E pixels
+  // costs ONE ordered compaction: per-thread count -> warp scan -> the 8 warp totals
+  constexpr int RH_E = 8;
   for (int y = ch * LSD_CHUNK; y < y1; ++y) {
     const size_t o = (size_t)im * stride + (size_t)y * W;
-    for (int x = threadIdx.x; x < W - 1; x += 256) {
-      const short2 g = gxy[o + x];
-      const int m2 = g.x * g.x + g.y * g.y;
-      uint16_t bv = LSD_BIN_UNDEF;  // undefined level-line angle (norm <= rho): never a seed
-      if (m2 >= m2_min) {
-        const double norm = sqrt((double)m2 / 4.0);
-        const int b = (int)(norm * coef);
-        bv = (uint16_t)b;
-        atomicAdd(&hist[b], 1u);
+    for (int x0 = 0; x0 < W - 1; x0 += 256 * RH_E, ++it) {
+      const int xb = x0 + tid * RH_E;
+      int bins[RH_E];
+      int cnt = 0;
+#pragma unroll
+      for (int e = 0; e < RH_E; ++e) {
+        bins[e] = -1;
+        if (xb + e < W - 1) {
+          const short2 g = gxy[o + xb + e];
+          const int m2 = g.x * g.x + g.y * g.y;
+          if (m2 >= m2_min) {   // defined level-line angle (norm > rho): a seed
+            const double norm = sqrt((double)m2 / 4.0);
+            bins[e] = (int)(norm * coef);
+            atomicAdd(&hist[bins[e]], 1u);
+            ++cnt;
+          }
+        }
       }
-      binmap[o + x] = bv;
+      int incl = cnt;   // inclusive scan of the counts over the warp
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+        if (lane >= off) incl += v;
+      }
+      if (lane == 31) wcnt[it & 1][wrp] = incl;
+      __syncthreads();
+      int woff = 0, tot = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = wcnt[it & 1][k];
+        if (k < wrp) woff += c;
+        tot += c;
+      }
+      int pos = base + woff + incl - cnt;
+#pragma unroll
+      for (int e = 0; e < RH_E; ++e) {
+        if (bins[e] >= 0) {
+          list_idx[lo + pos] = (uint32_t)(y * W + xb + e);
+          list_bin[lo + pos] = (uint16_t)bins[e];
+          ++pos;
+        }
+      }
+      base += tot;
     }
   }
   __syncthreads();
+  if (tid == 0) chunkn[(size_t)im * nchunks + ch] = base;
   uint32_t* out = chunkcnt + ((size_t)im * nchunks + ch) * n_bins;
-  for (int i = threadIdx.x; i < n_bins; i += 256) out[i] = hist[i];
+  for (int i = tid; i < n_bins; i += 256) out[i] = hist[i];
 }
 
 // one block (n_bins threads, <= 1024) per image: per-bin prefix over chunks, then start of each bin (bins descending)
@@ -404,12 +448,11 @@ __global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ chu
   if (b == n_bins - 1) nseeds[im] = (int)sc[b];
 }
 
-// one warp per (chunk, image): stable ranks via match_any, raster order preserved; the bin of the next 32 pixels is
-// fetched while the current group is ranked
-__global__ void __launch_bounds__(128) k_lsd_scatter(const uint16_t* __restrict__ binmap, size_t stride, int W, int H,
-                                                     int n_bins, int nchunks, const uint32_t* __restrict__ chunkcnt,
-                                                     const uint32_t* __restrict__ binstart,
-                                                     uint32_t* __restrict__ order) {
+// one warp per (chunk, image): walks the chunk's compact list (raster order), stable ranks via match_any
+__global__ void __launch_bounds__(128) k_lsd_scatter(const uint32_t* __restrict__ list_idx, const uint16_t* __restrict__ list_bin,
+                                                     const int* __restrict__ chunkn, size_t stride, int W, int n_bins,
+                                                     int nchunks, const uint32_t* __restrict__ chunkcnt,
+                                                     const uint32_t* __restrict__ binstart, uint32_t* __restrict__ order) {
   __shared__ uint32_t cnt[4][LSD_BINS_MAX];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ch = blockIdx.x * 4 + wid, im = blockIdx.y;
@@ -420,33 +463,32 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(const uint16_t* __restrict_
   for (int i = lane; i < n_bins; i += 32) c[i] = rc[i] + bs[i];
   __syncwarp();
   uint32_t* ord = order + (size_t)im * stride;
-  const int y1 = min((ch + 1) * LSD_CHUNK, H - 1);
-  const int ngrp = (W - 1 + 31) / 32;
-  for (int y = ch * LSD_CHUNK; y < y1; ++y) {
-    const uint16_t* brow = binmap + (size_t)im * stride + (size_t)y * W;
-    uint16_t nxt = lane < W - 1 ? brow[lane] : (uint16_t)LSD_BIN_UNDEF;
-    for (int gi = 0; gi < ngrp; ++gi) {
-      const int x = gi * 32 + lane;
-      const uint16_t bv = nxt;
-      const int xn = x + 32;
-      nxt = (gi + 1 < ngrp && xn < W - 1) ? brow[xn] : (uint16_t)LSD_BIN_UNDEF;
-      const bool valid = bv != LSD_BIN_UNDEF;
-      const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
-      if (valid) {
-        const int b = bv;
-        const unsigned peers = __match_any_sync(vm, b);
-        const int rank = __popc(peers & ((1u << lane) - 1));
-        const int leader = __ffs(peers) - 1;
-        uint32_t base = 0;
-        if (lane == leader) {
-          base = c[b];
-          c[b] = base + __popc(peers);
-        }
-        base = __shfl_sync(peers, base, leader);
-        ord[base + rank] = (uint32_t)(y * W + x);
+  const size_t lo = (size_t)im * stride + (size_t)ch * LSD_CHUNK * W;
+  const int n = chunkn[(size_t)im * nchunks + ch];
+  // the entries of the next 32-group are loaded while the current group is ranked
+  uint32_t nidx = lane < n ? list_idx[lo + lane] : 0u;
+  int nbin = lane < n ? (int)list_bin[lo + lane] : -1;
+  for (int i0 = 0; i0 < n; i0 += 32) {
+    const uint32_t idx = nidx;
+    const int b = nbin;
+    const int in = i0 + 32 + lane;
+    nidx = in < n ? list_idx[lo + in] : 0u;
+    nbin = in < n ? (int)list_bin[lo + in] : -1;
+    const bool valid = b >= 0;
+    const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
+    if (valid) {
+      const unsigned peers = __match_any_sync(vm, b);
+      const int rank = __popc(peers & ((1u << lane) - 1));
+      const int leader = __ffs(peers) - 1;
+      uint32_t base = 0;
+      if (lane == leader) {
+        base = c[b];
+        c[b] = base + __popc(peers);
       }
-      __syncwarp();
+      base = __shfl_sync(peers, base, leader);
+      ord[base + rank] = idx;
     }
+    __syncwarp();
   }
 }
 
@@ -925,7 +967,7 @@ static void lsd_release(LsdState* s) {
     cudaFree(s->regpts[p]); cudaFree(s->regions[p]); cudaFree(s->nregions[p]); cudaFree(s->segs[p]); cudaFree(s->kls[p]);
     cudaFree(s->kls_all[p]); cudaFree(s->nlines[p]);
   }
-  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap); cudaFree(s->rect_perm);
+  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap); cudaFree(s->seedlist); cudaFree(s->chunkn); cudaFree(s->rect_perm);
   cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->overflow); cudaFree(s->rs_tab);
   cudaFree(s->grad_lut); cudaFree(s->seed_lut);
 }
@@ -1010,6 +1052,8 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   PLF_CUDA(ctx, cudaMalloc(&s->blur, A * N + 64));      // + slack: plf_load4 may read the aligned word that holds the
   PLF_CUDA(ctx, cudaMalloc(&s->scaled, Asp * N + 64));  // last byte of the last image
   PLF_CUDA(ctx, cudaMalloc(&s->binmap, As * N * sizeof(uint16_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->seedlist, As * N * sizeof(uint32_t)));
+  PLF_CUDA(ctx, cudaMalloc(&s->chunkn, N * ((s->hs + LSD_CHUNK - 1) / LSD_CHUNK) * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->rect_perm, N * s->max_regions * sizeof(uint32_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->maxmag2, N * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->rowcnt, N * ((s->hs + LSD_CHUNK - 1) / LSD_CHUNK) * s->n_bins * sizeof(uint32_t)));
@@ -1075,9 +1119,11 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
   short2* gxy = s->gxy[par] + o * As;
   LsdPix* pix = s->pix[par] + o * s->pix_stride + (s->ws + 1);  // pixel (0,0) of the first image of the range
   uint16_t* binmap = s->binmap + o * As;
+  uint32_t* seedlist = s->seedlist + o * As;
   int* maxmag2 = s->maxmag2 + o;
   const int nchunks = (H - 1 + LSD_CHUNK - 1) / LSD_CHUNK;
   uint32_t* rowcnt = s->rowcnt + o * nchunks * s->n_bins;
+  int* chunkn = s->chunkn + o * nchunks;
   uint32_t* binstart = s->binstart + o * s->n_bins;
   int* nseeds = s->nseeds[par] + o;
   uint32_t* order = s->order[par] + o * As;
@@ -1122,13 +1168,13 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
   k_lsd_grad<<<dim3((W + 255) / 256, (H + 1) / 2, n), 256, 0, cs>>>(scaled, scaled_stride, scaled_pitch, W, H, s->grad_lut, s->m2_min, As, gxy, pix, s->pix_stride, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
-  k_lsd_rowhist<<<dim3(nchunks, n), 256, 0, cs>>>(gxy, s->m2_min, As, W, H, s->n_bins, nchunks, maxmag2, binmap, rowcnt);
+  k_lsd_rowhist<<<dim3(nchunks, n), 256, 0, cs>>>(gxy, s->m2_min, As, W, H, s->n_bins, nchunks, maxmag2, seedlist, binmap, chunkn, rowcnt);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rowhist");
   k_lsd_binscan<<<n, 1024, 0, cs>>>(rowcnt, nchunks, s->n_bins, binstart, nseeds);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_binscan");
-  k_lsd_scatter<<<dim3((nchunks + 3) / 4, n), 128, 0, cs>>>(binmap, As, W, H, s->n_bins, nchunks, rowcnt, binstart, order);
+  k_lsd_scatter<<<dim3((nchunks + 3) / 4, n), 128, 0, cs>>>(seedlist, binmap, chunkn, As, W, s->n_bins, nchunks, rowcnt, binstart, order);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_scatter");
   return PLF_OK;
