@@ -14,10 +14,12 @@
 //   k_blur_q8_fast   separable Q8.8 Gaussian (tile + halo staged by one TMA bulk-tensor copy, DP4A row pass), one rounding
 //                    (k_blur_q8: generic variant for tiny images)
 //   k_resize_exact4  (orb.cu) INTER_LINEAR_EXACT resample to scale
-//   k_lsd_grad       2x2 gradient -> (gx,gy) int16 pair + the 16-byte record {angle (cv::fastAtan2, degrees, f32), table
-//                    index, cosf, sinf} fetched from a table keyed by (gx,gy); per-image max of |grad|^2
+//   k_lsd_grad       2x2 gradient; for the DEFINED pixels only (|grad| > rho, ~12 %): the 16-byte record {angle
+//                    (cv::fastAtan2, degrees, f32), table index, cosf, sinf} fetched from a table keyed by (gx,gy), and one
+//                    entry of the raster-ordered seed list of the pixel's row segment; per-image max of |grad|^2.
+//                    Nothing dense leaves the kernel (the record map restores itself to "undefined", see k_lsd_fill_notdef)
 //   k_lsd_rowhist / k_lsd_binscan / k_lsd_scatter
-//                    stable counting sort of the defined pixels by magnitude bin (descending), raster order inside a
+//                    stable counting sort of the seed lists by magnitude bin (descending), raster order inside a
 //                    bin == OpenCV's ordered_points
 //   k_lsd_grow       region growing.  The algorithm is a sequential greedy partition (each accepted pixel updates the
 //                    region angle that the next test uses, and regions compete through the `used` map), so it is run by
@@ -64,15 +66,17 @@ struct LsdState {
   const void* tm_src[2] = {nullptr, nullptr};   // source buffers the cached tensor maps were encoded for
   CUtensorMap tm_blur[2];
   size_t tm_stride = 0; int tm_pitch = 0, tm_nimg = 0;
-  short2* gxy[2] = {nullptr, nullptr};      // [nimg][hs*ws]
   uint32_t* rect_perm = nullptr;  // [nimg][max_regions] regions in size-class order (k_lsd_rect_order)
   struct LsdPix* pix_raw[2] = {nullptr, nullptr};  // allocation (pix + look-ahead slack on both sides)
   struct LsdPix* pix[2] = {nullptr, nullptr};  // [nimg][guard + hs*ws]  {angle (deg, f32) | NOTDEF = undefined/used, cosf, sinf, pad}
   size_t pix_stride = 0;      // entries per image = guard (ws+1, permanently NOTDEF) + hs*ws
   int m2_min = 0;             // smallest gx^2+gy^2 whose gradient norm exceeds rho (defined pixel)
-  uint16_t* binmap = nullptr; // [nimg][hs*ws]  bins of the chunks' compact seed lists (chunk c's list starts at c * LSD_CHUNK * ws)
-  uint32_t* seedlist = nullptr; // [nimg][hs*ws] pixel indices of the same lists
-  int* chunkn = nullptr;      // [nimg][nchunks] list lengths
+  // seed lists per row segment (LSD_SEG columns): segment (y, xb) owns the entries [y * ws + LSD_SEG * xb, ...) of the three arrays
+  uint32_t* seedlist = nullptr; // [nimg][hs*ws] pixel index
+  uint32_t* seedm2 = nullptr;   // [nimg][hs*ws] gx^2 + gy^2
+  uint16_t* binmap = nullptr;   // [nimg][hs*ws] bin of the pseudo-ordering (k_lsd_rowhist)
+  int* segcnt = nullptr;        // [nimg][hs][nxb] entries per segment
+  int nxb = 0;                  // segments per row
   int* maxmag2 = nullptr;     // [nimg]
   uint32_t* rowcnt = nullptr; // [nimg][nchunks][n_bins]  per-chunk bin counts -> prefixes
   uint32_t* binstart = nullptr; // [nimg][n_bins]
@@ -283,54 +287,76 @@ __global__ void k_lsd_fill_notdef(LsdPix* __restrict__ pix, size_t n) {
 
 // pix points at pixel (0,0) of image 0 (i.e. past the guard); image stride pix_stride.
 // One thread produces the same column of TWO consecutive rows: 6 independent byte loads (3 source rows) and up to 2
-// table loads in flight per thread instead of a 4-load + 1-load chain per pixel, stores still coalesced row by row.
-__global__ void __launch_bounds__(256) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int IP, int W, int H,
-                                                  const LsdPix* __restrict__ lut, int m2_min, size_t stride,
-                                                  short2* __restrict__ gxy, LsdPix* __restrict__ pix, size_t pix_stride,
-                                                  int* __restrict__ maxmag2) {
-  const int x = blockIdx.x * 256 + threadIdx.x, y0 = blockIdx.y * 2, im = blockIdx.z;
+// table loads in flight per thread instead of a 4-load + 1-load chain per pixel.
+// Only the DEFINED pixels (gradient norm above rho, ~12 %) leave the kernel: their 16-byte record (the map's other records
+// already read "undefined", see k_lsd_fill_notdef) and one entry (pixel index, gx^2 + gy^2) of the raster-ordered SEED LIST of
+// their row segment - the 256 columns of this block; segment (y, xb) stores its entries at the segment's own pixel offset
+// y * W + 256 * xb of the list arrays, so it can never overflow, and its length in segcnt.  Nothing dense is written: the
+// seed ordering works on the lists, and the rectangle fit reads the gradient of a region point back from its record (li).
+#define LSD_SEG 256
+__global__ void __launch_bounds__(LSD_SEG) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int IP, int W, int H,
+                                                      const LsdPix* __restrict__ lut, int m2_min, size_t stride,
+                                                      LsdPix* __restrict__ pix, size_t pix_stride,
+                                                      uint32_t* __restrict__ list_idx, uint32_t* __restrict__ list_m2,
+                                                      int* __restrict__ segcnt, int nxb, int* __restrict__ maxmag2) {
+  const int x = blockIdx.x * LSD_SEG + threadIdx.x, y0 = blockIdx.y * 2, im = blockIdx.z;
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
   int mag2 = -1;
+  int li[2] = {-1, -1}, m2v[2] = {0, 0};
   if (x < W) {
     const uint8_t* p = img + (size_t)im * img_stride + (size_t)y0 * IP + x;   // IP = row pitch of the image
     const bool xin = x < W - 1, r0ok = xin && y0 < H - 1, r1ok = xin && y0 + 1 < H - 1;
     int a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0;
     if (r0ok) { a0 = p[0]; a1 = p[1]; b0 = p[IP]; b1 = p[IP + 1]; }
     if (r1ok) { c0 = p[2 * IP]; c1 = p[2 * IP + 1]; }
-    short2 g[2] = {make_short2(0, 0), make_short2(0, 0)};
-    int li[2] = {-1, -1};
     if (r0ok) {
       const int DA = b1 - a0, BC = a1 - b0, gx = DA + BC, gy = DA - BC, m2 = gx * gx + gy * gy;
-      g[0] = make_short2((short)gx, (short)gy);
-      if (m2 >= m2_min) { li[0] = (gx + 510) * LSD_LUT_DIM + (gy + 510); mag2 = m2; }  // defined angle (~10 % of the pixels)
+      if (m2 >= m2_min) { li[0] = (gx + 510) * LSD_LUT_DIM + (gy + 510); m2v[0] = m2; mag2 = m2; }  // defined angle (~12 % of the pixels)
     }
     if (r1ok) {
       const int DA = c1 - b0, BC = b1 - c0, gx = DA + BC, gy = DA - BC, m2 = gx * gx + gy * gy;
-      g[1] = make_short2((short)gx, (short)gy);
-      if (m2 >= m2_min) { li[1] = (gx + 510) * LSD_LUT_DIM + (gy + 510); mag2 = max(mag2, m2); }
+      if (m2 >= m2_min) { li[1] = (gx + 510) * LSD_LUT_DIM + (gy + 510); m2v[1] = m2; mag2 = max(mag2, m2); }
     }
     float4 e[2];
 #pragma unroll
     for (int r = 0; r < 2; ++r)
-      e[r] = li[r] >= 0 ? __ldg(reinterpret_cast<const float4*>(&lut[li[r]])) : make_float4(LSD_NOTDEF_F, 0.f, 0.f, 0.f);
+      if (li[r] >= 0) e[r] = __ldg(reinterpret_cast<const float4*>(&lut[li[r]]));
 #pragma unroll
     for (int r = 0; r < 2; ++r)
-      if (y0 + r < H) {
-        const size_t oi = (size_t)(y0 + r) * W + x;
-        gxy[(size_t)im * stride + oi] = g[r];
-        if (li[r] >= 0) *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + oi]) = e[r];   // undefined pixels already read NOTDEF (see k_lsd_fill_notdef)
-      }
+      if (li[r] >= 0) *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + (size_t)(y0 + r) * W + x]) = e[r];
   }
-  // per-image maximum: reduce in the CTA first, and only touch the (single, contended) address when it would grow
-  __shared__ int s_max[8];
+  // ordered compaction of the two row segments (x ascending) + the per-image maximum: one barrier
+  __shared__ int s_max[8], s_c0[8], s_c1[8];
+  const unsigned bal0 = __ballot_sync(0xFFFFFFFFu, li[0] >= 0), bal1 = __ballot_sync(0xFFFFFFFFu, li[1] >= 0);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) mag2 = max(mag2, __shfl_xor_sync(0xFFFFFFFFu, mag2, off));
-  if ((threadIdx.x & 31) == 0) s_max[threadIdx.x >> 5] = mag2;
+  if (lane == 0) { s_max[wrp] = mag2; s_c0[wrp] = __popc(bal0); s_c1[wrp] = __popc(bal1); }
   __syncthreads();
+  int w0 = 0, w1 = 0, t0 = 0, t1 = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    if (k < wrp) { w0 += s_c0[k]; w1 += s_c1[k]; }
+    t0 += s_c0[k]; t1 += s_c1[k];
+  }
+  const size_t lbase = (size_t)im * stride + (size_t)blockIdx.x * LSD_SEG;
+  if (li[0] >= 0) {
+    const size_t o = lbase + (size_t)y0 * W + w0 + __popc(bal0 & ((1u << lane) - 1u));
+    list_idx[o] = (uint32_t)(y0 * W + x);
+    list_m2[o] = (uint32_t)m2v[0];
+  }
+  if (li[1] >= 0) {
+    const size_t o = lbase + (size_t)(y0 + 1) * W + w1 + __popc(bal1 & ((1u << lane) - 1u));
+    list_idx[o] = (uint32_t)((y0 + 1) * W + x);
+    list_m2[o] = (uint32_t)m2v[1];
+  }
   if (threadIdx.x == 0) {
+    int* sc = segcnt + (size_t)im * ((size_t)H * nxb);
+    sc[(size_t)y0 * nxb + blockIdx.x] = t0;
+    if (y0 + 1 < H) sc[(size_t)(y0 + 1) * nxb + blockIdx.x] = t1;
     int m = s_max[0];
 #pragma unroll
     for (int k = 1; k < 8; ++k) m = max(m, s_max[k]);
-    if (m >= 0 && m > __ldcg(&maxmag2[im])) atomicMax(&maxmag2[im], m);
+    if (m >= 0 && m > __ldcg(&maxmag2[im])) atomicMax(&maxmag2[im], m);   // only touch the (contended) address when it would grow
   }
 }
 
@@ -341,77 +367,34 @@ __device__ __forceinline__ double lsd_bin_coef(int maxmag2, int n_bins) {
   return max_grad > 0 ? (double)(n_bins - 1) / max_grad : 0.0;
 }
 
-// The image is cut into chunks of LSD_CHUNK rows; one CTA histograms a chunk and compacts its DEFINED pixels (~12 %) into a
-// raster-ordered list (pixel index, bin) stored at the chunk's own offset of two per-image arrays (a chunk can never
-// overflow the space of its own pixels); one warp then scatters the chunk's list - 8 times fewer steps than walking a
-// dense bin map, and no dense map to write and read back.
+// The image is cut into chunks of LSD_CHUNK rows.  One CTA bins a chunk: its warps walk the chunk's row-segment lists (written
+// by the gradient kernel: only the defined pixels, ~12 %), turn gx^2 + gy^2 into the bin of the 1024-bin pseudo-ordering
+// (the per-image maximum is known by now) and count the bins; one warp then scatters the chunk's lists in raster order.
 #define LSD_CHUNK 16
-__global__ void __launch_bounds__(256) k_lsd_rowhist(const short2* __restrict__ gxy, int m2_min,
-                                                     size_t stride, int W, int H, int n_bins, int nchunks,
-                                                     const int* __restrict__ maxmag2, uint32_t* __restrict__ list_idx,
-                                                     uint16_t* __restrict__ list_bin, int* __restrict__ chunkn,
+__global__ void __launch_bounds__(256) k_lsd_rowhist(size_t stride, int W, int H, int n_bins, int nchunks, int nxb,
+                                                     const int* __restrict__ maxmag2, const uint32_t* __restrict__ list_m2,
+                                                     const int* __restrict__ segcnt, uint16_t* __restrict__ list_bin,
                                                      uint32_t* __restrict__ chunkcnt) {
   __shared__ uint32_t hist[LSD_BINS_MAX];
-  __shared__ int wcnt[2][8];
   const int ch = blockIdx.x, im = blockIdx.y, tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
   for (int i = tid; i < n_bins; i += 256) hist[i] = 0;
   __syncthreads();
   const double coef = lsd_bin_coef(maxmag2[im], n_bins);
-  const int y1 = min((ch + 1) * LSD_CHUNK, H - 1);
-  const size_t lo = (size_t)im * stride + (size_t)ch * LSD_CHUNK * W;   // this chunk's slice of the list arrays
-  int base = 0, it = 0;
-  // a thread owns RH_E consecutive pixels of the row (its entries stay in raster order), so a row of up to 256 * RH_E pixels
-  // costs ONE ordered compaction: per-thread count -> warp scan -> the 8 warp totals
-  constexpr int RH_E = 8;
-  for (int y = ch * LSD_CHUNK; y < y1; ++y) {
-    const size_t o = (size_t)im * stride + (size_t)y * W;
-    for (int x0 = 0; x0 < W - 1; x0 += 256 * RH_E, ++it) {
-      const int xb = x0 + tid * RH_E;
-      int bins[RH_E];
-      int cnt = 0;
-#pragma unroll
-      for (int e = 0; e < RH_E; ++e) {
-        bins[e] = -1;
-        if (xb + e < W - 1) {
-          const short2 g = gxy[o + xb + e];
-          const int m2 = g.x * g.x + g.y * g.y;
-          if (m2 >= m2_min) {   // defined level-line angle (norm > rho): a seed
-            const double norm = sqrt((double)m2 / 4.0);
-            bins[e] = (int)(norm * coef);
-            atomicAdd(&hist[bins[e]], 1u);
-            ++cnt;
-          }
-        }
-      }
-      int incl = cnt;   // inclusive scan of the counts over the warp
-#pragma unroll
-      for (int off = 1; off < 32; off <<= 1) {
-        const int v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
-        if (lane >= off) incl += v;
-      }
-      if (lane == 31) wcnt[it & 1][wrp] = incl;
-      __syncthreads();
-      int woff = 0, tot = 0;
-#pragma unroll
-      for (int k = 0; k < 8; ++k) {
-        const int c = wcnt[it & 1][k];
-        if (k < wrp) woff += c;
-        tot += c;
-      }
-      int pos = base + woff + incl - cnt;
-#pragma unroll
-      for (int e = 0; e < RH_E; ++e) {
-        if (bins[e] >= 0) {
-          list_idx[lo + pos] = (uint32_t)(y * W + xb + e);
-          list_bin[lo + pos] = (uint16_t)bins[e];
-          ++pos;
-        }
-      }
-      base += tot;
+  const int ya = ch * LSD_CHUNK, y1 = min((ch + 1) * LSD_CHUNK, H - 1);
+  const int nseg = (y1 - ya) * nxb;
+  const int* sc = segcnt + (size_t)im * ((size_t)H * nxb);
+  for (int sg = wrp; sg < nseg; sg += 8) {
+    const int y = ya + sg / nxb, xb = sg - (sg / nxb) * nxb;
+    const int n = sc[(size_t)y * nxb + xb];
+    const size_t o = (size_t)im * stride + (size_t)y * W + (size_t)xb * LSD_SEG;
+    for (int i = lane; i < n; i += 32) {
+      const double norm = sqrt((double)list_m2[o + i] / 4.0);
+      const int b = (int)(norm * coef);
+      list_bin[o + i] = (uint16_t)b;
+      atomicAdd(&hist[b], 1u);
     }
   }
   __syncthreads();
-  if (tid == 0) chunkn[(size_t)im * nchunks + ch] = base;
   uint32_t* out = chunkcnt + ((size_t)im * nchunks + ch) * n_bins;
   for (int i = tid; i < n_bins; i += 256) out[i] = hist[i];
 }
@@ -448,10 +431,10 @@ __global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ chu
   if (b == n_bins - 1) nseeds[im] = (int)sc[b];
 }
 
-// one warp per (chunk, image): walks the chunk's compact list (raster order), stable ranks via match_any
+// one warp per (chunk, image): walks the chunk's row-segment lists in raster order, stable ranks via match_any
 __global__ void __launch_bounds__(128) k_lsd_scatter(const uint32_t* __restrict__ list_idx, const uint16_t* __restrict__ list_bin,
-                                                     const int* __restrict__ chunkn, size_t stride, int W, int n_bins,
-                                                     int nchunks, const uint32_t* __restrict__ chunkcnt,
+                                                     const int* __restrict__ segcnt, size_t stride, int W, int H, int n_bins,
+                                                     int nchunks, int nxb, const uint32_t* __restrict__ chunkcnt,
                                                      const uint32_t* __restrict__ binstart, uint32_t* __restrict__ order) {
   __shared__ uint32_t cnt[4][LSD_BINS_MAX];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -463,32 +446,35 @@ __global__ void __launch_bounds__(128) k_lsd_scatter(const uint32_t* __restrict_
   for (int i = lane; i < n_bins; i += 32) c[i] = rc[i] + bs[i];
   __syncwarp();
   uint32_t* ord = order + (size_t)im * stride;
-  const size_t lo = (size_t)im * stride + (size_t)ch * LSD_CHUNK * W;
-  const int n = chunkn[(size_t)im * nchunks + ch];
-  // the entries of the next 32-group are loaded while the current group is ranked
-  uint32_t nidx = lane < n ? list_idx[lo + lane] : 0u;
-  int nbin = lane < n ? (int)list_bin[lo + lane] : -1;
-  for (int i0 = 0; i0 < n; i0 += 32) {
-    const uint32_t idx = nidx;
-    const int b = nbin;
-    const int in = i0 + 32 + lane;
-    nidx = in < n ? list_idx[lo + in] : 0u;
-    nbin = in < n ? (int)list_bin[lo + in] : -1;
-    const bool valid = b >= 0;
-    const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
-    if (valid) {
-      const unsigned peers = __match_any_sync(vm, b);
-      const int rank = __popc(peers & ((1u << lane) - 1));
-      const int leader = __ffs(peers) - 1;
-      uint32_t base = 0;
-      if (lane == leader) {
-        base = c[b];
-        c[b] = base + __popc(peers);
+  const int ya = ch * LSD_CHUNK, y1 = min((ch + 1) * LSD_CHUNK, H - 1);
+  const int nseg = (y1 - ya) * nxb;
+  const int* sc = segcnt + (size_t)im * ((size_t)H * nxb) + (size_t)ya * nxb;   // the chunk's segments are contiguous, row-major
+  int n_next = nseg > 0 ? sc[0] : 0;
+  for (int sg = 0; sg < nseg; ++sg) {
+    const int n = n_next;
+    n_next = sg + 1 < nseg ? sc[sg + 1] : 0;
+    const int y = ya + sg / nxb, xb = sg - (sg / nxb) * nxb;
+    const size_t o = (size_t)im * stride + (size_t)y * W + (size_t)xb * LSD_SEG;
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const bool valid = i < n;
+      const uint32_t idx = valid ? list_idx[o + i] : 0u;
+      const int b = valid ? (int)list_bin[o + i] : -1;
+      const unsigned vm = __ballot_sync(0xFFFFFFFFu, valid);
+      if (valid) {
+        const unsigned peers = __match_any_sync(vm, b);
+        const int rank = __popc(peers & ((1u << lane) - 1));
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) {
+          base = c[b];
+          c[b] = base + __popc(peers);
+        }
+        base = __shfl_sync(peers, base, leader);
+        ord[base + rank] = idx;
       }
-      base = __shfl_sync(peers, base, leader);
-      ord[base + rank] = idx;
+      __syncwarp();
     }
-    __syncwarp();
   }
 }
 
@@ -750,7 +736,7 @@ __global__ void __launch_bounds__(256) k_lsd_rect_order(const uint4* __restrict_
     perm[atomicAdd(&pos[min(31 - __clz((int)regions[i].y | 1), LSD_SIZE_BINS - 1)], 1)] = (uint32_t)i;
 }
 
-__global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gxy_all, size_t stride, int W,
+__global__ void __launch_bounds__(128) k_lsd_rects(const LsdPix* __restrict__ pix_all, size_t pix_stride, size_t stride, int W,
                                                    const uint32_t* __restrict__ regpts_all,
                                                    const uint4* __restrict__ regions_all, int max_regions,
                                                    const int* __restrict__ nregions, const uint32_t* __restrict__ perm_all,
@@ -760,11 +746,13 @@ __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gx
   const int ri = (int)perm_all[(size_t)im * max_regions + slot];
   const uint4 R = regions_all[(size_t)im * max_regions + ri];
   const uint32_t* pts = regpts_all + (size_t)im * stride + R.x;
-  const short2* gxy = gxy_all + (size_t)im * stride;
+  // the gradient of a region point comes back from its record: li = (gx + 510) * 1021 + (gy + 510) (region growing only
+  // overwrites the record's angle)
+  const LsdPix* recs = pix_all + (size_t)im * pix_stride;
   const int n = (int)R.y;
   const double reg_angle = __longlong_as_double((long long)(((unsigned long long)R.w << 32) | R.z));
   // The sums run in the region's point order (bit-exact with the CPU loop); what is batched is the LOADS: the point
-  // indices and the gradients of 8 points are fetched before their terms are added, so the dependent pts[k] -> gxy[p]
+  // indices and the gradients of 8 points are fetched before their terms are added, so the dependent pts[k] -> record
   // round trips overlap instead of serialising (the thread is otherwise one L2 / DRAM latency per point).
   constexpr int PF = 8;
   double x = 0, y = 0, sum = 0;
@@ -774,7 +762,11 @@ __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gx
 #pragma unroll
     for (int j = 0; j < PF; ++j) pp[j] = k0 + j < n ? pts[k0 + j] : 0u;
 #pragma unroll
-    for (int j = 0; j < PF; ++j) gg[j] = k0 + j < n ? gxy[pp[j]] : make_short2(0, 0);
+    for (int j = 0; j < PF; ++j) {
+      const uint32_t li = k0 + j < n ? __ldg(&recs[pp[j]].li) : 0u;
+      const int gxv = (int)(li / (uint32_t)LSD_LUT_DIM);
+      gg[j] = make_short2((short)(gxv - 510), (short)((int)li - gxv * LSD_LUT_DIM - 510));
+    }
 #pragma unroll
     for (int j = 0; j < PF; ++j) {
       if (k0 + j < n) {
@@ -796,7 +788,11 @@ __global__ void __launch_bounds__(128) k_lsd_rects(const short2* __restrict__ gx
 #pragma unroll
     for (int j = 0; j < PF; ++j) pp[j] = k0 + j < n ? pts[k0 + j] : 0u;
 #pragma unroll
-    for (int j = 0; j < PF; ++j) gg[j] = k0 + j < n ? gxy[pp[j]] : make_short2(0, 0);
+    for (int j = 0; j < PF; ++j) {
+      const uint32_t li = k0 + j < n ? __ldg(&recs[pp[j]].li) : 0u;
+      const int gxv = (int)(li / (uint32_t)LSD_LUT_DIM);
+      gg[j] = make_short2((short)(gxv - 510), (short)((int)li - gxv * LSD_LUT_DIM - 510));
+    }
 #pragma unroll
     for (int j = 0; j < PF; ++j) {
       if (k0 + j < n) {
@@ -963,11 +959,11 @@ __global__ void __launch_bounds__(1024) k_keylines(const float4* __restrict__ se
 // ---- host side -------------------------------------------------------------------------------------------------
 static void lsd_release(LsdState* s) {
   for (int p = 0; p < 2; ++p) {
-    cudaFree(s->gxy[p]); cudaFree(s->pix_raw[p]); cudaFree(s->order[p]); cudaFree(s->nseeds[p]);
+    cudaFree(s->pix_raw[p]); cudaFree(s->order[p]); cudaFree(s->nseeds[p]);
     cudaFree(s->regpts[p]); cudaFree(s->regions[p]); cudaFree(s->nregions[p]); cudaFree(s->segs[p]); cudaFree(s->kls[p]);
     cudaFree(s->kls_all[p]); cudaFree(s->nlines[p]);
   }
-  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap); cudaFree(s->seedlist); cudaFree(s->chunkn); cudaFree(s->rect_perm);
+  cudaFree(s->blur); cudaFree(s->scaled); cudaFree(s->binmap); cudaFree(s->seedlist); cudaFree(s->seedm2); cudaFree(s->segcnt); cudaFree(s->rect_perm);
   cudaFree(s->maxmag2); cudaFree(s->rowcnt); cudaFree(s->binstart); cudaFree(s->overflow); cudaFree(s->rs_tab);
   cudaFree(s->grad_lut); cudaFree(s->seed_lut);
 }
@@ -1053,7 +1049,9 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   PLF_CUDA(ctx, cudaMalloc(&s->scaled, Asp * N + 64));  // last byte of the last image
   PLF_CUDA(ctx, cudaMalloc(&s->binmap, As * N * sizeof(uint16_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->seedlist, As * N * sizeof(uint32_t)));
-  PLF_CUDA(ctx, cudaMalloc(&s->chunkn, N * ((s->hs + LSD_CHUNK - 1) / LSD_CHUNK) * sizeof(int)));
+  PLF_CUDA(ctx, cudaMalloc(&s->seedm2, As * N * sizeof(uint32_t)));
+  s->nxb = (s->ws + LSD_SEG - 1) / LSD_SEG;
+  PLF_CUDA(ctx, cudaMalloc(&s->segcnt, N * (size_t)s->hs * s->nxb * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->rect_perm, N * s->max_regions * sizeof(uint32_t)));
   PLF_CUDA(ctx, cudaMalloc(&s->maxmag2, N * sizeof(int)));
   PLF_CUDA(ctx, cudaMalloc(&s->rowcnt, N * ((s->hs + LSD_CHUNK - 1) / LSD_CHUNK) * s->n_bins * sizeof(uint32_t)));
@@ -1061,7 +1059,6 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   // buffers that cross from the pre-grow phase to the grow / match phases exist twice (parity of the batch), so that
   // batch i+1 can be extracted while batch i is still growing regions; standalone operators use parity 0 only
   for (int p = 0; p < (s->two_parities ? 2 : 1); ++p) {
-    PLF_CUDA(ctx, cudaMalloc(&s->gxy[p], As * N * sizeof(short2)));
     // 3 rows + 8 records of slack on both sides: the growing kernel's look-ahead prefetches need no clamping
     const size_t pad = 3 * (size_t)s->ws + 8;
     PLF_CUDA(ctx, cudaMalloc(&s->pix_raw[p], (s->pix_stride * N + 2 * pad) * sizeof(LsdPix)));
@@ -1116,14 +1113,14 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
   const uint8_t* imgs = d_imgs + o * img_stride;
   uint8_t* blur = s->blur + o * A;
   uint8_t* scaled_buf = s->scaled + o * Asp;
-  short2* gxy = s->gxy[par] + o * As;
   LsdPix* pix = s->pix[par] + o * s->pix_stride + (s->ws + 1);  // pixel (0,0) of the first image of the range
   uint16_t* binmap = s->binmap + o * As;
   uint32_t* seedlist = s->seedlist + o * As;
+  uint32_t* seedm2 = s->seedm2 + o * As;
+  int* segcnt = s->segcnt + o * (size_t)H * s->nxb;
   int* maxmag2 = s->maxmag2 + o;
   const int nchunks = (H - 1 + LSD_CHUNK - 1) / LSD_CHUNK;
   uint32_t* rowcnt = s->rowcnt + o * nchunks * s->n_bins;
-  int* chunkn = s->chunkn + o * nchunks;
   uint32_t* binstart = s->binstart + o * s->n_bins;
   int* nseeds = s->nseeds[par] + o;
   uint32_t* order = s->order[par] + o * As;
@@ -1165,16 +1162,17 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
     scaled_pitch = s->sp;
   }
   PLF_CUDA(ctx, cudaMemsetAsync(maxmag2, 0xFF, (size_t)n * sizeof(int), cs));  // -1
-  k_lsd_grad<<<dim3((W + 255) / 256, (H + 1) / 2, n), 256, 0, cs>>>(scaled, scaled_stride, scaled_pitch, W, H, s->grad_lut, s->m2_min, As, gxy, pix, s->pix_stride, maxmag2);
+  k_lsd_grad<<<dim3(s->nxb, (H + 1) / 2, n), LSD_SEG, 0, cs>>>(scaled, scaled_stride, scaled_pitch, W, H, s->grad_lut, s->m2_min, As, pix, s->pix_stride,
+                                                               seedlist, seedm2, segcnt, s->nxb, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
-  k_lsd_rowhist<<<dim3(nchunks, n), 256, 0, cs>>>(gxy, s->m2_min, As, W, H, s->n_bins, nchunks, maxmag2, seedlist, binmap, chunkn, rowcnt);
+  k_lsd_rowhist<<<dim3(nchunks, n), 256, 0, cs>>>(As, W, H, s->n_bins, nchunks, s->nxb, maxmag2, seedm2, segcnt, binmap, rowcnt);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rowhist");
   k_lsd_binscan<<<n, 1024, 0, cs>>>(rowcnt, nchunks, s->n_bins, binstart, nseeds);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_binscan");
-  k_lsd_scatter<<<dim3((nchunks + 3) / 4, n), 128, 0, cs>>>(seedlist, binmap, chunkn, As, W, s->n_bins, nchunks, rowcnt, binstart, order);
+  k_lsd_scatter<<<dim3((nchunks + 3) / 4, n), 128, 0, cs>>>(seedlist, binmap, segcnt, As, W, H, s->n_bins, nchunks, s->nxb, rowcnt, binstart, order);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_scatter");
   return PLF_OK;
@@ -1187,7 +1185,6 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   cudaStream_t cs = ctx->cur;
   const int W = s->ws, H = s->hs;
   const size_t As = (size_t)W * H, o = (size_t)img0;
-  short2* gxy = s->gxy[par] + o * As;
   LsdPix* pix = s->pix[par] + o * s->pix_stride + (s->ws + 1);
   int* nseeds = s->nseeds[par] + o;
   uint32_t* order = s->order[par] + o * As;
@@ -1207,7 +1204,7 @@ plf_status plf_lsd_grow_range(plf_ctx* ctx, int w, int h, int par, int img0, int
   uint32_t* perm = s->rect_perm + o * s->max_regions;
   k_lsd_rect_order<<<n, 256, 0, cs>>>(regions, s->max_regions, nregions, perm);
   PLF_LAUNCH_CHECK(ctx);
-  k_lsd_rects<<<dim3((s->max_regions + 127) / 128, n), 128, 0, cs>>>(gxy, As, W, regpts, regions, s->max_regions, nregions,
+  k_lsd_rects<<<dim3((s->max_regions + 127) / 128, n), 128, 0, cs>>>(pix, s->pix_stride, As, W, regpts, regions, s->max_regions, nregions,
                                                                      perm, s->prec, s->scale, segs);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_rects");
