@@ -286,76 +286,104 @@ __global__ void k_lsd_fill_notdef(LsdPix* __restrict__ pix, size_t n) {
 }
 
 // pix points at pixel (0,0) of image 0 (i.e. past the guard); image stride pix_stride.
-// One thread produces the same column of TWO consecutive rows: 6 independent byte loads (3 source rows) and up to 2
-// table loads in flight per thread instead of a 4-load + 1-load chain per pixel.
 // Only the DEFINED pixels (gradient norm above rho, ~12 %) leave the kernel: their 16-byte record (the map's other records
 // already read "undefined", see k_lsd_fill_notdef) and one entry (pixel index, gx^2 + gy^2) of the raster-ordered SEED LIST of
-// their row segment - the 256 columns of this block; segment (y, xb) stores its entries at the segment's own pixel offset
-// y * W + 256 * xb of the list arrays, so it can never overflow, and its length in segcnt.  Nothing dense is written: the
+// their row segment - the LSD_SEG columns of this block; segment (y, xb) stores its entries at the segment's own pixel offset
+// y * W + LSD_SEG * xb of the list arrays, so it can never overflow, and its length in segcnt.  Nothing dense is written: the
 // seed ordering works on the lists, and the rectangle fit reads the gradient of a region point back from its record (li).
-#define LSD_SEG 256
-__global__ void __launch_bounds__(LSD_SEG) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int IP, int W, int H,
-                                                      const LsdPix* __restrict__ lut, int m2_min, size_t stride,
-                                                      LsdPix* __restrict__ pix, size_t pix_stride,
-                                                      uint32_t* __restrict__ list_idx, uint32_t* __restrict__ list_m2,
-                                                      int* __restrict__ segcnt, int nxb, int* __restrict__ maxmag2) {
-  const int x = blockIdx.x * LSD_SEG + threadIdx.x, y0 = blockIdx.y * 2, im = blockIdx.z;
+#define LSD_SEG 512
+#define LSD_GRAD_THREADS (LSD_SEG / 4)
+// A thread produces FOUR adjacent columns of two rows from three aligned 32-bit words of the (16-byte pitched) image - the
+// fifth column of each row comes from the neighbour lane's word (lane 31 loads it) - so a warp issues 3 (+3) load instructions
+// for 256 pixels instead of 6 for 64.
+__global__ void __launch_bounds__(LSD_GRAD_THREADS) k_lsd_grad(const uint8_t* __restrict__ img, size_t img_stride, int IP, int W, int H,
+                                                               const LsdPix* __restrict__ lut, int m2_min, size_t stride,
+                                                               LsdPix* __restrict__ pix, size_t pix_stride,
+                                                               uint32_t* __restrict__ list_idx, uint32_t* __restrict__ list_m2,
+                                                               int* __restrict__ segcnt, int nxb, int* __restrict__ maxmag2) {
+  const int x4 = blockIdx.x * LSD_SEG + threadIdx.x * 4, y0 = blockIdx.y * 2, im = blockIdx.z;
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  int mag2 = -1;
-  int li[2] = {-1, -1}, m2v[2] = {0, 0};
-  if (x < W) {
-    const uint8_t* p = img + (size_t)im * img_stride + (size_t)y0 * IP + x;   // IP = row pitch of the image
-    const bool xin = x < W - 1, r0ok = xin && y0 < H - 1, r1ok = xin && y0 + 1 < H - 1;
-    int a0 = 0, a1 = 0, b0 = 0, b1 = 0, c0 = 0, c1 = 0;
-    if (r0ok) { a0 = p[0]; a1 = p[1]; b0 = p[IP]; b1 = p[IP + 1]; }
-    if (r1ok) { c0 = p[2 * IP]; c1 = p[2 * IP + 1]; }
-    if (r0ok) {
-      const int DA = b1 - a0, BC = a1 - b0, gx = DA + BC, gy = DA - BC, m2 = gx * gx + gy * gy;
-      if (m2 >= m2_min) { li[0] = (gx + 510) * LSD_LUT_DIM + (gy + 510); m2v[0] = m2; mag2 = m2; }  // defined angle (~12 % of the pixels)
-    }
-    if (r1ok) {
-      const int DA = c1 - b0, BC = b1 - c0, gx = DA + BC, gy = DA - BC, m2 = gx * gx + gy * gy;
-      if (m2 >= m2_min) { li[1] = (gx + 510) * LSD_LUT_DIM + (gy + 510); m2v[1] = m2; mag2 = max(mag2, m2); }
-    }
-    float4 e[2];
+  // words of rows y0 .. y0+2 at columns x4 .. x4+3 (rows / words beyond the image read as 0: those pixels are never defined -
+  // the last column and the last row of the map are excluded below)
+  uint32_t w[3] = {0u, 0u, 0u}, wn[3] = {0u, 0u, 0u};
+  const uint8_t* p = img + (size_t)im * img_stride + (size_t)y0 * IP + x4;
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-      if (li[r] >= 0) e[r] = __ldg(reinterpret_cast<const float4*>(&lut[li[r]]));
+  for (int r = 0; r < 3; ++r)
+    if (x4 < W && y0 + r < H) w[r] = __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)r * IP));   // IP is a multiple of 16, x4 of 4
 #pragma unroll
-    for (int r = 0; r < 2; ++r)
-      if (li[r] >= 0) *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + (size_t)(y0 + r) * W + x]) = e[r];
+  for (int r = 0; r < 3; ++r) {
+    wn[r] = __shfl_down_sync(0xFFFFFFFFu, w[r], 1);
+    if (lane == 31) wn[r] = (x4 + 4 < IP && y0 + r < H) ? __ldg(reinterpret_cast<const uint32_t*>(p + (size_t)r * IP + 4)) : 0u;
   }
+  int mag2 = -1;
+  int li[2][4], m2v[2][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const bool rok = y0 + r < H - 1;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      li[r][c] = -1; m2v[r][c] = 0;
+      // pixel (x, y) = (x4 + c, y0 + r): A = (x, y), B = (x+1, y), C = (x, y+1), D = (x+1, y+1)
+      const int A = (w[r] >> (8 * c)) & 0xFF, C = (w[r + 1] >> (8 * c)) & 0xFF;
+      const int B = c < 3 ? (int)((w[r] >> (8 * c + 8)) & 0xFF) : (int)(wn[r] & 0xFF);
+      const int D = c < 3 ? (int)((w[r + 1] >> (8 * c + 8)) & 0xFF) : (int)(wn[r + 1] & 0xFF);
+      if (rok && x4 + c < W - 1) {
+        const int DA = D - A, BC = B - C, gx = DA + BC, gy = DA - BC, m2 = gx * gx + gy * gy;
+        if (m2 >= m2_min) { li[r][c] = (gx + 510) * LSD_LUT_DIM + (gy + 510); m2v[r][c] = m2; mag2 = max(mag2, m2); }  // defined angle
+      }
+    }
+  }
+  // records of the defined pixels
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (li[r][c] >= 0)
+        *reinterpret_cast<float4*>(&pix[(size_t)im * pix_stride + (size_t)(y0 + r) * W + x4 + c]) =
+            __ldg(reinterpret_cast<const float4*>(&lut[li[r][c]]));
   // ordered compaction of the two row segments (x ascending) + the per-image maximum: one barrier
-  __shared__ int s_max[8], s_c0[8], s_c1[8];
-  const unsigned bal0 = __ballot_sync(0xFFFFFFFFu, li[0] >= 0), bal1 = __ballot_sync(0xFFFFFFFFu, li[1] >= 0);
+  __shared__ int s_max[4], s_c[2][4];
+  int cnt[2], incl[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    cnt[r] = (li[r][0] >= 0) + (li[r][1] >= 0) + (li[r][2] >= 0) + (li[r][3] >= 0);
+    incl[r] = cnt[r];
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int v = __shfl_up_sync(0xFFFFFFFFu, incl[r], off);
+      if (lane >= off) incl[r] += v;
+    }
+  }
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) mag2 = max(mag2, __shfl_xor_sync(0xFFFFFFFFu, mag2, off));
-  if (lane == 0) { s_max[wrp] = mag2; s_c0[wrp] = __popc(bal0); s_c1[wrp] = __popc(bal1); }
+  if (lane == 31) { s_c[0][wrp] = incl[0]; s_c[1][wrp] = incl[1]; }
+  if (lane == 0) s_max[wrp] = mag2;
   __syncthreads();
-  int w0 = 0, w1 = 0, t0 = 0, t1 = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    if (k < wrp) { w0 += s_c0[k]; w1 += s_c1[k]; }
-    t0 += s_c0[k]; t1 += s_c1[k];
-  }
   const size_t lbase = (size_t)im * stride + (size_t)blockIdx.x * LSD_SEG;
-  if (li[0] >= 0) {
-    const size_t o = lbase + (size_t)y0 * W + w0 + __popc(bal0 & ((1u << lane) - 1u));
-    list_idx[o] = (uint32_t)(y0 * W + x);
-    list_m2[o] = (uint32_t)m2v[0];
-  }
-  if (li[1] >= 0) {
-    const size_t o = lbase + (size_t)(y0 + 1) * W + w1 + __popc(bal1 & ((1u << lane) - 1u));
-    list_idx[o] = (uint32_t)((y0 + 1) * W + x);
-    list_m2[o] = (uint32_t)m2v[1];
+  int tot[2];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    int woff = 0;
+    tot[r] = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (k < wrp) woff += s_c[r][k];
+      tot[r] += s_c[r][k];
+    }
+    size_t o = lbase + (size_t)(y0 + r) * W + woff + incl[r] - cnt[r];
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (li[r][c] >= 0) {
+        list_idx[o] = (uint32_t)((y0 + r) * W + x4 + c);
+        list_m2[o] = (uint32_t)m2v[r][c];
+        ++o;
+      }
   }
   if (threadIdx.x == 0) {
     int* sc = segcnt + (size_t)im * ((size_t)H * nxb);
-    sc[(size_t)y0 * nxb + blockIdx.x] = t0;
-    if (y0 + 1 < H) sc[(size_t)(y0 + 1) * nxb + blockIdx.x] = t1;
-    int m = s_max[0];
-#pragma unroll
-    for (int k = 1; k < 8; ++k) m = max(m, s_max[k]);
+    sc[(size_t)y0 * nxb + blockIdx.x] = tot[0];
+    if (y0 + 1 < H) sc[(size_t)(y0 + 1) * nxb + blockIdx.x] = tot[1];
+    const int m = max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3]));
     if (m >= 0 && m > __ldcg(&maxmag2[im])) atomicMax(&maxmag2[im], m);   // only touch the (contended) address when it would grow
   }
 }
@@ -1162,7 +1190,7 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
     scaled_pitch = s->sp;
   }
   PLF_CUDA(ctx, cudaMemsetAsync(maxmag2, 0xFF, (size_t)n * sizeof(int), cs));  // -1
-  k_lsd_grad<<<dim3(s->nxb, (H + 1) / 2, n), LSD_SEG, 0, cs>>>(scaled, scaled_stride, scaled_pitch, W, H, s->grad_lut, s->m2_min, As, pix, s->pix_stride,
+  k_lsd_grad<<<dim3(s->nxb, (H + 1) / 2, n), LSD_GRAD_THREADS, 0, cs>>>(scaled, scaled_stride, scaled_pitch, W, H, s->grad_lut, s->m2_min, As, pix, s->pix_stride,
                                                                seedlist, seedm2, segcnt, s->nxb, maxmag2);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "lsd.k_lsd_grad");
