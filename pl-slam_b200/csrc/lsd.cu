@@ -32,8 +32,8 @@
 //                    one thread per region, regions permuted into size classes: weighted centroid, inertia-matrix
 //                    angle, extent - sequential fp64 sums in region order (bit-exact with the CPU loop)
 //   k_keylines       clamp + length filter + KeyLine fill with ordered compaction, optional top-K by response
-// Roofline: the gradient kernel is bound by its HBM writes (4.7 TB/s); region growing is latency-bound by construction
-// and is reported as time, not as a roofline fraction; the rest in DESIGN.md §4.
+// Roofline: region growing is latency-bound by construction and is reported as time, not as a roofline fraction;
+// the rest in DESIGN.md §4.
 #include <float.h>
 #include <stdlib.h>
 
@@ -427,36 +427,55 @@ __global__ void __launch_bounds__(256) k_lsd_rowhist(size_t stride, int W, int H
   for (int i = tid; i < n_bins; i += 256) out[i] = hist[i];
 }
 
-// one block (n_bins threads, <= 1024) per image: per-bin prefix over chunks, then start of each bin (bins descending)
+// one block (n_bins threads, <= 1024) per image: per-bin prefix over chunks, then start of each bin (bins descending).
+// The chunk counts of a bin are loaded 8 at a time before their prefixes are stored back (the loads of a plain
+// read-modify-write loop serialise behind the stores to the same array); the scan over the bins is two levels of warp shuffles.
 __global__ void __launch_bounds__(1024) k_lsd_binscan(uint32_t* __restrict__ chunkcnt, int nchunks, int n_bins,
                                                       uint32_t* __restrict__ binstart, int* __restrict__ nseeds) {
   __shared__ uint32_t tot[LSD_BINS_MAX];
-  const int im = blockIdx.x, b = threadIdx.x;
+  __shared__ uint32_t wsum[32];
+  const int im = blockIdx.x, b = threadIdx.x, lane = b & 31, wrp = b >> 5;
   uint32_t run = 0;
   if (b < n_bins) {
     uint32_t* c = chunkcnt + (size_t)im * nchunks * n_bins + b;
-    for (int k = 0; k < nchunks; ++k) {
-      const uint32_t v = c[(size_t)k * n_bins];
-      c[(size_t)k * n_bins] = run;
-      run += v;
+    for (int k0 = 0; k0 < nchunks; k0 += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = k0 + j < nchunks ? __ldcg(&c[(size_t)(k0 + j) * n_bins]) : 0u;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (k0 + j < nchunks) {
+          c[(size_t)(k0 + j) * n_bins] = run;
+          run += v[j];
+        }
     }
     tot[b] = run;
   }
   __syncthreads();
-  // exclusive scan over bins in DESCENDING bin order (Hillis-Steele on the reversed array)
-  __shared__ uint32_t sc[LSD_BINS_MAX];
-  const int rb = n_bins - 1 - b;  // reversed index
-  const uint32_t mine = b < n_bins ? tot[rb] : 0u;   // thread b holds reversed element b = bin (n_bins-1-b)
-  sc[b] = mine;
-  __syncthreads();
-  for (int off = 1; off < 1024; off <<= 1) {
-    const uint32_t v = b >= off ? sc[b - off] : 0u;
-    __syncthreads();
-    sc[b] += v;
-    __syncthreads();
+  // exclusive scan over bins in DESCENDING bin order: thread b holds reversed element b = bin (n_bins - 1 - b)
+  const int rb = n_bins - 1 - b;
+  const uint32_t mine = b < n_bins ? tot[rb] : 0u;
+  uint32_t incl = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, incl, off);
+    if (lane >= off) incl += v;
   }
-  if (b < n_bins) binstart[(size_t)im * n_bins + rb] = sc[b] - mine;
-  if (b == n_bins - 1) nseeds[im] = (int)sc[b];
+  if (lane == 31) wsum[wrp] = incl;
+  __syncthreads();
+  if (wrp == 0) {
+    uint32_t w = wsum[lane], wi = w;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, wi, off);
+      if (lane >= off) wi += v;
+    }
+    wsum[lane] = wi - w;   // exclusive prefix of the warp totals
+  }
+  __syncthreads();
+  const uint32_t excl = wsum[wrp] + incl - mine;
+  if (b < n_bins) binstart[(size_t)im * n_bins + rb] = excl;
+  if (b == n_bins - 1) nseeds[im] = (int)(excl + mine);
 }
 
 // one warp per (chunk, image): walks the chunk's row-segment lists in raster order, stable ranks via match_any
