@@ -92,12 +92,13 @@ def kernel_bytes(name, ab, n_kp, m_lines):
         "orb.k_rbrief": (32 * n_kp, 512 * n_kp + 32 * n_kp),         # survey: descriptors out; design: + the 37x37 patches read
         "lsd.k_blur_q8": (2 * A0,) * 2,
         "lsd.k_resize_exact": (A0 + Ns,) * 2,
-        "lsd.k_lsd_grad": (Ns + 8 * Ns, Ns + 4 * Ns + 2 * Ns),        # survey: read u8, write f32 mag + angle; design: (gx,gy) 4 B + a 16 B record for the ~12 % defined pixels
-        "lsd.k_lsd_rowhist": (4 * Ns, 4 * Ns + 6 * (Ns // 8) + ch),   # survey: half of the 8 Ns "write + read bin-sort index"; design: read (gx,gy), write the compact (index, bin) lists
+        # d = defined pixels (gradient above the threshold), ~ Ns / 8 on the KITTI-shape stream
+        "lsd.k_lsd_grad": (Ns + 8 * Ns, Ns + (16 + 8) * (Ns // 8)),   # survey: read u8, write f32 mag + angle; design: 16 B record + (index, |g|^2) list entry, defined pixels only
+        "lsd.k_lsd_rowhist": (4 * Ns, 6 * (Ns // 8) + ch),            # survey: half of the 8 Ns "write + read bin-sort index"; design: read |g|^2, write the u16 bin, chunk counters
         "lsd.k_lsd_binscan": (2 * ch,) * 2,
-        "lsd.k_lsd_scatter": (4 * Ns, 6 * (Ns // 8) + ch + 4 * (Ns // 8)),
+        "lsd.k_lsd_scatter": (4 * Ns, 6 * (Ns // 8) + ch + 4 * (Ns // 8)),   # design: read (index, bin) + bases, write the order
         "lsd.k_lsd_grow": (6 * Ns, 6 * Ns),                           # read angle + r/w used mask
-        "lsd.k_lsd_rects": (3 * 8 * Ns // 4,) * 2,
+        "lsd.k_lsd_rects": (3 * 8 * Ns // 4, 2 * (4 + 4) * (Ns // 8) + 4 * (Ns // 8)),   # design: 2 passes of (point, record li) + 1 of the point list
         "lsd.k_keylines": (16 * m_lines, 16 * 1200 + 68 * 1200),
         "lbd.k_blur5_sobel": (A0 + 4 * A0,) * 2,
         "lbd.k_lbd": (63 * ab["lbar"] * 4 * m_lines + 32 * m_lines,) * 2,

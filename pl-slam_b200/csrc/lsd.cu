@@ -91,7 +91,7 @@ struct LsdState {
   int* nlines[2] = {nullptr, nullptr};      // [nimg]
   int* overflow = nullptr;    // [1]
   int* rs_tab = nullptr;      // resize tables
-  size_t rs_x_off = 0, rs_y_off = 0;
+  size_t rs_x_off = 0, rs_y_off = 0, rs_xp_off = 0;
   struct LsdPix* grad_lut = nullptr; // [1021*1021] gradient (gx,gy) -> LsdPix
   float2* seed_lut = nullptr;        // [1021*1021] gradient (gx,gy) -> unit vector of a region seed
 };
@@ -1134,11 +1134,13 @@ plf_status plf_lsd_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (s->scale != 1.0) {
     PLF_CUDA(ctx, cudaMemcpyToSymbolAsync(c_lsd_taps, s->taps, sizeof(int) * 16, 0, cudaMemcpyHostToDevice, ctx->stream));
-    std::vector<int> tab(2 * (size_t)s->ws + 2 * (size_t)s->hs);
     s->rs_x_off = 0;
     s->rs_y_off = 2 * (size_t)s->ws;
+    s->rs_xp_off = (s->rs_y_off + 2 * (size_t)s->hs + 3) & ~(size_t)3;   // 16-byte aligned: read with 128-bit loads
+    std::vector<int> tab(s->rs_xp_off + plf_resize_packed_len(s->ws));
     plf_linear_coeffs_host(w, s->ws, 1.0 / s->scale, &tab[0], &tab[s->ws]);
     plf_linear_coeffs_host(h, s->hs, 1.0 / s->scale, &tab[s->rs_y_off], &tab[s->rs_y_off + s->hs]);
+    plf_resize_pack_x(&tab[0], &tab[s->ws], s->ws, &tab[s->rs_xp_off]);
     PLF_CUDA(ctx, cudaMalloc(&s->rs_tab, tab.size() * sizeof(int)));
     PLF_CUDA(ctx, cudaMemcpyAsync(s->rs_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     PLF_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1201,7 +1203,7 @@ plf_status plf_lsd_pre_range(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_str
     }
     PLF_LAUNCH_CHECK(ctx);
     plf_mark(ctx, "lsd.k_blur_q8");
-    st = plf_launch_resize_exact(ctx, blur, A, s->bp, w, h, scaled_buf, Asp, s->sp, W, H, s->rs_tab + s->rs_x_off, s->rs_tab + s->rs_y_off, n);
+    st = plf_launch_resize_exact(ctx, blur, A, s->bp, w, h, scaled_buf, Asp, s->sp, W, H, s->rs_tab + s->rs_x_off, s->rs_tab + s->rs_xp_off, s->rs_tab + s->rs_y_off, n);
     if (st) return st;
     plf_mark(ctx, "lsd.k_resize_exact");
     scaled = scaled_buf;

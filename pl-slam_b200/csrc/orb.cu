@@ -64,13 +64,14 @@ struct OrbState {
   int* hist = nullptr;       // [nimg][levels][256]
   // resize tables per level l>=1: x: ofs (int), c1 (int); y likewise
   int* rs_tab = nullptr;
-  size_t rs_x_off[ORB_MAX_LEVELS], rs_y_off[ORB_MAX_LEVELS];
+  size_t rs_x_off[ORB_MAX_LEVELS], rs_y_off[ORB_MAX_LEVELS], rs_xp_off[ORB_MAX_LEVELS];
   // outputs
   plf_keypoint* kps[2] = {nullptr, nullptr};  // [nimg][max_kp]
   short2* kp_lxy[2] = {nullptr, nullptr};     // level coordinates
   uint8_t* desc[2] = {nullptr, nullptr};      // [nimg][max_kp][32]
   int* kp_count[2] = {nullptr, nullptr};      // [nimg]
   int* overflow = nullptr;      // [1]
+  float2* trig = nullptr;       // [nimg][max_kp] (cos, sin) of the keypoint angle (k_orb_trig -> k_rbrief)
   float blur_k[7];
   // TMA descriptors (plf_tma.cuh): halo boxes of the FAST tile (96 x 38) and of the blur tile (80 x 38) per level; level 0
   // is the caller's image buffer (re-encoded when its address changes - the pipeline alternates between two)
@@ -93,7 +94,7 @@ __device__ __forceinline__ int orb_reflect101(int i, int n) {
 }
 
 // ---- pyramid ---------------------------------------------------------------------------------------
-// tab layout per level: [ox(dw) | cx(dw) | oy(dh) | cy(dh)]
+// tab layout per level: [ox(dw) | cx(dw) | oy(dh) | cy(dh) | packed x (k_resize_exact4)]
 __global__ void __launch_bounds__(256) k_resize_exact(const uint8_t* __restrict__ src, size_t src_stride, int sp, int sw,
                                                       int sh, uint8_t* __restrict__ dst, size_t dst_stride, int dp, int dw,
                                                       int dh, const int* __restrict__ tabx,
@@ -111,51 +112,68 @@ __global__ void __launch_bounds__(256) k_resize_exact(const uint8_t* __restrict_
   dst[(size_t)blockIdx.z * dst_stride + (size_t)y * dp + x] = (uint8_t)(v > 255 ? 255 : v);
 }
 
-// Four adjacent outputs per thread.  For scale factors up to 2 the four outputs read source columns ox0 .. ox0+7 at
-// most, i.e. two 32-bit words per source row (plf_load4), from which each output takes its byte pair with a shift.
-// Same integer arithmetic as k_resize_exact (bit-identical), about half the instructions per pixel.
+// Four adjacent outputs per thread.  For scale factors up to 1.9 the four outputs read source columns ox0 .. ox0+7 at
+// most: three aligned 32-bit words per source row, funnel-shifted to start at ox0.  Each output then takes its byte pair
+// with one PRMT and forms the horizontal blend p0*(256-cx) + p1*cx with one IDP.2A (the 16-bit weight pair comes packed
+// from the table: tabxp[e] = {ofs, (256-cx) | cx << 16}, padded to a multiple of four entries, two 128-bit loads per
+// thread).  Same integer arithmetic as k_resize_exact (bit-identical; v <= 255 by construction, so no clamp), half the
+// instructions of the shift-and-mask form.
 __global__ void __launch_bounds__(256) k_resize_exact4(const uint8_t* __restrict__ src, size_t src_stride, int sp, int sw,
                                                        int sh, uint8_t* __restrict__ dst, size_t dst_stride, int dp, int dw,
-                                                       int dh, const int* __restrict__ tabx,
+                                                       int dh, const int4* __restrict__ tabxp,
                                                        const int* __restrict__ taby) {
-  const int x = (blockIdx.x * 64 + threadIdx.x) * 4;  // block = 64 x 4 threads = 256 x 4 outputs
+  const int xq = blockIdx.x * 64 + threadIdx.x;  // block = 64 x 4 threads = 256 x 4 outputs
+  const int x = xq * 4;
   const int y = blockIdx.y * 4 + threadIdx.y;
   if (x >= dw || y >= dh) return;
-  const uint8_t* s = src + (size_t)blockIdx.z * src_stride;
-  const int oy = taby[y], cy = taby[dh + y];
-  int ox[4], cx[4];
+  const int4 t0 = __ldg(&tabxp[2 * xq]), t1 = __ldg(&tabxp[2 * xq + 1]);  // {ofs, weights} of outputs x .. x+3
+  const int oy = __ldg(&taby[y]), cy = __ldg(&taby[dh + y]);
+  // source bytes ox0 .. ox0+7 of rows oy and oy+1.  The second row is clamped to the image (its weight cy is 0 there), so
+  // every byte wanted lies inside the image or within 7 bytes of its end: unclamped loads (allocation slack).  Pitches and
+  // image strides are multiples of 16, so both rows have the same misalignment.
+  const uint8_t* r0 = src + (size_t)blockIdx.z * src_stride + (size_t)oy * sp + t0.x;
+  const int mis = (int)((uintptr_t)r0 & 3);
+  const uint32_t* pa = reinterpret_cast<const uint32_t*>(r0 - mis);
+  const uint32_t* pb = oy + 1 < sh ? reinterpret_cast<const uint32_t*>(r0 - mis + sp) : pa;
+  const uint32_t a0 = __ldg(pa), a1 = __ldg(pa + 1), a2 = __ldg(pa + 2);
+  const uint32_t b0 = __ldg(pb), b1 = __ldg(pb + 1), b2 = __ldg(pb + 2);
+  const int s8 = 8 * mis;
+  const uint32_t alo = __funnelshift_r(a0, a1, s8), ahi = __funnelshift_r(a1, a2, s8);
+  const uint32_t blo = __funnelshift_r(b0, b1, s8), bhi = __funnelshift_r(b1, b2, s8);
+  const uint32_t wy0 = (uint32_t)(256 - cy), wy1 = (uint32_t)cy;
+  const int ofs[4] = {t0.x, t0.z, t1.x, t1.z};
+  const uint32_t wx[4] = {(uint32_t)t0.y, (uint32_t)t0.w, (uint32_t)t1.y, (uint32_t)t1.w};
+  uint32_t v[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    const int xi = min(x + i, dw - 1);
-    ox[i] = tabx[xi];
-    cx[i] = tabx[dw + xi];
-  }
-  // source bytes ox[0] .. ox[0]+7 of rows oy and oy+1.  The second row is clamped to the image (its weight cy is 0
-  // there), so every byte wanted lies inside the image or within 7 bytes of its end: unclamped loads (allocation slack).
-  const uint8_t* r0 = s + (size_t)oy * sp + ox[0];
-  const uint8_t* r1 = oy + 1 < sh ? r0 + sp : r0;
-  const unsigned long long a = (unsigned long long)plf_load4_fast(r0) | ((unsigned long long)plf_load4_fast(r0 + 4) << 32);
-  const unsigned long long b = (unsigned long long)plf_load4_fast(r1) | ((unsigned long long)plf_load4_fast(r1 + 4) << 32);
-  uint8_t* d = dst + (size_t)blockIdx.z * dst_stride + (size_t)y * dp + x;
-  uint32_t pk = 0;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int sft = 8 * (ox[i] - ox[0]);
-    const uint32_t pa = (uint32_t)(a >> sft), pb = (uint32_t)(b >> sft);
-    const uint32_t h0 = (pa & 0xFFu) * (256 - cx[i]) + ((pa >> 8) & 0xFFu) * cx[i];
-    const uint32_t h1 = (pb & 0xFFu) * (256 - cx[i]) + ((pb >> 8) & 0xFFu) * cx[i];
-    const uint32_t v = (h0 * (256 - cy) + h1 * cy + 32768u) >> 16;
-    pk |= (v > 255 ? 255u : v) << (8 * i);
+    const uint32_t sel = (uint32_t)(ofs[i] - ofs[0]) * 0x11u + 0x10u;  // bytes k, k+1 of the 8-byte window
+    const uint32_t h0 = __dp2a_lo(wx[i], __byte_perm(alo, ahi, sel), 0u);
+    const uint32_t h1 = __dp2a_lo(wx[i], __byte_perm(blo, bhi, sel), 0u);
+    v[i] = (h0 * wy0 + h1 * wy1 + 32768u) >> 16;
   }
   // rows are 16-byte aligned (pitch) and x is a multiple of 4: one 32-bit store (bytes past dw land in the row's padding)
-  *reinterpret_cast<uint32_t*>(d) = pk;
+  uint8_t* d = dst + (size_t)blockIdx.z * dst_stride + (size_t)y * dp + x;
+  *reinterpret_cast<uint32_t*>(d) = (v[0] | (v[1] << 8)) | ((v[2] | (v[3] << 8)) << 16);
+}
+
+// Packed x table of k_resize_exact4 from (ofs, c1): 2 ints per output column, padded to a multiple of 4 columns with the
+// last column's entry.  `out` has plf_resize_packed_len(dw) ints and must start on a 16-byte boundary.
+size_t plf_resize_packed_len(int dw) { return 2 * (size_t)((dw + 3) & ~3); }
+void plf_resize_pack_x(const int* ofs, const int* c1, int dw, int* out) {
+  const int dw4 = (dw + 3) & ~3;
+  for (int e = 0; e < dw4; ++e) {
+    const int v = e < dw ? e : dw - 1;
+    out[2 * e] = ofs[v];
+    out[2 * e + 1] = (256 - c1[v]) | (c1[v] << 16);
+  }
 }
 
 plf_status plf_launch_resize_exact(plf_ctx* ctx, const uint8_t* src, size_t src_stride, int sp, int sw, int sh, uint8_t* dst,
-                                   size_t dst_stride, int dp, int dw, int dh, const int* tabx, const int* taby, int nimg) {
+                                   size_t dst_stride, int dp, int dw, int dh, const int* tabx, const int* tabxp, const int* taby, int nimg) {
   if ((double)sw <= 1.9 * (double)dw) {  // four outputs span at most 3 * 1.9 + 2 < 8 source columns
     dim3 grid((dw + 255) / 256, (dh + 3) / 4, nimg);
-    k_resize_exact4<<<grid, dim3(64, 4), 0, ctx->cur>>>(src, src_stride, sp, sw, sh, dst, dst_stride, dp, dw, dh, tabx, taby);
+    k_resize_exact4<<<grid, dim3(64, 4), 0, ctx->cur>>>(src, src_stride, sp, sw, sh, dst, dst_stride, dp, dw, dh,
+                                                        reinterpret_cast<const int4*>(tabxp), taby);
   } else {
     dim3 grid((dw + 255) / 256, dh, nimg);
     k_resize_exact<<<grid, 256, 0, ctx->cur>>>(src, src_stride, sp, sw, sh, dst, dst_stride, dp, dw, dh, tabx, taby);
@@ -542,6 +560,17 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const __grid_constant__ 
 }
 
 // ---- rBRIEF --------------------------------------------------------------------------------------------
+// Rotation of the sampling pattern: (float)cos / sin of the keypoint angle in double, as OpenCV's computeOrbDescriptors
+// evaluates it.  One THREAD per keypoint here - inside the warp-per-keypoint descriptor kernel the 32 lanes each paid the
+// two f64 evaluations for the same value.
+__global__ void __launch_bounds__(256) k_orb_trig(OrbGeom g, const plf_keypoint* __restrict__ kps,
+                                                  const int* __restrict__ kp_count, float2* __restrict__ trig) {
+  const int img = blockIdx.y, ki = blockIdx.x * 256 + threadIdx.x;
+  if (ki >= kp_count[img]) return;
+  const float angle = __fmul_rn(kps[(size_t)img * g.max_kp + ki].angle, (float)(3.14159265358979323846 / 180.f));
+  trig[(size_t)img * g.max_kp + ki] = make_float2((float)cos((double)angle), (float)sin((double)angle));
+}
+
 // One warp per keypoint.  The 37x37 neighbourhood of the (blurred) keypoint that the 512 rotated samples can reach
 // (|offset| <= 18) is first copied to shared memory with row-contiguous loads; the 16 samples of each lane then come
 // from shared memory instead of 16 scattered global sectors.
@@ -550,11 +579,17 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const __grid_constant__ 
 #define RB_P 40
 __global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur, OrbGeom g,
                                                 const plf_keypoint* __restrict__ kps,
-                                                const int* __restrict__ kp_count, const int8_t* __restrict__ pattern,
-                                                uint8_t* __restrict__ desc) {
-  __shared__ __align__(16) int8_t pat[1024];
+                                                const int* __restrict__ kp_count, const float2* __restrict__ trig,
+                                                const int8_t* __restrict__ pattern, uint8_t* __restrict__ desc) {
+  // the pattern as floats, transposed so that the 32 lanes of a warp read consecutive float4s for their j-th test:
+  // test tt = lane * 8 + j lives at patf[j * 32 + lane]
+  __shared__ __align__(16) float4 patf[256];
   __shared__ __align__(16) uint8_t patch[8][RB_D][RB_P];
-  reinterpret_cast<uint32_t*>(pat)[threadIdx.x] = reinterpret_cast<const uint32_t*>(pattern)[threadIdx.x];  // 1024 B
+  {
+    const uint32_t w = reinterpret_cast<const uint32_t*>(pattern)[threadIdx.x];  // 4 x int8 of test threadIdx.x
+    patf[(threadIdx.x & 7) * 32 + (threadIdx.x >> 3)] =
+        make_float4((float)(int8_t)(w & 0xFF), (float)(int8_t)((w >> 8) & 0xFF), (float)(int8_t)((w >> 16) & 0xFF), (float)(int8_t)(w >> 24));
+  }
   __syncthreads();
   const int img = blockIdx.y;
   const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -563,8 +598,8 @@ __global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur
   const plf_keypoint kp = kps[(size_t)img * g.max_kp + ki];
   const int l = kp.octave, W = g.bpitch[l];   // row pitch of the blurred level
   const float scale = __fdiv_rn(1.f, g.scale[l]);
-  const float angle = __fmul_rn(kp.angle, (float)(3.14159265358979323846 / 180.f));
-  const float a = (float)cos((double)angle), b = (float)sin((double)angle);
+  const float2 cs = __ldg(&trig[(size_t)img * g.max_kp + ki]);
+  const float a = cs.x, b = cs.y;
   const int cyi = __float2int_rn(__fmul_rn(kp.y, scale)), cxi = __float2int_rn(__fmul_rn(kp.x, scale));
   // keypoints are >= edge (19) pixels inside the level, so the 37x37 window never leaves it
   const uint8_t* base = blur + (size_t)img * g.blur_stride + g.blur_off[l] + (size_t)(cyi - RB_R) * W + (cxi - RB_R);
@@ -582,8 +617,8 @@ __global__ void __launch_bounds__(256) k_rbrief(const uint8_t* __restrict__ blur
   unsigned val = 0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int8_t* q = pat + (lane * 8 + j) * 4;
-    const float qx0 = (float)q[0], qy0 = (float)q[1], qx1 = (float)q[2], qy1 = (float)q[3];
+    const float4 q = patf[j * 32 + lane];
+    const float qx0 = q.x, qy0 = q.y, qx1 = q.z, qy1 = q.w;
     const int ix0 = __float2int_rn(__fsub_rn(__fmul_rn(qx0, a), __fmul_rn(qy0, b)));
     const int iy0 = __float2int_rn(__fadd_rn(__fmul_rn(qx0, b), __fmul_rn(qy0, a)));
     const int ix1 = __float2int_rn(__fsub_rn(__fmul_rn(qx1, a), __fmul_rn(qy1, b)));
@@ -630,7 +665,7 @@ void plf_linear_coeffs_host(int srcsize, int dstsize, double scale, int* ofs, in
 static void orb_release(OrbState* s) {
   if (!s) return;
   cudaFree(s->pyr); cudaFree(s->blur); cudaFree(s->cand); cudaFree(s->cand_count); cudaFree(s->hist);
-  cudaFree(s->rs_tab); cudaFree(s->overflow);
+  cudaFree(s->rs_tab); cudaFree(s->overflow); cudaFree(s->trig);
   for (int p = 0; p < 2; ++p) { cudaFree(s->kps[p]); cudaFree(s->kp_lxy[p]); cudaFree(s->desc[p]); cudaFree(s->kp_count[p]); }
   s->pyr = s->blur = nullptr;
 }
@@ -728,6 +763,10 @@ plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
     s->rs_y_off[l] = tab.size();
     tab.resize(tab.size() + 2 * dh);
     plf_linear_coeffs_host(sh, dh, 1.0 / ((double)dh / sh), &tab[s->rs_y_off[l]], &tab[s->rs_y_off[l] + dh]);
+    tab.resize((tab.size() + 3) & ~(size_t)3);   // the packed x table is read with 128-bit loads
+    s->rs_xp_off[l] = tab.size();
+    tab.resize(tab.size() + plf_resize_packed_len(dw));
+    plf_resize_pack_x(&tab[s->rs_x_off[l]], &tab[s->rs_x_off[l] + dw], dw, &tab[s->rs_xp_off[l]]);
   }
   const size_t N = (size_t)nimg;
   PLF_CUDA(ctx, cudaMalloc(&s->pyr, std::max<size_t>(pyr, 256) * N + 64));  // + slack for plf_load4 (see plf_image_span)
@@ -744,6 +783,7 @@ plf_status plf_orb_prepare(plf_ctx* ctx, int w, int h, int nimg, bool two_pariti
   }
   PLF_CUDA(ctx, cudaMalloc(&s->overflow, sizeof(int)));
   PLF_CUDA(ctx, cudaMemsetAsync(s->overflow, 0, sizeof(int), ctx->stream));
+  PLF_CUDA(ctx, cudaMalloc(&s->trig, N * g.max_kp * sizeof(float2)));
   if (!tab.empty())
     PLF_CUDA(ctx, cudaMemcpyAsync(s->rs_tab, tab.data(), tab.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   {  // getGaussianKernel(7, 2, CV_32F): host doubles -> float (pinned equal to cv2 in tests)
@@ -804,7 +844,8 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
     const uint8_t* src = (l == 1) ? d_imgs : s->pyr + g.pyr_off[l - 1];
     const size_t sstride = (l == 1) ? img_stride : g.pyr_stride;
     st = plf_launch_resize_exact(ctx, src, sstride, g.pitch[l - 1], g.w[l - 1], g.h[l - 1], s->pyr + g.pyr_off[l], g.pyr_stride,
-                                 g.pitch[l], g.w[l], g.h[l], s->rs_tab + s->rs_x_off[l], s->rs_tab + s->rs_y_off[l], nimg);
+                                 g.pitch[l], g.w[l], g.h[l], s->rs_tab + s->rs_x_off[l], s->rs_tab + s->rs_xp_off[l],
+                                 s->rs_tab + s->rs_y_off[l], nimg);
     if (st) return st;
   }
   plf_mark(ctx, "orb.k_resize_exact");
@@ -827,7 +868,9 @@ plf_status plf_orb_run(plf_ctx* ctx, const uint8_t* d_imgs, size_t img_stride, i
     PLF_LAUNCH_CHECK(ctx);
   }
   plf_mark(ctx, "orb.k_orb_blur7");
-  k_rbrief<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(s->blur, g, s->kps[par], s->kp_count[par], g_dev_pattern, s->desc[par]);
+  k_orb_trig<<<dim3((g.max_kp + 255) / 256, nimg), 256, 0, cs>>>(g, s->kps[par], s->kp_count[par], s->trig);
+  PLF_LAUNCH_CHECK(ctx);
+  k_rbrief<<<dim3((g.max_kp + 7) / 8, nimg), 256, 0, cs>>>(s->blur, g, s->kps[par], s->kp_count[par], s->trig, g_dev_pattern, s->desc[par]);
   PLF_LAUNCH_CHECK(ctx);
   plf_mark(ctx, "orb.k_rbrief");
   return PLF_OK;
