@@ -220,7 +220,16 @@ plf_status plf_create(const plf_params* params, const plf_camera* cam, const plf
   }
   ctx->cur = ctx->stream;
   bool ok = true;
-  for (int i = 0; i < 3 && ok; ++i) ok = cudaStreamCreateWithFlags(&ctx->aux[i], cudaStreamNonBlocking) == cudaSuccess;
+  // aux[1] carries the LSD chain of the batched pipeline, the longest dependent chain of a step.  PLF_G_PRIORITY=1 gives it the
+  // highest stream priority (its CTAs are dispatched ahead of the pending CTAs of the ORB / match streams).  Measured: no gain -
+  // the chain is slowed by sharing issue slots with the co-resident kernels, not by waiting for CTA slots - so
+  // equal priorities stay the default.
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  const char* gp = getenv("PLF_G_PRIORITY");
+  const bool g_high = gp && gp[0] == '1';
+  for (int i = 0; i < 3 && ok; ++i)
+    ok = cudaStreamCreateWithPriority(&ctx->aux[i], cudaStreamNonBlocking, (i == 1 && g_high) ? prio_hi : prio_lo) == cudaSuccess;
   if (!ok) {
     plf_destroy(ctx);
     return plf_fail(nullptr, PLF_ERR_NO_DEVICE, "plf_create: could not create auxiliary streams/events");
