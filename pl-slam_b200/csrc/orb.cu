@@ -222,7 +222,9 @@ __device__ int fast_corner_score(const int* d /*16*/) {
 //           centres are two VABSDIFF4 on the words of rows y-3 / y / y+3, and "some difference exceeds the threshold" is a
 //           3-instruction SWAR compare - a 9-arc of the 16-ring always contains one pixel of every opposite pair (k, k+8)
 //           (OpenCV's FAST_t uses the same test), so a group whose four bytes all fail is dropped after ~5 instructions per
-//           pixel; the surviving bytes go through the pairs (4,12), (2,10), (6,14) one pixel at a time and are compacted;
+//           pixel; groups that survive get the pairs (4,12), (2,10), (6,14) the same way (neighbour words by funnel shift);
+//           the bytes left go through the exact polarity-consistent pair tests one pixel at a time and are compacted
+//           (measured: the extra SWAR stages leave time and instruction count where they were - pass B dominates);
 //   pass B  full ring test + exact cornerScore on the compacted candidates (dense warps);
 //   NMS     3x3 strict maximum + border filter + append, over the candidates only (nothing else has a score).
 #define FN_OW 62
@@ -272,6 +274,26 @@ __global__ void __launch_bounds__(256, 5) k_fast_nms(const __grid_constant__ CUt
     const uint32_t wd = reinterpret_cast<const uint32_t*>(&pxb[sy + 6][0])[wcol];   // ring pixel 0: (x, y + 3)
     const uint32_t wu = reinterpret_cast<const uint32_t*>(&pxb[sy][0])[wcol];       // ring pixel 8: (x, y - 3)
     uint32_t t = fast_gt4(__vabsdiffu4(wc, wd), k7, th_small) | fast_gt4(__vabsdiffu4(wc, wu), k7, th_small);
+    if (t) {
+      // the other three opposite pairs, still four centres at a time: (4, 12) = (x +- 3, y) from the neighbour words of the
+      // centre row, (2, 10) / (6, 14) = (x +- 2, y +- 2) from rows y +- 2, each neighbour word a funnel shift of two aligned
+      // words.  |difference| > th for one pixel of EVERY pair is necessary for either polarity, so this only rejects; the
+      // byte loop below stays the exact (polarity-consistent) test.  Words beside the row's ends only feed bytes that are
+      // not score pixels (sx < 0 or sx >= 64).
+      const uint32_t* rc = reinterpret_cast<const uint32_t*>(&pxb[sy + 3][0]) + wcol;
+      const uint32_t cl = rc[-1], cr = rc[1];
+      t &= fast_gt4(__vabsdiffu4(wc, __funnelshift_r(wc, cr, 24)), k7, th_small) |
+           fast_gt4(__vabsdiffu4(wc, __funnelshift_r(cl, wc, 8)), k7, th_small);
+    }
+    if (t) {
+      const uint32_t* rp = reinterpret_cast<const uint32_t*>(&pxb[sy + 5][0]) + wcol;   // row y + 2
+      const uint32_t* rm = reinterpret_cast<const uint32_t*>(&pxb[sy + 1][0]) + wcol;   // row y - 2
+      const uint32_t p0 = rp[-1], p1 = rp[0], p2 = rp[1], m0 = rm[-1], m1 = rm[0], m2 = rm[1];
+      const uint32_t pr = __funnelshift_r(p1, p2, 16), pl = __funnelshift_r(p0, p1, 16);   // (x + 2, y + 2), (x - 2, y + 2)
+      const uint32_t mr = __funnelshift_r(m1, m2, 16), ml = __funnelshift_r(m0, m1, 16);   // (x + 2, y - 2), (x - 2, y - 2)
+      t &= (fast_gt4(__vabsdiffu4(wc, pr), k7, th_small) | fast_gt4(__vabsdiffu4(wc, ml), k7, th_small)) &
+           (fast_gt4(__vabsdiffu4(wc, mr), k7, th_small) | fast_gt4(__vabsdiffu4(wc, pl), k7, th_small));
+    }
     while (t) {
       const int b = (__ffs(t) - 1) >> 3;   // byte whose pair (0, 8) does not rule it out
       t &= ~(0x80u << (8 * b));
@@ -551,8 +573,8 @@ __global__ void __launch_bounds__(256) k_orb_blur7_fast(const __grid_constant__ 
         a = __fmaf_rn(k4, __fadd_rn(v[r + 4], v[r + 2]), a);
         a = __fmaf_rn(k5, __fadd_rn(v[r + 5], v[r + 1]), a);
         a = __fmaf_rn(k6, __fadd_rn(v[r + 6], v[r]), a);
-        int o = __float2int_rn(a);
-        o = o < 0 ? 0 : (o > 255 ? 255 : o);
+        uint32_t o;   // round half to even, saturated to [0, 255]: one conversion instruction
+        asm("cvt.rni.u8.f32 %0, %1;" : "=r"(o) : "f"(a));
         dst[(size_t)gy * BP + gx] = (uint8_t)o;
       }
     }
