@@ -1,7 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-python bench.py --gpus 1 --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2_s2_n1.json 2> gpurun_out/r2_s2_n1.err
-python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/r2_s2_n2.json 2> gpurun_out/r2_s2_n2.err
+python bench.py --gpus 1 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_s2_n1.json 2> gpurun_out/r2_s2_n1.err
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/r2_s2_n2.json 2> gpurun_out/r2_s2_n2.err
 python - <<PY
 import json
 a=json.load(open("gpurun_out/r2_s2_n1.json")); b=json.load(open("gpurun_out/r2_s2_n2.json"))
